@@ -1,0 +1,186 @@
+/* zenu_b200.h — native C ABI of the B200 (sm_100a) backend for ZeNu's CNN-training hot path.
+ *
+ * This is the drop-in boundary: a flat extern "C" surface in the style of zenu-cuda-kernel-sys
+ * (reference: zenu-cuda-kernel-sys/kernel/kernel.h:1-18, bindgen'd by zenu-cuda-kernel-sys/build.rs:37-53)
+ * that replaces, for this path only, what zenu-cuda reaches through cuDNN-frontend
+ * (zenu-cudnn-frontend-wrapper-sys/cudnn_frontend_wrapper/include/cudnn_frontend_wrapper.h:100-186),
+ * legacy cuDNN BatchNorm (zenu-cuda/src/cudnn/batch_norm.rs:51-91,206-249,380-414), cuBLAS GEMM
+ * (zenu-cuda/src/cublas/mod.rs:84-160) and the hand kernels of zenu-cuda-kernel-sys.
+ * The symbol-compatible shims for those two old interfaces are declared in
+ * zenu_kernel_compat.h and zenu_cudnn_frontend_compat.h; INTEGRATION.md shows the Rust bindings.
+ *
+ * Conventions
+ *  - every entry returns int: 0 = ZB_OK, otherwise a zb_status; zb_last_error() gives the message
+ *    (reference convention replaced: kernel-sys returns void / unchecked, the FE wrapper an enum).
+ *  - all pointers are DEVICE pointers unless a parameter is named host_*; the callee never allocates
+ *    or frees caller tensors (reference ownership: Matrix<Owned<T>> owns every buffer,
+ *    zenu-matrix/src/device/mod.rs:33-69).  Scratch lives inside zb_ctx.
+ *  - sizes are int64_t (the reference uses int and overflows above 2^31 elements).
+ *  - work is enqueued on the ctx stream; nothing synchronises the device implicitly.
+ *  - dtype: ZB_F32 or ZB_F64 (the reference's only element types, zenu-matrix/src/num.rs:44-86).
+ *  - layout: ZB_NCHW = the reference contract (activations NCHW, filters KCRS);
+ *            ZB_NHWC = the backend's native layout (activations NHWC, filters KRSC), zero-copy.
+ *  - math:   ZB_MATH_TF32  tcgen05 kind::tf32 tensor cores, fp32 accumulate   (rel. tol 1e-3)
+ *            ZB_MATH_FP32  FFMA (f32) / DFMA (f64) SIMT kernels                (rel. tol 1e-5)
+ *            ZB_MATH_DEFAULT = the ctx default (TF32 for f32; f64 always runs DFMA).
+ */
+#ifndef ZENU_B200_H
+#define ZENU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zb_ctx zb_ctx;
+
+typedef enum {
+  ZB_OK = 0,
+  ZB_ERR_INVALID = 1,      /* bad argument / shape mismatch (reference: shape_check panics, nn/conv/shape_check.rs:4-53) */
+  ZB_ERR_CUDA = 2,         /* CUDA runtime / driver failure */
+  ZB_ERR_UNSUPPORTED = 3,  /* valid request this build cannot serve (never a silent CPU fallback) */
+  ZB_ERR_TIMEOUT = 4,      /* a device-side barrier wait timed out (protocol bug guard) */
+  ZB_ERR_NCCL = 5
+} zb_status;
+
+typedef enum { ZB_F32 = 0, ZB_F64 = 1 } zb_dtype;
+typedef enum { ZB_NCHW = 0, ZB_NHWC = 1 } zb_layout;
+typedef enum { ZB_MATH_DEFAULT = 0, ZB_MATH_TF32 = 1, ZB_MATH_FP32 = 3 } zb_math_mode;
+typedef enum { ZB_OP_ADD = 0, ZB_OP_SUB = 1, ZB_OP_MUL = 2, ZB_OP_DIV = 3 } zb_binary_op;
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces the process-global Mutex<ZenuCudaState{cublas,cudnn,stream,mempool}> (zenu-cuda/src/lib.rs:18-112).
+ * `stream` may be NULL (the library creates its own non-blocking stream) or a cudaStream_t to share. */
+int zb_ctx_create(zb_ctx** out, int device, void* stream);
+int zb_ctx_destroy(zb_ctx* ctx);
+int zb_ctx_synchronize(zb_ctx* ctx);
+int zb_ctx_set_math(zb_ctx* ctx, int math_mode);
+void* zb_ctx_stream(zb_ctx* ctx);
+/* Non-zero status if any kernel since the last call hit a device-side timeout. Synchronises. */
+int zb_ctx_check(zb_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py reports the delta as gpu_launches). */
+unsigned long long zb_ctx_launch_count(zb_ctx* ctx);
+const char* zb_last_error(void);
+const char* zb_version(void);
+
+/* ---- convolution --------------------------------------------------------------------------------
+ * Replaces conv_fwd / conv_bkwd_data / conv_bkwd_weight (zenu-matrix/src/nn/conv/mod.rs:21-81;
+ * Nvidia impl nn/conv/nvidia.rs:16-122 -> zenu-cuda/src/cudnn/graph_conv.rs:40-268 -> conv.cpp:29-187).
+ * Shapes come from the live tensors (fixes SURVEY S3: the reference Conv2d layer bakes a 32x32 dummy). */
+typedef struct {
+  int64_t n, c, h, w;          /* input  N, C_in, H, W   */
+  int64_t k, kh, kw;           /* filter C_out, k_h, k_w */
+  int64_t pad_h, pad_w, stride_h, stride_w, dil_h, dil_w;
+} zb_conv2d_desc;
+
+int64_t zb_conv_out_size(int64_t in, int64_t k, int64_t pad, int64_t stride, int64_t dil);
+/* y = conv(x, w) (+ bias[k] when bias != NULL, fused in the epilogue; reference: separate conv_bias_add pass) */
+int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x,
+                    const void* w, const void* bias, void* y);
+int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
+                    const void* w, void* dx);
+int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
+                    const void* x, void* dw);
+/* conv2d_bias_add / conv2d_bias_bkwd (nn/conv/mod.rs:84-107; kernels array_array.cu:49-74,
+ * conv2d_bkwd_data.cu:121-195 — the latter is wrong for N>1 in the reference; this one is not). */
+int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const void* bias, void* y, int64_t n,
+                       int64_t k, int64_t h, int64_t w);
+int zb_conv2d_bias_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dbias, int64_t n, int64_t k,
+                       int64_t h, int64_t w);
+
+/* ---- batch normalisation ------------------------------------------------------------------------
+ * Replaces BatchNormalization::{batch_norm_2d_forward_train, batch_norm_2d_backward,
+ * bach_norm_2d_forward_inference} (zenu-matrix/src/nn/batch_norm.rs:130-280).  eps = 1e-10, momentum
+ * weights the OLD running stat, running variance unbiased, saved = mean and 1/sqrt(var+eps).
+ * Fusions (not in the reference, which runs relu / add as separate kernels):
+ *   relu != 0        y = max(bn(x) [+ residual], 0)
+ *   residual != NULL y = bn(x) + residual
+ * saved_mean / saved_inv_std may be NULL in fwd; in bwd NULL means "recompute from x" (batch_norm.rs:355-368). */
+int zb_bn2d_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w,
+                      double momentum, const void* x, const void* scale, const void* bias, void* running_mean,
+                      void* running_var, void* saved_mean, void* saved_inv_std, void* y, const void* residual,
+                      int relu);
+int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                      const void* scale, const void* bias, const void* mean, const void* var, void* y);
+/* dy is the gradient w.r.t. the (possibly fused) output.  When the forward fused relu, pass the forward
+ * OUTPUT in y (mask = y > 0); dres (optional) receives the gradient of the residual input (= masked dy). */
+int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                const void* dy, const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx,
+                void* dscale, void* dbias, const void* y, void* dres);
+
+/* ---- GEMM / Linear ------------------------------------------------------------------------------
+ * Replaces Gemm::gemm_unchecked (zenu-matrix/src/operation/mul.rs:12-29,113-147 -> cublas{S,D}gemm_v2_64,
+ * zenu-cuda/src/cublas/mod.rs:84-160).  Row-major: C[m,n] = alpha*op(A)*op(B) + beta*C. */
+int zb_gemm(zb_ctx* ctx, int dtype, int math, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
+            double alpha, const void* a, int64_t lda, const void* b, int64_t ldb, double beta, void* c, int64_t ldc);
+/* Linear layer (zenu-layer/src/layers/linear.rs:22-31): y[b,out] = x[b,in] * W^T + bias, W is [out,in].
+ * No materialised transposes (the reference makes four, zenu-autograd/src/functions/transpose.rs:24-32). */
+int zb_linear_fwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* bias, void* y,
+                  int64_t batch, int64_t in_f, int64_t out_f);
+int zb_linear_bwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* dy, void* dx, void* dw,
+                  void* dbias, int64_t batch, int64_t in_f, int64_t out_f);
+
+/* ---- elementwise / reductions / copies ------------------------------------------------------------
+ * relu, relu_backward_mask: ReluOps (zenu-matrix/src/operation/relu.rs:12-29; kernels activations.cu:3-41).
+ * relu_bwd fuses mask*dy (reference: mask kernel + mul kernel). */
+int zb_relu(zb_ctx* ctx, int dtype, const void* x, void* y, double alpha, int64_t n);
+int zb_relu_backward_mask(zb_ctx* ctx, int dtype, const void* x, void* mask, double alpha, int64_t n);
+int zb_relu_bwd(zb_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, double alpha, int64_t n);
+/* c = a op b (same shape), c = a op scalar: AddOps..DivOps (operation/basic_operations.rs:32-276). c may alias a. */
+int zb_binary(zb_ctx* ctx, int dtype, int op, const void* a, const void* b, void* c, int64_t n);
+int zb_binary_scalar(zb_ctx* ctx, int dtype, int op, const void* a, double scalar, void* c, int64_t n);
+/* c[r, j] = a[r, j] op b[j]: numpy-style trailing broadcast of a [cols] rhs (with_clousers.rs:108-240);
+ * one launch instead of one kernel per row. */
+int zb_binary_bcast_rows(zb_ctx* ctx, int dtype, int op, const void* a, const void* b, void* c, int64_t rows,
+                         int64_t cols);
+/* out[j] = sum_r a[r, j]  (Matrix::sum(axis 0), operation/sum.rs:9-31: bias / gamma / beta gradients) */
+int zb_sum_rows(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t rows, int64_t cols);
+int zb_fill(zb_ctx* ctx, int dtype, void* x, double value, int64_t n); /* zeros(): reference scales by 0 (NaN-unsafe) */
+int zb_copy(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n);
+/* layout transforms (replace transpose_by_index_new_matrix + to_default_stride copies) */
+int zb_nchw_to_nhwc(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w);
+int zb_nhwc_to_nchw(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w);
+
+/* ---- "next" rows: pooling and the loss head ----------------------------------
+ * max-pool: zenu-matrix/src/nn/pool2d.rs:52-190 (CPU semantics: zero padding takes part in the max,
+ * first maximum wins).  Global average pool is absent in the reference.
+ * softmax_xent: zenu-autograd/src/loss/cross_entropy.rs:12-23 fused with its backward. */
+int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t h,
+                     int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw);
+int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const void* dy, void* dx, int64_t n,
+                     int64_t c, int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph,
+                     int64_t pw);
+int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t hw);
+int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int64_t n, int64_t c, int64_t hw);
+/* loss (device scalar) = -(1/B) sum t*log(softmax(z)); dz (optional) = (softmax(z)*sum_j t - t)/B */
+int zb_softmax_xent(zb_ctx* ctx, int dtype, const void* z, const void* t, void* loss, void* dz, int64_t batch,
+                    int64_t classes);
+
+/* ---- optimizers -----------------------------------------------------------------------------------
+ * Replace Optimizer::update (zenu-optimizer/src/sgd.rs:20-30, adam.rs:19-58, adamw.rs:20-69): one fused
+ * kernel over a flat parameter bucket instead of >=2 / >=10 kernels + temporaries per tensor.
+ * grad_scale multiplies the gradient first (1/world after a data-parallel sum-allreduce). */
+int zb_sgd_step(zb_ctx* ctx, int dtype, void* param, const void* grad, double lr, double grad_scale, int64_t n);
+/* step_t is the 1-based step AFTER the increment; weight_decay is applied (AdamW, decoupled) when decay != 0 */
+int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m, void* v, double lr, double beta1,
+                 double beta2, double eps, double weight_decay, int decay, int64_t step_t, double grad_scale,
+                 int64_t n);
+
+/* ---- data parallel (new; the reference has no multi-GPU path) -------------------------
+ * One process per GPU.  Rank 0 calls zb_dp_unique_id (128 bytes, host), ships it to the others through
+ * whatever rendezvous the host has (torch.distributed / a file), then every rank calls zb_dp_init.
+ * zb_dp_allreduce_sum enqueues ncclAllReduce(sum) on the ctx comm stream, ordered after everything already
+ * enqueued on the compute stream; zb_dp_wait makes the compute stream wait for it. */
+int zb_dp_unique_id(zb_ctx* ctx, void* host_id128);
+int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world);
+int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n);
+int zb_dp_wait(zb_ctx* ctx);
+int zb_dp_rank(zb_ctx* ctx);
+int zb_dp_world(zb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZENU_B200_H */

@@ -1,0 +1,76 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU and exports every
+symbol the three public headers declare (include/*.h)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from zenu_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(_lib.LIB_PATH)
+
+
+def _declared(header):
+    pre = subprocess.run(["/usr/bin/gcc", "-E", "-P", "-x", "c", os.path.join(ROOT, "include", header)],
+                         check=True, capture_output=True, text=True).stdout
+    pre = re.sub(r"typedef[^;{]*\{[^}]*\}[^;]*;", "", pre, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_]\w*)\s*\([^()]*\)\s*;", pre)
+    return sorted(set(n for n in names if not n.startswith("__")))
+
+
+@pytest.mark.parametrize("header,minimum", [("zenu_b200.h", 40), ("zenu_kernel_compat.h", 120),
+                                            ("zenu_cudnn_frontend_compat.h", 15)])
+def test_exports_every_declared_symbol(lib, header, minimum):
+    names = _declared(header)
+    assert len(names) >= minimum, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"{header}: library does not export {missing}"
+
+
+def test_header_prototypes_parse():
+    protos = _lib.parse_header(os.path.join(ROOT, "include", "zenu_b200.h"))
+    assert protos["zb_conv2d_fprop"][1][4] is ctypes.c_void_p
+    assert protos["zb_conv_out_size"][0] is ctypes.c_int64
+    assert protos["zb_gemm"][1][8] is ctypes.c_double
+
+
+def test_host_only_entry_points(lib):
+    # pure host functions are safe without a GPU
+    lib.zb_conv_out_size.restype = ctypes.c_int64
+    lib.zb_conv_out_size.argtypes = [ctypes.c_int64] * 5
+    assert lib.zb_conv_out_size(224, 7, 3, 2, 1) == 112   # ResNet conv1
+    assert lib.zb_conv_out_size(56, 3, 1, 1, 1) == 56
+    assert lib.zb_conv_out_size(32, 3, 1, 1, 2) == 30     # dilation 2
+    lib.zb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.zb_version()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from zenu_b200 import ZenuB200Error, ops
+    with pytest.raises(ZenuB200Error):
+        ops.Context()
+
+
+def test_product_never_imports_oracle():
+    # the oracle is test infrastructure: nothing under zenu_b200/ may reference it
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "zenu_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"\boracle\b|zenu_oracle|libzenu_oracle", src):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

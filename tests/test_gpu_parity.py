@@ -1,0 +1,500 @@
+"""GPU parity tests proper: every call goes through the C ABI (libzenu_b200.so) and is compared with the CPU
+oracle (oracle/) on the same seeded inputs, and with the reference's golden vectors (tests/golden/).
+
+Tolerances (BASELINE.json north_star): rel 1e-3 for TF32 tensor-core math, 1e-5 for FFMA f32, 1e-10 for f64;
+golden-vector tests use the reference tests' own max-abs tolerances.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import zenu_oracle as zo  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32": 1e-3, "fp32": 1e-5, "f64": 1e-10}
+
+
+@pytest.fixture(scope="module")
+def zb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from zenu_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def ctx(zb):
+    c = zb.Context()
+    yield c
+    c.check()
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def lit(golden_dir):
+    with open(os.path.join(golden_dir, "literals.json")) as f:
+        return json.load(f)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    denom = np.linalg.norm(ref.ravel()) + 1e-300
+    rel_l2 = np.linalg.norm((got - ref).ravel()) / denom
+    max_rel = np.max(np.abs(got - ref)) / (np.max(np.abs(ref)) + 1e-300)
+    return max(rel_l2, max_rel)
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel())))
+
+
+def nhwc(a):
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))
+
+
+def nchw(a):
+    return np.ascontiguousarray(np.transpose(a, (0, 3, 1, 2)))
+
+
+def math_of(zb, name):
+    from zenu_b200 import ZB_MATH_FP32, ZB_MATH_TF32
+    return ZB_MATH_TF32 if name == "tf32" else ZB_MATH_FP32
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("math", ["tf32", "fp32"])
+def test_conv_golden_json(zb, ctx, golden_dir, math):
+    # zenu-matrix/src/nn/conv/mod.rs:131-179, tol 1e-4 (3->16 channels: served by the FFMA kernels in both modes)
+    d = np.load(os.path.join(golden_dir, "conv2d.npz"))
+    x, w = dev(d["input"]), dev(d["filter"])
+    m = math_of(zb, math)
+    y = zb.conv_fwd(ctx, x, w, pad=1, stride=1, dil=1, math=m)
+    assert maxabs(host(y), d["output"]) < 1e-4
+    dy = torch.ones_like(y)
+    assert maxabs(host(zb.conv_bkwd_data(ctx, dy, w, x.shape, 1, 1, 1, math=m)), d["grad_input"]) < 1e-4
+    assert maxabs(host(zb.conv_bkwd_weight(ctx, dy, x, w.shape, 1, 1, 1, math=m)), d["grad_weight"]) < 1e-4
+
+
+def test_conv_bias_golden_json(zb, ctx, golden_dir):
+    d = np.load(os.path.join(golden_dir, "conv_bias.npz"))
+    x, w, b = dev(d["input"]), dev(d["filter"]), dev(d["bias"])
+    y = zb.conv_fwd(ctx, x, w, pad=1, stride=1, dil=1, bias=b)
+    assert maxabs(host(y), d["output"]) < 1e-4
+    y2 = zb.conv2d_bias_add(ctx, zb.conv_fwd(ctx, x, w, pad=1), b)
+    assert maxabs(host(y2), d["output"]) < 1e-4
+    dy = torch.ones_like(y)
+    assert maxabs(host(zb.conv2d_bias_bkwd(ctx, dy)), d["grad_bias"]) < 1e-4
+
+
+def test_conv_small_literal(zb, ctx, lit):
+    c = lit["conv_fwd_small"]
+    x = dev(np.array(c["input"], np.float32).reshape(c["x_shape"]))
+    w = dev(np.array(c["filter"], np.float32).reshape(c["w_shape"]))
+    assert maxabs(host(zb.conv_fwd(ctx, x, w, pad=1)), c["output"]) < 1e-5
+
+
+def test_bn_goldens(zb, ctx, lit):
+    c = lit["bn_fwd_train"]
+    x = dev(np.array(c["x"], np.float32).reshape(c["shape"]))
+    rm, rv = dev(np.zeros(2, np.float32)), dev(np.zeros(2, np.float32))
+    y, sm, si = zb.batch_norm_2d_forward_train(ctx, c["momentum"], x, dev(np.array(c["scale"], np.float32)),
+                                               dev(np.array(c["bias"], np.float32)), rm, rv)
+    for got, key in ((y, "y"), (rm, "running_mean"), (rv, "running_variance"), (sm, "saved_mean"), (si, "saved_inv_std")):
+        assert maxabs(host(got), c[key]) < c["tol"], key
+    c = lit["bn_bwd"]
+    x = dev(np.array(c["x"], np.float32).reshape(c["shape"]))
+    dy = dev(np.array(c["y_grad"], np.float32).reshape(c["shape"]))
+    dx, ds, db = zb.batch_norm_2d_backward(ctx, x, dy, dev(np.array(c["scale"], np.float32)),
+                                           dev(np.array(c["saved_mean"], np.float32)), dev(np.array(c["saved_inv_std"], np.float32)))
+    assert maxabs(host(dx), c["x_grad"]) < c["tol"]
+    assert maxabs(host(ds), c["scale_grad"]) < c["tol"]
+    assert maxabs(host(db), c["bias_grad"]) < c["tol"]
+    c = lit["bn_infer"]
+    x = dev(np.array(c["x"], np.float32).reshape(c["shape"]))
+    y = zb.batch_norm_2d_forward_inference(ctx, x, *[dev(np.array(c[k], np.float32)) for k in ("scale", "bias", "mean", "variance")])
+    assert maxabs(host(y), c["y"]) < c["tol"]
+
+
+def test_bn_autograd_golden(zb, ctx, lit):
+    c = lit["bn_autograd"]
+    x = dev(np.array(c["x"], np.float32).reshape(c["shape"]))
+    dy = dev(np.array(c["y_grad"], np.float32).reshape(c["shape"]))
+    scale, bias = dev(np.array(c["scale"], np.float32)), dev(np.array(c["bias"], np.float32))
+    rm, rv = dev(np.array(c["prev_mean"], np.float32)), dev(np.array(c["prev_var"], np.float32))
+    y, sm, si = zb.batch_norm_2d_forward_train(ctx, c["momentum"], x, scale, bias, rm, rv)
+    assert maxabs(host(y), c["y"]) < c["tol_y"]
+    dx, ds, db = zb.batch_norm_2d_backward(ctx, x, dy, scale, sm, si)
+    assert maxabs(host(dx), c["x_grad"]) < c["tol_x_grad"]
+    assert maxabs(host(ds), c["scale_grad"]) < c["tol_param_grad"]
+    assert maxabs(host(db), c["bias_grad"]) < c["tol_param_grad"]
+    dx2, _, _ = zb.batch_norm_2d_backward(ctx, x, dy, scale)  # saved stats None -> recomputed
+    assert maxabs(host(dx2), c["x_grad"]) < c["tol_x_grad"]
+
+
+def test_gemm_relu_literals(zb, ctx, lit):
+    c = lit["gemm_3x4_4x5"]
+    a, b = np.array(c["a"], np.float32).reshape(3, 4), np.array(c["b"], np.float32).reshape(4, 5)
+    from zenu_b200 import ZB_MATH_FP32
+    out = host(zb.gemm(ctx, dev(a), dev(b), math=ZB_MATH_FP32))
+    assert float(np.abs(out.ravel() - np.array(c["c"])).sum()) < c["tol_asum"]
+    c = lit["relu"]
+    x = dev(np.array(c["x"], np.float32))
+    assert maxabs(host(zb.relu(ctx, x)), c["y"]) < c["tol"]
+    assert maxabs(host(zb.relu_backward_mask(ctx, x)), c["mask"]) < c["tol"]
+
+
+# ------------------------------------------------------------------------------------------------ conv vs oracle
+CONV_CASES = [
+    # n, c, h, w, k, r, s, pad, stride, dil
+    (2, 64, 14, 14, 128, 3, 3, 1, 1, 1),   # 3x3 s1 (im2col TMA)
+    (2, 64, 15, 17, 64, 3, 3, 1, 2, 1),    # 3x3 s2, odd sizes
+    (3, 128, 9, 9, 256, 1, 1, 0, 1, 1),    # 1x1 (plain GEMM)
+    (2, 64, 16, 16, 96, 1, 1, 0, 2, 1),    # 1x1 s2 (downsample)
+    (1, 32, 12, 12, 40, 3, 3, 2, 1, 2),    # dilation 2
+    (2, 32, 8, 8, 32, 5, 5, 2, 1, 1),      # 5x5
+    (2, 3, 20, 20, 16, 7, 7, 3, 2, 1),     # conv1-like: C=3 (FFMA path)
+    (1, 20, 7, 7, 12, 3, 3, 0, 1, 1),      # ragged channels, no padding
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("math", ["tf32", "fp32"])
+def test_conv_vs_oracle(zb, ctx, case, layout, math):
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    n, c, h, w, k, r, s, pad, stride, dil = case
+    rng = np.random.default_rng(1234 + sum(case))
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, s)) * np.sqrt(2.0 / (c * r * s))).astype(np.float32)
+    y_ref = zo.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), pad, stride, dil)
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    dx_ref = zo.conv2d_bkwd_data(dy.astype(np.float64), wt.astype(np.float64), x.shape, pad, stride, dil)
+    dw_ref = zo.conv2d_bkwd_filter(dy.astype(np.float64), x.astype(np.float64), wt.shape, pad, stride, dil)
+    m = math_of(zb, math)
+    if layout == "nchw":
+        L, X, W, DY, back_a, back_w = ZB_NCHW, dev(x), dev(wt), dev(dy), (lambda t: host(t)), (lambda t: host(t))
+    else:
+        L, X, W, DY = ZB_NHWC, dev(nhwc(x)), dev(nhwc(wt)), dev(nhwc(dy))
+        back_a = back_w = lambda t: nchw(host(t))
+    tol = TOL[math]
+    y = zb.conv_fwd(ctx, X, W, pad, stride, dil, layout=L, math=m)
+    assert rel_err(back_a(y), y_ref) < tol
+    dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, stride, dil, layout=L, math=m)
+    assert rel_err(back_a(dx), dx_ref) < tol
+    dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, stride, dil, layout=L, math=m)
+    assert rel_err(back_w(dw), dw_ref) < tol
+    ctx.check()
+
+
+def test_conv_f64_vs_oracle(zb, ctx):
+    n, c, h, w, k, r, s, pad, stride, dil = 2, 8, 10, 10, 6, 3, 3, 1, 2, 1
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((n, c, h, w))
+    wt = rng.standard_normal((k, c, r, s))
+    y_ref = zo.conv2d_fwd(x, wt, pad, stride, dil)
+    dy = rng.standard_normal(y_ref.shape)
+    y = zb.conv_fwd(ctx, dev(x), dev(wt), pad, stride, dil)
+    assert rel_err(host(y), y_ref) < TOL["f64"]
+    assert rel_err(host(zb.conv_bkwd_data(ctx, dev(dy), dev(wt), x.shape, pad, stride, dil)),
+                   zo.conv2d_bkwd_data(dy, wt, x.shape, pad, stride, dil)) < TOL["f64"]
+    assert rel_err(host(zb.conv_bkwd_weight(ctx, dev(dy), dev(x), wt.shape, pad, stride, dil)),
+                   zo.conv2d_bkwd_filter(dy, x, wt.shape, pad, stride, dil)) < TOL["f64"]
+
+
+def test_conv_bias_bwd_batched(zb, ctx):
+    # N > 1: the reference GPU kernel is wrong here; the CPU semantics are the contract
+    from zenu_b200 import ZB_NHWC
+    rng = np.random.default_rng(3)
+    dy = rng.standard_normal((5, 7, 6, 4)).astype(np.float32)
+    ref = zo.conv2d_bias_bkwd(dy.astype(np.float64))
+    assert rel_err(host(zb.conv2d_bias_bkwd(ctx, dev(dy))), ref) < 1e-5
+    assert rel_err(host(zb.conv2d_bias_bkwd(ctx, dev(nhwc(dy)), layout=ZB_NHWC)), ref) < 1e-5
+
+
+def test_conv_shape_errors(zb, ctx):
+    from zenu_b200 import ZenuB200Error
+    x = torch.zeros((1, 4, 8, 8), device="cuda")
+    w = torch.zeros((2, 3, 3, 3), device="cuda")
+    with pytest.raises(ZenuB200Error):
+        zb.conv_fwd(ctx, x, w, pad=1)
+    w = torch.zeros((2, 4, 11, 11), device="cuda")
+    with pytest.raises(ZenuB200Error):
+        zb.conv_fwd(ctx, x, w, pad=0)  # filter larger than input
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / Linear
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("math", ["tf32", "fp32"])
+@pytest.mark.parametrize("shape", [(256, 128, 64), (300, 200, 100), (64, 1000, 2048), (8, 8, 4096)])
+def test_gemm_vs_oracle(zb, ctx, ta, tb, math, shape):
+    m, n, k = shape
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((k, m) if ta else (m, k)).astype(np.float32)
+    b = rng.standard_normal((n, k) if tb else (k, n)).astype(np.float32)
+    c0 = rng.standard_normal((m, n)).astype(np.float32)
+    ref = zo.gemm(a.astype(np.float64), b.astype(np.float64), ta, tb, 0.5, 0.25, c0.astype(np.float64))
+    got = zb.gemm(ctx, dev(a), dev(b), ta, tb, 0.5, 0.25, dev(c0), math=math_of(zb, math))
+    assert rel_err(host(got), ref) < TOL[math]
+    ctx.check()
+
+
+@pytest.mark.parametrize("math", ["tf32", "fp32"])
+def test_linear_vs_oracle(zb, ctx, math):
+    rng = np.random.default_rng(11)
+    b, i, o = 64, 512, 10
+    x = rng.standard_normal((b, i)).astype(np.float32)
+    w = (rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32)
+    bias = rng.standard_normal((o,)).astype(np.float32)
+    dy = rng.standard_normal((b, o)).astype(np.float32)
+    m = math_of(zb, math)
+    y = zb.linear_fwd(ctx, dev(x), dev(w), dev(bias), math=m)
+    assert rel_err(host(y), zo.linear_fwd(x.astype(np.float64), w.astype(np.float64), bias.astype(np.float64))) < TOL[math]
+    dx, dw, db = zb.linear_bwd(ctx, dev(x), dev(w), dev(dy), math=m)
+    rdx, rdw, rdb = zo.linear_bwd(x.astype(np.float64), w.astype(np.float64), dy.astype(np.float64))
+    assert rel_err(host(dx), rdx) < TOL[math]
+    assert rel_err(host(dw), rdw) < TOL[math]
+    assert rel_err(host(db), rdb) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm
+@pytest.mark.parametrize("shape", [(4, 64, 9, 7), (3, 5, 6, 6), (2, 256, 4, 4), (16, 8, 1, 1)])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bn_vs_oracle(zb, ctx, shape, layout, dtype):
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    rng = np.random.default_rng(sum(shape))
+    n, c, h, w = shape
+    x = (rng.standard_normal(shape) * 2.0 + 3.0).astype(dtype)   # non-zero mean exercises the shifted statistics
+    dy = rng.standard_normal(shape).astype(dtype)
+    scale, bias = rng.standard_normal(c).astype(dtype), rng.standard_normal(c).astype(dtype)
+    rm0, rv0 = rng.standard_normal(c).astype(dtype), (rng.random(c) + 0.5).astype(dtype)
+    x64, dy64 = x.astype(np.float64), dy.astype(np.float64)
+    y_ref, rm_ref, rv_ref, sm_ref, si_ref = zo.bn2d_fwd_train(x64, scale.astype(np.float64), bias.astype(np.float64),
+                                                                rm0.astype(np.float64), rv0.astype(np.float64), 0.9)
+    dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x64, dy64, scale.astype(np.float64), sm_ref, si_ref)
+    tol = 2e-5 if dtype == np.float32 else 1e-10
+    if layout == "nchw":
+        L, X, DY, back = ZB_NCHW, dev(x), dev(dy), host
+    else:
+        L, X, DY, back = ZB_NHWC, dev(nhwc(x)), dev(nhwc(dy)), (lambda t: nchw(host(t)))
+    rm, rv = dev(rm0), dev(rv0)
+    y, sm, si = zb.batch_norm_2d_forward_train(ctx, 0.9, X, dev(scale), dev(bias), rm, rv, layout=L)
+    assert rel_err(back(y), y_ref) < tol
+    assert rel_err(host(rm), rm_ref) < tol and rel_err(host(rv), rv_ref) < tol
+    assert rel_err(host(sm), sm_ref) < tol and rel_err(host(si), si_ref) < tol
+    dx, ds, db = zb.batch_norm_2d_backward(ctx, X, DY, dev(scale), sm, si, layout=L)
+    assert rel_err(back(dx), dx_ref) < 20 * tol
+    assert rel_err(host(ds), ds_ref) < 20 * tol and rel_err(host(db), db_ref) < 20 * tol
+    yi = zb.batch_norm_2d_forward_inference(ctx, X, dev(scale), dev(bias), dev(rm0), dev(rv0), layout=L)
+    assert rel_err(back(yi), zo.bn2d_fwd_infer(x64, scale.astype(np.float64), bias.astype(np.float64),
+                                                 rm0.astype(np.float64), rv0.astype(np.float64))) < tol
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_bn_fused_relu_residual(zb, ctx, layout):
+    """Fused BN+add+ReLU fwd/bwd == the reference's separate nodes (BN -> add -> relu) composed from oracle ops."""
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    rng = np.random.default_rng(99)
+    shape = (4, 32, 6, 5)
+    c = shape[1]
+    x = rng.standard_normal(shape)
+    res = rng.standard_normal(shape)
+    dy = rng.standard_normal(shape)
+    scale, bias = rng.standard_normal(c), rng.standard_normal(c)
+    bn, _, _, sm, si = zo.bn2d_fwd_train(x, scale, bias, np.zeros(c), np.ones(c), 0.9)
+    z = zo.ewise("add", bn, res)
+    out_ref = zo.relu(z)
+    dz = zo.ewise("mul", dy, zo.relu_backward_mask(z))          # relu backward (activation/relu.rs:36-46)
+    dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x, dz, scale, sm, si)  # add backward passes dz to both inputs
+    f = np.float32
+    if layout == "nchw":
+        L, cv, back = ZB_NCHW, (lambda a: dev(a.astype(f))), host
+    else:
+        L, cv, back = ZB_NHWC, (lambda a: dev(nhwc(a.astype(f)))), (lambda t: nchw(host(t)))
+    X, R, DY = cv(x), cv(res), cv(dy)
+    S, B = dev(scale.astype(f)), dev(bias.astype(f))
+    y, smg, sig = zb.batch_norm_2d_forward_train(ctx, 0.9, X, S, B, dev(np.zeros(c, f)), dev(np.ones(c, f)), layout=L,
+                                                 residual=R, relu=True)
+    assert rel_err(back(y), out_ref) < 2e-5
+    dx, ds, db, dres = zb.batch_norm_2d_backward(ctx, X, DY, S, smg, sig, layout=L, y=y, want_residual_grad=True)
+    assert rel_err(back(dx), dx_ref) < 2e-4
+    assert rel_err(back(dres), dz) < 2e-5
+    assert rel_err(host(ds), ds_ref) < 2e-4 and rel_err(host(db), db_ref) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ elementwise / pool / loss / optim
+def test_elementwise_vs_oracle(zb, ctx):
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 1024, 100003):
+        a = rng.standard_normal(n).astype(np.float32)
+        b = (rng.standard_normal(n) + 3.0).astype(np.float32)
+        for op in ("add", "sub", "mul", "div"):
+            np.testing.assert_array_equal(host(zb.binary(ctx, op, dev(a), dev(b))), zo.ewise(op, a, b))
+            np.testing.assert_allclose(host(zb.binary(ctx, op, dev(a), 1.5)), zo.ewise(op, a, 1.5), rtol=1e-6)
+        np.testing.assert_array_equal(host(zb.relu(ctx, dev(a))), zo.relu(a))
+        np.testing.assert_array_equal(host(zb.relu_backward_mask(ctx, dev(a))), zo.relu_backward_mask(a))
+        np.testing.assert_array_equal(host(zb.relu_bwd(ctx, dev(a), dev(b))), zo.ewise("mul", b, zo.relu_backward_mask(a)))
+    a = rng.standard_normal((37, 24)).astype(np.float32)
+    v = rng.standard_normal(24).astype(np.float32)
+    np.testing.assert_array_equal(host(zb.binary(ctx, "add", dev(a), dev(v))), a + v)
+    np.testing.assert_allclose(host(zb.sum_rows(ctx, dev(a))), a.astype(np.float64).sum(0), rtol=1e-5, atol=1e-5)
+    x = rng.standard_normal((3, 5, 4, 6)).astype(np.float32)
+    np.testing.assert_array_equal(host(zb.to_nhwc(ctx, dev(x))), nhwc(x))
+    np.testing.assert_array_equal(host(zb.to_nchw(ctx, dev(nhwc(x)))), x)
+    e = torch.empty(0, device="cuda")
+    assert zb.relu(ctx, e).numel() == 0  # empty input
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_pool_and_gap(zb, ctx, layout):
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    rng = np.random.default_rng(8)
+    x = np.maximum(rng.standard_normal((2, 6, 11, 9)), 0).astype(np.float32)   # post-ReLU input with ties at 0
+    y_ref = zo.maxpool2d_fwd(x, 3, 2, 1)
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    dx_ref = zo.maxpool2d_bwd(x, dy, 3, 2, 1)
+    if layout == "nchw":
+        L, cv, back = ZB_NCHW, dev, host
+    else:
+        L, cv, back = ZB_NHWC, (lambda a: dev(nhwc(a))), (lambda t: nchw(host(t)))
+    y = zb.max_pool_2d(ctx, cv(x), 3, 2, 1, layout=L)
+    np.testing.assert_array_equal(back(y), y_ref)
+    dx = zb.max_pool_2d_backward(ctx, cv(x), cv(dy), 3, 2, 1, layout=L)
+    np.testing.assert_allclose(back(dx), dx_ref, rtol=1e-6, atol=1e-6)
+    g = zb.global_avg_pool(ctx, cv(x), layout=L)
+    np.testing.assert_allclose(host(g), zo.gap_fwd(x), rtol=1e-6, atol=1e-7)
+    dg = rng.standard_normal((2, 6)).astype(np.float32)
+    np.testing.assert_allclose(back(zb.global_avg_pool_backward(ctx, dev(dg), cv(x).shape, layout=L)), zo.gap_bwd(dg, (11, 9)), rtol=1e-6)
+
+
+def test_softmax_xent(zb, ctx):
+    rng = np.random.default_rng(21)
+    z = (rng.standard_normal((16, 1000)) * 3).astype(np.float32)
+    t = np.zeros((16, 1000), np.float32)
+    t[np.arange(16), rng.integers(0, 1000, 16)] = 1.0
+    loss_ref, dz_ref = zo.softmax_xent(z.astype(np.float64), t.astype(np.float64))
+    loss, dz = zb.softmax_cross_entropy(ctx, dev(z), dev(t))
+    assert abs(float(host(loss)[0]) - loss_ref) < 1e-5 * max(1.0, abs(loss_ref))
+    assert rel_err(host(dz), dz_ref) < 1e-5
+
+
+def test_optimizers_vs_oracle(zb, ctx, lit):
+    rng = np.random.default_rng(31)
+    n = 10007
+    p0 = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    p_ref = p0.copy()
+    zo.sgd_step(p_ref, g, 0.01)
+    p = dev(p0)
+    zb.sgd_step(ctx, p, dev(g), 0.01)
+    np.testing.assert_allclose(host(p), p_ref, rtol=1e-6, atol=1e-7)
+    for decay in (False, True):
+        p_ref, m_ref, v_ref = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        p, m, v = dev(p0), dev(np.zeros(n, np.float32)), dev(np.zeros(n, np.float32))
+        for step in (1, 2, 3):
+            zo.adam_step(p_ref, g, m_ref, v_ref, 0.01, 0.9, 0.999, 1e-8, step, 0.01, decay)
+            zb.adam_step(ctx, p, dev(g), m, v, 0.01, 0.9, 0.999, 1e-8, step, 0.01, decay)
+        np.testing.assert_allclose(host(p), p_ref, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(host(m), m_ref, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ compat shims
+def test_kernel_sys_shim(zb, ctx):
+    """The zenu-cuda-kernel-sys symbol names, called with raw device pointers (strided and unit-stride)."""
+    from zenu_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(64).astype(np.float32)
+    b = rng.standard_normal(64).astype(np.float32)
+    A, B = dev(a), dev(b)
+    C = torch.zeros(64, device="cuda")
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.array_array_add_float.argtypes = [vp, ci, vp, ci, vp, ci, ci]
+    lib.array_array_add_float.restype = None
+    lib.array_array_add_float(A.data_ptr(), 1, B.data_ptr(), 1, C.data_ptr(), 1, 64)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(C), a + b)
+    C.zero_()
+    lib.array_array_add_float(A.data_ptr(), 2, B.data_ptr(), 2, C.data_ptr(), 1, 32)   # strided inputs
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(C)[:32], a[::2] + b[::2])
+    lib.relu_float.argtypes = [vp, vp, cf, ci, ci, ci]
+    lib.relu_float.restype = None
+    lib.relu_float(A.data_ptr(), C.data_ptr(), 0.0, 64, 1, 1)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(host(C), np.maximum(a, 0))
+    dy = rng.standard_normal((3, 4, 5, 6)).astype(np.float32)
+    DB = torch.zeros(4, device="cuda")
+    lib.conv2d_bias_bkwd_float.argtypes = [vp, vp, ci, ci, ci, ci]
+    lib.conv2d_bias_bkwd_float.restype = None
+    lib.conv2d_bias_bkwd_float(dev(dy).data_ptr(), DB.data_ptr(), 3, 4, 5, 6)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(host(DB), zo.conv2d_bias_bkwd(dy), rtol=1e-5)
+    out = ctypes.c_float(0)
+    lib.memory_access_float.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float)]
+    lib.memory_access_float.restype = None
+    lib.memory_access_float(A.data_ptr(), 5, ctypes.byref(out))
+    assert out.value == a[5]
+
+
+def test_cudnn_frontend_shim(zb, ctx, golden_dir):
+    """create/check/workspace/execute on the reference's conv fixture through the cuDNN-frontend-shaped ABI."""
+    from zenu_b200 import _lib
+    lib = _lib.load()
+
+    class Shape(ctypes.Structure):
+        _fields_ = [("num_dims", ctypes.c_size_t), ("dims", ctypes.c_int64 * 8), ("strides", ctypes.c_int64 * 8)]
+
+    class Info(ctypes.Structure):
+        _fields_ = [("padding", ctypes.c_int64 * 2), ("stride", ctypes.c_int64 * 2), ("dilation", ctypes.c_int64 * 2),
+                    ("num_dims", ctypes.c_int64)]
+
+    class Bufs(ctypes.Structure):
+        _fields_ = [("X", ctypes.c_void_p), ("filter", ctypes.c_void_p), ("Y", ctypes.c_void_p)]
+
+    def shp(dims):
+        s = Shape()
+        s.num_dims = 4
+        st = 1
+        for i in (3, 2, 1, 0):
+            s.dims[i] = dims[i]
+            s.strides[i] = st
+            st *= dims[i]
+        return s
+
+    d = np.load(os.path.join(golden_dir, "conv2d.npz"))
+    x, w = dev(d["input"]), dev(d["filter"])
+    y = torch.zeros(d["output"].shape, device="cuda")
+    info = Info()
+    info.padding[:] = [1, 1]; info.stride[:] = [1, 1]; info.dilation[:] = [1, 1]; info.num_dims = 2
+    desc = ctypes.c_void_p()
+    xs, ws, ys = shp(x.shape), shp(w.shape), shp(y.shape)
+    lib.create_conv_descriptor.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
+    assert lib.create_conv_descriptor(ctypes.byref(desc), 1, ctypes.byref(xs), ctypes.byref(ws), ctypes.byref(ys), ctypes.byref(info)) == 0
+    lib.check_conv_graph.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.check_conv_graph(desc, None) == 0
+    size = ctypes.c_int64(-1)
+    lib.get_conv_workspace_size.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.get_conv_workspace_size(desc, ctypes.byref(size)) == 0 and size.value == 0
+    bufs = Bufs(x.data_ptr(), w.data_ptr(), y.data_ptr())
+    lib.execute_conv_forward.argtypes = [ctypes.c_void_p] * 4
+    assert lib.execute_conv_forward(desc, ctypes.byref(bufs), None, None) == 0
+    torch.cuda.synchronize()
+    assert maxabs(host(y), d["output"]) < 1e-4
+    lib.destroy_conv_descriptor.argtypes = [ctypes.c_void_p]
+    lib.destroy_conv_descriptor(desc)

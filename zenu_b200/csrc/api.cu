@@ -1,0 +1,224 @@
+// api.cu — C-ABI entry points for convolution, GEMM and Linear: argument validation and dispatch over
+// dtype x layout x math mode onto the tcgen05 path (umma_gemm.cu) or the FFMA/DFMA path (conv_simt.cu).
+// There is no CPU fallback anywhere: a request neither GPU path can serve returns ZB_ERR_UNSUPPORTED.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace zb {
+// umma_gemm.cu
+int umma_gemm(zb_ctx*, bool, bool, long long, long long, long long, float, const float*, long long, const float*, long long,
+              float, float*, long long, const float*);
+bool umma_conv_supported(const zb_conv2d_desc*);
+int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*);
+int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+// conv_simt.cu
+template <typename T> int simt_conv_fprop(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, const T*, T*);
+template <typename T> int simt_conv_dgrad(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, T*);
+template <typename T> int simt_conv_wgrad(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, T*);
+template <typename T> int simt_gemm(zb_ctx*, bool, bool, long long, long long, long long, T, const T*, long long, const T*, long long, T, T*, long long, const T*);
+// elementwise.cu / batchnorm.cu
+template <typename T> int transpose_batched(zb_ctx*, const T*, T*, long long, long long, long long);
+template <typename T> int bias_add_nchw(zb_ctx*, const T*, const T*, T*, long long, long long, long long);
+template <typename T> int channel_sum(zb_ctx*, int, long long, long long, long long, const T*, T*);
+
+static int check_desc(const zb_conv2d_desc* d, long long* P, long long* Q) {
+  ZB_REQUIRE(d != nullptr, "conv: desc is NULL");
+  ZB_REQUIRE(d->n > 0 && d->c > 0 && d->h > 0 && d->w > 0 && d->k > 0 && d->kh > 0 && d->kw > 0, "conv: non-positive extent");
+  ZB_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0 && d->pad_h >= 0 && d->pad_w >= 0,
+             "conv: bad stride/dilation/padding");
+  ZB_REQUIRE(d->h + 2 * d->pad_h >= d->dil_h * (d->kh - 1) + 1 && d->w + 2 * d->pad_w >= d->dil_w * (d->kw - 1) + 1,
+             "conv: filter larger than padded input");
+  *P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  *Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  ZB_REQUIRE(d->n * d->c * d->h * d->w < (1ll << 40) && d->n * d->k * (*P) * (*Q) < (1ll << 40), "conv: tensor too large");
+  return ZB_OK;
+}
+
+static int resolve_math(zb_ctx* ctx, int dtype, int math, int* out) {
+  int m = (math == ZB_MATH_DEFAULT) ? ctx->default_math : math;
+  ZB_REQUIRE(m == ZB_MATH_TF32 || m == ZB_MATH_FP32, "unknown math mode %d", math);
+  if (dtype == ZB_F64) m = ZB_MATH_FP32;  // f64 always runs DFMA
+  *out = m;
+  return ZB_OK;
+}
+
+// Scoped stream-ordered temporaries for the NCHW (reference-contract) staging path.
+struct Temp {
+  zb_ctx* ctx;
+  void* p = nullptr;
+  explicit Temp(zb_ctx* c) : ctx(c) {}
+  int alloc(size_t bytes) {
+    ZB_CHECK_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), ctx->stream));
+    return ZB_OK;
+  }
+  ~Temp() { if (p) cudaFreeAsync(p, ctx->stream); }
+};
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
+                    const void* bias, void* y) {
+  long long P, Q;
+  int rc = check_desc(d, &P, &Q);
+  if (rc != ZB_OK) return rc;
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "conv: unknown layout %d", layout);
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "conv: unknown dtype %d", dtype);
+  int m;
+  rc = resolve_math(ctx, dtype, math, &m);
+  if (rc != ZB_OK) return rc;
+  if (dtype == ZB_F64)
+    return simt_conv_fprop<double>(ctx, layout, d, static_cast<const double*>(x), static_cast<const double*>(w),
+                                   static_cast<const double*>(bias), static_cast<double*>(y));
+  const float* xf = static_cast<const float*>(x);
+  const float* wf = static_cast<const float*>(w);
+  const float* bf = static_cast<const float*>(bias);
+  float* yf = static_cast<float*>(y);
+  if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_fprop<float>(ctx, layout, d, xf, wf, bf, yf);
+  if (layout == ZB_NHWC) return umma_conv_fprop_nhwc(ctx, d, xf, wf, bf, yf);
+  // NCHW contract: stage through NHWC / KRSC
+  Temp tx(ctx), tw(ctx), ty(ctx);
+  if ((rc = tx.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
+  if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
+  if ((rc = ty.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, xf, static_cast<float*>(tx.p), d->n, d->c, d->h * d->w)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
+  if ((rc = umma_conv_fprop_nhwc(ctx, d, static_cast<float*>(tx.p), static_cast<float*>(tw.p), bf, static_cast<float*>(ty.p))) != ZB_OK) return rc;
+  return transpose_batched<float>(ctx, static_cast<float*>(ty.p), yf, d->n, P * Q, d->k);
+}
+
+int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
+                    void* dx) {
+  long long P, Q;
+  int rc = check_desc(d, &P, &Q);
+  if (rc != ZB_OK) return rc;
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "conv: unknown layout %d", layout);
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "conv: unknown dtype %d", dtype);
+  int m;
+  rc = resolve_math(ctx, dtype, math, &m);
+  if (rc != ZB_OK) return rc;
+  if (dtype == ZB_F64)
+    return simt_conv_dgrad<double>(ctx, layout, d, static_cast<const double*>(dy), static_cast<const double*>(w), static_cast<double*>(dx));
+  const float* gf = static_cast<const float*>(dy);
+  const float* wf = static_cast<const float*>(w);
+  float* df = static_cast<float*>(dx);
+  const bool tc_ok = (d->k % 32 == 0) && (d->c % 4 == 0) && d->kh * d->kw <= 64;
+  if (m == ZB_MATH_FP32 || !tc_ok) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
+  if (layout == ZB_NHWC) {
+    rc = umma_conv_dgrad_nhwc(ctx, d, gf, wf, df);
+    if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
+    return rc;
+  }
+  Temp tg(ctx), tw(ctx), td(ctx);
+  if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
+  if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
+  if ((rc = td.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
+  rc = umma_conv_dgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p));
+  if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
+  if (rc != ZB_OK) return rc;
+  return transpose_batched<float>(ctx, static_cast<float*>(td.p), df, d->n, d->h * d->w, d->c);
+}
+
+int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* x,
+                    void* dw) {
+  long long P, Q;
+  int rc = check_desc(d, &P, &Q);
+  if (rc != ZB_OK) return rc;
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "conv: unknown layout %d", layout);
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "conv: unknown dtype %d", dtype);
+  int m;
+  rc = resolve_math(ctx, dtype, math, &m);
+  if (rc != ZB_OK) return rc;
+  if (dtype == ZB_F64)
+    return simt_conv_wgrad<double>(ctx, layout, d, static_cast<const double*>(dy), static_cast<const double*>(x), static_cast<double*>(dw));
+  const float* gf = static_cast<const float*>(dy);
+  const float* xf = static_cast<const float*>(x);
+  float* wf = static_cast<float*>(dw);
+  if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_wgrad<float>(ctx, layout, d, gf, xf, wf);
+  if (layout == ZB_NHWC) return umma_conv_wgrad_nhwc(ctx, d, gf, xf, wf);
+  Temp tg(ctx), tx(ctx), tw(ctx);
+  if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
+  if ((rc = tx.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
+  if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
+  if ((rc = transpose_batched<float>(ctx, xf, static_cast<float*>(tx.p), d->n, d->c, d->h * d->w)) != ZB_OK) return rc;
+  if ((rc = umma_conv_wgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tx.p), static_cast<float*>(tw.p))) != ZB_OK) return rc;
+  return transpose_batched<float>(ctx, static_cast<float*>(tw.p), wf, d->k, d->kh * d->kw, d->c);  // KRSC -> KCRS
+}
+
+int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const void* bias, void* y, int64_t n, int64_t k,
+                       int64_t h, int64_t w) {
+  if (layout == ZB_NHWC) return zb_binary_bcast_rows(ctx, dtype, ZB_OP_ADD, x, bias, y, n * h * w, k);
+  ZB_REQUIRE(layout == ZB_NCHW, "bias_add: unknown layout %d", layout);
+  if (dtype == ZB_F32) return bias_add_nchw<float>(ctx, static_cast<const float*>(x), static_cast<const float*>(bias), static_cast<float*>(y), n, k, h * w);
+  if (dtype == ZB_F64) return bias_add_nchw<double>(ctx, static_cast<const double*>(x), static_cast<const double*>(bias), static_cast<double*>(y), n, k, h * w);
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_gemm(zb_ctx* ctx, int dtype, int math, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+            const void* a, int64_t lda, const void* b, int64_t ldb, double beta, void* c, int64_t ldc) {
+  ZB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative extent");
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "gemm: unknown dtype %d", dtype);
+  if (m == 0 || n == 0) return ZB_OK;
+  ZB_REQUIRE(lda >= (trans_a ? m : k) && ldb >= (trans_b ? k : n) && ldc >= n, "gemm: leading dimension too small");
+  int mm;
+  int rc = resolve_math(ctx, dtype, math, &mm);
+  if (rc != ZB_OK) return rc;
+  if (dtype == ZB_F64)
+    return simt_gemm<double>(ctx, trans_a != 0, trans_b != 0, m, n, k, alpha, static_cast<const double*>(a), lda,
+                             static_cast<const double*>(b), ldb, beta, static_cast<double*>(c), ldc, static_cast<const double*>(nullptr));
+  if (mm == ZB_MATH_TF32 && k > 0) {
+    rc = umma_gemm(ctx, trans_a != 0, trans_b != 0, m, n, k, static_cast<float>(alpha), static_cast<const float*>(a), lda,
+                   static_cast<const float*>(b), ldb, static_cast<float>(beta), static_cast<float*>(c), ldc, nullptr);
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
+  }
+  return simt_gemm<float>(ctx, trans_a != 0, trans_b != 0, m, n, k, static_cast<float>(alpha), static_cast<const float*>(a), lda,
+                          static_cast<const float*>(b), ldb, static_cast<float>(beta), static_cast<float*>(c), ldc, static_cast<const float*>(nullptr));
+}
+
+int zb_linear_fwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* bias, void* y, int64_t batch,
+                  int64_t in_f, int64_t out_f) {
+  ZB_REQUIRE(batch > 0 && in_f > 0 && out_f > 0, "linear: non-positive extent");
+  int mm;
+  int rc = resolve_math(ctx, dtype, math, &mm);
+  if (rc != ZB_OK) return rc;
+  if (dtype == ZB_F64)
+    return simt_gemm<double>(ctx, false, true, batch, out_f, in_f, 1.0, static_cast<const double*>(x), in_f,
+                             static_cast<const double*>(w), in_f, 0.0, static_cast<double*>(y), out_f, static_cast<const double*>(bias));
+  if (mm == ZB_MATH_TF32) {
+    rc = umma_gemm(ctx, false, true, batch, out_f, in_f, 1.f, static_cast<const float*>(x), in_f, static_cast<const float*>(w), in_f,
+                   0.f, static_cast<float*>(y), out_f, static_cast<const float*>(bias));
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
+  }
+  return simt_gemm<float>(ctx, false, true, batch, out_f, in_f, 1.f, static_cast<const float*>(x), in_f, static_cast<const float*>(w), in_f,
+                          0.f, static_cast<float*>(y), out_f, static_cast<const float*>(bias));
+}
+
+int zb_linear_bwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* dy, void* dx, void* dw,
+                  void* dbias, int64_t batch, int64_t in_f, int64_t out_f) {
+  ZB_REQUIRE(batch > 0 && in_f > 0 && out_f > 0, "linear: non-positive extent");
+  int rc;
+  if (dx) {  // dX[b,in] = dY[b,out] * W[out,in]
+    rc = zb_gemm(ctx, dtype, math, 0, 0, batch, in_f, out_f, 1.0, dy, out_f, w, in_f, 0.0, dx, in_f);
+    if (rc != ZB_OK) return rc;
+  }
+  if (dw) {  // dW[out,in] = dY^T[out,b] * X[b,in]
+    rc = zb_gemm(ctx, dtype, math, 1, 0, out_f, in_f, batch, 1.0, dy, out_f, x, in_f, 0.0, dw, in_f);
+    if (rc != ZB_OK) return rc;
+  }
+  if (dbias) {
+    rc = zb_sum_rows(ctx, dtype, dy, dbias, batch, out_f);
+    if (rc != ZB_OK) return rc;
+  }
+  return ZB_OK;
+}
+
+}  // extern "C"

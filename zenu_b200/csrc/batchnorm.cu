@@ -1,0 +1,733 @@
+// batchnorm.cu — BatchNorm2d forward (train / inference) and backward, with optional fused ReLU and
+// residual add, for NHWC (native) and NCHW (reference contract) tensors, f32 and f64.
+//
+// Replaces cudnnBatchNormalizationForwardTraining / Backward / ForwardInference (reference
+// zenu-cuda/src/cudnn/batch_norm.rs:51-91,206-249,380-414) with the semantics of the reference CPU path
+// (zenu-matrix/src/nn/batch_norm.rs:283-420): eps 1e-10, momentum on the OLD running stat, unbiased running
+// variance, saved mean and 1/sqrt(var+eps).  Also hosts the per-channel column reductions used by
+// conv2d_bias_bkwd and Matrix::sum(axis 0).
+//
+// Structure (every kernel is HBM-bound; 128-bit loads, no atomics, deterministic):
+//   reduce  : grid (channel groups, row slabs); each thread owns VN channels and walks rows with 4 loads in
+//             flight; block-level smem reduction -> partial[slab][stat][C]
+//   finalize: one thread per channel folds the slab partials in double precision
+//   apply   : same geometry as reduce; per-channel coefficients live in registers
+// Statistics use a per-channel shift (the first row) so the single-pass sum / sum-of-squares does not cancel.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace zb {
+
+constexpr double kBnEps = 1e-10;  // zenu-matrix/src/nn/batch_norm.rs:296
+
+template <typename T, int VN> struct VecT;
+template <> struct VecT<float, 4> { using type = float4; };
+template <> struct VecT<float, 1> { using type = float; };
+template <> struct VecT<double, 2> { using type = double2; };
+template <> struct VecT<double, 1> { using type = double; };
+
+template <typename T, int VN>
+__device__ __forceinline__ void ldv(const T* p, T* o) {
+  using V = typename VecT<T, VN>::type;
+  const V v = *reinterpret_cast<const V*>(p);
+  const T* s = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int e = 0; e < VN; ++e) o[e] = s[e];
+}
+template <typename T, int VN>
+__device__ __forceinline__ void stv(T* p, const T* o) {
+  using V = typename VecT<T, VN>::type;
+  V v;
+  T* s = reinterpret_cast<T*>(&v);
+#pragma unroll
+  for (int e = 0; e < VN; ++e) s[e] = o[e];
+  *reinterpret_cast<V*>(p) = v;
+}
+
+struct ColGeom {
+  int tx, ty, col_groups, slabs;
+  long long rows_per_slab, cvecs;
+};
+
+static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
+  ColGeom g;
+  g.cvecs = C / vn;
+  int tx = 1;
+  while (tx < 32 && tx < g.cvecs) tx <<= 1;
+  g.tx = tx;
+  g.ty = 256 / tx;
+  g.col_groups = static_cast<int>((g.cvecs + tx - 1) / tx);
+  long long max_slabs = std::max<long long>(1, (ctx->sm_count * 8ll) / g.col_groups);
+  long long want = (rows + g.ty * 16ll - 1) / (g.ty * 16ll);
+  g.slabs = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min(want, max_slabs), 65535)));
+  g.rows_per_slab = (rows + g.slabs - 1) / g.slabs;
+  g.slabs = static_cast<int>((rows + g.rows_per_slab - 1) / g.rows_per_slab);
+  return g;
+}
+
+// ---- functors for the NHWC column reduce: NS statistics from up to three input streams -------------------
+template <typename T, int VN>
+struct StatsF {  // sum(x - shift), sum((x - shift)^2); shift = first row
+  static constexpr int NS = 2, NIN = 1;
+  const T* x0;
+  long long sstride;  // element stride between the first elements of consecutive channels (1 NHWC, H*W NCHW)
+  T shift[VN];
+  __device__ void init(long long c0) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) shift[e] = x0[(c0 + e) * sstride];
+  }
+  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN]) const {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const T d = a[e] - shift[e];
+      acc[0][e] += d;
+      acc[1][e] += d * d;
+    }
+  }
+};
+template <typename T, int VN>
+struct SumF {  // plain column sum
+  static constexpr int NS = 1, NIN = 1;
+  __device__ void init(long long) {}
+  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN]) const {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[0][e] += a[e];
+  }
+};
+template <typename T, int VN, bool MASK>
+struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
+  static constexpr int NS = 2, NIN = MASK ? 3 : 2;
+  const T* mean;
+  const T* inv;
+  T m[VN], iv[VN];
+  __device__ void init(long long c0) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) { m[e] = mean[c0 + e]; iv[e] = inv[c0 + e]; }
+  }
+  __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN]) const {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const T g = (MASK && !(y[e] > T(0))) ? T(0) : dy[e];
+      acc[0][e] += g;
+      acc[1][e] += g * ((x[e] - m[e]) * iv[e]);
+    }
+  }
+};
+
+// partial layout: [slab][stat][C]
+template <typename T, int VN, typename F>
+__global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict__ in0, const T* __restrict__ in1,
+                                                       const T* __restrict__ in2, T* __restrict__ partial, long long rows,
+                                                       long long C, long long rows_per_slab, int tx_n, int ty_n) {
+  constexpr int NS = F::NS;
+  extern __shared__ unsigned char red_raw[];
+  T* red = reinterpret_cast<T*>(red_raw);  // [ty][NS][tx*VN]
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const long long cv = static_cast<long long>(blockIdx.x) * tx_n + tx;
+  const bool active = cv * VN < C;
+  const long long c0 = cv * VN;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
+  T acc[NS][VN];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[s][e] = T(0);
+  if (active) {
+    f.init(c0);
+    constexpr int U = 4;
+    long long r = r0 + ty;
+    for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+      T a[U][VN], b[U][VN], c[U][VN];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long off = (r + u * ty_n) * C + c0;
+        ldv<T, VN>(in0 + off, a[u]);
+        if (F::NIN >= 2) ldv<T, VN>(in1 + off, b[u]);
+        if (F::NIN >= 3) ldv<T, VN>(in2 + off, c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) f(a[u], b[u], c[u], acc);
+    }
+    for (; r < r1; r += ty_n) {
+      T a[VN], b[VN], c[VN];
+      const long long off = r * C + c0;
+      ldv<T, VN>(in0 + off, a);
+      if (F::NIN >= 2) ldv<T, VN>(in1 + off, b);
+      if (F::NIN >= 3) ldv<T, VN>(in2 + off, c);
+      f(a, b, c, acc);
+    }
+  }
+  const int row_elems = NS * tx_n * VN;
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int e = 0; e < VN; ++e) red[ty * row_elems + s * tx_n * VN + tx * VN + e] = acc[s][e];
+  __syncthreads();
+  // tree over ty
+  for (int half = ty_n >> 1; half > 0; half >>= 1) {
+    if (ty < half) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const int idx = s * tx_n * VN + tx * VN + e;
+          red[ty * row_elems + idx] += red[(ty + half) * row_elems + idx];
+        }
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int e = 0; e < VN; ++e)
+        partial[(static_cast<long long>(blockIdx.y) * NS + s) * C + c0 + e] = red[s * tx_n * VN + tx * VN + e];
+  }
+}
+
+// NCHW: block = (channel, slab of images); threads stride over the H*W plane of each image.
+template <typename T, typename F>
+__global__ void __launch_bounds__(256) col_reduce_nchw(F f, const T* __restrict__ in0, const T* __restrict__ in1,
+                                                       const T* __restrict__ in2, T* __restrict__ partial, long long N,
+                                                       long long C, long long HW, long long imgs_per_slab) {
+  constexpr int NS = F::NS;
+  __shared__ T red[NS][8];
+  const long long c = blockIdx.x;
+  const long long n0 = static_cast<long long>(blockIdx.y) * imgs_per_slab;
+  const long long n1 = (n0 + imgs_per_slab < N) ? n0 + imgs_per_slab : N;
+  T acc[NS][1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s][0] = T(0);
+  f.init(c);
+  for (long long n = n0; n < n1; ++n) {
+    const long long base = (n * C + c) * HW;
+    for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+      T a[1], b[1], d[1];
+      a[0] = in0[base + i];
+      if (F::NIN >= 2) b[0] = in1[base + i];
+      if (F::NIN >= 3) d[0] = in2[base + i];
+      f(a, b, d, acc);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const T v = warp_sum(acc[s][0]);
+    if (lane == 0) red[s][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      T v = T(0);
+      for (int w = 0; w < 8; ++w) v += red[s][w];
+      partial[(static_cast<long long>(blockIdx.y) * NS + s) * C + c] = v;
+    }
+  }
+}
+
+// ---- finalize kernels ---------------------------------------------------------------------------------
+// coef layout in workspace: [0]=mean [1]=inv_std (fwd) ; bwd: [0]=gamma*inv [1]=c1 [2]=c2
+template <typename T>
+__global__ void bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum,
+                                const T* __restrict__ x_first_row, long long shift_stride, T* __restrict__ run_mean,
+                                T* __restrict__ run_var, T* __restrict__ saved_mean, T* __restrict__ saved_inv,
+                                T* __restrict__ coef) {
+  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int i = 0; i < slabs; ++i) {
+    s += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 0) * C + c]);
+    ss += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 1) * C + c]);
+  }
+  const double shift = static_cast<double>(x_first_row[c * shift_stride]);
+  const double dm = s / count;
+  const double mean = shift + dm;
+  double var = ss / count - dm * dm;
+  if (var < 0.0) var = 0.0;
+  const double inv = 1.0 / sqrt(var + kBnEps);
+  if (run_mean) run_mean[c] = static_cast<T>(mean * (1.0 - momentum) + static_cast<double>(run_mean[c]) * momentum);
+  if (run_var) {
+    const double unbiased = var * (count / (count - 1.0));
+    run_var[c] = static_cast<T>(unbiased * (1.0 - momentum) + static_cast<double>(run_var[c]) * momentum);
+  }
+  if (saved_mean) saved_mean[c] = static_cast<T>(mean);
+  if (saved_inv) saved_inv[c] = static_cast<T>(inv);
+  coef[c] = static_cast<T>(mean);
+  coef[C + c] = static_cast<T>(inv);
+}
+
+template <typename T>
+__global__ void bn_infer_coef(const T* __restrict__ mean, const T* __restrict__ var, long long C, T* __restrict__ coef) {
+  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (c >= C) return;
+  coef[c] = mean[c];
+  coef[C + c] = static_cast<T>(1.0 / sqrt(static_cast<double>(var[c]) + kBnEps));
+}
+
+template <typename T>
+__global__ void bn_bwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count,
+                                const T* __restrict__ scale, const T* __restrict__ inv, T* __restrict__ dscale,
+                                T* __restrict__ dbias, T* __restrict__ coef) {
+  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int i = 0; i < slabs; ++i) {
+    s += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 0) * C + c]);
+    sx += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 1) * C + c]);
+  }
+  dbias[c] = static_cast<T>(s);
+  dscale[c] = static_cast<T>(sx);
+  coef[c] = static_cast<T>(static_cast<double>(scale[c]) * static_cast<double>(inv[c]));
+  coef[C + c] = static_cast<T>(s / count);
+  coef[2 * C + c] = static_cast<T>(sx / count);
+}
+
+template <typename T>
+__global__ void sum_finalize(const T* __restrict__ partial, int slabs, long long C, T* __restrict__ out) {
+  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int i = 0; i < slabs; ++i) s += static_cast<double>(partial[static_cast<long long>(i) * C + c]);
+  out[c] = static_cast<T>(s);
+}
+
+// ---- apply kernels ------------------------------------------------------------------------------------
+// forward: y = ((x - mean) * inv) * gamma + beta  [+ res] [relu]
+template <typename T, int VN, bool RELU, bool RES>
+__global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ res,
+                                                     T* __restrict__ y, const T* __restrict__ coef,
+                                                     const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                     long long rows, long long C, long long rows_per_slab, int tx_n,
+                                                     int ty_n) {
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
+  if (c0 >= C) return;
+  T m[VN], iv[VN], g[VN], b[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) { m[e] = coef[c0 + e]; iv[e] = coef[C + c0 + e]; g[e] = gamma[c0 + e]; b[e] = beta[c0 + e]; }
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
+  constexpr int U = 4;
+  long long r = r0 + ty;
+  for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+    T a[U][VN], rr[U][VN];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long off = (r + u * ty_n) * C + c0;
+      ldv<T, VN>(x + off, a[u]);
+      if (RES) ldv<T, VN>(res + off, rr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T o[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        T v = ((a[u][e] - m[e]) * iv[e]) * g[e] + b[e];
+        if (RES) v += rr[u][e];
+        if (RELU) v = v > T(0) ? v : T(0);
+        o[e] = v;
+      }
+      stv<T, VN>(y + (r + u * ty_n) * C + c0, o);
+    }
+  }
+  for (; r < r1; r += ty_n) {
+    T a[VN], rr[VN], o[VN];
+    const long long off = r * C + c0;
+    ldv<T, VN>(x + off, a);
+    if (RES) ldv<T, VN>(res + off, rr);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      T v = ((a[e] - m[e]) * iv[e]) * g[e] + b[e];
+      if (RES) v += rr[e];
+      if (RELU) v = v > T(0) ? v : T(0);
+      o[e] = v;
+    }
+    stv<T, VN>(y + off, o);
+  }
+}
+
+// backward: dx = coef * (dy' - c1 - xhat * c2);  dres = dy'
+template <typename T, int VN, bool MASK, bool DRES>
+__global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x, const T* __restrict__ dy,
+                                                         const T* __restrict__ y, T* __restrict__ dx,
+                                                         T* __restrict__ dres, const T* __restrict__ mean,
+                                                         const T* __restrict__ inv, const T* __restrict__ coef,
+                                                         long long rows, long long C, long long rows_per_slab, int tx_n,
+                                                         int ty_n) {
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
+  if (c0 >= C) return;
+  T m[VN], iv[VN], k0[VN], k1[VN], k2[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    m[e] = mean[c0 + e]; iv[e] = inv[c0 + e];
+    k0[e] = coef[c0 + e]; k1[e] = coef[C + c0 + e]; k2[e] = coef[2 * C + c0 + e];
+  }
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
+  constexpr int U = 2;
+  long long r = r0 + ty;
+  for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+    T a[U][VN], g[U][VN], yy[U][VN];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long off = (r + u * ty_n) * C + c0;
+      ldv<T, VN>(x + off, a[u]);
+      ldv<T, VN>(dy + off, g[u]);
+      if (MASK) ldv<T, VN>(y + off, yy[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T o[VN], gm[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        gm[e] = (MASK && !(yy[u][e] > T(0))) ? T(0) : g[u][e];
+        o[e] = k0[e] * (gm[e] - k1[e] - ((a[u][e] - m[e]) * iv[e]) * k2[e]);
+      }
+      const long long off = (r + u * ty_n) * C + c0;
+      stv<T, VN>(dx + off, o);
+      if (DRES) stv<T, VN>(dres + off, gm);
+    }
+  }
+  for (; r < r1; r += ty_n) {
+    T a[VN], g[VN], yy[VN], o[VN], gm[VN];
+    const long long off = r * C + c0;
+    ldv<T, VN>(x + off, a);
+    ldv<T, VN>(dy + off, g);
+    if (MASK) ldv<T, VN>(y + off, yy);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      gm[e] = (MASK && !(yy[e] > T(0))) ? T(0) : g[e];
+      o[e] = k0[e] * (gm[e] - k1[e] - ((a[e] - m[e]) * iv[e]) * k2[e]);
+    }
+    stv<T, VN>(dx + off, o);
+    if (DRES) stv<T, VN>(dres + off, gm);
+  }
+}
+
+// NCHW apply kernels: one block per (n, c) plane.
+template <typename T, bool RELU, bool RES>
+__global__ void __launch_bounds__(256) bn_apply_nchw(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                     const T* __restrict__ coef, const T* __restrict__ gamma,
+                                                     const T* __restrict__ beta, long long C, long long HW) {
+  const long long plane = blockIdx.x;
+  const long long c = plane % C;
+  const T m = coef[c], iv = coef[C + c], g = gamma[c], b = beta[c];
+  const long long base = plane * HW;
+  for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+    T v = ((x[base + i] - m) * iv) * g + b;
+    if (RES) v += res[base + i];
+    if (RELU) v = v > T(0) ? v : T(0);
+    y[base + i] = v;
+  }
+}
+template <typename T, bool MASK, bool DRES>
+__global__ void __launch_bounds__(256) bn_bwd_apply_nchw(const T* __restrict__ x, const T* __restrict__ dy,
+                                                         const T* __restrict__ y, T* __restrict__ dx, T* __restrict__ dres,
+                                                         const T* __restrict__ mean, const T* __restrict__ inv,
+                                                         const T* __restrict__ coef, long long C, long long HW) {
+  const long long plane = blockIdx.x;
+  const long long c = plane % C;
+  const T m = mean[c], iv = inv[c], k0 = coef[c], k1 = coef[C + c], k2 = coef[2 * C + c];
+  const long long base = plane * HW;
+  for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+    const T gm = (MASK && !(y[base + i] > T(0))) ? T(0) : dy[base + i];
+    dx[base + i] = k0 * (gm - k1 - ((x[base + i] - m) * iv) * k2);
+    if (DRES) dres[base + i] = gm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static inline bool al16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T> constexpr int vec_n() { return 16 / sizeof(T); }
+
+// Runs a column reduce (NHWC or NCHW) into `partial` ([slabs][NS][C]); returns the slab count.
+template <typename T, template <typename, int> class FT, typename Init>
+static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* in0, const T* in1,
+                          const T* in2, T* partial, long long partial_cap_elems, Init init, int* slabs_out) {
+  const long long rows = N * HW;
+  if (layout == ZB_NHWC) {
+    constexpr int VN = vec_n<T>();
+    const bool vec = (C % VN == 0) && al16(in0) && al16(in1) && al16(in2);
+    if (vec) {
+      using F = FT<T, VN>;
+      F f; init(f);
+      ColGeom g = col_geom(ctx, rows, C, VN);
+      ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
+      dim3 grid(g.col_groups, g.slabs);
+      const size_t smem = sizeof(T) * g.ty * F::NS * g.tx * VN;
+      col_reduce_nhwc<T, VN, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, g.rows_per_slab, g.tx, g.ty);
+      ZB_LAUNCH_CHECK(ctx);
+      *slabs_out = g.slabs;
+    } else {
+      using F = FT<T, 1>;
+      F f; init(f);
+      ColGeom g = col_geom(ctx, rows, C, 1);
+      ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
+      dim3 grid(g.col_groups, g.slabs);
+      const size_t smem = sizeof(T) * g.ty * F::NS * g.tx;
+      col_reduce_nhwc<T, 1, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, g.rows_per_slab, g.tx, g.ty);
+      ZB_LAUNCH_CHECK(ctx);
+      *slabs_out = g.slabs;
+    }
+  } else {
+    using F = FT<T, 1>;
+    F f; init(f);
+    ZB_REQUIRE(C <= 2147483647ll, "bn: too many channels");
+    long long slabs = std::max<long long>(1, std::min<long long>(N, (ctx->sm_count * 8ll + C - 1) / C));
+    const long long per = (N + slabs - 1) / slabs;
+    slabs = (N + per - 1) / per;
+    ZB_REQUIRE(slabs * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
+    dim3 grid(static_cast<unsigned>(C), static_cast<unsigned>(slabs));
+    col_reduce_nchw<T, F><<<grid, 256, 0, ctx->stream>>>(f, in0, in1, in2, partial, N, C, HW, per);
+    ZB_LAUNCH_CHECK(ctx);
+    *slabs_out = static_cast<int>(slabs);
+  }
+  return ZB_OK;
+}
+
+template <typename T, int VN> using StatsFT = StatsF<T, VN>;
+template <typename T, int VN> using SumFT = SumF<T, VN>;
+template <typename T, int VN> using BnBwdMaskFT = BnBwdF<T, VN, true>;
+template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, false>;
+
+// Upper bound on the slab count run_col_reduce may pick (sizes the partial buffer).
+static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
+  if (layout == ZB_NHWC) return ctx->sm_count * 8ll;
+  return std::max<long long>(1, std::min<long long>(N, (ctx->sm_count * 8ll + C - 1) / C));
+}
+
+template <typename T, bool RELU, bool RES>
+static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
+                        const T* coef, const T* gamma, const T* beta) {
+  const long long rows = N * HW;
+  if (layout == ZB_NHWC) {
+    constexpr int VN = vec_n<T>();
+    const bool vec = (C % VN == 0) && al16(x) && al16(res) && al16(y);
+    if (vec) {
+      ColGeom g = col_geom(ctx, rows, C, VN);
+      dim3 grid(g.col_groups, g.slabs);
+      bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+    } else {
+      ColGeom g = col_geom(ctx, rows, C, 1);
+      dim3 grid(g.col_groups, g.slabs);
+      bn_apply_nhwc<T, 1, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+    }
+  } else {
+    bn_apply_nchw<T, RELU, RES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, C, HW);
+  }
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+template <typename T>
+static int dispatch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
+                          const T* coef, const T* gamma, const T* beta, int relu) {
+  if (relu && res) return launch_apply<T, true, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+  if (relu) return launch_apply<T, true, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+  if (res) return launch_apply<T, false, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+  return launch_apply<T, false, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+}
+
+template <typename T>
+static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, double momentum,
+                          const T* x, const T* scale, const T* bias, T* run_mean, T* run_var, T* saved_mean,
+                          T* saved_inv, T* y, const T* res, int relu) {
+  ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
+  ZB_REQUIRE(N * H * W < 2147483647ll * 64, "bn: tensor too large");
+  const long long HW = H * W;
+  const long long ms = max_slabs(ctx, layout, N, C);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(T) * (ms * 2 * C + 2 * C), &ws);
+  if (rc != ZB_OK) return rc;
+  T* partial = static_cast<T*>(ws);
+  T* coef = partial + ms * 2 * C;
+  int slabs = 0;
+  rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
+                                  partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
+  if (rc != ZB_OK) return rc;
+  // shift used by the reduce = first row (NHWC: x[c]) or first element of channel c in image 0 (NCHW: x[c*HW])
+  bn_fwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
+                                                               layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
+                                                               saved_inv, coef);
+  ZB_LAUNCH_CHECK(ctx);
+  return dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu);
+}
+
+template <typename T>
+static int bn_fwd_infer_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, const T* x,
+                          const T* scale, const T* bias, const T* mean, const T* var, T* y) {
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(T) * 2 * C, &ws);
+  if (rc != ZB_OK) return rc;
+  T* coef = static_cast<T*>(ws);
+  bn_infer_coef<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(mean, var, C, coef);
+  ZB_LAUNCH_CHECK(ctx);
+  return dispatch_apply<T>(ctx, layout, N, C, H * W, x, static_cast<const T*>(nullptr), y, coef, scale, bias, 0);
+}
+
+template <typename T, bool MASK, bool DRES>
+static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* dy,
+                            const T* y, T* dx, T* dres, const T* mean, const T* inv, const T* coef) {
+  const long long rows = N * HW;
+  if (layout == ZB_NHWC) {
+    constexpr int VN = vec_n<T>();
+    const bool vec = (C % VN == 0) && al16(x) && al16(dy) && al16(y) && al16(dx) && al16(dres);
+    if (vec) {
+      ColGeom g = col_geom(ctx, rows, C, VN);
+      dim3 grid(g.col_groups, g.slabs);
+      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, rows, C, g.rows_per_slab, g.tx, g.ty);
+    } else {
+      ColGeom g = col_geom(ctx, rows, C, 1);
+      dim3 grid(g.col_groups, g.slabs);
+      bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, rows, C, g.rows_per_slab, g.tx, g.ty);
+    }
+  } else {
+    bn_bwd_apply_nchw<T, MASK, DRES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, C, HW);
+  }
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+template <typename T>
+static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, const T* x, const T* dy,
+                    const T* scale, const T* saved_mean, const T* saved_inv, T* dx, T* dscale, T* dbias, const T* y,
+                    T* dres) {
+  ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
+  const long long HW = H * W;
+  const long long ms = max_slabs(ctx, layout, N, C);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(T) * (ms * 2 * C + 5 * C), &ws);
+  if (rc != ZB_OK) return rc;
+  T* partial = static_cast<T*>(ws);
+  T* coef = partial + ms * 2 * C;  // 3*C
+  T* stats = coef + 3 * C;         // 2*C: recomputed mean / inv when not supplied
+  int slabs = 0;
+  const T* mean = saved_mean;
+  const T* inv = saved_inv;
+  if (mean == nullptr || inv == nullptr) {
+    // zenu-matrix/src/nn/batch_norm.rs:355-368: recompute the batch statistics from x
+    rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
+                                    partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
+    if (rc != ZB_OK) return rc;
+    bn_fwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), 0.0, x,
+                                                                 layout == ZB_NHWC ? 1 : HW, static_cast<T*>(nullptr),
+                                                                 static_cast<T*>(nullptr), static_cast<T*>(nullptr),
+                                                                 static_cast<T*>(nullptr), stats);
+    ZB_LAUNCH_CHECK(ctx);
+    if (mean == nullptr) mean = stats;
+    if (inv == nullptr) inv = stats + C;
+  }
+  if (y != nullptr)
+    rc = run_col_reduce<T, BnBwdMaskFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
+                                        [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
+  else
+    rc = run_col_reduce<T, BnBwdNoMaskFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
+                                          [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
+  if (rc != ZB_OK) return rc;
+  bn_bwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), scale, inv,
+                                                               dscale, dbias, coef);
+  ZB_LAUNCH_CHECK(ctx);
+  if (y != nullptr && dres != nullptr) return launch_bwd_apply<T, true, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  if (y != nullptr) return launch_bwd_apply<T, true, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  if (dres != nullptr) return launch_bwd_apply<T, false, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  return launch_bwd_apply<T, false, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+}
+
+// out[c] = sum over (n, hw) of a — conv bias gradient / Matrix::sum(axis 0) on a [rows][cols] matrix (NHWC, HW = 1)
+template <typename T>
+int channel_sum(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* a, T* out) {
+  if (N * C * HW == 0) return ZB_OK;
+  const long long ms = max_slabs(ctx, layout, N, C);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(T) * ms * C, &ws);
+  if (rc != ZB_OK) return rc;
+  T* partial = static_cast<T*>(ws);
+  int slabs = 0;
+  rc = run_col_reduce<T, SumFT>(ctx, layout, N, C, HW, a, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
+                                partial, ms * C, [&](auto&) {}, &slabs);
+  if (rc != ZB_OK) return rc;
+  sum_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, out);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+template int channel_sum<float>(zb_ctx*, int, long long, long long, long long, const float*, float*);
+template int channel_sum<double>(zb_ctx*, int, long long, long long, long long, const double*, double*);
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_bn2d_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, double momentum,
+                      const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
+                      void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu) {
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
+  if (dtype == ZB_F32)
+    return bn_fwd_train_t<float>(ctx, layout, n, c, h, w, momentum, static_cast<const float*>(x), static_cast<const float*>(scale),
+                                 static_cast<const float*>(bias), static_cast<float*>(running_mean), static_cast<float*>(running_var),
+                                 static_cast<float*>(saved_mean), static_cast<float*>(saved_inv_std), static_cast<float*>(y),
+                                 static_cast<const float*>(residual), relu);
+  if (dtype == ZB_F64)
+    return bn_fwd_train_t<double>(ctx, layout, n, c, h, w, momentum, static_cast<const double*>(x), static_cast<const double*>(scale),
+                                  static_cast<const double*>(bias), static_cast<double*>(running_mean), static_cast<double*>(running_var),
+                                  static_cast<double*>(saved_mean), static_cast<double*>(saved_inv_std), static_cast<double*>(y),
+                                  static_cast<const double*>(residual), relu);
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                      const void* scale, const void* bias, const void* mean, const void* var, void* y) {
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
+  if (dtype == ZB_F32)
+    return bn_fwd_infer_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(scale),
+                                 static_cast<const float*>(bias), static_cast<const float*>(mean), static_cast<const float*>(var),
+                                 static_cast<float*>(y));
+  if (dtype == ZB_F64)
+    return bn_fwd_infer_t<double>(ctx, layout, n, c, h, w, static_cast<const double*>(x), static_cast<const double*>(scale),
+                                  static_cast<const double*>(bias), static_cast<const double*>(mean), static_cast<const double*>(var),
+                                  static_cast<double*>(y));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                const void* dy, const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx,
+                void* dscale, void* dbias, const void* y, void* dres) {
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
+  if (dtype == ZB_F32)
+    return bn_bwd_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(dy),
+                           static_cast<const float*>(scale), static_cast<const float*>(saved_mean),
+                           static_cast<const float*>(saved_inv_std), static_cast<float*>(dx), static_cast<float*>(dscale),
+                           static_cast<float*>(dbias), static_cast<const float*>(y), static_cast<float*>(dres));
+  if (dtype == ZB_F64)
+    return bn_bwd_t<double>(ctx, layout, n, c, h, w, static_cast<const double*>(x), static_cast<const double*>(dy),
+                            static_cast<const double*>(scale), static_cast<const double*>(saved_mean),
+                            static_cast<const double*>(saved_inv_std), static_cast<double*>(dx), static_cast<double*>(dscale),
+                            static_cast<double*>(dbias), static_cast<const double*>(y), static_cast<double*>(dres));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_conv2d_bias_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dbias, int64_t n, int64_t k, int64_t h,
+                       int64_t w) {
+  if (dtype == ZB_F32) return channel_sum<float>(ctx, layout, n, k, h * w, static_cast<const float*>(dy), static_cast<float*>(dbias));
+  if (dtype == ZB_F64) return channel_sum<double>(ctx, layout, n, k, h * w, static_cast<const double*>(dy), static_cast<double*>(dbias));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_sum_rows(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t rows, int64_t cols) {
+  if (dtype == ZB_F32) return channel_sum<float>(ctx, ZB_NHWC, rows, cols, 1, static_cast<const float*>(a), static_cast<float*>(out));
+  if (dtype == ZB_F64) return channel_sum<double>(ctx, ZB_NHWC, rows, cols, 1, static_cast<const double*>(a), static_cast<double*>(out));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// common.cuh — context object, status/error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/zenu_b200.h"
+
+namespace zb {
+
+void set_last_error(const char* fmt, ...);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace zb
+
+// The context: one per process/rank, single owner (mirrors the reference's single global
+// ZENU_CUDA_STATE, zenu-cuda/src/lib.rs:18-25, minus the mutex and the library handles).
+struct zb_ctx {
+  int device;
+  int sm_count;
+  int driver_version;
+  cudaStream_t stream;       // compute stream (all kernels of this ctx)
+  cudaStream_t comm_stream;  // NCCL stream
+  bool owns_stream;
+  void* ws;                  // library-owned scratch (split-K partials, BN partial sums, layout staging)
+  size_t ws_bytes;
+  int* err_flag;             // device word: set by a kernel whose mbarrier wait timed out
+  zb::EncodeTiledFn encode_tiled;
+  zb::EncodeIm2colFn encode_im2col;
+  int default_math;          // zb_math_mode
+  // data-parallel state (dp.cu)
+  void* nccl_lib;
+  void* nccl_comm;
+  int rank, world;
+  cudaEvent_t ev_ready, ev_done;  // compute->comm and comm->compute fences
+  unsigned long long launches;  // number of kernels this ctx launched (bench.py's gpu_launches)
+};
+
+namespace zb {
+
+#define ZB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      zb::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ZB_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define ZB_REQUIRE(cond, ...)                \
+  do {                                       \
+    if (!(cond)) {                           \
+      zb::set_last_error(__VA_ARGS__);       \
+      return ZB_ERR_INVALID;                 \
+    }                                        \
+  } while (0)
+
+#define ZB_LAUNCH_CHECK(ctx)                                                                  \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t _e = cudaPeekAtLastError();                                                   \
+    if (_e != cudaSuccess) {                                                                  \
+      zb::set_last_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ZB_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+// Grow-only scratch; stream-ordered so earlier kernels that still read the old block stay valid.
+int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out);
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace zb

@@ -1,0 +1,129 @@
+// ctx.cu — context lifecycle, scratch arena, error reporting.
+// Replaces the reference's process-global ZenuCudaState (zenu-cuda/src/lib.rs:18-112) and its
+// cudaMallocAsync+synchronize allocation path (zenu-cuda/src/runtime/mod.rs:30-60).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace zb {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->ws_bytes) {
+    // stream-ordered: kernels already enqueued keep using the old block until they retire
+    if (ctx->ws) ZB_CHECK_CUDA(cudaFreeAsync(ctx->ws, ctx->stream));
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    size_t want = bytes + (bytes >> 2);
+    want = (want + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    ZB_CHECK_CUDA(cudaMallocAsync(&ctx->ws, want, ctx->stream));
+    ctx->ws_bytes = want;
+  }
+  *out = ctx->ws;
+  return ZB_OK;
+}
+
+}  // namespace zb
+
+extern "C" {
+
+const char* zb_last_error(void) { return zb::g_last_error; }
+const char* zb_version(void) { return "zenu_b200 0.1 (sm_100a; tcgen05 kind::tf32 + FFMA/DFMA)"; }
+
+int64_t zb_conv_out_size(int64_t in, int64_t k, int64_t pad, int64_t stride, int64_t dil) {
+  // reference: zenu-matrix/src/nn/conv/utils.rs:52-60
+  return ((in + 2 * pad - dil * (k - 1) - 1) / stride) + 1;
+}
+
+int zb_ctx_create(zb_ctx** out, int device, void* stream) {
+  ZB_REQUIRE(out != nullptr, "zb_ctx_create: out is NULL");
+  ZB_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ZB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    zb::set_last_error("zenu_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return ZB_ERR_UNSUPPORTED;
+  }
+  zb_ctx* ctx = new zb_ctx();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ZB_CHECK_CUDA(cudaDriverGetVersion(&ctx->driver_version));
+  if (stream) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->owns_stream = false;
+  } else {
+    ZB_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->owns_stream = true;
+  }
+  ZB_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  ZB_CHECK_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
+  ZB_CHECK_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+  // Driver entry points for tensor-map encoding, resolved at run time so the library does not link libcuda.
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  ZB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  ZB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+  ctx->encode_tiled = reinterpret_cast<zb::EncodeTiledFn>(fn);
+  fn = nullptr;
+  ZB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  ZB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available in this driver");
+  ctx->encode_im2col = reinterpret_cast<zb::EncodeIm2colFn>(fn);
+  ctx->default_math = ZB_MATH_TF32;
+  ctx->rank = 0;
+  ctx->world = 1;
+  *out = ctx;
+  return ZB_OK;
+}
+
+int zb_ctx_destroy(zb_ctx* ctx) {
+  if (!ctx) return ZB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->comm_stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->err_flag) cudaFree(ctx->err_flag);
+  cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ZB_OK;
+}
+
+int zb_ctx_synchronize(zb_ctx* ctx) {
+  ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ZB_OK;
+}
+
+int zb_ctx_set_math(zb_ctx* ctx, int math_mode) {
+  ZB_REQUIRE(math_mode == ZB_MATH_TF32 || math_mode == ZB_MATH_FP32, "unknown math mode %d", math_mode);
+  ctx->default_math = math_mode;
+  return ZB_OK;
+}
+
+void* zb_ctx_stream(zb_ctx* ctx) { return ctx->stream; }
+
+int zb_ctx_check(zb_ctx* ctx) {
+  ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  int flag = 0;
+  ZB_CHECK_CUDA(cudaMemcpy(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag != 0) {
+    cudaMemset(ctx->err_flag, 0, sizeof(int));
+    zb::set_last_error("device-side barrier wait timed out (tcgen05 pipeline protocol error)");
+    return ZB_ERR_TIMEOUT;
+  }
+  return ZB_OK;
+}
+
+unsigned long long zb_ctx_launch_count(zb_ctx* ctx) { return ctx->launches; }
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// dp.cu — data-parallel gradient exchange: NCCL sum-allreduce over NVLink 5 / NVSwitch on a dedicated
+// communication stream, fenced against the compute stream with events so that a bucket's allreduce overlaps
+// the backward kernels that follow it.  New relative to the reference, which is single-GPU only
+// (hook site = top of Optimizer::update, zenu-optimizer/src/sgd.rs:20-30).
+// NCCL is resolved with dlopen at run time (the library already loaded by the host process wins, e.g. the
+// copy bundled with PyTorch), so the C ABI itself has no link-time NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace zb {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return ZB_OK;
+  const char* cands[] = {getenv("ZENU_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* c : cands) {
+    if (!c) continue;
+    h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    set_last_error("cannot dlopen libnccl (set ZENU_B200_NCCL_LIB): %s", dlerror());
+    return ZB_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    set_last_error("libnccl is missing required symbols");
+    return ZB_ERR_NCCL;
+  }
+  g_nccl.lib = h;
+  return ZB_OK;
+}
+
+#define ZB_CHECK_NCCL(expr)                                                                         \
+  do {                                                                                              \
+    ncclResult_t _r = (expr);                                                                       \
+    if (_r != ncclSuccess) {                                                                        \
+      zb::set_last_error("%s failed: %s", #expr, zb::g_nccl.GetErrorString ? zb::g_nccl.GetErrorString(_r) : "?"); \
+      return ZB_ERR_NCCL;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_dp_unique_id(zb_ctx* ctx, void* host_id128) {
+  (void)ctx;
+  int rc = load_nccl();
+  if (rc != ZB_OK) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  ZB_CHECK_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(host_id128, &id, sizeof(id));
+  return ZB_OK;
+}
+
+int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world) {
+  ZB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "zb_dp_init: bad rank/world %d/%d", rank, world);
+  ctx->rank = rank;
+  ctx->world = world;
+  if (!ctx->ev_ready) {
+    ZB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    ZB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+  }
+  if (world == 1) return ZB_OK;
+  int rc = load_nccl();
+  if (rc != ZB_OK) return rc;
+  ncclUniqueId id;
+  memcpy(&id, host_id128, sizeof(id));
+  ncclComm_t comm;
+  ZB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ZB_CHECK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+  ctx->nccl_comm = comm;
+  return ZB_OK;
+}
+
+int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n) {
+  if (ctx->world <= 1 || n == 0) return ZB_OK;
+  ZB_REQUIRE(ctx->nccl_comm != nullptr, "zb_dp_allreduce_sum: zb_dp_init was not called");
+  ZB_CHECK_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
+  ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
+  ZB_CHECK_NCCL(g_nccl.AllReduce(buf, buf, static_cast<size_t>(n), dtype == ZB_F64 ? ncclFloat64 : ncclFloat32, ncclSum,
+                                 static_cast<ncclComm_t>(ctx->nccl_comm), ctx->comm_stream));
+  ZB_CHECK_CUDA(cudaEventRecord(ctx->ev_done, ctx->comm_stream));
+  return ZB_OK;
+}
+
+int zb_dp_wait(zb_ctx* ctx) {
+  if (ctx->world <= 1 || !ctx->ev_done) return ZB_OK;
+  ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_done, 0));
+  return ZB_OK;
+}
+
+int zb_dp_rank(zb_ctx* ctx) { return ctx->rank; }
+int zb_dp_world(zb_ctx* ctx) { return ctx->world; }
+
+}  // extern "C"

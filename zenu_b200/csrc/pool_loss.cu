@@ -1,0 +1,244 @@
+// pool_loss.cu — "next" rows of the scope table: max-pool, global average pool and the
+// fused softmax + cross-entropy loss head, so a ResNet training step closes on the device.
+//   max-pool: semantics of the reference CPU path (zenu-matrix/src/nn/pool2d.rs:77-150): padding contributes
+//             zeros to the max, the first maximum in (kh, kw) order receives the gradient.
+//   softmax_xent: zenu-autograd/src/loss/cross_entropy.rs:12-23 (+ softmax.rs / operation/softmax.rs),
+//             forward and backward in one pass over the logits.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace zb {
+
+struct PoolGeom {
+  long long N, C, H, W, P, Q;
+  int kh, kw, sh, sw, ph, pw;
+  long long sn, sc, s_h, s_w;      // input strides (elements)
+  long long on, oc, o_h, o_w;      // output strides
+  int nhwc;
+};
+
+__device__ __forceinline__ void pool_decode(const PoolGeom& g, long long i, long long& n, long long& c, long long& p,
+                                            long long& q) {
+  if (g.nhwc) { c = i % g.C; i /= g.C; q = i % g.Q; i /= g.Q; p = i % g.P; n = i / g.P; }
+  else { q = i % g.Q; i /= g.Q; p = i % g.P; i /= g.P; c = i % g.C; n = i / g.C; }
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolGeom g, const T* __restrict__ x, T* __restrict__ y,
+                                                      const T* __restrict__ dy, T* __restrict__ dx) {
+  const long long total = g.N * g.C * g.P * g.Q;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long n, c, p, q;
+    pool_decode(g, i, n, c, p, q);
+    const T* xb = x + n * g.sn + c * g.sc;
+    T best = T(0);
+    long long best_off = -1;
+    bool first = true;
+    for (int r = 0; r < g.kh; ++r) {
+      const long long ih = p * g.sh + r - g.ph;
+      for (int s = 0; s < g.kw; ++s) {
+        const long long iw = q * g.sw + s - g.pw;
+        const bool oob = ih < 0 || ih >= g.H || iw < 0 || iw >= g.W;
+        const T v = oob ? T(0) : xb[ih * g.s_h + iw * g.s_w];
+        if (first || v > best) {
+          best = v;
+          best_off = oob ? -1 : (ih * g.s_h + iw * g.s_w);
+          first = false;
+        }
+      }
+    }
+    const long long o = n * g.on + c * g.oc + p * g.o_h + q * g.o_w;
+    if (!BWD) {
+      y[o] = best;
+    } else if (best_off >= 0) {
+      atomicAdd(dx + n * g.sn + c * g.sc + best_off, dy[o]);
+    }
+  }
+}
+
+static PoolGeom pool_geom(int layout, long long n, long long c, long long h, long long w, long long kh, long long kw,
+                          long long sh, long long sw, long long ph, long long pw) {
+  PoolGeom g;
+  g.N = n; g.C = c; g.H = h; g.W = w;
+  g.P = (h + 2 * ph - kh) / sh + 1;
+  g.Q = (w + 2 * pw - kw) / sw + 1;
+  g.kh = static_cast<int>(kh); g.kw = static_cast<int>(kw); g.sh = static_cast<int>(sh); g.sw = static_cast<int>(sw);
+  g.ph = static_cast<int>(ph); g.pw = static_cast<int>(pw);
+  g.nhwc = (layout == ZB_NHWC);
+  if (g.nhwc) {
+    g.sn = h * w * c; g.sc = 1; g.s_h = w * c; g.s_w = c;
+    g.on = g.P * g.Q * c; g.oc = 1; g.o_h = g.Q * c; g.o_w = c;
+  } else {
+    g.sn = c * h * w; g.sc = h * w; g.s_h = w; g.s_w = 1;
+    g.on = c * g.P * g.Q; g.oc = g.P * g.Q; g.o_h = g.Q; g.o_w = 1;
+  }
+  return g;
+}
+
+template <typename T>
+static int maxpool_fwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, T* y) {
+  const long long total = g.N * g.C * g.P * g.Q;
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  maxpool_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<const T*>(nullptr), static_cast<T*>(nullptr));
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+template <typename T>
+static int maxpool_bwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, const T* dy, T* dx) {
+  const long long total = g.N * g.C * g.P * g.Q;
+  ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(T) * g.N * g.C * g.H * g.W, ctx->stream));
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  maxpool_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(g, x, static_cast<T*>(nullptr), dy, dx);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+// ---- global average pool: x [N][HW][C] (NHWC) or [N][C][HW] (NCHW) -> y [N][C] ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long N, long long C,
+                                                      long long HW, int nhwc) {
+  const long long total = N * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / C, c = i - n * C;
+    T s = T(0);
+    if (nhwc) {
+      const T* p = x + n * HW * C + c;
+      for (long long j = 0; j < HW; ++j) s += p[j * C];
+    } else {
+      const T* p = x + i * HW;
+      for (long long j = 0; j < HW; ++j) s += p[j];
+    }
+    y[i] = s / static_cast<T>(HW);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long long N, long long C,
+                                                      long long HW, int nhwc) {
+  const long long total = N * C * HW;
+  const T inv = T(1) / static_cast<T>(HW);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long n, c;
+    if (nhwc) { c = i % C; n = i / (C * HW); } else { const long long nc = i / HW; c = nc % C; n = nc / C; }
+    dx[i] = dy[n * C + c] / static_cast<T>(HW);
+    (void)inv;
+  }
+}
+
+// ---- softmax + cross entropy ------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T block_reduce(T v, T* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? (other > v ? other : v) : v + other;
+  }
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  T r = sh[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = is_max ? (sh[w] > r ? sh[w] : r) : r + sh[w];
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_xent_rows(const T* __restrict__ z, const T* __restrict__ t, T* __restrict__ row_loss,
+                                                         T* __restrict__ dz, long long B, long long K) {
+  __shared__ T sh[8];
+  const long long b = blockIdx.x;
+  const T* zb_ = z + b * K;
+  const T* tb = t + b * K;
+  T mx = -INFINITY;
+  for (long long j = threadIdx.x; j < K; j += blockDim.x) mx = zb_[j] > mx ? zb_[j] : mx;
+  mx = block_reduce<T>(mx, sh, true);
+  T se = T(0), ts = T(0);
+  for (long long j = threadIdx.x; j < K; j += blockDim.x) { se += exp(zb_[j] - mx); ts += tb[j]; }
+  se = block_reduce<T>(se, sh, false);
+  ts = block_reduce<T>(ts, sh, false);
+  T l = T(0);
+  for (long long j = threadIdx.x; j < K; j += blockDim.x) {
+    const T p = exp(zb_[j] - mx) / se;
+    if (tb[j] != T(0)) l += tb[j] * log(p);
+    if (dz) dz[b * K + j] = (p * ts - tb[j]) / static_cast<T>(B);
+  }
+  l = block_reduce<T>(l, sh, false);
+  if (threadIdx.x == 0) row_loss[b] = l;
+}
+template <typename T>
+__global__ void loss_finalize(const T* __restrict__ row_loss, T* __restrict__ loss, long long B) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    T s = T(0);
+    for (long long b = 0; b < B; ++b) s += row_loss[b];
+    *loss = -s / static_cast<T>(B);
+  }
+}
+
+template <typename T>
+static int softmax_xent_t(zb_ctx* ctx, const T* z, const T* t, T* loss, T* dz, long long B, long long K) {
+  ZB_REQUIRE(B > 0 && K > 0 && B <= 2147483647ll, "softmax_xent: bad shape");
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(T) * B, &ws);
+  if (rc != ZB_OK) return rc;
+  softmax_xent_rows<T><<<static_cast<unsigned>(B), 256, 0, ctx->stream>>>(z, t, static_cast<T*>(ws), dz, B, K);
+  ZB_LAUNCH_CHECK(ctx);
+  loss_finalize<T><<<1, 32, 0, ctx->stream>>>(static_cast<const T*>(ws), loss, B);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+extern "C" {
+
+int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t h, int64_t w,
+                     int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (dtype == ZB_F32) return maxpool_fwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<float*>(y));
+  if (dtype == ZB_F64) return maxpool_fwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<double*>(y));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const void* dy, void* dx, int64_t n, int64_t c,
+                     int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (dtype == ZB_F32) return maxpool_bwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx));
+  if (dtype == ZB_F64) return maxpool_bwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<const double*>(dy), static_cast<double*>(dx));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t hw) {
+  const long long total = n * c;
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  if (dtype == ZB_F32) gap_fwd_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(x), static_cast<float*>(y), n, c, hw, layout == ZB_NHWC);
+  else if (dtype == ZB_F64) gap_fwd_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(x), static_cast<double*>(y), n, c, hw, layout == ZB_NHWC);
+  else { zb::set_last_error("unknown dtype %d", dtype); return ZB_ERR_INVALID; }
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int64_t n, int64_t c, int64_t hw) {
+  const long long total = n * c * hw;
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  if (dtype == ZB_F32) gap_bwd_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(dy), static_cast<float*>(dx), n, c, hw, layout == ZB_NHWC);
+  else if (dtype == ZB_F64) gap_bwd_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(dy), static_cast<double*>(dx), n, c, hw, layout == ZB_NHWC);
+  else { zb::set_last_error("unknown dtype %d", dtype); return ZB_ERR_INVALID; }
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+int zb_softmax_xent(zb_ctx* ctx, int dtype, const void* z, const void* t, void* loss, void* dz, int64_t batch, int64_t classes) {
+  if (dtype == ZB_F32) return softmax_xent_t<float>(ctx, static_cast<const float*>(z), static_cast<const float*>(t), static_cast<float*>(loss), static_cast<float*>(dz), batch, classes);
+  if (dtype == ZB_F64) return softmax_xent_t<double>(ctx, static_cast<const double*>(z), static_cast<const double*>(t), static_cast<double*>(loss), static_cast<double*>(dz), batch, classes);
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+}  // extern "C"

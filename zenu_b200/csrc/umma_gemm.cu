@@ -1,0 +1,772 @@
+// umma_gemm.cu — the tensor-core hot path: one persistent, warp-specialised tcgen05 kernel that serves
+//   * Linear / generic row-major GEMM (all four transpose combinations),
+//   * Conv2d fprop / dgrad as implicit GEMM (TMA im2col loads of NHWC activations),
+//   * Conv2d wgrad as implicit GEMM with the pixel dimension as the reduction (MN-major operands, split-K),
+// plus the host-side planners that turn a conv/GEMM request into tensor maps + UmmaParams.
+//
+// Replaces: cuDNN-frontend conv graphs (reference conv.cpp:29-187 via graph_conv.rs:40-268) and
+// cublas{S}gemm_v2_64 (zenu-cuda/src/cublas/mod.rs:84-160).  f32 operands are consumed as TF32
+// (kind::tf32, fp32 accumulation in TMEM).
+//
+// Kernel anatomy (192 threads, 1 CTA / SM, grid = min(tiles, SMs), static round-robin tile schedule):
+//   warp 0   : TMA producer   — one elected lane fills a STAGES-deep smem ring (A 128x32, B BNx32 fp32, SWIZZLE_128B)
+//   warp 1   : MMA issuer     — one elected lane issues 4 x tcgen05.mma (K = 8 each) per stage into a
+//                               double-buffered TMEM accumulator (2 x BN columns); also owns TMEM alloc/dealloc
+//   warps 2-5: epilogue       — tcgen05.ld 32x32b.x32 -> registers -> alpha/bias/beta -> 128-bit global stores
+// Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty (MMA <-> epilogue).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "umma_gemm.cuh"
+
+namespace zb {
+
+using namespace ptx;
+
+template <int BN, int STAGES>
+struct UmmaSmem {
+  static constexpr int A_BYTES = kUmmaBM * kUmmaBK * 4;  // 16 KB
+  static constexpr int B_BYTES = BN * kUmmaBK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, tap, split;
+};
+__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
+  TileCoord t;
+  t.n_blk = tile % p.n_tiles;
+  tile /= p.n_tiles;
+  t.tap = tile % p.tap_tiles;
+  tile /= p.tap_tiles;
+  t.m_blk = tile % p.m_tiles;
+  t.split = tile / p.m_tiles;
+  return t;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ UmmaParams p) {
+  using L = UmmaSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  volatile int* err = p.err_flag;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      prefetch_tensormap(&tmA);
+      prefetch_tensormap(&tmB);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull_bar[s], 1);
+        mbar_init(&tempty_bar[s], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
+  const bool a_mn = (p.a_mode == A_TILED_MN);
+  const bool b_mn = (p.b_mode != B_TILED_K);
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int pq = p.conv_P * p.conv_Q;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
+        const int kb_begin = tc.split * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        int a_w = 0, a_h = 0, a_n = 0;
+        if (p.a_mode == A_IM2COL_K) {
+          const int img = m0 / pq, rem = m0 - img * pq;
+          const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+          a_w = p.lower_w + qq * p.stride_w;
+          a_h = p.lower_h + pp * p.stride_h;
+          a_n = img;
+        }
+        const int a_boxes = a_mn ? min(4, (p.M - m0 + 31) / 32) : 0;
+        const int b_boxes = b_mn ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
+        const uint32_t bytes = (a_mn ? a_boxes * 4096u : uint32_t(L::A_BYTES)) + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
+        bool ok = true;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1, err)) { ok = false; break; }
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          uint8_t* sA = smem + stage * L::STAGE_BYTES;
+          uint8_t* sB = sA + L::A_BYTES;
+          // ---- A operand
+          if (p.a_mode == A_TILED_K) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * kUmmaBK, m0);
+          } else if (p.a_mode == A_IM2COL_K) {
+            const int tap = kb / p.c_chunks, c0 = (kb - tap * p.c_chunks) * kUmmaBK;
+            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
+          } else {
+            for (int j = 0; j < a_boxes; ++j) tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, kb * kUmmaBK);
+          }
+          // ---- B operand
+          if (p.b_mode == B_TILED_K) {
+            int k0 = kb * kUmmaBK;
+            if (p.a_mode == A_IM2COL_K) {
+              const int tap = kb / p.c_chunks;
+              k0 = tap * p.b_tap_stride + (kb - tap * p.c_chunks) * kUmmaBK;
+            }
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          } else if (p.b_mode == B_TILED_MN) {
+            for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK);
+          } else {  // B_IM2COL_MN: K index = base pixel, N index = channel
+            const int pix = kb * kUmmaBK;
+            const int img = pix / pq, rem = pix - img * pq;
+            const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+            const int bw = p.lower_w + qq * p.stride_w, bh = p.lower_h + pp * p.stride_h;
+            for (int j = 0; j < b_boxes; ++j)
+              tma_load_im2col_4d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, bw, bh, img, p.tap_w[tc.tap], p.tap_h[tc.tap]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int kb_begin = tc.split * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        bool ok = true;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kUmmaBK / 8; ++k) {
+            const uint64_t da = a_mn ? make_smem_desc_sw128(a_base + k * 1024, 4096, 1024)
+                                     : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t db = b_mn ? make_smem_desc_sw128(b_base + k * 1024, 4096, 1024)
+                                     : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_tf32(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const bool partial = p.splits > 1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
+      if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      long long orow = row;
+      if (p.out_mode == OUT_SCATTER && row_ok) {
+        const int pq = p.conv_P * p.conv_Q;
+        const int img = row / pq, rem = row - img * pq;
+        const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+        orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
+      }
+      float* drow = p.D + static_cast<long long>(tc.split) * p.split_stride + orow * p.ldd + tc.tap * p.tap_col_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = drow + col0;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(r[v * 4 + e]);
+            const int col = col0 + v * 4;
+            if (!partial) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float val = p.alpha * o[e];
+                if (p.bias != nullptr && col + e < p.N) val += __ldg(p.bias + col + e);
+                o[e] = val;
+              }
+            }
+            if (vec_ok && col + 3 < p.N) {
+              if (!partial && p.beta != 0.f) {
+                const float4 old = *reinterpret_cast<const float4*>(dst + v * 4);
+                o[0] += p.beta * old.x; o[1] += p.beta * old.y; o[2] += p.beta * old.z; o[3] += p.beta * old.w;
+              }
+              *reinterpret_cast<float4*>(dst + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + e < p.N) {
+                  float val = o[e];
+                  if (!partial && p.beta != 0.f) val += p.beta * dst[v * 4 + e];
+                  dst[v * 4 + e] = val;
+                }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+// out[i] = alpha * sum_s partial[s][i] + bias[col] + beta * out[i]   (deterministic split-K reduction)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long rows,
+                                     long long cols, long long ldo, long long split_stride, int splits, float alpha,
+                                     float beta, const float* __restrict__ bias) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[s * split_stride + i];
+    const long long r = i / cols, c = i - r * cols;
+    float v = alpha * acc;
+    if (bias) v += bias[c];
+    if (beta != 0.f) v += beta * out[r * ldo + c];
+    out[r * ldo + c] = v;
+  }
+}
+
+// Wt[c][t][k] = W[k][taps[t]][c]  (KRSC source); used by dgrad so that the filter is K-major for the GEMM.
+struct TapList {
+  int rs[kUmmaMaxTaps];  // r*S+s of each tap, in GEMM-K order
+};
+__global__ void dgrad_filter_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int RS, int C, int ntaps,
+                                    const TapList taps) {
+  const long long total = static_cast<long long>(C) * ntaps * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const long long r = i / K;
+    const int t = static_cast<int>(r % ntaps), c = static_cast<int>(r / ntaps);
+    wt[i] = w[(static_cast<long long>(k) * RS + taps.rs[t]) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static CUtensorMapDataType operand_dtype() {
+  // TFLOAT32 makes the TMA unit round fp32 -> tf32 while loading (instead of the MMA truncating the low 13
+  // mantissa bits); ZENU_B200_TMA_F32=1 selects raw FLOAT32 loads for A/B comparison of the two behaviours.
+  static int raw = -1;
+  if (raw < 0) {
+    const char* e = getenv("ZENU_B200_TMA_F32");
+    raw = (e && e[0] == '1') ? 1 : 0;
+  }
+  return raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+}
+
+// 2-D row-major matrix [outer][inner], box (box_inner <= 32 fp32 = 128 B swizzle span, box_outer <= 256).
+static int make_map_2d(zb_ctx* ctx, CUtensorMap* map, const float* base, long long inner, long long outer,
+                       long long pitch_elems, int box_inner, int box_outer) {
+  ZB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
+  ZB_REQUIRE((pitch_elems * 4) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (got %lld elems)", pitch_elems);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode_tiled(map, operand_dtype(), 2, const_cast<float*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d", int(r), inner, outer,
+                   pitch_elems, box_inner, box_outer);
+    return ZB_ERR_CUDA;
+  }
+  return ZB_OK;
+}
+
+// NHWC activation tensor seen as (C, W, H, N) for im2col loads: `pixels` base pixels x 32 channels per load.
+static int make_map_im2col(zb_ctx* ctx, CUtensorMap* map, const float* base, long long N, long long H, long long W,
+                           long long C, int lower_w, int lower_h, int upper_w, int upper_h, int stride_w, int stride_h,
+                           int pixels) {
+  ZB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
+  ZB_REQUIRE(C % 4 == 0, "im2col TMA needs C %% 4 == 0 (got %lld)", C);
+  ZB_REQUIRE(lower_w >= -128 && lower_w <= 127 && lower_h >= -128 && lower_h <= 127 && upper_w >= -128 &&
+                 upper_w <= 127 && upper_h >= -128 && upper_h <= 127,
+             "im2col corner out of the 8-bit range");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
+                           static_cast<cuuint64_t>(H) * W * C * 4};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
+  CUresult r = ctx->encode_im2col(map, operand_dtype(), 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                  /*channelsPerPixel=*/32, /*pixelsPerColumn=*/static_cast<cuuint32_t>(pixels), estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeIm2col failed (%d): NHWC=%lldx%lldx%lldx%lld lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)",
+                   int(r), N, H, W, C, lower_w, lower_h, upper_w, upper_h, stride_w, stride_h);
+    return ZB_ERR_CUDA;
+  }
+  // Same small-tensor driver workaround CUTLASS applies (copy_traits_sm90_im2col.hpp): for drivers <= 13.1 and
+  // tensors under 128 KiB, bit 21 of the second descriptor word must be cleared.
+  if (ctx->driver_version <= 13010 && N * H * W * C * 4 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return ZB_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
+  using L = UmmaSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
+  const int grid = std::min(tiles, ctx->sm_count);
+  umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+static int pick_bn(long long n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
+
+static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
+  switch (bn) {
+    case 64: return launch_cfg<64, 8>(ctx, a, b, p);
+    case 128: return launch_cfg<128, 6>(ctx, a, b, p);
+    default: return launch_cfg<256, 4>(ctx, a, b, p);
+  }
+}
+
+// Chooses a split-K factor so that a problem with few output tiles still fills the SMs.
+static int pick_splits(zb_ctx* ctx, long long tiles, int kb_total, int min_kb_per_split) {
+  if (tiles >= ctx->sm_count || kb_total < 2 * min_kb_per_split) return 1;
+  long long want = (2ll * ctx->sm_count + tiles - 1) / tiles;  // ~2 waves
+  long long cap = kb_total / min_kb_per_split;
+  long long s = std::max(1ll, std::min(want, cap));
+  return static_cast<int>(std::min<long long>(s, 64));
+}
+
+static void finish_split_fields(UmmaParams& p, int splits) {
+  p.splits = splits;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+}
+
+static int run_with_splits(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, UmmaParams p, long long rows,
+                           long long cols, float* out, long long ldo, float alpha, float beta, const float* bias) {
+  if (p.splits <= 1) {
+    p.split_stride = 0;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.bias = bias;
+    return umma_launch(ctx, bn, a, b, p);
+  }
+  // partial buffers: [splits][rows][cols] dense
+  void* ws = nullptr;
+  const size_t need = sizeof(float) * static_cast<size_t>(p.splits) * rows * cols;
+  int rc = ctx_workspace(ctx, need, &ws);
+  if (rc != ZB_OK) return rc;
+  UmmaParams q = p;
+  q.D = static_cast<float*>(ws);
+  q.ldd = cols;
+  q.split_stride = rows * cols;
+  q.alpha = 1.f;
+  q.beta = 0.f;
+  q.bias = nullptr;
+  rc = umma_launch(ctx, bn, a, b, q);
+  if (rc != ZB_OK) return rc;
+  const long long total = rows * cols;
+  const int block = 256;
+  const int grid = static_cast<int>(std::min<long long>((total + block - 1) / block, ctx->sm_count * 8ll));
+  splitk_reduce_kernel<<<grid, block, 0, ctx->stream>>>(static_cast<const float*>(ws), out, rows, cols, ldo, rows * cols,
+                                                        q.splits, alpha, beta, bias);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+static void init_params(UmmaParams& p, zb_ctx* ctx) {
+  memset(&p, 0, sizeof(p));
+  p.tap_tiles = 1;
+  p.splits = 1;
+  p.ntaps = 1;
+  p.c_chunks = 1;
+  p.conv_P = p.conv_Q = 1;
+  p.stride_w = p.stride_h = 1;
+  p.alpha = 1.f;
+  p.err_flag = ctx->err_flag;
+}
+
+// ---------------------------------------------------------------------------------------------- GEMM
+// Row-major C[m,n] = alpha * op(A) * op(B) + beta * C (+ bias[n]).  Returns ZB_ERR_UNSUPPORTED when the operands
+// do not meet TMA alignment rules (caller then uses the SIMT kernel).
+int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n, long long k, float alpha,
+              const float* a, long long lda, const float* b, long long ldb, float beta, float* c, long long ldc,
+              const float* bias) {
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) ||
+      m <= 0 || n <= 0 || k <= 0 || m > 0x7fffffffll || n > 0x7fffffffll || k > 0x7fffffffll) {
+    set_last_error("umma_gemm: operands not TMA-compatible");
+    return ZB_ERR_UNSUPPORTED;
+  }
+  const int bn = pick_bn(n);
+  CUtensorMap ma, mb;
+  int rc;
+  UmmaParams p;
+  init_params(p, ctx);
+  if (!trans_a) {  // A stored [m][k]
+    rc = make_map_2d(ctx, &ma, a, k, m, lda, 32, kUmmaBM);
+    p.a_mode = A_TILED_K;
+  } else {  // A stored [k][m]
+    rc = make_map_2d(ctx, &ma, a, m, k, lda, 32, kUmmaBK);
+    p.a_mode = A_TILED_MN;
+  }
+  if (rc != ZB_OK) return rc;
+  if (trans_b) {  // B stored [n][k]
+    rc = make_map_2d(ctx, &mb, b, k, n, ldb, 32, bn);
+    p.b_mode = B_TILED_K;
+  } else {  // B stored [k][n]
+    rc = make_map_2d(ctx, &mb, b, n, k, ldb, 32, kUmmaBK);
+    p.b_mode = B_TILED_MN;
+  }
+  if (rc != ZB_OK) return rc;
+  p.M = static_cast<int>(m);
+  p.N = static_cast<int>(n);
+  p.m_tiles = ceil_div(m, kUmmaBM);
+  p.n_tiles = ceil_div(n, bn);
+  p.kb_total = ceil_div(k, kUmmaBK);
+  p.out_mode = OUT_ROWS;
+  p.D = c;
+  p.ldd = ldc;
+  finish_split_fields(p, pick_splits(ctx, static_cast<long long>(p.m_tiles) * p.n_tiles, p.kb_total, 8));
+  return run_with_splits(ctx, bn, ma, mb, p, m, n, c, ldc, alpha, beta, bias);
+}
+
+// ---------------------------------------------------------------------------------------------- conv
+bool umma_conv_supported(const zb_conv2d_desc* d) {
+  if (d->c % 32 != 0 || d->k % 4 != 0) return false;
+  if (d->kh * d->kw > kUmmaMaxTaps) return false;
+  if (d->dil_h * (d->kh - 1) > 255 || d->dil_w * (d->kw - 1) > 255) return false;
+  if (d->pad_h > 127 || d->pad_w > 127) return false;
+  return true;
+}
+
+// y[N,P,Q,K] = conv(x[N,H,W,C], w[K,R,S,C]) (+bias)
+int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias,
+                         float* y) {
+  if (!umma_conv_supported(d)) { set_last_error("umma fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
+  const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  const long long M = d->n * P * Q;
+  const int bn = pick_bn(d->k);
+  const int taps = static_cast<int>(d->kh * d->kw);
+  CUtensorMap ma, mb;
+  UmmaParams p;
+  init_params(p, ctx);
+  int rc;
+  const bool pointwise = (taps == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0);
+  if (pointwise) {
+    rc = make_map_2d(ctx, &ma, x, d->c, M, d->c, 32, kUmmaBM);
+    p.a_mode = A_TILED_K;
+  } else {
+    rc = make_map_im2col(ctx, &ma, x, d->n, d->h, d->w, d->c, -static_cast<int>(d->pad_w), -static_cast<int>(d->pad_h),
+                         static_cast<int>(d->pad_w - d->dil_w * (d->kw - 1)), static_cast<int>(d->pad_h - d->dil_h * (d->kh - 1)),
+                         static_cast<int>(d->stride_w), static_cast<int>(d->stride_h), kUmmaBM);
+    p.a_mode = A_IM2COL_K;
+  }
+  if (rc != ZB_OK) return rc;
+  rc = make_map_2d(ctx, &mb, w, static_cast<long long>(taps) * d->c, d->k, static_cast<long long>(taps) * d->c, 32, bn);
+  if (rc != ZB_OK) return rc;
+  p.b_mode = B_TILED_K;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(d->k);
+  p.m_tiles = ceil_div(M, kUmmaBM);
+  p.n_tiles = ceil_div(d->k, bn);
+  p.conv_P = static_cast<int>(P);
+  p.conv_Q = static_cast<int>(Q);
+  p.lower_w = -static_cast<int>(d->pad_w);
+  p.lower_h = -static_cast<int>(d->pad_h);
+  p.stride_w = static_cast<int>(d->stride_w);
+  p.stride_h = static_cast<int>(d->stride_h);
+  p.ntaps = taps;
+  p.c_chunks = static_cast<int>(d->c / 32);
+  p.b_tap_stride = static_cast<int>(d->c);
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      p.tap_w[r * d->kw + s] = static_cast<uint16_t>(s * d->dil_w);
+      p.tap_h[r * d->kw + s] = static_cast<uint16_t>(r * d->dil_h);
+    }
+  p.kb_total = taps * p.c_chunks;
+  p.out_mode = OUT_ROWS;
+  p.D = y;
+  p.ldd = d->k;
+  finish_split_fields(p, 1);
+  return run_with_splits(ctx, bn, ma, mb, p, M, d->k, y, d->k, 1.f, 0.f, bias);
+}
+
+// dx[N,H,W,C] = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Stride 1: one implicit GEMM over dy with the flipped filter.
+// Stride s > 1: one implicit GEMM per output parity class (h % s, w % s), scattered into dx.
+int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx) {
+  if (d->k % 32 != 0 || d->c % 4 != 0 || d->kh * d->kw > kUmmaMaxTaps) {
+    set_last_error("umma dgrad: shape unsupported");
+    return ZB_ERR_UNSUPPORTED;
+  }
+  const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  const int sh = static_cast<int>(d->stride_h), sw = static_cast<int>(d->stride_w);
+  const int R = static_cast<int>(d->kh), S = static_cast<int>(d->kw);
+  const int bn = pick_bn(d->c);
+
+  // Enumerate parity classes and their taps first so that unsupported geometry fails before any launch.
+  struct ClassPlan {
+    int a, b, Ha, Wb, lower_h, lower_w, upper_h, upper_w, ntaps;
+    int tap_rs[kUmmaMaxTaps];
+    int off_h[kUmmaMaxTaps], off_w[kUmmaMaxTaps];
+  };
+  std::vector<ClassPlan> plans;
+  bool need_zero = false;
+  for (int a = 0; a < sh; ++a)
+    for (int b = 0; b < sw; ++b) {
+      ClassPlan cp;
+      cp.a = a; cp.b = b; cp.ntaps = 0;
+      cp.Ha = static_cast<int>((d->h - a + sh - 1) / sh);
+      cp.Wb = static_cast<int>((d->w - b + sw - 1) / sw);
+      if (cp.Ha <= 0 || cp.Wb <= 0) continue;
+      int min_h = 1 << 30, min_w = 1 << 30;
+      for (int r = 0; r < R; ++r) {
+        const long long th = a + d->pad_h - r * d->dil_h;
+        if (((th % sh) + sh) % sh != 0) continue;
+        for (int s = 0; s < S; ++s) {
+          const long long tw = b + d->pad_w - s * d->dil_w;
+          if (((tw % sw) + sw) % sw != 0) continue;
+          const int oh = static_cast<int>(th >= 0 ? th / sh : -((-th) / sh));
+          const int ow = static_cast<int>(tw >= 0 ? tw / sw : -((-tw) / sw));
+          cp.tap_rs[cp.ntaps] = r * S + s;
+          cp.off_h[cp.ntaps] = oh;
+          cp.off_w[cp.ntaps] = ow;
+          min_h = std::min(min_h, oh);
+          min_w = std::min(min_w, ow);
+          cp.ntaps++;
+        }
+      }
+      if (cp.ntaps == 0) { need_zero = true; continue; }
+      cp.lower_h = min_h; cp.lower_w = min_w;
+      cp.upper_h = cp.Ha - static_cast<int>(P) + min_h;
+      cp.upper_w = cp.Wb - static_cast<int>(Q) + min_w;
+      for (int t = 0; t < cp.ntaps; ++t) {
+        cp.off_h[t] -= min_h;
+        cp.off_w[t] -= min_w;
+        if (cp.off_h[t] > 255 || cp.off_w[t] > 255) { set_last_error("umma dgrad: tap offset too large"); return ZB_ERR_UNSUPPORTED; }
+      }
+      if (cp.lower_h < -128 || cp.lower_h > 127 || cp.lower_w < -128 || cp.lower_w > 127 || cp.upper_h < -128 ||
+          cp.upper_h > 127 || cp.upper_w < -128 || cp.upper_w > 127) {
+        set_last_error("umma dgrad: corner out of range");
+        return ZB_ERR_UNSUPPORTED;
+      }
+      plans.push_back(cp);
+    }
+  if (need_zero) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
+
+  // workspace: transformed filters for all classes + tap index lists
+  size_t wt_elems = 0;
+  for (auto& cp : plans) wt_elems += static_cast<size_t>(d->c) * cp.ntaps * d->k;
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, wt_elems * sizeof(float), &ws);
+  if (rc != ZB_OK) return rc;
+  float* wt_base = static_cast<float*>(ws);
+
+  size_t wt_off = 0;
+  for (size_t ci = 0; ci < plans.size(); ++ci) {
+    const ClassPlan& cp = plans[ci];
+    float* wt = wt_base + wt_off;
+    wt_off += static_cast<size_t>(d->c) * cp.ntaps * d->k;
+    TapList tl;
+    memcpy(tl.rs, cp.tap_rs, sizeof(tl.rs));
+    {
+      const long long total = static_cast<long long>(d->c) * cp.ntaps * d->k;
+      const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
+      dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), cp.ntaps, tl);
+      ZB_LAUNCH_CHECK(ctx);
+    }
+    CUtensorMap ma, mb;
+    rc = make_map_im2col(ctx, &ma, dy, d->n, P, Q, d->k, cp.lower_w, cp.lower_h, cp.upper_w, cp.upper_h, 1, 1, kUmmaBM);
+    if (rc != ZB_OK) return rc;
+    rc = make_map_2d(ctx, &mb, wt, static_cast<long long>(cp.ntaps) * d->k, d->c, static_cast<long long>(cp.ntaps) * d->k, 32, bn);
+    if (rc != ZB_OK) return rc;
+    UmmaParams p;
+    init_params(p, ctx);
+    const long long M = d->n * static_cast<long long>(cp.Ha) * cp.Wb;
+    p.a_mode = A_IM2COL_K;
+    p.b_mode = B_TILED_K;
+    p.M = static_cast<int>(M);
+    p.N = static_cast<int>(d->c);
+    p.m_tiles = ceil_div(M, kUmmaBM);
+    p.n_tiles = ceil_div(d->c, bn);
+    p.conv_P = cp.Ha;
+    p.conv_Q = cp.Wb;
+    p.lower_w = cp.lower_w;
+    p.lower_h = cp.lower_h;
+    p.ntaps = cp.ntaps;
+    p.c_chunks = static_cast<int>(d->k / 32);
+    p.b_tap_stride = static_cast<int>(d->k);
+    for (int t = 0; t < cp.ntaps; ++t) {
+      p.tap_w[t] = static_cast<uint16_t>(cp.off_w[t]);
+      p.tap_h[t] = static_cast<uint16_t>(cp.off_h[t]);
+    }
+    p.kb_total = cp.ntaps * p.c_chunks;
+    p.D = dx;
+    p.ldd = d->c;
+    if (sh == 1 && sw == 1) {
+      p.out_mode = OUT_ROWS;
+    } else {
+      p.out_mode = OUT_SCATTER;
+      p.scat_OH = static_cast<int>(d->h);
+      p.scat_OW = static_cast<int>(d->w);
+      p.scat_sy = sh; p.scat_oy = cp.a;
+      p.scat_sx = sw; p.scat_ox = cp.b;
+    }
+    finish_split_fields(p, 1);
+    p.split_stride = 0;
+    rc = umma_launch(ctx, bn, ma, mb, p);
+    if (rc != ZB_OK) return rc;
+  }
+  return ZB_OK;
+}
+
+// dw[K,R,S,C] = wgrad(dy[N,P,Q,K], x[N,H,W,C]); reduction over N*P*Q pixels, split-K + deterministic reduce.
+int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, float* dw) {
+  if (d->c % 32 != 0 || d->k % 4 != 0 || d->kh * d->kw > kUmmaMaxTaps || d->pad_h > 127 || d->pad_w > 127 ||
+      d->dil_h * (d->kh - 1) > 255 || d->dil_w * (d->kw - 1) > 255) {
+    set_last_error("umma wgrad: shape unsupported");
+    return ZB_ERR_UNSUPPORTED;
+  }
+  const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  const long long NPQ = d->n * P * Q;
+  const int taps = static_cast<int>(d->kh * d->kw);
+  const int bn = pick_bn(d->c);
+  CUtensorMap ma, mb;
+  UmmaParams p;
+  init_params(p, ctx);
+  int rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK);
+  if (rc != ZB_OK) return rc;
+  p.a_mode = A_TILED_MN;
+  const bool pointwise = (taps == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0);
+  if (pointwise) {
+    rc = make_map_2d(ctx, &mb, x, d->c, NPQ, d->c, 32, kUmmaBK);
+    p.b_mode = B_TILED_MN;
+  } else {
+    rc = make_map_im2col(ctx, &mb, x, d->n, d->h, d->w, d->c, -static_cast<int>(d->pad_w), -static_cast<int>(d->pad_h),
+                         static_cast<int>(d->pad_w - d->dil_w * (d->kw - 1)), static_cast<int>(d->pad_h - d->dil_h * (d->kh - 1)),
+                         static_cast<int>(d->stride_w), static_cast<int>(d->stride_h), kUmmaBK);
+    p.b_mode = B_IM2COL_MN;
+  }
+  if (rc != ZB_OK) return rc;
+  p.M = static_cast<int>(d->k);
+  p.N = static_cast<int>(d->c);
+  p.m_tiles = ceil_div(d->k, kUmmaBM);
+  p.n_tiles = ceil_div(d->c, bn);
+  p.tap_tiles = taps;
+  p.conv_P = static_cast<int>(P);
+  p.conv_Q = static_cast<int>(Q);
+  p.lower_w = -static_cast<int>(d->pad_w);
+  p.lower_h = -static_cast<int>(d->pad_h);
+  p.stride_w = static_cast<int>(d->stride_w);
+  p.stride_h = static_cast<int>(d->stride_h);
+  p.ntaps = taps;
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      p.tap_w[r * d->kw + s] = static_cast<uint16_t>(s * d->dil_w);
+      p.tap_h[r * d->kw + s] = static_cast<uint16_t>(r * d->dil_h);
+    }
+  p.kb_total = ceil_div(NPQ, kUmmaBK);
+  p.out_mode = OUT_ROWS;
+  p.D = dw;
+  p.ldd = static_cast<long long>(taps) * d->c;
+  p.tap_col_stride = d->c;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * taps;
+  finish_split_fields(p, pick_splits(ctx, tiles, p.kb_total, 16));
+  if (p.splits <= 1) {
+    p.split_stride = 0;
+    return umma_launch(ctx, bn, ma, mb, p);
+  }
+  // partial buffers keep the [K][taps*C] shape of dw
+  const long long rows = d->k, cols = static_cast<long long>(taps) * d->c;
+  void* ws = nullptr;
+  rc = ctx_workspace(ctx, sizeof(float) * static_cast<size_t>(p.splits) * rows * cols, &ws);
+  if (rc != ZB_OK) return rc;
+  UmmaParams q = p;
+  q.D = static_cast<float*>(ws);
+  q.split_stride = rows * cols;
+  rc = umma_launch(ctx, bn, ma, mb, q);
+  if (rc != ZB_OK) return rc;
+  const long long total = rows * cols;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
+  splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ws), dw, rows, cols, cols, rows * cols,
+                                                      q.splits, 1.f, 0.f, nullptr);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+}  // namespace zb

@@ -1,0 +1,54 @@
+// umma_gemm.cuh — parameter block shared by the tcgen05 implicit-GEMM kernel and its host planners.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+
+namespace zb {
+
+constexpr int kUmmaBM = 128;      // accumulator rows per CTA tile (TMEM lanes)
+constexpr int kUmmaBK = 32;       // fp32 elements of K per pipeline stage (= one 128-byte swizzle row)
+constexpr int kUmmaMaxTaps = 64;  // filter taps addressable by one launch (7x7 = 49)
+
+enum UmmaAMode : int {
+  A_TILED_K = 0,   // A[M][K] row-major, K contiguous            (Linear, 1x1 conv, dgrad 1x1)
+  A_IM2COL_K = 1,  // NHWC activations through TMA im2col, K = (tap, channel chunk)   (fprop / dgrad 3x3)
+  A_TILED_MN = 2,  // A^T stored: [K][M] row-major, M contiguous (wgrad: dY[pixels][Kout])
+};
+enum UmmaBMode : int {
+  B_TILED_K = 0,    // B[N][K] row-major, K contiguous            (weights [Kout][taps*C])
+  B_TILED_MN = 2,   // B stored [K][N] row-major, N contiguous    (wgrad 1x1: X[pixels][Cin]; Linear dX)
+  B_IM2COL_MN = 3,  // NHWC activations through TMA im2col, N = channels, K = pixels (wgrad kxk)
+};
+enum UmmaOutMode : int {
+  OUT_ROWS = 0,     // D[row][col], row pitch ldd
+  OUT_SCATTER = 1,  // row m = (n,p,q) -> NHWC pixel (n, p*osy+oy0, q*osx+ox0) of an [N][OH][OW][ldd] tensor
+};
+
+struct UmmaParams {
+  // GEMM view
+  int M, N;              // logical output extent (rows, cols) of one "tap tile group"
+  int m_tiles, n_tiles;  // ceil(M/128), ceil(N/BN)
+  int tap_tiles;         // wgrad: one output tile group per filter tap; otherwise 1
+  int splits;            // split-K factor (K ranges go to separate partial buffers)
+  int kb_total;          // number of 32-wide K blocks in the full reduction
+  int kb_per_split;
+  int a_mode, b_mode, out_mode;
+  // im2col geometry (base-pixel grid P x Q per image, lower corner and traversal stride in input pixels)
+  int conv_P, conv_Q;
+  int lower_w, lower_h, stride_w, stride_h;
+  int ntaps, c_chunks;   // A_IM2COL_K: kb -> (tap = kb / c_chunks, c0 = 32 * (kb % c_chunks))
+  int b_tap_stride;      // columns of B per tap (padded C) for A_IM2COL_K
+  uint16_t tap_w[kUmmaMaxTaps];
+  uint16_t tap_h[kUmmaMaxTaps];
+  // output
+  float* D;
+  long long ldd;              // row pitch of D in elements
+  long long tap_col_stride;   // wgrad: column offset of tap t inside a D row (= Cin)
+  long long split_stride;     // elements between split-K partial buffers (0 when splits == 1)
+  const float* bias;          // optional [N], added when splits == 1
+  float alpha, beta;          // D = alpha*acc + bias + beta*D_old (splits == 1); partials store raw acc
+  int scat_OH, scat_OW, scat_sy, scat_oy, scat_sx, scat_ox;  // OUT_SCATTER geometry
+  int* err_flag;              // device word set to 1 on an mbarrier timeout
+};
+
+}  // namespace zb
