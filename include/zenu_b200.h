@@ -180,6 +180,42 @@ int zb_dp_wait(zb_ctx* ctx);
 int zb_dp_rank(zb_ctx* ctx);
 int zb_dp_world(zb_ctx* ctx);
 
+/* ---- host model API (layers / tape / optimizer above the op ABI) -----------------------------------
+ * C face of the C++ host side (zenu_b200/csrc/host): Module::call + Variable::backward + Optimizer::update
+ * (reference: zenu-layer/src/lib.rs:21-51, zenu-autograd/src/lib.rs:413-420, zenu-optimizer/src/lib.rs:8-10)
+ * for the architectures the configs name: "small_cnn" (zenu/examples/cifar10.rs:29-69), "resnet18", "resnet50"
+ * (torchvision v1.5 topology composed from Conv2d / BatchNorm2d / Linear).
+ * Inputs are NCHW (reference contract); parameters are exposed as device pointers with reference names
+ * ("conv1.conv2d.filter", "bn1.batch_norm_2d.scale", ...).  Conv filters are stored KRSC ([K,R,S,C]).
+ * fused != 0 uses the fused BN+ReLU(+residual) nodes; fused == 0 the reference's separate nodes. */
+typedef struct zb_model zb_model;
+typedef enum { ZB_OPT_SGD = 0, ZB_OPT_ADAM = 1, ZB_OPT_ADAMW = 2 } zb_optimizer_kind;
+typedef enum { ZB_PARAM_WEIGHT = 0, ZB_PARAM_BIAS = 1, ZB_PARAM_BUFFER = 2 } zb_param_kind;
+
+int zb_model_create(zb_ctx* ctx, const char* arch, int dtype, int num_classes, int fused, uint64_t seed,
+                    int64_t bucket_bytes, zb_model** out);
+int zb_model_destroy(zb_model* m);
+int zb_model_param_count(zb_model* m);
+/* shape gets up to 4 extents; data / grad are device pointers (grad is NULL for buffers) */
+int zb_model_param_info(zb_model* m, int index, char* name, int name_cap, int64_t* shape, int* ndim, int* kind,
+                        void** data, void** grad);
+int zb_model_set_train(zb_model* m, int train);
+int zb_model_set_optimizer(zb_model* m, int kind, double lr, double beta1, double beta2, double eps,
+                           double weight_decay);
+/* logits_out: device [batch, classes] */
+int zb_model_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w,
+                     void* logits_out);
+/* forward + loss + backward; gradients are left in the flat gradient buffer; bucket allreduces are enqueued on
+ * the comm stream as each bucket completes when the ctx is data parallel.  loss_dev: device scalar. */
+int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
+                              int64_t h, int64_t w, void* loss_dev);
+int zb_model_update(zb_model* m); /* Optimizer::update */
+/* forward_backward + update; if host_loss != NULL the loss is copied back (synchronises the stream) */
+int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
+                        int64_t h, int64_t w, void* loss_dev, double* host_loss);
+/* bytes currently held by the model's caching allocator (activations + parameters) */
+int64_t zb_model_bytes_reserved(zb_model* m);
+
 #ifdef __cplusplus
 }
 #endif

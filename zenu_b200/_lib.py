@@ -32,7 +32,7 @@ class ConvDesc(ctypes.Structure):
 
 _CTYPE = {
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "double": ctypes.c_double, "float": ctypes.c_float,
-    "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t,
+    "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64,
 }
 
 

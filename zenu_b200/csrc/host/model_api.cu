@@ -1,0 +1,163 @@
+// model_api.cu — extern "C" face of the host model (see include/zenu_b200.h "host model API").
+#include <cstring>
+
+#include "autograd.h"
+
+using namespace zb::host;
+
+struct zb_model {
+  zb_ctx* ctx;
+  std::unique_ptr<Runtime> rt;
+  std::shared_ptr<Model> model;
+  ParamStore params;
+  Optimizer opt;
+  bool opt_ready = false;
+  Variable last_loss;
+};
+
+#define ZB_HOST_TRY(body)                                  \
+  try {                                                    \
+    body;                                                  \
+    return ZB_OK;                                          \
+  } catch (const HostError& e) {                           \
+    zb::set_last_error("%s", e.what());                    \
+    return ZB_ERR_INVALID;                                 \
+  } catch (const std::exception& e) {                      \
+    zb::set_last_error("host error: %s", e.what());        \
+    return ZB_ERR_INVALID;                                 \
+  }
+
+static Variable run_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w) {
+  Runtime& rt = *m->rt;
+  Variable xin = Variable::leaf(rt.borrow(const_cast<void*>(x_nchw), {batch, c, h, w}));
+  Variable x = nchw_to_nhwc(rt, xin);
+  return m->model->call(rt, x);
+}
+
+extern "C" {
+
+int zb_model_create(zb_ctx* ctx, const char* arch, int dtype, int num_classes, int fused, uint64_t seed, int64_t bucket_bytes,
+                    zb_model** out) {
+  ZB_REQUIRE(ctx && arch && out, "zb_model_create: NULL argument");
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "zb_model_create: unknown dtype %d", dtype);
+  ZB_HOST_TRY({
+    auto m = std::make_unique<zb_model>();
+    m->ctx = ctx;
+    m->rt = std::make_unique<Runtime>(ctx);
+    m->rt->dtype = dtype;
+    m->model = make_model(arch, num_classes, fused != 0);
+    m->params.build(*m->rt, *m->model, seed, bucket_bytes > 0 ? bucket_bytes : (25ll << 20));
+    *out = m.release();
+  });
+}
+
+int zb_model_destroy(zb_model* m) {
+  if (!m) return ZB_OK;
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaStreamSynchronize(m->ctx->comm_stream);
+  if (m->last_loss.defined()) m->last_loss.clear_grad();
+  delete m;
+  return ZB_OK;
+}
+
+int zb_model_param_count(zb_model* m) { return static_cast<int>(m->params.entries.size()); }
+
+int zb_model_param_info(zb_model* m, int index, char* name, int name_cap, int64_t* shape, int* ndim, int* kind, void** data,
+                        void** grad) {
+  ZB_REQUIRE(index >= 0 && index < static_cast<int>(m->params.entries.size()), "param index out of range");
+  const ParamEntry& e = m->params.entries[index];
+  if (name && name_cap > 0) {
+    strncpy(name, e.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  const auto& s = e.var->data.shape;
+  if (ndim) *ndim = static_cast<int>(s.size());
+  if (shape) for (size_t i = 0; i < s.size() && i < 4; ++i) shape[i] = s[i];
+  if (kind) *kind = e.kind;
+  if (data) *data = e.var->data.ptr;
+  if (grad) *grad = e.var->grad_slot.ptr;
+  return ZB_OK;
+}
+
+int zb_model_set_train(zb_model* m, int train) {
+  m->rt->train = train != 0;
+  return ZB_OK;
+}
+
+int zb_model_set_optimizer(zb_model* m, int kind, double lr, double beta1, double beta2, double eps, double weight_decay) {
+  ZB_REQUIRE(kind >= 0 && kind <= 2, "unknown optimizer kind %d", kind);
+  ZB_HOST_TRY({
+    m->opt.kind = kind;
+    m->opt.lr = lr;
+    m->opt.beta1 = beta1;
+    m->opt.beta2 = beta2;
+    m->opt.eps = eps;
+    m->opt.weight_decay = weight_decay;
+    m->opt.init(*m->rt, m->params);
+    m->opt_ready = true;
+  });
+}
+
+int zb_model_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w, void* logits_out) {
+  ZB_HOST_TRY({
+    Variable logits = run_forward(m, x_nchw, batch, c, h, w);
+    check_rc(zb_copy(m->ctx, m->rt->dtype, logits->data.ptr, logits_out, logits->data.numel()), "copy logits");
+    logits.clear_grad();
+  });
+}
+
+int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h,
+                              int64_t w, void* loss_dev) {
+  ZB_HOST_TRY({
+    Runtime& rt = *m->rt;
+    if (m->last_loss.defined()) { m->last_loss.clear_grad(); m->last_loss = Variable(); }
+    for (auto& e : m->params.entries) e.var->grad = Tensor();  // loss.clear_grad() of the previous step
+    m->params.reset_pending();
+    Variable logits = run_forward(m, x_nchw, batch, c, h, w);
+    Tensor t = rt.borrow(const_cast<void*>(targets), {batch, logits.shape()[1]});
+    Variable loss = softmax_cross_entropy(rt, logits, t);
+    ParamStore& ps = m->params;
+    zb_ctx* ctx = m->ctx;
+    const size_t esz = rt.dtype == ZB_F64 ? 8 : 4;
+    // hook: called with -1-bucket each time a parameter of that bucket received its gradient
+    loss.backward(rt, [&](int code) {
+      const int b = -1 - code;
+      if (b < 0 || b >= static_cast<int>(ps.buckets.size())) return;
+      if (--ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1)
+        check_rc(zb_dp_allreduce_sum(ctx, rt.dtype, static_cast<uint8_t*>(ps.flat_grads.ptr) + ps.buckets[b].offset * esz,
+                                     ps.buckets[b].numel), "bucket allreduce");
+    });
+    if (loss_dev) check_rc(zb_copy(ctx, rt.dtype, loss->data.ptr, loss_dev, 1), "copy loss");
+    m->last_loss = loss;
+  });
+}
+
+int zb_model_update(zb_model* m) {
+  ZB_REQUIRE(m->opt_ready, "zb_model_update: call zb_model_set_optimizer first");
+  ZB_HOST_TRY({ m->opt.update(*m->rt, m->params); });
+}
+
+int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h, int64_t w,
+                        void* loss_dev, double* host_loss) {
+  int rc = zb_model_forward_backward(m, x_nchw, targets, batch, c, h, w, loss_dev);
+  if (rc != ZB_OK) return rc;
+  rc = zb_model_update(m);
+  if (rc != ZB_OK) return rc;
+  if (host_loss) {
+    ZB_REQUIRE(m->last_loss.defined(), "no loss");
+    if (m->rt->dtype == ZB_F64) {
+      ZB_CHECK_CUDA(cudaMemcpyAsync(host_loss, m->last_loss->data.ptr, 8, cudaMemcpyDeviceToHost, m->ctx->stream));
+      ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    } else {
+      float f = 0.f;
+      ZB_CHECK_CUDA(cudaMemcpyAsync(&f, m->last_loss->data.ptr, 4, cudaMemcpyDeviceToHost, m->ctx->stream));
+      ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+      *host_loss = f;
+    }
+  }
+  return ZB_OK;
+}
+
+int64_t zb_model_bytes_reserved(zb_model* m) { return static_cast<int64_t>(m->rt->alloc.bytes_reserved()); }
+
+}  // extern "C"

@@ -152,17 +152,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4      [46,48) version = 1 (Blackwell)
 //   [49,52) base offset = 0          [61,64) layout: 0 none, 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B
-// K-major SW128 (rows of 128 B = 32 tf32 along K): SBO = stride between 8-row groups (1024 B when dense),
-//   LBO unused (1).  MN-major SW128 (rows of 128 B = 32 elements along M/N, one row per k):
-//   LBO = stride between 32-element M/N groups, SBO = stride between 8-k groups (1024 B when dense).
-__host__ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                                   uint32_t sbo_bytes) {
+//           1 = SWIZZLE_128B_BASE32B (128 B span, 32-byte swizzle atoms)
+// K-major, SWIZZLE_128B (rows of 128 B = 32 tf32 along K): SBO = stride between 8-row groups (1024 B when
+//   dense), LBO unused (1).
+// MN-major tf32 operands must use SWIZZLE_128B_BASE32B (the only layout the tensor core accepts for 32-bit
+//   MN-major data; TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B = 32 elements along
+//   M/N, one row per k, swizzle period 4 rows.  LBO = stride between 32-element M/N groups,
+//   SBO = stride between 4-k groups (512 B when dense).
+constexpr uint32_t kSmemLayoutSw128 = 2;
+constexpr uint32_t kSmemLayoutSw128Base32 = 1;
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                             uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // version
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
 }
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate:

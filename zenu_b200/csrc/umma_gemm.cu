@@ -182,10 +182,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t b_base = a_base + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < kUmmaBK / 8; ++k) {
-            const uint64_t da = a_mn ? make_smem_desc_sw128(a_base + k * 1024, 4096, 1024)
-                                     : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t db = b_mn ? make_smem_desc_sw128(b_base + k * 1024, 4096, 1024)
-                                     : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            const uint64_t da = a_mn ? make_smem_desc(a_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
+                                     : make_smem_desc(a_base + k * 32, 16, 1024, kSmemLayoutSw128);
+            const uint64_t db = b_mn ? make_smem_desc(b_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
+                                     : make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128);
             umma_tf32(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -326,7 +326,7 @@ static CUtensorMapDataType operand_dtype() {
 
 // 2-D row-major matrix [outer][inner], box (box_inner <= 32 fp32 = 128 B swizzle span, box_outer <= 256).
 static int make_map_2d(zb_ctx* ctx, CUtensorMap* map, const float* base, long long inner, long long outer,
-                       long long pitch_elems, int box_inner, int box_outer) {
+                       long long pitch_elems, int box_inner, int box_outer, bool mn_major = false) {
   ZB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
   ZB_REQUIRE((pitch_elems * 4) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (got %lld elems)", pitch_elems);
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
@@ -334,7 +334,8 @@ static int make_map_2d(zb_ctx* ctx, CUtensorMap* map, const float* base, long lo
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ctx->encode_tiled(map, operand_dtype(), 2, const_cast<float*>(base), dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d", int(r), inner, outer,
@@ -347,7 +348,7 @@ static int make_map_2d(zb_ctx* ctx, CUtensorMap* map, const float* base, long lo
 // NHWC activation tensor seen as (C, W, H, N) for im2col loads: `pixels` base pixels x 32 channels per load.
 static int make_map_im2col(zb_ctx* ctx, CUtensorMap* map, const float* base, long long N, long long H, long long W,
                            long long C, int lower_w, int lower_h, int upper_w, int upper_h, int stride_w, int stride_h,
-                           int pixels) {
+                           int pixels, bool mn_major = false) {
   ZB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
   ZB_REQUIRE(C % 4 == 0, "im2col TMA needs C %% 4 == 0 (got %lld)", C);
   ZB_REQUIRE(lower_w >= -128 && lower_w <= 127 && lower_h >= -128 && lower_h <= 127 && upper_w >= -128 &&
@@ -362,7 +363,8 @@ static int make_map_im2col(zb_ctx* ctx, CUtensorMap* map, const float* base, lon
   cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
   CUresult r = ctx->encode_im2col(map, operand_dtype(), 4, const_cast<float*>(base), dims, strides, lower, upper,
                                   /*channelsPerPixel=*/32, /*pixelsPerColumn=*/static_cast<cuuint32_t>(pixels), estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeIm2col failed (%d): NHWC=%lldx%lldx%lldx%lld lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)",
@@ -479,7 +481,7 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
     rc = make_map_2d(ctx, &ma, a, k, m, lda, 32, kUmmaBM);
     p.a_mode = A_TILED_K;
   } else {  // A stored [k][m]
-    rc = make_map_2d(ctx, &ma, a, m, k, lda, 32, kUmmaBK);
+    rc = make_map_2d(ctx, &ma, a, m, k, lda, 32, kUmmaBK, true);
     p.a_mode = A_TILED_MN;
   }
   if (rc != ZB_OK) return rc;
@@ -487,7 +489,7 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
     rc = make_map_2d(ctx, &mb, b, k, n, ldb, 32, bn);
     p.b_mode = B_TILED_K;
   } else {  // B stored [k][n]
-    rc = make_map_2d(ctx, &mb, b, n, k, ldb, 32, kUmmaBK);
+    rc = make_map_2d(ctx, &mb, b, n, k, ldb, 32, kUmmaBK, true);
     p.b_mode = B_TILED_MN;
   }
   if (rc != ZB_OK) return rc;
@@ -709,17 +711,17 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   CUtensorMap ma, mb;
   UmmaParams p;
   init_params(p, ctx);
-  int rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK);
+  int rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK, true);
   if (rc != ZB_OK) return rc;
   p.a_mode = A_TILED_MN;
   const bool pointwise = (taps == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0);
   if (pointwise) {
-    rc = make_map_2d(ctx, &mb, x, d->c, NPQ, d->c, 32, kUmmaBK);
+    rc = make_map_2d(ctx, &mb, x, d->c, NPQ, d->c, 32, kUmmaBK, true);
     p.b_mode = B_TILED_MN;
   } else {
     rc = make_map_im2col(ctx, &mb, x, d->n, d->h, d->w, d->c, -static_cast<int>(d->pad_w), -static_cast<int>(d->pad_h),
                          static_cast<int>(d->pad_w - d->dil_w * (d->kw - 1)), static_cast<int>(d->pad_h - d->dil_h * (d->kh - 1)),
-                         static_cast<int>(d->stride_w), static_cast<int>(d->stride_h), kUmmaBK);
+                         static_cast<int>(d->stride_w), static_cast<int>(d->stride_h), kUmmaBK, true);
     p.b_mode = B_IM2COL_MN;
   }
   if (rc != ZB_OK) return rc;
