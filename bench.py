@@ -1,0 +1,333 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark: ResNet-50 f32/TF32 training throughput (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libzenu_b200.so through the host model API)
+  python bench.py --impl reference ...                      the reference's CPU path (oracle port) on the host cores
+
+A step = one full train step (forward, cross-entropy, backward, SGD update; with N > 1 the bucketed NCCL gradient
+allreduce overlapped with backward) of ResNet-50 on a synthetic batch of 256 images (3x224x224, 1000 classes) per GPU.
+`value` is timed with the batch already resident in HBM; `e2e` is the same step fed from pinned HOST memory (H2D copy of
+the batch every step, prefetched on a side stream, and a D2H read of the loss) — both through the public API.
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  L2: every step
+streams > 20 GB of activations, far larger than the 126 MB L2, so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "resnet50_train_images_per_s"
+UNIT = "images/s"
+FWD_GFLOP_PER_IMG = {"resnet50": 8.174 + 0.0041, "resnet18": 3.627 + 0.001, "small_cnn": 0.107}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:  # noqa: BLE001  (profiling recipe's stated fallback)
+        return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def synthetic_batch(batch, hw, classes, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((batch, 3, hw, hw), generator=g, dtype=torch.float32)
+    labels = torch.randint(0, classes, (batch,), generator=g)
+    t = torch.zeros((batch, classes), dtype=torch.float32)
+    t[torch.arange(batch), labels] = 1.0
+    return x, t
+
+
+def cpu_reference_steps(arch, classes, hw, sample_batch, steps, warmup):
+    """The reference's CPU algorithm (oracle port: im2col + OpenBLAS conv, CPU BatchNorm, ...) on the host cores."""
+    import numpy as np
+
+    from oracle import zenu_oracle as zo
+    from oracle import zenu_oracle_model as zm
+    cores = os.cpu_count() or 1
+    blas = zo.use_openblas(threads=cores)
+    model = zm.OracleModel(arch, classes, zm.init_params(arch, classes, seed=42))
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal((sample_batch, 3, hw, hw)).astype(np.float32)
+    t = np.zeros((sample_batch, classes), np.float32)
+    t[np.arange(sample_batch), rng.integers(0, classes, sample_batch)] = 1.0
+    for _ in range(warmup):
+        model.train_step(x, t, kind="sgd", lr=0.01)
+    t0 = time.perf_counter()
+    loss = 0.0
+    for _ in range(steps):
+        loss = model.train_step(x, t, kind="sgd", lr=0.01)
+    dt = time.perf_counter() - t0
+    return {"images_per_s": sample_batch * steps / dt, "sec_per_step": dt / max(steps, 1), "cores": cores,
+            "blas": "OpenBLAS (numpy bundled, all cores)" if blas else "plain C loops", "loss": float(loss)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = args.ref_batch
+    r = cpu_reference_steps(args.arch, args.classes, args.hw, sample, args.steps, min(args.warmup, 1))
+    ms = r["sec_per_step"] * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": f"each step = one full train step on {sample} of the 256 images",
+                   "note": "reference CPU path restated in C (oracle/): no Rust toolchain in this image, see DESIGN.md"},
+        "cpu_baseline": {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": f"{args.steps} train steps at batch {sample} (of 256), {r['blas']}"},
+        "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"{args.arch} train step (fwd + cross-entropy + bwd + SGD lr 0.01), batch {args.batch}/GPU, 3x{args.hw}x{args.hw}, "
+            f"{args.classes} classes, f32 storage, TF32 tensor-core math")
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    from zenu_b200 import nn, ops
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    ctx = ops.Context(device=local_rank)
+    lib = ctx.lib
+    if world > 1:
+        import ctypes
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            ops.check(lib.zb_dp_unique_id(ctx.handle, buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        ops.check(lib.zb_dp_init(ctx.handle, raw, rank, world))
+    model = nn.Model(ctx, args.arch, args.classes, fused=True, seed=42, bucket_mb=args.bucket_mb)
+    model.set_optimizer("sgd", lr=0.01)
+    x_host, t_host = synthetic_batch(args.batch, args.hw, args.classes, 1234 + rank)
+    x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
+    X, T = x_pin.cuda(non_blocking=True), t_pin.cuda(non_blocking=True)
+    loss_dev = torch.zeros(1, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        model.train_step(X, T, loss_out=loss_dev)
+    ctx.check()
+    # ---------------------------------------------------------------- timed region: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    import ctypes
+    ops.check(lib.zb_ctx_profile_enable(ctx.handle, 1))
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        model.train_step(X, T, loss_out=loss_dev)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    prof = {}
+    for cls, name in ((0, "tensor"), (1, "bn")):
+        n_ops, ms, work = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+        ops.check(lib.zb_ctx_profile_read(ctx.handle, cls, ctypes.byref(n_ops), ctypes.byref(ms), ctypes.byref(work)))
+        prof[name] = (n_ops.value, ms.value, work.value)
+    ops.check(lib.zb_ctx_profile_enable(ctx.handle, 0))
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_dev.item())
+    ctx.check()
+    # ---------------------------------------------------------------- e2e: batch comes from pinned host memory each step
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(X), torch.empty_like(T)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            bufs[i % 2][0].copy_(x_pin, non_blocking=True)
+            bufs[i % 2][1].copy_(t_pin, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    for e in consumed:
+        e.record()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    prefetch(0)
+    loss_host = 0.0
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        xb, tb = bufs[i % 2]
+        loss_host = model.train_step(xb, tb, loss_out=loss_dev, read_loss=True)   # D2H read of the loss, synchronises
+        consumed[i % 2].record()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    # ---------------------------------------------------------------- reduce over ranks (max time)
+    times = torch.tensor([elapsed_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    global_batch = args.batch * world
+    value = global_batch * args.steps / (elapsed_ms / 1e3)
+    e2e_value = global_batch * args.steps / (e2e_ms / 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0   # dense TF32 = 1/2 of the measured (sustained, in-step) bf16 GEMM rate
+    t_ops, t_ms, t_flops = prof["tensor"]
+    b_ops, b_ms, b_bytes = prof["bn"]
+    step_ms = elapsed_ms / args.steps
+    tensor_share = t_ms / elapsed_ms if elapsed_ms > 0 else 0.0
+    bn_share = b_ms / elapsed_ms if elapsed_ms > 0 else 0.0
+    tensor_tflops = (t_flops / (t_ms * 1e-3)) / 1e12 if t_ms > 0 else 0.0
+    bn_gbs = (b_bytes / (b_ms * 1e-3)) / 1e9 if b_ms > 0 else 0.0
+    if tensor_share >= bn_share:
+        roofline = {"kernel": "zb::umma_kernel (tcgen05 kind::tf32 implicit-GEMM conv/GEMM)", "bound": "tensor", "achieved": tensor_tflops,
+                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+                    "peak_source": f"{peaks['source']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate)",
+                    "launches_per_step": t_ops / args.steps, "share_of_step": tensor_share,
+                    "algorithmic_gflop_per_launch_avg": t_flops / max(t_ops, 1) / 1e9, "avg_launch_ms": t_ms / max(t_ops, 1)}
+    else:
+        roofline = {"kernel": "BatchNorm2d reduce/apply kernels (fused ReLU / residual)", "bound": "hbm", "achieved": bn_gbs,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bn_gbs / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": f"{peaks['source']}: hbm_gbs", "ops_per_step": b_ops / args.steps, "share_of_step": bn_share,
+                    "algorithmic_mb_per_op_avg": b_bytes / max(b_ops, 1) / 1e6, "avg_op_ms": b_ms / max(b_ops, 1)}
+    secondary = {"tensor": {"achieved_tflops": tensor_tflops, "frac_of_tf32_peak": tensor_tflops / tf32_peak if tf32_peak else None,
+                            "share_of_step": tensor_share, "launches_per_step": t_ops / args.steps},
+                 "bn_hbm": {"achieved_gbs": bn_gbs, "frac_of_hbm_peak": bn_gbs / peaks["hbm_gbs"], "share_of_step": bn_share,
+                            "ops_per_step": b_ops / args.steps}}
+    train_tflop_per_step = 3.0 * FWD_GFLOP_PER_IMG.get(args.arch, 0.0) * args.batch / 1e3
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_steps(args.arch, args.classes, args.hw, args.cpu_batch, 2, 1)
+        cpu_baseline = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                        "sample": f"2 train steps at batch {args.cpu_batch} (of 256) after 1 warm-up, {r['blas']}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "global_batch": global_batch, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (each step streams > 20 GB of activations; L2 is 126 MB)",
+                   "optimizer": "SGD lr 0.01 (zenu-optimizer/src/sgd.rs)", "grad_allreduce": "bucketed NCCL sum, overlapped with backward" if world > 1 else "none (1 GPU)",
+                   "input_grad_of_conv1": "computed (as the reference does)"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_host},
+        "roofline": roofline, "roofline_by_class": secondary,
+        "step_model_flops": {"algorithmic_tflop_per_step_per_gpu": train_tflop_per_step,
+                             "achieved_tflops_whole_step": train_tflop_per_step / (step_ms / 1e3) if step_ms > 0 else None},
+        "cpu_baseline": cpu_baseline, "final_loss": final_loss, "hbm_bytes_reserved": model.bytes_reserved(),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="resnet50", choices=["resnet50", "resnet18", "small_cnn"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--hw", type=int, default=224)
+    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--bucket-mb", type=int, default=25)
+    ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run (one rank per GPU)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

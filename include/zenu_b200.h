@@ -62,6 +62,11 @@ void* zb_ctx_stream(zb_ctx* ctx);
 int zb_ctx_check(zb_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py reports the delta as gpu_launches). */
 unsigned long long zb_ctx_launch_count(zb_ctx* ctx);
+/* Optional per-op timing with CUDA events on the ctx stream (used by bench.py for the live roofline figures).
+ * cls: 0 = tensor-core conv/GEMM launches (work = algorithmic FLOPs), 1 = BatchNorm ops (work = algorithmic
+ * bytes), 2 = other elementwise ops (bytes).  enable clears earlier records; read synchronises the stream. */
+int zb_ctx_profile_enable(zb_ctx* ctx, int enable);
+int zb_ctx_profile_read(zb_ctx* ctx, int cls, int64_t* ops, double* total_ms, double* work);
 const char* zb_last_error(void);
 const char* zb_version(void);
 

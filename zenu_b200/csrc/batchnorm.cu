@@ -547,6 +547,7 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
   T* partial = static_cast<T*>(ws);
   T* coef = partial + ms * 2 * C;
   int slabs = 0;
+  prof_begin(ctx, PROF_BN);
   rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
                                   partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
   if (rc != ZB_OK) return rc;
@@ -555,7 +556,10 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
                                                                layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
                                                                saved_inv, coef);
   ZB_LAUNCH_CHECK(ctx);
-  return dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu);
+  rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu);
+  // algorithmic bytes: x read twice + y written (+ residual read)
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * (res ? 4.0 : 3.0));
+  return rc;
 }
 
 template <typename T>
@@ -622,6 +626,7 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
     if (mean == nullptr) mean = stats;
     if (inv == nullptr) inv = stats + C;
   }
+  prof_begin(ctx, PROF_BN);
   if (y != nullptr)
     rc = run_col_reduce<T, BnBwdMaskFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
                                         [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
@@ -632,10 +637,13 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   bn_bwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), scale, inv,
                                                                dscale, dbias, coef);
   ZB_LAUNCH_CHECK(ctx);
-  if (y != nullptr && dres != nullptr) return launch_bwd_apply<T, true, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  if (y != nullptr) return launch_bwd_apply<T, true, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  if (dres != nullptr) return launch_bwd_apply<T, false, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  return launch_bwd_apply<T, false, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  if (y != nullptr && dres != nullptr) rc = launch_bwd_apply<T, true, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  else if (y != nullptr) rc = launch_bwd_apply<T, true, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  else if (dres != nullptr) rc = launch_bwd_apply<T, false, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  else rc = launch_bwd_apply<T, false, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written)
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * (5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
+  return rc;
 }
 
 // out[c] = sum over (n, hw) of a — conv bias gradient / Matrix::sum(axis 0) on a [rows][cols] matrix (NHWC, HW = 1)

@@ -22,6 +22,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 }  // namespace zb
 
+namespace zb { struct ProfState; }
+
 // The context: one per process/rank, single owner (mirrors the reference's single global
 // ZENU_CUDA_STATE, zenu-cuda/src/lib.rs:18-25, minus the mutex and the library handles).
 struct zb_ctx {
@@ -43,6 +45,7 @@ struct zb_ctx {
   int rank, world;
   cudaEvent_t ev_ready, ev_done;  // compute->comm and comm->compute fences
   unsigned long long launches;  // number of kernels this ctx launched (bench.py's gpu_launches)
+  zb::ProfState* prof;          // optional per-op CUDA-event timing (zb_ctx_profile_*)
 };
 
 namespace zb {
@@ -73,6 +76,13 @@ namespace zb {
       return ZB_ERR_CUDA;                                                                     \
     }                                                                                         \
   } while (0)
+
+// Per-op timing with CUDA events on the launching stream, grouped by kernel class (bench.py roofline):
+// class 0 = tcgen05 implicit-GEMM / GEMM launches (work = algorithmic FLOPs),
+// class 1 = BatchNorm ops (work = algorithmic bytes), class 2 = other elementwise (bytes).
+enum ProfClass { PROF_TENSOR = 0, PROF_BN = 1, PROF_EWISE = 2, PROF_NUM = 3 };
+void prof_begin(zb_ctx* ctx, int cls);
+void prof_end(zb_ctx* ctx, int cls, double work);
 
 // Grow-only scratch; stream-ordered so earlier kernels that still read the old block stay valid.
 int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out);

@@ -5,9 +5,41 @@
 #include <cstdio>
 #include <cstring>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace zb {
+
+struct ProfRecord { cudaEvent_t a, b; double work; };
+struct ProfState {
+  bool enabled = false;
+  std::vector<ProfRecord> rec[PROF_NUM];
+  cudaEvent_t open[PROF_NUM] = {nullptr, nullptr, nullptr};
+};
+
+void prof_begin(zb_ctx* ctx, int cls) {
+  if (!ctx->prof || !ctx->prof->enabled) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, ctx->stream);
+  ctx->prof->open[cls] = e;
+}
+void prof_end(zb_ctx* ctx, int cls, double work) {
+  if (!ctx->prof || !ctx->prof->enabled || !ctx->prof->open[cls]) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, ctx->stream);
+  ctx->prof->rec[cls].push_back({ctx->prof->open[cls], e, work});
+  ctx->prof->open[cls] = nullptr;
+}
+static void prof_clear(ProfState* p) {
+  for (int c = 0; c < PROF_NUM; ++c) {
+    for (auto& r : p->rec[c]) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    p->rec[c].clear();
+    if (p->open[c]) { cudaEventDestroy(p->open[c]); p->open[c] = nullptr; }
+  }
+}
 
 static thread_local char g_last_error[1024] = "";
 
@@ -91,11 +123,40 @@ int zb_ctx_destroy(zb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->comm_stream);
+  if (ctx->prof) { zb::prof_clear(ctx->prof); delete ctx->prof; }
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->err_flag) cudaFree(ctx->err_flag);
   cudaStreamDestroy(ctx->comm_stream);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return ZB_OK;
+}
+
+int zb_ctx_profile_enable(zb_ctx* ctx, int enable) {
+  if (!ctx->prof) ctx->prof = new zb::ProfState();
+  ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  zb::prof_clear(ctx->prof);
+  ctx->prof->enabled = enable != 0;
+  return ZB_OK;
+}
+
+int zb_ctx_profile_read(zb_ctx* ctx, int cls, int64_t* ops, double* total_ms, double* work) {
+  ZB_REQUIRE(cls >= 0 && cls < zb::PROF_NUM, "profile class out of range");
+  if (ops) *ops = 0;
+  if (total_ms) *total_ms = 0.0;
+  if (work) *work = 0.0;
+  if (!ctx->prof) return ZB_OK;
+  ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0, w = 0.0;
+  for (auto& r : ctx->prof->rec[cls]) {
+    float t = 0.f;
+    ZB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    w += r.work;
+  }
+  if (ops) *ops = static_cast<int64_t>(ctx->prof->rec[cls].size());
+  if (total_ms) *total_ms = ms;
+  if (work) *work = w;
   return ZB_OK;
 }
 

@@ -387,7 +387,10 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
   }
   const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
   const int grid = std::min(tiles, ctx->sm_count);
+  // algorithmic FLOPs of this launch: 2 * M * N * K over all taps (K counted in 32-wide blocks as issued)
+  prof_begin(ctx, PROF_TENSOR);
   umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
+  prof_end(ctx, PROF_TENSOR, p.prof_flops);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }
@@ -501,6 +504,7 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
   p.out_mode = OUT_ROWS;
   p.D = c;
   p.ldd = ldc;
+  p.prof_flops = 2.0 * m * n * k;
   finish_split_fields(p, pick_splits(ctx, static_cast<long long>(p.m_tiles) * p.n_tiles, p.kb_total, 8));
   return run_with_splits(ctx, bn, ma, mb, p, m, n, c, ldc, alpha, beta, bias);
 }
@@ -560,6 +564,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
       p.tap_h[r * d->kw + s] = static_cast<uint16_t>(r * d->dil_h);
     }
   p.kb_total = taps * p.c_chunks;
+  p.prof_flops = 2.0 * M * d->k * d->c * taps;  // = 2*N*P*Q*K*C*R*S
   p.out_mode = OUT_ROWS;
   p.D = y;
   p.ldd = d->k;
@@ -677,6 +682,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       p.tap_h[t] = static_cast<uint16_t>(cp.off_h[t]);
     }
     p.kb_total = cp.ntaps * p.c_chunks;
+    p.prof_flops = 2.0 * M * d->c * d->k * cp.ntaps;  // summed over parity classes = 2*N*P*Q*K*C*R*S up to borders
     p.D = dx;
     p.ldd = d->c;
     if (sh == 1 && sw == 1) {
@@ -743,6 +749,7 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       p.tap_h[r * d->kw + s] = static_cast<uint16_t>(r * d->dil_h);
     }
   p.kb_total = ceil_div(NPQ, kUmmaBK);
+  p.prof_flops = 2.0 * NPQ * d->k * d->c * taps;
   p.out_mode = OUT_ROWS;
   p.D = dw;
   p.ldd = static_cast<long long>(taps) * d->c;

@@ -49,6 +49,7 @@ struct UmmaParams {
   float alpha, beta;          // D = alpha*acc + bias + beta*D_old (splits == 1); partials store raw acc
   int scat_OH, scat_OW, scat_sy, scat_oy, scat_sx, scat_ox;  // OUT_SCATTER geometry
   int* err_flag;              // device word set to 1 on an mbarrier timeout
+  double prof_flops;          // host only: algorithmic FLOPs of this launch (profiling)
 };
 
 }  // namespace zb
