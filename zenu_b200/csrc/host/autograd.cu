@@ -417,6 +417,25 @@ Variable flatten(Runtime& rt, const Variable& x) {
   return make_output(x->data.view({s[0], rest}), fn);  // no copy (the reference copies, functions/flatten.rs:22-31)
 }
 
+// NHWC -> NCHW with gradient: used in front of flatten so that Linear sees the reference's C*H*W feature order
+struct ToNchwFn : Function {
+  const char* name() const override { return "nhwc_to_nchw"; }
+  void backward(Runtime& rt, const Tensor& gy) override {
+    const auto& s = inputs[0]->data.shape;  // NHWC
+    Tensor dx = grad_target(rt, *inputs[0]);
+    check_rc(zb_nchw_to_nhwc(rt.ctx, gy.dtype, gy.ptr, dx.ptr, s[0], s[3], s[1], s[2]), "to_nchw bwd");
+    commit_grad(rt, *inputs[0], dx);
+  }
+};
+Variable nhwc_to_nchw(Runtime& rt, const Variable& x) {
+  const auto& s = x.shape();
+  Tensor y = rt.empty({s[0], s[3], s[1], s[2]});
+  check_rc(zb_nhwc_to_nchw(rt.ctx, y.dtype, x->data.ptr, y.ptr, s[0], s[3], s[1], s[2]), "nhwc_to_nchw");
+  auto fn = std::make_shared<ToNchwFn>();
+  fn->inputs = {x.ptr()};
+  return make_output(y, fn);
+}
+
 Variable nchw_to_nhwc(Runtime& rt, const Variable& x) {
   const auto& s = x.shape();
   Tensor y = rt.empty({s[0], s[2], s[3], s[1]});
@@ -531,7 +550,7 @@ struct SmallCnn : Model {
     h = fused ? bn1->call_fused(rt, h, nullptr, true) : relu(rt, bn1->call(rt, h));
     h = conv2->call(rt, h);
     h = fused ? bn2->call_fused(rt, h, nullptr, true) : relu(rt, bn2->call(rt, h));
-    h = flatten(rt, h);
+    h = flatten(rt, nhwc_to_nchw(rt, h));  // reference feature order: [N, C*H*W] (functions/flatten.rs)
     h = relu(rt, linear1->call(rt, h));
     return linear2->call(rt, h);
   }

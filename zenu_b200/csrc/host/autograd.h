@@ -143,6 +143,7 @@ Variable max_pool_2d(Runtime& rt, const Variable& x, int64_t k, int64_t stride, 
 Variable global_avg_pool(Runtime& rt, const Variable& x);
 Variable flatten(Runtime& rt, const Variable& x);  // [N,H,W,C] -> [N, H*W*C] view
 Variable nchw_to_nhwc(Runtime& rt, const Variable& x);
+Variable nhwc_to_nchw(Runtime& rt, const Variable& x);  // differentiable
 Variable softmax_cross_entropy(Runtime& rt, const Variable& logits, const Tensor& targets);  // scalar loss
 
 // ---- layers ----------------------------------------------------------------------------------------------
