@@ -218,6 +218,11 @@ int zb_model_update(zb_model* m); /* Optimizer::update */
 /* forward_backward + update; if host_loss != NULL the loss is copied back (synchronises the stream) */
 int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
                         int64_t h, int64_t w, void* loss_dev, double* host_loss);
+/* Per-node timing (CUDA events on the compute stream around every tape node, forward and backward).  dump writes one
+ * line per distinct node key: "key\tcount\ttotal_ms\talgorithmic_flops\talgorithmic_bytes\n" (sums over count) and returns
+ * the buffer size needed (call with buf == NULL to size it). */
+int zb_model_profile_enable(zb_model* m, int enable);
+int64_t zb_model_profile_dump(zb_model* m, char* buf, int64_t cap);
 /* bytes currently held by the model's caching allocator (activations + parameters) */
 int64_t zb_model_bytes_reserved(zb_model* m);
 

@@ -71,6 +71,41 @@ Tensor Runtime::borrow(void* p, std::vector<int64_t> shape) {
   return t;
 }
 
+// ------------------------------------------------------------------------------------------------ per-node timing
+void OpProfiler::clear() {
+  for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  recs.clear();
+}
+ProfScope::ProfScope(Runtime& r, std::string key, double flops, double bytes) : rt(r) {
+  if (!rt.prof.enabled) return;
+  OpProfiler::Rec rec{std::move(key), nullptr, nullptr, flops, bytes};
+  cudaEventCreate(&rec.a);
+  cudaEventCreate(&rec.b);
+  cudaEventRecord(rec.a, rt.ctx->stream);
+  idx = rt.prof.recs.size();
+  rt.prof.recs.push_back(std::move(rec));
+}
+ProfScope::~ProfScope() {
+  if (idx != static_cast<size_t>(-1)) cudaEventRecord(rt.prof.recs[idx].b, rt.ctx->stream);
+}
+static std::string shape_str(const std::vector<int64_t>& s) {
+  std::string o;
+  for (size_t i = 0; i < s.size(); ++i) o += (i ? "x" : "") + std::to_string(s[i]);
+  return o;
+}
+static std::string conv_key(const char* pass, const zb_conv2d_desc& d) {
+  return std::string("conv.") + pass + " n" + std::to_string(d.n) + " c" + std::to_string(d.c) + " hw" + std::to_string(d.h) + " k" +
+         std::to_string(d.k) + " r" + std::to_string(d.kh) + " s" + std::to_string(d.stride_h);
+}
+static double conv_flops(const zb_conv2d_desc& d) {
+  const double P = zb_conv_out_size(d.h, d.kh, d.pad_h, d.stride_h, d.dil_h), Q = zb_conv_out_size(d.w, d.kw, d.pad_w, d.stride_w, d.dil_w);
+  return 2.0 * d.n * P * Q * d.k * d.c * d.kh * d.kw;
+}
+static double conv_bytes(const zb_conv2d_desc& d, size_t esz) {
+  const double P = zb_conv_out_size(d.h, d.kh, d.pad_h, d.stride_h, d.dil_h), Q = zb_conv_out_size(d.w, d.kw, d.pad_w, d.stride_w, d.dil_w);
+  return esz * (static_cast<double>(d.n) * d.h * d.w * d.c + static_cast<double>(d.k) * d.kh * d.kw * d.c + static_cast<double>(d.n) * P * Q * d.k);
+}
+
 // ------------------------------------------------------------------------------------------------ tape
 Variable Variable::leaf(Tensor t, bool requires_grad, std::string name) {
   auto p = std::make_shared<VariableInner>();
@@ -107,6 +142,7 @@ Tensor grad_target(Runtime& rt, VariableInner& v) {
 void commit_grad(Runtime& rt, VariableInner& v, const Tensor& g) {
   if (!v.grad.defined()) {
     if (v.is_param && v.grad_slot.defined() && g.ptr != v.grad_slot.ptr) {
+      ProfScope ps(rt, "grad.copy", 0.0, 2.0 * g.bytes());
       check_rc(zb_copy(rt.ctx, g.dtype, g.ptr, v.grad_slot.ptr, g.numel()), "grad copy");
       v.grad = v.grad_slot;
     } else {
@@ -116,6 +152,7 @@ void commit_grad(Runtime& rt, VariableInner& v, const Tensor& g) {
     return;
   }
   // second arrival: grad + old (lib.rs:480-481)
+  ProfScope ps(rt, "grad.accumulate " + shape_str(v.data.shape), 0.0, 3.0 * g.bytes());
   if (v.is_param || (v.grad.storage && v.grad.storage.use_count() == 1)) {
     check_rc(zb_binary(rt.ctx, g.dtype, ZB_OP_ADD, v.grad.ptr, g.ptr, v.grad.ptr, g.numel()), "grad accumulate");
   } else {
@@ -190,6 +227,7 @@ struct ConvFn : Function {
     VariableInner& wv = *inputs[1];
     if (wv.requires_grad) {
       Tensor dw = grad_target(rt, wv);
+      ProfScope ps(rt, conv_key("wgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
       check_rc(zb_conv2d_wgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, x.ptr, dw.ptr), "conv wgrad");
       commit_grad(rt, wv, dw);
     }
@@ -202,6 +240,7 @@ struct ConvFn : Function {
     }
     if (need_dx && (xv.requires_grad || xv.creator)) {
       Tensor dx = grad_target(rt, xv);
+      ProfScope ps(rt, conv_key("dgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
       check_rc(zb_conv2d_dgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, dx.ptr), "conv dgrad");
       commit_grad(rt, xv, dx);
     }
@@ -217,8 +256,11 @@ Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variabl
   fn->d = zb_conv2d_desc{xs[0], xs[3], xs[1], xs[2], ws[0], ws[1], ws[2], a.pad_h, a.pad_w, a.stride_h, a.stride_w, a.dil_h, a.dil_w};
   const int64_t P = out_size(xs[1], ws[1], a.pad_h, a.stride_h, a.dil_h), Q = out_size(xs[2], ws[2], a.pad_w, a.stride_w, a.dil_w);
   Tensor y = rt.empty({xs[0], P, Q, ws[0]});
-  check_rc(zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
-                           bias ? (*bias)->data.ptr : nullptr, y.ptr), "conv fprop");
+  {
+    ProfScope ps(rt, conv_key("fprop", fn->d), conv_flops(fn->d), conv_bytes(fn->d, y.elem_size()));
+    check_rc(zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
+                             bias ? (*bias)->data.ptr : nullptr, y.ptr), "conv fprop");
+  }
   fn->inputs = {x.ptr(), w.ptr()};
   if (bias) fn->inputs.push_back(bias->ptr());
   fn->has_bias = bias != nullptr;
@@ -246,6 +288,8 @@ struct BnFn : Function {
       if (inputs[3]->grad.defined()) dres = rt.empty(inputs[3]->data.shape);
       dres_ptr = dres.ptr;
     }
+    ProfScope ps(rt, std::string("bn.bwd") + (relu ? "+relu" : "") + (has_res ? "+res" : "") + " " + shape_str(x.shape), 0.0,
+                 static_cast<double>(x.bytes()) * (5.0 + (relu ? 2.0 : 0.0) + (has_res && relu ? 1.0 : 0.0)));
     check_rc(zb_bn2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
                          ds.ptr, db.ptr, relu ? y.ptr : nullptr, dres_ptr), "bn bwd");
     commit_grad(rt, xv, dx);
@@ -274,6 +318,8 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   auto fn = std::make_shared<BnFn>();
   fn->saved_mean = rt.empty({c});
   fn->saved_inv = rt.empty({c});
+  ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
+               static_cast<double>(y.bytes()) * (residual ? 4.0 : 3.0));
   check_rc(zb_bn2d_fwd_train(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
                              mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
                              residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0), "bn fwd");
@@ -293,6 +339,7 @@ struct ReluFn : Function {
   const char* name() const override { return "relu"; }
   void backward(Runtime& rt, const Tensor& gy) override {
     Tensor dx = grad_target(rt, *inputs[0]);
+    ProfScope ps(rt, "relu.bwd " + shape_str(x.shape), 0.0, 3.0 * x.bytes());
     check_rc(zb_relu_bwd(rt.ctx, gy.dtype, x.ptr, gy.ptr, dx.ptr, 0.0, gy.numel()), "relu bwd");
     commit_grad(rt, *inputs[0], dx);
     x = Tensor();
@@ -300,6 +347,7 @@ struct ReluFn : Function {
 };
 Variable relu(Runtime& rt, const Variable& x) {
   Tensor y = rt.empty(x.shape());
+  ProfScope ps(rt, "relu.fwd " + shape_str(x.shape()), 0.0, 2.0 * y.bytes());
   check_rc(zb_relu(rt.ctx, y.dtype, x->data.ptr, y.ptr, 0.0, y.numel()), "relu");
   auto fn = std::make_shared<ReluFn>();
   fn->inputs = {x.ptr()};
@@ -317,6 +365,7 @@ struct AddFn : Function {
 Variable add(Runtime& rt, const Variable& a, const Variable& b) {
   if (a.shape() != b.shape()) throw HostError("add: shape mismatch");
   Tensor y = rt.empty(a.shape());
+  ProfScope ps(rt, "add.fwd " + shape_str(a.shape()), 0.0, 3.0 * y.bytes());
   check_rc(zb_binary(rt.ctx, y.dtype, ZB_OP_ADD, a->data.ptr, b->data.ptr, y.ptr, y.numel()), "add");
   auto fn = std::make_shared<AddFn>();
   fn->inputs = {a.ptr(), b.ptr()};
@@ -336,6 +385,8 @@ struct LinearFn : Function {
     Tensor dx;
     const bool want_dx = xv.requires_grad || xv.creator;
     if (want_dx) dx = grad_target(rt, xv);
+    ProfScope ps(rt, "linear.bwd " + std::to_string(b) + "x" + std::to_string(in_f) + "x" + std::to_string(out_f),
+                 (want_dx ? 4.0 : 2.0) * b * in_f * out_f, 0.0);
     check_rc(zb_linear_bwd(rt.ctx, gy.dtype, ZB_MATH_DEFAULT, x.ptr, w.ptr, gy.ptr, want_dx ? dx.ptr : nullptr, dw.ptr,
                            has_bias ? db.ptr : nullptr, b, in_f, out_f), "linear bwd");
     commit_grad(rt, *inputs[1], dw);
@@ -349,6 +400,8 @@ Variable linear(Runtime& rt, const Variable& x, const Variable& w, const Variabl
   const auto& ws = w.shape();
   if (xs.size() != 2 || ws.size() != 2 || xs[1] != ws[1]) throw HostError("linear: bad shapes");
   Tensor y = rt.empty({xs[0], ws[0]});
+  ProfScope ps(rt, "linear.fwd " + std::to_string(xs[0]) + "x" + std::to_string(xs[1]) + "x" + std::to_string(ws[0]),
+               2.0 * xs[0] * xs[1] * ws[0], 0.0);
   check_rc(zb_linear_fwd(rt.ctx, y.dtype, ZB_MATH_DEFAULT, x->data.ptr, w->data.ptr, bias ? (*bias)->data.ptr : nullptr, y.ptr,
                          xs[0], xs[1], ws[0]), "linear fwd");
   auto fn = std::make_shared<LinearFn>();
@@ -367,6 +420,7 @@ struct MaxPoolFn : Function {
   const char* name() const override { return "max_pool_2d"; }
   void backward(Runtime& rt, const Tensor& gy) override {
     Tensor dx = grad_target(rt, *inputs[0]);
+    ProfScope ps(rt, "maxpool.bwd " + shape_str(x.shape), 0.0, 2.0 * x.bytes() + gy.bytes());
     check_rc(zb_maxpool2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, x.ptr, gy.ptr, dx.ptr, n, c, h, w, k, k, stride, stride, pad, pad), "maxpool bwd");
     commit_grad(rt, *inputs[0], dx);
     x = Tensor();
@@ -376,6 +430,7 @@ Variable max_pool_2d(Runtime& rt, const Variable& x, int64_t k, int64_t stride, 
   const auto& s = x.shape();
   const int64_t P = (s[1] + 2 * pad - k) / stride + 1, Q = (s[2] + 2 * pad - k) / stride + 1;
   Tensor y = rt.empty({s[0], P, Q, s[3]});
+  ProfScope ps(rt, "maxpool.fwd " + shape_str(s), 0.0, static_cast<double>(x->data.bytes() + y.bytes()));
   check_rc(zb_maxpool2d_fwd(rt.ctx, y.dtype, ZB_NHWC, x->data.ptr, y.ptr, s[0], s[3], s[1], s[2], k, k, stride, stride, pad, pad), "maxpool");
   auto fn = std::make_shared<MaxPoolFn>();
   fn->inputs = {x.ptr()};
@@ -389,6 +444,7 @@ struct GapFn : Function {
   const char* name() const override { return "global_avg_pool"; }
   void backward(Runtime& rt, const Tensor& gy) override {
     Tensor dx = grad_target(rt, *inputs[0]);
+    ProfScope ps(rt, "gap.bwd", 0.0, static_cast<double>(dx.bytes()));
     check_rc(zb_gap_bwd(rt.ctx, gy.dtype, ZB_NHWC, gy.ptr, dx.ptr, n, c, hw), "gap bwd");
     commit_grad(rt, *inputs[0], dx);
   }
@@ -396,6 +452,7 @@ struct GapFn : Function {
 Variable global_avg_pool(Runtime& rt, const Variable& x) {
   const auto& s = x.shape();
   Tensor y = rt.empty({s[0], s[3]});
+  ProfScope ps(rt, "gap.fwd", 0.0, static_cast<double>(x->data.bytes()));
   check_rc(zb_gap_fwd(rt.ctx, y.dtype, ZB_NHWC, x->data.ptr, y.ptr, s[0], s[3], s[1] * s[2]), "gap");
   auto fn = std::make_shared<GapFn>();
   fn->inputs = {x.ptr()};
@@ -439,6 +496,7 @@ Variable nhwc_to_nchw(Runtime& rt, const Variable& x) {
 Variable nchw_to_nhwc(Runtime& rt, const Variable& x) {
   const auto& s = x.shape();
   Tensor y = rt.empty({s[0], s[2], s[3], s[1]});
+  ProfScope ps(rt, "input.nchw_to_nhwc " + shape_str(s), 0.0, 2.0 * y.bytes());
   check_rc(zb_nchw_to_nhwc(rt.ctx, y.dtype, x->data.ptr, y.ptr, s[0], s[1], s[2], s[3]), "nchw_to_nhwc");
   // The reference computes the input gradient of every conv, the first one included (conv_without_bias.rs:110-121);
   // marking the network input as requiring a gradient keeps that work in the step.
@@ -459,6 +517,7 @@ Variable softmax_cross_entropy(Runtime& rt, const Variable& logits, const Tensor
   auto fn = std::make_shared<XentFn>();
   const bool need = logits->requires_grad;
   if (need) fn->dz = rt.empty(s);
+  ProfScope ps(rt, "softmax_xent " + shape_str(s), 0.0, 3.0 * logits->data.bytes());
   check_rc(zb_softmax_xent(rt.ctx, loss.dtype, logits->data.ptr, targets.ptr, loss.ptr, need ? fn->dz.ptr : nullptr, s[0], s[1]), "softmax_xent");
   fn->inputs = {logits.ptr()};
   return make_output(loss, fn);
@@ -762,11 +821,13 @@ void Optimizer::init(Runtime& rt, ParamStore& ps) {
   step = 0;
 }
 
+static double ps_bytes(const ParamStore& ps) { return static_cast<double>(ps.flat_params.bytes()); }
 void Optimizer::update(Runtime& rt, ParamStore& ps) {
   check_rc(zb_dp_wait(rt.ctx), "dp wait");
   const double gscale = 1.0 / static_cast<double>(std::max(1, zb_dp_world(rt.ctx)));
   const size_t esz = rt.dtype == ZB_F64 ? 8 : 4;
   ++step;
+  ProfScope scope(rt, "optimizer.update", 0.0, 3.0 * ps_bytes(ps));
   auto at = [&](const Tensor& t, int64_t off) { return static_cast<void*>(static_cast<uint8_t*>(t.ptr) + off * esz); };
   if (kind == OPT_SGD) {
     // p -= lr * g over the whole flat buffer (sgd.rs:20-30), gradient averaging folded in

@@ -70,15 +70,32 @@ struct Tensor {
   Tensor view(std::vector<int64_t> new_shape) const { Tensor t = *this; t.shape = std::move(new_shape); return t; }
 };
 
+// Optional per-node timing (CUDA events on the compute stream), keyed by "op.pass shape"; bench.py's per-layer table.
+struct OpProfiler {
+  struct Rec { std::string key; cudaEvent_t a, b; double flops, bytes; };
+  bool enabled = false;
+  std::vector<Rec> recs;
+  void clear();
+  ~OpProfiler() { clear(); }
+};
+
 struct Runtime {  // one per model: ctx + allocator + train flag (reference: global is_train, lib.rs:58-79)
   zb_ctx* ctx;
   Allocator alloc;
   bool train = true;
   int dtype = ZB_F32;
+  OpProfiler prof;
   explicit Runtime(zb_ctx* c) : ctx(c), alloc(c) {}
   Tensor empty(std::vector<int64_t> shape);
   Tensor zeros(std::vector<int64_t> shape);
   Tensor borrow(void* p, std::vector<int64_t> shape);  // non-owning
+};
+
+struct ProfScope {  // RAII: records an event pair around the kernels a node enqueues
+  Runtime& rt;
+  size_t idx = static_cast<size_t>(-1);
+  ProfScope(Runtime& r, std::string key, double flops = 0.0, double bytes = 0.0);
+  ~ProfScope();
 };
 
 // ---- tape ------------------------------------------------------------------------------------------

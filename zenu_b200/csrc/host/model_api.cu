@@ -1,5 +1,9 @@
 // model_api.cu — extern "C" face of the host model (see include/zenu_b200.h "host model API").
+#include <algorithm>
 #include <cstring>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "autograd.h"
 
@@ -156,6 +160,40 @@ int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, in
     }
   }
   return ZB_OK;
+}
+
+int zb_model_profile_enable(zb_model* m, int enable) {
+  ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  m->rt->prof.clear();
+  m->rt->prof.enabled = enable != 0;
+  return ZB_OK;
+}
+
+int64_t zb_model_profile_dump(zb_model* m, char* buf, int64_t cap) {
+  cudaStreamSynchronize(m->ctx->stream);
+  struct Agg { int64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : m->rt->prof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (!agg.count(r.key)) order.push_back(r.key);
+    Agg& a = agg[r.key];
+    a.n++; a.ms += t; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  std::string out;
+  char line[512];
+  for (auto& k : order) {
+    const Agg& a = agg[k];
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.6e\t%.6e\n", k.c_str(), static_cast<long long>(a.n), a.ms, a.flops, a.bytes);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(out.size(), static_cast<size_t>(cap - 1));
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return static_cast<int64_t>(out.size() + 1);
 }
 
 int64_t zb_model_bytes_reserved(zb_model* m) { return static_cast<int64_t>(m->rt->alloc.bytes_reserved()); }

@@ -36,9 +36,10 @@ class Model:
         check(self.lib.zb_model_create(ctx.handle, arch.encode(), self._zdt, self.num_classes, int(bool(fused)), int(seed),
                                        int(bucket_mb) << 20, ctypes.byref(self._h)))
         self._params = None
+        ctx._children.add(self)
 
     def close(self):
-        if self._h:
+        if self._h and self.ctx.handle:
             self.lib.zb_model_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -111,6 +112,21 @@ class Model:
         check(self.lib.zb_model_train_step(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(targets.data_ptr()), n, c, h, w,
                                            ctypes.c_void_p(loss.data_ptr()), ctypes.byref(host) if read_loss else None))
         return host.value if read_loss else loss
+
+    def profile(self, enable=True):
+        """Per-node CUDA-event timing of the tape (forward and backward nodes), see `profile_table`."""
+        check(self.lib.zb_model_profile_enable(self._h, int(bool(enable))))
+
+    def profile_table(self):
+        """[(key, count, total_ms, algorithmic_flops, algorithmic_bytes)] accumulated since profile(True)."""
+        need = int(self.lib.zb_model_profile_dump(self._h, None, 0))
+        buf = ctypes.create_string_buffer(need + 16)
+        self.lib.zb_model_profile_dump(self._h, buf, need + 16)
+        rows = []
+        for ln in buf.value.decode().splitlines():
+            k, n, ms, fl, by = ln.split("\t")
+            rows.append((k, int(n), float(ms), float(fl), float(by)))
+        return rows
 
     def bytes_reserved(self):
         return int(self.lib.zb_model_bytes_reserved(self._h))

@@ -8,6 +8,7 @@ memory; every op is one call into libzenu_b200.so on the Context's stream.  Shap
 `ZenuB200Error` (the reference panics in shape_check, nn/conv/shape_check.rs:4-53).
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -33,6 +34,7 @@ class Context:
         self.device = torch.cuda.current_device() if device is None else int(device)
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream().cuda_stream
+        self._children = weakref.WeakSet()   # models created on this ctx: destroyed before the ctx (they use its streams)
         self._h = ctypes.c_void_p()
         check(self.lib.zb_ctx_create(ctypes.byref(self._h), self.device,
                                      ctypes.c_void_p(s if s != 0 else _lib.CUDA_STREAM_LEGACY)))
@@ -44,6 +46,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             self.lib.zb_ctx_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -96,6 +100,8 @@ def conv_out_shape(x_shape, w_shape, layout, pad, stride, dil):
     lib = _lib.load()
     p = lib.zb_conv_out_size(d.h, d.kh, d.pad_h, d.stride_h, d.dil_h)
     q = lib.zb_conv_out_size(d.w, d.kw, d.pad_w, d.stride_w, d.dil_w)
+    if p <= 0 or q <= 0 or d.h + 2 * d.pad_h < d.dil_h * (d.kh - 1) + 1 or d.w + 2 * d.pad_w < d.dil_w * (d.kw - 1) + 1:
+        raise ZenuB200Error("conv: filter larger than the padded input (zenu-matrix/src/nn/conv/shape_check.rs:4-53)")
     return (d.n, d.k, p, q) if layout == ZB_NCHW else (d.n, p, q, d.k)
 
 
