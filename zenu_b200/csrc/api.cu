@@ -13,6 +13,9 @@ bool umma_conv_supported(const zb_conv2d_desc*);
 int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*);
 int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
 int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+bool umma_conv_smallc_supported(const zb_conv2d_desc*);
+int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*);
+int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*);
 // conv_simt.cu
 template <typename T> int simt_conv_fprop(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, const T*, T*);
 template <typename T> int simt_conv_dgrad(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, T*);
@@ -79,6 +82,8 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* wf = static_cast<const float*>(w);
   const float* bf = static_cast<const float*>(bias);
   float* yf = static_cast<float*>(y);
+  if (m == ZB_MATH_TF32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
+    return umma_conv_smallc_fprop(ctx, d, xf, 0, wf, bf, yf);
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_fprop<float>(ctx, layout, d, xf, wf, bf, yf);
   if (layout == ZB_NHWC) return umma_conv_fprop_nhwc(ctx, d, xf, wf, bf, yf);
   // NCHW contract: stage through NHWC / KRSC
@@ -107,7 +112,7 @@ int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* gf = static_cast<const float*>(dy);
   const float* wf = static_cast<const float*>(w);
   float* df = static_cast<float*>(dx);
-  const bool tc_ok = (d->k % 32 == 0) && (d->c % 4 == 0) && d->kh * d->kw <= 64;
+  const bool tc_ok = (d->k % 32 == 0) && d->kh * d->kw <= 64 && (layout == ZB_NHWC || d->c % 4 == 0);
   if (m == ZB_MATH_FP32 || !tc_ok) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
   if (layout == ZB_NHWC) {
     rc = umma_conv_dgrad_nhwc(ctx, d, gf, wf, df);
@@ -141,6 +146,7 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* gf = static_cast<const float*>(dy);
   const float* xf = static_cast<const float*>(x);
   float* wf = static_cast<float*>(dw);
+  if (m == ZB_MATH_TF32 && layout == ZB_NHWC && umma_conv_smallc_supported(d)) return umma_conv_smallc_wgrad(ctx, d, gf, xf, 0, wf);
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_wgrad<float>(ctx, layout, d, gf, xf, wf);
   if (layout == ZB_NHWC) return umma_conv_wgrad_nhwc(ctx, d, gf, xf, wf);
   Temp tg(ctx), tx(ctx), tw(ctx);

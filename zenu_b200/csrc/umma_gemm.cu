@@ -32,7 +32,9 @@ struct UmmaSmem {
   static constexpr int A_BYTES = kUmmaBM * kUmmaBK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * kUmmaBK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;   // 4 warps x [32 rows][32 cols] fp32 staging (coalesced stores)
+  static constexpr int EPI_BYTES = 4 * 4096;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -117,10 +119,19 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           a_w = p.lower_w + qq * p.stride_w;
           a_h = p.lower_h + pp * p.stride_h;
           a_n = img;
+        } else if (p.a_mode == A_WINDOW_K) {
+          const int per_img = p.win_p_tiles * p.win_q_tiles;
+          const int img = tc.m_blk / per_img, rem = tc.m_blk - img * per_img;
+          const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
+          a_w = qt * p.win_box_q;                                   // first output column of the tile
+          a_h = pt * p.win_box_p * p.stride_h + p.lower_h;          // input row of filter row 0
+          a_n = img;
         }
         const int a_boxes = a_mn ? min(4, (p.M - m0 + 31) / 32) : 0;
         const int b_boxes = b_mn ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
-        const uint32_t bytes = (a_mn ? a_boxes * 4096u : uint32_t(L::A_BYTES)) + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
+        const uint32_t a_bytes = a_mn ? a_boxes * 4096u
+                                      : (p.a_mode == A_WINDOW_K ? uint32_t(p.win_box_q * p.win_box_p) * 128u : uint32_t(L::A_BYTES));
+        const uint32_t bytes = a_bytes + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
         bool ok = true;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (!mbar_wait(&empty_bar[stage], phase ^ 1, err)) { ok = false; break; }
@@ -133,8 +144,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (p.a_mode == A_IM2COL_K) {
             const int tap = kb / p.c_chunks, c0 = (kb - tap * p.c_chunks) * kUmmaBK;
             tma_load_im2col_4d(sA, &tmA, &full_bar[stage], c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
+          } else if (p.a_mode == A_WINDOW_K) {
+            tma_load_4d(sA, &tmA, &full_bar[stage], 0, a_w, a_h + p.tap_h[kb], a_n);   // kb = filter row
           } else {
-            for (int j = 0; j < a_boxes; ++j) tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, kb * kUmmaBK);
+            int pix = kb * kUmmaBK;
+            if (p.b_mode == B_WINDOW_MN) {  // K blocks are 32-pixel runs inside one output row
+              const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
+              pix = row * p.conv_Q + qb * 32;
+            }
+            for (int j = 0; j < a_boxes; ++j) tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, pix);
           }
           // ---- B operand
           if (p.b_mode == B_TILED_K) {
@@ -146,6 +164,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
           } else if (p.b_mode == B_TILED_MN) {
             for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK);
+          } else if (p.b_mode == B_WINDOW_MN) {  // K index = pixel (32-pixel run of one output row), N index = window element
+            const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
+            const int img = row / p.conv_P, pp = row - img * p.conv_P;
+            tma_load_4d(sB, &tmB, &full_bar[stage], 0, qb * 32, pp * p.stride_h + p.lower_h + p.tap_h[tc.tap], img);
           } else {  // B_IM2COL_MN: K index = base pixel, N index = channel
             const int pix = kb * kUmmaBK;
             const int img = pix / pq, rem = pix - img * pq;
@@ -199,27 +221,49 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ================================ epilogue ================================
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter).  Per 32-column chunk: tcgen05.ld (lane = row) ->
+    // XOR-swizzled smem staging -> read back so that 8 lanes cover one row's 128 bytes -> coalesced 128-bit global
+    // stores (4 full cache lines per instruction) with alpha / bias / beta applied on the way out.
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4* stage4 = reinterpret_cast<float4*>(smem + L::EPI_OFFSET + ew * 4096);
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
     const bool partial = p.splits > 1;
+    const int sub_row = lane >> 3, piece = lane & 7;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
+      // element offset of this lane's row inside D (or -1 when the row does not exist)
+      long long my_off = -1;
+      {
+        const int l = ew * 32 + lane;
+        if (p.out_mode == OUT_WINDOW) {
+          const int per_img = p.win_p_tiles * p.win_q_tiles;
+          const int img = tc.m_blk / per_img, rem = tc.m_blk - img * per_img;
+          const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
+          const int pl = l / p.win_box_q, ql = l - pl * p.win_box_q;
+          const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
+          if (pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
+            my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
+        } else {
+          const int row = m0 + l;
+          if (row < p.M) {
+            long long orow = row;
+            if (p.out_mode == OUT_SCATTER) {
+              const int pq = p.conv_P * p.conv_Q;
+              const int img = row / pq, rem = row - img * pq;
+              const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+              orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
+            }
+            my_off = orow * p.ldd;
+          }
+        }
+        if (my_off >= 0) my_off += static_cast<long long>(tc.split) * p.split_stride + tc.tap * p.tap_col_stride;
+      }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
       tc_fence_after();
-      const int row = m0 + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      long long orow = row;
-      if (p.out_mode == OUT_SCATTER && row_ok) {
-        const int pq = p.conv_P * p.conv_Q;
-        const int img = row / pq, rem = row - img * pq;
-        const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
-        orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
-      }
-      float* drow = p.D + static_cast<long long>(tc.split) * p.split_stride + orow * p.ldd + tc.tap * p.tap_col_stride;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -227,39 +271,47 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
         tmem_ld_wait();
-        if (row_ok) {
-          float* dst = drow + col0;
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float o[4];
+        for (int v = 0; v < 8; ++v)
+          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+        __syncwarp();
+        const int col = col0 + piece * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!partial && p.bias != nullptr) {
+          if (col < p.N) bv.x = __ldg(p.bias + col);
+          if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
+          if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
+          if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(r[v * 4 + e]);
-            const int col = col0 + v * 4;
-            if (!partial) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float val = p.alpha * o[e];
-                if (p.bias != nullptr && col + e < p.N) val += __ldg(p.bias + col + e);
-                o[e] = val;
-              }
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub_row;
+          const long long off = __shfl_sync(0xffffffffu, my_off, rr);
+          float4 o = stage4[rr * 8 + (piece ^ (rr & 7))];
+          if (off < 0 || col >= p.N) continue;
+          float* dst = p.D + off + col;
+          if (!partial) {
+            o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
+          }
+          if (vec_ok && col + 3 < p.N) {
+            if (!partial && p.beta != 0.f) {
+              const float4 old = *reinterpret_cast<const float4*>(dst);
+              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
             }
-            if (vec_ok && col + 3 < p.N) {
-              if (!partial && p.beta != 0.f) {
-                const float4 old = *reinterpret_cast<const float4*>(dst + v * 4);
-                o[0] += p.beta * old.x; o[1] += p.beta * old.y; o[2] += p.beta * old.z; o[3] += p.beta * old.w;
-              }
-              *reinterpret_cast<float4*>(dst + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + e < p.N) {
-                  float val = o[e];
-                  if (!partial && p.beta != 0.f) val += p.beta * dst[v * 4 + e];
-                  dst[v * 4 + e] = val;
-                }
-            }
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) {
+                float val = ov[e];
+                if (!partial && p.beta != 0.f) val += p.beta * dst[e];
+                dst[e] = val;
+              }
           }
         }
+        __syncwarp();  // staging is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -395,10 +447,11 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
   return ZB_OK;
 }
 
-static int pick_bn(long long n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
+static int pick_bn(long long n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
 
 static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   switch (bn) {
+    case 32: return launch_cfg<32, 10>(ctx, a, b, p);
     case 64: return launch_cfg<64, 8>(ctx, a, b, p);
     case 128: return launch_cfg<128, 6>(ctx, a, b, p);
     default: return launch_cfg<256, 4>(ctx, a, b, p);
@@ -575,7 +628,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
 // dx[N,H,W,C] = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Stride 1: one implicit GEMM over dy with the flipped filter.
 // Stride s > 1: one implicit GEMM per output parity class (h % s, w % s), scattered into dx.
 int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx) {
-  if (d->k % 32 != 0 || d->c % 4 != 0 || d->kh * d->kw > kUmmaMaxTaps) {
+  if (d->k % 32 != 0 || d->kh * d->kw > kUmmaMaxTaps) {
     set_last_error("umma dgrad: shape unsupported");
     return ZB_ERR_UNSUPPORTED;
   }
@@ -774,6 +827,207 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
   splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ws), dw, rows, cols, cols, rows * cols,
                                                       q.splits, 1.f, 0.f, nullptr);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- small-C conv
+// Convs with C <= 4 input channels (the 7x7/s2 ResNet stem, the first layer of the CIFAR CNN): a 32-channel K block
+// does not exist, so the input is repacked once into zero-padded NHWC4 rows [N][H][Wp][4] and one K block is the
+// 32-float sliding window "8 taps x 4 channels of one filter row" starting at padded column q*stride_w.  Consecutive
+// output pixels' windows overlap in memory; a tiled tensor map whose q-dimension stride (16*stride_w bytes) is smaller
+// than the window (128 bytes) expresses exactly that, so one TMA box still lands a [pixels][32] K-major tile.
+// Filter rows are the GEMM-K blocks (K = R x 32, taps s >= S and channel 3 carry zero weights).
+bool umma_conv_smallc_supported(const zb_conv2d_desc* d) {
+  return d->c <= 4 && d->kw <= 8 && d->dil_w == 1 && d->kh <= kUmmaMaxTaps && d->k % 4 == 0 && d->pad_h <= 127 &&
+         d->dil_h * (d->kh - 1) <= 255;
+}
+
+// xp[n][h][wp][0..3] = x[n][c][h][wp - pad_w] (zero outside); src is NHWC (c_stride 1) or NCHW
+__global__ void smallc_pack_input_kernel(const float* __restrict__ x, float4* __restrict__ xp, long long N, int C, int H, int W,
+                                         int Wp, int pad_w, int nchw) {
+  const long long total = N * H * Wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wp = static_cast<int>(i % Wp);
+    const long long nh = i / Wp;
+    const int w = wp - pad_w;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (w >= 0 && w < W) {
+      if (nchw) {
+        const long long n = nh / H, h = nh - n * H;
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + ((n * C + c) * H + h) * W + w);
+      } else {
+        const float* src = x + (nh * W + w) * C;
+        for (int c = 0; c < C; ++c) v[c] = __ldg(src + c);
+      }
+    }
+    xp[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// wp[k][r][s*4+c] = w[k][r][s][c] (KRSC), zero elsewhere
+__global__ void smallc_pack_filter_kernel(const float* __restrict__ w, float* __restrict__ wp, int K, int R, int S, int C) {
+  const int total = K * R * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 31, kr = i >> 5;
+    const int sidx = j >> 2, c = j & 3;
+    wp[i] = (sidx < S && c < C) ? w[(static_cast<long long>(kr) * S + sidx) * C + c] : 0.f;
+  }
+}
+// dw[k][r][s][c] = alpha-free sum over split partials of dwp[split][k][r][s*4+c]
+__global__ void smallc_unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K, int R, int S, int C,
+                                        int splits, long long split_stride) {
+  const int total = K * R * S * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int sidx = (i / C) % S;
+    const int kr = i / (C * S);
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += dwp[sp * split_stride + static_cast<long long>(kr) * 32 + sidx * 4 + c];
+    dw[i] = acc;
+  }
+}
+
+static int make_map_window(zb_ctx* ctx, CUtensorMap* map, const float* base, long long N, long long H, long long Wp,
+                           long long Q, int stride_w, int box_q, int box_p, bool mn_major) {
+  cuuint64_t dims[4] = {32, static_cast<cuuint64_t>(Q), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride_w) * 16, static_cast<cuuint64_t>(Wp) * 16,
+                           static_cast<cuuint64_t>(H) * Wp * 16};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(box_q), static_cast<cuuint32_t>(box_p), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(map, operand_dtype(), 4, const_cast<float*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (sliding window) failed (%d): N=%lld H=%lld Wp=%lld Q=%lld stride=%d box=%dx%d", int(r), N, H,
+                   Wp, Q, stride_w, box_q, box_p);
+    return ZB_ERR_CUDA;
+  }
+  return ZB_OK;
+}
+
+struct SmallcGeom {
+  long long P, Q, Wp;
+  size_t xp_bytes, wp_bytes;
+};
+static SmallcGeom smallc_geom(const zb_conv2d_desc* d) {
+  SmallcGeom g;
+  g.P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  g.Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  // padded row: pad_w zero pixels, the W data pixels, then zeros so that the last window (8 pixels from padded column
+  // (Q-1)*stride_w) stays inside the row; window rows with q >= Q are out of the map's bounds and never touch memory
+  g.Wp = std::max<long long>(d->pad_w + d->w, (g.Q - 1) * d->stride_w + 8);
+  g.xp_bytes = (static_cast<size_t>(d->n) * d->h * g.Wp * 16 + 1023) & ~size_t(1023);
+  g.wp_bytes = (static_cast<size_t>(d->k) * d->kh * 32 * 4 + 1023) & ~size_t(1023);
+  return g;
+}
+static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcGeom& g, const float* x, int x_nchw, float* xp) {
+  const long long total = d->n * d->h * g.Wp;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  smallc_pack_input_kernel<<<grid, 256, 0, ctx->stream>>>(x, reinterpret_cast<float4*>(xp), d->n, static_cast<int>(d->c),
+                                                          static_cast<int>(d->h), static_cast<int>(d->w), static_cast<int>(g.Wp),
+                                                          static_cast<int>(d->pad_w), x_nchw);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+// y[N,P,Q,K] (NHWC) = conv(x, w[K,R,S,C]) (+bias); x is NHWC (x_nchw = 0) or NCHW (x_nchw = 1)
+int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
+                           float* y) {
+  if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
+  const SmallcGeom g = smallc_geom(d);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, g.xp_bytes + g.wp_bytes, &ws);
+  if (rc != ZB_OK) return rc;
+  float* xp = static_cast<float*>(ws);
+  float* wp = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + g.xp_bytes);
+  if ((rc = smallc_pack_input(ctx, d, g, x, x_nchw, xp)) != ZB_OK) return rc;
+  {
+    const int total = static_cast<int>(d->k * d->kh * 32);
+    smallc_pack_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wp, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                          static_cast<int>(d->kw), static_cast<int>(d->c));
+    ZB_LAUNCH_CHECK(ctx);
+  }
+  const int bn = pick_bn(d->k);
+  UmmaParams p;
+  init_params(p, ctx);
+  p.win_box_q = static_cast<int>(std::min<long long>(g.Q, kUmmaBM));
+  p.win_box_p = (d->stride_h == 1) ? static_cast<int>(std::max<long long>(1, std::min<long long>(kUmmaBM / p.win_box_q, g.P))) : 1;
+  p.win_q_tiles = ceil_div(g.Q, p.win_box_q);
+  p.win_p_tiles = ceil_div(g.P, p.win_box_p);
+  CUtensorMap ma, mb;
+  if ((rc = make_map_window(ctx, &ma, xp, d->n, d->h, g.Wp, g.Q, static_cast<int>(d->stride_w), p.win_box_q, p.win_box_p, false)) != ZB_OK) return rc;
+  if ((rc = make_map_2d(ctx, &mb, wp, d->kh * 32, d->k, d->kh * 32, 32, bn)) != ZB_OK) return rc;
+  p.a_mode = A_WINDOW_K;
+  p.b_mode = B_TILED_K;
+  p.out_mode = OUT_WINDOW;
+  p.M = static_cast<int>(d->n * g.P * g.Q);
+  p.N = static_cast<int>(d->k);
+  p.m_tiles = static_cast<int>(d->n) * p.win_p_tiles * p.win_q_tiles;
+  p.n_tiles = ceil_div(d->k, bn);
+  p.conv_P = static_cast<int>(g.P);
+  p.conv_Q = static_cast<int>(g.Q);
+  p.lower_h = -static_cast<int>(d->pad_h);
+  p.stride_h = static_cast<int>(d->stride_h);
+  p.stride_w = static_cast<int>(d->stride_w);
+  for (int r = 0; r < d->kh; ++r) p.tap_h[r] = static_cast<uint16_t>(r * d->dil_h);
+  p.kb_total = static_cast<int>(d->kh);
+  p.prof_flops = 2.0 * p.M * d->k * d->c * d->kh * d->kw;
+  p.D = y;
+  p.ldd = d->k;
+  finish_split_fields(p, 1);
+  return run_with_splits(ctx, bn, ma, mb, p, p.M, d->k, y, d->k, 1.f, 0.f, bias);
+}
+
+// dw[K,R,S,C] = wgrad(dy[N,P,Q,K] (NHWC), x); reduction over pixels in 32-pixel runs of one output row
+int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, int x_nchw, float* dw) {
+  if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C wgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
+  const SmallcGeom g = smallc_geom(d);
+  const long long NPQ = d->n * g.P * g.Q;
+  UmmaParams p;
+  init_params(p, ctx);
+  p.win_qblocks = ceil_div(g.Q, 32);
+  p.m_tiles = ceil_div(d->k, kUmmaBM);
+  p.n_tiles = 1;
+  p.tap_tiles = static_cast<int>(d->kh);
+  p.kb_total = static_cast<int>(d->n * g.P) * p.win_qblocks;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.tap_tiles;
+  finish_split_fields(p, pick_splits(ctx, tiles, p.kb_total, 16));
+  const long long rows = d->k, cols = d->kh * 32;
+  const size_t part_bytes = (sizeof(float) * static_cast<size_t>(p.splits) * rows * cols + 1023) & ~size_t(1023);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, g.xp_bytes + part_bytes, &ws);
+  if (rc != ZB_OK) return rc;
+  float* xp = static_cast<float*>(ws);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + g.xp_bytes);
+  if ((rc = smallc_pack_input(ctx, d, g, x, x_nchw, xp)) != ZB_OK) return rc;
+  CUtensorMap ma, mb;
+  if ((rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK, true)) != ZB_OK) return rc;
+  if ((rc = make_map_window(ctx, &mb, xp, d->n, d->h, g.Wp, g.Q, static_cast<int>(d->stride_w), 32, 1, true)) != ZB_OK) return rc;
+  p.a_mode = A_TILED_MN;
+  p.b_mode = B_WINDOW_MN;
+  p.out_mode = OUT_ROWS;
+  p.M = static_cast<int>(d->k);
+  p.N = 32;
+  p.conv_P = static_cast<int>(g.P);
+  p.conv_Q = static_cast<int>(g.Q);
+  p.lower_h = -static_cast<int>(d->pad_h);
+  p.stride_h = static_cast<int>(d->stride_h);
+  p.stride_w = static_cast<int>(d->stride_w);
+  for (int r = 0; r < d->kh; ++r) p.tap_h[r] = static_cast<uint16_t>(r * d->dil_h);
+  p.prof_flops = 2.0 * NPQ * d->k * d->c * d->kh * d->kw;
+  p.D = part;
+  p.ldd = cols;
+  p.tap_col_stride = 32;
+  p.split_stride = p.splits > 1 ? rows * cols : 0;
+  p.alpha = 1.f;
+  if ((rc = umma_launch(ctx, 32, ma, mb, p)) != ZB_OK) return rc;
+  const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
+  smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                        static_cast<int>(d->kw), static_cast<int>(d->c), p.splits,
+                                                                        rows * cols);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }

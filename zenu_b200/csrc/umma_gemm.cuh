@@ -13,15 +13,19 @@ enum UmmaAMode : int {
   A_TILED_K = 0,   // A[M][K] row-major, K contiguous            (Linear, 1x1 conv, dgrad 1x1)
   A_IM2COL_K = 1,  // NHWC activations through TMA im2col, K = (tap, channel chunk)   (fprop / dgrad 3x3)
   A_TILED_MN = 2,  // A^T stored: [K][M] row-major, M contiguous (wgrad: dY[pixels][Kout])
+  A_WINDOW_K = 3,  // small-C conv (C <= 4, e.g. the 7x7 stem): packed NHWC4 input, one 32-float sliding window
+                   // (8 taps x 4 channels of one filter row) per output pixel through an overlapped-stride tiled map
 };
 enum UmmaBMode : int {
   B_TILED_K = 0,    // B[N][K] row-major, K contiguous            (weights [Kout][taps*C])
   B_TILED_MN = 2,   // B stored [K][N] row-major, N contiguous    (wgrad 1x1: X[pixels][Cin]; Linear dX)
   B_IM2COL_MN = 3,  // NHWC activations through TMA im2col, N = channels, K = pixels (wgrad kxk)
+  B_WINDOW_MN = 4,  // small-C wgrad: the same sliding windows, N = 32 window elements, K = pixels
 };
 enum UmmaOutMode : int {
   OUT_ROWS = 0,     // D[row][col], row pitch ldd
   OUT_SCATTER = 1,  // row m = (n,p,q) -> NHWC pixel (n, p*osy+oy0, q*osx+ox0) of an [N][OH][OW][ldd] tensor
+  OUT_WINDOW = 2,   // A_WINDOW_K tiles: tile = (image, p-block, q-block), local row l -> (p0 + l / box_q, q0 + l % box_q)
 };
 
 struct UmmaParams {
@@ -38,6 +42,8 @@ struct UmmaParams {
   int lower_w, lower_h, stride_w, stride_h;
   int ntaps, c_chunks;   // A_IM2COL_K: kb -> (tap = kb / c_chunks, c0 = 32 * (kb % c_chunks))
   int b_tap_stride;      // columns of B per tap (padded C) for A_IM2COL_K
+  // sliding-window modes: box of win_box_q x win_box_p output pixels per M tile; win_qblocks 32-pixel K blocks per row
+  int win_box_q, win_box_p, win_q_tiles, win_p_tiles, win_qblocks;
   uint16_t tap_w[kUmmaMaxTaps];
   uint16_t tap_h[kUmmaMaxTaps];
   // output
