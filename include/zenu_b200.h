@@ -86,6 +86,9 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
                     const void* w, const void* bias, void* y);
 int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                     const void* w, void* dx);
+/* dx += dgrad(dy, w): gradient fan-in (zenu-autograd/src/lib.rs:480-481 `grad + old`) folded into the dgrad epilogue */
+int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
+                        const void* w, void* dx);
 int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                     const void* x, void* dw);
 /* conv2d_bias_add / conv2d_bias_bkwd (nn/conv/mod.rs:84-107; kernels array_array.cu:49-74,
@@ -114,6 +117,11 @@ int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, 
 int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                 const void* dy, const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx,
                 void* dscale, void* dbias, const void* y, void* dres);
+/* Backward of y = max(bn(x), 0) (fused BN+ReLU, no residual) that never reads y: the mask y > 0 is recomputed from x,
+ * scale, bias and the saved statistics with the forward's exact rounding sequence (20 instead of 28 bytes / element). */
+int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                     const void* dy, const void* scale, const void* bias, const void* saved_mean,
+                     const void* saved_inv_std, void* dx, void* dscale, void* dbias);
 
 /* ---- GEMM / Linear ------------------------------------------------------------------------------
  * Replaces Gemm::gemm_unchecked (zenu-matrix/src/operation/mul.rs:12-29,113-147 -> cublas{S,D}gemm_v2_64,
@@ -157,6 +165,13 @@ int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y,
 int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const void* dy, void* dx, int64_t n,
                      int64_t c, int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph,
                      int64_t pw);
+/* Indexed variant (NHWC, C % 4 == 0): forward also writes idx[N,P,Q,C] (uint8: winning tap r*kw+s, 255 = padding won);
+ * backward gathers from (dy, idx) instead of re-reading x: no memset, no atomics, deterministic. */
+int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, void* idx, int64_t n, int64_t c,
+                         int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw);
+int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, const void* idx, void* dx, int64_t n,
+                         int64_t c, int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph,
+                         int64_t pw);
 int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t hw);
 int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int64_t n, int64_t c, int64_t hw);
 /* loss (device scalar) = -(1/B) sum t*log(softmax(z)); dz (optional) = (softmax(z)*sum_j t - t)/B */

@@ -76,6 +76,26 @@ def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def tf32_round(a, mode="rna"):
+    """fp32 -> tf32 (10 explicit mantissa bits) -> fp32: what the tensor-core path does to GEMM/conv OPERANDS (products
+    and sums stay fp32).  Not part of the reference's algorithm: it models the device's operand rounding so that model-level
+    tests can separate "TF32 operand rounding" (expected, bounded) from kernel bugs.
+    mode: rna = nearest, ties away from zero (cvt.rna.tf32.f32, the TMA TFLOAT32 load); rz = truncate (what the MMA does
+    to raw fp32 bits)."""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32)
+    if mode == "rna":
+        r = (u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)
+    elif mode == "rne":
+        r = (u + np.uint32(0x0FFF) + ((u >> np.uint32(13)) & np.uint32(1))) & np.uint32(0xFFFFE000)
+    elif mode == "rz":
+        r = u & np.uint32(0xFFFFE000)
+    else:
+        raise ValueError(mode)
+    out = r.view(np.float32)
+    return np.where(np.isfinite(a), out, a)
+
+
 def conv_out(i, k, pad, stride, dil):
     return int(lib().zo_conv_dim_out_size(i, k, pad, stride, dil))
 

@@ -89,8 +89,12 @@ def init_params(arch, num_classes, seed=42, dtype=np.float32):
 
 
 class OracleModel:
-    def __init__(self, arch, num_classes, params, momentum=0.9):
+    def __init__(self, arch, num_classes, params, momentum=0.9, operand_round=None):
+        """operand_round: None = the reference's f32 arithmetic; "rna"/"rne"/"rz" = additionally round every conv / GEMM
+        OPERAND to tf32 first (zo.tf32_round), modelling the device's tensor-core math mode for model-level tests."""
         self.arch, self.num_classes, self.p, self.momentum = arch, num_classes, params, momentum
+        self.operand_round = operand_round
+        self.rnd = (lambda a: zo.tf32_round(a, operand_round)) if operand_round else (lambda a: a)
         self.dtype = next(iter(params.values())).dtype
         self.kinds = {k: v[1] for k, v in param_shapes(arch, num_classes).items()}
         self.state = {}
@@ -100,15 +104,16 @@ class OracleModel:
     def _conv(self, name, x, stride, pad, grads):
         w = self.p[name + ".conv2d.filter"]
         b = self.p.get(name + ".conv2d.bias")
-        y = zo.conv2d_fwd(x, w, pad, stride, 1)
+        rnd = self.rnd
+        y = zo.conv2d_fwd(rnd(x), rnd(w), pad, stride, 1)
         if b is not None:
             y = zo.conv2d_bias_add(y, b)
 
         def back(dy):
             if b is not None:
                 grads[name + ".conv2d.bias"] = zo.conv2d_bias_bkwd(dy)
-            grads[name + ".conv2d.filter"] = zo.conv2d_bkwd_filter(dy, x, w.shape, pad, stride, 1)
-            return zo.conv2d_bkwd_data(dy, w, x.shape, pad, stride, 1)
+            grads[name + ".conv2d.filter"] = zo.conv2d_bkwd_filter(rnd(dy), rnd(x), w.shape, pad, stride, 1)
+            return zo.conv2d_bkwd_data(rnd(dy), rnd(w), x.shape, pad, stride, 1)
         return y, back
 
     def _bn(self, name, x, grads):
@@ -130,10 +135,13 @@ class OracleModel:
 
     def _linear(self, name, x, grads):
         w, b = self.p[name + ".linear.weight"], self.p[name + ".linear.bias"]
-        y = zo.linear_fwd(x, w, b)
+        rnd = self.rnd
+        y = zo.linear_fwd(rnd(x), rnd(w), b)
 
         def back(dy):
-            dx, dw, db = zo.linear_bwd(x, w, dy)
+            dx, dw, db = zo.linear_bwd(rnd(x), rnd(w), rnd(dy))
+            if self.operand_round:
+                db = zo.linear_bwd(x, w, dy)[2]   # the bias gradient is a plain f32 column sum on the device
             grads[name + ".linear.weight"], grads[name + ".linear.bias"] = dw, db
             return dx
         return y, back

@@ -201,6 +201,58 @@ def test_conv_vs_oracle(zb, ctx, case, layout, math):
     ctx.check()
 
 
+def _net_layers(arch, hw):
+    from oracle import zenu_oracle_model as zm
+    if arch == "small_cnn":
+        return [("conv1", 3, 32, 3, 1, 1, hw), ("conv2", 32, 64, 3, 1, 1, hw)]
+    blocks, _ = zm._resnet_plan(18 if arch == "resnet18" else 50)
+    out = [("conv1", 3, 64, 7, 2, 3, hw)]
+    h = (hw + 6 - 7) // 2 + 1
+    h = (h + 2 - 3) // 2 + 1
+    for name, convs, down in blocks:
+        hin = h
+        for i, (ci, co, k, stride, pad) in enumerate(convs):
+            out.append((f"{name}.conv{i + 1}", ci, co, k, stride, pad, h))
+            h = (h + 2 * pad - k) // stride + 1
+        if down:
+            out.append((f"{name}.down", down[0], down[1], 1, down[3], 0, hin))
+    return out
+
+
+@pytest.mark.parametrize("arch,n,hw", [("small_cnn", 64, 32), ("resnet18", 16, 64), ("resnet50", 16, 64)])
+def test_conv_layers_vs_tf32_rounded_oracle(zb, ctx, arch, n, hw):
+    """Every distinct conv geometry of the configs' networks (stem 7x7/s2 with C=3, 3x3 s1/s2, 1x1 s1/s2, up to 2048
+    channels), fprop / dgrad / wgrad on the tcgen05 path, against the oracle fed with operands rounded to tf32
+    (nearest-even, zo.tf32_round).  With the operand rounding modelled only the fp32 summation order differs, so the bound is
+    2e-5 instead of the 1e-3 TF32 allowance: a kernel bug cannot hide inside the TF32 tolerance."""
+    from zenu_b200 import ZB_MATH_TF32, ZB_NHWC
+    zo.use_openblas()
+    try:
+        rng = np.random.default_rng(0)
+        seen = set()
+        for name, ci, co, k, stride, pad, h in _net_layers(arch, hw):
+            key = (ci, co, k, stride, pad, h)
+            if key in seen:
+                continue
+            seen.add(key)
+            x = rng.standard_normal((n, ci, h, h)).astype(np.float32)
+            w = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
+            xr, wr = zo.tf32_round(x, "rne"), zo.tf32_round(w, "rne")
+            y_ref = zo.conv2d_fwd(xr, wr, pad, stride, 1)
+            dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+            dyr = zo.tf32_round(dy, "rne")
+            X, W, DY = dev(nhwc(x)), dev(nhwc(w)), dev(nhwc(dy))
+            y = zb.conv_fwd(ctx, X, W, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+            assert rel_err(nchw(host(y)), y_ref) < 2e-5, (name, "fprop")
+            dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+            assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(dyr, wr, x.shape, pad, stride, 1)) < 2e-5, (name, "dgrad")
+            dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+            assert rel_err(nchw(host(dw)), zo.conv2d_bkwd_filter(dyr, xr, w.shape, pad, stride, 1)) < 2e-5, (name, "wgrad")
+        ctx.check()
+    finally:
+        zo.use_plain_gemm()
+
+
 def test_conv_f64_vs_oracle(zb, ctx):
     n, c, h, w, k, r, s, pad, stride, dil = 2, 8, 10, 10, 6, 3, 3, 1, 2, 1
     rng = np.random.default_rng(7)
@@ -335,6 +387,70 @@ def test_bn_fused_relu_residual(zb, ctx, layout):
     assert rel_err(back(dx), dx_ref) < 2e-4
     assert rel_err(back(dres), dz) < 2e-5
     assert rel_err(host(ds), ds_ref) < 2e-4 and rel_err(host(db), db_ref) < 2e-4
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_bn_relu_backward_recomputed_mask(zb, ctx, layout, dtype):
+    """zb_bn2d_relu_bwd (mask recomputed from x) == BN -> relu backward composed from oracle ops, and is bit-identical
+    to the y-reading variant."""
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    rng = np.random.default_rng(314)
+    shape = (6, 24, 7, 9)
+    c = shape[1]
+    f = np.float32 if dtype == "f32" else np.float64
+    x = rng.standard_normal(shape).astype(f)
+    dy = rng.standard_normal(shape).astype(f)
+    scale, bias = rng.standard_normal(c).astype(f), (0.3 * rng.standard_normal(c)).astype(f)
+    bn, _, _, sm, si = zo.bn2d_fwd_train(x.astype(np.float64), scale.astype(np.float64), bias.astype(np.float64), np.zeros(c), np.ones(c), 0.9)
+    dz = zo.ewise("mul", dy.astype(np.float64), zo.relu_backward_mask(bn))
+    dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x.astype(np.float64), dz, scale.astype(np.float64), sm, si)
+    if layout == "nchw":
+        L, cv, back = ZB_NCHW, dev, host
+    else:
+        L, cv, back = ZB_NHWC, (lambda a: dev(nhwc(a))), (lambda t: nchw(host(t)))
+    X, DY, S, B = cv(x), cv(dy), dev(scale), dev(bias)
+    y, smg, sig = zb.batch_norm_2d_forward_train(ctx, 0.9, X, S, B, dev(np.zeros(c, f)), dev(np.ones(c, f)), layout=L, relu=True)
+    dx, ds, db = zb.batch_norm_2d_relu_backward(ctx, X, DY, S, B, smg, sig, layout=L)
+    tol = 2e-4 if dtype == "f32" else 1e-10
+    # elements whose pre-activation is within rounding of zero may flip against the float64 oracle: compare in L2
+    assert rel_err(back(dx), dx_ref) < tol and rel_err(host(ds), ds_ref) < tol and rel_err(host(db), db_ref) < tol
+    dx2, ds2, db2 = zb.batch_norm_2d_backward(ctx, X, DY, S, smg, sig, layout=L, y=y)
+    np.testing.assert_array_equal(host(dx), host(dx2))
+    np.testing.assert_array_equal(host(ds), host(ds2))
+    np.testing.assert_array_equal(host(db), host(db2))
+
+
+def test_dgrad_accumulate(zb, ctx):
+    """dx += dgrad (fan-in folded into the epilogue) == dgrad + old, stride 1 and stride 2 (scatter epilogue)."""
+    from zenu_b200 import ZB_NHWC
+    rng = np.random.default_rng(77)
+    for (n, c, h, w, k, r, pad, stride) in ((2, 64, 12, 12, 64, 3, 1, 1), (2, 64, 13, 13, 32, 1, 0, 2), (2, 32, 9, 9, 64, 3, 1, 2)):
+        x_shape = (n, h, w, c)
+        wt = (rng.standard_normal((k, r, r, c)) * 0.1).astype(np.float32)
+        p = (h + 2 * pad - r) // stride + 1
+        dy = rng.standard_normal((n, p, p, k)).astype(np.float32)
+        old = rng.standard_normal(x_shape).astype(np.float32)
+        base = host(zb.conv_bkwd_data(ctx, dev(dy), dev(wt), x_shape, pad, stride, 1, layout=ZB_NHWC))
+        acc = dev(old.copy())
+        zb.conv_bkwd_data_accumulate(ctx, dev(dy), dev(wt), acc, pad, stride, 1, layout=ZB_NHWC)
+        np.testing.assert_allclose(host(acc), base + old, rtol=1e-6, atol=1e-6)
+    ctx.check()
+
+
+def test_maxpool_indexed(zb, ctx):
+    """Indexed NHWC max-pool: forward == oracle (zero padding takes part, first max wins), backward gather == oracle."""
+    rng = np.random.default_rng(18)
+    for shape, (k, s, p) in (((2, 8, 11, 9), (3, 2, 1)), ((1, 4, 8, 8), (2, 2, 0)), ((2, 12, 7, 10), (3, 1, 1))):
+        x = np.maximum(rng.standard_normal(shape), 0).astype(np.float32) - (0.2 if k == 3 and s == 1 else 0.0)
+        x = x.astype(np.float32)
+        y_ref = zo.maxpool2d_fwd(x, k, s, p)
+        dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+        dx_ref = zo.maxpool2d_bwd(x, dy, k, s, p)
+        y, idx = zb.max_pool_2d_indexed(ctx, dev(nhwc(x)), k, s, p)
+        np.testing.assert_array_equal(nchw(host(y)), y_ref)
+        dx = zb.max_pool_2d_indexed_backward(ctx, dev(nhwc(dy)), idx, nhwc(x).shape, k, s, p)
+        np.testing.assert_allclose(nchw(host(dx)), dx_ref, rtol=1e-6, atol=1e-6)
 
 
 # ------------------------------------------------------------------------------------------------ elementwise / pool / loss / optim

@@ -11,11 +11,13 @@ int umma_gemm(zb_ctx*, bool, bool, long long, long long, long long, float, const
               float, float*, long long, const float*);
 bool umma_conv_supported(const zb_conv2d_desc*);
 int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*);
-int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
 bool umma_conv_smallc_supported(const zb_conv2d_desc*);
 int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*);
 int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*);
+bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc*);
+int umma_conv_smallc_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
 // conv_simt.cu
 template <typename T> int simt_conv_fprop(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, const T*, T*);
 template <typename T> int simt_conv_dgrad(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, T*);
@@ -97,8 +99,38 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   return transpose_batched<float>(ctx, static_cast<float*>(ty.p), yf, d->n, P * Q, d->k);
 }
 
+static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
+                      void* dx, float beta);
+
 int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
                     void* dx) {
+  return dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 0.f);
+}
+
+int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
+                        void* dx) {
+  long long P, Q;
+  int rc = check_desc(d, &P, &Q);
+  if (rc != ZB_OK) return rc;
+  int m;
+  rc = resolve_math(ctx, dtype, math, &m);
+  if (rc != ZB_OK) return rc;
+  const bool fused = dtype == ZB_F32 && layout == ZB_NHWC && m == ZB_MATH_TF32 && (d->k % 32 == 0) && d->kh * d->kw <= 64;
+  if (fused) {
+    rc = dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 1.f);
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
+  }
+  // paths without an accumulating epilogue: compute into a temporary, then add
+  Temp t(ctx);
+  const size_t esz = dtype == ZB_F64 ? 8 : 4;
+  const long long n = d->n * d->c * d->h * d->w;
+  if ((rc = t.alloc(esz * n)) != ZB_OK) return rc;
+  if ((rc = dgrad_impl(ctx, dtype, layout, math, d, dy, w, t.p, 0.f)) != ZB_OK) return rc;
+  return zb_binary(ctx, dtype, ZB_OP_ADD, dx, t.p, dx, n);
+}
+
+static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
+                      void* dx, float beta) {
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
@@ -113,10 +145,15 @@ int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* wf = static_cast<const float*>(w);
   float* df = static_cast<float*>(dx);
   const bool tc_ok = (d->k % 32 == 0) && d->kh * d->kw <= 64 && (layout == ZB_NHWC || d->c % 4 == 0);
+  if (beta != 0.f && !(layout == ZB_NHWC && m == ZB_MATH_TF32 && tc_ok)) {
+    set_last_error("dgrad accumulate: not available on this path");
+    return ZB_ERR_UNSUPPORTED;
+  }
   if (m == ZB_MATH_FP32 || !tc_ok) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
+  if (layout == ZB_NHWC && beta == 0.f && umma_conv_smallc_dgrad_supported(d)) return umma_conv_smallc_dgrad(ctx, d, gf, wf, df);
   if (layout == ZB_NHWC) {
-    rc = umma_conv_dgrad_nhwc(ctx, d, gf, wf, df);
-    if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
+    rc = umma_conv_dgrad_nhwc(ctx, d, gf, wf, df, beta);
+    if (rc == ZB_ERR_UNSUPPORTED && beta == 0.f) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
     return rc;
   }
   Temp tg(ctx), tw(ctx), td(ctx);
@@ -125,7 +162,7 @@ int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   if ((rc = td.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
-  rc = umma_conv_dgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p));
+  rc = umma_conv_dgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p), 0.f);
   if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
   if (rc != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(td.p), df, d->n, d->h * d->w, d->c);

@@ -45,6 +45,15 @@ __device__ __forceinline__ void stv(T* p, const T* o) {
   *reinterpret_cast<V*>(p) = v;
 }
 
+// y = ((x - mean) * inv) * gamma + beta with a fixed rounding sequence: the backward of a fused BN+ReLU recomputes
+// this value from x to rebuild the ReLU mask, so forward and backward must round identically.
+__device__ __forceinline__ float bn_affine(float a, float m, float iv, float g, float b) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(a, m), iv), g, b);
+}
+__device__ __forceinline__ double bn_affine(double a, double m, double iv, double g, double b) {
+  return __fma_rn(__dmul_rn(__dsub_rn(a, m), iv), g, b);
+}
+
 struct ColGeom {
   int tx, ty, col_groups, slabs;
   long long rows_per_slab, cvecs;
@@ -95,20 +104,30 @@ struct SumF {  // plain column sum
     for (int e = 0; e < VN; ++e) acc[0][e] += a[e];
   }
 };
-template <typename T, int VN, bool MASK>
+// MASK: 0 = plain BN backward, 1 = ReLU mask from the saved output y (third stream), 2 = ReLU mask recomputed from x
+// (fused BN+ReLU without residual: y > 0 <=> bn_affine(x) > 0, so y is never read)
+template <typename T, int VN, int MASK>
 struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
-  static constexpr int NS = 2, NIN = MASK ? 3 : 2;
+  static constexpr int NS = 2, NIN = MASK == 1 ? 3 : 2;
   const T* mean;
   const T* inv;
-  T m[VN], iv[VN];
+  const T* gamma;
+  const T* beta;
+  T m[VN], iv[VN], gm[VN], bt[VN];
   __device__ void init(long long c0) {
 #pragma unroll
-    for (int e = 0; e < VN; ++e) { m[e] = mean[c0 + e]; iv[e] = inv[c0 + e]; }
+    for (int e = 0; e < VN; ++e) {
+      m[e] = mean[c0 + e]; iv[e] = inv[c0 + e];
+      if (MASK == 2) { gm[e] = gamma[c0 + e]; bt[e] = beta[c0 + e]; }
+    }
   }
   __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN]) const {
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
-      const T g = (MASK && !(y[e] > T(0))) ? T(0) : dy[e];
+      bool keep = true;
+      if (MASK == 1) keep = y[e] > T(0);
+      if (MASK == 2) keep = bn_affine(x[e], m[e], iv[e], gm[e], bt[e]) > T(0);
+      const T g = keep ? dy[e] : T(0);
       acc[0][e] += g;
       acc[1][e] += g * ((x[e] - m[e]) * iv[e]);
     }
@@ -229,19 +248,48 @@ __global__ void __launch_bounds__(256) col_reduce_nchw(F f, const T* __restrict_
 }
 
 // ---- finalize kernels ---------------------------------------------------------------------------------
+// Block = 32 channels x 8 slab lanes (256 threads): the slab partials of a channel are folded by 8 threads with
+// coalesced loads, then combined through shared memory in double precision.  (A single thread per channel walking
+// ~1000 slabs serially cost more than the reduce pass itself on 64-channel layers.)
+constexpr int kFinC = 32, kFinS = 8;
+template <typename T, int NS>
+__device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int slabs, long long C, long long c, bool active,
+                                              double (&out)[NS]) {
+  __shared__ double sh[NS][kFinS][kFinC + 1];
+  const int lc = threadIdx.x & (kFinC - 1), sl = threadIdx.x / kFinC;
+  double acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+  if (active) {
+#pragma unroll 4
+    for (int i = sl; i < slabs; i += kFinS)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] += static_cast<double>(partial[(static_cast<long long>(i) * NS + s) * C + c]);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) sh[s][sl][lc] = acc[s];
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < kFinS; ++j) v += sh[s][j][lc];
+    out[s] = v;
+  }
+}
+#define ZB_FIN_GRID(C) ceil_div((C), kFinC), kFinC * kFinS
+
 // coef layout in workspace: [0]=mean [1]=inv_std (fwd) ; bwd: [0]=gamma*inv [1]=c1 [2]=c2
 template <typename T>
-__global__ void bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum,
-                                const T* __restrict__ x_first_row, long long shift_stride, T* __restrict__ run_mean,
-                                T* __restrict__ run_var, T* __restrict__ saved_mean, T* __restrict__ saved_inv,
-                                T* __restrict__ coef) {
-  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int i = 0; i < slabs; ++i) {
-    s += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 0) * C + c]);
-    ss += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 1) * C + c]);
-  }
+__global__ void __launch_bounds__(kFinC * kFinS)
+bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum,
+                const T* __restrict__ x_first_row, long long shift_stride, T* __restrict__ run_mean, T* __restrict__ run_var,
+                T* __restrict__ saved_mean, T* __restrict__ saved_inv, T* __restrict__ coef) {
+  const long long c = blockIdx.x * static_cast<long long>(kFinC) + (threadIdx.x & (kFinC - 1));
+  double st[2];
+  fold_partials<T, 2>(partial, slabs, C, c, c < C, st);
+  if (c >= C || threadIdx.x >= kFinC) return;
+  const double s = st[0], ss = st[1];
   const double shift = static_cast<double>(x_first_row[c * shift_stride]);
   const double dm = s / count;
   const double mean = shift + dm;
@@ -268,16 +316,14 @@ __global__ void bn_infer_coef(const T* __restrict__ mean, const T* __restrict__ 
 }
 
 template <typename T>
-__global__ void bn_bwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count,
-                                const T* __restrict__ scale, const T* __restrict__ inv, T* __restrict__ dscale,
-                                T* __restrict__ dbias, T* __restrict__ coef) {
-  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int i = 0; i < slabs; ++i) {
-    s += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 0) * C + c]);
-    sx += static_cast<double>(partial[(static_cast<long long>(i) * 2 + 1) * C + c]);
-  }
+__global__ void __launch_bounds__(kFinC * kFinS)
+bn_bwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, const T* __restrict__ scale,
+                const T* __restrict__ inv, T* __restrict__ dscale, T* __restrict__ dbias, T* __restrict__ coef) {
+  const long long c = blockIdx.x * static_cast<long long>(kFinC) + (threadIdx.x & (kFinC - 1));
+  double st[2];
+  fold_partials<T, 2>(partial, slabs, C, c, c < C, st);
+  if (c >= C || threadIdx.x >= kFinC) return;
+  const double s = st[0], sx = st[1];
   dbias[c] = static_cast<T>(s);
   dscale[c] = static_cast<T>(sx);
   coef[c] = static_cast<T>(static_cast<double>(scale[c]) * static_cast<double>(inv[c]));
@@ -286,12 +332,13 @@ __global__ void bn_bwd_finalize(const T* __restrict__ partial, int slabs, long l
 }
 
 template <typename T>
-__global__ void sum_finalize(const T* __restrict__ partial, int slabs, long long C, T* __restrict__ out) {
-  const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int i = 0; i < slabs; ++i) s += static_cast<double>(partial[static_cast<long long>(i) * C + c]);
-  out[c] = static_cast<T>(s);
+__global__ void __launch_bounds__(kFinC * kFinS)
+sum_finalize(const T* __restrict__ partial, int slabs, long long C, T* __restrict__ out) {
+  const long long c = blockIdx.x * static_cast<long long>(kFinC) + (threadIdx.x & (kFinC - 1));
+  double st[1];
+  fold_partials<T, 1>(partial, slabs, C, c, c < C, st);
+  if (c >= C || threadIdx.x >= kFinC) return;
+  out[c] = static_cast<T>(st[0]);
 }
 
 // ---- apply kernels ------------------------------------------------------------------------------------
@@ -325,7 +372,7 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
       T o[VN];
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
-        T v = ((a[u][e] - m[e]) * iv[e]) * g[e] + b[e];
+        T v = bn_affine(a[u][e], m[e], iv[e], g[e], b[e]);
         if (RES) v += rr[u][e];
         if (RELU) v = v > T(0) ? v : T(0);
         o[e] = v;
@@ -340,7 +387,7 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
     if (RES) ldv<T, VN>(res + off, rr);
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
-      T v = ((a[e] - m[e]) * iv[e]) * g[e] + b[e];
+      T v = bn_affine(a[e], m[e], iv[e], g[e], b[e]);
       if (RES) v += rr[e];
       if (RELU) v = v > T(0) ? v : T(0);
       o[e] = v;
@@ -350,25 +397,27 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
 }
 
 // backward: dx = coef * (dy' - c1 - xhat * c2);  dres = dy'
-template <typename T, int VN, bool MASK, bool DRES>
+template <typename T, int VN, int MASK, bool DRES>
 __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x, const T* __restrict__ dy,
                                                          const T* __restrict__ y, T* __restrict__ dx,
                                                          T* __restrict__ dres, const T* __restrict__ mean,
                                                          const T* __restrict__ inv, const T* __restrict__ coef,
+                                                         const T* __restrict__ gamma, const T* __restrict__ beta,
                                                          long long rows, long long C, long long rows_per_slab, int tx_n,
                                                          int ty_n) {
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
   if (c0 >= C) return;
-  T m[VN], iv[VN], k0[VN], k1[VN], k2[VN];
+  T m[VN], iv[VN], k0[VN], k1[VN], k2[VN], ga[VN], be[VN];
 #pragma unroll
   for (int e = 0; e < VN; ++e) {
     m[e] = mean[c0 + e]; iv[e] = inv[c0 + e];
     k0[e] = coef[c0 + e]; k1[e] = coef[C + c0 + e]; k2[e] = coef[2 * C + c0 + e];
+    if (MASK == 2) { ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e]; }
   }
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
   const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
-  constexpr int U = 2;
+  constexpr int U = MASK == 1 ? 2 : 4;
   long long r = r0 + ty;
   for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
     T a[U][VN], g[U][VN], yy[U][VN];
@@ -377,14 +426,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
       const long long off = (r + u * ty_n) * C + c0;
       ldv<T, VN>(x + off, a[u]);
       ldv<T, VN>(dy + off, g[u]);
-      if (MASK) ldv<T, VN>(y + off, yy[u]);
+      if (MASK == 1) ldv<T, VN>(y + off, yy[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       T o[VN], gm[VN];
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
-        gm[e] = (MASK && !(yy[u][e] > T(0))) ? T(0) : g[u][e];
+        bool keep = true;
+        if (MASK == 1) keep = yy[u][e] > T(0);
+        if (MASK == 2) keep = bn_affine(a[u][e], m[e], iv[e], ga[e], be[e]) > T(0);
+        gm[e] = keep ? g[u][e] : T(0);
         o[e] = k0[e] * (gm[e] - k1[e] - ((a[u][e] - m[e]) * iv[e]) * k2[e]);
       }
       const long long off = (r + u * ty_n) * C + c0;
@@ -397,10 +449,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
     const long long off = r * C + c0;
     ldv<T, VN>(x + off, a);
     ldv<T, VN>(dy + off, g);
-    if (MASK) ldv<T, VN>(y + off, yy);
+    if (MASK == 1) ldv<T, VN>(y + off, yy);
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
-      gm[e] = (MASK && !(yy[e] > T(0))) ? T(0) : g[e];
+      bool keep = true;
+      if (MASK == 1) keep = yy[e] > T(0);
+      if (MASK == 2) keep = bn_affine(a[e], m[e], iv[e], ga[e], be[e]) > T(0);
+      gm[e] = keep ? g[e] : T(0);
       o[e] = k0[e] * (gm[e] - k1[e] - ((a[e] - m[e]) * iv[e]) * k2[e]);
     }
     stv<T, VN>(dx + off, o);
@@ -418,23 +473,28 @@ __global__ void __launch_bounds__(256) bn_apply_nchw(const T* __restrict__ x, co
   const T m = coef[c], iv = coef[C + c], g = gamma[c], b = beta[c];
   const long long base = plane * HW;
   for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
-    T v = ((x[base + i] - m) * iv) * g + b;
+    T v = bn_affine(x[base + i], m, iv, g, b);
     if (RES) v += res[base + i];
     if (RELU) v = v > T(0) ? v : T(0);
     y[base + i] = v;
   }
 }
-template <typename T, bool MASK, bool DRES>
+template <typename T, int MASK, bool DRES>
 __global__ void __launch_bounds__(256) bn_bwd_apply_nchw(const T* __restrict__ x, const T* __restrict__ dy,
                                                          const T* __restrict__ y, T* __restrict__ dx, T* __restrict__ dres,
                                                          const T* __restrict__ mean, const T* __restrict__ inv,
-                                                         const T* __restrict__ coef, long long C, long long HW) {
+                                                         const T* __restrict__ coef, const T* __restrict__ gamma,
+                                                         const T* __restrict__ beta, long long C, long long HW) {
   const long long plane = blockIdx.x;
   const long long c = plane % C;
   const T m = mean[c], iv = inv[c], k0 = coef[c], k1 = coef[C + c], k2 = coef[2 * C + c];
+  const T ga = MASK == 2 ? gamma[c] : T(0), be = MASK == 2 ? beta[c] : T(0);
   const long long base = plane * HW;
   for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
-    const T gm = (MASK && !(y[base + i] > T(0))) ? T(0) : dy[base + i];
+    bool keep = true;
+    if (MASK == 1) keep = y[base + i] > T(0);
+    if (MASK == 2) keep = bn_affine(x[base + i], m, iv, ga, be) > T(0);
+    const T gm = keep ? dy[base + i] : T(0);
     dx[base + i] = k0 * (gm - k1 - ((x[base + i] - m) * iv) * k2);
     if (DRES) dres[base + i] = gm;
   }
@@ -492,8 +552,9 @@ static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, lon
 
 template <typename T, int VN> using StatsFT = StatsF<T, VN>;
 template <typename T, int VN> using SumFT = SumF<T, VN>;
-template <typename T, int VN> using BnBwdMaskFT = BnBwdF<T, VN, true>;
-template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, false>;
+template <typename T, int VN> using BnBwdMaskFT = BnBwdF<T, VN, 1>;
+template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, 0>;
+template <typename T, int VN> using BnBwdRecomputeFT = BnBwdF<T, VN, 2>;
 
 // Upper bound on the slab count run_col_reduce may pick (sizes the partial buffer).
 static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
@@ -552,7 +613,7 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
                                   partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
   if (rc != ZB_OK) return rc;
   // shift used by the reduce = first row (NHWC: x[c]) or first element of channel c in image 0 (NCHW: x[c*HW])
-  bn_fwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
+  bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
                                                                layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
                                                                saved_inv, coef);
   ZB_LAUNCH_CHECK(ctx);
@@ -574,9 +635,10 @@ static int bn_fwd_infer_t(zb_ctx* ctx, int layout, long long N, long long C, lon
   return dispatch_apply<T>(ctx, layout, N, C, H * W, x, static_cast<const T*>(nullptr), y, coef, scale, bias, 0);
 }
 
-template <typename T, bool MASK, bool DRES>
+template <typename T, int MASK, bool DRES>
 static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* dy,
-                            const T* y, T* dx, T* dres, const T* mean, const T* inv, const T* coef) {
+                            const T* y, T* dx, T* dres, const T* mean, const T* inv, const T* coef, const T* gamma,
+                            const T* beta) {
   const long long rows = N * HW;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
@@ -584,14 +646,14 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
     if (vec) {
       ColGeom g = col_geom(ctx, rows, C, VN);
       dim3 grid(g.col_groups, g.slabs);
-      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, rows, C, g.rows_per_slab, g.tx, g.ty);
+      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
     } else {
       ColGeom g = col_geom(ctx, rows, C, 1);
       dim3 grid(g.col_groups, g.slabs);
-      bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, rows, C, g.rows_per_slab, g.tx, g.ty);
+      bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
     }
   } else {
-    bn_bwd_apply_nchw<T, MASK, DRES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, C, HW);
+    bn_bwd_apply_nchw<T, MASK, DRES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, C, HW);
   }
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
@@ -600,8 +662,10 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
 template <typename T>
 static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, const T* x, const T* dy,
                     const T* scale, const T* saved_mean, const T* saved_inv, T* dx, T* dscale, T* dbias, const T* y,
-                    T* dres) {
+                    T* dres, const T* relu_bias = nullptr) {
+  // relu_bias != NULL: backward of relu(bn(x)) with the ReLU mask recomputed from x, scale and this bias (y unused)
   ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
+  ZB_REQUIRE(!(relu_bias && (y || dres)), "bn bwd: mask recomputation excludes the y / residual-gradient arguments");
   const long long HW = H * W;
   const long long ms = max_slabs(ctx, layout, N, C);
   void* ws = nullptr;
@@ -618,7 +682,7 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
     rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
                                     partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
     if (rc != ZB_OK) return rc;
-    bn_fwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), 0.0, x,
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), 0.0, x,
                                                                  layout == ZB_NHWC ? 1 : HW, static_cast<T*>(nullptr),
                                                                  static_cast<T*>(nullptr), static_cast<T*>(nullptr),
                                                                  static_cast<T*>(nullptr), stats);
@@ -627,20 +691,24 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
     if (inv == nullptr) inv = stats + C;
   }
   prof_begin(ctx, PROF_BN);
-  if (y != nullptr)
+  if (relu_bias != nullptr)
+    rc = run_col_reduce<T, BnBwdRecomputeFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs);
+  else if (y != nullptr)
     rc = run_col_reduce<T, BnBwdMaskFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
                                         [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
   else
     rc = run_col_reduce<T, BnBwdNoMaskFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
                                           [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
   if (rc != ZB_OK) return rc;
-  bn_bwd_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), scale, inv,
+  bn_bwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), scale, inv,
                                                                dscale, dbias, coef);
   ZB_LAUNCH_CHECK(ctx);
-  if (y != nullptr && dres != nullptr) rc = launch_bwd_apply<T, true, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  else if (y != nullptr) rc = launch_bwd_apply<T, true, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  else if (dres != nullptr) rc = launch_bwd_apply<T, false, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
-  else rc = launch_bwd_apply<T, false, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef);
+  if (relu_bias != nullptr) rc = launch_bwd_apply<T, 2, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else if (y != nullptr && dres != nullptr) rc = launch_bwd_apply<T, 1, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else if (y != nullptr) rc = launch_bwd_apply<T, 1, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else if (dres != nullptr) rc = launch_bwd_apply<T, 0, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written)
   prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * (5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
   return rc;
@@ -659,7 +727,7 @@ int channel_sum(zb_ctx* ctx, int layout, long long N, long long C, long long HW,
   rc = run_col_reduce<T, SumFT>(ctx, layout, N, C, HW, a, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
                                 partial, ms * C, [&](auto&) {}, &slabs);
   if (rc != ZB_OK) return rc;
-  sum_finalize<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(partial, slabs, C, out);
+  sum_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, out);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }
@@ -719,6 +787,25 @@ int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_
                             static_cast<const double*>(scale), static_cast<const double*>(saved_mean),
                             static_cast<const double*>(saved_inv_std), static_cast<double*>(dx), static_cast<double*>(dscale),
                             static_cast<double*>(dbias), static_cast<const double*>(y), static_cast<double*>(dres));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+
+int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                     const void* dy, const void* scale, const void* bias, const void* saved_mean, const void* saved_inv_std,
+                     void* dx, void* dscale, void* dbias) {
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
+  ZB_REQUIRE(bias != nullptr && saved_mean != nullptr && saved_inv_std != nullptr, "bn relu bwd: bias and saved statistics are required");
+  if (dtype == ZB_F32)
+    return bn_bwd_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(dy),
+                           static_cast<const float*>(scale), static_cast<const float*>(saved_mean),
+                           static_cast<const float*>(saved_inv_std), static_cast<float*>(dx), static_cast<float*>(dscale),
+                           static_cast<float*>(dbias), nullptr, nullptr, static_cast<const float*>(bias));
+  if (dtype == ZB_F64)
+    return bn_bwd_t<double>(ctx, layout, n, c, h, w, static_cast<const double*>(x), static_cast<const double*>(dy),
+                            static_cast<const double*>(scale), static_cast<const double*>(saved_mean),
+                            static_cast<const double*>(saved_inv_std), static_cast<double*>(dx), static_cast<double*>(dscale),
+                            static_cast<double*>(dbias), nullptr, nullptr, static_cast<const double*>(bias));
   zb::set_last_error("unknown dtype %d", dtype);
   return ZB_ERR_INVALID;
 }

@@ -239,10 +239,15 @@ struct ConvFn : Function {
       commit_grad(rt, bv, db);
     }
     if (need_dx && (xv.requires_grad || xv.creator)) {
-      Tensor dx = grad_target(rt, xv);
       ProfScope ps(rt, conv_key("dgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
-      check_rc(zb_conv2d_dgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, dx.ptr), "conv dgrad");
-      commit_grad(rt, xv, dx);
+      if (xv.grad.defined() && !xv.is_param && xv.grad.storage && xv.grad.storage.use_count() == 1) {
+        // second arrival (residual fan-in): accumulate inside the dgrad epilogue instead of a separate add pass
+        check_rc(zb_conv2d_dgrad_acc(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, xv.grad.ptr), "conv dgrad (accumulate)");
+      } else {
+        Tensor dx = grad_target(rt, xv);
+        check_rc(zb_conv2d_dgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, dx.ptr), "conv dgrad");
+        commit_grad(rt, xv, dx);
+      }
     }
     x = Tensor();
   }
@@ -271,7 +276,7 @@ Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variabl
 }
 
 struct BnFn : Function {
-  Tensor x, y, scale, saved_mean, saved_inv;
+  Tensor x, y, scale, bias, saved_mean, saved_inv;
   int64_t n, c, h, w;
   bool relu, has_res;
   const char* name() const override { return "batch_norm_2d"; }
@@ -289,9 +294,13 @@ struct BnFn : Function {
       dres_ptr = dres.ptr;
     }
     ProfScope ps(rt, std::string("bn.bwd") + (relu ? "+relu" : "") + (has_res ? "+res" : "") + " " + shape_str(x.shape), 0.0,
-                 static_cast<double>(x.bytes()) * (5.0 + (relu ? 2.0 : 0.0) + (has_res && relu ? 1.0 : 0.0)));
-    check_rc(zb_bn2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
-                         ds.ptr, db.ptr, relu ? y.ptr : nullptr, dres_ptr), "bn bwd");
+                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? 3.0 : 0.0)));
+    if (relu && !has_res)  // mask recomputed from x: the forward output is neither kept nor read
+      check_rc(zb_bn2d_relu_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, bias.ptr, saved_mean.ptr,
+                                saved_inv.ptr, dx.ptr, ds.ptr, db.ptr), "bn relu bwd");
+    else
+      check_rc(zb_bn2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
+                           ds.ptr, db.ptr, relu ? y.ptr : nullptr, dres_ptr), "bn bwd");
     commit_grad(rt, xv, dx);
     commit_grad(rt, *inputs[1], ds);
     commit_grad(rt, *inputs[2], db);
@@ -327,9 +336,10 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   if (residual) fn->inputs.push_back(residual->ptr());
   fn->x = x->data;
   fn->scale = scale->data;
+  fn->bias = bias->data;
   fn->relu = relu;
   fn->has_res = residual != nullptr;
-  if (relu) fn->y = y;
+  if (relu && residual) fn->y = y;
   fn->n = n; fn->c = c; fn->h = h; fn->w = w;
   return make_output(y, fn);
 }
@@ -415,26 +425,36 @@ Variable linear(Runtime& rt, const Variable& x, const Variable& w, const Variabl
 }
 
 struct MaxPoolFn : Function {
-  Tensor x;
+  Tensor x, idx;  // idx (uint8 winning tap per output element) when the indexed NHWC kernels apply, else x is kept
   int64_t n, c, h, w, k, stride, pad;
   const char* name() const override { return "max_pool_2d"; }
   void backward(Runtime& rt, const Tensor& gy) override {
     Tensor dx = grad_target(rt, *inputs[0]);
-    ProfScope ps(rt, "maxpool.bwd " + shape_str(x.shape), 0.0, 2.0 * x.bytes() + gy.bytes());
-    check_rc(zb_maxpool2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, x.ptr, gy.ptr, dx.ptr, n, c, h, w, k, k, stride, stride, pad, pad), "maxpool bwd");
+    ProfScope ps(rt, "maxpool.bwd " + shape_str(inputs[0]->data.shape), 0.0, static_cast<double>(dx.bytes() + gy.bytes()) + gy.numel());
+    if (idx.defined())
+      check_rc(zb_maxpool2d_bwd_idx(rt.ctx, gy.dtype, ZB_NHWC, gy.ptr, idx.ptr, dx.ptr, n, c, h, w, k, k, stride, stride, pad, pad), "maxpool bwd");
+    else
+      check_rc(zb_maxpool2d_bwd(rt.ctx, gy.dtype, ZB_NHWC, x.ptr, gy.ptr, dx.ptr, n, c, h, w, k, k, stride, stride, pad, pad), "maxpool bwd");
     commit_grad(rt, *inputs[0], dx);
     x = Tensor();
+    idx = Tensor();
   }
 };
 Variable max_pool_2d(Runtime& rt, const Variable& x, int64_t k, int64_t stride, int64_t pad) {
   const auto& s = x.shape();
   const int64_t P = (s[1] + 2 * pad - k) / stride + 1, Q = (s[2] + 2 * pad - k) / stride + 1;
   Tensor y = rt.empty({s[0], P, Q, s[3]});
-  ProfScope ps(rt, "maxpool.fwd " + shape_str(s), 0.0, static_cast<double>(x->data.bytes() + y.bytes()));
-  check_rc(zb_maxpool2d_fwd(rt.ctx, y.dtype, ZB_NHWC, x->data.ptr, y.ptr, s[0], s[3], s[1], s[2], k, k, stride, stride, pad, pad), "maxpool");
   auto fn = std::make_shared<MaxPoolFn>();
+  ProfScope ps(rt, "maxpool.fwd " + shape_str(s), 0.0, static_cast<double>(x->data.bytes() + y.bytes()));
+  if (s[3] % 4 == 0 && k * k < 255) {
+    fn->idx = rt.empty({(y.numel() + 3) / 4});  // one byte per output element
+    fn->idx.dtype = ZB_F32;
+    check_rc(zb_maxpool2d_fwd_idx(rt.ctx, y.dtype, ZB_NHWC, x->data.ptr, y.ptr, fn->idx.ptr, s[0], s[3], s[1], s[2], k, k, stride, stride, pad, pad), "maxpool");
+  } else {
+    check_rc(zb_maxpool2d_fwd(rt.ctx, y.dtype, ZB_NHWC, x->data.ptr, y.ptr, s[0], s[3], s[1], s[2], k, k, stride, stride, pad, pad), "maxpool");
+    fn->x = x->data;
+  }
   fn->inputs = {x.ptr()};
-  fn->x = x->data;
   fn->n = s[0]; fn->c = s[3]; fn->h = s[1]; fn->w = s[2]; fn->k = k; fn->stride = stride; fn->pad = pad;
   return make_output(y, fn);
 }

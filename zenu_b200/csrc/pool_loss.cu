@@ -97,6 +97,116 @@ static int maxpool_bwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, const T* dy
   return ZB_OK;
 }
 
+// ---- indexed max-pool, NHWC, 4 channels per thread ------------------------------------------------------------
+// Forward also records which window tap won (uint8: r*kw+s, 255 = a padding zero won) so that backward is a gather
+// over the <= ceil(kh/sh)*ceil(kw/sw) windows covering an input pixel: no memset, no atomics, deterministic.
+template <typename T> struct Vec4T;
+template <> struct Vec4T<float> { using type = float4; };
+template <> struct Vec4T<double> { using type = double4; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, const T* __restrict__ x, T* __restrict__ y,
+                                                              uchar4* __restrict__ idx) {
+  using V = typename Vec4T<T>::type;
+  const long long c4n = g.C >> 2;
+  const long long total = g.N * g.P * g.Q * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long c4 = i % c4n;
+    long long t = i / c4n;
+    const long long q = t % g.Q; t /= g.Q;
+    const long long p = t % g.P;
+    const long long n = t / g.P;
+    const T* xb = x + n * g.sn + c4 * 4;
+    T best[4];
+    unsigned char bi[4];
+    bool first = true;
+    for (int r = 0; r < g.kh; ++r) {
+      const long long ih = p * g.sh + r - g.ph;
+      for (int s_ = 0; s_ < g.kw; ++s_) {
+        const long long iw = q * g.sw + s_ - g.pw;
+        const bool oob = ih < 0 || ih >= g.H || iw < 0 || iw >= g.W;
+        T v[4] = {T(0), T(0), T(0), T(0)};
+        if (!oob) {
+          const V vv = *reinterpret_cast<const V*>(xb + ih * g.s_h + iw * g.s_w);
+          v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
+        }
+        const unsigned char tap = oob ? 255 : static_cast<unsigned char>(r * g.kw + s_);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (first || v[e] > best[e]) { best[e] = v[e]; bi[e] = tap; }
+        first = false;
+      }
+    }
+    V o;
+    o.x = best[0]; o.y = best[1]; o.z = best[2]; o.w = best[3];
+    *reinterpret_cast<V*>(y + i * 4) = o;
+    idx[i] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_idx_bwd_kernel(const PoolGeom g, const T* __restrict__ dy,
+                                                              const uchar4* __restrict__ idx, T* __restrict__ dx) {
+  using V = typename Vec4T<T>::type;
+  const long long c4n = g.C >> 2;
+  const long long total = g.N * g.H * g.W * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long c4 = i % c4n;
+    long long t = i / c4n;
+    const long long w = t % g.W; t /= g.W;
+    const long long h = t % g.H;
+    const long long n = t / g.H;
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    // windows p with p*sh - ph <= h <= p*sh - ph + kh - 1
+    long long p_lo = (h + g.ph - g.kh + 1 + g.sh - 1);
+    p_lo = p_lo <= 0 ? 0 : p_lo / g.sh;
+    long long p_hi = (h + g.ph) / g.sh;
+    if (p_hi > g.P - 1) p_hi = g.P - 1;
+    long long q_lo = (w + g.pw - g.kw + 1 + g.sw - 1);
+    q_lo = q_lo <= 0 ? 0 : q_lo / g.sw;
+    long long q_hi = (w + g.pw) / g.sw;
+    if (q_hi > g.Q - 1) q_hi = g.Q - 1;
+    for (long long p = p_lo; p <= p_hi; ++p) {
+      const int r = static_cast<int>(h + g.ph - p * g.sh);
+      for (long long q = q_lo; q <= q_hi; ++q) {
+        const int s_ = static_cast<int>(w + g.pw - q * g.sw);
+        const unsigned char tap = static_cast<unsigned char>(r * g.kw + s_);
+        const long long o = ((n * g.P + p) * g.Q + q) * c4n + c4;
+        const uchar4 wi = idx[o];
+        const V gv = *reinterpret_cast<const V*>(dy + o * 4);
+        if (wi.x == tap) acc[0] += gv.x;
+        if (wi.y == tap) acc[1] += gv.y;
+        if (wi.z == tap) acc[2] += gv.z;
+        if (wi.w == tap) acc[3] += gv.w;
+      }
+    }
+    V o4;
+    o4.x = acc[0]; o4.y = acc[1]; o4.z = acc[2]; o4.w = acc[3];
+    *reinterpret_cast<V*>(dx + i * 4) = o4;
+  }
+}
+
+template <typename T>
+static int maxpool_idx_fwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, T* y, void* idx) {
+  const long long total = g.N * g.P * g.Q * (g.C >> 2);
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
+  maxpool_idx_fwd_kernel<T><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+template <typename T>
+static int maxpool_idx_bwd_t(zb_ctx* ctx, const PoolGeom& g, const T* dy, const void* idx, T* dx) {
+  const long long total = g.N * g.H * g.W * (g.C >> 2);
+  if (total == 0) return ZB_OK;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
+  maxpool_idx_bwd_kernel<T><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
 // ---- global average pool: x [N][HW][C] (NHWC) or [N][C][HW] (NCHW) -> y [N][C] ------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) gap_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long N, long long C,
@@ -211,6 +321,32 @@ int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const vo
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_bwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx));
   if (dtype == ZB_F64) return maxpool_bwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<const double*>(dy), static_cast<double*>(dx));
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+static int check_idx_pool(int layout, int64_t c, int64_t kh, int64_t kw, const void* a, const void* b) {
+  ZB_REQUIRE(layout == ZB_NHWC, "indexed max-pool: NHWC only");
+  ZB_REQUIRE(c % 4 == 0 && kh * kw < 255, "indexed max-pool: needs C %% 4 == 0 and fewer than 255 taps");
+  ZB_REQUIRE((reinterpret_cast<uintptr_t>(a) & 31) == 0 && (reinterpret_cast<uintptr_t>(b) & 31) == 0, "indexed max-pool: tensors must be 32-byte aligned");
+  return ZB_OK;
+}
+int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, void* idx, int64_t n, int64_t c, int64_t h,
+                         int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  int rc = check_idx_pool(layout, c, kh, kw, x, y);
+  if (rc != ZB_OK) return rc;
+  const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (dtype == ZB_F32) return maxpool_idx_fwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<float*>(y), idx);
+  if (dtype == ZB_F64) return maxpool_idx_fwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<double*>(y), idx);
+  zb::set_last_error("unknown dtype %d", dtype);
+  return ZB_ERR_INVALID;
+}
+int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, const void* idx, void* dx, int64_t n, int64_t c,
+                         int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  int rc = check_idx_pool(layout, c, kh, kw, dy, dx);
+  if (rc != ZB_OK) return rc;
+  const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (dtype == ZB_F32) return maxpool_idx_bwd_t<float>(ctx, g, static_cast<const float*>(dy), idx, static_cast<float*>(dx));
+  if (dtype == ZB_F64) return maxpool_idx_bwd_t<double>(ctx, g, static_cast<const double*>(dy), idx, static_cast<double*>(dx));
   zb::set_last_error("unknown dtype %d", dtype);
   return ZB_ERR_INVALID;
 }

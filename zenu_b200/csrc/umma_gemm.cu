@@ -54,6 +54,18 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
   return t;
 }
 
+// K-block range of a tile: split-K slices, or (small-C dgrad) the filter rows that reach input row h
+__device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoord& tc, int& kb_begin, int& kb_end) {
+  if (p.a_mode == A_ROWS_K) {
+    const int h = tc.m_blk % p.dg_H;
+    kb_begin = 0;
+    kb_end = p.dg_cnt[(h + p.dg_ph) % p.dg_sh] * p.c_chunks;
+  } else {
+    kb_begin = tc.split * p.kb_per_split;
+    kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -110,8 +122,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
-        const int kb_begin = tc.split * p.kb_per_split;
-        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        int kb_begin, kb_end;
+        tile_kb_range(p, tc, kb_begin, kb_end);
         int a_w = 0, a_h = 0, a_n = 0;
         if (p.a_mode == A_IM2COL_K) {
           const int img = m0 / pq, rem = m0 - img * pq;
@@ -126,11 +138,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           a_w = qt * p.win_box_q;                                   // first output column of the tile
           a_h = pt * p.win_box_p * p.stride_h + p.lower_h;          // input row of filter row 0
           a_n = img;
+        } else if (p.a_mode == A_ROWS_K) {
+          a_n = tc.m_blk / p.dg_H;
+          a_h = tc.m_blk - a_n * p.dg_H;                            // input row h of dX
         }
         const int a_boxes = a_mn ? min(4, (p.M - m0 + 31) / 32) : 0;
         const int b_boxes = b_mn ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
         const uint32_t a_bytes = a_mn ? a_boxes * 4096u
-                                      : (p.a_mode == A_WINDOW_K ? uint32_t(p.win_box_q * p.win_box_p) * 128u : uint32_t(L::A_BYTES));
+                                      : (p.a_mode == A_WINDOW_K ? uint32_t(p.win_box_q * p.win_box_p) * 128u
+                                         : (p.a_mode == A_ROWS_K ? uint32_t(p.win_box_q) * 128u : uint32_t(L::A_BYTES)));
         const uint32_t bytes = a_bytes + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
         bool ok = true;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -144,6 +160,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (p.a_mode == A_IM2COL_K) {
             const int tap = kb / p.c_chunks, c0 = (kb - tap * p.c_chunks) * kUmmaBK;
             tma_load_im2col_4d(sA, &tmA, &full_bar[stage], c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
+          } else if (p.a_mode == A_ROWS_K) {
+            const int i = kb / p.c_chunks;
+            const int r = p.dg_r[(a_h + p.dg_ph) % p.dg_sh][i];
+            const int prow = (a_h + p.dg_ph - r * p.dg_dh) / p.dg_sh;   // exact by construction of dg_r; may be < 0 or >= P (zero fill)
+            tma_load_4d(sA, &tmA, &full_bar[stage], (kb - i * p.c_chunks) * kUmmaBK, 0, prow, a_n);
           } else if (p.a_mode == A_WINDOW_K) {
             tma_load_4d(sA, &tmA, &full_bar[stage], 0, a_w, a_h + p.tap_h[kb], a_n);   // kb = filter row
           } else {
@@ -160,6 +181,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (p.a_mode == A_IM2COL_K) {
               const int tap = kb / p.c_chunks;
               k0 = tap * p.b_tap_stride + (kb - tap * p.c_chunks) * kUmmaBK;
+            } else if (p.a_mode == A_ROWS_K) {
+              const int i = kb / p.c_chunks;
+              k0 = p.dg_r[(a_h + p.dg_ph) % p.dg_sh][i] * p.b_tap_stride + (kb - i * p.c_chunks) * kUmmaBK;
             }
             tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
           } else if (p.b_mode == B_TILED_MN) {
@@ -167,7 +191,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (p.b_mode == B_WINDOW_MN) {  // K index = pixel (32-pixel run of one output row), N index = window element
             const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
             const int img = row / p.conv_P, pp = row - img * p.conv_P;
-            tma_load_4d(sB, &tmB, &full_bar[stage], 0, qb * 32, pp * p.stride_h + p.lower_h + p.tap_h[tc.tap], img);
+            for (int j = 0; j < b_boxes; ++j)   // one box per filter row folded into N (ntaps rows per tile group)
+              tma_load_4d(sB + j * 4096, &tmB, &full_bar[stage], 0, qb * 32,
+                          pp * p.stride_h + p.lower_h + p.tap_h[tc.tap * p.ntaps + j], img);
           } else {  // B_IM2COL_MN: K index = base pixel, N index = channel
             const int pix = kb * kUmmaBK;
             const int img = pix / pq, rem = pix - img * pq;
@@ -191,8 +217,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
-        const int kb_begin = tc.split * p.kb_per_split;
-        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        int kb_begin, kb_end;
+        tile_kb_range(p, tc, kb_begin, kb_end);
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -264,6 +290,43 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
       tc_fence_after();
+      if (p.out_mode == OUT_WDGRAD) {
+        // accumulator D[q][s*4+c] (N = 32) -> shared [128 q][32] tile (all four warps) -> every thread overlap-adds the
+        // filter columns s that reach its output element and stores the dense row dX[n][h][0..W)[0..C) coalesced
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free: the MMA warp may start the next tile
+        const float* tile_s = reinterpret_cast<const float*>(smem + L::EPI_OFFSET);
+        const int row_elems = p.dg_W * p.dg_C;
+        int kb0, kb1;
+        tile_kb_range(p, tc, kb0, kb1);
+        float* out_row = p.D + static_cast<long long>(tc.m_blk) * row_elems;
+        for (int o = ew * 32 + lane; o < row_elems; o += 128) {
+          const int w = o / p.dg_C, c = o - w * p.dg_C;
+          float sum = 0.f;
+          if (kb1 > kb0) {
+            for (int sx = (w + p.dg_pw) % p.dg_sw; sx < p.dg_S; sx += p.dg_sw) {
+              const int q = (w + p.dg_pw - sx) / p.dg_sw;
+              if (q >= 0 && q < p.conv_Q) {
+                const int j = sx * 4 + c;
+                sum += tile_s[q * 32 + (((j >> 2) ^ (q & 7)) << 2) + (j & 3)];
+              }
+            }
+          }
+          out_row[o] = sum;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -284,20 +347,33 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
           if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
         }
+        long long offs[8];
+        float4 vals[8], olds[8];
+        const bool col_ok = col < p.N;
+        const bool full_vec = vec_ok && col + 3 < p.N;
+        const bool use_beta = !partial && p.beta != 0.f;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + sub_row;
-          const long long off = __shfl_sync(0xffffffffu, my_off, rr);
-          float4 o = stage4[rr * 8 + (piece ^ (rr & 7))];
-          if (off < 0 || col >= p.N) continue;
-          float* dst = p.D + off + col;
+          offs[it] = __shfl_sync(0xffffffffu, my_off, rr);
+          vals[it] = stage4[rr * 8 + (piece ^ (rr & 7))];
+        }
+        if (use_beta && full_vec) {  // all reads of the old tile in flight before the first dependent store
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (offs[it] < 0 || !col_ok) continue;
+          float4 o = vals[it];
+          float* dst = p.D + offs[it] + col;
           if (!partial) {
             o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
           }
-          if (vec_ok && col + 3 < p.N) {
-            if (!partial && p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(dst);
-              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+          if (full_vec) {
+            if (use_beta) {
+              o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
             }
             *reinterpret_cast<float4*>(dst) = o;
           } else {
@@ -306,7 +382,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int e = 0; e < 4; ++e)
               if (col + e < p.N) {
                 float val = ov[e];
-                if (!partial && p.beta != 0.f) val += p.beta * dst[e];
+                if (use_beta) val += p.beta * dst[e];
                 dst[e] = val;
               }
           }
@@ -461,10 +537,11 @@ static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensor
 // Chooses a split-K factor so that a problem with few output tiles still fills the SMs.
 static int pick_splits(zb_ctx* ctx, long long tiles, int kb_total, int min_kb_per_split) {
   if (tiles >= ctx->sm_count || kb_total < 2 * min_kb_per_split) return 1;
-  long long want = (2ll * ctx->sm_count + tiles - 1) / tiles;  // ~2 waves
+  // largest factor that keeps tiles * splits within two full waves of the persistent grid (never 2 waves + a tail)
+  long long want = (2ll * ctx->sm_count) / tiles;
   long long cap = kb_total / min_kb_per_split;
   long long s = std::max(1ll, std::min(want, cap));
-  return static_cast<int>(std::min<long long>(s, 64));
+  return static_cast<int>(std::min<long long>(s, 2ll * ctx->sm_count));
 }
 
 static void finish_split_fields(UmmaParams& p, int splits) {
@@ -627,7 +704,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
 
 // dx[N,H,W,C] = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Stride 1: one implicit GEMM over dy with the flipped filter.
 // Stride s > 1: one implicit GEMM per output parity class (h % s, w % s), scattered into dx.
-int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx) {
+int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
   if (d->k % 32 != 0 || d->kh * d->kw > kUmmaMaxTaps) {
     set_last_error("umma dgrad: shape unsupported");
     return ZB_ERR_UNSUPPORTED;
@@ -686,7 +763,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       }
       plans.push_back(cp);
     }
-  if (need_zero) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
+  if (need_zero && beta == 0.f) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
 
   // workspace: transformed filters for all classes + tap index lists
   size_t wt_elems = 0;
@@ -749,6 +826,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     }
     finish_split_fields(p, 1);
     p.split_stride = 0;
+    p.beta = beta;  // dx = dgrad + beta * dx: gradient fan-in (residual shortcuts) without a separate add pass
     rc = umma_launch(ctx, bn, ma, mb, p);
     if (rc != ZB_OK) return rc;
   }
@@ -981,21 +1059,27 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
   return run_with_splits(ctx, bn, ma, mb, p, p.M, d->k, y, d->k, 1.f, 0.f, bias);
 }
 
-// dw[K,R,S,C] = wgrad(dy[N,P,Q,K] (NHWC), x); reduction over pixels in 32-pixel runs of one output row
+// dw[K,R,S,C] = wgrad(dy[N,P,Q,K] (NHWC), x); reduction over pixels in 32-pixel runs of one output row.
+// Up to 8 filter rows are folded into GEMM-N (N = R x 32 window elements share every dY tile), more rows fall back to one
+// tile group per filter row.
 int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, int x_nchw, float* dw) {
   if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C wgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const SmallcGeom g = smallc_geom(d);
   const long long NPQ = d->n * g.P * g.Q;
+  const int R = static_cast<int>(d->kh);
+  const int fold = R <= 8 ? R : 1;           // filter rows per tile group
+  const int bn = pick_bn(fold * 32);
   UmmaParams p;
   init_params(p, ctx);
   p.win_qblocks = ceil_div(g.Q, 32);
   p.m_tiles = ceil_div(d->k, kUmmaBM);
   p.n_tiles = 1;
-  p.tap_tiles = static_cast<int>(d->kh);
+  p.ntaps = fold;
+  p.tap_tiles = R / fold;
   p.kb_total = static_cast<int>(d->n * g.P) * p.win_qblocks;
   const long long tiles = static_cast<long long>(p.m_tiles) * p.tap_tiles;
   finish_split_fields(p, pick_splits(ctx, tiles, p.kb_total, 16));
-  const long long rows = d->k, cols = d->kh * 32;
+  const long long rows = d->k, cols = static_cast<long long>(R) * 32;
   const size_t part_bytes = (sizeof(float) * static_cast<size_t>(p.splits) * rows * cols + 1023) & ~size_t(1023);
   void* ws = nullptr;
   int rc = ctx_workspace(ctx, g.xp_bytes + part_bytes, &ws);
@@ -1010,26 +1094,114 @@ int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   p.b_mode = B_WINDOW_MN;
   p.out_mode = OUT_ROWS;
   p.M = static_cast<int>(d->k);
-  p.N = 32;
+  p.N = fold * 32;
   p.conv_P = static_cast<int>(g.P);
   p.conv_Q = static_cast<int>(g.Q);
   p.lower_h = -static_cast<int>(d->pad_h);
   p.stride_h = static_cast<int>(d->stride_h);
   p.stride_w = static_cast<int>(d->stride_w);
-  for (int r = 0; r < d->kh; ++r) p.tap_h[r] = static_cast<uint16_t>(r * d->dil_h);
+  for (int r = 0; r < R; ++r) p.tap_h[r] = static_cast<uint16_t>(r * d->dil_h);
   p.prof_flops = 2.0 * NPQ * d->k * d->c * d->kh * d->kw;
   p.D = part;
   p.ldd = cols;
-  p.tap_col_stride = 32;
+  p.tap_col_stride = fold * 32;
   p.split_stride = p.splits > 1 ? rows * cols : 0;
   p.alpha = 1.f;
-  if ((rc = umma_launch(ctx, 32, ma, mb, p)) != ZB_OK) return rc;
+  if ((rc = umma_launch(ctx, bn, ma, mb, p)) != ZB_OK) return rc;
   const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
   smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
                                                                         static_cast<int>(d->kw), static_cast<int>(d->c), p.splits,
                                                                         rows * cols);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
+}
+
+// wd[j = s*4+c][r*K + k] = w[k][r][s][c] (KRSC), zero elsewhere: the K-major B operand of the small-C dgrad
+__global__ void smallc_pack_dgrad_filter_kernel(const float* __restrict__ w, float* __restrict__ wd, int K, int R, int S, int C) {
+  const int total = 32 * R * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % K;
+    const int r = (i / K) % R;
+    const int j = i / (K * R);
+    const int sidx = j >> 2, c = j & 3;
+    wd[i] = (sidx < S && c < C) ? w[((static_cast<long long>(k) * R + r) * S + sidx) * C + c] : 0.f;
+  }
+}
+
+bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc* d) {
+  if (!(d->c <= 4 && d->kw <= 8 && d->dil_w == 1 && d->k % 32 == 0 && d->stride_h <= 4 && d->kh <= 16)) return false;
+  const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  if (Q > kUmmaBM) return false;
+  // every input-row parity class must be reached by at least one filter row
+  for (int a = 0; a < d->stride_h; ++a) {
+    int cnt = 0;
+    for (int r = 0; r < d->kh; ++r) cnt += ((a - r * d->dil_h) % d->stride_h + d->stride_h) % d->stride_h == 0;
+    if (cnt == 0) return false;
+  }
+  return true;
+}
+
+// dx[N,H,W,C] (NHWC, C <= 4) = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Tile = one input row (n, h): the accumulator
+// D[q][s*4+c] = sum over the filter rows r reaching h and over k of dY[n, p(h,r), q, k] * w[k,r,s,c]; the epilogue overlap-adds
+// the filter columns.  dY is fetched ~R/stride_h times instead of R*S times (general parity-class path).
+int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx) {
+  if (!umma_conv_smallc_dgrad_supported(d)) { set_last_error("umma small-C dgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
+  const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
+  const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
+  const int R = static_cast<int>(d->kh);
+  const size_t wd_bytes = sizeof(float) * 32 * R * d->k;
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, wd_bytes, &ws);
+  if (rc != ZB_OK) return rc;
+  float* wd = static_cast<float*>(ws);
+  {
+    const int total = static_cast<int>(32 * R * d->k);
+    smallc_pack_dgrad_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wd, static_cast<int>(d->k), R, static_cast<int>(d->kw),
+                                                                                static_cast<int>(d->c));
+    ZB_LAUNCH_CHECK(ctx);
+  }
+  UmmaParams p;
+  init_params(p, ctx);
+  p.win_box_q = static_cast<int>(Q);
+  CUtensorMap ma, mb;
+  {
+    ZB_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "TMA operand must be 16-byte aligned");
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->k), static_cast<cuuint64_t>(Q), static_cast<cuuint64_t>(P), static_cast<cuuint64_t>(d->n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->k) * 4, static_cast<cuuint64_t>(Q) * d->k * 4, static_cast<cuuint64_t>(P) * Q * d->k * 4};
+    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(Q), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ctx->encode_tiled(&ma, operand_dtype(), 4, const_cast<float*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (dY rows) failed (%d)", int(r)); return ZB_ERR_CUDA; }
+  }
+  if ((rc = make_map_2d(ctx, &mb, wd, static_cast<long long>(R) * d->k, 32, static_cast<long long>(R) * d->k, 32, 32)) != ZB_OK) return rc;
+  p.a_mode = A_ROWS_K;
+  p.b_mode = B_TILED_K;
+  p.out_mode = OUT_WDGRAD;
+  p.M = static_cast<int>(d->n * d->h) * kUmmaBM;
+  p.N = 32;
+  p.m_tiles = static_cast<int>(d->n * d->h);
+  p.n_tiles = 1;
+  p.conv_P = static_cast<int>(P);
+  p.conv_Q = static_cast<int>(Q);
+  p.c_chunks = static_cast<int>(d->k / 32);
+  p.b_tap_stride = static_cast<int>(d->k);
+  p.dg_H = static_cast<int>(d->h); p.dg_W = static_cast<int>(d->w); p.dg_C = static_cast<int>(d->c); p.dg_S = static_cast<int>(d->kw);
+  p.dg_sw = static_cast<int>(d->stride_w); p.dg_pw = static_cast<int>(d->pad_w);
+  p.dg_sh = static_cast<int>(d->stride_h); p.dg_ph = static_cast<int>(d->pad_h); p.dg_dh = static_cast<int>(d->dil_h);
+  for (int a = 0; a < p.dg_sh; ++a) {   // class a = (h + pad_h) % stride_h: rows r with (a - r*dil_h) % stride_h == 0
+    int cnt = 0;
+    for (int r = 0; r < R; ++r)
+      if (((a - r * p.dg_dh) % p.dg_sh + p.dg_sh) % p.dg_sh == 0) p.dg_r[a][cnt++] = static_cast<uint8_t>(r);
+    p.dg_cnt[a] = static_cast<uint8_t>(cnt);
+  }
+  p.kb_total = R * p.c_chunks;  // upper bound; the per-tile range comes from dg_cnt
+  p.prof_flops = 2.0 * d->n * P * Q * d->k * d->c * d->kh * d->kw;
+  p.D = dx;
+  p.ldd = d->c;
+  finish_split_fields(p, 1);
+  p.split_stride = 0;
+  return umma_launch(ctx, 32, ma, mb, p);
 }
 
 }  // namespace zb

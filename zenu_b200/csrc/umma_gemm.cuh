@@ -13,6 +13,7 @@ enum UmmaAMode : int {
   A_TILED_K = 0,   // A[M][K] row-major, K contiguous            (Linear, 1x1 conv, dgrad 1x1)
   A_IM2COL_K = 1,  // NHWC activations through TMA im2col, K = (tap, channel chunk)   (fprop / dgrad 3x3)
   A_TILED_MN = 2,  // A^T stored: [K][M] row-major, M contiguous (wgrad: dY[pixels][Kout])
+  A_ROWS_K = 4,    // small-C dgrad: dY[N][P][Q][K] rows through a 4-D tiled map, one (image, output row p) per K block
   A_WINDOW_K = 3,  // small-C conv (C <= 4, e.g. the 7x7 stem): packed NHWC4 input, one 32-float sliding window
                    // (8 taps x 4 channels of one filter row) per output pixel through an overlapped-stride tiled map
 };
@@ -25,6 +26,8 @@ enum UmmaBMode : int {
 enum UmmaOutMode : int {
   OUT_ROWS = 0,     // D[row][col], row pitch ldd
   OUT_SCATTER = 1,  // row m = (n,p,q) -> NHWC pixel (n, p*osy+oy0, q*osx+ox0) of an [N][OH][OW][ldd] tensor
+  OUT_WDGRAD = 3,   // small-C dgrad: tile = (image, input row h); accumulator D[q][s*4+c] is overlap-added over the
+                    // filter columns s into the dense row dX[n][h][0..W)[0..C)
   OUT_WINDOW = 2,   // A_WINDOW_K tiles: tile = (image, p-block, q-block), local row l -> (p0 + l / box_q, q0 + l % box_q)
 };
 
@@ -44,6 +47,10 @@ struct UmmaParams {
   int b_tap_stride;      // columns of B per tap (padded C) for A_IM2COL_K
   // sliding-window modes: box of win_box_q x win_box_p output pixels per M tile; win_qblocks 32-pixel K blocks per row
   int win_box_q, win_box_p, win_q_tiles, win_p_tiles, win_qblocks;
+  // small-C dgrad geometry: per input-row parity class a = (h + pad_h) % stride_h, the filter rows r that reach it
+  int dg_H, dg_W, dg_C, dg_S, dg_sw, dg_pw, dg_sh, dg_ph, dg_dh;
+  uint8_t dg_cnt[4];
+  uint8_t dg_r[4][16];
   uint16_t tap_w[kUmmaMaxTaps];
   uint16_t tap_h[kUmmaMaxTaps];
   // output

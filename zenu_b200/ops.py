@@ -125,6 +125,16 @@ def conv_bkwd_data(ctx, dy, w, x_shape, pad=0, stride=1, dil=1, layout=ZB_NCHW, 
     return dx
 
 
+def conv_bkwd_data_accumulate(ctx, dy, w, dx, pad=0, stride=1, dil=1, layout=ZB_NCHW, math=ZB_MATH_DEFAULT):
+    """dx += conv_bkwd_data(dy, w): the `grad + old` fan-in of Variable::set_grad (zenu-autograd/src/lib.rs:480-481)."""
+    _chk(dy, "conv_bkwd_data dy"); _chk(w, "conv_bkwd_data filter"); _chk(dx, "conv_bkwd_data dx")
+    d = _desc(tuple(dx.shape), tuple(w.shape), layout, pad, stride, dil)
+    if tuple(dy.shape) != conv_out_shape(tuple(dx.shape), tuple(w.shape), layout, pad, stride, dil):
+        raise ZenuB200Error("conv_bkwd_data: dy shape does not match the conv geometry")
+    check(ctx.lib.zb_conv2d_dgrad_acc(ctx.handle, _DT[dy.dtype], layout, math, ctypes.byref(d), _p(dy), _p(w), _p(dx)))
+    return dx
+
+
 def conv_bkwd_weight(ctx, dy, x, w_shape, pad=0, stride=1, dil=1, layout=ZB_NCHW, math=ZB_MATH_DEFAULT):
     _chk(dy, "conv_bkwd_weight dy"); _chk(x, "conv_bkwd_weight input")
     d = _desc(tuple(x.shape), tuple(w_shape), layout, pad, stride, dil)
@@ -187,6 +197,20 @@ def batch_norm_2d_backward(ctx, x, y_grad, scale, saving_mean=None, saving_inv_v
     check(ctx.lib.zb_bn2d_bwd(ctx.handle, _DT[x.dtype], layout, n, c, h, w, _p(x), _p(y_grad), _p(scale), _p(saving_mean),
                               _p(saving_inv_variance), _p(dx), _p(ds), _p(db), _p(y), _p(dres)))
     return (dx, ds, db, dres) if want_residual_grad else (dx, ds, db)
+
+
+def batch_norm_2d_relu_backward(ctx, x, y_grad, scale, bias, saving_mean, saving_inv_variance, layout=ZB_NCHW):
+    """Backward of relu(batch_norm(x)) (no residual) that recomputes the ReLU mask from x instead of reading y."""
+    for t, nm in ((x, "x"), (y_grad, "y_grad"), (scale, "scale"), (bias, "bias"), (saving_mean, "saving_mean"),
+                  (saving_inv_variance, "saving_inv_variance")):
+        _chk(t, "batch_norm_relu_backward " + nm)
+    n, c, h, w = _nkhw(x.shape, layout)
+    dx = torch.empty_like(x)
+    ds = torch.empty((c,), dtype=x.dtype, device=x.device)
+    db = torch.empty((c,), dtype=x.dtype, device=x.device)
+    check(ctx.lib.zb_bn2d_relu_bwd(ctx.handle, _DT[x.dtype], layout, n, c, h, w, _p(x), _p(y_grad), _p(scale), _p(bias),
+                                   _p(saving_mean), _p(saving_inv_variance), _p(dx), _p(ds), _p(db)))
+    return dx, ds, db
 
 
 def batch_norm_2d_forward_inference(ctx, x, scale, bias, mean, variance, layout=ZB_NCHW):
@@ -314,6 +338,27 @@ def max_pool_2d_backward(ctx, x, dy, kernel, stride, pad, layout=ZB_NCHW):
     (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(pad)
     dx = torch.empty_like(x)
     check(ctx.lib.zb_maxpool2d_bwd(ctx.handle, _DT[x.dtype], layout, _p(x), _p(dy), _p(dx), n, c, h, w, kh, kw, sh, sw, ph, pw))
+    return dx
+
+
+def max_pool_2d_indexed(ctx, x, kernel, stride, pad):
+    """NHWC only.  Returns (y, idx): idx[N,P,Q,C] uint8 = winning tap r*kw+s (255 = a padding zero won)."""
+    n, c, h, w = _nkhw(x.shape, ZB_NHWC)
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(pad)
+    p, q = (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1
+    y = torch.empty((n, p, q, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((n, p, q, c), dtype=torch.uint8, device=x.device)
+    check(ctx.lib.zb_maxpool2d_fwd_idx(ctx.handle, _DT[x.dtype], ZB_NHWC, _p(x), _p(y), ctypes.c_void_p(idx.data_ptr()), n, c, h, w,
+                                       kh, kw, sh, sw, ph, pw))
+    return y, idx
+
+
+def max_pool_2d_indexed_backward(ctx, dy, idx, x_shape, kernel, stride, pad):
+    n, c, h, w = _nkhw(x_shape, ZB_NHWC)
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(pad)
+    dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device)
+    check(ctx.lib.zb_maxpool2d_bwd_idx(ctx.handle, _DT[dy.dtype], ZB_NHWC, _p(dy), ctypes.c_void_p(idx.data_ptr()), _p(dx), n, c, h, w,
+                                       kh, kw, sh, sw, ph, pw))
     return dx
 
 
