@@ -46,7 +46,10 @@ typedef enum {
 } zb_status;
 
 typedef enum { ZB_F32 = 0, ZB_F64 = 1 } zb_dtype;
-typedef enum { ZB_NCHW = 0, ZB_NHWC = 1 } zb_layout;
+/* ZB_NCHW_X: conv fprop / wgrad only — the input x is NCHW (how the reference hands a batch to the first layer), the
+ * filter is KRSC and y / dy are NHWC.  Served for C <= 4 stems on the TF32 path (the NCHW -> NHWC4 repack is part of the
+ * conv's own staging pass); other shapes return ZB_ERR_UNSUPPORTED and the caller converts the layout first. */
+typedef enum { ZB_NCHW = 0, ZB_NHWC = 1, ZB_NCHW_X = 2 } zb_layout;
 typedef enum { ZB_MATH_DEFAULT = 0, ZB_MATH_TF32 = 1, ZB_MATH_FP32 = 3 } zb_math_mode;
 typedef enum { ZB_OP_ADD = 0, ZB_OP_SUB = 1, ZB_OP_MUL = 2, ZB_OP_DIV = 3 } zb_binary_op;
 

@@ -49,7 +49,7 @@ CASES = [
     ("resnet18", 16, 64, 10, "tf32", "sgd", 1e-3, 3e-3, 1e-2, 5e-3),
     ("resnet18", 4, 64, 10, "fp32", "adam", 1e-3, 2e-4, 6e-4, 2e-4),
     ("resnet50", 16, 64, 8, "tf32", "sgd", 1e-3, 1e-2, 0.2, 8e-2),
-    ("resnet50", 4, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 2e-2, 2e-3),
+    ("resnet50", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 0.1, 2e-3),
 ]
 
 

@@ -224,7 +224,7 @@ def test_conv_layers_vs_tf32_rounded_oracle(zb, ctx, arch, n, hw):
     """Every distinct conv geometry of the configs' networks (stem 7x7/s2 with C=3, 3x3 s1/s2, 1x1 s1/s2, up to 2048
     channels), fprop / dgrad / wgrad on the tcgen05 path, against the oracle fed with operands rounded to tf32
     (nearest-even, zo.tf32_round).  With the operand rounding modelled only the fp32 summation order differs, so the bound is
-    2e-5 instead of the 1e-3 TF32 allowance: a kernel bug cannot hide inside the TF32 tolerance."""
+    5e-5 instead of the 1e-3 TF32 allowance: a kernel bug cannot hide inside the TF32 tolerance."""
     from zenu_b200 import ZB_MATH_TF32, ZB_NHWC
     zo.use_openblas()
     try:
@@ -243,11 +243,11 @@ def test_conv_layers_vs_tf32_rounded_oracle(zb, ctx, arch, n, hw):
             dyr = zo.tf32_round(dy, "rne")
             X, W, DY = dev(nhwc(x)), dev(nhwc(w)), dev(nhwc(dy))
             y = zb.conv_fwd(ctx, X, W, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
-            assert rel_err(nchw(host(y)), y_ref) < 2e-5, (name, "fprop")
+            assert rel_err(nchw(host(y)), y_ref) < 5e-5, (name, "fprop")
             dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
-            assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(dyr, wr, x.shape, pad, stride, 1)) < 2e-5, (name, "dgrad")
+            assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(dyr, wr, x.shape, pad, stride, 1)) < 5e-5, (name, "dgrad")
             dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
-            assert rel_err(nchw(host(dw)), zo.conv2d_bkwd_filter(dyr, xr, w.shape, pad, stride, 1)) < 2e-5, (name, "wgrad")
+            assert rel_err(nchw(host(dw)), zo.conv2d_bkwd_filter(dyr, xr, w.shape, pad, stride, 1)) < 5e-5, (name, "wgrad")
         ctx.check()
     finally:
         zo.use_plain_gemm()

@@ -72,11 +72,18 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
-  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "conv: unknown layout %d", layout);
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC || layout == ZB_NCHW_X, "conv: unknown layout %d", layout);
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "conv: unknown dtype %d", dtype);
   int m;
   rc = resolve_math(ctx, dtype, math, &m);
   if (rc != ZB_OK) return rc;
+  if (layout == ZB_NCHW_X) {
+    if (dtype == ZB_F32 && m == ZB_MATH_TF32 && umma_conv_smallc_supported(d))
+      return umma_conv_smallc_fprop(ctx, d, static_cast<const float*>(x), 1, static_cast<const float*>(w), static_cast<const float*>(bias),
+                                    static_cast<float*>(y));
+    set_last_error("conv fprop: ZB_NCHW_X is served for C <= 4 on the TF32 path only");
+    return ZB_ERR_UNSUPPORTED;
+  }
   if (dtype == ZB_F64)
     return simt_conv_fprop<double>(ctx, layout, d, static_cast<const double*>(x), static_cast<const double*>(w),
                                    static_cast<const double*>(bias), static_cast<double*>(y));
@@ -173,11 +180,17 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
-  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "conv: unknown layout %d", layout);
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC || layout == ZB_NCHW_X, "conv: unknown layout %d", layout);
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "conv: unknown dtype %d", dtype);
   int m;
   rc = resolve_math(ctx, dtype, math, &m);
   if (rc != ZB_OK) return rc;
+  if (layout == ZB_NCHW_X) {
+    if (dtype == ZB_F32 && m == ZB_MATH_TF32 && umma_conv_smallc_supported(d))
+      return umma_conv_smallc_wgrad(ctx, d, static_cast<const float*>(dy), static_cast<const float*>(x), 1, static_cast<float*>(dw));
+    set_last_error("conv wgrad: ZB_NCHW_X is served for C <= 4 on the TF32 path only");
+    return ZB_ERR_UNSUPPORTED;
+  }
   if (dtype == ZB_F64)
     return simt_conv_wgrad<double>(ctx, layout, d, static_cast<const double*>(dy), static_cast<const double*>(x), static_cast<double*>(dw));
   const float* gf = static_cast<const float*>(dy);

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) col_reduce_nchw(F f, const T* __restrict_
 // Block = 32 channels x 8 slab lanes (256 threads): the slab partials of a channel are folded by 8 threads with
 // coalesced loads, then combined through shared memory in double precision.  (A single thread per channel walking
 // ~1000 slabs serially cost more than the reduce pass itself on 64-channel layers.)
-constexpr int kFinC = 32, kFinS = 8;
+constexpr int kFinC = 32, kFinS = 32;
 template <typename T, int NS>
 __device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int slabs, long long C, long long c, bool active,
                                               double (&out)[NS]) {

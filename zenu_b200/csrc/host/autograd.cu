@@ -221,6 +221,7 @@ struct ConvFn : Function {
   Tensor x, w;
   zb_conv2d_desc d;
   bool has_bias, need_dx;
+  int x_layout = ZB_NHWC;  // ZB_NCHW_X when the stem consumed the NCHW network input directly
   const char* name() const override { return "conv2d"; }
   void backward(Runtime& rt, const Tensor& gy) override {
     VariableInner& xv = *inputs[0];
@@ -228,7 +229,7 @@ struct ConvFn : Function {
     if (wv.requires_grad) {
       Tensor dw = grad_target(rt, wv);
       ProfScope ps(rt, conv_key("wgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
-      check_rc(zb_conv2d_wgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, x.ptr, dw.ptr), "conv wgrad");
+      check_rc(zb_conv2d_wgrad(rt.ctx, gy.dtype, x_layout, ZB_MATH_DEFAULT, &d, gy.ptr, x.ptr, dw.ptr), "conv wgrad");
       commit_grad(rt, wv, dw);
     }
     if (has_bias && inputs[2]->requires_grad) {
@@ -240,10 +241,11 @@ struct ConvFn : Function {
     }
     if (need_dx && (xv.requires_grad || xv.creator)) {
       ProfScope ps(rt, conv_key("dgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
-      if (xv.grad.defined() && !xv.is_param && xv.grad.storage && xv.grad.storage.use_count() == 1) {
+      if (xv.grad.defined() && !xv.is_param && xv.grad.storage && xv.grad.storage.use_count() == 1 && x_layout == ZB_NHWC) {
         // second arrival (residual fan-in): accumulate inside the dgrad epilogue instead of a separate add pass
         check_rc(zb_conv2d_dgrad_acc(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, xv.grad.ptr), "conv dgrad (accumulate)");
       } else {
+        // (for an NCHW network input the gradient is produced in NHWC order; nothing consumes it)
         Tensor dx = grad_target(rt, xv);
         check_rc(zb_conv2d_dgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, dx.ptr), "conv dgrad");
         commit_grad(rt, xv, dx);
@@ -253,15 +255,41 @@ struct ConvFn : Function {
   }
 };
 
-Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx) {
-  const auto& xs = x.shape();
+Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx) {
+  Variable x = x_in;
   const auto& ws = w.shape();
-  if (xs.size() != 4 || ws.size() != 4 || xs[3] != ws[3]) throw HostError("conv2d: bad shapes (NHWC input, KRSC filter)");
+  if (x.shape().size() != 4 || ws.size() != 4) throw HostError("conv2d: bad shapes (NHWC input, KRSC filter)");
   auto fn = std::make_shared<ConvFn>();
-  fn->d = zb_conv2d_desc{xs[0], xs[3], xs[1], xs[2], ws[0], ws[1], ws[2], a.pad_h, a.pad_w, a.stride_h, a.stride_w, a.dil_h, a.dil_w};
-  const int64_t P = out_size(xs[1], ws[1], a.pad_h, a.stride_h, a.dil_h), Q = out_size(xs[2], ws[2], a.pad_w, a.stride_w, a.dil_w);
-  Tensor y = rt.empty({xs[0], P, Q, ws[0]});
-  {
+  Tensor y;
+  bool done = false;
+  if (x->nchw) {
+    // stem: try to consume the NCHW batch directly (C <= 4 on the TF32 path repacks inside the conv's staging pass)
+    const auto& s = x.shape();  // [N, C, H, W]
+    if (s[1] != ws[3]) throw HostError("conv2d: channel mismatch");
+    fn->d = zb_conv2d_desc{s[0], s[1], s[2], s[3], ws[0], ws[1], ws[2], a.pad_h, a.pad_w, a.stride_h, a.stride_w, a.dil_h, a.dil_w};
+    const int64_t P = out_size(s[2], ws[1], a.pad_h, a.stride_h, a.dil_h), Q = out_size(s[3], ws[2], a.pad_w, a.stride_w, a.dil_w);
+    y = rt.empty({s[0], P, Q, ws[0]});
+    int rc;
+    {
+      ProfScope ps(rt, conv_key("fprop", fn->d), conv_flops(fn->d), conv_bytes(fn->d, y.elem_size()));
+      rc = zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NCHW_X, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
+                           bias ? (*bias)->data.ptr : nullptr, y.ptr);
+    }
+    if (rc == ZB_OK) {
+      fn->x_layout = ZB_NCHW_X;
+      done = true;
+    } else if (rc == ZB_ERR_UNSUPPORTED) {
+      x = nchw_to_nhwc(rt, x);
+    } else {
+      check_rc(rc, "conv fprop");
+    }
+  }
+  if (!done) {
+    const auto& xs = x.shape();
+    if (xs[3] != ws[3]) throw HostError("conv2d: bad shapes (NHWC input, KRSC filter)");
+    fn->d = zb_conv2d_desc{xs[0], xs[3], xs[1], xs[2], ws[0], ws[1], ws[2], a.pad_h, a.pad_w, a.stride_h, a.stride_w, a.dil_h, a.dil_w};
+    const int64_t P = out_size(xs[1], ws[1], a.pad_h, a.stride_h, a.dil_h), Q = out_size(xs[2], ws[2], a.pad_w, a.stride_w, a.dil_w);
+    y = rt.empty({xs[0], P, Q, ws[0]});
     ProfScope ps(rt, conv_key("fprop", fn->d), conv_flops(fn->d), conv_bytes(fn->d, y.elem_size()));
     check_rc(zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
                              bias ? (*bias)->data.ptr : nullptr, y.ptr), "conv fprop");

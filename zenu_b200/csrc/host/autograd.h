@@ -121,6 +121,7 @@ struct VariableInner {
   bool requires_grad = false;        // reference: is_train on parameters; inputs always get grads there
   bool is_param = false;
   int bucket = -1;                   // data-parallel bucket this parameter's gradient belongs to
+  bool nchw = false;                 // network input still in the reference's NCHW layout (consumed by the stem conv)
   std::string name;
 };
 

@@ -33,9 +33,12 @@ struct zb_model {
 
 static Variable run_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w) {
   Runtime& rt = *m->rt;
-  Variable xin = Variable::leaf(rt.borrow(const_cast<void*>(x_nchw), {batch, c, h, w}));
-  Variable x = nchw_to_nhwc(rt, xin);
-  return m->model->call(rt, x);
+  // The batch stays NCHW (the reference's input contract): the stem conv consumes it directly when it can, otherwise
+  // conv2d() converts it.  The reference computes the input gradient of every conv, the first one included
+  // (conv_without_bias.rs:110-121); requires_grad on the input keeps that work in the step.
+  Variable xin = Variable::leaf(rt.borrow(const_cast<void*>(x_nchw), {batch, c, h, w}), /*requires_grad=*/true);
+  xin->nchw = true;
+  return m->model->call(rt, xin);
 }
 
 extern "C" {

@@ -171,8 +171,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr uint32_t kSmemLayoutSw128 = 2;
 constexpr uint32_t kSmemLayoutSw128Base32 = 1;
 __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                             uint32_t layout_type) {
+                                                             uint32_t layout_type, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;

@@ -15,6 +15,7 @@
 //   warps 2-5: epilogue       — tcgen05.ld 32x32b.x32 -> registers -> alpha/bias/beta -> 128-bit global stores
 // Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty (MMA <-> epilogue).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -231,7 +232,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < kUmmaBK / 8; ++k) {
             const uint64_t da = a_mn ? make_smem_desc(a_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
-                                     : make_smem_desc(a_base + k * 32, 16, 1024, kSmemLayoutSw128);
+                                     : make_smem_desc(a_base + k * 32 + p.dbg_a_shift * 128, 16, 1024, kSmemLayoutSw128,
+                                                      p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0);
             const uint64_t db = b_mn ? make_smem_desc(b_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128);
             umma_tf32(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
@@ -592,6 +594,7 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
   p.stride_w = p.stride_h = 1;
   p.alpha = 1.f;
   p.err_flag = ctx->err_flag;
+  if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &p.dbg_a_shift, &p.dbg_base_mode);
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM
@@ -713,6 +716,10 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
   const int sh = static_cast<int>(d->stride_h), sw = static_cast<int>(d->stride_w);
   const int R = static_cast<int>(d->kh), S = static_cast<int>(d->kw);
+  if (R == 1 && S == 1 && sh == 1 && sw == 1 && d->pad_h == 0 && d->pad_w == 0 && d->c % 4 == 0 && d->k % 4 == 0) {
+    // pointwise: dx[pixels][C] = dy[pixels][K] * w[K][C]: a plain GEMM on the filter as stored (no transform, tiled loads)
+    return umma_gemm(ctx, false, false, d->n * P * Q, d->c, d->k, 1.f, dy, d->k, w, d->c, beta, dx, d->c, nullptr);
+  }
   const int bn = pick_bn(d->c);
 
   // Enumerate parity classes and their taps first so that unsupported geometry fails before any launch.
