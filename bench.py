@@ -45,6 +45,26 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) of the kernels whose
+    name starts with kernel_prefix, from the committed ncu summary of the same workload (profiles/*_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            t = json.load(f)
+        n = b = 0.0
+        for name, k in t["kernels"].items():
+            if name.startswith(kernel_prefix) and k.get("dram_bytes_per_launch", 0) > 0:
+                n += k["launches"]
+                b += k["dram_bytes_per_launch"] * k["launches"]
+        return (b / n if n else None), os.path.basename(files[-1])
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -208,6 +228,22 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss_dev.item())
     ctx.check()
+    # ---------------------------------------------------------------- per-node table (outside the timed region): 2 more steps
+    node_summary = None
+    try:
+        model.profile(True)
+        for _ in range(2):
+            model.train_step(X, T, loss_out=loss_dev)
+        rows = model.profile_table()
+        model.profile(False)
+        cls = {}
+        for k, n, ms, fl, by in rows:
+            c = k.split(".")[0] if k.split(".")[0] in ("conv", "bn") else "other"
+            e = cls.setdefault(c, {"ms_per_step": 0.0, "flops_per_step": 0.0, "bytes_per_step": 0.0})
+            e["ms_per_step"] += ms / 2; e["flops_per_step"] += fl / 2; e["bytes_per_step"] += by / 2
+        node_summary = cls
+    except Exception as e:  # noqa: BLE001
+        node_summary = None
     # ---------------------------------------------------------------- e2e: batch comes from pinned host memory each step
     copy_stream = torch.cuda.Stream()
     bufs = [(torch.empty_like(X), torch.empty_like(T)) for _ in range(2)]
@@ -260,8 +296,11 @@ def run_ours(args, rank, world, local_rank):
     tensor_tflops = (t_flops / (t_ms * 1e-3)) / 1e12 if t_ms > 0 else 0.0
     bn_gbs = (b_bytes / (b_ms * 1e-3)) / 1e9 if b_ms > 0 else 0.0
     if tensor_share >= bn_share:
+        traffic, traffic_src = ncu_traffic("umma_kernel")
         roofline = {"kernel": "zb::umma_kernel (tcgen05 kind::tf32 implicit-GEMM conv/GEMM)", "bound": "tensor", "achieved": tensor_tflops,
-                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+                    "peak": tf32_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tf32_peak if tf32_peak else None, "traffic": traffic,
+                    "traffic_source": f"profiles/{traffic_src}: ncu dram bytes per launch, averaged over the step's launches" if traffic else None,
+                    "algorithmic_bytes_per_launch_avg": node_summary["conv"]["bytes_per_step"] / max(t_ops / args.steps, 1) if node_summary else None,
                     "peak_source": f"{peaks['source']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate)",
                     "launches_per_step": t_ops / args.steps, "share_of_step": tensor_share,
                     "algorithmic_gflop_per_launch_avg": t_flops / max(t_ops, 1) / 1e9, "avg_launch_ms": t_ms / max(t_ops, 1)}
@@ -270,6 +309,13 @@ def run_ours(args, rank, world, local_rank):
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bn_gbs / peaks["hbm_gbs"], "traffic": None,
                     "peak_source": f"{peaks['source']}: hbm_gbs", "ops_per_step": b_ops / args.steps, "share_of_step": bn_share,
                     "algorithmic_mb_per_op_avg": b_bytes / max(b_ops, 1) / 1e6, "avg_op_ms": b_ms / max(b_ops, 1)}
+    by_node = None
+    if node_summary:
+        by_node = {c: {"ms_per_step": round(e["ms_per_step"], 3),
+                       "achieved_tflops": round(e["flops_per_step"] / e["ms_per_step"] / 1e9, 1) if e["flops_per_step"] else None,
+                       "achieved_gbs": round(e["bytes_per_step"] / e["ms_per_step"] / 1e6, 0) if e["bytes_per_step"] else None,
+                       "frac_of_hbm_peak": round(e["bytes_per_step"] / e["ms_per_step"] / 1e6 / peaks["hbm_gbs"], 3) if e["bytes_per_step"] else None}
+                   for c, e in node_summary.items()}
     secondary = {"tensor": {"achieved_tflops": tensor_tflops, "frac_of_tf32_peak": tensor_tflops / tf32_peak if tf32_peak else None,
                             "share_of_step": tensor_share, "launches_per_step": t_ops / args.steps},
                  "bn_hbm": {"achieved_gbs": bn_gbs, "frac_of_hbm_peak": bn_gbs / peaks["hbm_gbs"], "share_of_step": bn_share,
@@ -291,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_host},
-        "roofline": roofline, "roofline_by_class": secondary,
+        "roofline": roofline, "roofline_by_class": secondary, "tape_nodes_by_class": by_node,
         "step_model_flops": {"algorithmic_tflop_per_step_per_gpu": train_tflop_per_step,
                              "achieved_tflops_whole_step": train_tflop_per_step / (step_ms / 1e3) if step_ms > 0 else None},
         "cpu_baseline": cpu_baseline, "final_loss": final_loss, "hbm_bytes_reserved": model.bytes_reserved(),

@@ -196,6 +196,12 @@ int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m,
  * whatever rendezvous the host has (torch.distributed / a file), then every rank calls zb_dp_init.
  * zb_dp_allreduce_sum enqueues ncclAllReduce(sum) on the ctx comm stream, ordered after everything already
  * enqueued on the compute stream; zb_dp_wait makes the compute stream wait for it. */
+/* Bucket plan of the flat parameter / gradient buffers (pure host logic, callable without a GPU): parameters in forward
+ * order with kind 0 weight / 1 bias / 2 buffer; buckets of ~bucket_bytes are filled from the LAST parameter backwards
+ * (bucket 0 is complete first during backward); offsets are in elements, 16-byte aligned, weights before biases inside a
+ * bucket; buffers (kind 2) get offsets in their own area and bucket -1. */
+int zb_dp_plan_buckets(const int64_t* numel, const int* kind, int n, int64_t bucket_bytes, int elem_size, int* bucket_out,
+                       int64_t* offset_out, int* num_buckets, int64_t* total_elems, int64_t* buffer_elems);
 int zb_dp_unique_id(zb_ctx* ctx, void* host_id128);
 int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world);
 int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n);

@@ -65,6 +65,37 @@ using namespace zb;
 
 extern "C" {
 
+int zb_dp_plan_buckets(const int64_t* numel, const int* kind, int n, int64_t bucket_bytes, int elem_size, int* bucket_out,
+                       int64_t* offset_out, int* num_buckets, int64_t* total_elems, int64_t* buffer_elems) {
+  // Pure host logic (no CUDA call): parameters are listed in forward order; gradients arrive in reverse order during
+  // backward, so buckets are filled from the last parameter backwards (bucket 0 completes first).  Inside a bucket the
+  // weights come before the biases (AdamW decays weights() only, zenu-optimizer/src/adamw.rs:28,61-65); every tensor
+  // starts on a 16-byte boundary.  kind: 0 weight, 1 bias, 2 buffer (BN running statistics: no gradient, own area).
+  ZB_REQUIRE(numel && kind && bucket_out && offset_out && n >= 0 && bucket_bytes > 0 && elem_size > 0, "zb_dp_plan_buckets: bad argument");
+  auto align4 = [](int64_t v) { return (v + 3) & ~int64_t(3); };
+  int nb = 0;
+  int64_t acc = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    bucket_out[i] = -1;
+    if (kind[i] == 2) continue;
+    if (acc > 0 && (acc + numel[i]) * elem_size > bucket_bytes) { ++nb; acc = 0; }
+    bucket_out[i] = nb;
+    acc += numel[i];
+  }
+  const int buckets = nb + 1;
+  int64_t total = 0, buf_total = 0;
+  for (int b = 0; b < buckets; ++b)
+    for (int k = 0; k < 2; ++k)
+      for (int i = 0; i < n; ++i)
+        if (bucket_out[i] == b && kind[i] == k) { offset_out[i] = total; total += align4(numel[i]); }
+  for (int i = 0; i < n; ++i)
+    if (kind[i] == 2) { offset_out[i] = buf_total; buf_total += align4(numel[i]); }
+  if (num_buckets) *num_buckets = buckets;
+  if (total_elems) *total_elems = total;
+  if (buffer_elems) *buffer_elems = buf_total;
+  return ZB_OK;
+}
+
 int zb_dp_unique_id(zb_ctx* ctx, void* host_id128) {
   (void)ctx;
   int rc = load_nccl();

@@ -776,46 +776,33 @@ void ParamStore::build(Runtime& r, Model& model, uint64_t seed, int64_t bucket_b
   rt = &r;
   std::vector<ParamSpec> specs;
   model.collect(specs);
-  // bucket assignment in reverse forward order (gradients of the last layers arrive first)
+  // bucket assignment + flat layout: zb_dp_plan_buckets (pure host logic, shared with the CPU tests)
   const size_t esz = r.dtype == ZB_F64 ? 8 : 4;
-  std::vector<int> spec_bucket(specs.size(), -1);
-  int nb = 0;
-  int64_t acc = 0;
-  for (int i = static_cast<int>(specs.size()) - 1; i >= 0; --i) {
-    if (specs[i].kind == 2) continue;
-    int64_t n = 1;
-    for (auto s : specs[i].shape) n *= s;
-    if (acc > 0 && (acc + n) * static_cast<int64_t>(esz) > bucket_bytes) { ++nb; acc = 0; }
-    spec_bucket[i] = nb;
-    acc += n;
-  }
-  const int num_buckets = nb + 1;
-  buckets.assign(num_buckets, Bucket{0, 0, 0, 0});
-  // flat layout: bucket 0 | bucket 1 | ... ; inside a bucket weights first, then biases (AdamW decays weights only);
-  // every tensor starts on a 16-byte boundary so the vector kernels apply
-  auto align4 = [](int64_t n) { return (n + 3) & ~int64_t(3); };
-  int64_t total = 0, buf_total = 0;
+  std::vector<int64_t> numels(specs.size());
+  std::vector<int> kinds(specs.size()), spec_bucket(specs.size(), -1);
   std::vector<int64_t> offsets(specs.size(), 0);
-  for (int b = 0; b < num_buckets; ++b) {
-    buckets[b].offset = total;
-    for (int kind = 0; kind < 2; ++kind)
-      for (size_t i = 0; i < specs.size(); ++i)
-        if (spec_bucket[i] == b && specs[i].kind == kind) {
-          int64_t n = 1;
-          for (auto s : specs[i].shape) n *= s;
-          offsets[i] = total;
-          total += align4(n);
-          buckets[b].total++;
-        }
-    buckets[b].numel = total - buckets[b].offset;
+  for (size_t i = 0; i < specs.size(); ++i) {
+    int64_t n = 1;
+    for (auto sdim : specs[i].shape) n *= sdim;
+    numels[i] = n;
+    kinds[i] = specs[i].kind;
   }
-  for (size_t i = 0; i < specs.size(); ++i)
-    if (specs[i].kind == 2) {
-      int64_t n = 1;
-      for (auto s : specs[i].shape) n *= s;
-      offsets[i] = buf_total;
-      buf_total += align4(n);
-    }
+  int num_buckets = 0;
+  int64_t total = 0, buf_total = 0;
+  check_rc(zb_dp_plan_buckets(numels.data(), kinds.data(), static_cast<int>(specs.size()), bucket_bytes, static_cast<int>(esz),
+                              spec_bucket.data(), offsets.data(), &num_buckets, &total, &buf_total), "bucket plan");
+  buckets.assign(num_buckets, Bucket{0, 0, 0, 0});
+  for (int b = 0; b < num_buckets; ++b) {
+    int64_t lo = -1, hi = 0;
+    for (size_t i = 0; i < specs.size(); ++i)
+      if (spec_bucket[i] == b) {
+        if (lo < 0 || offsets[i] < lo) lo = offsets[i];
+        hi = std::max(hi, offsets[i] + ((numels[i] + 3) & ~int64_t(3)));
+        buckets[b].total++;
+      }
+    buckets[b].offset = lo < 0 ? 0 : lo;
+    buckets[b].numel = hi - buckets[b].offset;
+  }
   flat_params = r.zeros({total});
   flat_grads = r.zeros({total});
   flat_buffers = r.zeros({std::max<int64_t>(buf_total, 4)});
