@@ -208,7 +208,6 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     import ctypes
-    ops.check(lib.zb_ctx_profile_enable(ctx.handle, 1))
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -219,6 +218,16 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
+    # same K steps again with a CUDA-event pair around every tensor-core launch / BatchNorm op (the live roofline numbers);
+    # kept out of the headline region because ~280 extra event records per step cost ~2 % of it
+    ops.check(lib.zb_ctx_profile_enable(ctx.handle, 1))
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for _ in range(args.steps):
+        model.train_step(X, T, loss_out=loss_dev)
+    pv1.record()
+    torch.cuda.synchronize()
+    prof_elapsed_ms = pv0.elapsed_time(pv1)
     prof = {}
     for cls, name in ((0, "tensor"), (1, "bn")):
         n_ops, ms, work = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
@@ -291,8 +300,8 @@ def run_ours(args, rank, world, local_rank):
     t_ops, t_ms, t_flops = prof["tensor"]
     b_ops, b_ms, b_bytes = prof["bn"]
     step_ms = elapsed_ms / args.steps
-    tensor_share = t_ms / elapsed_ms if elapsed_ms > 0 else 0.0
-    bn_share = b_ms / elapsed_ms if elapsed_ms > 0 else 0.0
+    tensor_share = t_ms / prof_elapsed_ms if prof_elapsed_ms > 0 else 0.0
+    bn_share = b_ms / prof_elapsed_ms if prof_elapsed_ms > 0 else 0.0
     tensor_tflops = (t_flops / (t_ms * 1e-3)) / 1e12 if t_ms > 0 else 0.0
     bn_gbs = (b_bytes / (b_ms * 1e-3)) / 1e9 if b_ms > 0 else 0.0
     if tensor_share >= bn_share:
@@ -350,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="resnet50", choices=["resnet50", "resnet18", "small_cnn"])
