@@ -67,6 +67,164 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
   }
 }
 
+// ---------------------------------------------------------------------------------------------- epilogue (warps 2-5)
+// Shared by the implicit-GEMM kernel and the halo-reuse conv kernel: drains finished TMEM accumulators tile by tile.
+template <int BN>
+__device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err) {
+  const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
+  struct LL { int EPI_OFFSET; } Lv{epi_offset};
+    // ================================ epilogue ================================
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter).  Per 32-column chunk: tcgen05.ld (lane = row) ->
+    // XOR-swizzled smem staging -> read back so that 8 lanes cover one row's 128 bytes -> coalesced 128-bit global
+    // stores (4 full cache lines per instruction) with alpha / bias / beta applied on the way out.
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float4* stage4 = reinterpret_cast<float4*>(smem + Lv.EPI_OFFSET + ew * 4096);
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const bool partial = p.splits > 1;
+    const int sub_row = lane >> 3, piece = lane & 7;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
+      // element offset of this lane's row inside D (or -1 when the row does not exist)
+      long long my_off = -1;
+      {
+        const int l = ew * 32 + lane;
+        if (p.out_mode == OUT_WINDOW) {
+          const int per_img = p.win_p_tiles * p.win_q_tiles;
+          const int img = tc.m_blk / per_img, rem = tc.m_blk - img * per_img;
+          const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
+          const int pl = l / p.win_box_q, ql = l - pl * p.win_box_q;
+          const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
+          if (pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
+            my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
+        } else {
+          const int row = m0 + l;
+          if (row < p.M) {
+            long long orow = row;
+            if (p.out_mode == OUT_SCATTER) {
+              const int pq = p.conv_P * p.conv_Q;
+              const int img = row / pq, rem = row - img * pq;
+              const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+              orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
+            }
+            my_off = orow * p.ldd;
+          }
+        }
+        if (my_off >= 0) my_off += static_cast<long long>(tc.split) * p.split_stride + tc.tap * p.tap_col_stride;
+      }
+      if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
+      tc_fence_after();
+      if (p.out_mode == OUT_WDGRAD) {
+        // accumulator D[q][s*4+c] (N = 32) -> shared [128 q][32] tile (all four warps) -> every thread overlap-adds the
+        // filter columns s that reach its output element and stores the dense row dX[n][h][0..W)[0..C) coalesced
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free: the MMA warp may start the next tile
+        const float* tile_s = reinterpret_cast<const float*>(smem + Lv.EPI_OFFSET);
+        const int row_elems = p.dg_W * p.dg_C;
+        int kb0, kb1;
+        tile_kb_range(p, tc, kb0, kb1);
+        float* out_row = p.D + static_cast<long long>(tc.m_blk) * row_elems;
+        for (int o = ew * 32 + lane; o < row_elems; o += 128) {
+          const int w = o / p.dg_C, c = o - w * p.dg_C;
+          float sum = 0.f;
+          if (kb1 > kb0) {
+            for (int sx = (w + p.dg_pw) % p.dg_sw; sx < p.dg_S; sx += p.dg_sw) {
+              const int q = (w + p.dg_pw - sx) / p.dg_sw;
+              if (q >= 0 && q < p.conv_Q) {
+                const int j = sx * 4 + c;
+                sum += tile_s[q * 32 + (((j >> 2) ^ (q & 7)) << 2) + (j & 3)];
+              }
+            }
+          }
+          out_row[o] = sum;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+        __syncwarp();
+        const int col = col0 + piece * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!partial && p.bias != nullptr) {
+          if (col < p.N) bv.x = __ldg(p.bias + col);
+          if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
+          if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
+          if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
+        }
+        long long offs[8];
+        float4 vals[8], olds[8];
+        const bool col_ok = col < p.N;
+        const bool full_vec = vec_ok && col + 3 < p.N;
+        const bool use_beta = !partial && p.beta != 0.f;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub_row;
+          offs[it] = __shfl_sync(0xffffffffu, my_off, rr);
+          vals[it] = stage4[rr * 8 + (piece ^ (rr & 7))];
+        }
+        if (use_beta && full_vec) {  // all reads of the old tile in flight before the first dependent store
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (offs[it] < 0 || !col_ok) continue;
+          float4 o = vals[it];
+          float* dst = p.D + offs[it] + col;
+          if (!partial) {
+            o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
+          }
+          if (full_vec) {
+            if (use_beta) {
+              o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
+            }
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) {
+                float val = ov[e];
+                if (use_beta) val += p.beta * dst[e];
+                dst[e] = val;
+              }
+          }
+        }
+        __syncwarp();  // staging is rewritten by the next chunk
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -248,155 +406,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ================================ epilogue ================================
-    // Each warp owns 32 accumulator rows (its TMEM lane quarter).  Per 32-column chunk: tcgen05.ld (lane = row) ->
-    // XOR-swizzled smem staging -> read back so that 8 lanes cover one row's 128 bytes -> coalesced 128-bit global
-    // stores (4 full cache lines per instruction) with alpha / bias / beta applied on the way out.
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float4* stage4 = reinterpret_cast<float4*>(smem + L::EPI_OFFSET + ew * 4096);
-    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
-    const bool partial = p.splits > 1;
-    const int sub_row = lane >> 3, piece = lane & 7;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
-      const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
-      // element offset of this lane's row inside D (or -1 when the row does not exist)
-      long long my_off = -1;
-      {
-        const int l = ew * 32 + lane;
-        if (p.out_mode == OUT_WINDOW) {
-          const int per_img = p.win_p_tiles * p.win_q_tiles;
-          const int img = tc.m_blk / per_img, rem = tc.m_blk - img * per_img;
-          const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
-          const int pl = l / p.win_box_q, ql = l - pl * p.win_box_q;
-          const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
-          if (pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
-            my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
-        } else {
-          const int row = m0 + l;
-          if (row < p.M) {
-            long long orow = row;
-            if (p.out_mode == OUT_SCATTER) {
-              const int pq = p.conv_P * p.conv_Q;
-              const int img = row / pq, rem = row - img * pq;
-              const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
-              orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
-            }
-            my_off = orow * p.ldd;
-          }
-        }
-        if (my_off >= 0) my_off += static_cast<long long>(tc.split) * p.split_stride + tc.tap * p.tap_col_stride;
-      }
-      if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
-      tc_fence_after();
-      if (p.out_mode == OUT_WDGRAD) {
-        // accumulator D[q][s*4+c] (N = 32) -> shared [128 q][32] tile (all four warps) -> every thread overlap-adds the
-        // filter columns s that reach its output element and stores the dense row dX[n][h][0..W)[0..C) coalesced
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
-                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
-        tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free: the MMA warp may start the next tile
-        const float* tile_s = reinterpret_cast<const float*>(smem + L::EPI_OFFSET);
-        const int row_elems = p.dg_W * p.dg_C;
-        int kb0, kb1;
-        tile_kb_range(p, tc, kb0, kb1);
-        float* out_row = p.D + static_cast<long long>(tc.m_blk) * row_elems;
-        for (int o = ew * 32 + lane; o < row_elems; o += 128) {
-          const int w = o / p.dg_C, c = o - w * p.dg_C;
-          float sum = 0.f;
-          if (kb1 > kb0) {
-            for (int sx = (w + p.dg_pw) % p.dg_sw; sx < p.dg_S; sx += p.dg_sw) {
-              const int q = (w + p.dg_pw - sx) / p.dg_sw;
-              if (q >= 0 && q < p.conv_Q) {
-                const int j = sx * 4 + c;
-                sum += tile_s[q * 32 + (((j >> 2) ^ (q & 7)) << 2) + (j & 3)];
-              }
-            }
-          }
-          out_row[o] = sum;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
-                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
-        __syncwarp();
-        const int col = col0 + piece * 4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!partial && p.bias != nullptr) {
-          if (col < p.N) bv.x = __ldg(p.bias + col);
-          if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
-          if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
-          if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
-        }
-        long long offs[8];
-        float4 vals[8], olds[8];
-        const bool col_ok = col < p.N;
-        const bool full_vec = vec_ok && col + 3 < p.N;
-        const bool use_beta = !partial && p.beta != 0.f;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub_row;
-          offs[it] = __shfl_sync(0xffffffffu, my_off, rr);
-          vals[it] = stage4[rr * 8 + (piece ^ (rr & 7))];
-        }
-        if (use_beta && full_vec) {  // all reads of the old tile in flight before the first dependent store
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (offs[it] < 0 || !col_ok) continue;
-          float4 o = vals[it];
-          float* dst = p.D + offs[it] + col;
-          if (!partial) {
-            o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
-          }
-          if (full_vec) {
-            if (use_beta) {
-              o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
-            }
-            *reinterpret_cast<float4*>(dst) = o;
-          } else {
-            const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (col + e < p.N) {
-                float val = ov[e];
-                if (use_beta) val += p.beta * dst[e];
-                dst[e] = val;
-              }
-          }
-        }
-        __syncwarp();  // staging is rewritten by the next chunk
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
+    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err);
   }
 
   tc_fence_before();
@@ -406,6 +416,146 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
+
+// ---------------------------------------------------------------------------------------------- halo-reuse conv kernel
+// Stride-1 R x S convolutions (fprop, and dgrad written as a conv over dY with the flipped filter).  The implicit-GEMM kernel
+// above fetches the activation tile once per filter tap (9x for 3x3) and is bound by L2->SM traffic on the 64/128-channel
+// layers.  Here one TMA box lands a raster of (tp + R - 1) x Wr input pixels (Wr = W + 2*pad: halo columns come in as TMA
+// zero fill) for a 32-channel chunk, each pixel one 128-byte row of the K-major SWIZZLE_128B layout; the M tile is the raster
+// positions of tp output rows, and tap (r, s) is the SAME smem data read through a descriptor that starts r*Wr + s rows later
+// (the hardware swizzle is a function of the absolute smem address, so a start that is 128- but not 1024-byte aligned is
+// legal: measured with tools/probe_desc_shift.py).  Filter tiles stream through their own ring, or stay resident for the
+// whole persistent CTA when the filter fits (64 -> 64 channels).  Output positions in halo columns are computed and dropped.
+constexpr int kHaloMaxB = 24;
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.halo_slots * p.halo_slot_bytes;
+  const int epi_off = p.halo_slots * p.halo_slot_bytes + p.halo_b_stages * B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096);
+  uint64_t* a_empty = a_full + 4;
+  uint64_t* b_full = a_empty + 4;
+  uint64_t* b_empty = b_full + kHaloMaxB;
+  uint64_t* tfull_bar = b_empty + kHaloMaxB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  volatile int* err = p.err_flag;
+  if (warp == 0) {
+    if (elect_one()) { prefetch_tensormap(&tmA); prefetch_tensormap(&tmB); }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < kHaloMaxB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int taps = p.ntaps, chunks = p.c_chunks;
+  const bool resident = p.halo_b_resident != 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int ai = 0, bi = 0;
+      uint32_t aph = 0, bph = 0;
+      if (resident) {  // the whole [BN][taps*C] filter slice, once per CTA (n_tiles == 1)
+        mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(taps * chunks) * B_BYTES);
+        for (int c = 0; c < chunks; ++c)
+          for (int t = 0; t < taps; ++t)
+            tma_load_2d(sB + (c * taps + t) * B_BYTES, &tmB, &b_full[0], t * p.b_tap_stride + c * kUmmaBK, 0);
+      }
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+        const int img = m_blk / p.win_p_tiles, pt = m_blk - img * p.win_p_tiles;
+        const int h0 = pt * p.win_box_p + p.lower_h;
+        for (int c = 0; c < chunks && ok; ++c) {
+          if (!mbar_wait(&a_empty[ai], aph ^ 1, err)) { ok = false; break; }
+          mbar_arrive_expect_tx(&a_full[ai], static_cast<uint32_t>(p.halo_raster_bytes));
+          tma_load_4d(sA + ai * p.halo_slot_bytes, &tmA, &a_full[ai], c * kUmmaBK, p.lower_w, h0, img);
+          if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
+          if (!resident) {
+            for (int t = 0; t < taps; ++t) {
+              if (!mbar_wait(&b_empty[bi], bph ^ 1, err)) { ok = false; break; }
+              mbar_arrive_expect_tx(&b_full[bi], B_BYTES);
+              tma_load_2d(sB + bi * B_BYTES, &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK, n_blk * BN);
+              if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, 0, 0);
+      int ai = 0, bi = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      bool ok = true;
+      if (resident) ok = mbar_wait(&b_full[0], 0, err);
+      const uint32_t a_addr0 = smem_u32(sA), b_addr0 = smem_u32(sB);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int c = 0; c < chunks && ok; ++c) {
+          if (!mbar_wait(&a_full[ai], aph, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_base = a_addr0 + ai * p.halo_slot_bytes;
+          for (int t = 0; t < taps; ++t) {
+            uint32_t b_base;
+            if (resident) {
+              b_base = b_addr0 + (c * taps + t) * B_BYTES;
+            } else {
+              if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
+              tc_fence_after();
+              b_base = b_addr0 + bi * B_BYTES;
+            }
+            const uint32_t a_tap = a_base + static_cast<uint32_t>(p.tap_w[t]) * 128u;
+#pragma unroll
+            for (int k = 0; k < kUmmaBK / 8; ++k)
+              umma_tf32(d_tmem, make_smem_desc(a_tap + k * 32, 16, 1024, kSmemLayoutSw128),
+                        make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128), idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+            if (!resident) {
+              umma_commit(&b_empty[bi]);
+              if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[ai]);
+          if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
+        }
+        if (!ok) break;
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 
 // out[i] = alpha * sum_s partial[s][i] + bias[col] + beta * out[i]   (deterministic split-K reduction)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long rows,
@@ -642,6 +792,120 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
   return run_with_splits(ctx, bn, ma, mb, p, m, n, c, ldc, alpha, beta, bias);
 }
 
+// ---------------------------------------------------------------------------------------------- halo conv planner
+struct HaloPlan {
+  int Wr, tp, p_tiles, slots, slot_bytes, raster_bytes, b_stages, resident, bn;
+  size_t smem;
+};
+// in: [N][H][W][Cin] NHWC; filt: [Kout][R*S*Cin] (tap-major, channel-minor); out: [N][P][Q][Kout] with P = H + 2*ph - R + 1.
+static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long long Cin, long long Kout, int R, int S, int ph, int pw,
+                      HaloPlan* hp) {
+  (void)ctx;
+  if (getenv("ZENU_B200_NO_HALO")) return false;
+  const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
+  if (R * S < 2 || R * S > kUmmaMaxTaps || Cin % 32 != 0 || Kout % 4 != 0 || P <= 0 || Q <= 0 || ph < 0 || pw < 0) return false;
+  const long long Wr = W + 2 * pw;  // raster width = Q + S - 1
+  if (Wr > kUmmaBM || Wr > 256) return false;
+  int tp = static_cast<int>(std::min<long long>(P, kUmmaBM / Wr));
+  // balance the row blocks of an image (14 rows, tp 8 -> 7 + 7 instead of 8 + 6)
+  const int p_tiles = ceil_div(P, tp);
+  tp = ceil_div(P, p_tiles);
+  if (tp + R - 1 > 256) return false;
+  if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) return false;  // too many dead MMA rows
+  hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles;
+  hp->bn = pick_bn(Kout);
+  hp->raster_bytes = (tp + R - 1) * static_cast<int>(Wr) * 128;
+  // rows a tap descriptor may touch beyond the raster ((R-1)*Wr + S-1 + 127 is the last row read) stay inside the slot
+  const int last_row = (R - 1) * static_cast<int>(Wr) + (S - 1) + kUmmaBM;
+  hp->slot_bytes = (std::max(hp->raster_bytes, last_row * 128) + 1023) & ~1023;
+  const int b_bytes = hp->bn * 128;
+  const int chunks = static_cast<int>(Cin / 32);
+  const int budget = 227 * 1024 - 1024 - 16384 - 1024;  // alignment slack, epilogue staging, barriers
+  const int n_tiles = ceil_div(Kout, hp->bn);
+  hp->resident = 0;
+  if (n_tiles == 1 && R * S * chunks <= kHaloMaxB && R * S * chunks * b_bytes + 2 * hp->slot_bytes <= budget) {
+    hp->resident = 1;
+    hp->b_stages = R * S * chunks;
+    hp->slots = std::min(4, (budget - hp->b_stages * b_bytes) / hp->slot_bytes);
+  } else {
+    hp->slots = std::min(3, std::max(2, chunks >= 2 ? 3 : 2));
+    int left = budget - hp->slots * hp->slot_bytes;
+    if (left < 4 * b_bytes) { hp->slots = 2; left = budget - 2 * hp->slot_bytes; }
+    hp->b_stages = std::min(kHaloMaxB, left / b_bytes);
+    if (hp->b_stages < 3) return false;
+  }
+  hp->smem = static_cast<size_t>(hp->slots) * hp->slot_bytes + static_cast<size_t>(hp->b_stages) * b_bytes + 16384 + 1024 + 1024;
+  return true;
+}
+
+template <int BN>
+static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, size_t smem) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
+  prof_begin(ctx, PROF_TENSOR);
+  halo_conv_kernel<BN><<<grid, 192, smem, ctx->stream>>>(a, b, p);
+  prof_end(ctx, PROF_TENSOR, p.prof_flops);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+// tap_r/tap_s: raster offset of tap t (filter row / column in the orientation of `filt`)
+static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long long H, long long W, long long Cin, long long Kout, int R,
+                          int S, int ph, int pw, const float* in, const float* filt, const float* bias, float* out, float beta,
+                          double flops) {
+  const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
+  CUtensorMap ma, mb;
+  {
+    ZB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "TMA operand must be 16-byte aligned");
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 4, static_cast<cuuint64_t>(W) * Cin * 4, static_cast<cuuint64_t>(H) * W * Cin * 4};
+    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(hp.Wr), static_cast<cuuint32_t>(hp.tp + R - 1), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ctx->encode_tiled(&ma, operand_dtype(), 4, const_cast<float*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (halo raster) failed (%d)", int(r)); return ZB_ERR_CUDA; }
+  }
+  const int taps = R * S;
+  int rc = make_map_2d(ctx, &mb, filt, static_cast<long long>(taps) * Cin, Kout, static_cast<long long>(taps) * Cin, 32, hp.bn);
+  if (rc != ZB_OK) return rc;
+  UmmaParams p;
+  init_params(p, ctx);
+  p.a_mode = A_TILED_K;   // (unused by the halo kernel; the epilogue only looks at out_mode)
+  p.b_mode = B_TILED_K;
+  p.out_mode = OUT_WINDOW;
+  p.M = static_cast<int>(N * P * Q);
+  p.N = static_cast<int>(Kout);
+  p.m_tiles = static_cast<int>(N) * hp.p_tiles;
+  p.n_tiles = ceil_div(Kout, hp.bn);
+  p.win_box_q = hp.Wr; p.win_box_p = hp.tp; p.win_q_tiles = 1; p.win_p_tiles = hp.p_tiles;
+  p.conv_P = static_cast<int>(P); p.conv_Q = static_cast<int>(Q);
+  p.lower_w = -pw; p.lower_h = -ph;
+  p.ntaps = taps;
+  p.c_chunks = static_cast<int>(Cin / 32);
+  p.b_tap_stride = static_cast<int>(Cin);
+  for (int r = 0; r < R; ++r)
+    for (int sx = 0; sx < S; ++sx) p.tap_w[r * S + sx] = static_cast<uint16_t>(r * hp.Wr + sx);
+  p.halo_slots = hp.slots; p.halo_slot_bytes = hp.slot_bytes; p.halo_raster_bytes = hp.raster_bytes;
+  p.halo_b_stages = hp.b_stages; p.halo_b_resident = hp.resident;
+  p.kb_total = taps * p.c_chunks;
+  p.prof_flops = flops;
+  p.D = out;
+  p.ldd = Kout;
+  p.alpha = 1.f; p.beta = beta; p.bias = bias;
+  finish_split_fields(p, 1);
+  p.split_stride = 0;
+  switch (hp.bn) {
+    case 32: return halo_launch_bn<32>(ctx, ma, mb, p, hp.smem);
+    case 64: return halo_launch_bn<64>(ctx, ma, mb, p, hp.smem);
+    case 128: return halo_launch_bn<128>(ctx, ma, mb, p, hp.smem);
+    default: return halo_launch_bn<256>(ctx, ma, mb, p, hp.smem);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- conv
 bool umma_conv_supported(const zb_conv2d_desc* d) {
   if (d->c % 32 != 0 || d->k % 4 != 0) return false;
@@ -660,6 +924,13 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
   const long long M = d->n * P * Q;
   const int bn = pick_bn(d->k);
   const int taps = static_cast<int>(d->kh * d->kw);
+  if (d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1 && taps > 1) {
+    HaloPlan hp;
+    if (halo_plan(ctx, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw), static_cast<int>(d->pad_h),
+                  static_cast<int>(d->pad_w), &hp))
+      return umma_conv_halo(ctx, hp, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw),
+                            static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, 0.f, 2.0 * M * d->k * d->c * taps);
+  }
   CUtensorMap ma, mb;
   UmmaParams p;
   init_params(p, ctx);
@@ -719,6 +990,26 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if (R == 1 && S == 1 && sh == 1 && sw == 1 && d->pad_h == 0 && d->pad_w == 0 && d->c % 4 == 0 && d->k % 4 == 0) {
     // pointwise: dx[pixels][C] = dy[pixels][K] * w[K][C]: a plain GEMM on the filter as stored (no transform, tiled loads)
     return umma_gemm(ctx, false, false, d->n * P * Q, d->c, d->k, 1.f, dy, d->k, w, d->c, beta, dx, d->c, nullptr);
+  }
+  if (sh == 1 && sw == 1 && d->dil_h == 1 && d->dil_w == 1 && R * S > 1 && d->pad_h <= R - 1 && d->pad_w <= S - 1) {
+    // stride 1: dx = conv(dy, flipped filter) with padding R-1-pad; halo-reuse kernel over the dY raster
+    HaloPlan hp;
+    const int ph2 = R - 1 - static_cast<int>(d->pad_h), pw2 = S - 1 - static_cast<int>(d->pad_w);
+    if (halo_plan(ctx, d->n, P, Q, d->k, d->c, R, S, ph2, pw2, &hp)) {
+      void* ws = nullptr;
+      const size_t elems = static_cast<size_t>(d->c) * R * S * d->k;
+      int rc2 = ctx_workspace(ctx, elems * sizeof(float), &ws);
+      if (rc2 != ZB_OK) return rc2;
+      float* wt = static_cast<float*>(ws);
+      TapList tl;
+      for (int t = 0; t < R * S; ++t) tl.rs[t] = R * S - 1 - t;   // tap (r', s') of the flipped filter = (R-1-r', S-1-s')
+      const long long total = static_cast<long long>(elems);
+      const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
+      dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), R * S, tl);
+      ZB_LAUNCH_CHECK(ctx);
+      return umma_conv_halo(ctx, hp, d->n, P, Q, d->k, d->c, R, S, ph2, pw2, dy, wt, nullptr, dx, beta,
+                            2.0 * d->n * P * Q * d->k * d->c * R * S);
+    }
   }
   const int bn = pick_bn(d->c);
 
