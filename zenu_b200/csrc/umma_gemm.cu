@@ -82,8 +82,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     int acc = 0;
     uint32_t acc_phase = 0;
     float4* stage4 = reinterpret_cast<float4*>(smem + Lv.EPI_OFFSET + ew * 4096);
+    const uint32_t stage_u32 = smem_u32(stage4);
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+                        ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
+                        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const bool partial = p.splits > 1;
     const int sub_row = lane >> 3, piece = lane & 7;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -155,6 +157,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
+      // rows this lane stores after the transpose (8 per chunk, the same 8 for every chunk of the tile)
+      long long offs[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + sub_row);
+      const bool use_beta = !partial && p.beta != 0.f;
+      const bool plain = partial || (p.alpha == 1.f && p.bias == nullptr && !use_beta);   // store the accumulator as is
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -162,55 +170,60 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
         tmem_ld_wait();
+        if (p.dbg_epi == 2) continue;
 #pragma unroll
         for (int v = 0; v < 8; ++v)
-          stage4[lane * 8 + (v ^ (lane & 7))] = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
-                                                            __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+          sts128(stage_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), __uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                 __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
         __syncwarp();
         const int col = col0 + piece * 4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!partial && p.bias != nullptr) {
-          if (col < p.N) bv.x = __ldg(p.bias + col);
-          if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
-          if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
-          if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
-        }
-        long long offs[8];
-        float4 vals[8], olds[8];
-        const bool col_ok = col < p.N;
-        const bool full_vec = vec_ok && col + 3 < p.N;
-        const bool use_beta = !partial && p.beta != 0.f;
+        float4 vals[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + sub_row;
-          offs[it] = __shfl_sync(0xffffffffu, my_off, rr);
-          vals[it] = stage4[rr * 8 + (piece ^ (rr & 7))];
+          vals[it] = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
         }
-        if (use_beta && full_vec) {  // all reads of the old tile in flight before the first dependent store
+        if (vec_ok && col0 + 32 <= p.N) {   // warp-uniform fast path: whole 32-column chunk, 128-bit stores
+          if (plain) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it)
-            olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if (offs[it] < 0 || !col_ok) continue;
-          float4 o = vals[it];
-          float* dst = p.D + offs[it] + col;
-          if (!partial) {
-            o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
-          }
-          if (full_vec) {
-            if (use_beta) {
-              o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
-            }
-            *reinterpret_cast<float4*>(dst) = o;
+            for (int it = 0; it < 8; ++it)
+              if (offs[it] >= 0 && p.dbg_epi != 1) *reinterpret_cast<float4*>(p.D + offs[it] + col) = vals[it];
           } else {
-            const float ov[4] = {o.x, o.y, o.z, o.w};
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            float4 olds[8];
+            if (use_beta) {  // all reads of the old tile in flight before the first dependent store
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if (offs[it] < 0) continue;
+              float4 o = vals[it];
+              o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
+              if (use_beta) {
+                o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
+              }
+              *reinterpret_cast<float4*>(p.D + offs[it] + col) = o;
+            }
+          }
+        } else {   // ragged chunk or unaligned output: element-wise (kept out of registers: rare path)
+#pragma unroll 1
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub_row;
+            const long long off = __shfl_sync(0xffffffffu, my_off, rr);
+            const float4 v4 = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
+            if (off < 0) continue;
+            float* dst = p.D + off + col;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (col + e < p.N) {
-                float val = ov[e];
-                if (use_beta) val += p.beta * dst[e];
+                float val = e == 0 ? v4.x : (e == 1 ? v4.y : (e == 2 ? v4.z : v4.w));
+                if (!partial) {
+                  val = p.alpha * val + (p.bias != nullptr ? __ldg(p.bias + col + e) : 0.f);
+                  if (use_beta) val += p.beta * dst[e];
+                }
                 dst[e] = val;
               }
           }
@@ -745,6 +758,7 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
   p.alpha = 1.f;
   p.err_flag = ctx->err_flag;
   if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &p.dbg_a_shift, &p.dbg_base_mode);
+  if (const char* e = getenv("ZENU_B200_DBG_EPI")) p.dbg_epi = atoi(e);
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM

@@ -64,7 +64,7 @@ struct UmmaParams {
   // halo-reuse conv kernel (stride-1 RxS convs): one smem raster of (tp + R - 1) x Wr input pixels per 32-channel chunk
   // serves every filter tap through UMMA descriptors that start tap_w[t] rows (128 bytes each) into the raster
   int halo_slots, halo_slot_bytes, halo_raster_bytes, halo_b_stages, halo_b_resident;
-  int dbg_a_shift, dbg_base_mode;  // experiments only (ZENU_B200_DBG_ASHIFT): A descriptor start shifted by whole 128-byte rows
+  int dbg_a_shift, dbg_base_mode, dbg_epi;  // experiments only (ZENU_B200_DBG_ASHIFT): A descriptor start shifted by whole 128-byte rows
   int* err_flag;              // device word set to 1 on an mbarrier timeout
   double prof_flops;          // host only: algorithmic FLOPs of this launch (profiling)
 };
