@@ -50,7 +50,24 @@ CASES = [
     ("resnet18", 4, 64, 10, "fp32", "adam", 1e-3, 2e-4, 6e-4, 2e-4),
     ("resnet50", 16, 64, 8, "tf32", "sgd", 1e-3, 1e-2, 0.2, 8e-2),
     ("resnet50", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 0.1, 2e-3),
+    # the same network with the last BatchNorm scale of every residual branch at 0.1 ("zero-init residual" practice): at
+    # plain initialisation ResNet-50's gradient is chaotic under ANY operand rounding (ReLU-mask flips: oracle rne vs rna
+    # tf32 rounding alone moves the whole gradient by 41 %), damped it is well conditioned and the loss curve is pinned tightly
+    ("resnet50:damped", 16, 64, 8, "tf32", "sgd", 1e-3, 2e-3, 5e-3, 3e-2),
+    ("resnet50:damped", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 1e-3, 2e-3),
 ]
+
+
+def make_params(arch, classes):
+    """He-normal / reference Linear init (oracle.init_params); "<arch>:damped" sets the last BN scale of each residual branch to 0.1."""
+    base, _, variant = arch.partition(":")
+    params = zm.init_params(base, classes, seed=42)
+    if variant == "damped":
+        last = "bn3" if base == "resnet50" else "bn2"
+        for k in params:
+            if k.endswith(last + ".batch_norm_2d.scale"):
+                params[k][:] = 0.1
+    return base, params
 
 
 def whole(grads, names):
@@ -80,17 +97,18 @@ def oracle_self_sensitivity(arch, classes, params, x, t, math):
         finally:
             zo.use_plain_gemm()
     names = [k for k in ga if np.abs(ga[k]).max() >= 1e-6]
-    return rel(whole(gb, names), whole(ga, names)), abs(la - lb) / max(1.0, abs(la)), la, ga, names
+    twins = (a, ga, b, gb) if math == "tf32" else None
+    return rel(whole(gb, names), whole(ga, names)), abs(la - lb) / max(1.0, abs(la)), la, ga, names, twins
 
 
 @pytest.mark.parametrize("arch,n,hw,classes,math,opt,lr,ltol,ctol,lasttol", CASES)
 @pytest.mark.parametrize("fused", [True, False])
 def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol, ctol, lasttol, fused):
     pkg, ops, nn = zb
-    if arch == "resnet50" and not fused:
+    if arch.startswith("resnet50") and not fused:
         pytest.skip("covered by the fused variant")
     ctx = ops.Context(math=pkg.ZB_MATH_TF32 if math == "tf32" else pkg.ZB_MATH_FP32)
-    params = zm.init_params(arch, classes, seed=42)
+    arch, params = make_params(arch, classes)
     oracle = zm.OracleModel(arch, classes, {k: v.copy() for k, v in params.items()})   # the reference's f32 arithmetic
     model = nn.Model(ctx, arch, classes, fused=fused, seed=1)
     load_params(model, params)
@@ -116,7 +134,7 @@ def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol,
     last = "fc.linear.weight" if "fc.linear.weight" in grads_ref else "linear2.linear.weight"
     assert rel(got[last], grads_ref[last]) < lasttol, (last, rel(got[last], grads_ref[last]))
     # whole gradient: within 3x the reference algorithm's own sensitivity at this arithmetic (see oracle_self_sensitivity)
-    sens, _, _, g_model, names = oracle_self_sensitivity(arch, classes, params, x, t, math)
+    sens, _, _, g_model, names, twins = oracle_self_sensitivity(arch, classes, params, x, t, math)
     floor = 2e-3 if math == "tf32" else 2e-5
     err_model = rel(whole(got, names), whole(g_model, names))     # vs the oracle with the device's operand rounding modelled
     err_ref = rel(whole(got, names), whole(grads_ref, names))     # vs the reference's exact f32 arithmetic
@@ -131,11 +149,20 @@ def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol,
             assert rel(got[name], grads_ref[name]) < ptol, name
     oracle.update(grads_ref, **kw)
     model.update()
+    if twins:       # the two tf32-operand oracles (rne / rna rounding) train along: their spread is the curve's own sensitivity
+        twins[0].update(twins[1], **kw)
+        twins[2].update(twins[3], **kw)
     # ---- steps 2..3: loss curve
     for _ in range(2):
         l_ref = oracle.train_step(x, t, **kw)
         l_gpu = model.train_step(X, T, read_loss=True)
-        assert abs(l_gpu - l_ref) < ctol * max(1.0, abs(l_ref)), (l_gpu, l_ref)
+        spread = 0.0
+        if twins:
+            l_rne, l_rna = twins[0].train_step(x, t, **kw), twins[2].train_step(x, t, **kw)
+            spread = max(abs(l_rne - l_rna), abs(l_rna - l_ref), abs(l_rne - l_ref))
+        # within the stated tolerance of the reference's f32 curve, widened only by what tf32 operand rounding itself does to
+        # the REFERENCE algorithm on this network (zero for the well-conditioned cases)
+        assert abs(l_gpu - l_ref) < ctol * max(1.0, abs(l_ref)) + 2.0 * spread, (l_gpu, l_ref, spread)
     # parameters and BN running statistics after three updates
     for name in ("fc.linear.weight", "linear2.linear.weight", "bn1.batch_norm_2d.mean", "batch_norm1.batch_norm_2d.variance"):
         if name in named:
