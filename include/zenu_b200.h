@@ -21,6 +21,8 @@
  *  - layout: ZB_NCHW = the reference contract (activations NCHW, filters KCRS);
  *            ZB_NHWC = the backend's native layout (activations NHWC, filters KRSC), zero-copy.
  *  - math:   ZB_MATH_TF32  tcgen05 kind::tf32 tensor cores, fp32 accumulate   (rel. tol 1e-3)
+ *            ZB_MATH_TF32X3 3xTF32 split on the same tensor-core kernels (hi/lo operand split, three accumulating
+ *                          passes lo*hi + hi*lo + hi*hi)                         (rel. tol 1e-5)
  *            ZB_MATH_FP32  FFMA (f32) / DFMA (f64) SIMT kernels                (rel. tol 1e-5)
  *            ZB_MATH_DEFAULT = the ctx default (TF32 for f32; f64 always runs DFMA).
  */
@@ -50,7 +52,7 @@ typedef enum { ZB_F32 = 0, ZB_F64 = 1 } zb_dtype;
  * filter is KRSC and y / dy are NHWC.  Served for C <= 4 stems on the TF32 path (the NCHW -> NHWC4 repack is part of the
  * conv's own staging pass); other shapes return ZB_ERR_UNSUPPORTED and the caller converts the layout first. */
 typedef enum { ZB_NCHW = 0, ZB_NHWC = 1, ZB_NCHW_X = 2 } zb_layout;
-typedef enum { ZB_MATH_DEFAULT = 0, ZB_MATH_TF32 = 1, ZB_MATH_FP32 = 3 } zb_math_mode;
+typedef enum { ZB_MATH_DEFAULT = 0, ZB_MATH_TF32 = 1, ZB_MATH_TF32X3 = 2, ZB_MATH_FP32 = 3 } zb_math_mode;
 typedef enum { ZB_OP_ADD = 0, ZB_OP_SUB = 1, ZB_OP_MUL = 2, ZB_OP_DIV = 3 } zb_binary_op;
 
 /* ---- context ------------------------------------------------------------------------------------

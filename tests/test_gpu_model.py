@@ -55,6 +55,10 @@ CASES = [
     # tf32 rounding alone moves the whole gradient by 41 %), damped it is well conditioned and the loss curve is pinned tightly
     ("resnet50:damped", 16, 64, 8, "tf32", "sgd", 1e-3, 2e-3, 5e-3, 3e-2),
     ("resnet50:damped", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 1e-3, 2e-3),
+    # 3xTF32 (hi/lo operand split on the tensor cores): held to the same f32-level tolerances as the FFMA path
+    ("small_cnn", 16, 32, 10, "tf32x3", "adamw", 1e-3, 1e-4, 3e-4, 1e-4),
+    ("resnet18", 4, 64, 10, "tf32x3", "adam", 1e-3, 2e-4, 6e-4, 2e-4),
+    ("resnet50:damped", 16, 64, 8, "tf32x3", "sgd", 1e-3, 2e-4, 1e-3, 2e-3),
 ]
 
 
@@ -107,7 +111,7 @@ def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol,
     pkg, ops, nn = zb
     if arch.startswith("resnet50") and not fused:
         pytest.skip("covered by the fused variant")
-    ctx = ops.Context(math=pkg.ZB_MATH_TF32 if math == "tf32" else pkg.ZB_MATH_FP32)
+    ctx = ops.Context(math={"tf32": pkg.ZB_MATH_TF32, "tf32x3": pkg.ZB_MATH_TF32X3, "fp32": pkg.ZB_MATH_FP32}[math])
     arch, params = make_params(arch, classes)
     oracle = zm.OracleModel(arch, classes, {k: v.copy() for k, v in params.items()})   # the reference's f32 arithmetic
     model = nn.Model(ctx, arch, classes, fused=fused, seed=1)

@@ -17,7 +17,7 @@ from oracle import zenu_oracle as zo  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"tf32": 1e-3, "fp32": 1e-5, "f64": 1e-10}
+TOL = {"tf32": 1e-3, "tf32x3": 1e-5, "fp32": 1e-5, "f64": 1e-10}
 
 
 @pytest.fixture(scope="module")
@@ -72,8 +72,8 @@ def nchw(a):
 
 
 def math_of(zb, name):
-    from zenu_b200 import ZB_MATH_FP32, ZB_MATH_TF32
-    return ZB_MATH_TF32 if name == "tf32" else ZB_MATH_FP32
+    from zenu_b200 import ZB_MATH_FP32, ZB_MATH_TF32, ZB_MATH_TF32X3
+    return {"tf32": ZB_MATH_TF32, "tf32x3": ZB_MATH_TF32X3, "fp32": ZB_MATH_FP32}[name]
 
 
 # ------------------------------------------------------------------------------------------------ golden vectors
@@ -169,12 +169,16 @@ CONV_CASES = [
     (2, 32, 8, 8, 32, 5, 5, 2, 1, 1),      # 5x5
     (2, 3, 20, 20, 16, 7, 7, 3, 2, 1),     # conv1-like: C=3 (FFMA path)
     (1, 20, 7, 7, 12, 3, 3, 0, 1, 1),      # ragged channels, no padding
+    (3, 32, 9, 11, 192, 3, 3, 1, 1, 1),    # halo wgrad: two k tiles (the second half full), odd sizes, 3 images
+    (2, 64, 10, 10, 40, 3, 3, 0, 1, 1),    # halo kernels without padding, ragged k tile
+    (2, 32, 8, 12, 64, 1, 3, 1, 1, 1),     # 1x3 filter
+    (2, 32, 12, 8, 32, 3, 1, 0, 1, 1),     # 3x1 filter
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
-@pytest.mark.parametrize("math", ["tf32", "fp32"])
+@pytest.mark.parametrize("math", ["tf32", "tf32x3", "fp32"])
 def test_conv_vs_oracle(zb, ctx, case, layout, math):
     from zenu_b200 import ZB_NCHW, ZB_NHWC
     n, c, h, w, k, r, s, pad, stride, dil = case
@@ -253,6 +257,38 @@ def test_conv_layers_vs_tf32_rounded_oracle(zb, ctx, arch, n, hw):
         zo.use_plain_gemm()
 
 
+@pytest.mark.parametrize("arch,n,hw", [("small_cnn", 16, 32), ("resnet50", 4, 64)])
+def test_conv_layers_tf32x3(zb, ctx, arch, n, hw):
+    """3xTF32 on every distinct conv geometry of the networks (incl. the C=3 stem's sliding-window path, the halo-reuse 3x3
+    kernel, strided dgrad parity classes and split-K wgrad), against the oracle's exact arithmetic in f64: rel. 1e-5."""
+    from zenu_b200 import ZB_MATH_TF32X3, ZB_NHWC
+    rng = np.random.default_rng(5)
+    seen = set()
+    for name, ci, co, k, stride, pad, h in _net_layers(arch, hw):
+        key = (ci, co, k, stride, pad, h)
+        if key in seen:
+            continue
+        seen.add(key)
+        x = rng.standard_normal((n, ci, h, h)).astype(np.float32)
+        w = (rng.standard_normal((co, ci, k, k)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32)
+        x64, w64 = x.astype(np.float64), w.astype(np.float64)
+        y_ref = zo.conv2d_fwd(x64, w64, pad, stride, 1)
+        dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+        X, W, DY = dev(nhwc(x)), dev(nhwc(w)), dev(nhwc(dy))
+        y = zb.conv_fwd(ctx, X, W, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+        assert rel_err(nchw(host(y)), y_ref) < 1e-5, (name, "fprop")
+        dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+        assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(dy.astype(np.float64), w64, x.shape, pad, stride, 1)) < 1e-5, (name, "dgrad")
+        dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+        assert rel_err(nchw(host(dw)), zo.conv2d_bkwd_filter(dy.astype(np.float64), x64, w.shape, pad, stride, 1)) < 1e-5, (name, "wgrad")
+        # accumulate form (residual fan-in): dx2 = base + dgrad
+        if ci % 32 == 0 and co % 32 == 0:
+            base = torch.ones_like(dx)
+            zb.conv_bkwd_data_accumulate(ctx, DY, W, base, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+            assert rel_err(host(base) - 1.0, host(dx)) < 1e-4, (name, "dgrad accumulate")
+    ctx.check()
+
+
 def test_conv_f64_vs_oracle(zb, ctx):
     n, c, h, w, k, r, s, pad, stride, dil = 2, 8, 10, 10, 6, 3, 3, 1, 2, 1
     rng = np.random.default_rng(7)
@@ -291,7 +327,7 @@ def test_conv_shape_errors(zb, ctx):
 
 # ------------------------------------------------------------------------------------------------ GEMM / Linear
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("math", ["tf32", "fp32"])
+@pytest.mark.parametrize("math", ["tf32", "tf32x3", "fp32"])
 @pytest.mark.parametrize("shape", [(256, 128, 64), (300, 200, 100), (64, 1000, 2048), (8, 8, 4096)])
 def test_gemm_vs_oracle(zb, ctx, ta, tb, math, shape):
     m, n, k = shape
@@ -305,7 +341,7 @@ def test_gemm_vs_oracle(zb, ctx, ta, tb, math, shape):
     ctx.check()
 
 
-@pytest.mark.parametrize("math", ["tf32", "fp32"])
+@pytest.mark.parametrize("math", ["tf32", "tf32x3", "fp32"])
 def test_linear_vs_oracle(zb, ctx, math):
     rng = np.random.default_rng(11)
     b, i, o = 64, 512, 10

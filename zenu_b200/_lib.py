@@ -15,7 +15,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 ZB_OK = 0
 ZB_F32, ZB_F64 = 0, 1
 ZB_NCHW, ZB_NHWC, ZB_NCHW_X = 0, 1, 2
-ZB_MATH_DEFAULT, ZB_MATH_TF32, ZB_MATH_FP32 = 0, 1, 3
+ZB_MATH_DEFAULT, ZB_MATH_TF32, ZB_MATH_TF32X3, ZB_MATH_FP32 = 0, 1, 2, 3
 ZB_OP_ADD, ZB_OP_SUB, ZB_OP_MUL, ZB_OP_DIV = 0, 1, 2, 3
 CUDA_STREAM_LEGACY = 0x1
 

@@ -9,15 +9,16 @@ namespace zb {
 // umma_gemm.cu
 int umma_gemm(zb_ctx*, bool, bool, long long, long long, long long, float, const float*, long long, const float*, long long,
               float, float*, long long, const float*);
+void umma_set_chain_limit(int);
 bool umma_conv_supported(const zb_conv2d_desc*);
-int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*);
+int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*, float);
 int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
-int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 bool umma_conv_smallc_supported(const zb_conv2d_desc*);
-int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*);
-int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*);
+int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*, float);
+int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*, float);
 bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc*);
-int umma_conv_smallc_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*);
+int umma_conv_smallc_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 // conv_simt.cu
 template <typename T> int simt_conv_fprop(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, const T*, T*);
 template <typename T> int simt_conv_dgrad(zb_ctx*, int, const zb_conv2d_desc*, const T*, const T*, T*);
@@ -43,7 +44,7 @@ static int check_desc(const zb_conv2d_desc* d, long long* P, long long* Q) {
 
 static int resolve_math(zb_ctx* ctx, int dtype, int math, int* out) {
   int m = (math == ZB_MATH_DEFAULT) ? ctx->default_math : math;
-  ZB_REQUIRE(m == ZB_MATH_TF32 || m == ZB_MATH_FP32, "unknown math mode %d", math);
+  ZB_REQUIRE(m == ZB_MATH_TF32 || m == ZB_MATH_TF32X3 || m == ZB_MATH_FP32, "unknown math mode %d", math);
   if (dtype == ZB_F64) m = ZB_MATH_FP32;  // f64 always runs DFMA
   *out = m;
   return ZB_OK;
@@ -60,6 +61,104 @@ struct Temp {
   }
   ~Temp() { if (p) cudaFreeAsync(p, ctx->stream); }
 };
+
+// ---------------------------------------------------------------------------------------------- 3xTF32
+// ZB_MATH_TF32X3: every f32 operand is split once into hi = tf32(x) (round to nearest) and lo = x - hi (exact in fp32, at most
+// 13 significant bits), and the product is accumulated on the tensor cores as lo*hi + hi*lo + hi*hi (the lo*lo term, ~2^-22
+// relative, is dropped) by three launches of the same tcgen05 kernels, the 2nd and 3rd with an accumulating (beta = 1) epilogue.
+// Inside each launch the TMEM accumulation chain is limited to 64 MMA steps (UmmaParams::chain_kb).
+// Result: f32-level accuracy (rel. 1e-5 contract, ~1e-6 measured) at roughly a third of the TF32 rate, with no SIMT fallback.
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    hi[i] = hf;
+    lo[i] = v - hf;
+  }
+}
+
+struct SplitOperand {
+  Temp t;
+  const float* hi = nullptr;
+  const float* lo = nullptr;
+  explicit SplitOperand(zb_ctx* c) : t(c) {}
+  int make(const float* x, long long n) {
+    int rc = t.alloc(sizeof(float) * 2 * static_cast<size_t>(n));
+    if (rc != ZB_OK) return rc;
+    float* h = static_cast<float*>(t.p);
+    float* l = h + n;
+    const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, t.ctx->sm_count * 16ll));
+    split_tf32_kernel<<<std::max(grid, 1), 256, 0, t.ctx->stream>>>(x, h, l, n);
+    ZB_LAUNCH_CHECK(t.ctx);
+    hi = h;
+    lo = l;
+    return ZB_OK;
+  }
+};
+
+// call(a_part, b_part, beta, last): `last` carries the bias; the first pass keeps the caller's beta, the others accumulate.
+template <typename F>
+static int run_tf32x3(zb_ctx* ctx, const float* a, long long na, const float* b, long long nb, float beta, F&& call) {
+  SplitOperand sa(ctx), sb(ctx);
+  int rc;
+  // The tensor core accumulates into TMEM with truncation: over thousands of MMA steps that bias alone reaches 1e-5.
+  // Chains are cut every 16 K blocks (64 MMA steps) and joined by round-to-nearest fp32 adds in the epilogue.
+  struct ChainScope { ChainScope() { umma_set_chain_limit(16); } ~ChainScope() { umma_set_chain_limit(0); } } chain_scope;
+  if ((rc = sa.make(a, na)) != ZB_OK) return rc;
+  if ((rc = sb.make(b, nb)) != ZB_OK) return rc;
+  if ((rc = call(sa.lo, sb.hi, beta, false)) != ZB_OK) return rc;   // ZB_ERR_UNSUPPORTED surfaces before anything is written
+  if ((rc = call(sa.hi, sb.lo, 1.f, false)) != ZB_OK) return rc;
+  return call(sa.hi, sb.hi, 1.f, true);
+}
+
+static int tc_gemm(zb_ctx* ctx, int mm, bool ta, bool tb, long long m, long long n, long long k, float alpha, const float* a,
+                   long long lda, const float* b, long long ldb, float beta, float* c, long long ldc, const float* bias) {
+  if (mm != ZB_MATH_TF32X3) return umma_gemm(ctx, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, bias);
+  const long long na = ((ta ? k : m) - 1) * lda + (ta ? m : k), nb = ((tb ? n : k) - 1) * ldb + (tb ? k : n);
+  return run_tf32x3(ctx, a, na, b, nb, beta, [&](const float* ap, const float* bp, float bt, bool last) {
+    return umma_gemm(ctx, ta, tb, m, n, k, alpha, ap, lda, bp, ldb, bt, c, ldc, last ? bias : nullptr);
+  });
+}
+
+static int tc_fprop_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias, float* y) {
+  if (mm != ZB_MATH_TF32X3) return umma_conv_fprop_nhwc(ctx, d, x, w, bias, y, 0.f);
+  return run_tf32x3(ctx, x, d->n * d->h * d->w * d->c, w, d->k * d->kh * d->kw * d->c, 0.f,
+                    [&](const float* xp, const float* wp, float bt, bool last) {
+                      return umma_conv_fprop_nhwc(ctx, d, xp, wp, last ? bias : nullptr, y, bt);
+                    });
+}
+
+static int tc_smallc_fprop(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
+                           float* y) {
+  if (mm != ZB_MATH_TF32X3) return umma_conv_smallc_fprop(ctx, d, x, x_nchw, w, bias, y, 0.f);
+  return run_tf32x3(ctx, x, d->n * d->h * d->w * d->c, w, d->k * d->kh * d->kw * d->c, 0.f,
+                    [&](const float* xp, const float* wp, float bt, bool last) {
+                      return umma_conv_smallc_fprop(ctx, d, xp, x_nchw, wp, last ? bias : nullptr, y, bt);
+                    });
+}
+
+static int tc_dgrad_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, long long P, long long Q, const float* dy, const float* w,
+                         float* dx, float beta, bool smallc) {
+  if (mm != ZB_MATH_TF32X3)
+    return smallc ? umma_conv_smallc_dgrad(ctx, d, dy, w, dx, beta) : umma_conv_dgrad_nhwc(ctx, d, dy, w, dx, beta);
+  return run_tf32x3(ctx, dy, d->n * P * Q * d->k, w, d->k * d->kh * d->kw * d->c, beta,
+                    [&](const float* gp, const float* wp, float bt, bool) {
+                      return smallc ? umma_conv_smallc_dgrad(ctx, d, gp, wp, dx, bt) : umma_conv_dgrad_nhwc(ctx, d, gp, wp, dx, bt);
+                    });
+}
+
+static int tc_wgrad_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, long long P, long long Q, const float* dy, const float* x,
+                         int x_nchw, float* dw, bool smallc) {
+  if (mm != ZB_MATH_TF32X3)
+    return smallc ? umma_conv_smallc_wgrad(ctx, d, dy, x, x_nchw, dw, 0.f) : umma_conv_wgrad_nhwc(ctx, d, dy, x, dw, 0.f);
+  return run_tf32x3(ctx, dy, d->n * P * Q * d->k, x, d->n * d->h * d->w * d->c, 0.f,
+                    [&](const float* gp, const float* xp, float bt, bool) {
+                      return smallc ? umma_conv_smallc_wgrad(ctx, d, gp, xp, x_nchw, dw, bt) : umma_conv_wgrad_nhwc(ctx, d, gp, xp, dw, bt);
+                    });
+}
 
 }  // namespace zb
 
@@ -78,10 +177,10 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   rc = resolve_math(ctx, dtype, math, &m);
   if (rc != ZB_OK) return rc;
   if (layout == ZB_NCHW_X) {
-    if (dtype == ZB_F32 && m == ZB_MATH_TF32 && umma_conv_smallc_supported(d))
-      return umma_conv_smallc_fprop(ctx, d, static_cast<const float*>(x), 1, static_cast<const float*>(w), static_cast<const float*>(bias),
-                                    static_cast<float*>(y));
-    set_last_error("conv fprop: ZB_NCHW_X is served for C <= 4 on the TF32 path only");
+    if (dtype == ZB_F32 && m != ZB_MATH_FP32 && umma_conv_smallc_supported(d))
+      return tc_smallc_fprop(ctx, m, d, static_cast<const float*>(x), 1, static_cast<const float*>(w), static_cast<const float*>(bias),
+                             static_cast<float*>(y));
+    set_last_error("conv fprop: ZB_NCHW_X is served for C <= 4 on the TF32 / 3xTF32 paths only");
     return ZB_ERR_UNSUPPORTED;
   }
   if (dtype == ZB_F64)
@@ -91,10 +190,10 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* wf = static_cast<const float*>(w);
   const float* bf = static_cast<const float*>(bias);
   float* yf = static_cast<float*>(y);
-  if (m == ZB_MATH_TF32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
-    return umma_conv_smallc_fprop(ctx, d, xf, 0, wf, bf, yf);
+  if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
+    return tc_smallc_fprop(ctx, m, d, xf, 0, wf, bf, yf);
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_fprop<float>(ctx, layout, d, xf, wf, bf, yf);
-  if (layout == ZB_NHWC) return umma_conv_fprop_nhwc(ctx, d, xf, wf, bf, yf);
+  if (layout == ZB_NHWC) return tc_fprop_nhwc(ctx, m, d, xf, wf, bf, yf);
   // NCHW contract: stage through NHWC / KRSC
   Temp tx(ctx), tw(ctx), ty(ctx);
   if ((rc = tx.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
@@ -102,7 +201,7 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   if ((rc = ty.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, xf, static_cast<float*>(tx.p), d->n, d->c, d->h * d->w)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
-  if ((rc = umma_conv_fprop_nhwc(ctx, d, static_cast<float*>(tx.p), static_cast<float*>(tw.p), bf, static_cast<float*>(ty.p))) != ZB_OK) return rc;
+  if ((rc = tc_fprop_nhwc(ctx, m, d, static_cast<float*>(tx.p), static_cast<float*>(tw.p), bf, static_cast<float*>(ty.p))) != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(ty.p), yf, d->n, P * Q, d->k);
 }
 
@@ -122,7 +221,7 @@ int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_c
   int m;
   rc = resolve_math(ctx, dtype, math, &m);
   if (rc != ZB_OK) return rc;
-  const bool fused = dtype == ZB_F32 && layout == ZB_NHWC && m == ZB_MATH_TF32 && (d->k % 32 == 0) && d->kh * d->kw <= 64;
+  const bool fused = dtype == ZB_F32 && layout == ZB_NHWC && m != ZB_MATH_FP32 && (d->k % 32 == 0) && d->kh * d->kw <= 64;
   if (fused) {
     rc = dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 1.f);
     if (rc != ZB_ERR_UNSUPPORTED) return rc;
@@ -152,14 +251,14 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   const float* wf = static_cast<const float*>(w);
   float* df = static_cast<float*>(dx);
   const bool tc_ok = (d->k % 32 == 0) && d->kh * d->kw <= 64 && (layout == ZB_NHWC || d->c % 4 == 0);
-  if (beta != 0.f && !(layout == ZB_NHWC && m == ZB_MATH_TF32 && tc_ok)) {
+  if (beta != 0.f && !(layout == ZB_NHWC && m != ZB_MATH_FP32 && tc_ok)) {
     set_last_error("dgrad accumulate: not available on this path");
     return ZB_ERR_UNSUPPORTED;
   }
   if (m == ZB_MATH_FP32 || !tc_ok) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
-  if (layout == ZB_NHWC && beta == 0.f && umma_conv_smallc_dgrad_supported(d)) return umma_conv_smallc_dgrad(ctx, d, gf, wf, df);
+  if (layout == ZB_NHWC && beta == 0.f && umma_conv_smallc_dgrad_supported(d)) return tc_dgrad_nhwc(ctx, m, d, P, Q, gf, wf, df, 0.f, true);
   if (layout == ZB_NHWC) {
-    rc = umma_conv_dgrad_nhwc(ctx, d, gf, wf, df, beta);
+    rc = tc_dgrad_nhwc(ctx, m, d, P, Q, gf, wf, df, beta, false);
     if (rc == ZB_ERR_UNSUPPORTED && beta == 0.f) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
     return rc;
   }
@@ -169,7 +268,7 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   if ((rc = td.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
-  rc = umma_conv_dgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p), 0.f);
+  rc = tc_dgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p), 0.f, false);
   if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
   if (rc != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(td.p), df, d->n, d->h * d->w, d->c);
@@ -186,9 +285,9 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   rc = resolve_math(ctx, dtype, math, &m);
   if (rc != ZB_OK) return rc;
   if (layout == ZB_NCHW_X) {
-    if (dtype == ZB_F32 && m == ZB_MATH_TF32 && umma_conv_smallc_supported(d))
-      return umma_conv_smallc_wgrad(ctx, d, static_cast<const float*>(dy), static_cast<const float*>(x), 1, static_cast<float*>(dw));
-    set_last_error("conv wgrad: ZB_NCHW_X is served for C <= 4 on the TF32 path only");
+    if (dtype == ZB_F32 && m != ZB_MATH_FP32 && umma_conv_smallc_supported(d))
+      return tc_wgrad_nhwc(ctx, m, d, P, Q, static_cast<const float*>(dy), static_cast<const float*>(x), 1, static_cast<float*>(dw), true);
+    set_last_error("conv wgrad: ZB_NCHW_X is served for C <= 4 on the TF32 / 3xTF32 paths only");
     return ZB_ERR_UNSUPPORTED;
   }
   if (dtype == ZB_F64)
@@ -196,16 +295,16 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* gf = static_cast<const float*>(dy);
   const float* xf = static_cast<const float*>(x);
   float* wf = static_cast<float*>(dw);
-  if (m == ZB_MATH_TF32 && layout == ZB_NHWC && umma_conv_smallc_supported(d)) return umma_conv_smallc_wgrad(ctx, d, gf, xf, 0, wf);
+  if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d)) return tc_wgrad_nhwc(ctx, m, d, P, Q, gf, xf, 0, wf, true);
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_wgrad<float>(ctx, layout, d, gf, xf, wf);
-  if (layout == ZB_NHWC) return umma_conv_wgrad_nhwc(ctx, d, gf, xf, wf);
+  if (layout == ZB_NHWC) return tc_wgrad_nhwc(ctx, m, d, P, Q, gf, xf, 0, wf, false);
   Temp tg(ctx), tx(ctx), tw(ctx);
   if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
   if ((rc = tx.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
   if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, xf, static_cast<float*>(tx.p), d->n, d->c, d->h * d->w)) != ZB_OK) return rc;
-  if ((rc = umma_conv_wgrad_nhwc(ctx, d, static_cast<float*>(tg.p), static_cast<float*>(tx.p), static_cast<float*>(tw.p))) != ZB_OK) return rc;
+  if ((rc = tc_wgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), static_cast<float*>(tx.p), 0, static_cast<float*>(tw.p), false)) != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(tw.p), wf, d->k, d->kh * d->kw, d->c);  // KRSC -> KCRS
 }
 
@@ -231,9 +330,9 @@ int zb_gemm(zb_ctx* ctx, int dtype, int math, int trans_a, int trans_b, int64_t 
   if (dtype == ZB_F64)
     return simt_gemm<double>(ctx, trans_a != 0, trans_b != 0, m, n, k, alpha, static_cast<const double*>(a), lda,
                              static_cast<const double*>(b), ldb, beta, static_cast<double*>(c), ldc, static_cast<const double*>(nullptr));
-  if (mm == ZB_MATH_TF32 && k > 0) {
-    rc = umma_gemm(ctx, trans_a != 0, trans_b != 0, m, n, k, static_cast<float>(alpha), static_cast<const float*>(a), lda,
-                   static_cast<const float*>(b), ldb, static_cast<float>(beta), static_cast<float*>(c), ldc, nullptr);
+  if (mm != ZB_MATH_FP32 && k > 0) {
+    rc = tc_gemm(ctx, mm, trans_a != 0, trans_b != 0, m, n, k, static_cast<float>(alpha), static_cast<const float*>(a), lda,
+                 static_cast<const float*>(b), ldb, static_cast<float>(beta), static_cast<float*>(c), ldc, nullptr);
     if (rc != ZB_ERR_UNSUPPORTED) return rc;
   }
   return simt_gemm<float>(ctx, trans_a != 0, trans_b != 0, m, n, k, static_cast<float>(alpha), static_cast<const float*>(a), lda,
@@ -249,9 +348,9 @@ int zb_linear_fwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w
   if (dtype == ZB_F64)
     return simt_gemm<double>(ctx, false, true, batch, out_f, in_f, 1.0, static_cast<const double*>(x), in_f,
                              static_cast<const double*>(w), in_f, 0.0, static_cast<double*>(y), out_f, static_cast<const double*>(bias));
-  if (mm == ZB_MATH_TF32) {
-    rc = umma_gemm(ctx, false, true, batch, out_f, in_f, 1.f, static_cast<const float*>(x), in_f, static_cast<const float*>(w), in_f,
-                   0.f, static_cast<float*>(y), out_f, static_cast<const float*>(bias));
+  if (mm != ZB_MATH_FP32) {
+    rc = tc_gemm(ctx, mm, false, true, batch, out_f, in_f, 1.f, static_cast<const float*>(x), in_f, static_cast<const float*>(w), in_f,
+                 0.f, static_cast<float*>(y), out_f, static_cast<const float*>(bias));
     if (rc != ZB_ERR_UNSUPPORTED) return rc;
   }
   return simt_gemm<float>(ctx, false, true, batch, out_f, in_f, 1.f, static_cast<const float*>(x), in_f, static_cast<const float*>(w), in_f,

@@ -86,7 +86,7 @@ struct StatsF {  // sum(x - shift), sum((x - shift)^2); shift = first row
 #pragma unroll
     for (int e = 0; e < VN; ++e) shift[e] = x0[(c0 + e) * sstride];
   }
-  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN]) const {
+  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN], long long) const {
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       const T d = a[e] - shift[e];
@@ -99,16 +99,19 @@ template <typename T, int VN>
 struct SumF {  // plain column sum
   static constexpr int NS = 1, NIN = 1;
   __device__ void init(long long) {}
-  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN]) const {
+  __device__ void operator()(const T* a, const T*, const T*, T (*acc)[VN], long long) const {
 #pragma unroll
     for (int e = 0; e < VN; ++e) acc[0][e] += a[e];
   }
 };
 // MASK: 0 = plain BN backward, 1 = ReLU mask from the saved output y (third stream), 2 = ReLU mask recomputed from x
-// (fused BN+ReLU without residual: y > 0 <=> bn_affine(x) > 0, so y is never read)
+// (fused BN+ReLU without residual: y > 0 <=> bn_affine(x) > 0, so y is never read), 3 = as 1, and the masked gradient
+// dy' is also written to gm_out (it IS the residual-branch gradient; the apply pass then reads it instead of dy and y:
+// 7 tensor passes instead of 8 for the fused BN+add+ReLU backward)
 template <typename T, int VN, int MASK>
 struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
-  static constexpr int NS = 2, NIN = MASK == 1 ? 3 : 2;
+  static constexpr int NS = 2, NIN = (MASK == 1 || MASK == 3) ? 3 : 2;
+  T* gm_out;
   const T* mean;
   const T* inv;
   const T* gamma;
@@ -121,16 +124,19 @@ struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
       if (MASK == 2) { gm[e] = gamma[c0 + e]; bt[e] = beta[c0 + e]; }
     }
   }
-  __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN]) const {
+  __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN], long long off) const {
+    T gv[VN];
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       bool keep = true;
-      if (MASK == 1) keep = y[e] > T(0);
+      if (MASK == 1 || MASK == 3) keep = y[e] > T(0);
       if (MASK == 2) keep = bn_affine(x[e], m[e], iv[e], gm[e], bt[e]) > T(0);
       const T g = keep ? dy[e] : T(0);
+      gv[e] = g;
       acc[0][e] += g;
       acc[1][e] += g * ((x[e] - m[e]) * iv[e]);
     }
+    if (MASK == 3) stv<T, VN>(gm_out + off, gv);
   }
 };
 
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict_
         if (F::NIN >= 3) ldv<T, VN>(in2 + off, c[u]);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) f(a[u], b[u], c[u], acc);
+      for (int u = 0; u < U; ++u) f(a[u], b[u], c[u], acc, (r + u * ty_n) * C + c0);
     }
     for (; r < r1; r += ty_n) {
       T a[VN], b[VN], c[VN];
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict_
       ldv<T, VN>(in0 + off, a);
       if (F::NIN >= 2) ldv<T, VN>(in1 + off, b);
       if (F::NIN >= 3) ldv<T, VN>(in2 + off, c);
-      f(a, b, c, acc);
+      f(a, b, c, acc, off);
     }
   }
   const int row_elems = NS * tx_n * VN;
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(256) col_reduce_nchw(F f, const T* __restrict_
       a[0] = in0[base + i];
       if (F::NIN >= 2) b[0] = in1[base + i];
       if (F::NIN >= 3) d[0] = in2[base + i];
-      f(a, b, d, acc);
+      f(a, b, d, acc, base + i);
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -555,6 +561,7 @@ template <typename T, int VN> using SumFT = SumF<T, VN>;
 template <typename T, int VN> using BnBwdMaskFT = BnBwdF<T, VN, 1>;
 template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, 0>;
 template <typename T, int VN> using BnBwdRecomputeFT = BnBwdF<T, VN, 2>;
+template <typename T, int VN> using BnBwdMaskStoreFT = BnBwdF<T, VN, 3>;
 
 // Upper bound on the slab count run_col_reduce may pick (sizes the partial buffer).
 static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
@@ -694,6 +701,9 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   if (relu_bias != nullptr)
     rc = run_col_reduce<T, BnBwdRecomputeFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
                                              [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs);
+  else if (y != nullptr && dres != nullptr)
+    rc = run_col_reduce<T, BnBwdMaskStoreFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; }, &slabs);
   else if (y != nullptr)
     rc = run_col_reduce<T, BnBwdMaskFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
                                         [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
@@ -705,12 +715,14 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
                                                                dscale, dbias, coef);
   ZB_LAUNCH_CHECK(ctx);
   if (relu_bias != nullptr) rc = launch_bwd_apply<T, 2, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
-  else if (y != nullptr && dres != nullptr) rc = launch_bwd_apply<T, 1, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else if (y != nullptr && dres != nullptr)   // dres already holds the masked gradient (written by the reduce pass)
+    rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dres, static_cast<const T*>(nullptr), dx, static_cast<T*>(nullptr), mean, inv, coef, scale, relu_bias);
   else if (y != nullptr) rc = launch_bwd_apply<T, 1, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   else if (dres != nullptr) rc = launch_bwd_apply<T, 0, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   else rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
-  // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written)
-  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * (5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
+  // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written); the fused
+  // BN+add+ReLU backward reads x twice, dy and y once, writes and re-reads the masked gradient, writes dx: 7 passes
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * ((y && dres) ? 7.0 : 5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
   return rc;
 }
 

@@ -166,7 +166,7 @@ int zb_ctx_synchronize(zb_ctx* ctx) {
 }
 
 int zb_ctx_set_math(zb_ctx* ctx, int math_mode) {
-  ZB_REQUIRE(math_mode == ZB_MATH_TF32 || math_mode == ZB_MATH_FP32, "unknown math mode %d", math_mode);
+  ZB_REQUIRE(math_mode == ZB_MATH_TF32 || math_mode == ZB_MATH_TF32X3 || math_mode == ZB_MATH_FP32, "unknown math mode %d", math_mode);
   ctx->default_math = math_mode;
   return ZB_OK;
 }

@@ -322,7 +322,7 @@ struct BnFn : Function {
       dres_ptr = dres.ptr;
     }
     ProfScope ps(rt, std::string("bn.bwd") + (relu ? "+relu" : "") + (has_res ? "+res" : "") + " " + shape_str(x.shape), 0.0,
-                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? 3.0 : 0.0)));
+                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? 2.0 : 0.0)));
     if (relu && !has_res)  // mask recomputed from x: the forward output is neither kept nor read
       check_rc(zb_bn2d_relu_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, bias.ptr, saved_mean.ptr,
                                 saved_inv.ptr, dx.ptr, ds.ptr, db.ptr), "bn relu bwd");

@@ -104,31 +104,32 @@ template <typename T> struct Vec4T;
 template <> struct Vec4T<float> { using type = float4; };
 template <> struct Vec4T<double> { using type = double4; };
 
-template <typename T>
+// I = int when every element index fits in 31 bits (64-bit divides dominated the old version: 1.1 TB/s -> HBM-bound now)
+template <typename T, typename I>
 __global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, const T* __restrict__ x, T* __restrict__ y,
                                                               uchar4* __restrict__ idx) {
   using V = typename Vec4T<T>::type;
-  const long long c4n = g.C >> 2;
-  const long long total = g.N * g.P * g.Q * c4n;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long c4 = i % c4n;
-    long long t = i / c4n;
-    const long long q = t % g.Q; t /= g.Q;
-    const long long p = t % g.P;
-    const long long n = t / g.P;
-    const T* xb = x + n * g.sn + c4 * 4;
+  const I c4n = static_cast<I>(g.C >> 2), Q = static_cast<I>(g.Q), P = static_cast<I>(g.P), H = static_cast<I>(g.H), W = static_cast<I>(g.W);
+  const I total = static_cast<I>(g.N) * P * Q * c4n;
+  const I s_h = static_cast<I>(g.s_h), s_w = static_cast<I>(g.s_w), sn = static_cast<I>(g.sn);
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < total; i += static_cast<I>(gridDim.x) * blockDim.x) {
+    const I c4 = i % c4n;
+    I t = i / c4n;
+    const I q = t % Q; t /= Q;
+    const I p = t % P;
+    const I n = t / P;
+    const T* xb = x + n * sn + c4 * 4;
     T best[4];
     unsigned char bi[4];
     bool first = true;
     for (int r = 0; r < g.kh; ++r) {
-      const long long ih = p * g.sh + r - g.ph;
+      const I ih = p * g.sh + r - g.ph;
       for (int s_ = 0; s_ < g.kw; ++s_) {
-        const long long iw = q * g.sw + s_ - g.pw;
-        const bool oob = ih < 0 || ih >= g.H || iw < 0 || iw >= g.W;
+        const I iw = q * g.sw + s_ - g.pw;
+        const bool oob = ih < 0 || ih >= H || iw < 0 || iw >= W;
         T v[4] = {T(0), T(0), T(0), T(0)};
         if (!oob) {
-          const V vv = *reinterpret_cast<const V*>(xb + ih * g.s_h + iw * g.s_w);
+          const V vv = *reinterpret_cast<const V*>(xb + ih * s_h + iw * s_w);
           v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
         }
         const unsigned char tap = oob ? 255 : static_cast<unsigned char>(r * g.kw + s_);
@@ -140,42 +141,41 @@ __global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, 
     }
     V o;
     o.x = best[0]; o.y = best[1]; o.z = best[2]; o.w = best[3];
-    *reinterpret_cast<V*>(y + i * 4) = o;
+    *reinterpret_cast<V*>(y + static_cast<long long>(i) * 4) = o;
     idx[i] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
   }
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256) maxpool_idx_bwd_kernel(const PoolGeom g, const T* __restrict__ dy,
                                                               const uchar4* __restrict__ idx, T* __restrict__ dx) {
   using V = typename Vec4T<T>::type;
-  const long long c4n = g.C >> 2;
-  const long long total = g.N * g.H * g.W * c4n;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long c4 = i % c4n;
-    long long t = i / c4n;
-    const long long w = t % g.W; t /= g.W;
-    const long long h = t % g.H;
-    const long long n = t / g.H;
+  const I c4n = static_cast<I>(g.C >> 2), Q = static_cast<I>(g.Q), P = static_cast<I>(g.P), H = static_cast<I>(g.H), W = static_cast<I>(g.W);
+  const I total = static_cast<I>(g.N) * H * W * c4n;
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < total; i += static_cast<I>(gridDim.x) * blockDim.x) {
+    const I c4 = i % c4n;
+    I t = i / c4n;
+    const I w = t % W; t /= W;
+    const I h = t % H;
+    const I n = t / H;
     T acc[4] = {T(0), T(0), T(0), T(0)};
     // windows p with p*sh - ph <= h <= p*sh - ph + kh - 1
-    long long p_lo = (h + g.ph - g.kh + 1 + g.sh - 1);
+    I p_lo = (h + g.ph - g.kh + 1 + g.sh - 1);
     p_lo = p_lo <= 0 ? 0 : p_lo / g.sh;
-    long long p_hi = (h + g.ph) / g.sh;
-    if (p_hi > g.P - 1) p_hi = g.P - 1;
-    long long q_lo = (w + g.pw - g.kw + 1 + g.sw - 1);
+    I p_hi = (h + g.ph) / g.sh;
+    if (p_hi > P - 1) p_hi = P - 1;
+    I q_lo = (w + g.pw - g.kw + 1 + g.sw - 1);
     q_lo = q_lo <= 0 ? 0 : q_lo / g.sw;
-    long long q_hi = (w + g.pw) / g.sw;
-    if (q_hi > g.Q - 1) q_hi = g.Q - 1;
-    for (long long p = p_lo; p <= p_hi; ++p) {
+    I q_hi = (w + g.pw) / g.sw;
+    if (q_hi > Q - 1) q_hi = Q - 1;
+    for (I p = p_lo; p <= p_hi; ++p) {
       const int r = static_cast<int>(h + g.ph - p * g.sh);
-      for (long long q = q_lo; q <= q_hi; ++q) {
+      for (I q = q_lo; q <= q_hi; ++q) {
         const int s_ = static_cast<int>(w + g.pw - q * g.sw);
         const unsigned char tap = static_cast<unsigned char>(r * g.kw + s_);
-        const long long o = ((n * g.P + p) * g.Q + q) * c4n + c4;
+        const I o = ((n * P + p) * Q + q) * c4n + c4;
         const uchar4 wi = idx[o];
-        const V gv = *reinterpret_cast<const V*>(dy + o * 4);
+        const V gv = *(reinterpret_cast<const V*>(dy) + o);
         if (wi.x == tap) acc[0] += gv.x;
         if (wi.y == tap) acc[1] += gv.y;
         if (wi.z == tap) acc[2] += gv.z;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) maxpool_idx_bwd_kernel(const PoolGeom g, 
     }
     V o4;
     o4.x = acc[0]; o4.y = acc[1]; o4.z = acc[2]; o4.w = acc[3];
-    *reinterpret_cast<V*>(dx + i * 4) = o4;
+    *reinterpret_cast<V*>(dx + static_cast<long long>(i) * 4) = o4;
   }
 }
 
@@ -193,7 +193,10 @@ static int maxpool_idx_fwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, T* y, v
   const long long total = g.N * g.P * g.Q * (g.C >> 2);
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
-  maxpool_idx_fwd_kernel<T><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
+  if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24))
+    maxpool_idx_fwd_kernel<T, int><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
+  else
+    maxpool_idx_fwd_kernel<T, long long><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }
@@ -202,7 +205,10 @@ static int maxpool_idx_bwd_t(zb_ctx* ctx, const PoolGeom& g, const T* dy, const 
   const long long total = g.N * g.H * g.W * (g.C >> 2);
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
-  maxpool_idx_bwd_kernel<T><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
+  if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24))
+    maxpool_idx_bwd_kernel<T, int><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
+  else
+    maxpool_idx_bwd_kernel<T, long long><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }

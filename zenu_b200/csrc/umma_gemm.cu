@@ -71,7 +71,8 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
 // Shared by the implicit-GEMM kernel and the halo-reuse conv kernel: drains finished TMEM accumulators tile by tile.
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
-                                              uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err) {
+                                              uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
+                                              bool halo = false) {
   const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
   struct LL { int EPI_OFFSET; } Lv{epi_offset};
     // ================================ epilogue ================================
@@ -118,9 +119,18 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         }
         if (my_off >= 0) my_off += static_cast<long long>(tc.split) * p.split_stride + tc.tap * p.tap_col_stride;
       }
-      if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
-      tc_fence_after();
+      // accumulator flushes of this tile (see UmmaParams::chain_kb): all but the first accumulate into D
+      int n_sub = 1;
+      if (halo) {
+        if (p.halo_chain > 0) n_sub = (p.c_chunks + p.halo_chain - 1) / p.halo_chain;
+      } else if (p.chain_kb > 0) {
+        int kb0, kb1;
+        tile_kb_range(p, tc, kb0, kb1);
+        n_sub = max(1, (kb1 - kb0 + p.chain_kb - 1) / p.chain_kb);
+      }
       if (p.out_mode == OUT_WDGRAD) {
+        if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) break;
+        tc_fence_after();
         // accumulator D[q][s*4+c] (N = 32) -> shared [128 q][32] tile (all four warps) -> every thread overlap-adds the
         // filter columns s that reach its output element and stores the dense row dX[n][h][0..W)[0..C) coalesced
         uint32_t r[32];
@@ -150,7 +160,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
               }
             }
           }
-          out_row[o] = sum;
+          out_row[o] = p.beta != 0.f ? sum + p.beta * out_row[o] : sum;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
         acc ^= 1;
@@ -161,8 +171,25 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       long long offs[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + sub_row);
-      const bool use_beta = !partial && p.beta != 0.f;
-      const bool plain = partial || (p.alpha == 1.f && p.bias == nullptr && !use_beta);   // store the accumulator as is
+      bool dead = false;
+#pragma unroll 1
+      for (int sub = 0; sub < n_sub; ++sub) {
+      const float e_alpha = partial ? 1.f : p.alpha;
+      const float e_beta = sub == 0 ? (partial ? 0.f : p.beta) : 1.f;
+      const float* e_bias = (sub == 0 && !partial) ? p.bias : nullptr;
+      const bool use_beta = e_beta != 0.f;
+      const bool plain = e_alpha == 1.f && e_bias == nullptr && !use_beta;   // store the accumulator as is
+      // beta != 0 (gradient fan-in, 3xTF32 passes): the old tile is fetched one 32-column chunk ahead, the first chunk
+      // before the accumulator is even complete, so the read latency hides behind the MMAs / the previous chunk's stores
+      float4 olds[8];
+      const bool prefetch = use_beta && vec_ok;
+      if (prefetch && n0 + 32 <= p.N) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + n0 + piece * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) { dead = true; break; }
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -190,20 +217,22 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
               if (offs[it] >= 0 && p.dbg_epi != 1) *reinterpret_cast<float4*>(p.D + offs[it] + col) = vals[it];
           } else {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            float4 olds[8];
-            if (use_beta) {  // all reads of the old tile in flight before the first dependent store
+            if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
+            float4 cur[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) cur[it] = olds[it];
+            if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               if (offs[it] < 0) continue;
               float4 o = vals[it];
-              o.x = p.alpha * o.x + bv.x; o.y = p.alpha * o.y + bv.y; o.z = p.alpha * o.z + bv.z; o.w = p.alpha * o.w + bv.w;
+              o.x = e_alpha * o.x + bv.x; o.y = e_alpha * o.y + bv.y; o.z = e_alpha * o.z + bv.z; o.w = e_alpha * o.w + bv.w;
               if (use_beta) {
-                o.x += p.beta * olds[it].x; o.y += p.beta * olds[it].y; o.z += p.beta * olds[it].z; o.w += p.beta * olds[it].w;
+                o.x += e_beta * cur[it].x; o.y += e_beta * cur[it].y; o.z += e_beta * cur[it].z; o.w += e_beta * cur[it].w;
               }
               *reinterpret_cast<float4*>(p.D + offs[it] + col) = o;
             }
@@ -220,10 +249,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             for (int e = 0; e < 4; ++e)
               if (col + e < p.N) {
                 float val = e == 0 ? v4.x : (e == 1 ? v4.y : (e == 2 ? v4.z : v4.w));
-                if (!partial) {
-                  val = p.alpha * val + (p.bias != nullptr ? __ldg(p.bias + col + e) : 0.f);
-                  if (use_beta) val += p.beta * dst[e];
-                }
+                val = e_alpha * val + (e_bias != nullptr ? __ldg(e_bias + col + e) : 0.f);
+                if (use_beta) val += e_beta * dst[e];
                 dst[e] = val;
               }
           }
@@ -235,6 +262,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      }
+      if (dead) break;
     }
 }
 
@@ -359,7 +388,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
           } else if (p.b_mode == B_TILED_MN) {
-            for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK);
+            for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK - p.dbg_b_shift);
           } else if (p.b_mode == B_WINDOW_MN) {  // K index = pixel (32-pixel run of one output row), N index = window element
             const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
             const int img = row / p.conv_P, pp = row - img * p.conv_P;
@@ -391,11 +420,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const TileCoord tc = decode_tile(p, tile);
         int kb_begin, kb_end;
         tile_kb_range(p, tc, kb_begin, kb_end);
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) break;
+        bool ok = true;
+        int kb = kb_begin;
+        do {   // one pass per accumulator flush (a single one unless chain_kb limits the chain length)
+        const int sub_begin = kb;
+        const int sub_end = p.chain_kb > 0 ? min(kb_end, kb + p.chain_kb) : kb_end;
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) { ok = false; break; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        bool ok = true;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (; kb < sub_end; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -405,9 +438,9 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t da = a_mn ? make_smem_desc(a_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(a_base + k * 32 + p.dbg_a_shift * 128, 16, 1024, kSmemLayoutSw128,
                                                       p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0);
-            const uint64_t db = b_mn ? make_smem_desc(b_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
+            const uint64_t db = b_mn ? make_smem_desc(b_base + k * 1024 + p.dbg_b_shift * 128, p.dbg_b_lbo ? p.dbg_b_lbo : 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128);
-            umma_tf32(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, da, db, idesc, (kb > sub_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -416,6 +449,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        } while (kb < kb_end);
+        if (!ok) break;
       }
     }
   } else {
@@ -523,10 +558,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (resident) ok = mbar_wait(&b_full[0], 0, err);
       const uint32_t a_addr0 = smem_u32(sA), b_addr0 = smem_u32(sB);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) break;
+        for (int c = 0; c < chunks && ok;) {   // one pass per accumulator flush (halo_chain channel chunks each)
+        const int c_begin = c;
+        const int c_end = p.halo_chain > 0 ? min(chunks, c + p.halo_chain) : chunks;
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) { ok = false; break; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int c = 0; c < chunks && ok; ++c) {
+        for (; c < c_end && ok; ++c) {
           if (!mbar_wait(&a_full[ai], aph, err)) { ok = false; break; }
           tc_fence_after();
           const uint32_t a_base = a_addr0 + ai * p.halo_slot_bytes;
@@ -543,7 +581,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kUmmaBK / 8; ++k)
               umma_tf32(d_tmem, make_smem_desc(a_tap + k * 32, 16, 1024, kSmemLayoutSw128),
-                        make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128), idesc, (c > 0 || t > 0 || k > 0) ? 1u : 0u);
+                        make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128), idesc, (c > c_begin || t > 0 || k > 0) ? 1u : 0u);
             if (!resident) {
               umma_commit(&b_empty[bi]);
               if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
@@ -556,10 +594,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        }
+        if (!ok) break;
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err);
+    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true);
   }
   tc_fence_before();
   __syncthreads();
@@ -747,8 +787,15 @@ static int run_with_splits(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUte
   return ZB_OK;
 }
 
+// Accumulation-chain limit applied to every launch planned by this thread (set around the three 3xTF32 passes by api.cu).
+static thread_local int tl_chain_kb = 0;
+void umma_set_chain_limit(int kb) { tl_chain_kb = kb; }
+int umma_chain_limit() { return tl_chain_kb; }
+int umma_conv_wgrad_halo(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);  // umma_wgrad.cu
+
 static void init_params(UmmaParams& p, zb_ctx* ctx) {
   memset(&p, 0, sizeof(p));
+  p.chain_kb = tl_chain_kb;
   p.tap_tiles = 1;
   p.splits = 1;
   p.ntaps = 1;
@@ -759,6 +806,7 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
   p.err_flag = ctx->err_flag;
   if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &p.dbg_a_shift, &p.dbg_base_mode);
   if (const char* e = getenv("ZENU_B200_DBG_EPI")) p.dbg_epi = atoi(e);
+  if (const char* e = getenv("ZENU_B200_DBG_BSHIFT")) sscanf(e, "%d,%d", &p.dbg_b_shift, &p.dbg_b_lbo);
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM
@@ -905,6 +953,7 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
     for (int sx = 0; sx < S; ++sx) p.tap_w[r * S + sx] = static_cast<uint16_t>(r * hp.Wr + sx);
   p.halo_slots = hp.slots; p.halo_slot_bytes = hp.slot_bytes; p.halo_raster_bytes = hp.raster_bytes;
   p.halo_b_stages = hp.b_stages; p.halo_b_resident = hp.resident;
+  p.halo_chain = p.chain_kb > 0 ? std::max(1, p.chain_kb / taps) : 0;
   p.kb_total = taps * p.c_chunks;
   p.prof_flops = flops;
   p.D = out;
@@ -931,7 +980,7 @@ bool umma_conv_supported(const zb_conv2d_desc* d) {
 
 // y[N,P,Q,K] = conv(x[N,H,W,C], w[K,R,S,C]) (+bias)
 int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias,
-                         float* y) {
+                         float* y, float beta) {
   if (!umma_conv_supported(d)) { set_last_error("umma fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
@@ -943,7 +992,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
     if (halo_plan(ctx, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw), static_cast<int>(d->pad_h),
                   static_cast<int>(d->pad_w), &hp))
       return umma_conv_halo(ctx, hp, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw),
-                            static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, 0.f, 2.0 * M * d->k * d->c * taps);
+                            static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, beta, 2.0 * M * d->k * d->c * taps);
   }
   CUtensorMap ma, mb;
   UmmaParams p;
@@ -987,7 +1036,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
   p.D = y;
   p.ldd = d->k;
   finish_split_fields(p, 1);
-  return run_with_splits(ctx, bn, ma, mb, p, M, d->k, y, d->k, 1.f, 0.f, bias);
+  return run_with_splits(ctx, bn, ma, mb, p, M, d->k, y, d->k, 1.f, beta, bias);
 }
 
 // dx[N,H,W,C] = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Stride 1: one implicit GEMM over dy with the flipped filter.
@@ -1146,7 +1195,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
 }
 
 // dw[K,R,S,C] = wgrad(dy[N,P,Q,K], x[N,H,W,C]); reduction over N*P*Q pixels, split-K + deterministic reduce.
-int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, float* dw) {
+int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, float* dw, float beta) {
   if (d->c % 32 != 0 || d->k % 4 != 0 || d->kh * d->kw > kUmmaMaxTaps || d->pad_h > 127 || d->pad_w > 127 ||
       d->dil_h * (d->kh - 1) > 255 || d->dil_w * (d->kw - 1) > 255) {
     set_last_error("umma wgrad: shape unsupported");
@@ -1157,10 +1206,12 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long NPQ = d->n * P * Q;
   const int taps = static_cast<int>(d->kh * d->kw);
   const int bn = pick_bn(d->c);
+  int rc = umma_conv_wgrad_halo(ctx, d, dy, x, dw, beta);   // stride-1 R x S filters: every tap from one smem raster
+  if (rc != ZB_ERR_UNSUPPORTED) return rc;
   CUtensorMap ma, mb;
   UmmaParams p;
   init_params(p, ctx);
-  int rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK, true);
+  rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK, true);
   if (rc != ZB_OK) return rc;
   p.a_mode = A_TILED_MN;
   const bool pointwise = (taps == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0);
@@ -1201,6 +1252,7 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   finish_split_fields(p, pick_splits(ctx, tiles, p.kb_total, 16));
   if (p.splits <= 1) {
     p.split_stride = 0;
+    p.beta = beta;
     return umma_launch(ctx, bn, ma, mb, p);
   }
   // partial buffers keep the [K][taps*C] shape of dw
@@ -1216,7 +1268,7 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long total = rows * cols;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
   splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ws), dw, rows, cols, cols, rows * cols,
-                                                      q.splits, 1.f, 0.f, nullptr);
+                                                      q.splits, 1.f, beta, nullptr);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }
@@ -1267,7 +1319,7 @@ __global__ void smallc_pack_filter_kernel(const float* __restrict__ w, float* __
 }
 // dw[k][r][s][c] = alpha-free sum over split partials of dwp[split][k][r][s*4+c]
 __global__ void smallc_unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K, int R, int S, int C,
-                                        int splits, long long split_stride) {
+                                        int splits, long long split_stride, float beta) {
   const int total = K * R * S * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -1275,7 +1327,7 @@ __global__ void smallc_unpack_dw_kernel(const float* __restrict__ dwp, float* __
     const int kr = i / (C * S);
     float acc = 0.f;
     for (int sp = 0; sp < splits; ++sp) acc += dwp[sp * split_stride + static_cast<long long>(kr) * 32 + sidx * 4 + c];
-    dw[i] = acc;
+    dw[i] = beta != 0.f ? acc + beta * dw[i] : acc;
   }
 }
 
@@ -1325,7 +1377,7 @@ static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcG
 
 // y[N,P,Q,K] (NHWC) = conv(x, w[K,R,S,C]) (+bias); x is NHWC (x_nchw = 0) or NCHW (x_nchw = 1)
 int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
-                           float* y) {
+                           float* y, float beta) {
   if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const SmallcGeom g = smallc_geom(d);
   void* ws = nullptr;
@@ -1368,13 +1420,14 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
   p.D = y;
   p.ldd = d->k;
   finish_split_fields(p, 1);
-  return run_with_splits(ctx, bn, ma, mb, p, p.M, d->k, y, d->k, 1.f, 0.f, bias);
+  return run_with_splits(ctx, bn, ma, mb, p, p.M, d->k, y, d->k, 1.f, beta, bias);
 }
 
 // dw[K,R,S,C] = wgrad(dy[N,P,Q,K] (NHWC), x); reduction over pixels in 32-pixel runs of one output row.
 // Up to 8 filter rows are folded into GEMM-N (N = R x 32 window elements share every dY tile), more rows fall back to one
 // tile group per filter row.
-int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, int x_nchw, float* dw) {
+int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, int x_nchw, float* dw,
+                           float beta) {
   if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C wgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const SmallcGeom g = smallc_geom(d);
   const long long NPQ = d->n * g.P * g.Q;
@@ -1423,7 +1476,7 @@ int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
   smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
                                                                         static_cast<int>(d->kw), static_cast<int>(d->c), p.splits,
-                                                                        rows * cols);
+                                                                        rows * cols, beta);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
 }
@@ -1456,7 +1509,7 @@ bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc* d) {
 // dx[N,H,W,C] (NHWC, C <= 4) = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Tile = one input row (n, h): the accumulator
 // D[q][s*4+c] = sum over the filter rows r reaching h and over k of dY[n, p(h,r), q, k] * w[k,r,s,c]; the epilogue overlap-adds
 // the filter columns.  dY is fetched ~R/stride_h times instead of R*S times (general parity-class path).
-int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx) {
+int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
   if (!umma_conv_smallc_dgrad_supported(d)) { set_last_error("umma small-C dgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
@@ -1513,6 +1566,8 @@ int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   p.ldd = d->c;
   finish_split_fields(p, 1);
   p.split_stride = 0;
+  p.beta = beta;
+  p.chain_kb = 0;  // the overlap-add epilogue drains one accumulator per tile (K <= R * k/32 blocks: a short chain anyway)
   return umma_launch(ctx, 32, ma, mb, p);
 }
 

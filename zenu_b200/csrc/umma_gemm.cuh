@@ -64,6 +64,11 @@ struct UmmaParams {
   // halo-reuse conv kernel (stride-1 RxS convs): one smem raster of (tp + R - 1) x Wr input pixels per 32-channel chunk
   // serves every filter tap through UMMA descriptors that start tap_w[t] rows (128 bytes each) into the raster
   int halo_slots, halo_slot_bytes, halo_raster_bytes, halo_b_stages, halo_b_resident;
+  // accumulation-chain limit (3xTF32 mode): the tensor core adds into TMEM with truncation, a bias that grows with the number
+  // of MMA steps; with chain_kb > 0 the accumulator is flushed through the epilogue (fp32 round-to-nearest adds into D) every
+  // chain_kb K blocks (halo kernel: every halo_chain channel chunks) instead of once per tile.  0 = one chain per tile.
+  int chain_kb, halo_chain;
+  int dbg_b_shift, dbg_b_lbo;  // experiments only (ZENU_B200_DBG_BSHIFT): MN-major B descriptor start shifted by 128-byte rows / overlapped N boxes
   int dbg_a_shift, dbg_base_mode, dbg_epi;  // experiments only (ZENU_B200_DBG_ASHIFT): A descriptor start shifted by whole 128-byte rows
   int* err_flag;              // device word set to 1 on an mbarrier timeout
   double prof_flops;          // host only: algorithmic FLOPs of this launch (profiling)
