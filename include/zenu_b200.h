@@ -89,6 +89,16 @@ int64_t zb_conv_out_size(int64_t in, int64_t k, int64_t pad, int64_t stride, int
 /* y = conv(x, w) (+ bias[k] when bias != NULL, fused in the epilogue; reference: separate conv_bias_add pass) */
 int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x,
                     const void* w, const void* bias, void* y);
+/* Conv fprop that also emits the per-channel statistics a following BatchNorm2d (training) needs, accumulated in the
+ * conv epilogue while the output tile is still in registers: stat_partial [rows][2][k] = partial sums of (y - shift[k]) and
+ * (y - shift[k])^2 over the pixels each row covers (NHWC output, f32, tensor-core paths).  `stat_partial` must hold
+ * zb_conv2d_bnstats_rows(ctx) x 2 x k floats; `shift` [k] is any per-channel offset (the BN running mean is a good one), the
+ * same pointer is handed to zb_bn2d_fwd_train_prestats.  *stat_rows = rows written, or 0 when this shape / math mode cannot
+ * fuse them (the conv result is complete either way; the caller then runs the plain zb_bn2d_fwd_train). */
+int zb_conv2d_bnstats_rows(zb_ctx* ctx);
+int zb_conv2d_fprop_bnstats(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x,
+                            const void* w, const void* bias, void* y, const void* shift, void* stat_partial,
+                            int64_t* stat_rows);
 int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                     const void* w, void* dx);
 /* dx += dgrad(dy, w): gradient fan-in (zenu-autograd/src/lib.rs:480-481 `grad + old`) folded into the dgrad epilogue */
@@ -115,6 +125,12 @@ int zb_bn2d_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, 
                       double momentum, const void* x, const void* scale, const void* bias, void* running_mean,
                       void* running_var, void* saved_mean, void* saved_inv_std, void* y, const void* residual,
                       int relu);
+/* Same as zb_bn2d_fwd_train with the statistics pass replaced by the partial sums zb_conv2d_fprop_bnstats produced
+ * (x is that conv's output; NHWC f32): x is read once instead of twice. */
+int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w,
+                               double momentum, const void* x, const void* scale, const void* bias, void* running_mean,
+                               void* running_var, void* saved_mean, void* saved_inv_std, void* y, const void* residual,
+                               int relu, const void* stat_partial, int64_t stat_rows, const void* shift);
 int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                       const void* scale, const void* bias, const void* mean, const void* var, void* y);
 /* dy is the gradient w.r.t. the (possibly fused) output.  When the forward fused relu, pass the forward

@@ -393,6 +393,44 @@ def test_bn_vs_oracle(zb, ctx, shape, layout, dtype):
                                                  rm0.astype(np.float64), rv0.astype(np.float64))) < tol
 
 
+@pytest.mark.parametrize("case", [
+    (4, 64, 14, 14, 256, 1, 0, 1),     # 1x1 GEMM path, 2 column tiles of 128 -> one of 256
+    (3, 64, 18, 18, 64, 3, 1, 1),      # halo-reuse 3x3 (dead halo rows must not enter the statistics)
+    (2, 128, 15, 15, 512, 1, 0, 2),    # strided 1x1 (im2col path), ragged last M tile
+    (2, 32, 16, 16, 96, 3, 1, 2),      # 3x3 stride 2 (im2col path), N = 96 (BN 128 tile, partly empty)
+    (2, 3, 40, 40, 64, 7, 3, 2),       # C = 3 stem (sliding-window path)
+])
+def test_conv_fused_bn_statistics(zb, ctx, case):
+    """conv fprop + BatchNorm statistics fused in the conv epilogue, then BN apply from those partials == the oracle's
+    conv -> BatchNorm(train) on the same inputs; also == the unfused GPU path (same y, same saved statistics)."""
+    from zenu_b200 import ZB_NHWC
+    n, c, hw, _, k, r, pad, stride = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((n, c, hw, hw)).astype(np.float32)
+    w = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, k).astype(np.float32)
+    bias = rng.standard_normal(k).astype(np.float32)
+    rmean = (0.3 * rng.standard_normal(k)).astype(np.float32)      # non-trivial shift
+    rvar = rng.uniform(0.5, 2.0, k).astype(np.float32)
+    X, W = dev(nhwc(x)), dev(nhwc(w))
+    rm1, rv1, rm2, rv2 = dev(rmean), dev(rvar), dev(rmean), dev(rvar)
+    y, partial, rows = zb.conv_fwd_bnstats(ctx, X, W, rm1, pad, stride, 1, layout=ZB_NHWC)
+    assert rows > 0, "statistics were not fused for this shape"
+    a, sm, si = zb.batch_norm_2d_forward_train_prestats(ctx, 0.9, y, dev(scale), dev(bias), rm1, rv1, partial, rows, rm1, relu=True)
+    y2 = zb.conv_fwd(ctx, X, W, pad, stride, 1, layout=ZB_NHWC)
+    a2, sm2, si2 = zb.batch_norm_2d_forward_train(ctx, 0.9, y2, dev(scale), dev(bias), rm2, rv2, layout=ZB_NHWC, relu=True)
+    np.testing.assert_array_equal(host(y), host(y2))
+    assert rel_err(host(sm), host(sm2)) < 1e-5 and rel_err(host(si), host(si2)) < 1e-5
+    assert rel_err(host(rm1), host(rm2)) < 1e-5 and rel_err(host(rv1), host(rv2)) < 1e-5
+    assert rel_err(host(a), host(a2)) < 1e-5
+    # against the oracle BatchNorm fed with the SAME conv output (conv parity itself is covered above)
+    ref, rm_ref, rv_ref, sm_ref, si_ref = zo.bn2d_fwd_train(nchw(host(y)), scale, bias, rmean.copy(), rvar.copy(), 0.9)
+    assert rel_err(nchw(host(a)), zo.relu(ref)) < 1e-4
+    assert rel_err(host(sm), sm_ref) < 1e-4 and rel_err(host(si), si_ref) < 1e-4
+    assert rel_err(host(rm1), rm_ref) < 1e-4 and rel_err(host(rv1), rv_ref) < 1e-4
+    ctx.check()
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 def test_bn_fused_relu_residual(zb, ctx, layout):
     """Fused BN+add+ReLU fwd/bwd == the reference's separate nodes (BN -> add -> relu) composed from oracle ops."""
@@ -477,7 +515,7 @@ def test_dgrad_accumulate(zb, ctx):
 def test_maxpool_indexed(zb, ctx):
     """Indexed NHWC max-pool: forward == oracle (zero padding takes part, first max wins), backward gather == oracle."""
     rng = np.random.default_rng(18)
-    for shape, (k, s, p) in (((2, 8, 11, 9), (3, 2, 1)), ((1, 4, 8, 8), (2, 2, 0)), ((2, 12, 7, 10), (3, 1, 1))):
+    for shape, (k, s, p) in (((2, 8, 11, 9), (3, 2, 1)), ((1, 4, 8, 8), (2, 2, 0)), ((2, 12, 7, 10), (3, 1, 1)), ((1, 4, 9, 12), (5, 2, 2))):
         x = np.maximum(rng.standard_normal(shape), 0).astype(np.float32) - (0.2 if k == 3 and s == 1 else 0.0)
         x = x.astype(np.float32)
         y_ref = zo.maxpool2d_fwd(x, k, s, p)

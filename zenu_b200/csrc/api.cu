@@ -11,11 +11,11 @@ int umma_gemm(zb_ctx*, bool, bool, long long, long long, long long, float, const
               float, float*, long long, const float*);
 void umma_set_chain_limit(int);
 bool umma_conv_supported(const zb_conv2d_desc*);
-int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*, float);
+int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*, float, const float*, float*, int*);
 int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 bool umma_conv_smallc_supported(const zb_conv2d_desc*);
-int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*, float);
+int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*, float, const float*, float*, int*);
 int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*, float);
 bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc*);
 int umma_conv_smallc_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
@@ -123,20 +123,30 @@ static int tc_gemm(zb_ctx* ctx, int mm, bool ta, bool tb, long long m, long long
   });
 }
 
-static int tc_fprop_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias, float* y) {
-  if (mm != ZB_MATH_TF32X3) return umma_conv_fprop_nhwc(ctx, d, x, w, bias, y, 0.f);
+struct BnStats {   // fused BatchNorm statistics request (zb_conv2d_fprop_bnstats); rows stays 0 when the path cannot fuse them
+  const float* shift = nullptr;
+  float* partial = nullptr;
+  int rows = 0;
+};
+
+static int tc_fprop_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias, float* y,
+                         BnStats* bs = nullptr) {
+  if (mm != ZB_MATH_TF32X3)
+    return umma_conv_fprop_nhwc(ctx, d, x, w, bias, y, 0.f, bs ? bs->shift : nullptr, bs ? bs->partial : nullptr, bs ? &bs->rows : nullptr);
   return run_tf32x3(ctx, x, d->n * d->h * d->w * d->c, w, d->k * d->kh * d->kw * d->c, 0.f,
                     [&](const float* xp, const float* wp, float bt, bool last) {
-                      return umma_conv_fprop_nhwc(ctx, d, xp, wp, last ? bias : nullptr, y, bt);
+                      return umma_conv_fprop_nhwc(ctx, d, xp, wp, last ? bias : nullptr, y, bt, nullptr, nullptr, nullptr);
                     });
 }
 
 static int tc_smallc_fprop(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
-                           float* y) {
-  if (mm != ZB_MATH_TF32X3) return umma_conv_smallc_fprop(ctx, d, x, x_nchw, w, bias, y, 0.f);
+                           float* y, BnStats* bs = nullptr) {
+  if (mm != ZB_MATH_TF32X3)
+    return umma_conv_smallc_fprop(ctx, d, x, x_nchw, w, bias, y, 0.f, bs ? bs->shift : nullptr, bs ? bs->partial : nullptr,
+                                  bs ? &bs->rows : nullptr);
   return run_tf32x3(ctx, x, d->n * d->h * d->w * d->c, w, d->k * d->kh * d->kw * d->c, 0.f,
                     [&](const float* xp, const float* wp, float bt, bool last) {
-                      return umma_conv_smallc_fprop(ctx, d, xp, x_nchw, wp, last ? bias : nullptr, y, bt);
+                      return umma_conv_smallc_fprop(ctx, d, xp, x_nchw, wp, last ? bias : nullptr, y, bt, nullptr, nullptr, nullptr);
                     });
 }
 
@@ -166,8 +176,29 @@ using namespace zb;
 
 extern "C" {
 
+static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
+                      const void* bias, void* y, BnStats* bs);
+
 int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
                     const void* bias, void* y) {
+  return fprop_impl(ctx, dtype, layout, math, d, x, w, bias, y, nullptr);
+}
+
+int zb_conv2d_bnstats_rows(zb_ctx* ctx) { return ctx->sm_count * 4; }
+
+int zb_conv2d_fprop_bnstats(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
+                            const void* bias, void* y, const void* shift, void* stat_partial, int64_t* stat_rows) {
+  ZB_REQUIRE(shift != nullptr && stat_partial != nullptr && stat_rows != nullptr, "conv fprop + bn stats: NULL statistics argument");
+  BnStats bs;
+  bs.shift = static_cast<const float*>(shift);
+  bs.partial = static_cast<float*>(stat_partial);
+  const int rc = fprop_impl(ctx, dtype, layout, math, d, x, w, bias, y, dtype == ZB_F32 ? &bs : nullptr);
+  *stat_rows = bs.rows;
+  return rc;
+}
+
+static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
+                      const void* bias, void* y, BnStats* bs) {
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
@@ -179,7 +210,7 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   if (layout == ZB_NCHW_X) {
     if (dtype == ZB_F32 && m != ZB_MATH_FP32 && umma_conv_smallc_supported(d))
       return tc_smallc_fprop(ctx, m, d, static_cast<const float*>(x), 1, static_cast<const float*>(w), static_cast<const float*>(bias),
-                             static_cast<float*>(y));
+                             static_cast<float*>(y), bs);
     set_last_error("conv fprop: ZB_NCHW_X is served for C <= 4 on the TF32 / 3xTF32 paths only");
     return ZB_ERR_UNSUPPORTED;
   }
@@ -191,9 +222,9 @@ int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* bf = static_cast<const float*>(bias);
   float* yf = static_cast<float*>(y);
   if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
-    return tc_smallc_fprop(ctx, m, d, xf, 0, wf, bf, yf);
+    return tc_smallc_fprop(ctx, m, d, xf, 0, wf, bf, yf, bs);
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_fprop<float>(ctx, layout, d, xf, wf, bf, yf);
-  if (layout == ZB_NHWC) return tc_fprop_nhwc(ctx, m, d, xf, wf, bf, yf);
+  if (layout == ZB_NHWC) return tc_fprop_nhwc(ctx, m, d, xf, wf, bf, yf, bs);
   // NCHW contract: stage through NHWC / KRSC
   Temp tx(ctx), tw(ctx), ty(ctx);
   if ((rc = tx.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;

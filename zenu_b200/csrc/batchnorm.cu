@@ -289,7 +289,7 @@ __device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int
 template <typename T>
 __global__ void __launch_bounds__(kFinC * kFinS)
 bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum,
-                const T* __restrict__ x_first_row, long long shift_stride, T* __restrict__ run_mean, T* __restrict__ run_var,
+                const T* x_first_row, long long shift_stride, T* run_mean, T* __restrict__ run_var,
                 T* __restrict__ saved_mean, T* __restrict__ saved_inv, T* __restrict__ coef) {
   const long long c = blockIdx.x * static_cast<long long>(kFinC) + (threadIdx.x & (kFinC - 1));
   double st[2];
@@ -604,7 +604,10 @@ static int dispatch_apply(zb_ctx* ctx, int layout, long long N, long long C, lon
 template <typename T>
 static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, double momentum,
                           const T* x, const T* scale, const T* bias, T* run_mean, T* run_var, T* saved_mean,
-                          T* saved_inv, T* y, const T* res, int relu) {
+                          T* saved_inv, T* y, const T* res, int relu, const T* pre_partial = nullptr, int pre_rows = 0,
+                          const T* pre_shift = nullptr) {
+  // pre_partial != NULL: the statistics pass already happened inside the producing conv's epilogue
+  // (zb_conv2d_fprop_bnstats): [pre_rows][2][C] partial sums of (x - pre_shift) and its square
   ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
   ZB_REQUIRE(N * H * W < 2147483647ll * 64, "bn: tensor too large");
   const long long HW = H * W;
@@ -616,17 +619,23 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
   T* coef = partial + ms * 2 * C;
   int slabs = 0;
   prof_begin(ctx, PROF_BN);
-  rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
-                                  partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
-  if (rc != ZB_OK) return rc;
-  // shift used by the reduce = first row (NHWC: x[c]) or first element of channel c in image 0 (NCHW: x[c*HW])
-  bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
-                                                               layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
-                                                               saved_inv, coef);
-  ZB_LAUNCH_CHECK(ctx);
+  if (pre_partial != nullptr) {
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(pre_partial, pre_rows, C, static_cast<double>(N * HW), momentum, pre_shift,
+                                                                 1, run_mean, run_var, saved_mean, saved_inv, coef);
+    ZB_LAUNCH_CHECK(ctx);
+  } else {
+    rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
+                                    partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
+    if (rc != ZB_OK) return rc;
+    // shift used by the reduce = first row (NHWC: x[c]) or first element of channel c in image 0 (NCHW: x[c*HW])
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
+                                                                 layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
+                                                                 saved_inv, coef);
+    ZB_LAUNCH_CHECK(ctx);
+  }
   rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu);
-  // algorithmic bytes: x read twice + y written (+ residual read)
-  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * (res ? 4.0 : 3.0));
+  // algorithmic bytes: x read twice (once when the statistics came with the conv) + y written (+ residual read)
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * ((res ? 4.0 : 3.0) - (pre_partial ? 1.0 : 0.0)));
   return rc;
 }
 
@@ -768,6 +777,19 @@ int zb_bn2d_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, 
                                   static_cast<const double*>(residual), relu);
   zb::set_last_error("unknown dtype %d", dtype);
   return ZB_ERR_INVALID;
+}
+
+int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, double momentum,
+                               const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
+                               void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu,
+                               const void* stat_partial, int64_t stat_rows, const void* shift) {
+  ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32, "bn prestats: NHWC f32 only");
+  ZB_REQUIRE(stat_partial != nullptr && shift != nullptr && stat_rows > 0 && stat_rows < (1 << 30), "bn prestats: missing statistics");
+  return bn_fwd_train_t<float>(ctx, layout, n, c, h, w, momentum, static_cast<const float*>(x), static_cast<const float*>(scale),
+                               static_cast<const float*>(bias), static_cast<float*>(running_mean), static_cast<float*>(running_var),
+                               static_cast<float*>(saved_mean), static_cast<float*>(saved_inv_std), static_cast<float*>(y),
+                               static_cast<const float*>(residual), relu, static_cast<const float*>(stat_partial),
+                               static_cast<int>(stat_rows), static_cast<const float*>(shift));
 }
 
 int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,

@@ -255,8 +255,22 @@ struct ConvFn : Function {
   }
 };
 
-Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx) {
+Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx,
+                const Variable* bn_shift) {
   Variable x = x_in;
+  // fused BatchNorm statistics: only while training, f32 (the kernel reports 0 rows when the shape cannot fuse them)
+  Tensor stats;
+  int64_t stat_rows = 0;
+  const bool want_stats = bn_shift != nullptr && rt.train && rt.dtype == ZB_F32 && w.shape().size() == 4 &&
+                          (*bn_shift)->data.numel() == w.shape()[0] && getenv("ZENU_B200_NO_BNSTATS") == nullptr;
+  if (want_stats) stats = rt.empty({static_cast<int64_t>(zb_conv2d_bnstats_rows(rt.ctx)), 2, w.shape()[0]});
+  auto run_fprop = [&](int layout, const zb_conv2d_desc* d, const void* xp, void* yp, int dtype) {
+    const void* bp = bias ? (*bias)->data.ptr : nullptr;
+    if (want_stats)
+      return zb_conv2d_fprop_bnstats(rt.ctx, dtype, layout, ZB_MATH_DEFAULT, d, xp, w->data.ptr, bp, yp, (*bn_shift)->data.ptr, stats.ptr,
+                                     &stat_rows);
+    return zb_conv2d_fprop(rt.ctx, dtype, layout, ZB_MATH_DEFAULT, d, xp, w->data.ptr, bp, yp);
+  };
   const auto& ws = w.shape();
   if (x.shape().size() != 4 || ws.size() != 4) throw HostError("conv2d: bad shapes (NHWC input, KRSC filter)");
   auto fn = std::make_shared<ConvFn>();
@@ -272,8 +286,7 @@ Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Vari
     int rc;
     {
       ProfScope ps(rt, conv_key("fprop", fn->d), conv_flops(fn->d), conv_bytes(fn->d, y.elem_size()));
-      rc = zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NCHW_X, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
-                           bias ? (*bias)->data.ptr : nullptr, y.ptr);
+      rc = run_fprop(ZB_NCHW_X, &fn->d, x->data.ptr, y.ptr, y.dtype);
     }
     if (rc == ZB_OK) {
       fn->x_layout = ZB_NCHW_X;
@@ -291,8 +304,7 @@ Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Vari
     const int64_t P = out_size(xs[1], ws[1], a.pad_h, a.stride_h, a.dil_h), Q = out_size(xs[2], ws[2], a.pad_w, a.stride_w, a.dil_w);
     y = rt.empty({xs[0], P, Q, ws[0]});
     ProfScope ps(rt, conv_key("fprop", fn->d), conv_flops(fn->d), conv_bytes(fn->d, y.elem_size()));
-    check_rc(zb_conv2d_fprop(rt.ctx, y.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &fn->d, x->data.ptr, w->data.ptr,
-                             bias ? (*bias)->data.ptr : nullptr, y.ptr), "conv fprop");
+    check_rc(run_fprop(ZB_NHWC, &fn->d, x->data.ptr, y.ptr, y.dtype), "conv fprop");
   }
   fn->inputs = {x.ptr(), w.ptr()};
   if (bias) fn->inputs.push_back(bias->ptr());
@@ -300,7 +312,13 @@ Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Vari
   fn->need_dx = need_dx;
   fn->x = x->data;
   fn->w = w->data;
-  return make_output(y, fn);
+  Variable out = make_output(y, fn);
+  if (want_stats && stat_rows > 0) {
+    out->bn_stats = stats;
+    out->bn_stat_rows = stat_rows;
+    out->bn_shift = (*bn_shift)->data.ptr;
+  }
+  return out;
 }
 
 struct BnFn : Function {
@@ -357,9 +375,18 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   fn->saved_inv = rt.empty({c});
   ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
                static_cast<double>(y.bytes()) * (residual ? 4.0 : 3.0));
-  check_rc(zb_bn2d_fwd_train(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
-                             mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
-                             residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0), "bn fwd");
+  if (x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr) {   // statistics came with the producing conv
+    check_rc(zb_bn2d_fwd_train_prestats(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
+                                        mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
+                                        residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0, x->bn_stats.ptr, x->bn_stat_rows,
+                                        x->bn_shift), "bn fwd (fused statistics)");
+    x->bn_stats = Tensor();
+    x->bn_stat_rows = 0;
+  } else {
+    check_rc(zb_bn2d_fwd_train(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
+                               mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
+                               residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0), "bn fwd");
+  }
   fn->inputs = {x.ptr(), scale.ptr(), bias.ptr()};
   if (residual) fn->inputs.push_back(residual->ptr());
   fn->x = x->data;
@@ -584,7 +611,9 @@ static std::string join(const std::string& p, const char* leaf) { return p.empty
 
 Conv2d::Conv2d(int64_t ci, int64_t co, int64_t k, int64_t stride, int64_t pad, int64_t dil, bool b)
     : args{pad, pad, stride, stride, dil, dil}, has_bias(b), cin(ci), cout(co), kh(k), kw(k) {}
-Variable Conv2d::call(Runtime& rt, const Variable& x) { return conv2d(rt, x, filter, has_bias ? &bias : nullptr, args, need_dx); }
+Variable Conv2d::call(Runtime& rt, const Variable& x) {
+  return conv2d(rt, x, filter, has_bias ? &bias : nullptr, args, need_dx, next_bn ? &next_bn->mean : nullptr);
+}
 void Conv2d::weights(const std::string& p, ParamMap& o) const { o[join(p, "conv2d.filter")] = filter; }
 void Conv2d::biases(const std::string& p, ParamMap& o) const { if (has_bias) o[join(p, "conv2d.bias")] = bias; }
 
@@ -646,6 +675,7 @@ struct SmallCnn : Model {
     linear1 = std::make_shared<Linear>(64 * 32 * 32, 512, true);
     linear2 = std::make_shared<Linear>(512, num_classes, true);
     children = {{"conv1", conv1}, {"batch_norm1", bn1}, {"conv2", conv2}, {"batch_norm2", bn2}, {"linear1", linear1}, {"linear2", linear2}};
+    if (fused) { conv1->next_bn = bn1.get(); conv2->next_bn = bn2.get(); }
   }
   void collect(std::vector<ParamSpec>& s) override {
     spec_conv(s, "conv1", *conv1); spec_bn(s, "batch_norm1", *bn1);
@@ -684,6 +714,10 @@ struct ResBlock : Module {
     if (stride != 1 || cin != cout) {
       down_conv = std::make_shared<Conv2d>(cin, cout, 1, stride, 0, 1, false);
       down_bn = std::make_shared<BatchNorm2d>(cout, 0.9);
+    }
+    if (fused) {   // every conv feeds a BatchNorm: its statistics pass runs inside the conv epilogue
+      for (size_t i = 0; i < convs.size(); ++i) convs[i]->next_bn = bns[i].get();
+      if (down_conv) down_conv->next_bn = down_bn.get();
     }
   }
   void collect(std::vector<ParamSpec>& s, const std::string& p) {
@@ -732,6 +766,7 @@ struct ResNet : Model {
     conv1 = std::make_shared<Conv2d>(3, 64, 7, 2, 3, 1, false);
     conv1->need_dx = true;  // the reference computes the input gradient of every conv (conv_without_bias.rs:110-121)
     bn1 = std::make_shared<BatchNorm2d>(64, 0.9);
+    if (fused) conv1->next_bn = bn1.get();
     children = {{"conv1", conv1}, {"bn1", bn1}};
     int64_t cin = 64;
     for (int stage = 0; stage < 4; ++stage) {

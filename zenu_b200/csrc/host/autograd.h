@@ -122,6 +122,10 @@ struct VariableInner {
   bool is_param = false;
   int bucket = -1;                   // data-parallel bucket this parameter's gradient belongs to
   bool nchw = false;                 // network input still in the reference's NCHW layout (consumed by the stem conv)
+  // conv output followed by a BatchNorm: per-channel statistics already accumulated in the conv epilogue
+  Tensor bn_stats;                   // [rows][2][K] partial sums (zb_conv2d_fprop_bnstats)
+  int64_t bn_stat_rows = 0;
+  const void* bn_shift = nullptr;    // the shift vector they were taken against (the BN's running mean)
   std::string name;
 };
 
@@ -150,7 +154,9 @@ void commit_grad(Runtime& rt, VariableInner& v, const Tensor& g);  // g was prod
 
 // ---- differentiable functions (NHWC activations, KRSC filters) ------------------------------------------
 struct ConvArgs { int64_t pad_h, pad_w, stride_h, stride_w, dil_h, dil_w; };
-Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx = true);
+// bn_shift: running mean of the BatchNorm2d that consumes the output (training): its statistics pass is fused into the conv
+Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variable* bias, const ConvArgs& a, bool need_dx = true,
+                const Variable* bn_shift = nullptr);
 // BatchNorm2d with optional fused residual add and ReLU; running stats updated in place when training
 Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, const Variable& bias, const Variable& mean,
                        const Variable& variance, double momentum, const Variable* residual, bool relu);
@@ -189,6 +195,7 @@ struct Conv2d : Module {
   ConvArgs args;
   bool has_bias, need_dx = true;
   int64_t cin, cout, kh, kw;
+  const struct BatchNorm2d* next_bn = nullptr;   // set by fused model builders: the BatchNorm2d applied to this conv's output
   Conv2d(int64_t cin, int64_t cout, int64_t k, int64_t stride, int64_t pad, int64_t dil, bool bias);
   Variable call(Runtime& rt, const Variable& x) override;
   void weights(const std::string& p, ParamMap& o) const override;

@@ -188,6 +188,78 @@ __global__ void __launch_bounds__(256) maxpool_idx_bwd_kernel(const PoolGeom g, 
   }
 }
 
+// Backward for stride (2, 2): one thread owns a 2 x 2 input patch (x 4 channels).  The windows covering the patch are loaded
+// once for its four pixels instead of once per pixel (3x3/s2: 4 window reads per patch instead of 9), which is what the
+// per-pixel gather above is bound by (L2 read volume, not HBM).
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_idx_bwd_s2_kernel(const PoolGeom g, const T* __restrict__ dy,
+                                                                 const uchar4* __restrict__ idx, T* __restrict__ dx) {
+  using V = typename Vec4T<T>::type;
+  const int c4n = static_cast<int>(g.C >> 2), Q = static_cast<int>(g.Q), P = static_cast<int>(g.P), H = static_cast<int>(g.H), W = static_cast<int>(g.W);
+  const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+  const int total = static_cast<int>(g.N) * H2 * W2 * c4n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = i % c4n;
+    int t = i / c4n;
+    const int b = t % W2; t /= W2;
+    const int a = t % H2;
+    const int n = t / H2;
+    const int h0 = 2 * a, w0 = 2 * b;
+    T acc[2][2][4];
+#pragma unroll
+    for (int y = 0; y < 2; ++y)
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[y][x][e] = T(0);
+    // windows p with p*2 - ph <= h0 + 1 and p*2 - ph + kh - 1 >= h0
+    int p_lo = h0 + g.ph - g.kh + 1;
+    p_lo = p_lo <= 0 ? 0 : (p_lo + 1) >> 1;
+    int p_hi = (h0 + 1 + g.ph) >> 1;
+    if (p_hi > P - 1) p_hi = P - 1;
+    int q_lo = w0 + g.pw - g.kw + 1;
+    q_lo = q_lo <= 0 ? 0 : (q_lo + 1) >> 1;
+    int q_hi = (w0 + 1 + g.pw) >> 1;
+    if (q_hi > Q - 1) q_hi = Q - 1;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const int r0 = h0 + g.ph - 2 * p;           // filter row of patch row 0 (row 1: r0 + 1)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const int s0 = w0 + g.pw - 2 * q;
+        const int o = ((n * P + p) * Q + q) * c4n + c4;
+        const uchar4 wi = idx[o];
+        const V gv = *(reinterpret_cast<const V*>(dy) + o);
+        const unsigned char win[4] = {wi.x, wi.y, wi.z, wi.w};
+        const T gvv[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          const int r = r0 + y;
+          if (r < 0 || r >= g.kh) continue;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int s_ = s0 + x;
+            if (s_ < 0 || s_ >= g.kw) continue;
+            const unsigned char tap = static_cast<unsigned char>(r * g.kw + s_);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (win[e] == tap) acc[y][x][e] += gvv[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int y = 0; y < 2; ++y) {
+      if (h0 + y >= H) continue;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (w0 + x >= W) continue;
+        V o4;
+        o4.x = acc[y][x][0]; o4.y = acc[y][x][1]; o4.z = acc[y][x][2]; o4.w = acc[y][x][3];
+        *(reinterpret_cast<V*>(dx) + ((static_cast<long long>(n) * H + h0 + y) * W + w0 + x) * c4n + c4) = o4;
+      }
+    }
+  }
+}
+
 template <typename T>
 static int maxpool_idx_fwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, T* y, void* idx) {
   const long long total = g.N * g.P * g.Q * (g.C >> 2);
@@ -205,7 +277,11 @@ static int maxpool_idx_bwd_t(zb_ctx* ctx, const PoolGeom& g, const T* dy, const 
   const long long total = g.N * g.H * g.W * (g.C >> 2);
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
-  if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24))
+  if (g.sh == 2 && g.sw == 2 && g.N * (g.H + 1) * (g.W + 1) * g.C < (1ll << 31) - (1ll << 24)) {
+    const long long patches = g.N * ((g.H + 1) / 2) * ((g.W + 1) / 2) * (g.C >> 2);
+    const int grid2 = static_cast<int>(std::min<long long>((patches + 255) / 256, ctx->sm_count * 32ll));
+    maxpool_idx_bwd_s2_kernel<T><<<grid2, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
+  } else if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24))
     maxpool_idx_bwd_kernel<T, int><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);
   else
     maxpool_idx_bwd_kernel<T, long long><<<grid, 256, 0, ctx->stream>>>(g, dy, static_cast<const uchar4*>(idx), dx);

@@ -35,7 +35,9 @@ struct UmmaSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;   // 4 warps x [32 rows][32 cols] fp32 staging (coalesced stores)
   static constexpr int EPI_BYTES = 4 * 4096;
-  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+  static constexpr int STAT_OFFSET = EPI_OFFSET + EPI_BYTES;   // 4 warps x [2 stats][BN] fp32 (fused BatchNorm statistics)
+  static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
+  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -89,6 +91,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const bool partial = p.splits > 1;
     const int sub_row = lane >> 3, piece = lane & 7;
+    float* stat_w = reinterpret_cast<float*>(smem + Lv.EPI_OFFSET + 4 * 4096) + ew * 2 * BN;   // this warp's [2][BN] statistics
+    const bool stats = p.stat_partial != nullptr;
+    if (stats) {
+      for (int j = lane; j < 2 * BN; j += 32) stat_w[j] = 0.f;
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
@@ -143,24 +151,29 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM buffer is free: the MMA warp may start the next tile
-        const float* tile_s = reinterpret_cast<const float*>(smem + Lv.EPI_OFFSET);
-        const int row_elems = p.dg_W * p.dg_C;
+        // one thread per output pixel w: the <= ceil(S / stride_w) filter columns that reach it are 128-bit smem reads (4 channels
+        // of one tap), q steps down by one as the column steps up by stride_w
+        const float4* tile4 = reinterpret_cast<const float4*>(smem + Lv.EPI_OFFSET);
         int kb0, kb1;
         tile_kb_range(p, tc, kb0, kb1);
-        float* out_row = p.D + static_cast<long long>(tc.m_blk) * row_elems;
-        for (int o = ew * 32 + lane; o < row_elems; o += 128) {
-          const int w = o / p.dg_C, c = o - w * p.dg_C;
-          float sum = 0.f;
+        float* out_row = p.D + static_cast<long long>(tc.m_blk) * (p.dg_W * p.dg_C);
+        for (int w = ew * 32 + lane; w < p.dg_W; w += 128) {
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kb1 > kb0) {
-            for (int sx = (w + p.dg_pw) % p.dg_sw; sx < p.dg_S; sx += p.dg_sw) {
-              const int q = (w + p.dg_pw - sx) / p.dg_sw;
+            const int sx0 = (w + p.dg_pw) % p.dg_sw;
+            int q = (w + p.dg_pw - sx0) / p.dg_sw;
+            for (int sx = sx0; sx < p.dg_S; sx += p.dg_sw, --q) {
               if (q >= 0 && q < p.conv_Q) {
-                const int j = sx * 4 + c;
-                sum += tile_s[q * 32 + (((j >> 2) ^ (q & 7)) << 2) + (j & 3)];
+                const float4 v = tile4[q * 8 + (sx ^ (q & 7))];
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
               }
             }
           }
-          out_row[o] = p.beta != 0.f ? sum + p.beta * out_row[o] : sum;
+          float* o = out_row + w * p.dg_C;
+          const float vals4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < p.dg_C) o[c] = p.beta != 0.f ? vals4[c] + p.beta * o[c] : vals4[c];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
         acc ^= 1;
@@ -234,7 +247,34 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
               if (use_beta) {
                 o.x += e_beta * cur[it].x; o.y += e_beta * cur[it].y; o.z += e_beta * cur[it].z; o.w += e_beta * cur[it].w;
               }
+              vals[it] = o;
               *reinterpret_cast<float4*>(p.D + offs[it] + col) = o;
+            }
+          }
+          if (stats) {   // BatchNorm statistics of the values just stored (rows that exist only)
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.stat_shift + col));
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if (offs[it] < 0) continue;
+              const float dx = vals[it].x - sh.x, dy = vals[it].y - sh.y, dz = vals[it].z - sh.z, dw = vals[it].w - sh.w;
+              s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+              s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+              s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+              s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+              s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+            }
+            if (sub_row == 0) {
+              float4* a1 = reinterpret_cast<float4*>(stat_w + c * 32 + piece * 4);
+              float4* a2 = reinterpret_cast<float4*>(stat_w + BN + c * 32 + piece * 4);
+              float4 t1 = *a1, t2 = *a2;
+              t1.x += s1.x; t1.y += s1.y; t1.z += s1.z; t1.w += s1.w;
+              t2.x += s2.x; t2.y += s2.y; t2.z += s2.z; t2.w += s2.w;
+              *a1 = t1; *a2 = t2;
             }
           }
         } else {   // ragged chunk or unaligned output: element-wise (kept out of registers: rare path)
@@ -264,6 +304,18 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       if (acc == 0) acc_phase ^= 1;
       }
       if (dead) break;
+    }
+    if (stats) {   // one row of partials per epilogue warp: [row][2][N]
+      __syncwarp();
+      const int n_blk = blockIdx.x % p.n_tiles;
+      const long long row = static_cast<long long>(blockIdx.x / p.n_tiles) * 4 + ew;
+      for (int j = lane; j < BN; j += 32) {
+        const int col = n_blk * BN + j;
+        if (col < p.N) {
+          p.stat_partial[(row * 2 + 0) * p.N + col] = stat_w[j];
+          p.stat_partial[(row * 2 + 1) * p.N + col] = stat_w[BN + j];
+        }
+      }
     }
 }
 
@@ -486,7 +538,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.halo_slots * p.halo_slot_bytes;
   const int epi_off = p.halo_slots * p.halo_slot_bytes + p.halo_b_stages * B_BYTES;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096 + 4 * 2 * BN * 4);   // after the epilogue staging + statistics
   uint64_t* a_empty = a_full + 4;
   uint64_t* b_full = a_empty + 4;
   uint64_t* b_empty = b_full + kHaloMaxB;
@@ -710,6 +762,27 @@ static int make_map_im2col(zb_ctx* ctx, CUtensorMap* map, const float* base, lon
   return ZB_OK;
 }
 
+// Launches that accumulate BatchNorm statistics use a grid that is a multiple of n_tiles (see UmmaParams::stat_partial).
+static int stat_grid(zb_ctx* ctx, int tiles, int n_tiles) {
+  const int g = std::min(tiles, ctx->sm_count);
+  return std::max(n_tiles, g / n_tiles * n_tiles);
+}
+struct StatRequest {   // optional fused-BN-statistics request of a conv fprop
+  const float* shift = nullptr;
+  float* partial = nullptr;
+  int* rows = nullptr;   // out: rows of [2][K] partials written (0 = the planner could not fuse them)
+};
+static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int tiles, long long kout, const float* y, const float* bias) {
+  if (st == nullptr || st->partial == nullptr) return;
+  *st->rows = 0;
+  if (kout % 32 != 0 || p.chain_kb > 0 || p.splits > 1 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(bias) & 15) != 0 || (reinterpret_cast<uintptr_t>(st->shift) & 15) != 0 || p.n_tiles > ctx->sm_count)
+    return;
+  p.stat_partial = st->partial;
+  p.stat_shift = st->shift;
+  *st->rows = stat_grid(ctx, tiles, p.n_tiles) / p.n_tiles * 4;
+}
+
 template <int BN, int STAGES>
 static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   using L = UmmaSmem<BN, STAGES>;
@@ -719,7 +792,7 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
-  const int grid = std::min(tiles, ctx->sm_count);
+  const int grid = p.stat_partial ? stat_grid(ctx, tiles, p.n_tiles) : std::min(tiles, ctx->sm_count);
   // algorithmic FLOPs of this launch: 2 * M * N * K over all taps (K counted in 32-wide blocks as issued)
   prof_begin(ctx, PROF_TENSOR);
   umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
@@ -882,7 +955,7 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   hp->slot_bytes = (std::max(hp->raster_bytes, last_row * 128) + 1023) & ~1023;
   const int b_bytes = hp->bn * 128;
   const int chunks = static_cast<int>(Cin / 32);
-  const int budget = 227 * 1024 - 1024 - 16384 - 1024;  // alignment slack, epilogue staging, barriers
+  const int budget = 227 * 1024 - 1024 - 16384 - 32 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
   const int n_tiles = ceil_div(Kout, hp->bn);
   hp->resident = 0;
   if (n_tiles == 1 && R * S * chunks <= kHaloMaxB && R * S * chunks * b_bytes + 2 * hp->slot_bytes <= budget) {
@@ -896,7 +969,7 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
     hp->b_stages = std::min(kHaloMaxB, left / b_bytes);
     if (hp->b_stages < 3) return false;
   }
-  hp->smem = static_cast<size_t>(hp->slots) * hp->slot_bytes + static_cast<size_t>(hp->b_stages) * b_bytes + 16384 + 1024 + 1024;
+  hp->smem = static_cast<size_t>(hp->slots) * hp->slot_bytes + static_cast<size_t>(hp->b_stages) * b_bytes + 16384 + 32 * hp->bn + 1024 + 1024;
   return true;
 }
 
@@ -907,7 +980,7 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
     ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
-  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
+  const int grid = p.stat_partial ? stat_grid(ctx, p.m_tiles * p.n_tiles, p.n_tiles) : std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
   prof_begin(ctx, PROF_TENSOR);
   halo_conv_kernel<BN><<<grid, 192, smem, ctx->stream>>>(a, b, p);
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
@@ -918,7 +991,7 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
 // tap_r/tap_s: raster offset of tap t (filter row / column in the orientation of `filt`)
 static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long long H, long long W, long long Cin, long long Kout, int R,
                           int S, int ph, int pw, const float* in, const float* filt, const float* bias, float* out, float beta,
-                          double flops) {
+                          double flops, const StatRequest* st = nullptr) {
   const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
   CUtensorMap ma, mb;
   {
@@ -961,6 +1034,7 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   p.alpha = 1.f; p.beta = beta; p.bias = bias;
   finish_split_fields(p, 1);
   p.split_stride = 0;
+  stat_attach(ctx, p, st, p.m_tiles * p.n_tiles, Kout, out, bias);
   switch (hp.bn) {
     case 32: return halo_launch_bn<32>(ctx, ma, mb, p, hp.smem);
     case 64: return halo_launch_bn<64>(ctx, ma, mb, p, hp.smem);
@@ -980,7 +1054,10 @@ bool umma_conv_supported(const zb_conv2d_desc* d) {
 
 // y[N,P,Q,K] = conv(x[N,H,W,C], w[K,R,S,C]) (+bias)
 int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, const float* w, const float* bias,
-                         float* y, float beta) {
+                         float* y, float beta, const float* stat_shift, float* stat_partial, int* stat_rows) {
+  StatRequest st;
+  st.shift = stat_shift; st.partial = stat_partial; st.rows = stat_rows;
+  if (stat_rows) *stat_rows = 0;
   if (!umma_conv_supported(d)) { set_last_error("umma fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
@@ -992,7 +1069,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
     if (halo_plan(ctx, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw), static_cast<int>(d->pad_h),
                   static_cast<int>(d->pad_w), &hp))
       return umma_conv_halo(ctx, hp, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw),
-                            static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, beta, 2.0 * M * d->k * d->c * taps);
+                            static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, beta, 2.0 * M * d->k * d->c * taps, &st);
   }
   CUtensorMap ma, mb;
   UmmaParams p;
@@ -1036,6 +1113,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
   p.D = y;
   p.ldd = d->k;
   finish_split_fields(p, 1);
+  if (beta == 0.f) stat_attach(ctx, p, &st, p.m_tiles * p.n_tiles, d->k, y, bias);
   return run_with_splits(ctx, bn, ma, mb, p, M, d->k, y, d->k, 1.f, beta, bias);
 }
 
@@ -1377,7 +1455,10 @@ static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcG
 
 // y[N,P,Q,K] (NHWC) = conv(x, w[K,R,S,C]) (+bias); x is NHWC (x_nchw = 0) or NCHW (x_nchw = 1)
 int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
-                           float* y, float beta) {
+                           float* y, float beta, const float* stat_shift, float* stat_partial, int* stat_rows) {
+  StatRequest st;
+  st.shift = stat_shift; st.partial = stat_partial; st.rows = stat_rows;
+  if (stat_rows) *stat_rows = 0;
   if (!umma_conv_smallc_supported(d)) { set_last_error("umma small-C fprop: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
   const SmallcGeom g = smallc_geom(d);
   void* ws = nullptr;
@@ -1420,6 +1501,7 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
   p.D = y;
   p.ldd = d->k;
   finish_split_fields(p, 1);
+  if (beta == 0.f) stat_attach(ctx, p, &st, p.m_tiles * p.n_tiles, d->k, y, bias);
   return run_with_splits(ctx, bn, ma, mb, p, p.M, d->k, y, d->k, 1.f, beta, bias);
 }
 

@@ -68,6 +68,11 @@ struct UmmaParams {
   // of MMA steps; with chain_kb > 0 the accumulator is flushed through the epilogue (fp32 round-to-nearest adds into D) every
   // chain_kb K blocks (halo kernel: every halo_chain channel chunks) instead of once per tile.  0 = one chain per tile.
   int chain_kb, halo_chain;
+  // fused BatchNorm statistics (conv fprop followed by BN): per-column sum(y - shift) and sum((y - shift)^2) of the tile rows
+  // this CTA stores, accumulated per epilogue warp in shared memory over all its tiles (the grid is a multiple of n_tiles, so
+  // a CTA only ever sees one column block) and written once to stat_partial[(blockIdx.x / n_tiles) * 4 + warp][2][N]
+  float* stat_partial;
+  const float* stat_shift;
   int dbg_b_shift, dbg_b_lbo;  // experiments only (ZENU_B200_DBG_BSHIFT): MN-major B descriptor start shifted by 128-byte rows / overlapped N boxes
   int dbg_a_shift, dbg_base_mode, dbg_epi;  // experiments only (ZENU_B200_DBG_ASHIFT): A descriptor start shifted by whole 128-byte rows
   int* err_flag;              // device word set to 1 on an mbarrier timeout

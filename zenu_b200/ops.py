@@ -115,6 +115,33 @@ def conv_fwd(ctx, x, w, pad=0, stride=1, dil=1, bias=None, layout=ZB_NCHW, math=
     return y
 
 
+def conv_fwd_bnstats(ctx, x, w, shift, pad=0, stride=1, dil=1, bias=None, layout=ZB_NHWC, math=ZB_MATH_DEFAULT):
+    """conv_fwd that also returns the BatchNorm statistics partials of its output, accumulated in the conv epilogue:
+    (y, partial [rows][2][K], rows).  rows == 0: this shape / math mode cannot fuse them (y is complete either way)."""
+    _chk(x, "conv_fwd input"); _chk(w, "conv_fwd filter"); _chk(bias, "conv_fwd bias"); _chk(shift, "conv_fwd shift")
+    d = _desc(tuple(x.shape), tuple(w.shape), layout, pad, stride, dil)
+    y = torch.empty(conv_out_shape(tuple(x.shape), tuple(w.shape), layout, pad, stride, dil), dtype=x.dtype, device=x.device)
+    cap = ctx.lib.zb_conv2d_bnstats_rows(ctx.handle)
+    partial = torch.zeros((cap, 2, d.k), dtype=x.dtype, device=x.device)
+    rows = ctypes.c_int64(0)
+    check(ctx.lib.zb_conv2d_fprop_bnstats(ctx.handle, _DT[x.dtype], layout, math, ctypes.byref(d), _p(x), _p(w), _p(bias), _p(y),
+                                          _p(shift), _p(partial), ctypes.byref(rows)))
+    return y, partial, int(rows.value)
+
+
+def batch_norm_2d_forward_train_prestats(ctx, momentum, x, scale, bias, mean, variance, partial, rows, shift, layout=ZB_NHWC,
+                                         residual=None, relu=False):
+    """batch_norm_2d_forward_train whose statistics pass was done by conv_fwd_bnstats (x = that conv's output)."""
+    n, c, h, w = _nkhw(x.shape, layout)
+    y = torch.empty_like(x)
+    sm = torch.empty((c,), dtype=x.dtype, device=x.device)
+    si = torch.empty((c,), dtype=x.dtype, device=x.device)
+    check(ctx.lib.zb_bn2d_fwd_train_prestats(ctx.handle, _DT[x.dtype], layout, n, c, h, w, float(momentum), _p(x), _p(scale), _p(bias),
+                                             _p(mean), _p(variance), _p(sm), _p(si), _p(y), _p(residual), int(bool(relu)),
+                                             _p(partial), int(rows), _p(shift)))
+    return y, sm, si
+
+
 def conv_bkwd_data(ctx, dy, w, x_shape, pad=0, stride=1, dil=1, layout=ZB_NCHW, math=ZB_MATH_DEFAULT):
     _chk(dy, "conv_bkwd_data dy"); _chk(w, "conv_bkwd_data filter")
     d = _desc(tuple(x_shape), tuple(w.shape), layout, pad, stride, dil)
