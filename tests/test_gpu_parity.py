@@ -173,6 +173,9 @@ CONV_CASES = [
     (2, 64, 10, 10, 40, 3, 3, 0, 1, 1),    # halo kernels without padding, ragged k tile
     (2, 32, 8, 12, 64, 1, 3, 1, 1, 1),     # 1x3 filter
     (2, 32, 12, 8, 32, 3, 1, 0, 1, 1),     # 3x1 filter
+    (2, 3, 21, 19, 32, 5, 5, 2, 2, 1),     # small-C (stem) kernels: odd sizes, 5x5 s2
+    (1, 4, 30, 40, 64, 3, 3, 1, 1, 1),     # small-C, C = 4, stride 1, two k chunks
+    (2, 2, 17, 23, 32, 7, 7, 3, 3, 1),     # small-C, stride 3
 ]
 
 

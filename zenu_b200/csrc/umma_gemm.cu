@@ -35,8 +35,8 @@ struct UmmaSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;   // 4 warps x [32 rows][32 cols] fp32 staging (coalesced stores)
   static constexpr int EPI_BYTES = 4 * 4096;
-  static constexpr int STAT_OFFSET = EPI_OFFSET + EPI_BYTES;   // 4 warps x [2 stats][BN] fp32 (fused BatchNorm statistics)
-  static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
+  static constexpr int STAT_OFFSET = EPI_OFFSET + EPI_BYTES;   // 4 warps x [sum, sum of squares, shift][BN] fp32 (fused BatchNorm statistics)
+  static constexpr int STAT_BYTES = 4 * 3 * BN * 4;
   static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
@@ -91,10 +91,15 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const bool partial = p.splits > 1;
     const int sub_row = lane >> 3, piece = lane & 7;
-    float* stat_w = reinterpret_cast<float*>(smem + Lv.EPI_OFFSET + 4 * 4096) + ew * 2 * BN;   // this warp's [2][BN] statistics
+    float* stat_w = reinterpret_cast<float*>(smem + Lv.EPI_OFFSET + 4 * 4096) + ew * 3 * BN;   // this warp's [3][BN]: sum, sum sq, shift
     const bool stats = p.stat_partial != nullptr;
-    if (stats) {
-      for (int j = lane; j < 2 * BN; j += 32) stat_w[j] = 0.f;
+    if (stats) {   // the grid is a multiple of n_tiles: this CTA only ever sees column block blockIdx.x % n_tiles
+      const int nb0 = (blockIdx.x % p.n_tiles) * BN;
+      for (int j = lane; j < BN; j += 32) {
+        stat_w[j] = 0.f;
+        stat_w[BN + j] = 0.f;
+        stat_w[2 * BN + j] = nb0 + j < p.N ? __ldg(p.stat_shift + nb0 + j) : 0.f;
+      }
       __syncwarp();
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -252,7 +257,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             }
           }
           if (stats) {   // BatchNorm statistics of the values just stored (rows that exist only)
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.stat_shift + col));
+            const float4 sh = *reinterpret_cast<const float4*>(stat_w + 2 * BN + c * 32 + piece * 4);
             float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -538,7 +543,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.halo_slots * p.halo_slot_bytes;
   const int epi_off = p.halo_slots * p.halo_slot_bytes + p.halo_b_stages * B_BYTES;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096 + 4 * 2 * BN * 4);   // after the epilogue staging + statistics
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096 + 4 * 3 * BN * 4);   // after the epilogue staging + statistics
   uint64_t* a_empty = a_full + 4;
   uint64_t* b_full = a_empty + 4;
   uint64_t* b_empty = b_full + kHaloMaxB;
@@ -865,6 +870,7 @@ static thread_local int tl_chain_kb = 0;
 void umma_set_chain_limit(int kb) { tl_chain_kb = kb; }
 int umma_chain_limit() { return tl_chain_kb; }
 int umma_conv_wgrad_halo(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);  // umma_wgrad.cu
+int umma_conv_stem_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);  // umma_stem_dgrad.cu
 
 static void init_params(UmmaParams& p, zb_ctx* ctx) {
   memset(&p, 0, sizeof(p));
@@ -955,7 +961,7 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   hp->slot_bytes = (std::max(hp->raster_bytes, last_row * 128) + 1023) & ~1023;
   const int b_bytes = hp->bn * 128;
   const int chunks = static_cast<int>(Cin / 32);
-  const int budget = 227 * 1024 - 1024 - 16384 - 32 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
+  const int budget = 227 * 1024 - 1024 - 16384 - 48 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
   const int n_tiles = ceil_div(Kout, hp->bn);
   hp->resident = 0;
   if (n_tiles == 1 && R * S * chunks <= kHaloMaxB && R * S * chunks * b_bytes + 2 * hp->slot_bytes <= budget) {
@@ -969,7 +975,7 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
     hp->b_stages = std::min(kHaloMaxB, left / b_bytes);
     if (hp->b_stages < 3) return false;
   }
-  hp->smem = static_cast<size_t>(hp->slots) * hp->slot_bytes + static_cast<size_t>(hp->b_stages) * b_bytes + 16384 + 32 * hp->bn + 1024 + 1024;
+  hp->smem = static_cast<size_t>(hp->slots) * hp->slot_bytes + static_cast<size_t>(hp->b_stages) * b_bytes + 16384 + 48 * hp->bn + 1024 + 1024;
   return true;
 }
 
@@ -1593,6 +1599,10 @@ bool umma_conv_smallc_dgrad_supported(const zb_conv2d_desc* d) {
 // the filter columns.  dY is fetched ~R/stride_h times instead of R*S times (general parity-class path).
 int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
   if (!umma_conv_smallc_dgrad_supported(d)) { set_last_error("umma small-C dgrad: shape unsupported"); return ZB_ERR_UNSUPPORTED; }
+  {   // 8 input rows per tile, filter resident in smem (umma_stem_dgrad.cu); falls through to the row-per-tile kernel otherwise
+    const int rc0 = umma_conv_stem_dgrad(ctx, d, dy, w, dx, beta);
+    if (rc0 != ZB_ERR_UNSUPPORTED) return rc0;
+  }
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
   const int R = static_cast<int>(d->kh);
