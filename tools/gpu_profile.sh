@@ -1,0 +1,15 @@
+#!/bin/bash
+# ncu evidence for profiles/ (run under gpurun, 1 GPU): launch list with DRAM bytes of one ResNet-50 step, then --set full
+# captures of the tensor-core kernels and the BatchNorm kernels.  Usage: bash tools/gpu_profile.sh <tag>
+TAG=${1:-r1}
+mkdir -p gpurun_out
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    --profile-from-start off --replay-mode application --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python tools/ncu_step.py > gpurun_out/ncu_launches_${TAG}.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'umma_kernel|halo_conv_kernel|wgrad_halo_kernel|stem_dgrad_kernel' -c 12 -f -o gpurun_out/prof_umma_${TAG} \
+    python tools/ncu_step.py > gpurun_out/ncu_full_umma_${TAG}.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'bn_|col_reduce' -c 8 -f -o gpurun_out/prof_bn_${TAG} \
+    python tools/ncu_step.py > gpurun_out/ncu_full_bn_${TAG}.log 2>&1
+ls -la gpurun_out | tail -12

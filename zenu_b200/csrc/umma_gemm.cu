@@ -28,7 +28,8 @@ namespace zb {
 
 using namespace ptx;
 
-template <int BN, int STAGES>
+constexpr int kOldDepth = 3;   // 32-column chunks of the old output tile in flight per epilogue warp (beta != 0 launches)
+template <int BN, int STAGES, bool OLD = false>
 struct UmmaSmem {
   static constexpr int A_BYTES = kUmmaBM * kUmmaBK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * kUmmaBK * 4;
@@ -37,7 +38,9 @@ struct UmmaSmem {
   static constexpr int EPI_BYTES = 4 * 4096;
   static constexpr int STAT_OFFSET = EPI_OFFSET + EPI_BYTES;   // 4 warps x [sum, sum of squares, shift][BN] fp32 (fused BatchNorm statistics)
   static constexpr int STAT_BYTES = 4 * 3 * BN * 4;
-  static constexpr int BAR_OFFSET = STAT_OFFSET + STAT_BYTES;
+  static constexpr int OLD_OFFSET = STAT_OFFSET + STAT_BYTES;   // beta launches: 4 warps x kOldDepth x 4 KB cp.async landing buffers
+  static constexpr int OLD_BYTES = OLD ? 4 * kOldDepth * 4096 : 0;
+  static constexpr int BAR_OFFSET = OLD_OFFSET + OLD_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -74,7 +77,7 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
-                                              bool halo = false) {
+                                              bool halo = false, uint8_t* old_smem = nullptr) {
   const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
   struct LL { int EPI_OFFSET; } Lv{epi_offset};
     // ================================ epilogue ================================
@@ -201,7 +204,25 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       // before the accumulator is even complete, so the read latency hides behind the MMAs / the previous chunk's stores
       float4 olds[8];
       const bool prefetch = use_beta && vec_ok;
-      if (prefetch && n0 + 32 <= p.N) {
+      // deep variant (old_smem != nullptr): kOldDepth chunks in flight per warp through cp.async into warp-private smem slots
+      // (slot = [chunk % depth][row group it][lane], 16 bytes each); one register chunk ahead is not enough memory-level
+      // parallelism for the K = 64..256 gradient fan-in GEMMs, whose time is the read-modify-write of the output
+      const bool deep = prefetch && old_smem != nullptr;
+      const uint32_t old_u32 = deep ? smem_u32(old_smem) + ew * (kOldDepth * 4096) + lane * 16 : 0u;
+      auto issue_old = [&](int c) {
+        if (n0 + c * 32 + 32 <= p.N && c < BN / 32) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (offs[it] >= 0)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(old_u32 + ((c % kOldDepth) * 8 + it) * 512),
+                           "l"(p.D + offs[it] + n0 + c * 32 + piece * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (deep) {
+#pragma unroll
+        for (int c = 0; c < kOldDepth; ++c) issue_old(c);
+      } else if (prefetch && n0 + 32 <= p.N) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + n0 + piece * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -237,12 +258,20 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
             float4 cur[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) cur[it] = olds[it];
-            if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
+            if (deep) {
+              asm volatile("cp.async.wait_group %0;" ::"n"(kOldDepth - 1) : "memory");
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cur[it] = offs[it] >= 0 ? lds128(old_u32 + ((c % kOldDepth) * 8 + it) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+              issue_old(c + kOldDepth);   // refills the slot just read
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) cur[it] = olds[it];
+              if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -324,11 +353,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool OLD = false>
 __global__ void __launch_bounds__(192, 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ UmmaParams p) {
-  using L = UmmaSmem<BN, STAGES>;
+  using L = UmmaSmem<BN, STAGES, OLD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -511,7 +540,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err);
+    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, OLD ? smem + L::OLD_OFFSET : nullptr);
   }
 
   tc_fence_before();
@@ -788,19 +817,20 @@ static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int t
   *st->rows = stat_grid(ctx, tiles, p.n_tiles) / p.n_tiles * 4;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool OLD = false>
 static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
-  using L = UmmaSmem<BN, STAGES>;
+  using L = UmmaSmem<BN, STAGES, OLD>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
   const int grid = p.stat_partial ? stat_grid(ctx, tiles, p.n_tiles) : std::min(tiles, ctx->sm_count);
   // algorithmic FLOPs of this launch: 2 * M * N * K over all taps (K counted in 32-wide blocks as issued)
   prof_begin(ctx, PROF_TENSOR);
-  umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
+  umma_kernel<BN, STAGES, OLD><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
@@ -809,6 +839,16 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
 static int pick_bn(long long n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
 
 static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
+  // launches whose epilogue reads the old output tile (beta != 0, chained 3xTF32 flushes): a shallower operand ring makes
+  // room for the deep old-tile prefetch buffers (these are short-K, output-bound problems)
+  if ((p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && getenv("ZENU_B200_NO_DEEP_BETA") == nullptr) {
+    switch (bn) {
+      case 32: return launch_cfg<32, 7, true>(ctx, a, b, p);
+      case 64: return launch_cfg<64, 6, true>(ctx, a, b, p);
+      case 128: return launch_cfg<128, 4, true>(ctx, a, b, p);
+      default: return launch_cfg<256, 3, true>(ctx, a, b, p);
+    }
+  }
   switch (bn) {
     case 32: return launch_cfg<32, 10>(ctx, a, b, p);
     case 64: return launch_cfg<64, 8>(ctx, a, b, p);

@@ -96,7 +96,8 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(kUmmaBM, 32, 0, 0);
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      const uint32_t a0 = smem_u32(sA);
+      const uint64_t db_first = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(b_bar, 0, err);
@@ -111,18 +112,24 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int c = 0; c < p.chunks; ++c) {
             if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t a_base = a0 + stage * 16384;
-            for (int hl = 0; hl <= h1 - h0; ++hl) {
-              const int t = h0 + hl + p.ph - pr * p.sh;   // = r * dil_h for the filter row that links input row h to dY row pr
-              if (t < 0 || t % p.dh != 0) continue;
-              const int r = t / p.dh;
-              if (r >= p.R) continue;
-              const uint32_t b_base = b0 + (r * p.chunks + c) * 4096;
+            // (the issuing thread is the critical path here: N = 32 MMAs retire faster than scalar code can describe them, so
+            // descriptors are advanced by adding to their 14-bit address field and the dil_h == 1 case avoids the divisions)
+            const uint64_t da0 = make_smem_desc(a0 + stage * 16384, 16, 1024, kSmemLayoutSw128);
+            int t = h0 + p.ph - pr * p.sh;   // = r * dil_h for the filter row that links input row h0 + hl to dY row pr
+            for (int hl = 0; hl <= h1 - h0; ++hl, ++t) {
+              int r = t;
+              if (p.dh != 1) {
+                if (t < 0 || t % p.dh != 0) continue;
+                r = t / p.dh;
+              }
+              if (r < 0 || r >= p.R) continue;
+              const uint64_t db0 = db_first + static_cast<uint64_t>((r * p.chunks + c) * 256);   // 4096-byte tiles, >> 4
               const uint32_t d_tmem = tmem_base + (acc * kSdTH + hl) * 32;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_tf32(d_tmem, make_smem_desc(a_base + k * 32, 16, 1024, kSmemLayoutSw128),
-                          make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128), idesc, ((started >> hl) & 1u) | (k > 0 ? 1u : 0u));
+              const uint32_t st = (started >> hl) & 1u;
+              umma_tf32(d_tmem, da0, db0, idesc, st);
+              umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+              umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+              umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
               started |= 1u << hl;
             }
             umma_commit(&empty_bar[stage]);
@@ -140,6 +147,14 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ew = warp & 3;
     int acc = 0, rowbuf = 0;
     uint32_t acc_phase = 0;
+    // the filter columns reaching pixel w do not depend on the row: first column / its q for this thread's (up to) two pixels
+    int w_sx0[2], w_q0[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int w = ew * 32 + lane + i * 128;
+      w_sx0[i] = (w + p.pw) % p.sw;
+      w_q0[i] = (w + p.pw - w_sx0[i]) / p.sw;
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.h_blocks, hb = tile - img * p.h_blocks;
       const int h0 = hb * kSdTH, h1 = min(h0 + kSdTH, p.H) - 1;
@@ -161,11 +176,13 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (hl == h1 - h0 && lane == 0) mbar_arrive(&tempty_bar[acc]);
         float* out_row = p.dx + (static_cast<long long>(img) * p.H + h0 + hl) * (static_cast<long long>(p.W) * p.C);
-        for (int w = ew * 32 + lane; w < p.W; w += 128) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int w = ew * 32 + lane + i * 128;
+          if (w >= p.W) break;
           float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int sx0 = (w + p.pw) % p.sw;
-          int q = (w + p.pw - sx0) / p.sw;
-          for (int sx = sx0; sx < p.S; sx += p.sw, --q) {
+          int q = w_q0[i];
+          for (int sx = w_sx0[i]; sx < p.S; sx += p.sw, --q) {
             if (q >= 0 && q < p.Q) {
               const float4 t = stage4[q * 8 + (sx ^ (q & 7))];
               sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
@@ -215,7 +232,7 @@ int umma_conv_stem_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     return ZB_ERR_UNSUPPORTED;
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   const long long Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
-  if (Q > kUmmaBM || P <= 0 || Q <= 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return ZB_ERR_UNSUPPORTED;
+  if (Q > kUmmaBM || d->w > 256 || P <= 0 || Q <= 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return ZB_ERR_UNSUPPORTED;
   // every input row must be reached by at least one filter row (otherwise its accumulator would never be written)
   for (int a = 0; a < d->stride_h; ++a) {
     int cnt = 0;
