@@ -49,6 +49,7 @@ struct UmmaSmem {
 struct TileCoord {
   int m_blk, n_blk, tap, split;
 };
+template <bool V> struct FullTag { static constexpr bool value = V; };
 __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
   TileCoord t;
   t.n_blk = tile % p.n_tiles;
@@ -188,10 +189,27 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      // rows this lane stores after the transpose (8 per chunk, the same 8 for every chunk of the tile)
-      long long offs[8];
+      // rows this lane stores after the transpose (8 per chunk, the same 8 for every chunk of the tile), as 32-bit element
+      // offsets from the warp's first existing row (-1: the row does not exist: ragged last tile, halo positions).  The
+      // epilogue warps are instruction-bound on the output-dominated layers (ncu: ~0.28 IPC per scheduler, no single hot
+      // stall), so the per-chunk code is kept lean: one 64-bit base, IMAD.WIDE addressing, and a branch-free variant for
+      // tiles whose 32 rows all exist.
+      const unsigned valid_mask = __ballot_sync(0xffffffffu, my_off >= 0);
+      long long base_off = 0;
+      int rel = -1;
+      bool tile_vec = vec_ok;
+      if (valid_mask != 0u) {
+        base_off = __shfl_sync(0xffffffffu, my_off, __ffs(valid_mask) - 1);
+        const long long dlt = my_off - base_off;
+        if (__any_sync(0xffffffffu, my_off >= 0 && (dlt < 0 || dlt > 0x3fffffffll))) tile_vec = false;
+        rel = my_off >= 0 ? static_cast<int>(dlt) : -1;
+      }
+      int off32[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + sub_row);
+      for (int it = 0; it < 8; ++it) off32[it] = __shfl_sync(0xffffffffu, rel, it * 4 + sub_row);
+      const bool full = valid_mask == 0xffffffffu;
+      float* const wb = p.D + base_off + n0 + piece * 4;   // element (row it, chunk c) = wb[off32[it] + c * 32 ..+3]
+      const uint32_t stat_u32 = smem_u32(stat_w) + piece * 16;
       bool dead = false;
 #pragma unroll 1
       for (int sub = 0; sub < n_sub; ++sub) {
@@ -200,22 +218,22 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       const float* e_bias = (sub == 0 && !partial) ? p.bias : nullptr;
       const bool use_beta = e_beta != 0.f;
       const bool plain = e_alpha == 1.f && e_bias == nullptr && !use_beta;   // store the accumulator as is
-      // beta != 0 (gradient fan-in, 3xTF32 passes): the old tile is fetched one 32-column chunk ahead, the first chunk
-      // before the accumulator is even complete, so the read latency hides behind the MMAs / the previous chunk's stores
-      float4 olds[8];
-      const bool prefetch = use_beta && vec_ok;
+      // beta != 0 (gradient fan-in, 3xTF32 passes): the old tile is fetched ahead of use, the first chunk(s) before the
+      // accumulator is even complete, so the read latency hides behind the MMAs / the previous chunk's stores.
       // deep variant (old_smem != nullptr): kOldDepth chunks in flight per warp through cp.async into warp-private smem slots
       // (slot = [chunk % depth][row group it][lane], 16 bytes each); one register chunk ahead is not enough memory-level
       // parallelism for the K = 64..256 gradient fan-in GEMMs, whose time is the read-modify-write of the output
+      float4 olds[8];
+      const bool prefetch = use_beta && tile_vec;
       const bool deep = prefetch && old_smem != nullptr;
       const uint32_t old_u32 = deep ? smem_u32(old_smem) + ew * (kOldDepth * 4096) + lane * 16 : 0u;
       auto issue_old = [&](int c) {
         if (n0 + c * 32 + 32 <= p.N && c < BN / 32) {
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            if (offs[it] >= 0)
+            if (off32[it] >= 0)
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(old_u32 + ((c % kOldDepth) * 8 + it) * 512),
-                           "l"(p.D + offs[it] + n0 + c * 32 + piece * 4) : "memory");
+                           "l"(wb + (off32[it] + c * 32)) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
@@ -225,112 +243,116 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       } else if (prefetch && n0 + 32 <= p.N) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
-          olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + n0 + piece * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          olds[it] = off32[it] >= 0 ? *reinterpret_cast<const float4*>(wb + off32[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) { dead = true; break; }
       tc_fence_after();
+      // FULL: every row of this warp exists (no per-row predicates)
+      auto chunk_loop = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        if (p.dbg_epi == 2) continue;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
+          if (p.dbg_epi == 2) continue;
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          sts128(stage_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), __uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
-                 __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
-        __syncwarp();
-        const int col = col0 + piece * 4;
-        float4 vals[8];
+          for (int v = 0; v < 8; ++v)
+            sts128(stage_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), __uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
+                   __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+          __syncwarp();
+          const int col = col0 + piece * 4;
+          if (tile_vec && col0 + 32 <= p.N) {   // warp-uniform fast path: whole 32-column chunk, 128-bit stores
+            float4 vals[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub_row;
-          vals[it] = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
-        }
-        if (vec_ok && col0 + 32 <= p.N) {   // warp-uniform fast path: whole 32-column chunk, 128-bit stores
-          if (plain) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (offs[it] >= 0 && p.dbg_epi != 1) *reinterpret_cast<float4*>(p.D + offs[it] + col) = vals[it];
-          } else {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
-            float4 cur[8];
-            if (deep) {
-              asm volatile("cp.async.wait_group %0;" ::"n"(kOldDepth - 1) : "memory");
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sub_row;
+              vals[it] = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
+            }
+            const int coff = c * 32;
+            if (plain) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                cur[it] = offs[it] >= 0 ? lds128(old_u32 + ((c % kOldDepth) * 8 + it) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
-              issue_old(c + kOldDepth);   // refills the slot just read
+                if ((FULL || off32[it] >= 0) && p.dbg_epi != 1) *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = vals[it];
             } else {
-#pragma unroll
-              for (int it = 0; it < 8; ++it) cur[it] = olds[it];
-              if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
+              float4 cur[8];
+              if (deep) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kOldDepth - 1) : "memory");
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
-                  olds[it] = offs[it] >= 0 ? *reinterpret_cast<const float4*>(p.D + offs[it] + col + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  cur[it] = (FULL || off32[it] >= 0) ? lds128(old_u32 + ((c % kOldDepth) * 8 + it) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+                issue_old(c + kOldDepth);   // refills the slot just read
+              } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) cur[it] = olds[it];
+                if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
+#pragma unroll
+                  for (int it = 0; it < 8; ++it)
+                    olds[it] = (FULL || off32[it] >= 0) ? *reinterpret_cast<const float4*>(wb + (off32[it] + coff + 32))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                if (!FULL && off32[it] < 0) continue;
+                float4 o = vals[it];
+                o.x = e_alpha * o.x + bv.x; o.y = e_alpha * o.y + bv.y; o.z = e_alpha * o.z + bv.z; o.w = e_alpha * o.w + bv.w;
+                if (use_beta) {
+                  o.x += e_beta * cur[it].x; o.y += e_beta * cur[it].y; o.z += e_beta * cur[it].z; o.w += e_beta * cur[it].w;
+                }
+                vals[it] = o;
+                *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = o;
               }
             }
+            if (stats) {   // BatchNorm statistics of the values just stored (rows that exist only)
+              const float4 sh = lds128(stat_u32 + (2 * BN + coff) * 4);
+              float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              if (offs[it] < 0) continue;
-              float4 o = vals[it];
-              o.x = e_alpha * o.x + bv.x; o.y = e_alpha * o.y + bv.y; o.z = e_alpha * o.z + bv.z; o.w = e_alpha * o.w + bv.w;
-              if (use_beta) {
-                o.x += e_beta * cur[it].x; o.y += e_beta * cur[it].y; o.z += e_beta * cur[it].z; o.w += e_beta * cur[it].w;
+              for (int it = 0; it < 8; ++it) {
+                if (!FULL && off32[it] < 0) continue;
+                const float dx = vals[it].x - sh.x, dy = vals[it].y - sh.y, dz = vals[it].z - sh.z, dw = vals[it].w - sh.w;
+                s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+                s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
               }
-              vals[it] = o;
-              *reinterpret_cast<float4*>(p.D + offs[it] + col) = o;
-            }
-          }
-          if (stats) {   // BatchNorm statistics of the values just stored (rows that exist only)
-            const float4 sh = *reinterpret_cast<const float4*>(stat_w + 2 * BN + c * 32 + piece * 4);
-            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              if (offs[it] < 0) continue;
-              const float dx = vals[it].x - sh.x, dy = vals[it].y - sh.y, dz = vals[it].z - sh.z, dw = vals[it].w - sh.w;
-              s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
-              s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+              for (int o = 8; o <= 16; o <<= 1) {
+                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+              }
+              if (sub_row == 0) {
+                const float4 t1 = lds128(stat_u32 + coff * 4), t2 = lds128(stat_u32 + (BN + coff) * 4);
+                sts128(stat_u32 + coff * 4, t1.x + s1.x, t1.y + s1.y, t1.z + s1.z, t1.w + s1.w);
+                sts128(stat_u32 + (BN + coff) * 4, t2.x + s2.x, t2.y + s2.y, t2.z + s2.z, t2.w + s2.w);
+              }
             }
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-              s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-              s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-              s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
-            }
-            if (sub_row == 0) {
-              float4* a1 = reinterpret_cast<float4*>(stat_w + c * 32 + piece * 4);
-              float4* a2 = reinterpret_cast<float4*>(stat_w + BN + c * 32 + piece * 4);
-              float4 t1 = *a1, t2 = *a2;
-              t1.x += s1.x; t1.y += s1.y; t1.z += s1.z; t1.w += s1.w;
-              t2.x += s2.x; t2.y += s2.y; t2.z += s2.z; t2.w += s2.w;
-              *a1 = t1; *a2 = t2;
-            }
-          }
-        } else {   // ragged chunk or unaligned output: element-wise (kept out of registers: rare path)
+          } else {   // ragged chunk or unaligned output: element-wise (kept out of registers: rare path)
 #pragma unroll 1
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + sub_row;
-            const long long off = __shfl_sync(0xffffffffu, my_off, rr);
-            const float4 v4 = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
-            if (off < 0) continue;
-            float* dst = p.D + off + col;
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sub_row;
+              const long long off = __shfl_sync(0xffffffffu, my_off, rr);
+              const float4 v4 = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
+              if (off < 0) continue;
+              float* dst = p.D + off + col;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (col + e < p.N) {
-                float val = e == 0 ? v4.x : (e == 1 ? v4.y : (e == 2 ? v4.z : v4.w));
-                val = e_alpha * val + (e_bias != nullptr ? __ldg(e_bias + col + e) : 0.f);
-                if (use_beta) val += e_beta * dst[e];
-                dst[e] = val;
-              }
+              for (int e = 0; e < 4; ++e)
+                if (col + e < p.N) {
+                  float val = e == 0 ? v4.x : (e == 1 ? v4.y : (e == 2 ? v4.z : v4.w));
+                  val = e_alpha * val + (e_bias != nullptr ? __ldg(e_bias + col + e) : 0.f);
+                  if (use_beta) val += e_beta * dst[e];
+                  dst[e] = val;
+                }
+            }
           }
+          __syncwarp();  // staging is rewritten by the next chunk
         }
-        __syncwarp();  // staging is rewritten by the next chunk
-      }
+      };
+      if (full) chunk_loop(FullTag<true>{}); else chunk_loop(FullTag<false>{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
