@@ -45,9 +45,12 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+TENSOR_KERNELS = ("umma_kernel", "halo_conv_kernel", "wgrad_halo_kernel", "stem_dgrad_kernel")   # every PROF_TENSOR launch
+
+
 def ncu_traffic(kernel_prefix):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of one step) of the kernels whose
-    name starts with kernel_prefix, from the committed ncu summary of the same workload (profiles/*_traffic.json)."""
+    name starts with one of kernel_prefix, from the committed ncu summary of the same workload (profiles/*_traffic.json)."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
     if not files:
@@ -57,7 +60,7 @@ def ncu_traffic(kernel_prefix):
             t = json.load(f)
         n = b = 0.0
         for name, k in t["kernels"].items():
-            if name.startswith(kernel_prefix) and k.get("dram_bytes_per_launch", 0) > 0:
+            if name.startswith(tuple(kernel_prefix) if not isinstance(kernel_prefix, str) else kernel_prefix) and k.get("dram_bytes_per_launch", 0) > 0:
                 n += k["launches"]
                 b += k["dram_bytes_per_launch"] * k["launches"]
         return (b / n if n else None), os.path.basename(files[-1])
@@ -305,8 +308,9 @@ def run_ours(args, rank, world, local_rank):
     tensor_tflops = (t_flops / (t_ms * 1e-3)) / 1e12 if t_ms > 0 else 0.0
     bn_gbs = (b_bytes / (b_ms * 1e-3)) / 1e9 if b_ms > 0 else 0.0
     if tensor_share >= bn_share:
-        traffic, traffic_src = ncu_traffic("umma_kernel")
-        roofline = {"kernel": "zb::umma_kernel (tcgen05 kind::tf32 implicit-GEMM conv/GEMM)", "bound": "tensor", "achieved": tensor_tflops,
+        traffic, traffic_src = ncu_traffic(TENSOR_KERNELS)
+        roofline = {"kernel": "tcgen05 kind::tf32 conv/GEMM kernels (zb::umma_kernel, halo_conv_kernel, wgrad_halo_kernel, stem_dgrad_kernel)",
+                    "bound": "tensor", "achieved": tensor_tflops,
                     "peak": tf32_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tf32_peak if tf32_peak else None, "traffic": traffic,
                     "traffic_source": f"profiles/{traffic_src}: ncu dram bytes per launch, averaged over the step's launches" if traffic else None,
                     "algorithmic_bytes_per_launch_avg": node_summary["conv"]["bytes_per_step"] / max(t_ops / args.steps, 1) if node_summary else None,
