@@ -131,6 +131,18 @@ int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, in
                                double momentum, const void* x, const void* scale, const void* bias, void* running_mean,
                                void* running_var, void* saved_mean, void* saved_inv_std, void* y, const void* residual,
                                int relu, const void* stat_partial, int64_t stat_rows, const void* shift);
+/* Superset of the two forwards above (NHWC f32): stat_partial may be NULL (statistics computed here), relu_mask may be NULL.
+ * relu_mask (relu != 0, c % 32 == 0): zb_bn2d_relu_mask_words(n,c,h,w) 32-bit words, bit i = (output element i > 0) in NHWC
+ * order.  zb_bn2d_bwd_mask then takes the ReLU mask from it instead of re-reading the forward output: the fused
+ * BN+add+ReLU backward moves 6 tensor passes instead of 7 (dres is required: it receives the masked gradient). */
+int64_t zb_bn2d_relu_mask_words(int64_t n, int64_t c, int64_t h, int64_t w);
+int zb_bn2d_fwd_train_fused(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w,
+                            double momentum, const void* x, const void* scale, const void* bias, void* running_mean,
+                            void* running_var, void* saved_mean, void* saved_inv_std, void* y, const void* residual,
+                            int relu, const void* stat_partial, int64_t stat_rows, const void* shift, void* relu_mask);
+int zb_bn2d_bwd_mask(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
+                     const void* dy, const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx,
+                     void* dscale, void* dbias, const void* relu_mask, void* dres);
 int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                       const void* scale, const void* bias, const void* mean, const void* var, void* y);
 /* dy is the gradient w.r.t. the (possibly fused) output.  When the forward fused relu, pass the forward

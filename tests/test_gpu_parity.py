@@ -466,6 +466,41 @@ def test_bn_fused_relu_residual(zb, ctx, layout):
     assert rel_err(host(ds), ds_ref) < 2e-4 and rel_err(host(db), db_ref) < 2e-4
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 9, 7), (3, 32, 5, 5), (2, 256, 6, 6)])
+def test_bn_add_relu_bit_mask(zb, ctx, shape):
+    """Fused BN+add+ReLU whose forward writes a 1-bit ReLU mask and whose backward reads it instead of y: identical results to the
+    y-based fused path (bit-exact) and equal to the reference's separate batch_norm -> add -> relu nodes (oracle)."""
+    rng = np.random.default_rng(sum(shape))
+    n, c, h, w = shape
+    x = rng.standard_normal(shape).astype(np.float32)
+    res = rng.standard_normal(shape).astype(np.float32)
+    dy = rng.standard_normal(shape).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    bias = (0.2 * rng.standard_normal(c)).astype(np.float32)
+    from zenu_b200 import ZB_NHWC
+    X, R, DY = dev(nhwc(x)), dev(nhwc(res)), dev(nhwc(dy))
+    rm, rv = dev(np.zeros(c, np.float32)), dev(np.ones(c, np.float32))
+    y, sm, si, mask = zb.batch_norm_2d_forward_train_masked(ctx, 0.9, X, dev(scale), dev(bias), rm, rv, residual=R)
+    rm2, rv2 = dev(np.zeros(c, np.float32)), dev(np.ones(c, np.float32))
+    y2, sm2, si2 = zb.batch_norm_2d_forward_train(ctx, 0.9, X, dev(scale), dev(bias), rm2, rv2, layout=ZB_NHWC, residual=R, relu=True)
+    np.testing.assert_array_equal(host(y), host(y2))
+    bits = np.unpackbits(host(mask).view(np.uint8), bitorder="little")[: x.size]
+    np.testing.assert_array_equal(bits.astype(bool), (host(y).ravel() > 0))
+    dx, ds, db, dres = zb.batch_norm_2d_backward_masked(ctx, X, DY, dev(scale), sm, si, mask)
+    dx2, ds2, db2, dres2 = zb.batch_norm_2d_backward(ctx, X, DY, dev(scale), sm2, si2, layout=ZB_NHWC, y=y2, want_residual_grad=True)
+    for a, b in ((dx, dx2), (ds, ds2), (db, db2), (dres, dres2)):
+        np.testing.assert_array_equal(host(a), host(b))
+    # oracle: separate nodes
+    bn_ref, _, _, sm_ref, si_ref = zo.bn2d_fwd_train(x, scale, bias, np.zeros(c, np.float32), np.ones(c, np.float32), 0.9)
+    out_ref = zo.relu(zo.ewise("add", bn_ref, res))
+    assert rel_err(nchw(host(y)), out_ref) < 1e-5
+    g = zo.ewise("mul", dy, (out_ref > 0).astype(np.float32))
+    dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x, g, scale, sm_ref, si_ref)
+    assert rel_err(nchw(host(dx)), dx_ref) < 1e-4 and rel_err(host(ds), ds_ref) < 1e-4 and rel_err(host(db), db_ref) < 1e-4
+    assert rel_err(nchw(host(dres)), g) < 1e-6
+    ctx.check()
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
 def test_bn_relu_backward_recomputed_mask(zb, ctx, layout, dtype):

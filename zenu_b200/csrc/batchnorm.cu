@@ -112,6 +112,7 @@ template <typename T, int VN, int MASK>
 struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
   static constexpr int NS = 2, NIN = (MASK == 1 || MASK == 3) ? 3 : 2;
   T* gm_out;
+  const uint32_t* bits;   // MASK == 4: as 3, with the ReLU mask read from the 1-bit-per-element array the forward wrote
   const T* mean;
   const T* inv;
   const T* gamma;
@@ -126,17 +127,20 @@ struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
   }
   __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN], long long off) const {
     T gv[VN];
+    unsigned nib = 0u;
+    if (MASK == 4) nib = __ldg(bits + (off >> 5)) >> (off & 31);   // VN consecutive bits (VN divides 32, off % VN == 0)
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       bool keep = true;
       if (MASK == 1 || MASK == 3) keep = y[e] > T(0);
       if (MASK == 2) keep = bn_affine(x[e], m[e], iv[e], gm[e], bt[e]) > T(0);
+      if (MASK == 4) keep = ((nib >> e) & 1u) != 0u;
       const T g = keep ? dy[e] : T(0);
       gv[e] = g;
       acc[0][e] += g;
       acc[1][e] += g * ((x[e] - m[e]) * iv[e]);
     }
-    if (MASK == 3) stv<T, VN>(gm_out + off, gv);
+    if (MASK == 3 || MASK == 4) stv<T, VN>(gm_out + off, gv);
   }
 };
 
@@ -349,12 +353,24 @@ sum_finalize(const T* __restrict__ partial, int slabs, long long C, T* __restric
 
 // ---- apply kernels ------------------------------------------------------------------------------------
 // forward: y = ((x - mean) * inv) * gamma + beta  [+ res] [relu]
+// ReLU mask, 1 bit per element (bit index = NHWC element index): each thread owns 4 consecutive bits, the 8 lanes that share
+// a 32-bit word (consecutive tx, same row) OR their nibbles together and one of them stores the word.  Needs C % 32 == 0.
+__device__ __forceinline__ void store_mask_nibble(uint32_t* __restrict__ mask, long long off, unsigned nib) {
+  const int l7 = threadIdx.x & 7;
+  unsigned w = nib << (l7 * 4);
+  const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
+  w |= __shfl_xor_sync(grp, w, 1);
+  w |= __shfl_xor_sync(grp, w, 2);
+  w |= __shfl_xor_sync(grp, w, 4);
+  if (l7 == 0) mask[off >> 5] = w;
+}
+
 template <typename T, int VN, bool RELU, bool RES>
 __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ res,
                                                      T* __restrict__ y, const T* __restrict__ coef,
                                                      const T* __restrict__ gamma, const T* __restrict__ beta,
                                                      long long rows, long long C, long long rows_per_slab, int tx_n,
-                                                     int ty_n) {
+                                                     int ty_n, uint32_t* __restrict__ mask = nullptr) {
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
   if (c0 >= C) return;
@@ -376,14 +392,16 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       T o[VN];
+      unsigned nib = 0u;
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         T v = bn_affine(a[u][e], m[e], iv[e], g[e], b[e]);
         if (RES) v += rr[u][e];
-        if (RELU) v = v > T(0) ? v : T(0);
+        if (RELU) { nib |= (v > T(0) ? 1u : 0u) << e; v = v > T(0) ? v : T(0); }
         o[e] = v;
       }
       stv<T, VN>(y + (r + u * ty_n) * C + c0, o);
+      if (RELU && VN == 4 && mask != nullptr) store_mask_nibble(mask, (r + u * ty_n) * C + c0, nib);
     }
   }
   for (; r < r1; r += ty_n) {
@@ -391,14 +409,16 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
     const long long off = r * C + c0;
     ldv<T, VN>(x + off, a);
     if (RES) ldv<T, VN>(res + off, rr);
+    unsigned nib = 0u;
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       T v = bn_affine(a[e], m[e], iv[e], g[e], b[e]);
       if (RES) v += rr[e];
-      if (RELU) v = v > T(0) ? v : T(0);
+      if (RELU) { nib |= (v > T(0) ? 1u : 0u) << e; v = v > T(0) ? v : T(0); }
       o[e] = v;
     }
     stv<T, VN>(y + off, o);
+    if (RELU && VN == 4 && mask != nullptr) store_mask_nibble(mask, off, nib);
   }
 }
 
@@ -562,6 +582,7 @@ template <typename T, int VN> using BnBwdMaskFT = BnBwdF<T, VN, 1>;
 template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, 0>;
 template <typename T, int VN> using BnBwdRecomputeFT = BnBwdF<T, VN, 2>;
 template <typename T, int VN> using BnBwdMaskStoreFT = BnBwdF<T, VN, 3>;
+template <typename T, int VN> using BnBwdBitsStoreFT = BnBwdF<T, VN, 4>;
 
 // Upper bound on the slab count run_col_reduce may pick (sizes the partial buffer).
 static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
@@ -571,7 +592,7 @@ static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
 
 template <typename T, bool RELU, bool RES>
 static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
-                        const T* coef, const T* gamma, const T* beta) {
+                        const T* coef, const T* gamma, const T* beta, uint32_t* mask = nullptr) {
   const long long rows = N * HW;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
@@ -579,13 +600,16 @@ static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long 
     if (vec) {
       ColGeom g = col_geom(ctx, rows, C, VN);
       dim3 grid(g.col_groups, g.slabs);
-      bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+      ZB_REQUIRE(mask == nullptr || (sizeof(T) == 4 && RELU && C % 32 == 0), "bn: ReLU bit mask needs f32, relu and C %% 32 == 0");
+      bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty, mask);
     } else {
+      ZB_REQUIRE(mask == nullptr, "bn: ReLU bit mask needs 16-byte aligned NHWC tensors");
       ColGeom g = col_geom(ctx, rows, C, 1);
       dim3 grid(g.col_groups, g.slabs);
       bn_apply_nhwc<T, 1, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
     }
   } else {
+    ZB_REQUIRE(mask == nullptr, "bn: ReLU bit mask is NHWC only");
     bn_apply_nchw<T, RELU, RES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, C, HW);
   }
   ZB_LAUNCH_CHECK(ctx);
@@ -594,9 +618,10 @@ static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long 
 
 template <typename T>
 static int dispatch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
-                          const T* coef, const T* gamma, const T* beta, int relu) {
-  if (relu && res) return launch_apply<T, true, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
-  if (relu) return launch_apply<T, true, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+                          const T* coef, const T* gamma, const T* beta, int relu, uint32_t* mask = nullptr) {
+  ZB_REQUIRE(mask == nullptr || relu, "bn: a ReLU bit mask without relu");
+  if (relu && res) return launch_apply<T, true, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask);
+  if (relu) return launch_apply<T, true, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask);
   if (res) return launch_apply<T, false, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
   return launch_apply<T, false, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
 }
@@ -605,7 +630,7 @@ template <typename T>
 static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, double momentum,
                           const T* x, const T* scale, const T* bias, T* run_mean, T* run_var, T* saved_mean,
                           T* saved_inv, T* y, const T* res, int relu, const T* pre_partial = nullptr, int pre_rows = 0,
-                          const T* pre_shift = nullptr) {
+                          const T* pre_shift = nullptr, uint32_t* relu_mask = nullptr) {
   // pre_partial != NULL: the statistics pass already happened inside the producing conv's epilogue
   // (zb_conv2d_fprop_bnstats): [pre_rows][2][C] partial sums of (x - pre_shift) and its square
   ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
@@ -633,7 +658,7 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
                                                                  saved_inv, coef);
     ZB_LAUNCH_CHECK(ctx);
   }
-  rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu);
+  rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu, relu_mask);
   // algorithmic bytes: x read twice (once when the statistics came with the conv) + y written (+ residual read)
   prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * ((res ? 4.0 : 3.0) - (pre_partial ? 1.0 : 0.0)));
   return rc;
@@ -678,7 +703,8 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
 template <typename T>
 static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long H, long long W, const T* x, const T* dy,
                     const T* scale, const T* saved_mean, const T* saved_inv, T* dx, T* dscale, T* dbias, const T* y,
-                    T* dres, const T* relu_bias = nullptr) {
+                    T* dres, const T* relu_bias = nullptr, const uint32_t* relu_mask = nullptr) {
+  // relu_mask != NULL: the ReLU mask comes from the 1-bit array the fused forward wrote (y is not read); needs dres
   // relu_bias != NULL: backward of relu(bn(x)) with the ReLU mask recomputed from x, scale and this bias (y unused)
   ZB_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "bn: empty tensor");
   ZB_REQUIRE(!(relu_bias && (y || dres)), "bn bwd: mask recomputation excludes the y / residual-gradient arguments");
@@ -710,6 +736,9 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   if (relu_bias != nullptr)
     rc = run_col_reduce<T, BnBwdRecomputeFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
                                              [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs);
+  else if (relu_mask != nullptr)
+    rc = run_col_reduce<T, BnBwdBitsStoreFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; f.bits = relu_mask; }, &slabs);
   else if (y != nullptr && dres != nullptr)
     rc = run_col_reduce<T, BnBwdMaskStoreFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
                                              [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; }, &slabs);
@@ -724,14 +753,15 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
                                                                dscale, dbias, coef);
   ZB_LAUNCH_CHECK(ctx);
   if (relu_bias != nullptr) rc = launch_bwd_apply<T, 2, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
-  else if (y != nullptr && dres != nullptr)   // dres already holds the masked gradient (written by the reduce pass)
+  else if ((y != nullptr || relu_mask != nullptr) && dres != nullptr)   // dres already holds the masked gradient (written by the reduce pass)
     rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dres, static_cast<const T*>(nullptr), dx, static_cast<T*>(nullptr), mean, inv, coef, scale, relu_bias);
   else if (y != nullptr) rc = launch_bwd_apply<T, 1, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   else if (dres != nullptr) rc = launch_bwd_apply<T, 0, true>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   else rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
   // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written); the fused
   // BN+add+ReLU backward reads x twice, dy and y once, writes and re-reads the masked gradient, writes dx: 7 passes
-  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * ((y && dres) ? 7.0 : 5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) *
+                             (relu_mask ? 6.0 + 1.0 / 32.0 : (y && dres) ? 7.0 : 5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
   return rc;
 }
 
@@ -783,13 +813,40 @@ int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, in
                                const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
                                void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu,
                                const void* stat_partial, int64_t stat_rows, const void* shift) {
-  ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32, "bn prestats: NHWC f32 only");
-  ZB_REQUIRE(stat_partial != nullptr && shift != nullptr && stat_rows > 0 && stat_rows < (1 << 30), "bn prestats: missing statistics");
+  ZB_REQUIRE(stat_partial != nullptr && shift != nullptr && stat_rows > 0, "bn prestats: missing statistics");
+  return zb_bn2d_fwd_train_fused(ctx, dtype, layout, n, c, h, w, momentum, x, scale, bias, running_mean, running_var, saved_mean,
+                                 saved_inv_std, y, residual, relu, stat_partial, stat_rows, shift, nullptr);
+}
+
+int64_t zb_bn2d_relu_mask_words(int64_t n, int64_t c, int64_t h, int64_t w) { return (n * c * h * w + 31) / 32; }
+
+int zb_bn2d_fwd_train_fused(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, double momentum,
+                            const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
+                            void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu,
+                            const void* stat_partial, int64_t stat_rows, const void* shift, void* relu_mask) {
+  ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32, "bn fused forward: NHWC f32 only");
+  ZB_REQUIRE(stat_partial == nullptr || (shift != nullptr && stat_rows > 0 && stat_rows < (1 << 30)), "bn fused forward: bad statistics");
+  ZB_REQUIRE(relu_mask == nullptr || (relu && c % 32 == 0), "bn fused forward: the ReLU bit mask needs relu and C %% 32 == 0");
   return bn_fwd_train_t<float>(ctx, layout, n, c, h, w, momentum, static_cast<const float*>(x), static_cast<const float*>(scale),
                                static_cast<const float*>(bias), static_cast<float*>(running_mean), static_cast<float*>(running_var),
                                static_cast<float*>(saved_mean), static_cast<float*>(saved_inv_std), static_cast<float*>(y),
                                static_cast<const float*>(residual), relu, static_cast<const float*>(stat_partial),
-                               static_cast<int>(stat_rows), static_cast<const float*>(shift));
+                               static_cast<int>(stat_rows), static_cast<const float*>(shift), static_cast<uint32_t*>(relu_mask));
+}
+
+int zb_bn2d_bwd_mask(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x, const void* dy,
+                     const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx, void* dscale, void* dbias,
+                     const void* relu_mask, void* dres) {
+  ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32 && c % 32 == 0, "bn bwd (bit mask): NHWC f32 with C %% 32 == 0 only");
+  ZB_REQUIRE(relu_mask != nullptr && dres != nullptr && saved_mean != nullptr && saved_inv_std != nullptr,
+             "bn bwd (bit mask): mask, residual-gradient buffer and saved statistics are required");
+  ZB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dres) & 15) == 0,
+             "bn bwd (bit mask): tensors must be 16-byte aligned");
+  return bn_bwd_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(dy),
+                         static_cast<const float*>(scale), static_cast<const float*>(saved_mean), static_cast<const float*>(saved_inv_std),
+                         static_cast<float*>(dx), static_cast<float*>(dscale), static_cast<float*>(dbias), nullptr, static_cast<float*>(dres),
+                         nullptr, static_cast<const uint32_t*>(relu_mask));
 }
 
 int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,

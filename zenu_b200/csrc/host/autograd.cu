@@ -323,6 +323,7 @@ Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Vari
 
 struct BnFn : Function {
   Tensor x, y, scale, bias, saved_mean, saved_inv;
+  Tensor relu_mask;   // fused BN+add+ReLU: 1 bit per output element written by the forward (replaces keeping / re-reading y)
   int64_t n, c, h, w;
   bool relu, has_res;
   const char* name() const override { return "batch_norm_2d"; }
@@ -340,8 +341,11 @@ struct BnFn : Function {
       dres_ptr = dres.ptr;
     }
     ProfScope ps(rt, std::string("bn.bwd") + (relu ? "+relu" : "") + (has_res ? "+res" : "") + " " + shape_str(x.shape), 0.0,
-                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? 2.0 : 0.0)));
-    if (relu && !has_res)  // mask recomputed from x: the forward output is neither kept nor read
+                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? (relu_mask.defined() ? 1.0 + 1.0 / 32.0 : 2.0) : 0.0)));
+    if (relu_mask.defined())
+      check_rc(zb_bn2d_bwd_mask(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
+                                ds.ptr, db.ptr, relu_mask.ptr, dres_ptr), "bn bwd (bit mask)");
+    else if (relu && !has_res)  // mask recomputed from x: the forward output is neither kept nor read
       check_rc(zb_bn2d_relu_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, bias.ptr, saved_mean.ptr,
                                 saved_inv.ptr, dx.ptr, ds.ptr, db.ptr), "bn relu bwd");
     else
@@ -353,6 +357,7 @@ struct BnFn : Function {
     if (has_res) commit_grad(rt, *inputs[3], relu ? dres : gy);
     x = Tensor();
     y = Tensor();
+    relu_mask = Tensor();
   }
 };
 
@@ -375,11 +380,15 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   fn->saved_inv = rt.empty({c});
   ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
                static_cast<double>(y.bytes()) * (residual ? 4.0 : 3.0));
-  if (x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr) {   // statistics came with the producing conv
-    check_rc(zb_bn2d_fwd_train_prestats(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
-                                        mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
-                                        residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0, x->bn_stats.ptr, x->bn_stat_rows,
-                                        x->bn_shift), "bn fwd (fused statistics)");
+  const bool have_stats = x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr;   // statistics came with the producing conv
+  const bool want_mask = relu && residual != nullptr && y.dtype == ZB_F32 && c % 32 == 0 && getenv("ZENU_B200_NO_RELU_MASK") == nullptr;
+  if (want_mask) fn->relu_mask = rt.empty({zb_bn2d_relu_mask_words(n, c, h, w)});
+  if (have_stats || want_mask) {
+    check_rc(zb_bn2d_fwd_train_fused(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,
+                                     mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr, y.ptr,
+                                     residual ? (*residual)->data.ptr : nullptr, relu ? 1 : 0, have_stats ? x->bn_stats.ptr : nullptr,
+                                     have_stats ? x->bn_stat_rows : 0, have_stats ? x->bn_shift : nullptr,
+                                     want_mask ? fn->relu_mask.ptr : nullptr), "bn fwd (fused)");
     x->bn_stats = Tensor();
     x->bn_stat_rows = 0;
   } else {
@@ -394,7 +403,7 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   fn->bias = bias->data;
   fn->relu = relu;
   fn->has_res = residual != nullptr;
-  if (relu && residual) fn->y = y;
+  if (relu && residual && !fn->relu_mask.defined()) fn->y = y;
   fn->n = n; fn->c = c; fn->h = h; fn->w = w;
   return make_output(y, fn);
 }

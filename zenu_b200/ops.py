@@ -210,6 +210,29 @@ def batch_norm_2d_forward_train(ctx, momentum, x, scale, bias, mean, variance, l
     return y, sm, si
 
 
+def batch_norm_2d_forward_train_masked(ctx, momentum, x, scale, bias, mean, variance, residual=None):
+    """NHWC f32 fused BN(+residual)+ReLU forward that also writes the 1-bit ReLU mask: (y, saving_mean, saving_inv, mask)."""
+    n, c, h, w = _nkhw(x.shape, ZB_NHWC)
+    y = torch.empty_like(x)
+    sm = torch.empty((c,), dtype=x.dtype, device=x.device)
+    si = torch.empty((c,), dtype=x.dtype, device=x.device)
+    mask = torch.zeros((int(ctx.lib.zb_bn2d_relu_mask_words(n, c, h, w)),), dtype=torch.int32, device=x.device)
+    check(ctx.lib.zb_bn2d_fwd_train_fused(ctx.handle, _DT[x.dtype], ZB_NHWC, n, c, h, w, float(momentum), _p(x), _p(scale), _p(bias),
+                                          _p(mean), _p(variance), _p(sm), _p(si), _p(y), _p(residual), 1, None, 0, None, _p(mask)))
+    return y, sm, si, mask
+
+
+def batch_norm_2d_backward_masked(ctx, x, y_grad, scale, saving_mean, saving_inv_variance, mask):
+    """Backward of the fused BN+add+ReLU with the ReLU mask taken from `mask`: (x_grad, scale_grad, bias_grad, residual_grad)."""
+    n, c, h, w = _nkhw(x.shape, ZB_NHWC)
+    dx, dres = torch.empty_like(x), torch.empty_like(x)
+    ds = torch.empty((c,), dtype=x.dtype, device=x.device)
+    db = torch.empty((c,), dtype=x.dtype, device=x.device)
+    check(ctx.lib.zb_bn2d_bwd_mask(ctx.handle, _DT[x.dtype], ZB_NHWC, n, c, h, w, _p(x), _p(y_grad), _p(scale), _p(saving_mean),
+                                   _p(saving_inv_variance), _p(dx), _p(ds), _p(db), _p(mask), _p(dres)))
+    return dx, ds, db, dres
+
+
 def batch_norm_2d_backward(ctx, x, y_grad, scale, saving_mean=None, saving_inv_variance=None, layout=ZB_NCHW,
                            y=None, want_residual_grad=False):
     """Returns (x_grad, scale_grad, bias_grad[, residual_grad]).  Pass the fused forward output in `y` when it had relu."""
