@@ -378,10 +378,11 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   auto fn = std::make_shared<BnFn>();
   fn->saved_mean = rt.empty({c});
   fn->saved_inv = rt.empty({c});
-  ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
-               static_cast<double>(y.bytes()) * (residual ? 4.0 : 3.0));
   const bool have_stats = x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr;   // statistics came with the producing conv
   const bool want_mask = relu && residual != nullptr && y.dtype == ZB_F32 && c % 32 == 0 && getenv("ZENU_B200_NO_RELU_MASK") == nullptr;
+  // algorithmic bytes: x read twice (once when the statistics came with the conv), y written (+ residual read)
+  ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
+               static_cast<double>(y.bytes()) * ((residual ? 4.0 : 3.0) - (have_stats ? 1.0 : 0.0)));
   if (want_mask) fn->relu_mask = rt.empty({zb_bn2d_relu_mask_words(n, c, h, w)});
   if (have_stats || want_mask) {
     check_rc(zb_bn2d_fwd_train_fused(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, momentum, x->data.ptr, scale->data.ptr, bias->data.ptr,

@@ -226,6 +226,8 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long P = d->h + 2 * ph - R + 1, Q = d->w + 2 * pw - S + 1;
   const long long Wr = d->w + 2 * pw;
   if (P <= 0 || Q <= 0 || Wr > 256 || d->n * P > 0x3fffffffll) return ZB_ERR_UNSUPPORTED;
+  // tiny images (7x7): a tile is one image of <= 64 raster pixels, 42 KB of loads per 24 MMAs: L2 bound, the per-tap kernel wins
+  if (P * Wr <= 64 && getenv("ZENU_B200_WGRAD_HALO_ALL") == nullptr) return ZB_ERR_UNSUPPORTED;
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
   p.R = R; p.S = S; p.Wr = static_cast<int>(Wr);
