@@ -239,6 +239,15 @@ int zb_dp_wait(zb_ctx* ctx);
 int zb_dp_rank(zb_ctx* ctx);
 int zb_dp_world(zb_ctx* ctx);
 
+/* ---- input pipeline -------------------------------------------------------------------------------------------------
+ * The batch crosses PCIe as uint8 (NHWC as decoded, or NCHW) and is expanded on the device into the model's NCHW input:
+ * dst[n][c][h][w] = (src / 255 - mean[c]) / std[c] (host_mean / host_std: c host doubles, NULL = 0 / 1); int32 labels become
+ * the one-hot rows the reference's cross_entropy expects.  Replaces the per-sample Vec<Variable> + CPU concat + synchronous
+ * f32 cudaMemcpy of zenu/src/dataset.rs:74-100. */
+int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src_u8, void* dst_nchw, int64_t n, int64_t c,
+                         int64_t h, int64_t w, const double* host_mean, const double* host_std);
+int zb_onehot(zb_ctx* ctx, int dtype, const void* labels_i32, void* out, int64_t n, int64_t classes);
+
 /* ---- host model API (layers / tape / optimizer above the op ABI) -----------------------------------
  * C face of the C++ host side (zenu_b200/csrc/host): Module::call + Variable::backward + Optimizer::update
  * (reference: zenu-layer/src/lib.rs:21-51, zenu-autograd/src/lib.rs:413-420, zenu-optimizer/src/lib.rs:8-10)
@@ -279,6 +288,23 @@ int zb_model_profile_enable(zb_model* m, int enable);
 int64_t zb_model_profile_dump(zb_model* m, char* buf, int64_t cap);
 /* bytes currently held by the model's caching allocator (activations + parameters) */
 int64_t zb_model_bytes_reserved(zb_model* m);
+
+/* ---- model files (reference: zenu::save_model / load_model, zenu/src/lib.rs:26-67) -------------------------------
+ * bincode 1.3.3 image of HashMap<String, Variable>: per entry {key, shape, stride, data, data_type "f32"|"f64", ptr_offset}
+ * (zenu-matrix/src/impl_serde.rs:11-40) in the reference's layouts (filters [K,C,R,S], conv bias [1,K,1,1]).
+ * zb_model_load mirrors load_model: a key the model does not have is an error, parameters the file does not name are
+ * left untouched.  The zb_ckpt_* functions are the host-only reader / writer underneath (no GPU needed): all pointers
+ * are HOST pointers; data returned by zb_ckpt_entry is dense row-major and owned by the zb_ckpt. */
+typedef struct zb_ckpt zb_ckpt;
+int zb_model_save(zb_model* m, const char* path);
+int zb_model_load(zb_model* m, const char* path);
+int zb_ckpt_write(const char* path, int dtype, int n, const char* const* names, const int* ndims,
+                  const int64_t* const* shapes, const void* const* host_data);
+int zb_ckpt_open(const char* path, zb_ckpt** out);
+int zb_ckpt_count(const zb_ckpt* ck);
+int zb_ckpt_entry(const zb_ckpt* ck, int index, char* name, int name_cap, int64_t* shape, int* ndim, int* dtype,
+                  const void** host_data, int64_t* numel);
+int zb_ckpt_close(zb_ckpt* ck);
 
 #ifdef __cplusplus
 }

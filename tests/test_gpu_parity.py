@@ -610,6 +610,26 @@ def test_pool_and_gap(zb, ctx, layout):
     np.testing.assert_allclose(back(zb.global_avg_pool_backward(ctx, dev(dg), cv(x).shape, layout=L)), zo.gap_bwd(dg, (11, 9)), rtol=1e-6)
 
 
+def test_input_pipeline(zb, ctx):
+    """uint8 batch -> normalised NCHW float batch and int labels -> one-hot, against numpy."""
+    from zenu_b200 import ZB_NCHW, ZB_NHWC
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (3, 10, 7, 3), dtype=np.uint8)          # NHWC as decoded
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    ref = ((img.astype(np.float64) / 255.0 - np.array(mean)) / np.array(std)).transpose(0, 3, 1, 2)
+    for dt, tol in ((torch.float32, 1e-6), (torch.float64, 1e-6)):
+        got = zb.input_u8_to_float(ctx, torch.from_numpy(img).cuda(), mean, std, src_layout=ZB_NHWC, dtype=dt)
+        assert got.shape == (3, 3, 10, 7) and maxabs(host(got), ref) < tol * 10
+        got2 = zb.input_u8_to_float(ctx, torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2))).cuda(), mean, std, src_layout=ZB_NCHW, dtype=dt)
+        np.testing.assert_array_equal(host(got2), host(got))
+    plain = zb.input_u8_to_float(ctx, torch.from_numpy(img).cuda())
+    assert maxabs(host(plain), img.transpose(0, 3, 1, 2) / 255.0) < 1e-6
+    labels = rng.integers(0, 10, 17).astype(np.int32)
+    oh = host(zb.onehot(ctx, torch.from_numpy(labels).cuda(), 10))
+    np.testing.assert_array_equal(oh, np.eye(10, dtype=np.float32)[labels])
+    ctx.check()
+
+
 def test_softmax_xent(zb, ctx):
     rng = np.random.default_rng(21)
     z = (rng.standard_normal((16, 1000)) * 3).astype(np.float32)

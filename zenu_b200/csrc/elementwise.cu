@@ -238,6 +238,34 @@ using namespace zb;
     return ZB_ERR_INVALID;                                    \
   } while (0)
 
+// ---- input pipeline: uint8 images -> normalised f32/f64 NCHW batch, int labels -> one-hot targets -----------
+// Replaces the reference's host path (per-sample Vec<Variable> + CPU concat + synchronous cudaMemcpy of f32,
+// zenu/src/dataset.rs:74-100): the batch crosses PCIe as bytes (4x fewer) and is expanded on the device.
+struct NormCoef { float scale[8], shift[8]; };   // out = u8 * scale[c] + shift[c]
+template <typename T>
+__global__ void __launch_bounds__(256) u8_to_float_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, long long N, int C,
+                                                          long long HW, int src_nhwc, NormCoef nc) {
+  const long long total = N * C * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long hw = i % HW;
+    const long long ncc = i / HW;
+    const int c = static_cast<int>(ncc % C);
+    const long long n = ncc / C;
+    const uint8_t v = src_nhwc ? src[(n * HW + hw) * C + c] : src[i];
+    dst[i] = static_cast<T>(static_cast<float>(v) * nc.scale[c] + nc.shift[c]);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ labels, T* __restrict__ out, long long N, long long K) {
+  const long long total = N * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / K, k = i - n * K;
+    out[i] = labels[n] == k ? T(1) : T(0);
+  }
+}
+
 extern "C" {
 
 int zb_relu(zb_ctx* ctx, int dtype, const void* x, void* y, double alpha, int64_t n) {
@@ -297,4 +325,38 @@ int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m,
                   adam_t<double>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, step_t, grad_scale, n));
 }
 
+int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src_u8, void* dst_nchw, int64_t n, int64_t c, int64_t h,
+                         int64_t w, const double* host_mean, const double* host_std) {
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "input: unknown dtype %d", dtype);
+  ZB_REQUIRE(src_layout == ZB_NCHW || src_layout == ZB_NHWC, "input: unknown source layout %d", src_layout);
+  ZB_REQUIRE(c >= 1 && c <= 8, "input: 1..8 channels supported (got %lld)", static_cast<long long>(c));
+  if (n * c * h * w == 0) return ZB_OK;
+  NormCoef nc;
+  for (int i = 0; i < 8; ++i) {   // (u8 / 255 - mean) / std
+    const double m = host_mean && i < c ? host_mean[i] : 0.0, sd = host_std && i < c ? host_std[i] : 1.0;
+    ZB_REQUIRE(sd != 0.0, "input: std[%d] is zero", i);
+    nc.scale[i] = static_cast<float>(1.0 / (255.0 * sd));
+    nc.shift[i] = static_cast<float>(-m / sd);
+  }
+  const long long total = n * c * h * w;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  if (dtype == ZB_F32)
+    u8_to_float_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(src_u8), static_cast<float*>(dst_nchw), n,
+                                                                 static_cast<int>(c), h * w, src_layout == ZB_NHWC, nc);
+  else
+    u8_to_float_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(src_u8), static_cast<double*>(dst_nchw), n,
+                                                                  static_cast<int>(c), h * w, src_layout == ZB_NHWC, nc);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+int zb_onehot(zb_ctx* ctx, int dtype, const void* labels_i32, void* out, int64_t n, int64_t classes) {
+  ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "onehot: unknown dtype %d", dtype);
+  if (n * classes == 0) return ZB_OK;
+  const long long total = n * classes;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
+  if (dtype == ZB_F32) onehot_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const int*>(labels_i32), static_cast<float*>(out), n, classes);
+  else onehot_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const int*>(labels_i32), static_cast<double*>(out), n, classes);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
 }  // extern "C"

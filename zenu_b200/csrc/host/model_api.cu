@@ -31,6 +31,12 @@ struct zb_model {
     return ZB_ERR_INVALID;                                 \
   }
 
+namespace zb { namespace host {   // accessors for checkpoint.cu
+ParamStore& model_params(zb_model* m) { return m->params; }
+zb_ctx* model_ctx(zb_model* m) { return m->ctx; }
+int model_dtype(zb_model* m) { return m->rt->dtype; }
+} }
+
 static Variable run_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w) {
   Runtime& rt = *m->rt;
   // The batch stays NCHW (the reference's input contract): the stem conv consumes it directly when it can, otherwise

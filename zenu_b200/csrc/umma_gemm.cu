@@ -78,7 +78,9 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
-                                              bool halo = false, uint8_t* old_smem = nullptr) {
+                                              bool halo = false, uint8_t* old_smem = nullptr, int n_acc = 2, int group = 1) {
+  // n_acc TMEM accumulators of BN columns are drained in rotation; a CTA takes tiles in groups of `group` consecutive ids
+  // (group > 1: the multi-row stem kernel finishes `group` accumulators per scheduling step)
   const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
   struct LL { int EPI_OFFSET; } Lv{epi_offset};
     // ================================ epilogue ================================
@@ -106,7 +108,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       }
       __syncwarp();
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int groups = total_tiles / group;
+    for (int step = 0;; ++step) {
+      const int grp = blockIdx.x + (step / group) * gridDim.x;
+      if (grp >= groups) break;
+      const int tile = grp * group + step % group;
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
       // element offset of this lane's row inside D (or -1 when the row does not exist)
@@ -185,8 +191,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             if (c < p.dg_C) o[c] = p.beta != 0.f ? vals4[c] + p.beta * o[c] : vals4[c];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the tile is rewritten by the next accumulator
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       // rows this lane stores after the transpose (8 per chunk, the same 8 for every chunk of the tile), as 32-bit element
@@ -356,8 +361,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
       if (dead) break;
     }
@@ -717,6 +721,133 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- multi-row stem fprop
+// Small-C (C <= 4) forward conv, several output rows per tile.  The sliding-window box of an input row (Q windows x 32 floats,
+// see "small-C conv" below) depends only on the input row, so with TP output rows per tile one box feeds every (output row,
+// filter row) pair that reads it: (TP-1)*sh + R boxes per TP rows instead of R per row (7x7/s2, TP = 4: 3.25 instead of 7), and
+// the packed filter ([K][R*32], R tiles of BN x 32) stays resident in smem instead of being re-fetched per tile.  The
+// one-row-per-tile form was bound by exactly that L2->SM traffic (154 KB per 28 KB of output).  TP accumulators per tile, two
+// tile sets in TMEM (2*TP*BN <= 512 columns); the shared epilogue drains them as consecutive OUT_WINDOW tiles.
+constexpr int kStemMaxStages = 8;
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+stem_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ UmmaParams p) {
+  constexpr int TP = 512 / (2 * BN);
+  constexpr int B_TILE = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int R = p.ntaps;                       // filter rows
+  uint8_t* sB = smem;                          // R resident filter tiles
+  uint8_t* sA = sB + R * B_TILE;               // halo_slots stages x 16 KB window boxes
+  const int epi_off = R * B_TILE + p.halo_slots * 16384;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + epi_off + 4 * 4096 + 4 * 3 * BN * 4);
+  uint64_t* empty_bar = full_bar + kStemMaxStages;
+  uint64_t* b_bar = empty_bar + kStemMaxStages;
+  uint64_t* tfull_bar = b_bar + 1;             // 2 * TP
+  uint64_t* tempty_bar = tfull_bar + 2 * TP;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2 * TP);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  volatile int* err = p.err_flag;
+  if (warp == 0) {
+    if (elect_one()) { prefetch_tensormap(&tmA); prefetch_tensormap(&tmB); }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < kStemMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(b_bar, 1);
+      for (int i = 0; i < 2 * TP; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // tiles of the epilogue = (image, output row) with rows padded to a multiple of TP per image; a scheduling step = TP rows
+  const int p_groups = p.win_p_tiles / TP;                 // row groups per image
+  const int groups = (p.m_tiles / TP);                     // = N * p_groups
+  const int sh = p.stride_h, dh = p.win_qblocks;           // (win_qblocks carries dil_h for this kernel)
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_bar, static_cast<uint32_t>(R) * B_TILE);
+      for (int r = 0; r < R; ++r) tma_load_2d(sB + r * B_TILE, &tmB, b_bar, r * 32, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int g = blockIdx.x; g < groups && ok; g += gridDim.x) {
+        const int img = g / p_groups, p0 = (g - img * p_groups) * TP;
+        const int ih_lo = p0 * sh + p.lower_h, ih_hi = (p0 + TP - 1) * sh + p.lower_h + (R - 1) * dh;
+        for (int ih = ih_lo; ih <= ih_hi; ++ih) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1, err)) { ok = false; break; }
+          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.win_box_q) * 128u);
+          tma_load_4d(sA + stage * 16384, &tmA, &full_bar[stage], 0, 0, ih, img);   // rows outside the image: zero fill
+          if (++stage == p.halo_slots) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, 0, 0);
+      const uint32_t a0 = smem_u32(sA);
+      const uint64_t db_first = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
+      int stage = 0, set = 0;
+      uint32_t phase = 0, set_phase = 0;
+      bool ok = mbar_wait(b_bar, 0, err);
+      for (int g = blockIdx.x; g < groups && ok; g += gridDim.x) {
+        const int img = g / p_groups, p0 = (g - img * p_groups) * TP;
+        (void)img;
+        const int ih_lo = p0 * sh + p.lower_h, ih_hi = (p0 + TP - 1) * sh + p.lower_h + (R - 1) * dh;
+        for (int pl = 0; pl < TP && ok; ++pl)
+          if (!mbar_wait(&tempty_bar[set * TP + pl], set_phase ^ 1, err)) ok = false;
+        if (!ok) break;
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int ih = ih_lo; ih <= ih_hi; ++ih) {
+          if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint64_t da0 = make_smem_desc(a0 + stage * 16384, 16, 1024, kSmemLayoutSw128);
+          int t = ih - ih_lo;                       // = r * dil_h for output row p0 (pl = 0); decreases by sh per row
+          for (int pl = 0; pl < TP; ++pl, t -= sh) {
+            int r = t;
+            if (dh != 1) {
+              if (t < 0 || t % dh != 0) continue;
+              r = t / dh;
+            }
+            if (r < 0 || r >= R) continue;
+            const uint64_t db0 = db_first + static_cast<uint64_t>(r * (B_TILE >> 4));
+            const uint32_t d_tmem = tmem_base + (set * TP + pl) * BN;
+            umma_tf32(d_tmem, da0, db0, idesc, (started >> pl) & 1u);
+            umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+            umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+            umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
+            started |= 1u << pl;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.halo_slots) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        for (int pl = 0; pl < TP; ++pl) umma_commit(&tfull_bar[set * TP + pl]);
+        set ^= 1;
+        if (set == 0) set_phase ^= 1;
+      }
+    }
+  } else {
+    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, nullptr, 2 * TP, TP);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
 
 // out[i] = alpha * sum_s partial[s][i] + bias[col] + beta * out[i]   (deterministic split-K reduction)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long rows,
@@ -1521,6 +1652,20 @@ static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcG
   return ZB_OK;
 }
 
+template <int BN>
+static int stem_fprop_launch(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int grid, size_t smem) {
+  static size_t attr = 0;   // per instantiation: each kernel needs its own opt-in to > 48 KB of dynamic shared memory
+  if (smem > attr) {
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  prof_begin(ctx, PROF_TENSOR);
+  stem_fprop_kernel<BN><<<grid, 192, smem, ctx->stream>>>(a, b, p);
+  prof_end(ctx, PROF_TENSOR, p.prof_flops);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
 // y[N,P,Q,K] (NHWC) = conv(x, w[K,R,S,C]) (+bias); x is NHWC (x_nchw = 0) or NCHW (x_nchw = 1)
 int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, int x_nchw, const float* w, const float* bias,
                            float* y, float beta, const float* stat_shift, float* stat_partial, int* stat_rows) {
@@ -1542,6 +1687,45 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
     ZB_LAUNCH_CHECK(ctx);
   }
   const int bn = pick_bn(d->k);
+  if (g.Q <= kUmmaBM && bn <= 128 && d->k <= bn && getenv("ZENU_B200_NO_STEM_FPROP") == nullptr) {
+    // several output rows per tile, resident filter (stem_fprop_kernel)
+    const int TP = 512 / (2 * bn), R = static_cast<int>(d->kh);
+    const int budget = 227 * 1024 - 1024 - 512 - 16384 - 48 * bn;
+    const int stages = std::min(kStemMaxStages, (budget - R * bn * 128) / 16384);
+    const long long P_pad = (g.P + TP - 1) / TP * TP;
+    if (stages >= 3 && d->n * P_pad < 0x3fffffffll) {
+      UmmaParams p;
+      init_params(p, ctx);
+      p.chain_kb = 0;   // K = R blocks: a short accumulation chain in any math mode
+      CUtensorMap ma, mb;
+      if ((rc = make_map_window(ctx, &ma, xp, d->n, d->h, g.Wp, g.Q, static_cast<int>(d->stride_w), static_cast<int>(g.Q), 1, false)) != ZB_OK) return rc;
+      if ((rc = make_map_2d(ctx, &mb, wp, d->kh * 32, d->k, d->kh * 32, 32, bn)) != ZB_OK) return rc;
+      p.a_mode = A_WINDOW_K; p.b_mode = B_TILED_K; p.out_mode = OUT_WINDOW;
+      p.win_box_q = static_cast<int>(g.Q); p.win_box_p = 1; p.win_q_tiles = 1; p.win_p_tiles = static_cast<int>(P_pad);
+      p.M = static_cast<int>(d->n * g.P * g.Q); p.N = static_cast<int>(d->k);
+      p.m_tiles = static_cast<int>(d->n * P_pad); p.n_tiles = 1;
+      p.conv_P = static_cast<int>(g.P); p.conv_Q = static_cast<int>(g.Q);
+      p.lower_h = -static_cast<int>(d->pad_h); p.stride_h = static_cast<int>(d->stride_h); p.stride_w = static_cast<int>(d->stride_w);
+      p.win_qblocks = static_cast<int>(d->dil_h);   // (this kernel reads dil_h from win_qblocks)
+      p.ntaps = R; p.halo_slots = stages; p.kb_total = R;
+      p.prof_flops = 2.0 * p.M * d->k * d->c * d->kh * d->kw;
+      p.D = y; p.ldd = d->k; p.alpha = 1.f; p.beta = beta; p.bias = bias;
+      finish_split_fields(p, 1);
+      p.split_stride = 0;
+      const int groups = p.m_tiles / TP;
+      const int grid = std::min(groups, ctx->sm_count);
+      if (beta == 0.f) {
+        stat_attach(ctx, p, &st, p.m_tiles, d->k, y, bias);
+        if (p.stat_partial != nullptr) *st.rows = grid * 4;   // one partial row per epilogue warp of each launched CTA
+      }
+      const size_t smem = static_cast<size_t>(R) * bn * 128 + static_cast<size_t>(stages) * 16384 + 16384 + 48 * bn + 512 + 1024;
+      switch (bn) {
+        case 32: return stem_fprop_launch<32>(ctx, ma, mb, p, grid, smem);
+        case 64: return stem_fprop_launch<64>(ctx, ma, mb, p, grid, smem);
+        default: return stem_fprop_launch<128>(ctx, ma, mb, p, grid, smem);
+      }
+    }
+  }
   UmmaParams p;
   init_params(p, ctx);
   p.win_box_q = static_cast<int>(std::min<long long>(g.Q, kUmmaBM));

@@ -83,6 +83,13 @@ class Model:
     def train(self, flag=True):
         check(self.lib.zb_model_set_train(self._h, int(bool(flag))))
 
+    # ---- zenu::save_model / load_model (reference file format, zenu/src/lib.rs:26-67) ------------------------------------
+    def save(self, path):
+        check(self.lib.zb_model_save(self._h, str(path).encode()))
+
+    def load(self, path):
+        check(self.lib.zb_model_load(self._h, str(path).encode()))
+
     def set_optimizer(self, kind="sgd", lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
         check(self.lib.zb_model_set_optimizer(self._h, OPT[kind], float(lr), float(beta1), float(beta2), float(eps),
                                               float(weight_decay)))

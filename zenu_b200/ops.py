@@ -442,3 +442,27 @@ def adam_step(ctx, param, grad, m, v, lr, beta1, beta2, eps, step_t, weight_deca
     check(ctx.lib.zb_adam_step(ctx.handle, _DT[param.dtype], _p(param), _p(grad), _p(m), _p(v), float(lr), float(beta1),
                                float(beta2), float(eps), float(weight_decay), int(bool(decay)), int(step_t), float(grad_scale),
                                param.numel()))
+
+
+# ---- input pipeline ---------------------------------------------------------------------------------------------------
+def input_u8_to_float(ctx, src_u8, mean=None, std=None, src_layout=ZB_NHWC, dtype=torch.float32):
+    """uint8 batch ([N,H,W,C] for ZB_NHWC, [N,C,H,W] for ZB_NCHW) -> normalised NCHW float batch on the device."""
+    if not src_u8.is_cuda or not src_u8.is_contiguous() or src_u8.dtype != torch.uint8:
+        raise ZenuB200Error("input_u8_to_float: contiguous uint8 CUDA tensor expected")
+    if src_layout == ZB_NHWC:
+        n, h, w, c = src_u8.shape
+    else:
+        n, c, h, w = src_u8.shape
+    out = torch.empty((n, c, h, w), dtype=dtype, device=src_u8.device)
+    m = (ctypes.c_double * c)(*[float(v) for v in mean]) if mean is not None else None
+    s = (ctypes.c_double * c)(*[float(v) for v in std]) if std is not None else None
+    check(ctx.lib.zb_input_u8_to_float(ctx.handle, _DT[dtype], src_layout, _p(src_u8), _p(out), n, c, h, w, m, s))
+    return out
+
+
+def onehot(ctx, labels, classes, dtype=torch.float32):
+    if not labels.is_cuda or not labels.is_contiguous() or labels.dtype != torch.int32:
+        raise ZenuB200Error("onehot: contiguous int32 CUDA labels expected")
+    out = torch.empty((labels.numel(), classes), dtype=dtype, device=labels.device)
+    check(ctx.lib.zb_onehot(ctx.handle, _DT[dtype], _p(labels), _p(out), labels.numel(), classes))
+    return out
