@@ -261,11 +261,15 @@ __global__ void __launch_bounds__(256) col_reduce_nchw(F f, const T* __restrict_
 // Block = 32 channels x 8 slab lanes (256 threads): the slab partials of a channel are folded by 8 threads with
 // coalesced loads, then combined through shared memory in double precision.  (A single thread per channel walking
 // ~1000 slabs serially cost more than the reduce pass itself on 64-channel layers.)
-constexpr int kFinC = 32, kFinS = 32;
+constexpr int kFinC = 8, kFinS = 128;
 template <typename T, int NS>
 __device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int slabs, long long C, long long c, bool active,
                                               double (&out)[NS]) {
-  __shared__ double sh[NS][kFinS][kFinC + 1];
+  // thread = (channel lc, slab lane sl); a warp holds 4 slab lanes x 8 channels: two xor-shuffles fold them, then the 32 warp
+  // sums of a channel are added from shared memory.  (8 channels x 128 slab lanes per block: ~10 dependent load rounds of the
+  // previous 32 x 32 arrangement become ~3, and a 64-channel layer gets 8 blocks instead of 2: these ~100 tiny kernels per step
+  // sit between every BatchNorm reduce and apply pass.)
+  __shared__ double sh[NS][kFinS / 4][kFinC];
   const int lc = threadIdx.x & (kFinC - 1), sl = threadIdx.x / kFinC;
   double acc[NS];
 #pragma unroll
@@ -277,13 +281,17 @@ __device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int
       for (int s = 0; s < NS; ++s) acc[s] += static_cast<double>(partial[(static_cast<long long>(i) * NS + s) * C + c]);
   }
 #pragma unroll
-  for (int s = 0; s < NS; ++s) sh[s][sl][lc] = acc[s];
+  for (int s = 0; s < NS; ++s) {
+    acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 8);
+    acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 16);
+    if ((threadIdx.x & 31) < kFinC) sh[s][threadIdx.x >> 5][lc] = acc[s];
+  }
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     double v = 0.0;
 #pragma unroll
-    for (int j = 0; j < kFinS; ++j) v += sh[s][j][lc];
+    for (int j = 0; j < kFinS / 4; ++j) v += sh[s][j][lc];
     out[s] = v;
   }
 }

@@ -856,8 +856,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
   const long long total = rows * cols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[s * split_stride + i];
+    // four independent partial sums, 8 loads in flight (the loop used to be one dependent L2 round trip per split)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = 0;
+#pragma unroll 2
+    for (; s + 4 <= splits; s += 4) {
+      const float v0 = partial[(s + 0) * split_stride + i], v1 = partial[(s + 1) * split_stride + i];
+      const float v2 = partial[(s + 2) * split_stride + i], v3 = partial[(s + 3) * split_stride + i];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; s < splits; ++s) a0 += partial[s * split_stride + i];
+    const float acc = (a0 + a1) + (a2 + a3);
     const long long r = i / cols, c = i - r * cols;
     float v = alpha * acc;
     if (bias) v += bias[c];

@@ -176,11 +176,19 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* 
                                     int splits, float beta) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+#pragma unroll 2
+    for (; s + 2 <= splits; s += 2) {   // independent accumulators: several 128-bit loads in flight per thread
+      const float4 v = partial[s * split_stride4 + i], u = partial[(s + 1) * split_stride4 + i];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
+    }
+    if (s < splits) {
       const float4 v = partial[s * split_stride4 + i];
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     if (beta != 0.f) {
       const float4 o = out[i];
       a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w;
