@@ -23,7 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "resnet50_train_images_per_s"
+METRIC = "resnet50_train_images_per_s"   # BASELINE.json metric; other --arch values report <arch>_train_images_per_s
 UNIT = "images/s"
 FWD_GFLOP_PER_IMG = {"resnet50": 8.174 + 0.0041, "resnet18": 3.627 + 0.001, "small_cnn": 0.107}
 
@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
     r = cpu_reference_steps(args.arch, args.classes, args.hw, sample, args.steps, min(args.warmup, 1))
     ms = r["sec_per_step"] * 1e3
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": f"each step = one full train step on {sample} of the 256 images",
@@ -161,6 +161,10 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(args):
+    return METRIC if args.arch == "resnet50" else f"{args.arch}_train_images_per_s"
 
 
 def workload_name(args):
@@ -340,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
         cpu_baseline = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                         "sample": f"2 train steps at batch {args.cpu_batch} (of 256) after 1 warm-up, {r['blas']}"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": global_batch, "parallelism": f"dp{world}",
