@@ -14,6 +14,7 @@
 //   apply   : same geometry as reduce; per-channel coefficients live in registers
 // Statistics use a per-channel shift (the first row) so the single-pass sum / sum-of-squares does not cancel.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -68,7 +69,12 @@ static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
   g.ty = 256 / tx;
   g.col_groups = static_cast<int>((g.cvecs + tx - 1) / tx);
   long long max_slabs = std::max<long long>(1, (ctx->sm_count * 8ll) / g.col_groups);
-  long long want = (rows + g.ty * 16ll - 1) / (g.ty * 16ll);
+  static int rows_per_thread = -1;   // rows each thread walks per slab (tuning knob: ZENU_B200_BN_ROWS)
+  if (rows_per_thread < 0) {
+    const char* e = getenv("ZENU_B200_BN_ROWS");
+    rows_per_thread = e ? std::max(4, atoi(e)) : 16;
+  }
+  long long want = (rows + g.ty * static_cast<long long>(rows_per_thread) - 1) / (g.ty * static_cast<long long>(rows_per_thread));
   g.slabs = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min(want, max_slabs), 65535)));
   g.rows_per_slab = (rows + g.slabs - 1) / g.slabs;
   g.slabs = static_cast<int>((rows + g.rows_per_slab - 1) / g.rows_per_slab);

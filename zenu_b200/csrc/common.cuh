@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -86,6 +87,9 @@ void prof_end(zb_ctx* ctx, int cls, double work);
 
 // Grow-only scratch; stream-ordered so earlier kernels that still read the old block stay valid.
 int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out);
+
+// Environment switches select code paths for A/B experiments; they are read once per process, never per call.
+#define ZB_ENV_FLAG(name) ([]() -> bool { static const bool v = getenv(name) != nullptr; return v; }())
 
 static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 

@@ -262,7 +262,7 @@ Variable conv2d(Runtime& rt, const Variable& x_in, const Variable& w, const Vari
   Tensor stats;
   int64_t stat_rows = 0;
   const bool want_stats = bn_shift != nullptr && rt.train && rt.dtype == ZB_F32 && w.shape().size() == 4 &&
-                          (*bn_shift)->data.numel() == w.shape()[0] && getenv("ZENU_B200_NO_BNSTATS") == nullptr;
+                          (*bn_shift)->data.numel() == w.shape()[0] && !ZB_ENV_FLAG("ZENU_B200_NO_BNSTATS");
   if (want_stats) stats = rt.empty({static_cast<int64_t>(zb_conv2d_bnstats_rows(rt.ctx)), 2, w.shape()[0]});
   auto run_fprop = [&](int layout, const zb_conv2d_desc* d, const void* xp, void* yp, int dtype) {
     const void* bp = bias ? (*bias)->data.ptr : nullptr;
@@ -379,7 +379,7 @@ Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, co
   fn->saved_mean = rt.empty({c});
   fn->saved_inv = rt.empty({c});
   const bool have_stats = x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr;   // statistics came with the producing conv
-  const bool want_mask = relu && residual != nullptr && y.dtype == ZB_F32 && c % 32 == 0 && getenv("ZENU_B200_NO_RELU_MASK") == nullptr;
+  const bool want_mask = relu && residual != nullptr && y.dtype == ZB_F32 && c % 32 == 0 && !ZB_ENV_FLAG("ZENU_B200_NO_RELU_MASK");
   // algorithmic bytes: x read twice (once when the statistics came with the conv), y written (+ residual read)
   ProfScope ps(rt, std::string("bn.fwd") + (relu ? "+relu" : "") + (residual ? "+res" : "") + " " + shape_str(s), 0.0,
                static_cast<double>(y.bytes()) * ((residual ? 4.0 : 3.0) - (have_stats ? 1.0 : 0.0)));

@@ -1003,7 +1003,7 @@ static int pick_bn(long long n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 12
 static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   // launches whose epilogue reads the old output tile (beta != 0, chained 3xTF32 flushes): a shallower operand ring makes
   // room for the deep old-tile prefetch buffers (these are short-K, output-bound problems)
-  if ((p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && getenv("ZENU_B200_NO_DEEP_BETA") == nullptr) {
+  if ((p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && !ZB_ENV_FLAG("ZENU_B200_NO_DEEP_BETA")) {
     switch (bn) {
       case 32: return launch_cfg<32, 7, true>(ctx, a, b, p);
       case 64: return launch_cfg<64, 6, true>(ctx, a, b, p);
@@ -1085,9 +1085,17 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
   p.stride_w = p.stride_h = 1;
   p.alpha = 1.f;
   p.err_flag = ctx->err_flag;
-  if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &p.dbg_a_shift, &p.dbg_base_mode);
-  if (const char* e = getenv("ZENU_B200_DBG_EPI")) p.dbg_epi = atoi(e);
-  if (const char* e = getenv("ZENU_B200_DBG_BSHIFT")) sscanf(e, "%d,%d", &p.dbg_b_shift, &p.dbg_b_lbo);
+  struct DbgEnv {   // hardware-probe knobs (tools/probe_*.py), parsed once
+    int a_shift = 0, base_mode = 0, epi = 0, b_shift = 0, b_lbo = 0;
+    DbgEnv() {
+      if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &a_shift, &base_mode);
+      if (const char* e = getenv("ZENU_B200_DBG_EPI")) epi = atoi(e);
+      if (const char* e = getenv("ZENU_B200_DBG_BSHIFT")) sscanf(e, "%d,%d", &b_shift, &b_lbo);
+    }
+  };
+  static const DbgEnv dbg;
+  p.dbg_a_shift = dbg.a_shift; p.dbg_base_mode = dbg.base_mode; p.dbg_epi = dbg.epi;
+  p.dbg_b_shift = dbg.b_shift; p.dbg_b_lbo = dbg.b_lbo;
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM
@@ -1144,7 +1152,7 @@ struct HaloPlan {
 static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long long Cin, long long Kout, int R, int S, int ph, int pw,
                       HaloPlan* hp) {
   (void)ctx;
-  if (getenv("ZENU_B200_NO_HALO")) return false;
+  if (ZB_ENV_FLAG("ZENU_B200_NO_HALO")) return false;
   const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
   if (R * S < 2 || R * S > kUmmaMaxTaps || Cin % 32 != 0 || Kout % 4 != 0 || P <= 0 || Q <= 0 || ph < 0 || pw < 0) return false;
   const long long Wr = W + 2 * pw;  // raster width = Q + S - 1
@@ -1696,7 +1704,7 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
     ZB_LAUNCH_CHECK(ctx);
   }
   const int bn = pick_bn(d->k);
-  if (g.Q <= kUmmaBM && bn <= 128 && d->k <= bn && getenv("ZENU_B200_NO_STEM_FPROP") == nullptr) {
+  if (g.Q <= kUmmaBM && bn <= 128 && d->k <= bn && !ZB_ENV_FLAG("ZENU_B200_NO_STEM_FPROP")) {
     // several output rows per tile, resident filter (stem_fprop_kernel)
     const int TP = 512 / (2 * bn), R = static_cast<int>(d->kh);
     const int budget = 227 * 1024 - 1024 - 512 - 16384 - 48 * bn;

@@ -227,7 +227,7 @@ static CUtensorMapDataType sd_dtype() {
 
 // Returns ZB_ERR_UNSUPPORTED (nothing launched) when the geometry is not served by this kernel.
 int umma_conv_stem_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
-  if (getenv("ZENU_B200_NO_STEM_DGRAD")) return ZB_ERR_UNSUPPORTED;
+  if (ZB_ENV_FLAG("ZENU_B200_NO_STEM_DGRAD")) return ZB_ERR_UNSUPPORTED;
   if (!(d->c <= 4 && d->kw <= 8 && d->dil_w == 1 && d->k % 32 == 0 && d->kh <= 16 && d->stride_h <= 8 && d->stride_w <= 8))
     return ZB_ERR_UNSUPPORTED;
   const long long P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);

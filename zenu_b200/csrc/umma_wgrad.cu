@@ -227,7 +227,7 @@ static int make_raster_map(zb_ctx* ctx, CUtensorMap* map, const float* base, lon
 int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, float* dw, float beta) {
   const int R = static_cast<int>(d->kh), S = static_cast<int>(d->kw);
   const int ph = static_cast<int>(d->pad_h), pw = static_cast<int>(d->pad_w);
-  if (getenv("ZENU_B200_NO_WGRAD_HALO") || umma_chain_limit() > 0) return ZB_ERR_UNSUPPORTED;
+  if (ZB_ENV_FLAG("ZENU_B200_NO_WGRAD_HALO") || umma_chain_limit() > 0) return ZB_ERR_UNSUPPORTED;
   if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1 || R * S < 2 || R > 8 || R * S * 32 > 512 ||
       d->c % 32 != 0 || d->k % 4 != 0 || (reinterpret_cast<uintptr_t>(dw) & 15) != 0)
     return ZB_ERR_UNSUPPORTED;
@@ -235,7 +235,7 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long Wr = d->w + 2 * pw;
   if (P <= 0 || Q <= 0 || Wr > 256 || d->n * P > 0x3fffffffll) return ZB_ERR_UNSUPPORTED;
   // tiny images (7x7): a tile is one image of <= 64 raster pixels, 42 KB of loads per 24 MMAs: L2 bound, the per-tap kernel wins
-  if (P * Wr <= 64 && getenv("ZENU_B200_WGRAD_HALO_ALL") == nullptr) return ZB_ERR_UNSUPPORTED;
+  if (P * Wr <= 64 && !ZB_ENV_FLAG("ZENU_B200_WGRAD_HALO_ALL")) return ZB_ERR_UNSUPPORTED;
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
   p.R = R; p.S = S; p.Wr = static_cast<int>(Wr);
