@@ -524,6 +524,15 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+      // The issuing thread is on the critical path of small-N tiles (an N = 64 MMA is ~32 cycles of tensor work): descriptors are
+      // formed once per launch and advanced by adding to their 14-bit address field (smem addresses < 256 KB: no carry out).
+      const uint64_t a_desc0 = (a_mn ? make_smem_desc(0, 4096, 512, kSmemLayoutSw128Base32)
+                                     : make_smem_desc(0, 16, 1024, kSmemLayoutSw128, p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0)) +
+                               ((smem_u32(smem) + (a_mn ? 0 : p.dbg_a_shift * 128)) >> 4);
+      const uint64_t b_desc0 = (b_mn ? make_smem_desc(0, p.dbg_b_lbo ? p.dbg_b_lbo : 4096, 512, kSmemLayoutSw128Base32)
+                                     : make_smem_desc(0, 16, 1024, kSmemLayoutSw128)) +
+                               ((smem_u32(smem) + L::A_BYTES + (b_mn ? p.dbg_b_shift * 128 : 0)) >> 4);
+      const uint32_t a_kstep = a_mn ? (1024 >> 4) : (32 >> 4), b_kstep = b_mn ? (1024 >> 4) : (32 >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -543,17 +552,12 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (; kb < sub_end; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_base = a_base + L::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < kUmmaBK / 8; ++k) {
-            const uint64_t da = a_mn ? make_smem_desc(a_base + k * 1024, 4096, 512, kSmemLayoutSw128Base32)
-                                     : make_smem_desc(a_base + k * 32 + p.dbg_a_shift * 128, 16, 1024, kSmemLayoutSw128,
-                                                      p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0);
-            const uint64_t db = b_mn ? make_smem_desc(b_base + k * 1024 + p.dbg_b_shift * 128, p.dbg_b_lbo ? p.dbg_b_lbo : 4096, 512, kSmemLayoutSw128Base32)
-                                     : make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128);
-            umma_tf32(d_tmem, da, db, idesc, (kb > sub_begin || k > 0) ? 1u : 0u);
-          }
+          const uint32_t st_off = static_cast<uint32_t>(stage * L::STAGE_BYTES) >> 4;
+          const uint64_t da = a_desc0 + st_off, db = b_desc0 + st_off;
+          umma_tf32(d_tmem, da, db, idesc, kb > sub_begin ? 1u : 0u);
+          umma_tf32(d_tmem, da + a_kstep, db + b_kstep, idesc, 1u);
+          umma_tf32(d_tmem, da + 2 * a_kstep, db + 2 * b_kstep, idesc, 1u);
+          umma_tf32(d_tmem, da + 3 * a_kstep, db + 3 * b_kstep, idesc, 1u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -668,7 +672,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t aph = 0, bph = 0, acc_phase = 0;
       bool ok = true;
       if (resident) ok = mbar_wait(&b_full[0], 0, err);
-      const uint32_t a_addr0 = smem_u32(sA), b_addr0 = smem_u32(sB);
+      const uint32_t a_addr0 = smem_u32(sA);
+      // descriptors advanced by integer adds on their address field (see umma_kernel): ~6 instructions per MMA instead of ~30
+      const uint64_t a_desc0 = make_smem_desc(0, 16, 1024, kSmemLayoutSw128);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         for (int c = 0; c < chunks && ok;) {   // one pass per accumulator flush (halo_chain channel chunks each)
         const int c_begin = c;
@@ -679,21 +686,21 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (; c < c_end && ok; ++c) {
           if (!mbar_wait(&a_full[ai], aph, err)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t a_base = a_addr0 + ai * p.halo_slot_bytes;
+          const uint64_t a_slot = a_desc0 + ((a_addr0 + ai * p.halo_slot_bytes) >> 4);
           for (int t = 0; t < taps; ++t) {
-            uint32_t b_base;
+            uint64_t db;
             if (resident) {
-              b_base = b_addr0 + (c * taps + t) * B_BYTES;
+              db = b_desc0 + static_cast<uint32_t>((c * taps + t) * (B_BYTES >> 4));
             } else {
               if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
               tc_fence_after();
-              b_base = b_addr0 + bi * B_BYTES;
+              db = b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4));
             }
-            const uint32_t a_tap = a_base + static_cast<uint32_t>(p.tap_w[t]) * 128u;
-#pragma unroll
-            for (int k = 0; k < kUmmaBK / 8; ++k)
-              umma_tf32(d_tmem, make_smem_desc(a_tap + k * 32, 16, 1024, kSmemLayoutSw128),
-                        make_smem_desc(b_base + k * 32, 16, 1024, kSmemLayoutSw128), idesc, (c > c_begin || t > 0 || k > 0) ? 1u : 0u);
+            const uint64_t da = a_slot + static_cast<uint32_t>(p.tap_w[t]) * 8u;   // tap = whole 128-byte rows
+            umma_tf32(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
+            umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
+            umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
             if (!resident) {
               umma_commit(&b_empty[bi]);
               if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }

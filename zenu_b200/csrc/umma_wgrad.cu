@@ -123,18 +123,22 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       const int ksteps = p.kt_pad >> 3;
       const uint32_t smem0 = smem_u32(smem);
+      const uint64_t a_desc0 = make_smem_desc(0, p.a_box_bytes, 512, kSmemLayoutSw128Base32);
+      const uint64_t b_desc0 = make_smem_desc(0, 128, 512, kSmemLayoutSw128Base32);
+      const uint32_t row_step = static_cast<uint32_t>(p.Wr * 128) >> 4;   // one filter row = Wr raster rows of 128 bytes
       bool ok = true;
       for (int tile = t_begin; tile < t_end; ++tile) {
         if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t a_base = smem0 + stage * p.stage_bytes;
-        const uint32_t x_base = a_base + p.a_boxes * p.a_box_bytes;
+        // descriptors advanced by integer adds on their address field (the issuing thread is on the critical path)
+        const uint32_t a_off = (smem0 + stage * p.stage_bytes) >> 4;
+        const uint64_t da0 = a_desc0 + a_off;
+        const uint64_t db0 = b_desc0 + a_off + static_cast<uint32_t>((p.a_boxes * p.a_box_bytes) >> 4);
         for (int i = 0; i < ksteps; ++i) {
-          const uint64_t da = make_smem_desc(a_base + i * 1024, p.a_box_bytes, 512, kSmemLayoutSw128Base32);
-          for (int r = 0; r < p.R; ++r) {
-            const uint64_t db = make_smem_desc(x_base + (r * p.Wr) * 128 + i * 1024, 128, 512, kSmemLayoutSw128Base32);
-            umma_tf32(tmem_base + r * acc_cols, da, db, idesc, (tile > t_begin || i > 0) ? 1u : 0u);
-          }
+          const uint64_t da = da0 + static_cast<uint32_t>(i * 64);
+          uint64_t db = db0 + static_cast<uint32_t>(i * 64);
+          const uint32_t accum = (tile > t_begin || i > 0) ? 1u : 0u;
+          for (int r = 0; r < p.R; ++r, db += row_step) umma_tf32(tmem_base + r * acc_cols, da, db, idesc, accum);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
