@@ -78,7 +78,10 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
-                                              bool halo = false, uint8_t* old_smem = nullptr, int n_acc = 2, int group = 1) {
+                                              bool halo = false, uint8_t* old_smem = nullptr, int n_acc = 2, int group = 1,
+                                              int cluster = 1) {
+  // cluster > 1 (halo kernel with multicast filter tiles): the CTAs of a cluster walk tile groups in lockstep: group q ->
+  // column block q % n_tiles, row block (q / n_tiles) * cluster + rank; a row block past the end is a dummy (nothing stored)
   // n_acc TMEM accumulators of BN columns are drained in rotation; a CTA takes tiles in groups of `group` consecutive ids
   // (group > 1: the multi-row stem kernel finishes `group` accumulators per scheduling step)
   const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
@@ -100,7 +103,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     float* stat_w = reinterpret_cast<float*>(smem + Lv.EPI_OFFSET + 4 * 4096) + ew * 3 * BN;   // this warp's [3][BN]: sum, sum sq, shift
     const bool stats = p.stat_partial != nullptr;
     if (stats) {   // the grid is a multiple of n_tiles: this CTA only ever sees column block blockIdx.x % n_tiles
-      const int nb0 = (blockIdx.x % p.n_tiles) * BN;
+      const int nb0 = ((blockIdx.x / cluster) % p.n_tiles) * BN;
       for (int j = lane; j < BN; j += 32) {
         stat_w[j] = 0.f;
         stat_w[BN + j] = 0.f;
@@ -109,11 +112,24 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       __syncwarp();
     }
     const int groups = total_tiles / group;
+    const int cl_id = blockIdx.x / cluster, n_cl = gridDim.x / cluster, cl_rank = blockIdx.x % cluster;
+    const int cl_groups = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles;
     for (int step = 0;; ++step) {
-      const int grp = blockIdx.x + (step / group) * gridDim.x;
-      if (grp >= groups) break;
-      const int tile = grp * group + step % group;
-      const TileCoord tc = decode_tile(p, tile);
+      TileCoord tc;
+      bool tile_exists = true;
+      if (cluster == 1) {
+        const int grp = blockIdx.x + (step / group) * gridDim.x;
+        if (grp >= groups) break;
+        tc = decode_tile(p, grp * group + step % group);
+      } else {
+        const int q = cl_id + step * n_cl;
+        if (q >= cl_groups) break;
+        tc.n_blk = q % p.n_tiles;
+        tc.m_blk = (q / p.n_tiles) * cluster + cl_rank;
+        tc.tap = 0;
+        tc.split = 0;
+        tile_exists = tc.m_blk < p.m_tiles;
+      }
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
       // element offset of this lane's row inside D (or -1 when the row does not exist)
       long long my_off = -1;
@@ -125,7 +141,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
           const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
           const int pl = l / p.win_box_q, ql = l - pl * p.win_box_q;
           const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
-          if (pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
+          if (tile_exists && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
             my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
         } else {
           const int row = m0 + l;
@@ -367,8 +383,9 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     }
     if (stats) {   // one row of partials per epilogue warp: [row][2][N]
       __syncwarp();
-      const int n_blk = blockIdx.x % p.n_tiles;
-      const long long row = static_cast<long long>(blockIdx.x / p.n_tiles) * 4 + ew;
+      const int n_blk = (blockIdx.x / cluster) % p.n_tiles;
+      const long long row = (cluster == 1 ? static_cast<long long>(blockIdx.x / p.n_tiles)
+                                          : static_cast<long long>((blockIdx.x / cluster) / p.n_tiles) * cluster + blockIdx.x % cluster) * 4 + ew;
       for (int j = lane; j < BN; j += 32) {
         const int col = n_blk * BN + j;
         if (col < p.N) {
@@ -590,8 +607,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // (the hardware swizzle is a function of the absolute smem address, so a start that is 128- but not 1024-byte aligned is
 // legal: measured with tools/probe_desc_shift.py).  Filter tiles stream through their own ring, or stay resident for the
 // whole persistent CTA when the filter fits (64 -> 64 channels).  Output positions in halo columns are computed and dropped.
+// CL > 1: thread-block cluster of CL CTAs working on CL consecutive row blocks of the same column block in lockstep.  The
+// streamed filter tiles are what bounds the >= 128-channel 3x3 layers (a 128-pixel tile re-reads the whole [BN][taps*C] filter
+// slice from L2: 0.6-4.7 MB per tile, 8-14 TB/s of L2->SM traffic at the measured speeds), so each CTA fetches 1/CL of every
+// filter tile and TMA-multicasts it into all CL shared memories; a ring slot is refilled once the MMA warps of ALL CTAs have
+// released it (tcgen05.commit multicast onto every CTA's b_empty barrier).  Rasters stay private.
 constexpr int kHaloMaxB = 24;
-template <int BN>
+template <int BN, int CL = 1>
 __global__ void __launch_bounds__(192, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ UmmaParams p) {
@@ -618,7 +640,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (elect_one()) {
       for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < kHaloMaxB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+      for (int i = 0; i < kHaloMaxB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
       fence_barrier_init();
     }
@@ -628,11 +650,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.m_tiles * p.n_tiles;
   const int taps = p.ntaps, chunks = p.c_chunks;
   const bool resident = p.halo_b_resident != 0;
+  // tile walk: group q -> column block q % n_tiles, row block (q / n_tiles) * CL + rank (past the end: a dummy, loads are zero fill)
+  const int cl_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
+  const int total_q = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;
+  constexpr uint16_t kClMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -645,8 +672,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sB + (c * taps + t) * B_BYTES, &tmB, &b_full[0], t * p.b_tap_stride + c * kUmmaBK, 0);
       }
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      for (int q = cl_id; q < total_q && ok; q += n_cl) {
+        const int n_blk = q % p.n_tiles, m_blk = (q / p.n_tiles) * CL + cl_rank;
         const int img = m_blk / p.win_p_tiles, pt = m_blk - img * p.win_p_tiles;
         const int h0 = pt * p.win_box_p + p.lower_h;
         for (int c = 0; c < chunks && ok; ++c) {
@@ -658,7 +685,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = 0; t < taps; ++t) {
               if (!mbar_wait(&b_empty[bi], bph ^ 1, err)) { ok = false; break; }
               mbar_arrive_expect_tx(&b_full[bi], B_BYTES);
-              tma_load_2d(sB + bi * B_BYTES, &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK, n_blk * BN);
+              if (CL == 1)
+                tma_load_2d(sB + bi * B_BYTES, &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK, n_blk * BN);
+              else   // this CTA's 1/CL of the tile rows (the map's box is BN / CL rows), delivered to every CTA of the cluster
+                tma_load_2d_multicast(sB + bi * B_BYTES + cl_rank * (B_BYTES / CL), &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK,
+                                      n_blk * BN + cl_rank * (BN / CL), kClMask);
               if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
             }
           }
@@ -676,7 +707,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // descriptors advanced by integer adds on their address field (see umma_kernel): ~6 instructions per MMA instead of ~30
       const uint64_t a_desc0 = make_smem_desc(0, 16, 1024, kSmemLayoutSw128);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int q = cl_id; q < total_q && ok; q += n_cl) {
         for (int c = 0; c < chunks && ok;) {   // one pass per accumulator flush (halo_chain channel chunks each)
         const int c_begin = c;
         const int c_end = p.halo_chain > 0 ? min(chunks, c + p.halo_chain) : chunks;
@@ -702,7 +733,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
             umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
             if (!resident) {
-              umma_commit(&b_empty[bi]);
+              if (CL == 1) umma_commit(&b_empty[bi]); else umma_commit_multicast(&b_empty[bi], kClMask);
               if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
             }
           }
@@ -718,10 +749,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true);
+    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true, nullptr, 2, 1, CL);
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into this CTA or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -1196,16 +1228,31 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   return true;
 }
 
-template <int BN>
-static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, size_t smem) {
+template <int BN, int CL>
+static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, size_t smem, int grid) {
   static size_t attr = 0;
   if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
-  const int grid = p.stat_partial ? stat_grid(ctx, p.m_tiles * p.n_tiles, p.n_tiles) : std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
   prof_begin(ctx, PROF_TENSOR);
-  halo_conv_kernel<BN><<<grid, 192, smem, ctx->stream>>>(a, b, p);
+  if (CL == 1) {
+    halo_conv_kernel<BN, CL><<<grid, 192, smem, ctx->stream>>>(a, b, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ZB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, halo_conv_kernel<BN, CL>, a, b, p));
+  }
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
@@ -1228,7 +1275,9 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (halo raster) failed (%d)", int(r)); return ZB_ERR_CUDA; }
   }
   const int taps = R * S;
-  int rc = make_map_2d(ctx, &mb, filt, static_cast<long long>(taps) * Cin, Kout, static_cast<long long>(taps) * Cin, 32, hp.bn);
+  // streamed filter + at least two row blocks: pairs of CTAs share every filter tile through TMA multicast (halo_conv_kernel CL = 2)
+  const int cl = (!hp.resident && hp.bn >= 64 && static_cast<long long>(N) * hp.p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 2 : 1;
+  int rc = make_map_2d(ctx, &mb, filt, static_cast<long long>(taps) * Cin, Kout, static_cast<long long>(taps) * Cin, 32, hp.bn / cl);
   if (rc != ZB_OK) return rc;
   UmmaParams p;
   init_params(p, ctx);
@@ -1258,11 +1307,27 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   finish_split_fields(p, 1);
   p.split_stride = 0;
   stat_attach(ctx, p, st, p.m_tiles * p.n_tiles, Kout, out, bias);
+  if (cl == 1) {
+    const int grid = p.stat_partial ? stat_grid(ctx, p.m_tiles * p.n_tiles, p.n_tiles) : std::min(p.m_tiles * p.n_tiles, ctx->sm_count);
+    switch (hp.bn) {
+      case 32: return halo_launch_bn<32, 1>(ctx, ma, mb, p, hp.smem, grid);
+      case 64: return halo_launch_bn<64, 1>(ctx, ma, mb, p, hp.smem, grid);
+      case 128: return halo_launch_bn<128, 1>(ctx, ma, mb, p, hp.smem, grid);
+      default: return halo_launch_bn<256, 1>(ctx, ma, mb, p, hp.smem, grid);
+    }
+  }
+  // clusters walk groups of `cl` row blocks; with fused statistics the cluster count is a multiple of n_tiles (one column block per CTA)
+  const int groups = ceil_div(p.m_tiles, cl) * p.n_tiles;
+  int clusters = std::min(groups, ctx->sm_count / cl);
+  if (p.stat_partial) {
+    clusters = std::max(p.n_tiles, clusters / p.n_tiles * p.n_tiles);
+    *st->rows = clusters / p.n_tiles * cl * 4;
+  }
+  const int grid = clusters * cl;
   switch (hp.bn) {
-    case 32: return halo_launch_bn<32>(ctx, ma, mb, p, hp.smem);
-    case 64: return halo_launch_bn<64>(ctx, ma, mb, p, hp.smem);
-    case 128: return halo_launch_bn<128>(ctx, ma, mb, p, hp.smem);
-    default: return halo_launch_bn<256>(ctx, ma, mb, p, hp.smem);
+    case 64: return halo_launch_bn<64, 2>(ctx, ma, mb, p, hp.smem, grid);
+    case 128: return halo_launch_bn<128, 2>(ctx, ma, mb, p, hp.smem, grid);
+    default: return halo_launch_bn<256, 2>(ctx, ma, mb, p, hp.smem, grid);
   }
 }
 
