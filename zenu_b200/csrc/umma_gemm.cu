@@ -811,7 +811,7 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // tiles of the epilogue = (image, output row) with rows padded to a multiple of TP per image; a scheduling step = TP rows
   const int p_groups = p.win_p_tiles / TP;                 // row groups per image
   const int groups = (p.m_tiles / TP);                     // = N * p_groups
-  const int sh = p.stride_h, dh = p.win_qblocks;           // (win_qblocks carries dil_h for this kernel)
+  const int sh = p.stride_h, dh = p.dg_dh;                 // filter-row dilation
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1795,7 +1795,7 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
       p.m_tiles = static_cast<int>(d->n * P_pad); p.n_tiles = 1;
       p.conv_P = static_cast<int>(g.P); p.conv_Q = static_cast<int>(g.Q);
       p.lower_h = -static_cast<int>(d->pad_h); p.stride_h = static_cast<int>(d->stride_h); p.stride_w = static_cast<int>(d->stride_w);
-      p.win_qblocks = static_cast<int>(d->dil_h);   // (this kernel reads dil_h from win_qblocks)
+      p.dg_dh = static_cast<int>(d->dil_h);
       p.ntaps = R; p.halo_slots = stages; p.kb_total = R;
       p.prof_flops = 2.0 * p.M * d->k * d->c * d->kh * d->kw;
       p.D = y; p.ldd = d->k; p.alpha = 1.f; p.beta = beta; p.bias = bias;
