@@ -1112,6 +1112,7 @@ void umma_set_chain_limit(int kb) { tl_chain_kb = kb; }
 int umma_chain_limit() { return tl_chain_kb; }
 int umma_conv_wgrad_halo(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);  // umma_wgrad.cu
 int umma_conv_stem_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);  // umma_stem_dgrad.cu
+int umma_conv_stem_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, long long, long long, long long, float*, int, int*);  // umma_stem_wgrad.cu
 
 static void init_params(UmmaParams& p, zb_ctx* ctx) {
   memset(&p, 0, sizeof(p));
@@ -1868,13 +1869,27 @@ int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   const long long tiles = static_cast<long long>(p.m_tiles) * p.tap_tiles;
   finish_split_fields(p, pick_splits(ctx, tiles, p.kb_total, 16));
   const long long rows = d->k, cols = static_cast<long long>(R) * 32;
-  const size_t part_bytes = (sizeof(float) * static_cast<size_t>(p.splits) * rows * cols + 1023) & ~size_t(1023);
+  const int max_parts = std::max(p.splits, ctx->sm_count);   // the strip-walking kernel writes one partial per CTA
+  const size_t part_bytes = (sizeof(float) * static_cast<size_t>(max_parts) * rows * cols + 1023) & ~size_t(1023);
   void* ws = nullptr;
   int rc = ctx_workspace(ctx, g.xp_bytes + part_bytes, &ws);
   if (rc != ZB_OK) return rc;
   float* xp = static_cast<float*>(ws);
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + g.xp_bytes);
   if ((rc = smallc_pack_input(ctx, d, g, x, x_nchw, xp)) != ZB_OK) return rc;
+  if (fold == R && p.chain_kb == 0) {   // column strips walked down the output rows, window boxes reused (umma_stem_wgrad.cu)
+    int parts = 0;
+    rc = umma_conv_stem_wgrad(ctx, d, dy, xp, g.Wp, g.P, g.Q, part, max_parts, &parts);
+    if (rc == ZB_OK) {
+      const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
+      smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                            static_cast<int>(d->kw), static_cast<int>(d->c), parts,
+                                                                            rows * cols, beta);
+      ZB_LAUNCH_CHECK(ctx);
+      return ZB_OK;
+    }
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
+  }
   CUtensorMap ma, mb;
   if ((rc = make_map_2d(ctx, &ma, dy, d->k, NPQ, d->k, 32, kUmmaBK, true)) != ZB_OK) return rc;
   if ((rc = make_map_window(ctx, &mb, xp, d->n, d->h, g.Wp, g.Q, static_cast<int>(d->stride_w), 32, 1, true)) != ZB_OK) return rc;
