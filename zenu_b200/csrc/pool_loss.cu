@@ -313,12 +313,19 @@ __global__ void __launch_bounds__(256) gap_bwd_kernel(const T* __restrict__ dy, 
                                                       long long HW, int nhwc) {
   const long long total = N * C * HW;
   const T inv = T(1) / static_cast<T>(HW);
+  if (nhwc && total < (1ll << 31)) {   // 32-bit index math: this kernel is pure address arithmetic around one store
+    const int c_n = static_cast<int>(C), chw = static_cast<int>(C * HW), tot = static_cast<int>(total);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+      const int n = i / chw, c = i % c_n;
+      dx[i] = dy[n * c_n + c] * inv;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     long long n, c;
     if (nhwc) { c = i % C; n = i / (C * HW); } else { const long long nc = i / HW; c = nc % C; n = nc / C; }
-    dx[i] = dy[n * C + c] / static_cast<T>(HW);
-    (void)inv;
+    dx[i] = dy[n * C + c] * inv;
   }
 }
 

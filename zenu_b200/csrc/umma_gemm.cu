@@ -1061,8 +1061,14 @@ static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensor
 // Chooses a split-K factor so that a problem with few output tiles still fills the SMs.
 static int pick_splits(zb_ctx* ctx, long long tiles, int kb_total, int min_kb_per_split) {
   if (tiles >= ctx->sm_count || kb_total < 2 * min_kb_per_split) return 1;
-  // largest factor that keeps tiles * splits within two full waves of the persistent grid (never 2 waves + a tail)
-  long long want = (2ll * ctx->sm_count) / tiles;
+  // largest factor that keeps tiles * splits within ONE full wave of the persistent grid: two waves halve the K range per CTA
+  // but double the partial-buffer traffic (write + deterministic reduce), which measured slower (wgrad 6.97 -> 6.74 ms / step)
+  static int waves = -1;   // tuning knob: ZENU_B200_SPLIT_WAVES
+  if (waves < 0) {
+    const char* e = getenv("ZENU_B200_SPLIT_WAVES");
+    waves = e ? std::max(1, atoi(e)) : 1;
+  }
+  long long want = (static_cast<long long>(waves) * ctx->sm_count) / tiles;
   long long cap = kb_total / min_kb_per_split;
   long long s = std::max(1ll, std::min(want, cap));
   return static_cast<int>(std::min<long long>(s, 2ll * ctx->sm_count));
