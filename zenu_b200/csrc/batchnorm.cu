@@ -68,7 +68,12 @@ static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
   g.tx = tx;
   g.ty = 256 / tx;
   g.col_groups = static_cast<int>((g.cvecs + tx - 1) / tx);
-  long long max_slabs = std::max<long long>(1, (ctx->sm_count * 8ll) / g.col_groups);
+  static int ctas_per_sm = -1;   // CTAs per SM the grid is sized for (tuning knob: ZENU_B200_BN_CTAS)
+  if (ctas_per_sm < 0) {
+    const char* e = getenv("ZENU_B200_BN_CTAS");
+    ctas_per_sm = e ? std::min(8, std::max(1, atoi(e))) : 8;
+  }
+  long long max_slabs = std::max<long long>(1, (ctx->sm_count * static_cast<long long>(ctas_per_sm)) / g.col_groups);
   static int rows_per_thread = -1;   // rows each thread walks per slab (tuning knob: ZENU_B200_BN_ROWS)
   if (rows_per_thread < 0) {
     const char* e = getenv("ZENU_B200_BN_ROWS");
