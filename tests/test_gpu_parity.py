@@ -176,6 +176,8 @@ CONV_CASES = [
     (2, 3, 21, 19, 32, 5, 5, 2, 2, 1),     # small-C (stem) kernels: odd sizes, 5x5 s2
     (1, 4, 30, 40, 64, 3, 3, 1, 1, 1),     # small-C, C = 4, stride 1, two k chunks
     (2, 2, 17, 23, 32, 7, 7, 3, 3, 1),     # small-C, stride 3
+    (1, 3, 18, 70, 128, 3, 3, 1, 2, 1),    # small-C, 128 output channels (4 dY boxes), three 32-pixel runs per row
+    (2, 3, 12, 12, 96, 5, 5, 2, 1, 1),     # small-C, 96 output channels (ragged k tile), stride 1
 ]
 
 
