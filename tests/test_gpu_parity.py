@@ -346,6 +346,52 @@ def test_gemm_vs_oracle(zb, ctx, ta, tb, math, shape):
     ctx.check()
 
 
+# CTA-pair (tcgen05 cta_group::2) launches: BN = 256 tiles, an even number of 128-row blocks and >= 16 K blocks per tile.  Ragged M / N / K,
+# the ring wrapping several times, every operand-major combination (the MN-major forms are what wgrad and the pointwise dgrad use),
+# alpha / beta through the deep old-tile variant, and the three math modes (3xTF32 adds the chained accumulator flushes).
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("math", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("shape", [(512, 256, 512), (500, 200, 520), (1024, 512, 2048), (256, 1000, 1024)])
+def test_gemm_cta_pair_shapes(zb, ctx, ta, tb, math, shape):
+    m, n, k = shape
+    rng = np.random.default_rng(7 * m + 3 * n + k)
+    a = rng.standard_normal((k, m) if ta else (m, k)).astype(np.float32)
+    b = rng.standard_normal((n, k) if tb else (k, n)).astype(np.float32)
+    c0 = rng.standard_normal((m, n)).astype(np.float32)
+    ref = zo.gemm(a.astype(np.float64), b.astype(np.float64), ta, tb, 1.0, 0.0, c0.astype(np.float64))
+    got = zb.gemm(ctx, dev(a), dev(b), ta, tb, 1.0, 0.0, None, math=math_of(zb, math))
+    assert rel_err(host(got), ref) < TOL[math]
+    ref = zo.gemm(a.astype(np.float64), b.astype(np.float64), ta, tb, 0.5, 0.25, c0.astype(np.float64))
+    got = zb.gemm(ctx, dev(a), dev(b), ta, tb, 0.5, 0.25, dev(c0), math=math_of(zb, math))
+    assert rel_err(host(got), ref) < TOL[math]
+    ctx.check()
+
+
+# convolutions that run on CTA pairs: pointwise 512 -> 256 (fprop: K-major filter; dgrad of 256 -> 512: MN-major filter),
+# a strided 3x3 through im2col loads (fprop, the dgrad parity classes with enough taps), wgrad with MN-major im2col loads
+@pytest.mark.parametrize("case", [(2, 512, 14, 14, 256, 1, 0, 1), (2, 256, 14, 14, 512, 1, 0, 1), (4, 256, 15, 17, 256, 3, 1, 2),
+                                  (3, 512, 9, 9, 512, 1, 0, 2)])
+def test_conv_cta_pair_shapes(zb, ctx, case):
+    from zenu_b200 import ZB_NHWC
+    n, c, h, w, k, r, pad, stride = case
+    rng = np.random.default_rng(99 + sum(case))
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+    y_ref = zo.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), pad, stride, 1)
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    dx_ref = zo.conv2d_bkwd_data(dy.astype(np.float64), wt.astype(np.float64), x.shape, pad, stride, 1)
+    dw_ref = zo.conv2d_bkwd_filter(dy.astype(np.float64), x.astype(np.float64), wt.shape, pad, stride, 1)
+    X, W, DY = dev(nhwc(x)), dev(nhwc(wt)), dev(nhwc(dy))
+    m = math_of(zb, "tf32")
+    y = zb.conv_fwd(ctx, X, W, pad, stride, 1, layout=ZB_NHWC, math=m)
+    assert rel_err(nchw(host(y)), y_ref) < TOL["tf32"]
+    dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, stride, 1, layout=ZB_NHWC, math=m)
+    assert rel_err(nchw(host(dx)), dx_ref) < TOL["tf32"]
+    dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, stride, 1, layout=ZB_NHWC, math=m)
+    assert rel_err(nchw(host(dw)), dw_ref) < TOL["tf32"]
+    ctx.check()
+
+
 @pytest.mark.parametrize("math", ["tf32", "tf32x3", "fp32"])
 def test_linear_vs_oracle(zb, ctx, math):
     rng = np.random.default_rng(11)

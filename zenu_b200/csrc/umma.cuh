@@ -118,6 +118,36 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of every 
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cluster address of `local` (a shared::cta address of this CTA's window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {   // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier of this CTA that is arrived on from another CTA of the cluster (acquire at cluster scope), bounded
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > ZB_MBAR_TIMEOUT_CYCLES || (err_flag && *err_flag)) {
+      if (err_flag) *err_flag = 1;
+      return false;
+    }
+  }
+}
+
 // 2-D tiled load delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of cta_mask
 __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                       uint16_t cta_mask) {
@@ -125,6 +155,18 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUte
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+// im2col-mode load delivered to every CTA of cta_mask (same smem offset, same mbarrier offset)
+__device__ __forceinline__ void tma_load_im2col_4d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                             int n, uint16_t off_w, uint16_t off_h, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+        "h"(off_h), "h"(cta_mask)
       : "memory");
 }
 
@@ -177,6 +219,53 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+
+// ---- CTA pair (cta_group::2): one M = 256 MMA spans two CTAs of a cluster; A comes from each CTA's own smem (its 128 rows), B
+// is split (each CTA holds N/2 rows at the same smem offset), D lands in each CTA's own TMEM.  Issued by the leader (rank 0) only.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one full warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this smem offset in both CTAs of the pair once all previously issued MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+// TMA loads of a CTA pair: the data lands in this CTA's shared memory, the bytes are counted on an mbarrier that may live in the
+// peer CTA (`bar_cluster_addr` is a shared::cluster address, e.g. mapa_shared(smem_u32(bar), 0) = the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c, int w,
+                                                        int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+        "h"(off_h)
+      : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <- lane base+i).

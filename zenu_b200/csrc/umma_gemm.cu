@@ -29,10 +29,10 @@ namespace zb {
 using namespace ptx;
 
 constexpr int kOldDepth = 3;   // 32-column chunks of the old output tile in flight per epilogue warp (beta != 0 launches)
-template <int BN, int STAGES, bool OLD = false>
+template <int BN, int STAGES, bool OLD = false, int CL = 1>
 struct UmmaSmem {
   static constexpr int A_BYTES = kUmmaBM * kUmmaBK * 4;  // 16 KB
-  static constexpr int B_BYTES = BN * kUmmaBK * 4;
+  static constexpr int B_BYTES = (BN / CL) * kUmmaBK * 4;   // CTA pair (CL = 2): each CTA holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;   // 4 warps x [32 rows][32 cols] fp32 staging (coalesced stores)
   static constexpr int EPI_BYTES = 4 * 4096;
@@ -43,7 +43,8 @@ struct UmmaSmem {
   static constexpr int BAR_OFFSET = OLD_OFFSET + OLD_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // a pair always takes the whole TMEM so that both CTAs get the same base (the leader's MMA addresses both with one column offset)
+  static constexpr int TMEM_COLS = CL > 1 ? 512 : (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
 struct TileCoord {
@@ -58,6 +59,20 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
   tile /= p.tap_tiles;
   t.m_blk = tile % p.m_tiles;
   t.split = tile / p.m_tiles;
+  return t;
+}
+
+// Cluster walk (CL CTAs on CL consecutive row blocks of the same column block / tap / split): work item q of the cluster ->
+// this CTA's tile.  m_tiles need not be a multiple of CL for the halo kernel (a row block past the end is a dummy).
+__device__ __forceinline__ TileCoord decode_tile_cluster(const UmmaParams& p, int q, int cl, int rank) {
+  TileCoord t;
+  const int m_groups = (p.m_tiles + cl - 1) / cl;
+  t.n_blk = q % p.n_tiles;
+  q /= p.n_tiles;
+  t.tap = q % p.tap_tiles;
+  q /= p.tap_tiles;
+  t.m_blk = (q % m_groups) * cl + rank;
+  t.split = q / m_groups;
   return t;
 }
 
@@ -79,7 +94,9 @@ template <int BN>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
                                               bool halo = false, uint8_t* old_smem = nullptr, int n_acc = 2, int group = 1,
-                                              int cluster = 1) {
+                                              int cluster = 1, bool pair_mma = false) {
+  // pair_mma: the accumulators are written by the cta_group::2 MMAs of the cluster's leader CTA (rank 0), which waits for the
+  // epilogues of BOTH CTAs before it overwrites a TMEM buffer: every warp releases a buffer on the leader's tempty barrier
   // cluster > 1 (halo kernel with multicast filter tiles): the CTAs of a cluster walk tile groups in lockstep: group q ->
   // column block q % n_tiles, row block (q / n_tiles) * cluster + rank; a row block past the end is a dummy (nothing stored)
   // n_acc TMEM accumulators of BN columns are drained in rotation; a CTA takes tiles in groups of `group` consecutive ids
@@ -113,7 +130,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     }
     const int groups = total_tiles / group;
     const int cl_id = blockIdx.x / cluster, n_cl = gridDim.x / cluster, cl_rank = blockIdx.x % cluster;
-    const int cl_groups = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles;
+    const int cl_groups = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles * p.tap_tiles * p.splits;
     for (int step = 0;; ++step) {
       TileCoord tc;
       bool tile_exists = true;
@@ -124,10 +141,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       } else {
         const int q = cl_id + step * n_cl;
         if (q >= cl_groups) break;
-        tc.n_blk = q % p.n_tiles;
-        tc.m_blk = (q / p.n_tiles) * cluster + cl_rank;
-        tc.tap = 0;
-        tc.split = 0;
+        tc = decode_tile_cluster(p, q, cluster, cl_rank);
         tile_exists = tc.m_blk < p.m_tiles;
       }
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
@@ -376,7 +390,9 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       if (full) chunk_loop(FullTag<true>{}); else chunk_loop(FullTag<false>{});
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (pair_mma) mbar_arrive_remote(mapa_shared(smem_u32(&tempty_bar[acc]), 0)); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
       if (dead) break;
@@ -396,11 +412,19 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     }
 }
 
-template <int BN, int STAGES, bool OLD = false>
+// CL = 2: CTA pairs (clusters of two CTAs, tcgen05 cta_group::2).  The pair owns a 256 x BN tile: each CTA loads its own 128 rows of
+// A and HALF of the B tile into its own shared memory, the leader (rank 0) issues M = 256 MMAs that read both shared memories and
+// write each CTA's 128 accumulator rows into that CTA's TMEM, and each CTA's epilogue drains its own TMEM.  A K block then costs a
+// CTA A + B/2 = 32 KB of TMA traffic into its shared memory instead of 48 KB (BN = 256): measured, an SM ingests at most ~70-80 B/clk
+// through TMA (tools/probes/tma_bw), and a private 128 x 256 fp32 tile needs 96 B/clk at the full tensor rate.  (Sharing B by TMA
+// multicast between two independent CTAs was measured first: it lowers the L2 reads but not the bytes an SM ingests, and bought
+// nothing.)  Barriers: both producers count their bytes on the LEADER's full barrier (cta_group::2 TMA loads), the leader's
+// tcgen05.commit is multicast onto both CTAs' empty / tmem-full barriers, both epilogues arrive on the leader's tmem-empty barrier.
+template <int BN, int STAGES, bool OLD = false, int CL = 1>
 __global__ void __launch_bounds__(192, 1)
 umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ UmmaParams p) {
-  using L = UmmaSmem<BN, STAGES, OLD>;
+  using L = UmmaSmem<BN, STAGES, OLD, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -426,20 +450,29 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull_bar[s], 1);
-        mbar_init(&tempty_bar[s], 4);
+        mbar_init(&tempty_bar[s], 4 * CL);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, L::TMEM_COLS);
-    tmem_relinquish();
+    if (CL == 1) {
+      tmem_alloc(tmem_slot, L::TMEM_COLS);
+      tmem_relinquish();
+    } else {
+      tmem_alloc_pair(tmem_slot, L::TMEM_COLS);
+      tmem_relinquish_pair();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
+  // work items: tiles (CL = 1), or pairs of row blocks walked by the cluster (m_tiles % CL == 0, checked by the host)
+  const int total_tiles = (p.m_tiles / CL) * p.n_tiles * p.tap_tiles * p.splits;
+  const int cl_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
   const bool a_mn = (p.a_mode == A_TILED_MN);
   const bool b_mn = (p.b_mode != B_TILED_K);
 
@@ -449,8 +482,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       const int pq = p.conv_P * p.conv_Q;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int tile = w_first; tile < total_tiles; tile += w_step) {
+        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank) : decode_tile(p, tile);
         const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
         int kb_begin, kb_end;
         tile_kb_range(p, tc, kb_begin, kb_end);
@@ -472,24 +505,36 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           a_n = tc.m_blk / p.dg_H;
           a_h = tc.m_blk - a_n * p.dg_H;                            // input row h of dX
         }
+        // MN-major operands come in 32-wide boxes; a pair CTA loads the boxes of its own half of the B tile (columns nB0 ...)
+        const int nB0 = n0 + cl_rank * (BN / CL);
         const int a_boxes = a_mn ? min(4, (p.M - m0 + 31) / 32) : 0;
-        const int b_boxes = b_mn ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
+        const int b_boxes = b_mn ? max(0, min(BN / CL / 32, (p.N - nB0 + 31) / 32)) : 0;
         const uint32_t a_bytes = a_mn ? a_boxes * 4096u
                                       : (p.a_mode == A_WINDOW_K ? uint32_t(p.win_box_q * p.win_box_p) * 128u
                                          : (p.a_mode == A_ROWS_K ? uint32_t(p.win_box_q) * 128u : uint32_t(L::A_BYTES)));
-        const uint32_t bytes = a_bytes + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
+        uint32_t bytes = a_bytes + (b_mn ? b_boxes * 4096u : uint32_t(L::B_BYTES));
+        if (CL > 1) {   // the leader's full barrier also counts what the peer (row block m0 + 128, second half of B) loads
+          const int pa = a_mn ? min(4, (p.M - (m0 + kUmmaBM) + 31) / 32) : 0;
+          const int pb = b_mn ? max(0, min(BN / CL / 32, (p.N - (n0 + BN / CL) + 31) / 32)) : 0;
+          bytes += (a_mn ? pa * 4096u : uint32_t(L::A_BYTES)) + (b_mn ? pb * 4096u : uint32_t(L::B_BYTES));
+        }
+        // cta_group::2 loads signal the barrier at this offset in the leader CTA
+        const uint32_t full0 = CL > 1 ? mapa_shared(smem_u32(full_bar), 0) : 0u;
         bool ok = true;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (!mbar_wait(&empty_bar[stage], phase ^ 1, err)) { ok = false; break; }
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          if (CL == 1 || cl_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], bytes);
           uint8_t* sA = smem + stage * L::STAGE_BYTES;
           uint8_t* sB = sA + L::A_BYTES;
+          const uint32_t fullp = full0 + stage * 8;
           // ---- A operand
           if (p.a_mode == A_TILED_K) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * kUmmaBK, m0);
+            if (CL == 1) tma_load_2d(sA, &tmA, &full_bar[stage], kb * kUmmaBK, m0);
+            else tma_load_2d_pair(sA, &tmA, fullp, kb * kUmmaBK, m0);
           } else if (p.a_mode == A_IM2COL_K) {
             const int tap = kb / p.c_chunks, c0 = (kb - tap * p.c_chunks) * kUmmaBK;
-            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
+            if (CL == 1) tma_load_im2col_4d(sA, &tmA, &full_bar[stage], c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
+            else tma_load_im2col_4d_pair(sA, &tmA, fullp, c0, a_w, a_h, a_n, p.tap_w[tap], p.tap_h[tap]);
           } else if (p.a_mode == A_ROWS_K) {
             const int i = kb / p.c_chunks;
             const int r = p.dg_r[(a_h + p.dg_ph) % p.dg_sh][i];
@@ -503,7 +548,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
               pix = row * p.conv_Q + qb * 32;
             }
-            for (int j = 0; j < a_boxes; ++j) tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, pix);
+            for (int j = 0; j < a_boxes; ++j) {
+              if (CL == 1) tma_load_2d(sA + j * 4096, &tmA, &full_bar[stage], m0 + 32 * j, pix);
+              else tma_load_2d_pair(sA + j * 4096, &tmA, fullp, m0 + 32 * j, pix);
+            }
           }
           // ---- B operand
           if (p.b_mode == B_TILED_K) {
@@ -515,9 +563,16 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int i = kb / p.c_chunks;
               k0 = p.dg_r[(a_h + p.dg_ph) % p.dg_sh][i] * p.b_tap_stride + (kb - i * p.c_chunks) * kUmmaBK;
             }
-            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+            if (CL == 1)
+              tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+            else   // this CTA's half of the tile rows (the map's box is BN / 2 rows)
+              tma_load_2d_pair(sB, &tmB, fullp, k0, nB0);
           } else if (p.b_mode == B_TILED_MN) {
-            for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK - p.dbg_b_shift);
+            if (CL == 1) {
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK - p.dbg_b_shift);
+            } else {
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(sB + j * 4096, &tmB, fullp, nB0 + 32 * j, kb * kUmmaBK);
+            }
           } else if (p.b_mode == B_WINDOW_MN) {  // K index = pixel (32-pixel run of one output row), N index = window element
             const int row = kb / p.win_qblocks, qb = kb - row * p.win_qblocks;
             const int img = row / p.conv_P, pp = row - img * p.conv_P;
@@ -529,8 +584,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int img = pix / pq, rem = pix - img * pq;
             const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
             const int bw = p.lower_w + qq * p.stride_w, bh = p.lower_h + pp * p.stride_h;
-            for (int j = 0; j < b_boxes; ++j)
-              tma_load_im2col_4d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, bw, bh, img, p.tap_w[tc.tap], p.tap_h[tc.tap]);
+            if (CL == 1) {
+              for (int j = 0; j < b_boxes; ++j)
+                tma_load_im2col_4d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, bw, bh, img, p.tap_w[tc.tap], p.tap_h[tc.tap]);
+            } else {
+              for (int j = 0; j < b_boxes; ++j)
+                tma_load_im2col_4d_pair(sB + j * 4096, &tmB, fullp, nB0 + 32 * j, bw, bh, img, p.tap_w[tc.tap], p.tap_h[tc.tap]);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -539,23 +599,24 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    if ((CL == 1 || cl_rank == 0) && elect_one()) {   // pair: the leader issues for both CTAs
+      const uint32_t idesc = make_idesc_tf32(kUmmaBM * CL, BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
       // The issuing thread is on the critical path of small-N tiles (an N = 64 MMA is ~32 cycles of tensor work): descriptors are
-      // formed once per launch and advanced by adding to their 14-bit address field (smem addresses < 256 KB: no carry out).
+      // formed once per launch and advanced by adding to their 14-bit address field (smem addresses < 256 KB: no carry out; in a
+      // cluster the shared-window address of rank 1 carries the CTA rank in bit 24, which must not leak into the LBO field).
       const uint64_t a_desc0 = (a_mn ? make_smem_desc(0, 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(0, 16, 1024, kSmemLayoutSw128, p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0)) +
-                               ((smem_u32(smem) + (a_mn ? 0 : p.dbg_a_shift * 128)) >> 4);
+                               (((smem_u32(smem) & 0x3FFFFu) + (a_mn ? 0 : p.dbg_a_shift * 128)) >> 4);
       const uint64_t b_desc0 = (b_mn ? make_smem_desc(0, p.dbg_b_lbo ? p.dbg_b_lbo : 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(0, 16, 1024, kSmemLayoutSw128)) +
-                               ((smem_u32(smem) + L::A_BYTES + (b_mn ? p.dbg_b_shift * 128 : 0)) >> 4);
+                               (((smem_u32(smem) & 0x3FFFFu) + L::A_BYTES + (b_mn ? p.dbg_b_shift * 128 : 0)) >> 4);
       const uint32_t a_kstep = a_mn ? (1024 >> 4) : (32 >> 4), b_kstep = b_mn ? (1024 >> 4) : (32 >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int tile = w_first; tile < total_tiles; tile += w_step) {
+        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank) : decode_tile(p, tile);
         int kb_begin, kb_end;
         tile_kb_range(p, tc, kb_begin, kb_end);
         bool ok = true;
@@ -563,7 +624,10 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         do {   // one pass per accumulator flush (a single one unless chain_kb limits the chain length)
         const int sub_begin = kb;
         const int sub_end = p.chain_kb > 0 ? min(kb_end, kb + p.chain_kb) : kb_end;
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) { ok = false; break; }
+        if (!(CL == 1 ? mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err) : mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1, err))) {
+          ok = false;
+          break;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (; kb < sub_end; ++kb) {
@@ -571,15 +635,23 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t st_off = static_cast<uint32_t>(stage * L::STAGE_BYTES) >> 4;
           const uint64_t da = a_desc0 + st_off, db = b_desc0 + st_off;
-          umma_tf32(d_tmem, da, db, idesc, kb > sub_begin ? 1u : 0u);
-          umma_tf32(d_tmem, da + a_kstep, db + b_kstep, idesc, 1u);
-          umma_tf32(d_tmem, da + 2 * a_kstep, db + 2 * b_kstep, idesc, 1u);
-          umma_tf32(d_tmem, da + 3 * a_kstep, db + 3 * b_kstep, idesc, 1u);
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (CL == 1) {
+            umma_tf32(d_tmem, da, db, idesc, kb > sub_begin ? 1u : 0u);
+            umma_tf32(d_tmem, da + a_kstep, db + b_kstep, idesc, 1u);
+            umma_tf32(d_tmem, da + 2 * a_kstep, db + 2 * b_kstep, idesc, 1u);
+            umma_tf32(d_tmem, da + 3 * a_kstep, db + 3 * b_kstep, idesc, 1u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          } else {
+            umma_tf32_pair(d_tmem, da, db, idesc, kb > sub_begin ? 1u : 0u);
+            umma_tf32_pair(d_tmem, da + a_kstep, db + b_kstep, idesc, 1u);
+            umma_tf32_pair(d_tmem, da + 2 * a_kstep, db + 2 * b_kstep, idesc, 1u);
+            umma_tf32_pair(d_tmem, da + 3 * a_kstep, db + 3 * b_kstep, idesc, 1u);
+            umma_commit_pair(&empty_bar[stage]);  // ... in both CTAs
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (CL == 1) umma_commit(&tfull_bar[acc]); else umma_commit_pair(&tfull_bar[acc]);  // accumulator complete -> epilogue(s)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         } while (kb < kb_end);
@@ -587,14 +659,16 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, OLD ? smem + L::OLD_OFFSET : nullptr);
+    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, OLD ? smem + L::OLD_OFFSET : nullptr,
+                      2, 1, CL, CL > 1);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while the leader's MMAs may still read this CTA's smem or a peer signals its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, L::TMEM_COLS);
+    if (CL == 1) tmem_dealloc(tmem_base, L::TMEM_COLS); else tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -703,7 +777,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t aph = 0, bph = 0, acc_phase = 0;
       bool ok = true;
       if (resident) ok = mbar_wait(&b_full[0], 0, err);
-      const uint32_t a_addr0 = smem_u32(sA);
+      const uint32_t a_addr0 = smem_u32(sA) & 0x3FFFFu;   // (rank bits of a cluster CTA's shared-window address dropped)
       // descriptors advanced by integer adds on their address field (see umma_kernel): ~6 instructions per MMA instead of ~30
       const uint64_t a_desc0 = make_smem_desc(0, 16, 1024, kSmemLayoutSw128);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
@@ -1007,7 +1081,37 @@ struct StatRequest {   // optional fused-BN-statistics request of a conv fprop
   float* partial = nullptr;
   int* rows = nullptr;   // out: rows of [2][K] partials written (0 = the planner could not fuse them)
 };
-static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int tiles, long long kout, const float* y, const float* bias) {
+// CTA pairs (umma_kernel CL = 2, see the kernel): for the wide tiles, whose operand traffic into shared memory is what bounds them.
+// Measured (tools/yardstick_gemm.py, tools/bench_conv.py): 10-12 % faster where the main loop is what takes the time (BN = 256 and at
+// least 16 K blocks per tile: 50176 x 256 x 1024 0.067 -> 0.060 ms, 50176 x 512 x 1024 0.106 -> 0.094 ms), slower on the short-K,
+// output-bound problems (the two epilogues of a pair release their TMEM buffer together: 200704 x 512 x 128 0.095 -> 0.121 ms) and
+// neutral to slightly slower at BN = 128, so only the former run on pairs.
+static int pair_cl(const UmmaParams& p, int bn) {
+  static int mode = -1;   // ZENU_B200_PAIR: 0 = never, 1 = BN = 256 with >= 16 K blocks per tile (default), 2 = whenever legal (BN >= 128)
+  if (mode < 0) {
+    const char* e = getenv("ZENU_B200_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0 || bn < 128) return 1;
+  if (mode == 1 && (bn < 256 || p.kb_per_split < 16)) return 1;
+  if (p.m_tiles < 2 || (p.m_tiles & 1)) return 1;
+  if (p.a_mode != A_TILED_K && p.a_mode != A_IM2COL_K && p.a_mode != A_TILED_MN) return 1;
+  if (p.b_mode != B_TILED_K && p.b_mode != B_TILED_MN && p.b_mode != B_IM2COL_MN) return 1;
+  if (p.b_mode == B_TILED_K && p.hb_base == nullptr) return 1;
+  if (p.out_mode != OUT_ROWS && p.out_mode != OUT_SCATTER) return 1;
+  if (p.dbg_b_shift != 0 || p.dbg_a_shift != 0) return 1;
+  return 2;
+}
+// persistent grid of a launch: one CTA per SM (or per tile), a multiple of n_tiles (of cl * n_tiles) with fused statistics
+static int launch_grid(zb_ctx* ctx, const UmmaParams& p, int cl) {
+  const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
+  if (cl == 1) return p.stat_partial ? stat_grid(ctx, tiles, p.n_tiles) : std::min(tiles, ctx->sm_count);
+  int clusters = std::min(tiles / cl, ctx->sm_count / cl);
+  if (p.stat_partial) clusters = std::max(p.n_tiles, clusters / p.n_tiles * p.n_tiles);
+  return clusters * cl;
+}
+static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int tiles, long long kout, const float* y, const float* bias,
+                        int pair_bn = 0) {
   if (st == nullptr || st->partial == nullptr) return;
   *st->rows = 0;
   if (kout % 32 != 0 || p.chain_kb > 0 || p.splits > 1 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 ||
@@ -1015,7 +1119,7 @@ static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int t
     return;
   p.stat_partial = st->partial;
   p.stat_shift = st->shift;
-  *st->rows = stat_grid(ctx, tiles, p.n_tiles) / p.n_tiles * 4;
+  *st->rows = (pair_bn > 0 ? launch_grid(ctx, p, pair_cl(p, pair_bn)) : stat_grid(ctx, tiles, p.n_tiles)) / p.n_tiles * 4;
 }
 
 template <int BN, int STAGES, bool OLD = false>
@@ -1027,8 +1131,7 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
     ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles * p.tap_tiles * p.splits;
-  const int grid = p.stat_partial ? stat_grid(ctx, tiles, p.n_tiles) : std::min(tiles, ctx->sm_count);
+  const int grid = launch_grid(ctx, p, 1);
   // algorithmic FLOPs of this launch: 2 * M * N * K over all taps (K counted in 32-wide blocks as issued)
   prof_begin(ctx, PROF_TENSOR);
   umma_kernel<BN, STAGES, OLD><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
@@ -1037,12 +1140,58 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
   return ZB_OK;
 }
 
+// the same launch on CTA pairs; a K-major B map is re-encoded with a box of BN / 2 rows (each CTA fetches its half)
+template <int BN, int STAGES, bool OLD = false>
+static int launch_cfg_pair(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
+  using L = UmmaSmem<BN, STAGES, OLD, 2>;
+  static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES, OLD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  CUtensorMap b2 = b;
+  if (p.b_mode == B_TILED_K) {
+    const int rc = make_map_2d(ctx, &b2, p.hb_base, p.hb_inner, p.hb_outer, p.hb_pitch, 32, BN / 2);
+    if (rc != ZB_OK) return rc;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(launch_grid(ctx, p, 2));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  prof_begin(ctx, PROF_TENSOR);
+  ZB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_kernel<BN, STAGES, OLD, 2>, a, b2, p));
+  prof_end(ctx, PROF_TENSOR, p.prof_flops);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
+
+// K-major B operand [outer = N][inner = K]: records the matrix in p for launch_cfg_pair
+static int make_map_bk(zb_ctx* ctx, CUtensorMap* map, UmmaParams& p, const float* base, long long inner, long long outer,
+                       long long pitch_elems, int bn) {
+  p.hb_base = base; p.hb_inner = inner; p.hb_outer = outer; p.hb_pitch = pitch_elems;
+  return make_map_2d(ctx, map, base, inner, outer, pitch_elems, 32, bn);
+}
+
 static int pick_bn(long long n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
 
 static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   // launches whose epilogue reads the old output tile (beta != 0, chained 3xTF32 flushes): a shallower operand ring makes
   // room for the deep old-tile prefetch buffers (these are short-K, output-bound problems)
-  if ((p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && !ZB_ENV_FLAG("ZENU_B200_NO_DEEP_BETA")) {
+  const bool deep_old = (p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && !ZB_ENV_FLAG("ZENU_B200_NO_DEEP_BETA");
+  if (pair_cl(p, bn) == 2) {
+    if (deep_old) return bn == 128 ? launch_cfg_pair<128, 6, true>(ctx, a, b, p) : launch_cfg_pair<256, 4, true>(ctx, a, b, p);
+    return bn == 128 ? launch_cfg_pair<128, 8>(ctx, a, b, p) : launch_cfg_pair<256, 6>(ctx, a, b, p);
+  }
+  if (deep_old) {
     switch (bn) {
       case 32: return launch_cfg<32, 7, true>(ctx, a, b, p);
       case 64: return launch_cfg<64, 6, true>(ctx, a, b, p);
@@ -1169,7 +1318,7 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
   }
   if (rc != ZB_OK) return rc;
   if (trans_b) {  // B stored [n][k]
-    rc = make_map_2d(ctx, &mb, b, k, n, ldb, 32, bn);
+    rc = make_map_bk(ctx, &mb, p, b, k, n, ldb, bn);
     p.b_mode = B_TILED_K;
   } else {  // B stored [k][n]
     rc = make_map_2d(ctx, &mb, b, n, k, ldb, 32, kUmmaBK, true);
@@ -1381,7 +1530,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
     p.a_mode = A_IM2COL_K;
   }
   if (rc != ZB_OK) return rc;
-  rc = make_map_2d(ctx, &mb, w, static_cast<long long>(taps) * d->c, d->k, static_cast<long long>(taps) * d->c, 32, bn);
+  rc = make_map_bk(ctx, &mb, p, w, static_cast<long long>(taps) * d->c, d->k, static_cast<long long>(taps) * d->c, bn);
   if (rc != ZB_OK) return rc;
   p.b_mode = B_TILED_K;
   p.M = static_cast<int>(M);
@@ -1408,7 +1557,7 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
   p.D = y;
   p.ldd = d->k;
   finish_split_fields(p, 1);
-  if (beta == 0.f) stat_attach(ctx, p, &st, p.m_tiles * p.n_tiles, d->k, y, bias);
+  if (beta == 0.f) stat_attach(ctx, p, &st, p.m_tiles * p.n_tiles, d->k, y, bias, bn);
   return run_with_splits(ctx, bn, ma, mb, p, M, d->k, y, d->k, 1.f, beta, bias);
 }
 
@@ -1523,10 +1672,10 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     CUtensorMap ma, mb;
     rc = make_map_im2col(ctx, &ma, dy, d->n, P, Q, d->k, cp.lower_w, cp.lower_h, cp.upper_w, cp.upper_h, 1, 1, kUmmaBM);
     if (rc != ZB_OK) return rc;
-    rc = make_map_2d(ctx, &mb, wt, static_cast<long long>(cp.ntaps) * d->k, d->c, static_cast<long long>(cp.ntaps) * d->k, 32, bn);
-    if (rc != ZB_OK) return rc;
     UmmaParams p;
     init_params(p, ctx);
+    rc = make_map_bk(ctx, &mb, p, wt, static_cast<long long>(cp.ntaps) * d->k, d->c, static_cast<long long>(cp.ntaps) * d->k, bn);
+    if (rc != ZB_OK) return rc;
     const long long M = d->n * static_cast<long long>(cp.Ha) * cp.Wb;
     p.a_mode = A_IM2COL_K;
     p.b_mode = B_TILED_K;
