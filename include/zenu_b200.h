@@ -281,6 +281,12 @@ int zb_model_update(zb_model* m); /* Optimizer::update */
 /* forward_backward + update; if host_loss != NULL the loss is copied back (synchronises the stream) */
 int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
                         int64_t h, int64_t w, void* loss_dev, double* host_loss);
+/* CUDA-graph replay of zb_model_train_step (the reference rebuilds and walks its Rc<RefCell> tape every step,
+ * zenu-autograd/src/lib.rs:220-237): after two eager steps the step is captured from the compute stream once per distinct
+ * (buffers, shape) signature and replayed, NCCL bucket allreduces included.  Used with SGD and a ctx whose compute stream can be
+ * captured (not the legacy default stream); any other configuration keeps running eagerly. */
+int zb_model_set_graph(zb_model* m, int enable);
+int zb_model_graph_count(zb_model* m); /* step graphs captured so far (0: every step so far ran eagerly) */
 /* Per-node timing (CUDA events on the compute stream around every tape node, forward and backward).  dump writes one
  * line per distinct node key: "key\tcount\ttotal_ms\talgorithmic_flops\talgorithmic_bytes\n" (sums over count) and returns
  * the buffer size needed (call with buf == NULL to size it). */

@@ -176,6 +176,41 @@ def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol,
     ctx.close()
 
 
+@pytest.mark.parametrize("arch,n,hw,classes", [("small_cnn", 64, 32, 10), ("resnet18", 8, 64, 10)])
+def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes):
+    """zb_model_set_graph: the captured-and-replayed step is the same sequence of kernels as the eager step, so losses and
+    parameters agree bit for bit; two input buffers alternate (two captured signatures)."""
+    pkg, ops, nn = zb
+    xs = [torch.from_numpy(batch(n, hw, classes, 11 + i)[0]).cuda() for i in range(2)]
+    T = torch.from_numpy(batch(n, hw, classes, 11)[1]).cuda()
+    runs = []
+    side = torch.cuda.Stream()   # stream capture needs a real stream: the ctx adopts torch's current one
+    torch.cuda.synchronize()
+    for use_graph in (False, True):
+        with torch.cuda.stream(side):
+            ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+            model = nn.Model(ctx, arch, classes, seed=5)
+            model.set_optimizer("sgd", lr=1e-3)
+            if use_graph:
+                model.set_graph(True)
+            loss_buf = torch.empty((1,), dtype=torch.float32, device="cuda")
+            l0 = ctx.launch_count()
+            losses = [model.train_step(xs[i % 2], T, loss_out=loss_buf, read_loss=True) for i in range(9)]
+            launches = ctx.launch_count() - l0
+            ctx.check()
+            assert model.graph_count() == (2 if use_graph else 0)
+            params = {k: v["data"].clone() for k, v in model.named_parameters().items()}
+            runs.append((losses, params, launches))
+            model.close()
+            ctx.close()
+        torch.cuda.synchronize()
+    (la, pa, na), (lb, pb, nb) = runs
+    assert all(np.isfinite(la)) and la == lb
+    assert na == nb and na > 0
+    for k in pa:
+        assert torch.equal(pa[k], pb[k]), k
+
+
 def test_inference_mode_uses_running_stats(zb):
     pkg, ops, nn = zb
     ctx = ops.Context(math=pkg.ZB_MATH_FP32)

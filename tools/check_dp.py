@@ -60,11 +60,52 @@ def main():
         other = got.clone()
         dist.broadcast(other, 0)
         worst_sync = max(worst_sync, float((got - other).abs().max()))
-    stats = torch.tensor([worst_mean, worst_sync], device="cuda")
+    # ---- (3) the DP step replayed from a CUDA graph (bucket allreduces captured on the comm stream) == the eager DP step
+    def dp_ctx():
+        c = ops.Context(device=local)
+        u = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            b = (ctypes.c_ubyte * 128)()
+            ops.check(c.lib.zb_dp_unique_id(c.handle, b))
+            u = torch.tensor(list(b), dtype=torch.uint8)
+        u = u.cuda()
+        dist.broadcast(u, 0)
+        torch.cuda.current_stream().synchronize()
+        ops.check(c.lib.zb_dp_init(c.handle, bytes(u.cpu().tolist()), rank, world))
+        return c
+
+    finals, graphs = [], 0
+    side = torch.cuda.Stream()
+    for use_graph in (False, True):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            c = dp_ctx()
+            mm = nn.Model(c, arch, classes, seed=42, bucket_mb=1)
+            mm.set_optimizer("sgd", lr=lr)
+            if use_graph:
+                mm.set_graph(True)
+            lb = torch.zeros(1, device="cuda")
+            for _ in range(6):
+                mm.train_step(X, T, loss_out=lb)
+            c.check()
+            if use_graph:
+                graphs = mm.graph_count()
+            finals.append({k: v["data"].clone() for k, v in mm.named_parameters().items() if v["grad"] is not None})
+            mm.close(); c.close()
+        torch.cuda.synchronize()
+    worst_graph = 0.0
+    for k in finals[0]:
+        denom = float(finals[0][k].abs().max()) + 1e-12
+        worst_graph = max(worst_graph, float((finals[0][k] - finals[1][k]).abs().max()) / denom)
+        other = finals[1][k].clone()
+        dist.broadcast(other, 0)
+        worst_sync = max(worst_sync, float((finals[1][k] - other).abs().max()))
+    stats = torch.tensor([worst_mean, worst_sync, worst_graph, float(graphs)], device="cuda")
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     if rank == 0:
-        ok = float(stats[0]) < 1e-5 and float(stats[1]) == 0.0
-        print(json.dumps({"world": world, "params_vs_mean_gradient_max_rel": float(stats[0]), "rank_divergence_max_abs": float(stats[1]), "ok": ok}), flush=True)
+        ok = float(stats[0]) < 1e-5 and float(stats[1]) == 0.0 and float(stats[2]) < 1e-5 and int(stats[3]) == 1
+        print(json.dumps({"world": world, "params_vs_mean_gradient_max_rel": float(stats[0]), "rank_divergence_max_abs": float(stats[1]),
+                          "graph_vs_eager_max_rel": float(stats[2]), "step_graphs": int(stats[3]), "ok": ok}), flush=True)
     m.close(); ctx.close(); m0.close(); ctx0.close()
     dist.destroy_process_group()
 

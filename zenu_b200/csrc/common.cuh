@@ -82,6 +82,7 @@ namespace zb {
 // class 0 = tcgen05 implicit-GEMM / GEMM launches (work = algorithmic FLOPs),
 // class 1 = BatchNorm ops (work = algorithmic bytes), class 2 = other elementwise (bytes).
 enum ProfClass { PROF_TENSOR = 0, PROF_BN = 1, PROF_EWISE = 2, PROF_NUM = 3 };
+bool prof_active(zb_ctx* ctx);   // per-op timing is recording (events are being interleaved with the launches)
 void prof_begin(zb_ctx* ctx, int cls);
 void prof_end(zb_ctx* ctx, int cls, double work);
 

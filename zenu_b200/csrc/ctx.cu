@@ -18,6 +18,7 @@ struct ProfState {
   cudaEvent_t open[PROF_NUM] = {nullptr, nullptr, nullptr};
 };
 
+bool prof_active(zb_ctx* ctx) { return ctx->prof && ctx->prof->enabled; }
 void prof_begin(zb_ctx* ctx, int cls) {
   if (!ctx->prof || !ctx->prof->enabled) return;
   cudaEvent_t e;

@@ -40,6 +40,7 @@ void Allocator::free(void* p, size_t bytes) {
   free_[bytes].push_back(p);
 }
 void Allocator::release_cached() {
+  ++generation_;
   for (auto& kv : free_) {
     for (void* p : kv.second) { cudaFree(p); reserved_ -= kv.first; }
     kv.second.clear();

@@ -45,10 +45,13 @@ class Allocator {
   void free(void* p, size_t bytes);
   size_t bytes_reserved() const { return reserved_; }
   void release_cached();
+  // bumped whenever cached blocks went back to the driver: captured CUDA graphs that address them are stale
+  uint64_t generation() const { return generation_; }
  private:
   zb_ctx* ctx_;
   std::unordered_map<size_t, std::vector<void*>> free_;
   size_t reserved_ = 0;
+  uint64_t generation_ = 0;
 };
 
 struct Storage {

@@ -17,6 +17,23 @@ struct zb_model {
   Optimizer opt;
   bool opt_ready = false;
   Variable last_loss;
+  // CUDA-graph replay of the train step (zb_model_set_graph): one instantiated graph per distinct call signature
+  struct StepGraph {
+    const void* x; const void* t; void* loss_dev;
+    int64_t b, c, h, w;
+    uint64_t generation;        // Allocator::generation() at capture time
+    unsigned long long launches;  // kernels per replay (for zb_ctx_launch_count)
+    cudaGraphExec_t exec;
+  };
+  bool graph_enabled = false;
+  int eager_steps = 0;          // steps run eagerly since the last (re)configuration: capture starts after two
+  std::vector<StepGraph> graphs;
+  void* pinned_loss = nullptr;  // 8 bytes of pinned host memory: the loss read-back node of the graphs
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+    eager_steps = 0;
+  }
 };
 
 #define ZB_HOST_TRY(body)                                  \
@@ -69,6 +86,8 @@ int zb_model_destroy(zb_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->comm_stream);
   if (m->last_loss.defined()) m->last_loss.clear_grad();
+  m->drop_graphs();
+  if (m->pinned_loss) cudaFreeHost(m->pinned_loss);
   delete m;
   return ZB_OK;
 }
@@ -150,8 +169,85 @@ int zb_model_update(zb_model* m) {
   ZB_HOST_TRY({ m->opt.update(*m->rt, m->params); });
 }
 
+int zb_model_set_graph(zb_model* m, int enable) {
+  ZB_REQUIRE(m, "zb_model_set_graph: NULL model");
+  ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  m->drop_graphs();
+  m->graph_enabled = enable != 0;
+  if (m->graph_enabled && !m->pinned_loss) ZB_CHECK_CUDA(cudaMallocHost(&m->pinned_loss, 8));
+  return ZB_OK;
+}
+
+int zb_model_graph_count(zb_model* m) { return m ? static_cast<int>(m->graphs.size()) : 0; }
+
+// Train step through a CUDA graph.  The tape is dynamic (rebuilt by the host every step, like the reference's), but for a fixed
+// model, batch shape and buffer addresses it enqueues the same kernels with the same arguments: after two eager steps (the caching
+// allocator and the scratch arena have reached their steady state, every kernel attribute is set) the step is captured once from
+// the compute stream and replayed.  Data parallel: the bucket allreduces are captured with it (the comm stream forks from the
+// compute stream at each bucket's ready event and joins at the optimizer's wait).  Replay is used only where the host contributes
+// nothing per step: SGD (Adam's bias correction is a host-side function of the step count), no per-node profiling.  Returns 1 when the step was run from a graph, 0 when the caller should run it eagerly, < 0 on error.
+static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b, int64_t c, int64_t h, int64_t w, void* loss_dev,
+                            double* host_loss) {
+  zb_ctx* ctx = m->ctx;
+  if (!m->graph_enabled || m->opt.kind != OPT_SGD || !m->opt_ready || m->rt->prof.enabled || zb::prof_active(ctx))
+    return 0;
+  const size_t esz = m->rt->dtype == ZB_F64 ? 8 : 4;
+  const uint64_t gen = m->rt->alloc.generation();
+  zb_model::StepGraph* hit = nullptr;
+  for (auto& g : m->graphs)
+    if (g.x == x && g.t == t && g.loss_dev == loss_dev && g.b == b && g.c == c && g.h == h && g.w == w) hit = &g;
+  if (hit && hit->generation != gen) { m->drop_graphs(); hit = nullptr; }
+  if (!hit) {
+    if (m->eager_steps < 2) { ++m->eager_steps; return 0; }
+    if (m->graphs.size() >= 4) m->drop_graphs();   // callers rotating through many buffers: start over rather than grow
+    const unsigned long long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();            // e.g. the ctx runs on the legacy default stream, which cannot be captured
+      m->graph_enabled = false;
+      return 0;
+    }
+    int rc = zb_model_forward_backward(m, x, t, b, c, h, w, loss_dev);
+    if (rc == ZB_OK) rc = zb_model_update(m);
+    if (rc == ZB_OK && cudaMemcpyAsync(m->pinned_loss, m->last_loss->data.ptr, esz, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = ZB_ERR_CUDA;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    const unsigned long long captured = ctx->launches - l0;
+    ctx->launches = l0;
+    if (rc != ZB_OK || ce != cudaSuccess || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != ZB_OK) return rc < 0 ? rc : -rc;   // the step's own error (message already recorded)
+      m->graph_enabled = false;                    // this step cannot be captured: stay eager from now on
+      return 0;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); m->graph_enabled = false; return 0; }
+    m->graphs.push_back({x, t, loss_dev, b, c, h, w, m->rt->alloc.generation(), captured, exec});
+    hit = &m->graphs.back();
+  }
+  if (cudaGraphLaunch(hit->exec, ctx->stream) != cudaSuccess) {
+    zb::set_last_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return -ZB_ERR_CUDA;
+  }
+  ctx->launches += hit->launches;
+  if (host_loss) {
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      zb::set_last_error("train step graph: %s", cudaGetErrorString(cudaGetLastError()));
+      return -ZB_ERR_CUDA;
+    }
+    *host_loss = esz == 8 ? *static_cast<double*>(m->pinned_loss) : static_cast<double>(*static_cast<float*>(m->pinned_loss));
+  }
+  return 1;
+}
+
 int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h, int64_t w,
                         void* loss_dev, double* host_loss) {
+  const int g = train_step_graph(m, x_nchw, targets, batch, c, h, w, loss_dev, host_loss);
+  if (g == 1) return ZB_OK;
+  if (g < 0) return -g;
   int rc = zb_model_forward_backward(m, x_nchw, targets, batch, c, h, w, loss_dev);
   if (rc != ZB_OK) return rc;
   rc = zb_model_update(m);

@@ -114,11 +114,27 @@ class Model:
     def train_step(self, x, targets, loss_out=None, read_loss=False):
         """One optimisation step.  With read_loss the scalar loss is copied to the host (synchronises)."""
         n, c, h, w = x.shape
-        loss = loss_out if loss_out is not None else torch.empty((1,), dtype=self.dtype, device=x.device)
+        if loss_out is not None:
+            loss = loss_out
+        elif getattr(self, "_graph", False):   # graph replay is keyed by the buffer addresses: one persistent loss scalar
+            if getattr(self, "_loss_buf", None) is None:
+                self._loss_buf = torch.empty((1,), dtype=self.dtype, device=x.device)
+            loss = self._loss_buf
+        else:
+            loss = torch.empty((1,), dtype=self.dtype, device=x.device)
         host = ctypes.c_double(0.0)
         check(self.lib.zb_model_train_step(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(targets.data_ptr()), n, c, h, w,
                                            ctypes.c_void_p(loss.data_ptr()), ctypes.byref(host) if read_loss else None))
         return host.value if read_loss else loss
+
+    def set_graph(self, enable=True):
+        """Replay `train_step` from a CUDA graph (captured after two eager steps; single GPU + SGD, otherwise stays eager)."""
+        check(self.lib.zb_model_set_graph(self._h, int(bool(enable))))
+        self._graph = bool(enable)
+
+    def graph_count(self):
+        """Number of step graphs captured so far (0 = every step ran eagerly)."""
+        return int(self.lib.zb_model_graph_count(self._h))
 
     def profile(self, enable=True):
         """Per-node CUDA-event timing of the tape (forward and backward nodes), see `profile_table`."""
