@@ -686,15 +686,21 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // slice from L2: 0.6-4.7 MB per tile, 8-14 TB/s of L2->SM traffic at the measured speeds), so each CTA fetches 1/CL of every
 // filter tile and TMA-multicasts it into all CL shared memories; a ring slot is refilled once the MMA warps of ALL CTAs have
 // released it (tcgen05.commit multicast onto every CTA's b_empty barrier).  Rasters stay private.
+// PAIR (with CL = 2): the two CTAs form a tcgen05 CTA pair instead (cta_group::2, see umma_kernel): each CTA lands its own raster and
+// HALF of every filter tile (BN / 2 rows) in its own shared memory, the leader issues M = 256 MMAs for both row blocks, commits are
+// multicast, both epilogues release TMEM on the leader's barrier.  One instruction then covers two row blocks, which is what the
+// N <= 128 layers need: a cta_group::1 MMA has an issue floor of 77 cycles whatever N is (41 % of the tensor rate at N = 64), a
+// cta_group::2 MMA one of 46 cycles for twice the rows (70 % at N = 64, 100 % at N = 128; tools/probes/mma_rate_2cta.cu).
 constexpr int kHaloMaxB = 24;
-template <int BN, int CL = 1>
+template <int BN, int CL = 1, bool PAIR = false>
 __global__ void __launch_bounds__(192, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ UmmaParams p) {
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_BYTES = BN * 128;
-  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;   // filter tile bytes in THIS CTA's shared memory
+  constexpr int TMEM_COLS = PAIR ? 512 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.halo_slots * p.halo_slot_bytes;
   const int epi_off = p.halo_slots * p.halo_slot_bytes + p.halo_b_stages * B_BYTES;
@@ -714,13 +720,18 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (elect_one()) {
       for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < kHaloMaxB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      for (int i = 0; i < kHaloMaxB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], PAIR ? 1 : CL); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 8 : 4); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -739,11 +750,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int ai = 0, bi = 0;
       uint32_t aph = 0, bph = 0;
-      if (resident) {  // the whole [BN][taps*C] filter slice, once per CTA (n_tiles == 1)
-        mbar_arrive_expect_tx(&b_full[0], static_cast<uint32_t>(taps * chunks) * B_BYTES);
+      const bool lead = !PAIR || cl_rank == 0;   // pair: both CTAs' loads are counted on the leader's barriers
+      const uint32_t afull0 = PAIR ? mapa_shared(smem_u32(a_full), 0) : 0u, bfull0 = PAIR ? mapa_shared(smem_u32(b_full), 0) : 0u;
+      constexpr uint32_t kShare = PAIR ? 2u : 1u;
+      if (resident) {  // the whole [BN][taps*C] filter slice, once per CTA (n_tiles == 1); pair: this CTA's half of the rows
+        if (lead) mbar_arrive_expect_tx(&b_full[0], kShare * static_cast<uint32_t>(taps * chunks) * B_BYTES);
         for (int c = 0; c < chunks; ++c)
-          for (int t = 0; t < taps; ++t)
-            tma_load_2d(sB + (c * taps + t) * B_BYTES, &tmB, &b_full[0], t * p.b_tap_stride + c * kUmmaBK, 0);
+          for (int t = 0; t < taps; ++t) {
+            if (PAIR) tma_load_2d_pair(sB + (c * taps + t) * B_BYTES, &tmB, bfull0, t * p.b_tap_stride + c * kUmmaBK, cl_rank * (BN / 2));
+            else tma_load_2d(sB + (c * taps + t) * B_BYTES, &tmB, &b_full[0], t * p.b_tap_stride + c * kUmmaBK, 0);
+          }
       }
       bool ok = true;
       for (int q = cl_id; q < total_q && ok; q += n_cl) {
@@ -752,14 +768,17 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int h0 = pt * p.win_box_p + p.lower_h;
         for (int c = 0; c < chunks && ok; ++c) {
           if (!mbar_wait(&a_empty[ai], aph ^ 1, err)) { ok = false; break; }
-          mbar_arrive_expect_tx(&a_full[ai], static_cast<uint32_t>(p.halo_raster_bytes));
-          tma_load_4d(sA + ai * p.halo_slot_bytes, &tmA, &a_full[ai], c * kUmmaBK, p.lower_w, h0, img);
+          if (lead) mbar_arrive_expect_tx(&a_full[ai], kShare * static_cast<uint32_t>(p.halo_raster_bytes));
+          if (PAIR) tma_load_4d_pair(sA + ai * p.halo_slot_bytes, &tmA, afull0 + ai * 8, c * kUmmaBK, p.lower_w, h0, img);
+          else tma_load_4d(sA + ai * p.halo_slot_bytes, &tmA, &a_full[ai], c * kUmmaBK, p.lower_w, h0, img);
           if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
           if (!resident) {
             for (int t = 0; t < taps; ++t) {
               if (!mbar_wait(&b_empty[bi], bph ^ 1, err)) { ok = false; break; }
-              mbar_arrive_expect_tx(&b_full[bi], B_BYTES);
-              if (CL == 1)
+              if (lead) mbar_arrive_expect_tx(&b_full[bi], kShare * B_BYTES);
+              if (PAIR)   // this CTA's half of the tile rows, into its own shared memory only
+                tma_load_2d_pair(sB + bi * B_BYTES, &tmB, bfull0 + bi * 8, t * p.b_tap_stride + c * kUmmaBK, n_blk * BN + cl_rank * (BN / 2));
+              else if (CL == 1)
                 tma_load_2d(sB + bi * B_BYTES, &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK, n_blk * BN);
               else   // this CTA's 1/CL of the tile rows (the map's box is BN / CL rows), delivered to every CTA of the cluster
                 tma_load_2d_multicast(sB + bi * B_BYTES + cl_rank * (B_BYTES / CL), &tmB, &b_full[bi], t * p.b_tap_stride + c * kUmmaBK,
@@ -771,8 +790,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, 0, 0);
+    if ((!PAIR || cl_rank == 0) && elect_one()) {   // pair: the leader issues for both CTAs
+      const uint32_t idesc = make_idesc_tf32(PAIR ? 2 * kUmmaBM : kUmmaBM, BN, 0, 0);
       int ai = 0, bi = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_phase = 0;
       bool ok = true;
@@ -785,7 +804,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < chunks && ok;) {   // one pass per accumulator flush (halo_chain channel chunks each)
         const int c_begin = c;
         const int c_end = p.halo_chain > 0 ? min(chunks, c + p.halo_chain) : chunks;
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err)) { ok = false; break; }
+        if (!(PAIR ? mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1, err) : mbar_wait(&tempty_bar[acc], acc_phase ^ 1, err))) {
+          ok = false;
+          break;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (; c < c_end && ok; ++c) {
@@ -802,20 +824,29 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               db = b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4));
             }
             const uint64_t da = a_slot + static_cast<uint32_t>(p.tap_w[t]) * 8u;   // tap = whole 128-byte rows
-            umma_tf32(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
-            umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
-            umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
+            if (PAIR) {
+              umma_tf32_pair(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_tf32_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_tf32_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
+            }
             if (!resident) {
-              if (CL == 1) umma_commit(&b_empty[bi]); else umma_commit_multicast(&b_empty[bi], kClMask);
+              if (PAIR) umma_commit_pair(&b_empty[bi]);
+              else if (CL == 1) umma_commit(&b_empty[bi]);
+              else umma_commit_multicast(&b_empty[bi], kClMask);
               if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
             }
           }
-          umma_commit(&a_empty[ai]);
+          if (PAIR) umma_commit_pair(&a_empty[ai]); else umma_commit(&a_empty[ai]);
           if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);
+        if (PAIR) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         }
@@ -823,14 +854,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true, nullptr, 2, 1, CL);
+    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true, nullptr, 2, 1, CL, PAIR);
   }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into this CTA or signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -1341,6 +1372,7 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
 // ---------------------------------------------------------------------------------------------- halo conv planner
 struct HaloPlan {
   int Wr, tp, p_tiles, slots, slot_bytes, raster_bytes, b_stages, resident, bn;
+  int pair;   // run on CTA pairs (halo_conv_kernel<BN, 2, true>): each CTA holds half of every filter tile
   size_t smem;
 };
 // in: [N][H][W][Cin] NHWC; filt: [Kout][R*S*Cin] (tap-major, channel-minor); out: [N][P][Q][Kout] with P = H + 2*ph - R + 1.
@@ -1360,11 +1392,14 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) return false;  // too many dead MMA rows
   hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles;
   hp->bn = pick_bn(Kout);
+  // CTA pairs: ZENU_B200_HALO_PAIR = 0 never, 1 (default) the N <= 128 layers (bound by the MMA issue rate), 2 every layer
+  static const int pair_mode = []() { const char* e = getenv("ZENU_B200_HALO_PAIR"); return e ? atoi(e) : 1; }();
+  hp->pair = (pair_mode > 0 && hp->bn >= 64 && (pair_mode > 1 || hp->bn <= 128) && N * p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 1 : 0;
   hp->raster_bytes = (tp + R - 1) * static_cast<int>(Wr) * 128;
   // rows a tap descriptor may touch beyond the raster ((R-1)*Wr + S-1 + 127 is the last row read) stay inside the slot
   const int last_row = (R - 1) * static_cast<int>(Wr) + (S - 1) + kUmmaBM;
   hp->slot_bytes = (std::max(hp->raster_bytes, last_row * 128) + 1023) & ~1023;
-  const int b_bytes = hp->bn * 128;
+  const int b_bytes = hp->bn * 128 / (hp->pair ? 2 : 1);
   const int chunks = static_cast<int>(Cin / 32);
   const int budget = 227 * 1024 - 1024 - 16384 - 48 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
   const int n_tiles = ceil_div(Kout, hp->bn);
@@ -1384,16 +1419,16 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   return true;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool PAIR = false>
 static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, size_t smem, int grid) {
   static size_t attr = 0;
   if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
   prof_begin(ctx, PROF_TENSOR);
   if (CL == 1) {
-    halo_conv_kernel<BN, CL><<<grid, 192, smem, ctx->stream>>>(a, b, p);
+    halo_conv_kernel<BN, CL, PAIR><<<grid, 192, smem, ctx->stream>>>(a, b, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -1407,7 +1442,7 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ZB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, halo_conv_kernel<BN, CL>, a, b, p));
+    ZB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, halo_conv_kernel<BN, CL, PAIR>, a, b, p));
   }
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
   ZB_LAUNCH_CHECK(ctx);
@@ -1432,7 +1467,7 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   }
   const int taps = R * S;
   // streamed filter + at least two row blocks: pairs of CTAs share every filter tile through TMA multicast (halo_conv_kernel CL = 2)
-  const int cl = (!hp.resident && hp.bn >= 64 && static_cast<long long>(N) * hp.p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 2 : 1;
+  const int cl = (hp.pair || (!hp.resident && hp.bn >= 64 && static_cast<long long>(N) * hp.p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER"))) ? 2 : 1;
   int rc = make_map_2d(ctx, &mb, filt, static_cast<long long>(taps) * Cin, Kout, static_cast<long long>(taps) * Cin, 32, hp.bn / cl);
   if (rc != ZB_OK) return rc;
   UmmaParams p;
@@ -1480,6 +1515,13 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
     *st->rows = clusters / p.n_tiles * cl * 4;
   }
   const int grid = clusters * cl;
+  if (hp.pair) {
+    switch (hp.bn) {
+      case 64: return halo_launch_bn<64, 2, true>(ctx, ma, mb, p, hp.smem, grid);
+      case 128: return halo_launch_bn<128, 2, true>(ctx, ma, mb, p, hp.smem, grid);
+      default: return halo_launch_bn<256, 2, true>(ctx, ma, mb, p, hp.smem, grid);
+    }
+  }
   switch (hp.bn) {
     case 64: return halo_launch_bn<64, 2>(ctx, ma, mb, p, hp.smem, grid);
     case 128: return halo_launch_bn<128, 2>(ctx, ma, mb, p, hp.smem, grid);
