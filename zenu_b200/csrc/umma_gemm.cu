@@ -1392,8 +1392,10 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) return false;  // too many dead MMA rows
   hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles;
   hp->bn = pick_bn(Kout);
-  // CTA pairs: ZENU_B200_HALO_PAIR = 0 never, 1 (default) the N <= 128 layers (bound by the MMA issue rate), 2 every layer
-  static const int pair_mode = []() { const char* e = getenv("ZENU_B200_HALO_PAIR"); return e ? atoi(e) : 1; }();
+  // CTA pairs: ZENU_B200_HALO_PAIR = 0 never, 1 only the N <= 128 layers, 2 (default) every layer.  Measured (tools/bench_conv.py --only
+  // 3x3, fprop / dgrad): 256 -> 256 @14x14 0.113 -> 0.101 / 0.116 -> 0.105 ms, 128 -> 128 @28x28 0.145 -> 0.137 / 0.149 -> 0.138,
+  // 64 -> 64 @56x56 0.211 -> 0.205 / 0.212 -> 0.205 (that layer is not bound by the MMA issue rate after all).
+  static const int pair_mode = []() { const char* e = getenv("ZENU_B200_HALO_PAIR"); return e ? atoi(e) : 2; }();
   hp->pair = (pair_mode > 0 && hp->bn >= 64 && (pair_mode > 1 || hp->bn <= 128) && N * p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 1 : 0;
   hp->raster_bytes = (tp + R - 1) * static_cast<int>(Wr) * 128;
   // rows a tap descriptor may touch beyond the raster ((R-1)*Wr + S-1 + 127 is the last row read) stay inside the slot
