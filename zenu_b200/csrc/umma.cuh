@@ -124,17 +124,21 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {   // release at cluster scope
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope) on purpose: what the waiting side needs
+// ordered are this thread's tcgen05 operations, which tcgen05.fence::before_thread_sync / after_thread_sync take care of; a
+// .release.cluster arrive compiles to an ERRBAR that waits for all of the warp's outstanding global stores (measured: ~1300 cycles
+// per epilogue tile, 17 % of the epilogue warps' time in the 64-channel halo kernel, and the reason short-K GEMMs lost on CTA pairs).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait on a barrier of this CTA that is arrived on from another CTA of the cluster (acquire at cluster scope), bounded
+// wait on a barrier of this CTA that is arrived on from another CTA of the cluster, bounded
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
   long long t0 = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)

@@ -1113,18 +1113,18 @@ struct StatRequest {   // optional fused-BN-statistics request of a conv fprop
   int* rows = nullptr;   // out: rows of [2][K] partials written (0 = the planner could not fuse them)
 };
 // CTA pairs (umma_kernel CL = 2, see the kernel): for the wide tiles, whose operand traffic into shared memory is what bounds them.
-// Measured (tools/yardstick_gemm.py, tools/bench_conv.py): 10-12 % faster where the main loop is what takes the time (BN = 256 and at
-// least 16 K blocks per tile: 50176 x 256 x 1024 0.067 -> 0.060 ms, 50176 x 512 x 1024 0.106 -> 0.094 ms), slower on the short-K,
-// output-bound problems (the two epilogues of a pair release their TMEM buffer together: 200704 x 512 x 128 0.095 -> 0.121 ms) and
-// neutral to slightly slower at BN = 128, so only the former run on pairs.
+// Measured (tools/yardstick_gemm.py, tools/bench_conv.py): 10-16 % faster from K = 256 up at BN = 256 (50176 x 1024 x 256 0.073 -> 0.061 ms,
+// 50176 x 512 x 1024 0.106 -> 0.093), still slower on the shortest-K, purely output-bound problems (the leader waits for the epilogues
+// of BOTH CTAs before it reuses a TMEM buffer: 200704 x 512 x 128 0.095 -> 0.103, 802816 x 256 x 64 0.192 -> 0.198) and neutral to
+// slightly slower at BN = 128, so only the former run on pairs.
 static int pair_cl(const UmmaParams& p, int bn) {
-  static int mode = -1;   // ZENU_B200_PAIR: 0 = never, 1 = BN = 256 with >= 16 K blocks per tile (default), 2 = whenever legal (BN >= 128)
+  static int mode = -1;   // ZENU_B200_PAIR: 0 = never, 1 = BN = 256 with >= 8 K blocks per tile (default), 2 = whenever legal (BN >= 128)
   if (mode < 0) {
     const char* e = getenv("ZENU_B200_PAIR");
     mode = e ? atoi(e) : 1;
   }
   if (mode == 0 || bn < 128) return 1;
-  if (mode == 1 && (bn < 256 || p.kb_per_split < 16)) return 1;
+  if (mode == 1 && (bn < 256 || p.kb_per_split < 8)) return 1;
   if (p.m_tiles < 2 || (p.m_tiles & 1)) return 1;
   if (p.a_mode != A_TILED_K && p.a_mode != A_IM2COL_K && p.a_mode != A_TILED_MN) return 1;
   if (p.b_mode != B_TILED_K && p.b_mode != B_TILED_MN && p.b_mode != B_IM2COL_MN) return 1;
