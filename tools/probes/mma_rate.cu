@@ -28,6 +28,9 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // mode: 0 = K-major, 4 K-steps per 128-byte row group, same accumulator; 1 = K-major, rotating over `nacc` accumulators;
 //       2 = MN-major, same accumulator; 3 = MN-major rotating; 4 = K-major but every MMA re-reads K-step 0 (same 32 bytes of each row)
+//       6 = K-major, 8 MMAs per loop trip with compile-time descriptor offsets (how few cycles can ONE thread spend per MMA?)
+//       5 = K-major, the A descriptor starts 0/1/2/58/59/60/116/117/118 rows (128 bytes each) into the tile, changing every 4 MMAs:
+//           the shifted-descriptor taps of the halo-reuse conv kernels (3x3 filter over a 58-pixel-wide raster)
 __global__ void __launch_bounds__(128, 1) probe(int n, int mode, int nacc, int iters, long long* cycles) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -49,17 +52,26 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int mode, int nacc, int i
   const uint32_t tm = tslot;
   if (threadIdx.x == 0) {
     const bool mn = mode == 2 || mode == 3;
-    const uint32_t a0 = su32(smem), b0 = su32(smem) + 16384;
+    const uint32_t a0 = su32(smem), b0 = su32(smem) + (mode == 5 ? 32768 : 16384);
+    const uint32_t taps[9] = {0, 1, 2, 58, 59, 60, 116, 117, 118};
     const uint64_t da0 = mn ? desc(a0, 4096, 512, 1) : desc(a0, 16, 1024, 2);
     const uint64_t db0 = mn ? desc(b0, 4096, 512, 1) : desc(b0, 16, 1024, 2);
     const uint32_t kstep = mn ? 64 : 2;
     const uint32_t id = idesc_tf32(128, n, mn, mn);
     const bool rotate = mode == 1 || mode == 3;
-    const long long t0 = clock64();
+    long long t0 = clock64();
+    if (mode == 6) {   // the leanest possible issue stream: 8 MMAs per loop trip, descriptors are compile-time offsets from two registers
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma(tm, da0 + (j & 3) * 2, db0 + (j & 3) * 2, id, (i + j) > 0 ? 1u : 0u);
+      }
+    } else
     for (int i = 0; i < iters; ++i) {
       const uint32_t k = mode == 4 ? 0 : (i & 3);
       const uint32_t d = tm + (rotate ? (i % nacc) * n : 0);
-      mma(d, da0 + k * kstep, db0 + k * kstep, id, i >= nacc ? 1u : 0u);
+      const uint32_t shift = mode == 5 ? taps[(i >> 2) % 9] * 8u : 0u;
+      mma(d, da0 + shift + k * kstep, db0 + k * kstep, id, i >= nacc ? 1u : 0u);
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(&bar)) : "memory");
     asm volatile("{\n.reg .pred P;\nW: mbarrier.try_wait.parity.shared::cta.b64 P, [%0], 0;\n@P bra D;\nbra W;\nD:\n}" ::"r"(su32(&bar)) : "memory");
@@ -78,10 +90,11 @@ int main() {
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   const int iters = 4096;
   const char* names[] = {"K-major SW128, same accumulator", "K-major SW128, rotating accumulators", "MN-major SW128/32B, same accumulator",
-                         "MN-major SW128/32B, rotating accumulators", "K-major, every MMA reads K-step 0"};
+                         "MN-major SW128/32B, rotating accumulators", "K-major, every MMA reads K-step 0",
+                         "K-major, A start shifted by 3x3 halo taps", "K-major, unrolled x8, constant descriptor offsets"};
   for (int grid : {1, sms}) {
     for (int n : {32, 64, 96, 128, 256}) {
-      for (int mode = 0; mode < 5; ++mode) {
+      for (int mode = 0; mode < 7; ++mode) {
         const int nacc = (mode == 1 || mode == 3) ? (512 / n >= 4 ? 4 : 512 / n) : 1;
         probe<<<grid, 128, 80 * 1024>>>(n, mode, nacc, iters, d);
         CK(cudaDeviceSynchronize());

@@ -26,7 +26,8 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) probe(int n, int iters, long long* cycles, int* status) {
+// shifted != 0: the A descriptor starts 0/1/2/58/59/60/116/117/118 rows into the tile, changing every 4 MMAs (halo-kernel taps)
+__global__ void __launch_bounds__(128, 1) probe(int n, int iters, long long* cycles, int* status, int shifted) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -50,13 +51,15 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int iters, long long* cyc
   const uint32_t tm = tslot;
   long long t0 = clock64();
   if (threadIdx.x == 0 && rank == 0) {
-    const uint32_t a0 = su32(smem), b0 = su32(smem) + 16384;
+    const uint32_t a0 = su32(smem), b0 = su32(smem) + (shifted ? 32768 : 16384);
+    const uint32_t taps[9] = {0, 1, 2, 58, 59, 60, 116, 117, 118};
     const uint64_t da0 = desc(a0, 16, 1024, 2), db0 = desc(b0, 16, 1024, 2);
     const uint32_t id = idesc_tf32(256, n);
     t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint32_t k = i & 3;
-      asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tm), "l"(da0 + k * 2),
+      const uint32_t shift = shifted ? taps[(i >> 2) % 9] * 8u : 0u;
+      asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tm), "l"(da0 + shift + k * 2),
                    "l"(db0 + k * 2), "r"(id), "r"(i > 0 ? 1u : 0u)
                    : "memory");
     }
@@ -91,6 +94,7 @@ int main() {
   CK(cudaMemset(st, 0, sizeof(int)));
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   const int iters = 4096;
+  for (int shifted : {0, 1})
   for (int grid : {2, sms / 2 * 2}) {
     for (int n : {32, 64, 128, 256}) {
       cudaLaunchConfig_t cfg = {};
@@ -101,7 +105,7 @@ int main() {
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, probe, n, iters, d, st));
+      CK(cudaLaunchKernelEx(&cfg, probe, n, iters, d, st, shifted));
       CK(cudaDeviceSynchronize());
       long long h[128];
       int hs = 0;
@@ -110,8 +114,8 @@ int main() {
       long long mx = 0;
       for (int i = 0; i < grid / 2; ++i) mx = h[i] > mx ? h[i] : mx;
       const double per = double(mx) / iters;
-      printf("grid %3d  M 256 (cta_group::2)  N %3d  %7.1f clk/MMA   (%5.1f %% of the pair's tensor rate)%s\n", grid, n, per, 100.0 * (n / 2.0) / per,
-             hs ? "  [TIMEOUT]" : "");
+      printf("grid %3d  M 256 (cta_group::2)  N %3d  %s %7.1f clk/MMA   (%5.1f %% of the pair's tensor rate)%s\n", grid, n,
+             shifted ? "A shifted by 3x3 halo taps" : "aligned operands          ", per, 100.0 * (n / 2.0) / per, hs ? "  [TIMEOUT]" : "");
     }
   }
   return 0;

@@ -800,6 +800,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // descriptors advanced by integer adds on their address field (see umma_kernel): ~6 instructions per MMA instead of ~30
       const uint64_t a_desc0 = make_smem_desc(0, 16, 1024, kSmemLayoutSw128);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
+      uint32_t tapoff[9];   // descriptor offset of tap t (whole 128-byte raster rows), in registers for the unrolled 3x3 path
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tapoff[t] = static_cast<uint32_t>(p.tap_w[t]) * 8u;
       for (int q = cl_id; q < total_q && ok; q += n_cl) {
         for (int c = 0; c < chunks && ok;) {   // one pass per accumulator flush (halo_chain channel chunks each)
         const int c_begin = c;
@@ -814,32 +817,59 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!mbar_wait(&a_full[ai], aph, err)) { ok = false; break; }
           tc_fence_after();
           const uint64_t a_slot = a_desc0 + ((a_addr0 + ai * p.halo_slot_bytes) >> 4);
-          for (int t = 0; t < taps; ++t) {
-            uint64_t db;
-            if (resident) {
-              db = b_desc0 + static_cast<uint32_t>((c * taps + t) * (B_BYTES >> 4));
-            } else {
-              if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
-              tc_fence_after();
-              db = b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4));
-            }
-            const uint64_t da = a_slot + static_cast<uint32_t>(p.tap_w[t]) * 8u;   // tap = whole 128-byte rows
+          // The issuing thread is the bottleneck of the small-N layers, not the tensor pipe: one thread needs ~45 cycles per
+          // tcgen05.mma when the descriptors are ready-made registers, but ~100 when every tap goes through a constant-memory table
+          // lookup, R2UR moves and loop control (tools/probes/mma_rate.cu: 98 -> 48 clk/MMA at N = 64, 98 -> 64 = the full tensor rate
+          // at N = 128).  3x3 filters therefore take a fully unrolled path: tap offsets held in registers, 36 MMAs back to back per
+          // channel chunk when the filter is resident.
+          auto mma4 = [&](uint64_t da, uint64_t db, uint32_t first_acc) {
             if (PAIR) {
-              umma_tf32_pair(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
+              umma_tf32_pair(d_tmem, da, db, idesc, first_acc);
               umma_tf32_pair(d_tmem, da + 2, db + 2, idesc, 1u);
               umma_tf32_pair(d_tmem, da + 4, db + 4, idesc, 1u);
               umma_tf32_pair(d_tmem, da + 6, db + 6, idesc, 1u);
             } else {
-              umma_tf32(d_tmem, da, db, idesc, (c > c_begin || t > 0) ? 1u : 0u);
+              umma_tf32(d_tmem, da, db, idesc, first_acc);
               umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
               umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
               umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
             }
-            if (!resident) {
-              if (PAIR) umma_commit_pair(&b_empty[bi]);
-              else if (CL == 1) umma_commit(&b_empty[bi]);
-              else umma_commit_multicast(&b_empty[bi], kClMask);
-              if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
+          };
+          auto b_release = [&]() {
+            if (PAIR) umma_commit_pair(&b_empty[bi]);
+            else if (CL == 1) umma_commit(&b_empty[bi]);
+            else umma_commit_multicast(&b_empty[bi], kClMask);
+            if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
+          };
+          if (taps == 9 && resident) {
+            uint64_t db = b_desc0 + static_cast<uint32_t>(c * 9 * (B_BYTES >> 4));
+            mma4(a_slot + tapoff[0], db, c > c_begin ? 1u : 0u);
+#pragma unroll
+            for (int t = 1; t < 9; ++t) {
+              db += B_BYTES >> 4;
+              mma4(a_slot + tapoff[t], db, 1u);
+            }
+          } else if (taps == 9) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
+              tc_fence_after();
+              mma4(a_slot + tapoff[t], b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4)), (c > c_begin || t > 0) ? 1u : 0u);
+              b_release();
+            }
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < taps; ++t) {
+              uint64_t db;
+              if (resident) {
+                db = b_desc0 + static_cast<uint32_t>((c * taps + t) * (B_BYTES >> 4));
+              } else {
+                if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
+                tc_fence_after();
+                db = b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4));
+              }
+              mma4(a_slot + static_cast<uint32_t>(p.tap_w[t]) * 8u, db, (c > c_begin || t > 0) ? 1u : 0u);   // tap = whole 128-byte rows
+              if (!resident) b_release();
             }
           }
           if (PAIR) umma_commit_pair(&a_empty[ai]); else umma_commit(&a_empty[ai]);
