@@ -134,11 +134,30 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t a_off = (smem0 + stage * p.stage_bytes) >> 4;
         const uint64_t da0 = a_desc0 + a_off;
         const uint64_t db0 = b_desc0 + a_off + static_cast<uint32_t>((p.a_boxes * p.a_box_bytes) >> 4);
-        for (int i = 0; i < ksteps; ++i) {
-          const uint64_t da = da0 + static_cast<uint32_t>(i * 64);
-          uint64_t db = db0 + static_cast<uint32_t>(i * 64);
-          const uint32_t accum = (tile > t_begin || i > 0) ? 1u : 0u;
-          for (int r = 0; r < p.R; ++r, db += row_step) umma_tf32(tmem_base + r * acc_cols, da, db, idesc, accum);
+        // One thread issues every MMA and its instruction stream is what bounds these N = S*32 <= 96 wide MMAs (~45 cycles per
+        // tcgen05.mma with ready-made descriptors, ~100 through a runtime-count inner loop: tools/probes/mma_rate.cu), so the
+        // 3-row filter gets a fully unrolled body: three MMAs per K step on precomputed descriptor offsets.
+        if (p.R == 3) {
+          const uint32_t t1 = tmem_base + acc_cols, t2 = tmem_base + 2 * acc_cols;
+          const uint64_t db1 = db0 + row_step, db2 = db0 + 2 * row_step;
+          const uint32_t first = tile > t_begin ? 1u : 0u;
+          umma_tf32(tmem_base, da0, db0, idesc, first);
+          umma_tf32(t1, da0, db1, idesc, first);
+          umma_tf32(t2, da0, db2, idesc, first);
+#pragma unroll 4
+          for (int i = 1; i < ksteps; ++i) {
+            const uint32_t o = static_cast<uint32_t>(i * 64);
+            umma_tf32(tmem_base, da0 + o, db0 + o, idesc, 1u);
+            umma_tf32(t1, da0 + o, db1 + o, idesc, 1u);
+            umma_tf32(t2, da0 + o, db2 + o, idesc, 1u);
+          }
+        } else {
+          for (int i = 0; i < ksteps; ++i) {
+            const uint64_t da = da0 + static_cast<uint32_t>(i * 64);
+            uint64_t db = db0 + static_cast<uint32_t>(i * 64);
+            const uint32_t accum = (tile > t_begin || i > 0) ? 1u : 0u;
+            for (int r = 0; r < p.R; ++r, db += row_step) umma_tf32(tmem_base + r * acc_cols, da, db, idesc, accum);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
