@@ -971,6 +971,7 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t idesc = make_idesc_tf32(kUmmaBM, BN, 0, 0);
       const uint32_t a0 = smem_u32(sA);
       const uint64_t db_first = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
+      const uint64_t da_base = make_smem_desc(a0, 16, 1024, kSmemLayoutSw128);   // + stage * 1024 (16 KB slots, 16-byte units)
       int stage = 0, set = 0;
       uint32_t phase = 0, set_phase = 0;
       bool ok = mbar_wait(b_bar, 0, err);
@@ -986,22 +987,37 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ih = ih_lo; ih <= ih_hi; ++ih) {
           if (!mbar_wait(&full_bar[stage], phase, err)) { ok = false; break; }
           tc_fence_after();
-          const uint64_t da0 = make_smem_desc(a0 + stage * 16384, 16, 1024, kSmemLayoutSw128);
-          int t = ih - ih_lo;                       // = r * dil_h for output row p0 (pl = 0); decreases by sh per row
-          for (int pl = 0; pl < TP; ++pl, t -= sh) {
-            int r = t;
-            if (dh != 1) {
-              if (t < 0 || t % dh != 0) continue;
-              r = t / dh;
+          const uint64_t da0 = da_base + static_cast<uint32_t>(stage * (16384 >> 4));
+          const int t0 = ih - ih_lo;                       // = r * dil_h for output row p0 (pl = 0); decreases by sh per row
+          if (dh == 1) {
+            // (the issuing thread bounds these N = BN <= 128 MMAs: unrolled over the TP rows, the accumulate flag is "not filter
+            // row 0" because every output row meets its filter rows in ascending order)
+#pragma unroll
+            for (int pl = 0; pl < TP; ++pl) {
+              const int r = t0 - pl * sh;
+              if (r >= 0 && r < R) {
+                const uint64_t db0 = db_first + static_cast<uint32_t>(r * (B_TILE >> 4));
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((set * TP + pl) * BN);
+                umma_tf32(d_tmem, da0, db0, idesc, r > 0 ? 1u : 0u);
+                umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
+              }
             }
-            if (r < 0 || r >= R) continue;
-            const uint64_t db0 = db_first + static_cast<uint64_t>(r * (B_TILE >> 4));
-            const uint32_t d_tmem = tmem_base + (set * TP + pl) * BN;
-            umma_tf32(d_tmem, da0, db0, idesc, (started >> pl) & 1u);
-            umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
-            umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
-            umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
-            started |= 1u << pl;
+          } else {
+            int t = t0;
+            for (int pl = 0; pl < TP; ++pl, t -= sh) {
+              if (t < 0 || t % dh != 0) continue;
+              const int r = t / dh;
+              if (r >= R) continue;
+              const uint64_t db0 = db_first + static_cast<uint64_t>(r * (B_TILE >> 4));
+              const uint32_t d_tmem = tmem_base + (set * TP + pl) * BN;
+              umma_tf32(d_tmem, da0, db0, idesc, (started >> pl) & 1u);
+              umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+              umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+              umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
+              started |= 1u << pl;
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.halo_slots) { stage = 0; phase ^= 1; }

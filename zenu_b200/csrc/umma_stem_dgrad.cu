@@ -98,6 +98,8 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t idesc = make_idesc_tf32(kUmmaBM, 32, 0, 0);
       const uint32_t a0 = smem_u32(sA);
       const uint64_t db_first = make_smem_desc(smem_u32(sB), 16, 1024, kSmemLayoutSw128);
+      const uint64_t da_base = make_smem_desc(a0, 16, 1024, kSmemLayoutSw128);   // + stage * 1024 (16 KB stages, address field in 16-byte units)
+      const uint32_t db_row_step = static_cast<uint32_t>(p.chunks * 256);         // next filter row of the transformed filter
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(b_bar, 0, err);
@@ -114,23 +116,34 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             // (the issuing thread is the critical path here: N = 32 MMAs retire faster than scalar code can describe them, so
             // descriptors are advanced by adding to their 14-bit address field and the dil_h == 1 case avoids the divisions)
-            const uint64_t da0 = make_smem_desc(a0 + stage * 16384, 16, 1024, kSmemLayoutSw128);
-            int t = h0 + p.ph - pr * p.sh;   // = r * dil_h for the filter row that links input row h0 + hl to dY row pr
-            for (int hl = 0; hl <= h1 - h0; ++hl, ++t) {
-              int r = t;
-              if (p.dh != 1) {
-                if (t < 0 || t % p.dh != 0) continue;
-                r = t / p.dh;
+            const uint64_t da0 = da_base + static_cast<uint32_t>(stage * (16384 >> 4));
+            const int t0 = h0 + p.ph - pr * p.sh;   // = r * dil_h for the filter row that links input row h0 to dY row pr
+            if (p.dh == 1) {
+              // rows of the tile this dY row reaches: 0 <= t0 + hl < R; one MMA group each, descriptors / TMEM address by adds
+              const int hl_lo = max(0, -t0), hl_hi = min(h1 - h0, p.R - 1 - t0);
+              uint64_t db0 = db_first + static_cast<uint32_t>(((t0 + hl_lo) * p.chunks + c) * 256);   // 4096-byte tiles, >> 4
+              uint32_t d_tmem = tmem_base + static_cast<uint32_t>((acc * kSdTH + hl_lo) * 32);
+              for (int hl = hl_lo; hl <= hl_hi; ++hl, db0 += db_row_step, d_tmem += 32) {
+                umma_tf32(d_tmem, da0, db0, idesc, (started >> hl) & 1u);
+                umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
               }
-              if (r < 0 || r >= p.R) continue;
-              const uint64_t db0 = db_first + static_cast<uint64_t>((r * p.chunks + c) * 256);   // 4096-byte tiles, >> 4
-              const uint32_t d_tmem = tmem_base + (acc * kSdTH + hl) * 32;
-              const uint32_t st = (started >> hl) & 1u;
-              umma_tf32(d_tmem, da0, db0, idesc, st);
-              umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
-              umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
-              umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
-              started |= 1u << hl;
+              if (hl_hi >= hl_lo) started |= ((2u << hl_hi) - 1u) & ~((1u << hl_lo) - 1u);
+            } else {
+              int t = t0;
+              for (int hl = 0; hl <= h1 - h0; ++hl, ++t) {
+                if (t < 0 || t % p.dh != 0) continue;
+                const int r = t / p.dh;
+                if (r >= p.R) continue;
+                const uint64_t db0 = db_first + static_cast<uint64_t>((r * p.chunks + c) * 256);
+                const uint32_t d_tmem = tmem_base + (acc * kSdTH + hl) * 32;
+                umma_tf32(d_tmem, da0, db0, idesc, (started >> hl) & 1u);
+                umma_tf32(d_tmem, da0 + 2, db0 + 2, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 4, db0 + 4, idesc, 1u);
+                umma_tf32(d_tmem, da0 + 6, db0 + 6, idesc, 1u);
+                started |= 1u << hl;
+              }
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
