@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE.json configs[4]: BatchNorm2d (+ReLU, +residual add) forward / backward bandwidth sweep, NHWC f32, tensors from 1 MB to
 2 GB, against the measured HBM copy bandwidth.  Algorithmic bytes / element: fwd 12 (+4 with residual); bwd 20 (BN+ReLU, mask
-recomputed from x), 32 with residual (x, dy, y read twice; dx, dres written).
+recomputed from x); with residual 24.25 through the 1-bit ReLU mask of the fused forward (what the model runs), 28 through y.
 Usage: python tools/bench_bn.py [--out gpurun_out/bn_sweep.json]"""
 import argparse
 import json
@@ -55,11 +55,17 @@ def main():
                 return sorted(ts)[len(ts) // 2]
             y, sm, si = ops.batch_norm_2d_forward_train(ctx, 0.9, x, sc, bi, rm, rv, layout=ZB_NHWC, relu=True)
             y2, sm2, si2 = ops.batch_norm_2d_forward_train(ctx, 0.9, x, sc, bi, rm, rv, layout=ZB_NHWC, residual=res, relu=True)
+            y3, sm3, si3, mask3 = ops.batch_norm_2d_forward_train_masked(ctx, 0.9, x, sc, bi, rm, rv, residual=res)
             cases = {
                 "fwd+relu": (12, lambda: ops.batch_norm_2d_forward_train(ctx, 0.9, x, sc, bi, rm, rv, layout=ZB_NHWC, relu=True)),
                 "fwd+relu+res": (16, lambda: ops.batch_norm_2d_forward_train(ctx, 0.9, x, sc, bi, rm, rv, layout=ZB_NHWC, residual=res, relu=True)),
                 "bwd+relu": (20, lambda: ops.batch_norm_2d_relu_backward(ctx, x, dy, sc, bi, sm, si, layout=ZB_NHWC)),
-                "bwd+relu+res": (32, lambda: ops.batch_norm_2d_backward(ctx, x, dy, sc, sm2, si2, layout=ZB_NHWC, y=y2, want_residual_grad=True)),
+                # what the model runs: the 1-bit ReLU mask written by the fused forward (x, dy, mask read; masked gradient written
+                # and re-read; x re-read; dx written: 6 passes + 2/32)
+                "bwd+relu+res": (24.25, lambda: ops.batch_norm_2d_backward_masked(ctx, x, dy, sc, sm3, si3, mask3)),
+                # the y-based form of the reference's separate nodes (7 passes)
+                "bwd+relu+res (y)": (28, lambda: ops.batch_norm_2d_backward(ctx, x, dy, sc, sm2, si2, layout=ZB_NHWC, y=y2, want_residual_grad=True)),
+                "fwd+relu+res+mask": (16.125, lambda: ops.batch_norm_2d_forward_train_masked(ctx, 0.9, x, sc, bi, rm, rv, residual=res)),
             }
             for name, (bpe, fn) in cases.items():
                 ms = timeit(fn)
@@ -68,7 +74,7 @@ def main():
             ctx.check()
             rows.append({"c": c, "shape": list(shape), "mbytes": numel * 4 / 1e6, **out})
             print(f"C={c:<5d} {numel * 4 / 1e6:8.1f} MB |" + "".join(f" {k} {v['gbs']:6.0f} GB/s {v['frac_of_hbm_peak'] * 100:5.1f}% |" for k, v in out.items()), flush=True)
-            del x, res, dy, y, y2
+            del x, res, dy, y, y2, y3
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:
         json.dump({"hbm_gbs": hbm, "peak_source": src, "l2": "256 MB scratch write between launches", "rows": rows}, f, indent=1)
