@@ -221,6 +221,16 @@ int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m,
                  double beta2, double eps, double weight_decay, int decay, int64_t step_t, double grad_scale,
                  int64_t n);
 
+/* The same update with the bias corrections 1/(1-beta1^t), 1/(1-beta2^t) read from a device table instead of being kernel
+ * arguments, so that a captured step (zb_model_set_graph) stays valid as t advances: entry i of `table` ([count][2], dtype) holds
+ * the corrections of step first_step + i (computed on the host with the reference's arithmetic, adam.rs:23-25) and the kernel
+ * uses entry *step_index (device int32); zb_adam_advance adds 1 to it after the step's last launch. */
+int zb_adam_table_fill(zb_ctx* ctx, int dtype, double beta1, double beta2, int64_t first_step, int64_t count, void* table);
+int zb_adam_step_table(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m, void* v, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, int decay, const void* table,
+                       const int32_t* step_index, double grad_scale, int64_t n);
+int zb_adam_advance(zb_ctx* ctx, int32_t* step_index);
+
 /* ---- data parallel (new; the reference has no multi-GPU path) -------------------------
  * One process per GPU.  Rank 0 calls zb_dp_unique_id (128 bytes, host), ships it to the others through
  * whatever rendezvous the host has (torch.distributed / a file), then every rank calls zb_dp_init.
@@ -283,8 +293,8 @@ int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_one
                         int64_t h, int64_t w, void* loss_dev, double* host_loss);
 /* CUDA-graph replay of zb_model_train_step (the reference rebuilds and walks its Rc<RefCell> tape every step,
  * zenu-autograd/src/lib.rs:220-237): after two eager steps the step is captured from the compute stream once per distinct
- * (buffers, shape) signature and replayed, NCCL bucket allreduces included.  Used with SGD and a ctx whose compute stream can be
- * captured (not the legacy default stream); any other configuration keeps running eagerly. */
+ * (buffers, shape) signature and replayed, NCCL bucket allreduces included.  Needs a ctx whose compute stream can be captured
+ * (not the legacy default stream); otherwise, and while per-node profiling is on, steps keep running eagerly. */
 int zb_model_set_graph(zb_model* m, int enable);
 int zb_model_graph_count(zb_model* m); /* step graphs captured so far (0: every step so far ran eagerly) */
 /* Per-node timing (CUDA events on the compute stream around every tape node, forward and backward).  dump writes one

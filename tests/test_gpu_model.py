@@ -176,8 +176,9 @@ def test_train_steps_match_oracle(zb, arch, n, hw, classes, math, opt, lr, ltol,
     ctx.close()
 
 
-@pytest.mark.parametrize("arch,n,hw,classes", [("small_cnn", 64, 32, 10), ("resnet18", 8, 64, 10)])
-def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes):
+@pytest.mark.parametrize("arch,n,hw,classes,opt", [("small_cnn", 64, 32, 10, "sgd"), ("resnet18", 8, 64, 10, "sgd"),
+                                                   ("small_cnn", 16, 32, 10, "adamw"), ("resnet18", 4, 64, 10, "adam")])
+def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes, opt):
     """zb_model_set_graph: the captured-and-replayed step is the same sequence of kernels as the eager step, so losses and
     parameters agree bit for bit; two input buffers alternate (two captured signatures)."""
     pkg, ops, nn = zb
@@ -190,7 +191,7 @@ def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes):
         with torch.cuda.stream(side):
             ctx = ops.Context(math=pkg.ZB_MATH_TF32)
             model = nn.Model(ctx, arch, classes, seed=5)
-            model.set_optimizer("sgd", lr=1e-3)
+            model.set_optimizer(opt, lr=1e-3 if opt == "sgd" else 1e-5, weight_decay=0.01 if opt == "adamw" else 0.0)
             if use_graph:
                 model.set_graph(True)
             loss_buf = torch.empty((1,), dtype=torch.float32, device="cuda")
@@ -209,6 +210,35 @@ def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes):
     assert na == nb and na > 0
     for k in pa:
         assert torch.equal(pa[k], pb[k]), k
+
+
+def test_graph_mode_stays_eager_where_it_cannot_capture(zb):
+    """A ctx on the legacy default stream cannot be captured: zb_model_set_graph must leave it on the eager path (no graph
+    captured) with unchanged results; the same model on a real stream is captured (Adam included: its bias corrections come from
+    a device table) and agrees with it bit for bit."""
+    pkg, ops, nn = zb
+    x, t = batch(16, 32, 10, 3)
+    X, T = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    losses = {}
+    for tag, opt, use_side, graph in (("adam-eager", "adamw", True, False), ("adam-graph", "adamw", True, True),
+                                      ("sgd-legacy-eager", "sgd", False, False), ("sgd-legacy-graph", "sgd", False, True)):
+        with torch.cuda.stream(side if use_side else torch.cuda.default_stream()):
+            ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+            model = nn.Model(ctx, "small_cnn", 10, seed=9)
+            model.set_optimizer(opt, lr=1e-3, weight_decay=0.01)
+            if graph:
+                model.set_graph(True)
+            lb = torch.empty((1,), dtype=torch.float32, device="cuda")
+            losses[tag] = [model.train_step(X, T, loss_out=lb, read_loss=True) for _ in range(5)]
+            ctx.check()
+            assert model.graph_count() == (1 if (graph and use_side) else 0)
+            model.close()
+            ctx.close()
+        torch.cuda.synchronize()
+    assert losses["adam-eager"] == losses["adam-graph"]
+    assert losses["sgd-legacy-eager"] == losses["sgd-legacy-graph"]
 
 
 def test_inference_mode_uses_running_stats(zb):

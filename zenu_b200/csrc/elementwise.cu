@@ -6,6 +6,8 @@
 // updates (zenu-optimizer/src/sgd.rs:20-30, adam.rs:19-58, adamw.rs:20-69).
 #include <algorithm>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace zb {
@@ -153,6 +155,29 @@ __global__ void __launch_bounds__(256) adam_kernel(T* __restrict__ p, const T* _
   }
 }
 
+// bias corrections from a device table (graph-replayable step, see zb_adam_step_table)
+template <typename T>
+__global__ void __launch_bounds__(256) adam_table_kernel(T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m, T* __restrict__ v,
+                                                         T lr, T beta1, T beta2, T eps, T wd, int decay, const T* __restrict__ table,
+                                                         const int* __restrict__ step_index, T gscale, long long n) {
+  const int idx = *step_index;
+  const T inv_bc1 = table[2 * idx], inv_bc2 = table[2 * idx + 1];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const T gi = g[i] * gscale;
+    const T mi = m[i] * beta1 + gi * (T(1) - beta1);
+    const T vi = v[i] * beta2 + (gi * gi) * (T(1) - beta2);
+    m[i] = mi;
+    v[i] = vi;
+    const T mh = mi * inv_bc1, vh = vi * inv_bc2;
+    const T upd = mh / (sqrt(vh) + eps);
+    T pi = p[i];
+    if (decay) pi -= (pi * lr) * wd;
+    p[i] = pi - upd * lr;
+  }
+}
+__global__ void adam_advance_kernel(int* step_index) { *step_index += 1; }
+
 // ------------------------------------------------------------------------------------------------ layout
 // [B][R][C] -> [B][C][R] tiled transpose (NCHW<->NHWC with R = C_ch / HW as appropriate).
 template <typename T>
@@ -218,6 +243,31 @@ static int adam_t(zb_ctx* ctx, void* p, const void* g, void* m, void* v, double 
   return ZB_OK;
 }
 
+template <typename T>
+static int adam_table_fill_t(zb_ctx* ctx, double b1, double b2, long long first_step, long long count, void* table) {
+  std::vector<T> h(static_cast<size_t>(2 * count));
+  for (long long i = 0; i < count; ++i) {   // T-precision powers like adam_t (and the reference, adam.rs:23-25)
+    const T b1t = static_cast<T>(pow(static_cast<T>(b1), static_cast<T>(first_step + i)));
+    const T b2t = static_cast<T>(pow(static_cast<T>(b2), static_cast<T>(first_step + i)));
+    h[2 * i] = T(1) / (T(1) - b1t);
+    h[2 * i + 1] = T(1) / (T(1) - b2t);
+  }
+  ZB_CHECK_CUDA(cudaMemcpyAsync(table, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));   // h is pageable and dies here (rare: once per `count` steps)
+  return ZB_OK;
+}
+template <typename T>
+static int adam_table_t(zb_ctx* ctx, void* p, const void* g, void* m, void* v, double lr, double b1, double b2, double eps, double wd,
+                        int decay, const void* table, const int32_t* step_index, double gscale, long long n) {
+  if (n <= 0) return ZB_OK;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, ctx->sm_count * 16ll)));
+  adam_table_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<T*>(p), static_cast<const T*>(g), static_cast<T*>(m), static_cast<T*>(v),
+                                                      static_cast<T>(lr), static_cast<T>(b1), static_cast<T>(b2), static_cast<T>(eps),
+                                                      static_cast<T>(wd), decay, static_cast<const T*>(table), step_index,
+                                                      static_cast<T>(gscale), n);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
+}
 // used by api.cu for NCHW bias add
 template <typename T>
 int bias_add_nchw(zb_ctx* ctx, const T* x, const T* bias, T* y, long long n, long long k, long long hw) {
@@ -323,6 +373,25 @@ int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m,
                  double beta2, double eps, double weight_decay, int decay, int64_t step_t, double grad_scale, int64_t n) {
   ZB_DTYPE_SWITCH(dtype, adam_t<float>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, step_t, grad_scale, n),
                   adam_t<double>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, step_t, grad_scale, n));
+}
+
+int zb_adam_table_fill(zb_ctx* ctx, int dtype, double beta1, double beta2, int64_t first_step, int64_t count, void* table) {
+  ZB_REQUIRE(table != nullptr && first_step >= 1 && count >= 1, "zb_adam_table_fill: bad argument");
+  ZB_DTYPE_SWITCH(dtype, adam_table_fill_t<float>(ctx, beta1, beta2, first_step, count, table),
+                  adam_table_fill_t<double>(ctx, beta1, beta2, first_step, count, table));
+}
+int zb_adam_step_table(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m, void* v, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, int decay, const void* table, const int32_t* step_index, double grad_scale,
+                       int64_t n) {
+  ZB_REQUIRE(table != nullptr && step_index != nullptr, "zb_adam_step_table: NULL table / step index");
+  ZB_DTYPE_SWITCH(dtype, adam_table_t<float>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, table, step_index, grad_scale, n),
+                  adam_table_t<double>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, table, step_index, grad_scale, n));
+}
+int zb_adam_advance(zb_ctx* ctx, int32_t* step_index) {
+  ZB_REQUIRE(step_index != nullptr, "zb_adam_advance: NULL step index");
+  adam_advance_kernel<<<1, 1, 0, ctx->stream>>>(step_index);
+  ZB_LAUNCH_CHECK(ctx);
+  return ZB_OK;
 }
 
 int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src_u8, void* dst_nchw, int64_t n, int64_t c, int64_t h,

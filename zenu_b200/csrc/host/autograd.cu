@@ -900,6 +900,21 @@ void Optimizer::init(Runtime& rt, ParamStore& ps) {
     v = rt.zeros({ps.flat_params.numel()});
   }
   step = 0;
+  tbl_first = 0;
+}
+
+void Optimizer::begin_step(Runtime& rt) {
+  ++step;
+  if (kind == OPT_SGD) return;
+  if (!bc_table.defined()) {
+    bc_table = rt.empty({kTblSteps, 2});
+    step_index = rt.empty({2});   // (one int32 used; sized in elements of the model dtype)
+  }
+  if (tbl_first == 0 || step >= tbl_first + kTblSteps) {   // (re)fill the window starting at this step, index back to 0
+    tbl_first = step;
+    check_rc(zb_adam_table_fill(rt.ctx, rt.dtype, beta1, beta2, tbl_first, kTblSteps, bc_table.ptr), "adam table");
+    if (cudaMemsetAsync(step_index.ptr, 0, 4, rt.ctx->stream) != cudaSuccess) throw HostError("adam step index reset failed");
+  }
 }
 
 static double ps_bytes(const ParamStore& ps) { return static_cast<double>(ps.flat_params.bytes()); }
@@ -907,15 +922,16 @@ void Optimizer::update(Runtime& rt, ParamStore& ps) {
   check_rc(zb_dp_wait(rt.ctx), "dp wait");
   const double gscale = 1.0 / static_cast<double>(std::max(1, zb_dp_world(rt.ctx)));
   const size_t esz = rt.dtype == ZB_F64 ? 8 : 4;
-  ++step;
+  if (!in_replay_capture) begin_step(rt);
+  const int32_t* sidx = kind == OPT_SGD ? nullptr : static_cast<const int32_t*>(step_index.ptr);
   ProfScope scope(rt, "optimizer.update", 0.0, 3.0 * ps_bytes(ps));
   auto at = [&](const Tensor& t, int64_t off) { return static_cast<void*>(static_cast<uint8_t*>(t.ptr) + off * esz); };
   if (kind == OPT_SGD) {
     // p -= lr * g over the whole flat buffer (sgd.rs:20-30), gradient averaging folded in
     check_rc(zb_sgd_step(rt.ctx, rt.dtype, ps.flat_params.ptr, ps.flat_grads.ptr, lr, gscale, ps.flat_params.numel()), "sgd step");
   } else if (kind == OPT_ADAM) {
-    check_rc(zb_adam_step(rt.ctx, rt.dtype, ps.flat_params.ptr, ps.flat_grads.ptr, m.ptr, v.ptr, lr, beta1, beta2, eps, 0.0, 0, step,
-                          gscale, ps.flat_params.numel()), "adam step");
+    check_rc(zb_adam_step_table(rt.ctx, rt.dtype, ps.flat_params.ptr, ps.flat_grads.ptr, m.ptr, v.ptr, lr, beta1, beta2, eps, 0.0, 0,
+                                bc_table.ptr, sidx, gscale, ps.flat_params.numel()), "adam step");
   } else {
     // AdamW: decoupled decay on weights() only (adamw.rs:28,61-65): per bucket, the weight run then the bias run
     for (auto& b : ps.buckets) {
@@ -924,13 +940,14 @@ void Optimizer::update(Runtime& rt, ParamStore& ps) {
         if (e.kind == 0 && e.bucket == static_cast<int>(&b - &ps.buckets[0])) w_end = std::max(w_end, e.offset + ((e.numel + 3) & ~int64_t(3)));
       const int64_t nw = w_end - b.offset, nbias = b.numel - nw;
       if (nw > 0)
-        check_rc(zb_adam_step(rt.ctx, rt.dtype, at(ps.flat_params, b.offset), at(ps.flat_grads, b.offset), at(m, b.offset),
-                              at(v, b.offset), lr, beta1, beta2, eps, weight_decay, 1, step, gscale, nw), "adamw step");
+        check_rc(zb_adam_step_table(rt.ctx, rt.dtype, at(ps.flat_params, b.offset), at(ps.flat_grads, b.offset), at(m, b.offset),
+                                    at(v, b.offset), lr, beta1, beta2, eps, weight_decay, 1, bc_table.ptr, sidx, gscale, nw), "adamw step");
       if (nbias > 0)
-        check_rc(zb_adam_step(rt.ctx, rt.dtype, at(ps.flat_params, w_end), at(ps.flat_grads, w_end), at(m, w_end), at(v, w_end), lr,
-                              beta1, beta2, eps, weight_decay, 0, step, gscale, nbias), "adamw step");
+        check_rc(zb_adam_step_table(rt.ctx, rt.dtype, at(ps.flat_params, w_end), at(ps.flat_grads, w_end), at(m, w_end), at(v, w_end), lr,
+                                    beta1, beta2, eps, weight_decay, 0, bc_table.ptr, sidx, gscale, nbias), "adamw step");
     }
   }
+  if (kind != OPT_SGD) check_rc(zb_adam_advance(rt.ctx, static_cast<int32_t*>(step_index.ptr)), "adam advance");
 }
 
 }  // namespace host

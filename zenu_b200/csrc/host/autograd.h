@@ -265,7 +265,16 @@ struct Optimizer {
   double lr = 0.01, beta1 = 0.9, beta2 = 0.999, eps = 1e-8, weight_decay = 0.0;
   int64_t step = 0;
   Tensor m, v;  // Adam state over the flat parameter buffer
+  // Adam bias corrections for steps [tbl_first, tbl_first + kTblSteps) in device memory + the device-side index of the current
+  // step: the kernels take nothing that changes from step to step as an argument, so a captured step can be replayed
+  static constexpr int64_t kTblSteps = 4096;
+  Tensor bc_table, step_index;
+  int64_t tbl_first = 0;
   void init(Runtime& rt, ParamStore& ps);
+  // advances the host step count and makes the device table cover it (called by update(), and by the graph replay path instead
+  // of update())
+  void begin_step(Runtime& rt);
+  bool in_replay_capture = false;   // set by the step-graph capture, which calls begin_step itself (outside the captured region)
   // Optimizer::update: waits for the bucket allreduces (data parallel), then one fused kernel per bucket
   void update(Runtime& rt, ParamStore& ps);
 };

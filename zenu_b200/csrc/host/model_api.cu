@@ -118,6 +118,8 @@ int zb_model_set_train(zb_model* m, int train) {
 
 int zb_model_set_optimizer(zb_model* m, int kind, double lr, double beta1, double beta2, double eps, double weight_decay) {
   ZB_REQUIRE(kind >= 0 && kind <= 2, "unknown optimizer kind %d", kind);
+  cudaStreamSynchronize(m->ctx->stream);
+  m->drop_graphs();   // learning rate, betas ... are kernel arguments baked into captured steps
   ZB_HOST_TRY({
     m->opt.kind = kind;
     m->opt.lr = lr;
@@ -184,13 +186,12 @@ int zb_model_graph_count(zb_model* m) { return m ? static_cast<int>(m->graphs.si
 // model, batch shape and buffer addresses it enqueues the same kernels with the same arguments: after two eager steps (the caching
 // allocator and the scratch arena have reached their steady state, every kernel attribute is set) the step is captured once from
 // the compute stream and replayed.  Data parallel: the bucket allreduces are captured with it (the comm stream forks from the
-// compute stream at each bucket's ready event and joins at the optimizer's wait).  Replay is used only where the host contributes
-// nothing per step: SGD (Adam's bias correction is a host-side function of the step count), no per-node profiling.  Returns 1 when the step was run from a graph, 0 when the caller should run it eagerly, < 0 on error.
+// compute stream at each bucket's ready event and joins at the optimizer's wait).  Nothing the host computes per step is a kernel
+// argument: Adam's bias corrections come from a device table indexed by a device-side step counter (zb_adam_step_table).  Returns 1 when the step was run from a graph, 0 when the caller should run it eagerly, < 0 on error.
 static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b, int64_t c, int64_t h, int64_t w, void* loss_dev,
                             double* host_loss) {
   zb_ctx* ctx = m->ctx;
-  if (!m->graph_enabled || m->opt.kind != OPT_SGD || !m->opt_ready || m->rt->prof.enabled || zb::prof_active(ctx))
-    return 0;
+  if (!m->graph_enabled || !m->opt_ready || m->rt->prof.enabled || zb::prof_active(ctx)) return 0;
   const size_t esz = m->rt->dtype == ZB_F64 ? 8 : 4;
   const uint64_t gen = m->rt->alloc.generation();
   zb_model::StepGraph* hit = nullptr;
@@ -208,7 +209,9 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
       return 0;
     }
     int rc = zb_model_forward_backward(m, x, t, b, c, h, w, loss_dev);
+    m->opt.in_replay_capture = true;   // the step count / Adam table is advanced below, once per replay, outside the graph
     if (rc == ZB_OK) rc = zb_model_update(m);
+    m->opt.in_replay_capture = false;
     if (rc == ZB_OK && cudaMemcpyAsync(m->pinned_loss, m->last_loss->data.ptr, esz, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
       rc = ZB_ERR_CUDA;
     const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
@@ -227,6 +230,12 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
     if (ie != cudaSuccess) { cudaGetLastError(); m->graph_enabled = false; return 0; }
     m->graphs.push_back({x, t, loss_dev, b, c, h, w, m->rt->alloc.generation(), captured, exec});
     hit = &m->graphs.back();
+  }
+  try {
+    m->opt.begin_step(*m->rt);   // host step count; Adam: (re)fill the bias-correction window when the step leaves it
+  } catch (const std::exception& e) {
+    zb::set_last_error("%s", e.what());
+    return -ZB_ERR_CUDA;
   }
   if (cudaGraphLaunch(hit->exec, ctx->stream) != cudaSuccess) {
     zb::set_last_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
