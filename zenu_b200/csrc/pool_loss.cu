@@ -105,7 +105,9 @@ template <> struct Vec4T<float> { using type = float4; };
 template <> struct Vec4T<double> { using type = double4; };
 
 // I = int when every element index fits in 31 bits (64-bit divides dominated the old version: 1.1 TB/s -> HBM-bound now)
-template <typename T, typename I>
+// KH x KW > 0: compile-time window (3 x 3 is what the networks use): the nine 128-bit loads of an output are independent of its
+// compare chain, and fully unrolled they are all in flight together instead of one per trip of a runtime-count loop
+template <typename T, typename I, int KH = 0, int KW = 0>
 __global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, const T* __restrict__ x, T* __restrict__ y,
                                                               uchar4* __restrict__ idx) {
   using V = typename Vec4T<T>::type;
@@ -122,9 +124,12 @@ __global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, 
     T best[4];
     unsigned char bi[4];
     bool first = true;
-    for (int r = 0; r < g.kh; ++r) {
+    const int kh = KH ? KH : g.kh, kw = KW ? KW : g.kw;
+#pragma unroll
+    for (int r = 0; r < kh; ++r) {
       const I ih = p * g.sh + r - g.ph;
-      for (int s_ = 0; s_ < g.kw; ++s_) {
+#pragma unroll
+      for (int s_ = 0; s_ < kw; ++s_) {
         const I iw = q * g.sw + s_ - g.pw;
         const bool oob = ih < 0 || ih >= H || iw < 0 || iw >= W;
         T v[4] = {T(0), T(0), T(0), T(0)};
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(256) maxpool_idx_fwd_kernel(const PoolGeom g, 
           const V vv = *reinterpret_cast<const V*>(xb + ih * s_h + iw * s_w);
           v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
         }
-        const unsigned char tap = oob ? 255 : static_cast<unsigned char>(r * g.kw + s_);
+        const unsigned char tap = oob ? 255 : static_cast<unsigned char>(r * kw + s_);
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (first || v[e] > best[e]) { best[e] = v[e]; bi[e] = tap; }
@@ -265,9 +270,10 @@ static int maxpool_idx_fwd_t(zb_ctx* ctx, const PoolGeom& g, const T* x, T* y, v
   const long long total = g.N * g.P * g.Q * (g.C >> 2);
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll));
-  if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24))
-    maxpool_idx_fwd_kernel<T, int><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
-  else
+  if (g.N * g.H * g.W * g.C < (1ll << 31) - (1ll << 24)) {
+    if (g.kh == 3 && g.kw == 3) maxpool_idx_fwd_kernel<T, int, 3, 3><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
+    else maxpool_idx_fwd_kernel<T, int><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
+  } else
     maxpool_idx_fwd_kernel<T, long long><<<grid, 256, 0, ctx->stream>>>(g, x, y, static_cast<uchar4*>(idx));
   ZB_LAUNCH_CHECK(ctx);
   return ZB_OK;
