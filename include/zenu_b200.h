@@ -62,6 +62,11 @@ int zb_ctx_create(zb_ctx** out, int device, void* stream);
 int zb_ctx_destroy(zb_ctx* ctx);
 int zb_ctx_synchronize(zb_ctx* ctx);
 int zb_ctx_set_math(zb_ctx* ctx, int math_mode);
+/* BatchNorm epsilon used by every zb_bn2d_* call of this ctx.  Default 1e-10, the reference's constant on both of its paths
+ * (zenu-matrix/src/nn/batch_norm.rs:296, zenu-cuda/src/cudnn/batch_norm.rs:82); the cuDNN-frontend BatchNorm shim sets the value its
+ * descriptor was created with around each call. */
+int zb_ctx_set_bn_epsilon(zb_ctx* ctx, double eps);
+double zb_ctx_bn_epsilon(zb_ctx* ctx);
 void* zb_ctx_stream(zb_ctx* ctx);
 /* Non-zero status if any kernel since the last call hit a device-side timeout. Synchronises. */
 int zb_ctx_check(zb_ctx* ctx);
@@ -106,6 +111,20 @@ int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_c
                         const void* w, void* dx);
 int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                     const void* x, void* dw);
+/* ---- plan description (parity-test support: which kernel variant serves a shape) ------------------------------------------
+ * zb_conv2d_plan_describe runs the SAME dispatch and host planners as zb_conv2d_{fprop,dgrad,wgrad} in a dry mode (nothing is
+ * launched, allocated or written; no tensor needs to exist) and writes one "kernel<variant> key=value ...;" segment per launch the
+ * call would make into buf (NUL-terminated, truncated to cap).  Values that depend on the batch size rather than on the kernel variant
+ * carry a '~' prefix, so a test can assert that the variant exercised at a small batch is the one the benchmarked batch takes.
+ * Returns the buffer size needed (call with buf == NULL to size it), or -(zb_status) on failure.
+ * zb_ctx_plan_trace(ctx, 1) records the same segments for REAL calls made by this thread; zb_ctx_plan_trace_read returns and clears them. */
+typedef enum { ZB_PLAN_FPROP = 0, ZB_PLAN_DGRAD = 1, ZB_PLAN_WGRAD = 2 } zb_plan_op;
+typedef enum { ZB_PLAN_BNSTATS = 1, ZB_PLAN_BIAS = 2, ZB_PLAN_ACCUMULATE = 4 } zb_plan_flags;
+int64_t zb_conv2d_plan_describe(zb_ctx* ctx, int op, int dtype, int layout, int math, const zb_conv2d_desc* d, int flags, char* buf,
+                                int64_t cap);
+int zb_ctx_plan_trace(zb_ctx* ctx, int enable);
+int64_t zb_ctx_plan_trace_read(zb_ctx* ctx, char* buf, int64_t cap);
+
 /* conv2d_bias_add / conv2d_bias_bkwd (nn/conv/mod.rs:84-107; kernels array_array.cu:49-74,
  * conv2d_bkwd_data.cu:121-195 — the latter is wrong for N>1 in the reference; this one is not). */
 int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const void* bias, void* y, int64_t n,

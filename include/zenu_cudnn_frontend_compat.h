@@ -6,11 +6,16 @@
  * frees its descriptors (cudnn_frontend_wrapper.cpp:13,39,66,91,118 `new` without a matching export).
  * Tensors are NCHW / KCRS with the default (contiguous) strides the reference asserts
  * (zenu-matrix/src/nn/conv/interface.rs:270-281); other strides return NOT_SUPPORTED.
- * The wrapper's BatchNorm graph entry points are not mirrored: the reference marks them experimental and never
- * calls them (zenu-cuda/src/cudnn/graph_batchnorm.rs:1); BatchNorm goes through zb_bn2d_* (zenu_b200.h).
+ * The wrapper's BatchNorm graph entry points (cudnn_frontend_wrapper.h:33-98) are mirrored too: the reference marks them
+ * experimental and never calls them at run time (zenu-cuda/src/cudnn/graph_batchnorm.rs:1), but graph_batchnorm.rs:5-11 is a compiled
+ * `pub mod` that imports all nine, so zenu-cuda does not link without them.  They are served by zb_bn2d_fwd_train / zb_bn2d_bwd with
+ * cuDNN-frontend's conventions translated: `momentum` weights the NEW statistic there (next = (1 - m) * prev + m * batch; the
+ * reference's legacy path weights the old one), epsilon is the descriptor's, prev_/next_ running statistics are separate buffers,
+ * peer_stats_* (multi-GPU BN) are ignored, X may be NCHW- or NHWC-strided.
  */
 #ifndef ZENU_CUDNN_FRONTEND_COMPAT_H
 #define ZENU_CUDNN_FRONTEND_COMPAT_H
+#include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
@@ -26,6 +31,53 @@ typedef struct {
   int64_t strides[8];
 } CudnnTensorShapeStride;
 
+/* ---- BatchNorm (cudnn_frontend_wrapper.h:33-98) ---- */
+typedef struct BatchNormDescriptor BatchNormDescriptor;
+typedef struct {
+  void* X;
+  void* mean;
+  void* inv_variance;
+  void* scale;
+  void* bias;
+  void* peer_stats_0;
+  void* peer_stats_1;
+  void* prev_running_mean;
+  void* prev_running_var;
+  void* next_running_mean;
+  void* next_running_var;
+  void* Y;
+} BatchNormExecutionBuffers;
+CudnnFrontendError_t create_batch_norm_descriptor(BatchNormDescriptor** desc, CudnnFrontendDataType_t data_type,
+                                                  const CudnnTensorShapeStride* shape, float epsilon, float momentum, bool is_training);
+void batch_norm_desc_debug(BatchNormDescriptor* desc);
+CudnnFrontendError_t check_graph(BatchNormDescriptor* desc, void* handle);
+CudnnFrontendError_t get_workspace_size(BatchNormDescriptor* desc, int64_t* workspace_size);
+CudnnFrontendError_t execute_batch_norm_forward_training(BatchNormDescriptor* desc, BatchNormExecutionBuffers* buffers, void* workspace,
+                                                         void* handle);
+void destroy_batch_norm_descriptor(BatchNormDescriptor* desc);
+
+typedef struct BatchNormBkwdDescriptor BatchNormBkwdDescriptor;
+typedef struct {
+  void* X;
+  void* DY;
+  void* scale;
+  void* mean;
+  void* inv_variance;
+  void* dscale;
+  void* dbias;
+  void* DX;
+  void* peer_stats_0;
+  void* peer_stats_1;
+} BatchNormBkwdExecutionBuffers;
+CudnnFrontendError_t create_batch_norm_backward_data_descriptor(BatchNormBkwdDescriptor** desc, CudnnFrontendDataType_t data_type,
+                                                                const CudnnTensorShapeStride* shape);
+CudnnFrontendError_t check_backward_data_graph(BatchNormBkwdDescriptor* desc, void* handle);
+CudnnFrontendError_t get_backward_data_workspace_size(BatchNormBkwdDescriptor* desc, int64_t* workspace_size);
+CudnnFrontendError_t execute_batch_norm_backward_data(BatchNormBkwdDescriptor* desc, BatchNormBkwdExecutionBuffers* buffers,
+                                                      void* workspace, void* handle);
+void destroy_batch_norm_backward_data_descriptor(BatchNormBkwdDescriptor* desc);
+
+/* ---- convolution (cudnn_frontend_wrapper.h:100-186) ---- */
 typedef struct { void* X; void* filter; void* Y; } ConvBufers;
 typedef struct { int64_t padding[2]; int64_t stride[2]; int64_t dilation[2]; int64_t num_dims; } ConvInfo;
 typedef struct { void* DY; void* filter; void* DX; } ConvBkwdDataBuffers;

@@ -3,7 +3,7 @@
 
 Run in the build container only (reads /root/reference, which does not exist on the GPU box):
     python tests/golden/make_golden.py
-Outputs (committed): tests/golden/conv2d.npz, conv_bias.npz, literals.json
+Outputs (committed): tests/golden/conv2d.npz, conv_bias.npz, literals.json, ref_symbols.json
 
 Sources (all under /root/reference):
   test_data_json/conv2d.json, conv_bias.json                  (PyTorch-generated, serde Matrix form)
@@ -13,6 +13,8 @@ Sources (all under /root/reference):
   zenu-matrix/src/operation/relu.rs:255-297                    ReLU / mask
   zenu-optimizer/tests/net_test.rs:82-260                      SGD / Adam / AdamW one-step literals
   zenu-cuda/src/cudnn/graph_conv.rs:433-623                    conv fwd 1x2x4x4 * 3x2x3x3 literals
+  zenu-cuda-kernel-sys/kernel/*.h, zenu-cudnn-frontend-wrapper-sys/.../cudnn_frontend_wrapper.h
+                                                               every extern "C" prototype of the two FFI surfaces (ref_symbols.json)
 """
 import json
 import os
@@ -119,5 +121,49 @@ def main():
         print(k, {kk: (len(vv) if isinstance(vv, list) else vv) for kk, vv in v.items() if not isinstance(vv, dict)})
 
 
+def c_prototypes(path, text=None):
+    """{name: {"ret": type, "args": [types]}} of every function prototype in a C header (comments / preprocessor lines dropped,
+    parameter names dropped, whitespace normalised: "float *a" -> "float*").  `text`: already-preprocessed source instead of a file."""
+    src = text if text is not None else open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    src = re.sub(r"typedef\s+(?:struct|enum)\s*\w*\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b([A-Za-z_]\w*)\s*\(([^()]*)\)\s*;", src):
+        ret, name, args = " ".join(m.group(1).split()), m.group(2), m.group(3).strip()
+        if not ret or ret.startswith("typedef") or ret in ("extern", "return"):
+            continue
+        types = []
+        for a in ([] if args in ("", "void") else args.split(",")):
+            a = " ".join(a.replace("*", " * ").split())
+            toks = a.split(" ")
+            if len(toks) > 1 and toks[-1] != "*" and re.match(r"[A-Za-z_]\w*$", toks[-1]):
+                toks = toks[:-1]   # parameter name
+            types.append("".join(t if t == "*" else (" " + t) for t in toks).strip().replace(" *", "*"))
+        out[name] = {"ret": ret.replace(" *", "*"), "args": types}
+    return out
+
+
+def ref_symbols():
+    """The reference's two native FFI surfaces on the hot path, as the bindgen'd Rust crates see them."""
+    ksys = {}
+    kdir = os.path.join(REF, "zenu-cuda-kernel-sys", "kernel")
+    for h in sorted(os.listdir(kdir)):
+        if h.endswith(".h") and h != "kernel.h":
+            for k, v in c_prototypes(os.path.join(kdir, h)).items():
+                v["header"] = "zenu-cuda-kernel-sys/kernel/" + h
+                ksys[k] = v
+    fe_path = "zenu-cudnn-frontend-wrapper-sys/cudnn_frontend_wrapper/include/cudnn_frontend_wrapper.h"
+    fe = c_prototypes(os.path.join(REF, fe_path))
+    for v in fe.values():
+        v["header"] = fe_path
+    out = {"kernel_sys": ksys, "cudnn_frontend_wrapper": fe}
+    with open(os.path.join(OUT, "ref_symbols.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("ref_symbols", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    ref_symbols()

@@ -29,12 +29,46 @@ def _declared(header):
 
 
 @pytest.mark.parametrize("header,minimum", [("zenu_b200.h", 40), ("zenu_kernel_compat.h", 120),
-                                            ("zenu_cudnn_frontend_compat.h", 15)])
+                                            ("zenu_cudnn_frontend_compat.h", 26)])
 def test_exports_every_declared_symbol(lib, header, minimum):
     names = _declared(header)
     assert len(names) >= minimum, names
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"{header}: library does not export {missing}"
+
+
+def _golden_tools():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("surface,header,count", [("kernel_sys", "zenu_kernel_compat.h", 126),
+                                                  ("cudnn_frontend_wrapper", "zenu_cudnn_frontend_compat.h", 21)])
+def test_reference_ffi_surface_is_exported_with_the_reference_prototypes(lib, surface, header, count):
+    """The .so against the REFERENCE's headers, not this repo's own: tests/golden/ref_symbols.json holds every prototype of
+    zenu-cuda-kernel-sys/kernel/*.h and cudnn_frontend_wrapper.h (extracted from /root/reference by tests/golden/make_golden.py).
+    Every one of them must be exported, and the compat header must declare it with the same return type and parameter list
+    (`cudnnHandle_t*` is carried as `void*`: there is no cuDNN behind this library), so the bindgen'd Rust crates
+    (zenu-cuda-kernel-sys/build.rs:37-53, zenu-cudnn-frontend-wrapper-sys/build.rs) link and call unchanged."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "ref_symbols.json")) as f:
+        ref = json.load(f)[surface]
+    assert len(ref) == count
+    missing = [n for n in ref if not hasattr(lib, n)]
+    assert not missing, f"reference symbols the library does not export: {missing}"
+    pre = subprocess.run(["/usr/bin/gcc", "-E", "-P", "-x", "c", os.path.join(ROOT, "include", header)],
+                         check=True, capture_output=True, text=True).stdout   # the kernel-sys header is macro-generated
+    ours = _golden_tools().c_prototypes(None, text=pre)
+    norm = lambda t: t.replace("cudnnHandle_t*", "void*").replace("bool", "_Bool")  # noqa: E731  (stdbool.h: bool is _Bool after cpp)
+    bad = []
+    for name, proto in ref.items():
+        mine = ours.get(name)
+        if mine is None or norm(proto["ret"]) != mine["ret"] or [norm(a) for a in proto["args"]] != mine["args"]:
+            bad.append((name, proto, mine))
+    assert not bad, bad
 
 
 def test_header_prototypes_parse():

@@ -48,17 +48,18 @@ CASES = [
     ("small_cnn", 16, 32, 10, "fp32", "adamw", 1e-3, 1e-4, 3e-4, 1e-4),
     ("resnet18", 16, 64, 10, "tf32", "sgd", 1e-3, 3e-3, 1e-2, 5e-3),
     ("resnet18", 4, 64, 10, "fp32", "adam", 1e-3, 2e-4, 6e-4, 2e-4),
-    ("resnet50", 16, 64, 8, "tf32", "sgd", 1e-3, 1e-2, 0.2, 8e-2),
-    ("resnet50", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 0.1, 2e-3),
-    # the same network with the last BatchNorm scale of every residual branch at 0.1 ("zero-init residual" practice): at
+    # ResNet-50 with the last BatchNorm scale of every residual branch at 0.1 ("zero-init residual" practice): at
     # plain initialisation ResNet-50's gradient is chaotic under ANY operand rounding (ReLU-mask flips: oracle rne vs rna
-    # tf32 rounding alone moves the whole gradient by 41 %), damped it is well conditioned and the loss curve is pinned tightly
+    # tf32 rounding alone moves the whole gradient by 41 %, the loss curve by 20 %: a tolerance that wide cannot fail on a real bug,
+    # so the plain-initialisation cases of round 1 are gone); damped it is well conditioned and the loss curve is pinned tightly
     ("resnet50:damped", 16, 64, 8, "tf32", "sgd", 1e-3, 2e-3, 5e-3, 3e-2),
     ("resnet50:damped", 16, 64, 8, "fp32", "sgd", 1e-3, 2e-4, 1e-3, 2e-3),
     # 3xTF32 (hi/lo operand split on the tensor cores): held to the same f32-level tolerances as the FFMA path
     ("small_cnn", 16, 32, 10, "tf32x3", "adamw", 1e-3, 1e-4, 3e-4, 1e-4),
     ("resnet18", 4, 64, 10, "tf32x3", "adam", 1e-3, 2e-4, 6e-4, 2e-4),
     ("resnet50:damped", 16, 64, 8, "tf32x3", "sgd", 1e-3, 2e-4, 1e-3, 2e-3),
+    # the benchmarked geometry: 3 x 224 x 224 input, so every layer runs at its real 112 / 56 / 28 / 14 / 7 spatial size
+    ("resnet50:damped", 32, 224, 8, "tf32", "sgd", 1e-3, 2e-3, 5e-3, 3e-2),
 ]
 
 

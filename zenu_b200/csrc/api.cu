@@ -2,6 +2,8 @@
 // dtype x layout x math mode onto the tcgen05 path (umma_gemm.cu) or the FFMA/DFMA path (conv_simt.cu).
 // There is no CPU fallback anywhere: a request neither GPU path can serve returns ZB_ERR_UNSUPPORTED.
 #include <algorithm>
+#include <cstring>
+#include <string>
 
 #include "common.cuh"
 
@@ -55,11 +57,17 @@ struct Temp {
   zb_ctx* ctx;
   void* p = nullptr;
   explicit Temp(zb_ctx* c) : ctx(c) {}
+  bool fake = false;   // plan dry run (zb_conv2d_plan_describe): an address nothing dereferences
   int alloc(size_t bytes) {
+    if (plan_dry()) {
+      fake = true;
+      p = reinterpret_cast<void*>(uintptr_t(1) << 40);
+      return ZB_OK;
+    }
     ZB_CHECK_CUDA(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), ctx->stream));
     return ZB_OK;
   }
-  ~Temp() { if (p) cudaFreeAsync(p, ctx->stream); }
+  ~Temp() { if (p && !fake) cudaFreeAsync(p, ctx->stream); }
 };
 
 // ---------------------------------------------------------------------------------------------- 3xTF32
@@ -91,8 +99,8 @@ struct SplitOperand {
     float* h = static_cast<float*>(t.p);
     float* l = h + n;
     const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, t.ctx->sm_count * 16ll));
-    split_tf32_kernel<<<std::max(grid, 1), 256, 0, t.ctx->stream>>>(x, h, l, n);
-    ZB_LAUNCH_CHECK(t.ctx);
+    plan_note("split_tf32;");
+    ZB_KLAUNCH(t.ctx, split_tf32_kernel<<<std::max(grid, 1), 256, 0, t.ctx->stream>>>(x, h, l, n));
     hi = h;
     lo = l;
     return ZB_OK;
@@ -337,6 +345,68 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   if ((rc = transpose_batched<float>(ctx, xf, static_cast<float*>(tx.p), d->n, d->c, d->h * d->w)) != ZB_OK) return rc;
   if ((rc = tc_wgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), static_cast<float*>(tx.p), 0, static_cast<float*>(tw.p), false)) != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(tw.p), wf, d->k, d->kh * d->kw, d->c);  // KRSC -> KCRS
+}
+
+// ---- plan trace ---------------------------------------------------------------------------------------------------------
+static int64_t copy_trace(const std::string& text, char* buf, int64_t cap) {
+  if (buf != nullptr && cap > 0) {
+    const size_t n = std::min<size_t>(text.size(), static_cast<size_t>(cap - 1));
+    memcpy(buf, text.data(), n);
+    buf[n] = 0;
+  }
+  return static_cast<int64_t>(text.size()) + 1;
+}
+
+int64_t zb_conv2d_plan_describe(zb_ctx* ctx, int op, int dtype, int layout, int math, const zb_conv2d_desc* d, int flags, char* buf,
+                                int64_t cap) {
+  if (ctx == nullptr || d == nullptr) { zb::set_last_error("plan_describe: NULL argument"); return -1; }
+  PlanTrace tr;
+  tr.dry = true;
+  PlanTrace* prev = tl_plan;
+  tl_plan = &tr;
+  // Fake operand addresses (16-byte aligned, never dereferenced: nothing is launched in dry mode).  The real entry points run, so the
+  // description cannot drift from what a call does.
+  void* const A = reinterpret_cast<void*>(uintptr_t(5) << 40);
+  void* const B = reinterpret_cast<void*>(uintptr_t(6) << 40);
+  void* const C = reinterpret_cast<void*>(uintptr_t(7) << 40);
+  void* const S = reinterpret_cast<void*>(uintptr_t(9) << 40);
+  void* const T = reinterpret_cast<void*>(uintptr_t(10) << 40);
+  int rc;
+  int64_t rows = 0;
+  switch (op) {
+    case ZB_PLAN_FPROP:
+      if (flags & ZB_PLAN_BNSTATS) rc = zb_conv2d_fprop_bnstats(ctx, dtype, layout, math, d, A, B, (flags & ZB_PLAN_BIAS) ? S : nullptr, C, S, T, &rows);
+      else rc = zb_conv2d_fprop(ctx, dtype, layout, math, d, A, B, (flags & ZB_PLAN_BIAS) ? S : nullptr, C);
+      break;
+    case ZB_PLAN_DGRAD:
+      rc = (flags & ZB_PLAN_ACCUMULATE) ? zb_conv2d_dgrad_acc(ctx, dtype, layout, math, d, A, B, C) : zb_conv2d_dgrad(ctx, dtype, layout, math, d, A, B, C);
+      break;
+    case ZB_PLAN_WGRAD: rc = zb_conv2d_wgrad(ctx, dtype, layout, math, d, A, B, C); break;
+    default: zb::set_last_error("plan_describe: unknown op %d", op); rc = ZB_ERR_INVALID; break;
+  }
+  tl_plan = prev;
+  if (rc != ZB_OK) return -static_cast<int64_t>(rc);
+  return copy_trace(tr.text, buf, cap);
+}
+
+int zb_ctx_plan_trace(zb_ctx* ctx, int enable) {
+  ZB_REQUIRE(ctx != nullptr, "plan_trace: ctx is NULL");
+  if (enable) {
+    if (tl_plan == nullptr) tl_plan = new PlanTrace();
+    tl_plan->dry = false;
+    tl_plan->text.clear();
+  } else if (tl_plan != nullptr && !tl_plan->dry) {
+    delete tl_plan;
+    tl_plan = nullptr;
+  }
+  return ZB_OK;
+}
+
+int64_t zb_ctx_plan_trace_read(zb_ctx* ctx, char* buf, int64_t cap) {
+  if (ctx == nullptr || tl_plan == nullptr) { if (buf && cap > 0) buf[0] = 0; return 1; }
+  const int64_t need = copy_trace(tl_plan->text, buf, cap);
+  if (buf != nullptr) tl_plan->text.clear();
+  return need;
 }
 
 int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const void* bias, void* y, int64_t n, int64_t k,

@@ -20,7 +20,7 @@
 
 namespace zb {
 
-constexpr double kBnEps = 1e-10;  // zenu-matrix/src/nn/batch_norm.rs:296
+// epsilon: zb_ctx::bn_eps, 1e-10 by default (zenu-matrix/src/nn/batch_norm.rs:296); the cuDNN-frontend BatchNorm shim passes its own
 
 template <typename T, int VN> struct VecT;
 template <> struct VecT<float, 4> { using type = float4; };
@@ -311,7 +311,7 @@ __device__ __forceinline__ void fold_partials(const T* __restrict__ partial, int
 // coef layout in workspace: [0]=mean [1]=inv_std (fwd) ; bwd: [0]=gamma*inv [1]=c1 [2]=c2
 template <typename T>
 __global__ void __launch_bounds__(kFinC * kFinS)
-bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum,
+bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double count, double momentum, double eps,
                 const T* x_first_row, long long shift_stride, T* run_mean, T* __restrict__ run_var,
                 T* __restrict__ saved_mean, T* __restrict__ saved_inv, T* __restrict__ coef) {
   const long long c = blockIdx.x * static_cast<long long>(kFinC) + (threadIdx.x & (kFinC - 1));
@@ -324,7 +324,7 @@ bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double co
   const double mean = shift + dm;
   double var = ss / count - dm * dm;
   if (var < 0.0) var = 0.0;
-  const double inv = 1.0 / sqrt(var + kBnEps);
+  const double inv = 1.0 / sqrt(var + eps);
   if (run_mean) run_mean[c] = static_cast<T>(mean * (1.0 - momentum) + static_cast<double>(run_mean[c]) * momentum);
   if (run_var) {
     const double unbiased = var * (count / (count - 1.0));
@@ -337,11 +337,11 @@ bn_fwd_finalize(const T* __restrict__ partial, int slabs, long long C, double co
 }
 
 template <typename T>
-__global__ void bn_infer_coef(const T* __restrict__ mean, const T* __restrict__ var, long long C, T* __restrict__ coef) {
+__global__ void bn_infer_coef(const T* __restrict__ mean, const T* __restrict__ var, long long C, double eps, T* __restrict__ coef) {
   const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (c >= C) return;
   coef[c] = mean[c];
-  coef[C + c] = static_cast<T>(1.0 / sqrt(static_cast<double>(var[c]) + kBnEps));
+  coef[C + c] = static_cast<T>(1.0 / sqrt(static_cast<double>(var[c]) + eps));
 }
 
 template <typename T>
@@ -664,7 +664,7 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
   int slabs = 0;
   prof_begin(ctx, PROF_BN);
   if (pre_partial != nullptr) {
-    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(pre_partial, pre_rows, C, static_cast<double>(N * HW), momentum, pre_shift,
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(pre_partial, pre_rows, C, static_cast<double>(N * HW), momentum, ctx->bn_eps, pre_shift,
                                                                  1, run_mean, run_var, saved_mean, saved_inv, coef);
     ZB_LAUNCH_CHECK(ctx);
   } else {
@@ -672,7 +672,7 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
                                     partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
     if (rc != ZB_OK) return rc;
     // shift used by the reduce = first row (NHWC: x[c]) or first element of channel c in image 0 (NCHW: x[c*HW])
-    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, x,
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, ctx->bn_eps, x,
                                                                  layout == ZB_NHWC ? 1 : HW, run_mean, run_var, saved_mean,
                                                                  saved_inv, coef);
     ZB_LAUNCH_CHECK(ctx);
@@ -690,7 +690,7 @@ static int bn_fwd_infer_t(zb_ctx* ctx, int layout, long long N, long long C, lon
   int rc = ctx_workspace(ctx, sizeof(T) * 2 * C, &ws);
   if (rc != ZB_OK) return rc;
   T* coef = static_cast<T*>(ws);
-  bn_infer_coef<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(mean, var, C, coef);
+  bn_infer_coef<T><<<ceil_div(C, 128), 128, 0, ctx->stream>>>(mean, var, C, ctx->bn_eps, coef);
   ZB_LAUNCH_CHECK(ctx);
   return dispatch_apply<T>(ctx, layout, N, C, H * W, x, static_cast<const T*>(nullptr), y, coef, scale, bias, 0);
 }
@@ -743,7 +743,7 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
     rc = run_col_reduce<T, StatsFT>(ctx, layout, N, C, HW, x, static_cast<const T*>(nullptr), static_cast<const T*>(nullptr),
                                     partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = (layout == ZB_NHWC ? 1 : HW); }, &slabs);
     if (rc != ZB_OK) return rc;
-    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), 0.0, x,
+    bn_fwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), 0.0, ctx->bn_eps, x,
                                                                  layout == ZB_NHWC ? 1 : HW, static_cast<T*>(nullptr),
                                                                  static_cast<T*>(nullptr), static_cast<T*>(nullptr),
                                                                  static_cast<T*>(nullptr), stats);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -40,6 +41,7 @@ struct zb_ctx {
   zb::EncodeTiledFn encode_tiled;
   zb::EncodeIm2colFn encode_im2col;
   int default_math;          // zb_math_mode
+  double bn_eps;             // BatchNorm epsilon (reference CPU path: 1e-10, zenu-matrix/src/nn/batch_norm.rs:296)
   // data-parallel state (dp.cu)
   void* nccl_lib;
   void* nccl_comm;
@@ -76,6 +78,27 @@ namespace zb {
       zb::set_last_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return ZB_ERR_CUDA;                                                                     \
     }                                                                                         \
+  } while (0)
+
+// Plan trace (zb_conv2d_plan_describe / zb_ctx_plan_trace): while a PlanTrace is installed on the calling thread every launcher
+// appends one "kernel<variant> key=value ...;" segment per launch it plans (size-dependent values carry a '~' prefix so that a
+// test can compare the VARIANT chosen for a small batch with the one chosen for the benchmarked batch).  In dry mode the host
+// planners run unchanged -- same dispatch, same tensor-map encodes, same heuristics -- but nothing is launched, allocated or
+// written: scratch and temporaries are fake addresses.
+struct PlanTrace {
+  bool dry = false;
+  std::string text;
+};
+extern thread_local PlanTrace* tl_plan;
+static inline bool plan_dry() { return tl_plan != nullptr && tl_plan->dry; }
+void plan_note(const char* fmt, ...);
+// every kernel launch / async memset goes through this: skipped in dry mode, counted and checked otherwise
+#define ZB_KLAUNCH(ctx, ...)            \
+  do {                                  \
+    if (!zb::plan_dry()) {              \
+      __VA_ARGS__;                      \
+      ZB_LAUNCH_CHECK(ctx);             \
+    }                                   \
   } while (0)
 
 // Per-op timing with CUDA events on the launching stream, grouped by kernel class (bench.py roofline):

@@ -52,7 +52,121 @@ static CudnnFrontendError_t status_of(int rc) {
 
 using namespace zb;
 
+namespace zb {
+// BatchNorm descriptor shim (reference: src/batchnorm.cpp:166-281).  X is a 4-D tensor [N, C, H, W] whose strides say where the
+// channel dimension lives: default strides = NCHW, channel stride 1 = NHWC (both contiguous); anything else is NOT_SUPPORTED.
+struct BnShim {
+  int dtype;
+  int layout;      // ZB_NCHW / ZB_NHWC, -1 = strides this library does not serve
+  int64_t n, c, h, w;
+  double eps, momentum;
+  bool training, backward;
+};
+static int bn_layout(const CudnnTensorShapeStride* s) {
+  if (default_strides(s)) return ZB_NCHW;
+  const int64_t n = s->dims[0], c = s->dims[1], h = s->dims[2], w = s->dims[3];
+  const bool nhwc = (c == 1 || s->strides[1] == 1) && (w == 1 || s->strides[3] == c) && (h == 1 || s->strides[2] == w * c) &&
+                    (n == 1 || s->strides[0] == h * w * c);
+  return nhwc ? ZB_NHWC : -1;
+}
+static CudnnFrontendError_t make_bn_shim(BnShim** out, CudnnFrontendDataType_t dt, const CudnnTensorShapeStride* shape, double eps,
+                                         double momentum, bool training, bool backward) {
+  if (!out || !shape) return INVALID_VALUE;
+  if (dt != DATA_TYPE_FLOAT && dt != DATA_TYPE_DOUBLE) return NOT_SUPPORTED;
+  if (shape->num_dims != 4) return NOT_SUPPORTED;   // reference: "only supports BN1D or BN2D" as 4-D shapes (batchnorm.cpp:19-29)
+  for (int i = 0; i < 4; ++i)
+    if (shape->dims[i] <= 0) return INVALID_VALUE;
+  BnShim* s = new BnShim();
+  s->dtype = dt == DATA_TYPE_FLOAT ? ZB_F32 : ZB_F64;
+  s->layout = bn_layout(shape);
+  s->n = shape->dims[0]; s->c = shape->dims[1]; s->h = shape->dims[2]; s->w = shape->dims[3];
+  s->eps = eps; s->momentum = momentum; s->training = training; s->backward = backward;
+  *out = s;
+  return SUCCESS;
+}
+// runs `call` with the ctx epsilon set to the descriptor's
+template <typename F>
+static CudnnFrontendError_t with_eps(zb_ctx* ctx, double eps, F&& call) {
+  const double keep = zb_ctx_bn_epsilon(ctx);
+  zb_ctx_set_bn_epsilon(ctx, eps);
+  const int rc = call();
+  zb_ctx_set_bn_epsilon(ctx, keep);
+  return status_of(rc);
+}
+}  // namespace zb
+
 extern "C" {
+
+CudnnFrontendError_t create_batch_norm_descriptor(BatchNormDescriptor** desc, CudnnFrontendDataType_t dt, const CudnnTensorShapeStride* shape,
+                                                  float epsilon, float momentum, bool is_training) {
+  return make_bn_shim(reinterpret_cast<BnShim**>(desc), dt, shape, epsilon, momentum, is_training, false);
+}
+void batch_norm_desc_debug(BatchNormDescriptor* desc) {
+  const BnShim* s = reinterpret_cast<const BnShim*>(desc);
+  if (!s) return;
+  printf("BatchNorm %s X [%lld, %lld, %lld, %lld] %s %s epsilon %g momentum %g running stats %d\n", s->backward ? "backward" : "forward",
+         static_cast<long long>(s->n), static_cast<long long>(s->c), static_cast<long long>(s->h), static_cast<long long>(s->w),
+         s->layout == ZB_NCHW ? "NCHW" : s->layout == ZB_NHWC ? "NHWC" : "unsupported strides", s->dtype == ZB_F32 ? "float" : "double",
+         s->eps, s->momentum, s->training ? 1 : 0);
+}
+CudnnFrontendError_t check_graph(BatchNormDescriptor* desc, void*) {
+  return (desc && reinterpret_cast<BnShim*>(desc)->layout >= 0) ? SUCCESS : NOT_SUPPORTED;
+}
+CudnnFrontendError_t get_workspace_size(BatchNormDescriptor* desc, int64_t* ws) {
+  if (!desc || !ws) return INVALID_VALUE;
+  *ws = 0;
+  return SUCCESS;
+}
+CudnnFrontendError_t execute_batch_norm_forward_training(BatchNormDescriptor* desc, BatchNormExecutionBuffers* b, void*, void*) {
+  BnShim* s = reinterpret_cast<BnShim*>(desc);
+  zb_ctx* ctx = compat_ctx();
+  if (!s || !b || !ctx || s->backward) return INVALID_VALUE;
+  if (s->layout < 0) return NOT_SUPPORTED;
+  void* rm = nullptr;
+  void* rv = nullptr;
+  if (s->training) {   // has_running_stats (batchnorm.cpp:146-149,196-201): next = (1 - momentum) * prev + momentum * batch
+    if (!b->prev_running_mean || !b->prev_running_var || !b->next_running_mean || !b->next_running_var) return INVALID_VALUE;
+    const size_t bytes = static_cast<size_t>(s->c) * (s->dtype == ZB_F32 ? 4 : 8);
+    if (b->next_running_mean != b->prev_running_mean &&
+        cudaMemcpyAsync(b->next_running_mean, b->prev_running_mean, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(zb_ctx_stream(ctx))) != cudaSuccess)
+      return FAILURE;
+    if (b->next_running_var != b->prev_running_var &&
+        cudaMemcpyAsync(b->next_running_var, b->prev_running_var, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(zb_ctx_stream(ctx))) != cudaSuccess)
+      return FAILURE;
+    rm = b->next_running_mean;
+    rv = b->next_running_var;
+  }
+  return with_eps(ctx, s->eps, [&]() {
+    // zb_bn2d_fwd_train weights the OLD running statistic with its momentum argument (the reference CPU convention)
+    return zb_bn2d_fwd_train(ctx, s->dtype, s->layout, s->n, s->c, s->h, s->w, 1.0 - s->momentum, b->X, b->scale, b->bias, rm, rv, b->mean,
+                             b->inv_variance, b->Y, nullptr, 0);
+  });
+}
+void destroy_batch_norm_descriptor(BatchNormDescriptor* desc) { delete reinterpret_cast<BnShim*>(desc); }
+
+CudnnFrontendError_t create_batch_norm_backward_data_descriptor(BatchNormBkwdDescriptor** desc, CudnnFrontendDataType_t dt,
+                                                                const CudnnTensorShapeStride* shape) {
+  return make_bn_shim(reinterpret_cast<BnShim**>(desc), dt, shape, 0.0, 0.0, true, true);
+}
+CudnnFrontendError_t check_backward_data_graph(BatchNormBkwdDescriptor* desc, void*) {
+  return (desc && reinterpret_cast<BnShim*>(desc)->layout >= 0) ? SUCCESS : NOT_SUPPORTED;
+}
+CudnnFrontendError_t get_backward_data_workspace_size(BatchNormBkwdDescriptor* desc, int64_t* ws) {
+  if (!desc || !ws) return INVALID_VALUE;
+  *ws = 0;
+  return SUCCESS;
+}
+CudnnFrontendError_t execute_batch_norm_backward_data(BatchNormBkwdDescriptor* desc, BatchNormBkwdExecutionBuffers* b, void*, void*) {
+  BnShim* s = reinterpret_cast<BnShim*>(desc);
+  zb_ctx* ctx = compat_ctx();
+  if (!s || !b || !ctx || !s->backward) return INVALID_VALUE;
+  if (s->layout < 0) return NOT_SUPPORTED;
+  if (!b->mean || !b->inv_variance) return INVALID_VALUE;   // the graph is built with set_saved_mean_and_inv_variance (batchnorm.cpp:232-234)
+  // dscale / dbias come back in the io data type (the reference tags them FLOAT for every io type, batchnorm.cpp:238-239)
+  return status_of(zb_bn2d_bwd(ctx, s->dtype, s->layout, s->n, s->c, s->h, s->w, b->X, b->DY, b->scale, b->mean, b->inv_variance, b->DX,
+                               b->dscale, b->dbias, nullptr, nullptr));
+}
+void destroy_batch_norm_backward_data_descriptor(BatchNormBkwdDescriptor* desc) { delete reinterpret_cast<BnShim*>(desc); }
 
 CudnnFrontendError_t create_conv_descriptor(ConvDescriptor** desc, CudnnFrontendDataType_t dt, CudnnTensorShapeStride* x,
                                             CudnnTensorShapeStride* w, CudnnTensorShapeStride* y, ConvInfo* info) {

@@ -198,8 +198,8 @@ int simt_conv_fprop(zb_ctx* ctx, int layout, const zb_conv2d_desc* d, const T* x
   fill_params(p, layout, d);
   p.Mg = p.N * p.P * p.Q; p.Ng = p.K; p.Kg = p.C * p.R * p.S; p.k_per_split = p.Kg;
   dim3 grid(ceil_div(p.Mg, SBM), ceil_div(p.Ng, SBN), 1);
-  simt_conv_kernel<T, SIMT_FPROP><<<grid, 256, 0, ctx->stream>>>(p, x, w, bias, y);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("simt_conv_fprop<%s> layout=%d;", sizeof(T) == 8 ? "f64" : "f32", layout);
+  ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_FPROP><<<grid, 256, 0, ctx->stream>>>(p, x, w, bias, y));
   return ZB_OK;
 }
 
@@ -209,8 +209,8 @@ int simt_conv_dgrad(zb_ctx* ctx, int layout, const zb_conv2d_desc* d, const T* d
   fill_params(p, layout, d);
   p.Mg = p.N * p.H * p.W; p.Ng = p.C; p.Kg = p.K * p.R * p.S; p.k_per_split = p.Kg;
   dim3 grid(ceil_div(p.Mg, SBM), ceil_div(p.Ng, SBN), 1);
-  simt_conv_kernel<T, SIMT_DGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, w, static_cast<const T*>(nullptr), dx);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("simt_conv_dgrad<%s> layout=%d;", sizeof(T) == 8 ? "f64" : "f32", layout);
+  ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_DGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, w, static_cast<const T*>(nullptr), dx));
   return ZB_OK;
 }
 
@@ -224,10 +224,10 @@ int simt_conv_wgrad(zb_ctx* ctx, int layout, const zb_conv2d_desc* d, const T* d
   splits = std::min<long long>(splits, 65535);
   p.k_per_split = ((p.Kg + splits - 1) / splits + SBK - 1) / SBK * SBK;
   splits = (p.Kg + p.k_per_split - 1) / p.k_per_split;
-  if (splits > 1) ZB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(T) * p.K * p.C * p.R * p.S, ctx->stream));
+  if (splits > 1 && !plan_dry()) ZB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(T) * p.K * p.C * p.R * p.S, ctx->stream));
   dim3 grid(ceil_div(p.Mg, SBM), ceil_div(p.Ng, SBN), static_cast<unsigned>(splits));
-  simt_conv_kernel<T, SIMT_WGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, x, static_cast<const T*>(nullptr), dw);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("simt_conv_wgrad<%s> layout=%d atomics=%d ~splits=%lld;", sizeof(T) == 8 ? "f64" : "f32", layout, splits > 1 ? 1 : 0, splits);
+  ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_WGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, x, static_cast<const T*>(nullptr), dw));
   return ZB_OK;
 }
 
@@ -298,8 +298,8 @@ template <typename T>
 int simt_gemm(zb_ctx* ctx, bool ta, bool tb, long long m, long long n, long long k, T alpha, const T* a, long long lda,
               const T* b, long long ldb, T beta, T* c, long long ldc, const T* bias) {
   dim3 grid(ceil_div(m, SBM), ceil_div(n, SBN), 1);
-  simt_gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(ta ? 1 : 0, tb ? 1 : 0, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, bias);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("simt_gemm<%s>;", sizeof(T) == 8 ? "f64" : "f32");
+  ZB_KLAUNCH(ctx, simt_gemm_kernel<T><<<grid, 256, 0, ctx->stream>>>(ta ? 1 : 0, tb ? 1 : 0, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, bias));
   return ZB_OK;
 }
 

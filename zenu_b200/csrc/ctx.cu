@@ -51,7 +51,22 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+thread_local PlanTrace* tl_plan = nullptr;
+void plan_note(const char* fmt, ...) {
+  if (tl_plan == nullptr) return;
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  tl_plan->text += buf;
+}
+
 int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out) {
+  if (plan_dry()) {   // planning only: an aligned address that is never dereferenced
+    *out = reinterpret_cast<void*>(uintptr_t(3) << 40);
+    return ZB_OK;
+  }
   if (bytes > ctx->ws_bytes) {
     // stream-ordered: kernels already enqueued keep using the old block until they retire
     if (ctx->ws) ZB_CHECK_CUDA(cudaFreeAsync(ctx->ws, ctx->stream));
@@ -113,6 +128,7 @@ int zb_ctx_create(zb_ctx** out, int device, void* stream) {
   ZB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available in this driver");
   ctx->encode_im2col = reinterpret_cast<zb::EncodeIm2colFn>(fn);
   ctx->default_math = ZB_MATH_TF32;
+  ctx->bn_eps = 1e-10;
   ctx->rank = 0;
   ctx->world = 1;
   *out = ctx;
@@ -171,6 +187,13 @@ int zb_ctx_set_math(zb_ctx* ctx, int math_mode) {
   ctx->default_math = math_mode;
   return ZB_OK;
 }
+
+int zb_ctx_set_bn_epsilon(zb_ctx* ctx, double eps) {
+  ZB_REQUIRE(ctx != nullptr && eps >= 0.0, "zb_ctx_set_bn_epsilon: bad argument");
+  ctx->bn_eps = eps;
+  return ZB_OK;
+}
+double zb_ctx_bn_epsilon(zb_ctx* ctx) { return ctx ? ctx->bn_eps : 0.0; }
 
 void* zb_ctx_stream(zb_ctx* ctx) { return ctx->stream; }
 

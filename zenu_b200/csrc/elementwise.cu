@@ -75,6 +75,7 @@ int launch_map(zb_ctx* ctx, F f, T* out, const T* in0, const T* in1, long long n
   const bool vec = aligned16(out) && aligned16(in0) && aligned16(in1);
   const long long work = vec ? (n + Vec<T>::N - 1) / Vec<T>::N : n;
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((work + 1023) / 1024, ctx->sm_count * 8ll)));
+  if (plan_dry()) { plan_note("map;"); return ZB_OK; }
   if (vec)
     map_kernel<T, NIN, true, F><<<grid, 256, 0, ctx->stream>>>(f, out, in0, in1, n);
   else
@@ -207,8 +208,8 @@ int transpose_batched(zb_ctx* ctx, const T* src, T* dst, long long batch, long l
   if (batch * rows * cols == 0) return ZB_OK;
   ZB_REQUIRE(batch <= 65535 && (rows + 31) / 32 <= 65535, "transpose: dimension too large for the launch grid");
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>(batch));
-  transpose_kernel<T><<<grid, 256, 0, ctx->stream>>>(src, dst, rows, cols);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("transpose;");
+  ZB_KLAUNCH(ctx, transpose_kernel<T><<<grid, 256, 0, ctx->stream>>>(src, dst, rows, cols));
   return ZB_OK;
 }
 template int transpose_batched<float>(zb_ctx*, const float*, float*, long long, long long, long long);

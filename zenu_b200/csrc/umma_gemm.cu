@@ -1199,6 +1199,15 @@ static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int t
   *st->rows = (pair_bn > 0 ? launch_grid(ctx, p, pair_cl(p, pair_bn)) : stat_grid(ctx, tiles, p.n_tiles)) / p.n_tiles * 4;
 }
 
+// plan-trace segment of one umma_kernel launch ('~' = value depends on the batch size, not on the kernel variant)
+static void note_umma(const UmmaParams& p, int bn, int stages, bool old, int cl, int grid) {
+  if (tl_plan == nullptr) return;
+  plan_note("umma<bn=%d,stages=%d,old=%d,cl=%d> a_mode=%d b_mode=%d out_mode=%d n_tiles=%d tap_tiles=%d ntaps=%d splitk=%d beta=%d bias=%d stats=%d chain=%d "
+            "~m_tiles=%d ~splits=%d ~kb_per_split=%d ~grid=%d;",
+            bn, stages, old ? 1 : 0, cl, p.a_mode, p.b_mode, p.out_mode, p.n_tiles, p.tap_tiles, p.ntaps, p.splits > 1 ? 1 : 0, p.beta != 0.f ? 1 : 0,
+            p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.chain_kb, p.m_tiles, p.splits, p.kb_per_split, grid);
+}
+
 template <int BN, int STAGES, bool OLD = false>
 static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   using L = UmmaSmem<BN, STAGES, OLD>;
@@ -1209,6 +1218,8 @@ static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
     attr_set = true;
   }
   const int grid = launch_grid(ctx, p, 1);
+  note_umma(p, BN, STAGES, OLD, 1, grid);
+  if (plan_dry()) return ZB_OK;
   // algorithmic FLOPs of this launch: 2 * M * N * K over all taps (K counted in 32-wide blocks as issued)
   prof_begin(ctx, PROF_TENSOR);
   umma_kernel<BN, STAGES, OLD><<<grid, 192, L::TOTAL, ctx->stream>>>(a, b, p);
@@ -1244,6 +1255,8 @@ static int launch_cfg_pair(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap&
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  note_umma(p, BN, STAGES, OLD, 2, static_cast<int>(cfg.gridDim.x));
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   ZB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, umma_kernel<BN, STAGES, OLD, 2>, a, b2, p));
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
@@ -1332,9 +1345,9 @@ static int run_with_splits(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUte
   const long long total = rows * cols;
   const int block = 256;
   const int grid = static_cast<int>(std::min<long long>((total + block - 1) / block, ctx->sm_count * 8ll));
-  splitk_reduce_kernel<<<grid, block, 0, ctx->stream>>>(static_cast<const float*>(ws), out, rows, cols, ldo, rows * cols,
-                                                        q.splits, alpha, beta, bias);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("splitk_reduce;");
+  ZB_KLAUNCH(ctx, splitk_reduce_kernel<<<grid, block, 0, ctx->stream>>>(static_cast<const float*>(ws), out, rows, cols, ldo, rows * cols,
+                                                                     q.splits, alpha, beta, bias));
   return ZB_OK;
 }
 
@@ -1474,6 +1487,10 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
     ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
+  plan_note("halo_conv<bn=%d,cl=%d,pair=%d> resident=%d slots=%d b_stages=%d n_tiles=%d ntaps=%d c_chunks=%d beta=%d bias=%d stats=%d chain=%d tp=%d "
+            "~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
+            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.m_tiles, grid);
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   if (CL == 1) {
     halo_conv_kernel<BN, CL, PAIR><<<grid, 192, smem, ctx->stream>>>(a, b, p);
@@ -1680,8 +1697,8 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       for (int t = 0; t < R * S; ++t) tl.rs[t] = R * S - 1 - t;   // tap (r', s') of the flipped filter = (R-1-r', S-1-s')
       const long long total = static_cast<long long>(elems);
       const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
-      dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), R * S, tl);
-      ZB_LAUNCH_CHECK(ctx);
+      plan_note("dgrad_filter;");
+      ZB_KLAUNCH(ctx, dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), R * S, tl));
       return umma_conv_halo(ctx, hp, d->n, P, Q, d->k, d->c, R, S, ph2, pw2, dy, wt, nullptr, dx, beta,
                             2.0 * d->n * P * Q * d->k * d->c * R * S);
     }
@@ -1736,7 +1753,10 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       }
       plans.push_back(cp);
     }
-  if (need_zero && beta == 0.f) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
+  if (need_zero && beta == 0.f) {
+    plan_note("memset_dx;");
+    if (!plan_dry()) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
+  }
 
   // workspace: transformed filters for all classes + tap index lists
   size_t wt_elems = 0;
@@ -1756,8 +1776,8 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     {
       const long long total = static_cast<long long>(d->c) * cp.ntaps * d->k;
       const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
-      dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), cp.ntaps, tl);
-      ZB_LAUNCH_CHECK(ctx);
+      plan_note("dgrad_filter(class %d,%d);", cp.a, cp.b);
+      ZB_KLAUNCH(ctx, dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), cp.ntaps, tl));
     }
     CUtensorMap ma, mb;
     rc = make_map_im2col(ctx, &ma, dy, d->n, P, Q, d->k, cp.lower_w, cp.lower_h, cp.upper_w, cp.upper_h, 1, 1, kUmmaBM);
@@ -1879,9 +1899,9 @@ int umma_conv_wgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if (rc != ZB_OK) return rc;
   const long long total = rows * cols;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
-  splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ws), dw, rows, cols, cols, rows * cols,
-                                                      q.splits, 1.f, beta, nullptr);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("splitk_reduce;");
+  ZB_KLAUNCH(ctx, splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ws), dw, rows, cols, cols, rows * cols,
+                                                                   q.splits, 1.f, beta, nullptr));
   return ZB_OK;
 }
 
@@ -1980,10 +2000,10 @@ static SmallcGeom smallc_geom(const zb_conv2d_desc* d) {
 static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcGeom& g, const float* x, int x_nchw, float* xp) {
   const long long total = d->n * d->h * g.Wp;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
-  smallc_pack_input_kernel<<<grid, 256, 0, ctx->stream>>>(x, reinterpret_cast<float4*>(xp), d->n, static_cast<int>(d->c),
-                                                          static_cast<int>(d->h), static_cast<int>(d->w), static_cast<int>(g.Wp),
-                                                          static_cast<int>(d->pad_w), x_nchw);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("smallc_pack_input(nchw=%d);", x_nchw);
+  ZB_KLAUNCH(ctx, smallc_pack_input_kernel<<<grid, 256, 0, ctx->stream>>>(x, reinterpret_cast<float4*>(xp), d->n, static_cast<int>(d->c),
+                                                                       static_cast<int>(d->h), static_cast<int>(d->w), static_cast<int>(g.Wp),
+                                                                       static_cast<int>(d->pad_w), x_nchw));
   return ZB_OK;
 }
 
@@ -1994,6 +2014,9 @@ static int stem_fprop_launch(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMa
     ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
+  plan_note("stem_fprop<bn=%d> stages=%d taps=%d beta=%d bias=%d stats=%d ~m_tiles=%d ~grid=%d;", BN, p.halo_slots, p.ntaps, p.beta != 0.f ? 1 : 0,
+            p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.m_tiles, grid);
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   stem_fprop_kernel<BN><<<grid, 192, smem, ctx->stream>>>(a, b, p);
   prof_end(ctx, PROF_TENSOR, p.prof_flops);
@@ -2017,9 +2040,9 @@ int umma_conv_smallc_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x,
   if ((rc = smallc_pack_input(ctx, d, g, x, x_nchw, xp)) != ZB_OK) return rc;
   {
     const int total = static_cast<int>(d->k * d->kh * 32);
-    smallc_pack_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wp, static_cast<int>(d->k), static_cast<int>(d->kh),
-                                                                          static_cast<int>(d->kw), static_cast<int>(d->c));
-    ZB_LAUNCH_CHECK(ctx);
+    plan_note("smallc_pack_filter;");
+    ZB_KLAUNCH(ctx, smallc_pack_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wp, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                                         static_cast<int>(d->kw), static_cast<int>(d->c)));
   }
   const int bn = pick_bn(d->k);
   if (g.Q <= kUmmaBM && bn <= 128 && d->k <= bn && !ZB_ENV_FLAG("ZENU_B200_NO_STEM_FPROP")) {
@@ -2127,10 +2150,10 @@ int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
     rc = umma_conv_stem_wgrad(ctx, d, dy, xp, g.Wp, g.P, g.Q, part, max_parts, &parts);
     if (rc == ZB_OK) {
       const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
-      smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
-                                                                            static_cast<int>(d->kw), static_cast<int>(d->c), parts,
-                                                                            rows * cols, beta);
-      ZB_LAUNCH_CHECK(ctx);
+      plan_note("smallc_unpack_dw;");
+      ZB_KLAUNCH(ctx, smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                                         static_cast<int>(d->kw), static_cast<int>(d->c), parts,
+                                                                                         rows * cols, beta));
       return ZB_OK;
     }
     if (rc != ZB_ERR_UNSUPPORTED) return rc;
@@ -2157,10 +2180,10 @@ int umma_conv_smallc_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   p.alpha = 1.f;
   if ((rc = umma_launch(ctx, bn, ma, mb, p)) != ZB_OK) return rc;
   const int total = static_cast<int>(d->k * d->kh * d->kw * d->c);
-  smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
-                                                                        static_cast<int>(d->kw), static_cast<int>(d->c), p.splits,
-                                                                        rows * cols, beta);
-  ZB_LAUNCH_CHECK(ctx);
+  plan_note("smallc_unpack_dw;");
+  ZB_KLAUNCH(ctx, smallc_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(part, dw, static_cast<int>(d->k), static_cast<int>(d->kh),
+                                                                                     static_cast<int>(d->kw), static_cast<int>(d->c), p.splits,
+                                                                                     rows * cols, beta));
   return ZB_OK;
 }
 
@@ -2208,9 +2231,9 @@ int umma_conv_smallc_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy
   float* wd = static_cast<float*>(ws);
   {
     const int total = static_cast<int>(32 * R * d->k);
-    smallc_pack_dgrad_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wd, static_cast<int>(d->k), R, static_cast<int>(d->kw),
-                                                                                static_cast<int>(d->c));
-    ZB_LAUNCH_CHECK(ctx);
+    plan_note("smallc_pack_dgrad_filter;");
+    ZB_KLAUNCH(ctx, smallc_pack_dgrad_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wd, static_cast<int>(d->k), R, static_cast<int>(d->kw),
+                                                                                               static_cast<int>(d->c)));
   }
   UmmaParams p;
   init_params(p, ctx);

@@ -274,8 +274,8 @@ int umma_conv_stem_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   float* wd = static_cast<float*>(ws);
   {
     const int total = 32 * p.R * p.K;
-    stem_dgrad_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wd, p.K, p.R, p.S, p.C);
-    ZB_LAUNCH_CHECK(ctx);
+    plan_note("stem_dgrad_filter;");
+    ZB_KLAUNCH(ctx, stem_dgrad_filter_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(w, wd, p.K, p.R, p.S, p.C));
   }
   CUtensorMap ma, mb;
   {
@@ -303,6 +303,8 @@ int umma_conv_stem_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     attr = smem;
   }
   const int grid = std::min(p.total_tiles, ctx->sm_count);
+  plan_note("stem_dgrad stages=%d b_tiles=%d beta=%d ~tiles=%d ~grid=%d;", p.stages, p.b_tiles, beta != 0.f ? 1 : 0, p.total_tiles, grid);
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   stem_dgrad_kernel<<<grid, 192, smem, ctx->stream>>>(ma, mb, p);
   prof_end(ctx, PROF_TENSOR, 2.0 * d->n * P * Q * d->k * d->c * d->kh * d->kw);

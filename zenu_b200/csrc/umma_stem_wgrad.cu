@@ -223,6 +223,9 @@ int umma_conv_stem_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
+  plan_note("stem_wgrad ring=%d k_boxes=%d ~strips=%d ~grid=%d;", p.ring, p.k_boxes, p.strips, grid);
+  *splits_out = grid;
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   stem_wgrad_kernel<<<grid, 192, smem, ctx->stream>>>(ma, mb, p);
   prof_end(ctx, PROF_TENSOR, 2.0 * d->n * P * Q * d->k * d->c * d->kh * d->kw);

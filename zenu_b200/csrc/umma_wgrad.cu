@@ -309,6 +309,9 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     ZB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
+  plan_note("wgrad_halo R=%d S=%d a_boxes=%d stages=%d roles=%d tp=%d beta=%d ~splits=%d ~grid=%d;wgrad_reduce;", R, S, p.a_boxes, p.stages, roles,
+            p.tp, beta != 0.f ? 1 : 0, p.splits, roles * p.splits);
+  if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   wgrad_halo_kernel<<<roles * p.splits, 192, smem, ctx->stream>>>(ma, mb, p);
   prof_end(ctx, PROF_TENSOR, 2.0 * d->n * P * Q * d->k * d->c * R * S);

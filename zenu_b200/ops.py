@@ -172,6 +172,40 @@ def conv_bkwd_weight(ctx, dy, x, w_shape, pad=0, stride=1, dil=1, layout=ZB_NCHW
     return dw
 
 
+PLAN_FPROP, PLAN_DGRAD, PLAN_WGRAD = 0, 1, 2
+PLAN_BNSTATS, PLAN_BIAS, PLAN_ACCUMULATE = 1, 2, 4
+
+
+def conv_plan_describe(ctx, op, x_shape, w_shape, pad=0, stride=1, dil=1, layout=ZB_NHWC, math=ZB_MATH_DEFAULT, flags=0,
+                       dtype=torch.float32):
+    """The launches zb_conv2d_{fprop,dgrad,wgrad} would make for this geometry (dry run of the same planners, nothing is
+    launched or allocated): one "kernel<variant> key=value ...;" segment per launch; '~'-prefixed values depend on the batch."""
+    d = _desc(tuple(x_shape), tuple(w_shape), layout, pad, stride, dil)
+    need = ctx.lib.zb_conv2d_plan_describe(ctx.handle, op, _DT[dtype], layout, math, ctypes.byref(d), flags, None, 0)
+    if need < 0:
+        check(int(-need))
+    buf = ctypes.create_string_buffer(int(need))
+    ctx.lib.zb_conv2d_plan_describe(ctx.handle, op, _DT[dtype], layout, math, ctypes.byref(d), flags, buf, need)
+    return buf.value.decode()
+
+
+def plan_variant(text):
+    """A plan description without its batch-size-dependent ('~') values."""
+    return ";".join(" ".join(t for t in seg.split() if not t.startswith("~")) for seg in text.split(";") if seg.strip())
+
+
+def plan_trace(ctx, enable=True):
+    """Record the plan segments of the REAL conv / GEMM calls this thread makes from now on (read with plan_trace_read)."""
+    check(ctx.lib.zb_ctx_plan_trace(ctx.handle, int(bool(enable))))
+
+
+def plan_trace_read(ctx):
+    need = ctx.lib.zb_ctx_plan_trace_read(ctx.handle, None, 0)
+    buf = ctypes.create_string_buffer(int(need))
+    ctx.lib.zb_ctx_plan_trace_read(ctx.handle, buf, need)
+    return buf.value.decode()
+
+
 def _nkhw(shape, layout):
     return (shape[0], shape[1], shape[2], shape[3]) if layout == ZB_NCHW else (shape[0], shape[3], shape[1], shape[2])
 
