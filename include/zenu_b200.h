@@ -277,6 +277,24 @@ int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src
                          int64_t h, int64_t w, const double* host_mean, const double* host_std);
 int zb_onehot(zb_ctx* ctx, int dtype, const void* labels_i32, void* out, int64_t n, int64_t classes);
 
+/* Library-owned staging around those two kernels: `slots` (2..8) sets of pinned host buffers (uint8 images in src_layout + int32
+ * labels) and their device twins, a copy stream, and per-slot events.  The decoder fills slot s's pinned buffers
+ * (zb_input_stage_host_buffers; zb_input_stage_host_sync first when the slot is being reused), zb_input_stage_submit enqueues the
+ * host->device copy of the BYTES on the copy stream (it overlaps the training step of the previous batch), zb_input_stage_wait makes
+ * the ctx compute stream wait for that copy, expands the batch on the device and returns the model's inputs: x [n][c][h][w] and
+ * one-hot targets [n][classes] in `dtype` (device pointers, stable per slot).  Nothing synchronises the host except host_sync.
+ * Replaces zenu/src/dataset.rs:74-100 (per-sample Variables + CPU concat) + the synchronous f32 copy of Matrix::to::<Nvidia>()
+ * (zenu-matrix/src/matrix.rs:139-160,486). */
+typedef struct zb_input_stage zb_input_stage;
+int zb_input_stage_create(zb_ctx* ctx, int dtype, int src_layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t classes,
+                          const double* host_mean, const double* host_std, int slots, zb_input_stage** out);
+int zb_input_stage_destroy(zb_input_stage* st);
+int64_t zb_input_stage_h2d_bytes(const zb_input_stage* st); /* bytes one submit moves across PCIe */
+int zb_input_stage_host_buffers(zb_input_stage* st, int slot, void** images_u8, void** labels_i32);
+int zb_input_stage_host_sync(zb_input_stage* st, int slot);
+int zb_input_stage_submit(zb_input_stage* st, int slot);
+int zb_input_stage_wait(zb_input_stage* st, int slot, void** x_nchw, void** targets_onehot);
+
 /* ---- host model API (layers / tape / optimizer above the op ABI) -----------------------------------
  * C face of the C++ host side (zenu_b200/csrc/host): Module::call + Variable::backward + Optimizer::update
  * (reference: zenu-layer/src/lib.rs:21-51, zenu-autograd/src/lib.rs:413-420, zenu-optimizer/src/lib.rs:8-10)
@@ -333,6 +351,14 @@ int64_t zb_model_bytes_reserved(zb_model* m);
 typedef struct zb_ckpt zb_ckpt;
 int zb_model_save(zb_model* m, const char* path);
 int zb_model_load(zb_model* m, const char* path);
+/* Training-state files (DP resume): the same container with, next to the parameters, the optimizer state the reference
+ * keeps in memory only (zenu-optimizer/src/adam.rs:9-17,62-89: step, m and v as HashMap<String, Variable> keyed by parameter name):
+ * "optimizer.step" (scalar: updates done so far) and, for Adam / AdamW, "optimizer.m.<param>" / "optimizer.v.<param>" in the
+ * parameter's own reference layout.  zb_model_load_state restores all of it (set the optimizer kind and its hyper-parameters with
+ * zb_model_set_optimizer first; they are configuration, not state): training resumed from a state file continues bit-identically
+ * to the uninterrupted run.  A plain model file is also accepted (parameters only). */
+int zb_model_save_state(zb_model* m, const char* path);
+int zb_model_load_state(zb_model* m, const char* path);
 int zb_ckpt_write(const char* path, int dtype, int n, const char* const* names, const int* ndims,
                   const int64_t* const* shapes, const void* const* host_data);
 int zb_ckpt_open(const char* path, zb_ckpt** out);

@@ -108,3 +108,74 @@ def test_model_save_load_reference_layout(tmp_path):
     b.load(tmp_path / "partial.bin")
     assert float(b.named_parameters()["linear2.linear.bias"]["data"].min()) == 0.25
     a.close(); b.close(); ctx.close()
+
+
+def test_reader_rejects_hostile_shapes(tmp_path):
+    """A corrupt file must come back as the reference's "Failed to load model" error, never as an exception escaping the C
+    boundary or a giant allocation: extents are file content."""
+    data = [1.0, 2.0]
+    for shape, stride in (([1 << 40], [1]), ([1 << 62, 4], [4, 1]), ([(1 << 64) - 3], [1]), ([1 << 33, 1 << 33], [1, 1])):
+        p = tmp_path / "hostile.bin"
+        p.write_bytes(_u64(1) + _entry("w", shape, stride, data, "f32"))
+        with pytest.raises(ZenuB200Error, match="Failed to load model"):
+            checkpoint.read_state_dict(p)
+    p = tmp_path / "count.bin"
+    p.write_bytes(_u64(1 << 40))
+    with pytest.raises(ZenuB200Error, match="Failed to load model"):
+        checkpoint.read_state_dict(p)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opt", ["adamw", "adam", "sgd"])
+def test_resume_from_state_file_equals_uninterrupted_training(tmp_path, opt):
+    """zb_model_save_state / zb_model_load_state (parameters + Adam m / v + step): 3 steps, save, restore into a
+    freshly created model, 3 more steps == 6 uninterrupted steps, bit for bit (losses, parameters, BN running statistics)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from zenu_b200 import nn, ops
+    rng = np.random.default_rng(12)
+    xs = [torch.from_numpy(rng.standard_normal((16, 3, 32, 32)).astype(np.float32)).cuda() for _ in range(6)]
+    t = np.zeros((16, 10), np.float32)
+    t[np.arange(16), rng.integers(0, 10, 16)] = 1.0
+    T = torch.from_numpy(t).cuda()
+    kw = dict(kind=opt, lr=1e-3, weight_decay=0.01 if opt == "adamw" else 0.0)
+    ctx = ops.Context()
+    a = nn.Model(ctx, "small_cnn", 10, seed=1)
+    a.set_optimizer(**kw)
+    ref = [a.train_step(x, T, read_loss=True) for x in xs]
+    b = nn.Model(ctx, "small_cnn", 10, seed=1)
+    b.set_optimizer(**kw)
+    first = [b.train_step(x, T, read_loss=True) for x in xs[:3]]
+    path = tmp_path / "state.bin"
+    b.save_state(path)
+    sd = checkpoint.read_state_dict(path)
+    assert float(sd["optimizer.step"]) == 3.0
+    if opt != "sgd":   # Adam state is stored per parameter, in the parameter's reference layout (filters KCRS)
+        assert sd["optimizer.m.conv2.conv2d.filter"].shape == (64, 32, 3, 3) and sd["optimizer.v.linear2.linear.bias"].shape == (10,)
+        assert "optimizer.m.batch_norm1.batch_norm_2d.mean" not in sd
+        assert np.abs(sd["optimizer.v.conv2.conv2d.filter"]).max() > 0
+    else:
+        assert not any(k.startswith("optimizer.m.") for k in sd)
+    c = nn.Model(ctx, "small_cnn", 10, seed=99)          # different initial weights: everything must come from the file
+    c.set_optimizer(**kw)
+    c.load_state(path)
+    rest = [c.train_step(x, T, read_loss=True) for x in xs[3:]]
+    assert first + rest == ref
+    pa, pc = a.named_parameters(), c.named_parameters()
+    for k in pa:
+        assert torch.equal(pa[k]["data"], pc[k]["data"]), k
+    if opt != "sgd":   # Adam state into an SGD model is refused before anything is written
+        d = nn.Model(ctx, "small_cnn", 10, seed=5)
+        d.set_optimizer("sgd", lr=1e-3)
+        before = d.named_parameters()["linear2.linear.weight"]["data"].clone()
+        with pytest.raises(ZenuB200Error):
+            d.load_state(path)
+        assert torch.equal(before, d.named_parameters()["linear2.linear.weight"]["data"])
+        d.close()
+    # a plain model file (reference format) is a valid state file, and a state file is NOT a valid plain model file
+    c.save(tmp_path / "plain.bin")
+    c.load_state(tmp_path / "plain.bin")
+    with pytest.raises(ZenuB200Error):
+        c.load(path)
+    a.close(); b.close(); c.close(); ctx.close()

@@ -265,3 +265,63 @@ def test_bad_arch_reports_error(zb):
     with pytest.raises(pkg.ZenuB200Error):
         nn.Model(ctx, "vgg16", 10)
     ctx.close()
+
+
+def test_step_graphs_with_changing_shapes_and_scratch_growth(zb):
+    """(1) every new (buffers, shape) signature warms up eagerly on its own before it is captured -- a larger batch
+    arriving after the first capture must not be captured on its first step (its scratch / activation buffers do not exist yet);
+    (2) the ctx scratch arena is part of a captured step: when a later call on the same ctx makes it grow (here a wgrad with large
+    split-K partials) the graphs are dropped instead of replaying with a dangling pointer; (3) train / eval mode is part of the
+    signature.  The whole sequence must match an eager twin bit for bit."""
+    pkg, ops, nn = zb
+    xa, ta = batch(16, 32, 10, 21)
+    xb, tb = batch(48, 32, 10, 22)
+    XA, TA, XB, TB = (torch.from_numpy(a).cuda() for a in (xa, ta, xb, tb))
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    runs = []
+    for use_graph in (False, True):
+        with torch.cuda.stream(side):
+            ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+            model = nn.Model(ctx, "small_cnn", 10, seed=4)
+            model.set_optimizer("sgd", lr=1e-3)
+            if use_graph:
+                model.set_graph(True)
+            la = torch.empty((1,), dtype=torch.float32, device="cuda")
+            lb = torch.empty((1,), dtype=torch.float32, device="cuda")
+            losses, counts = [], []
+            for _ in range(4):
+                losses.append(model.train_step(XA, TA, loss_out=la, read_loss=True))
+                counts.append(model.graph_count())
+            for _ in range(4):     # larger batch: runs eagerly first; that step grows the scratch arena, so the first graph is dropped
+                losses.append(model.train_step(XB, TB, loss_out=lb, read_loss=True))
+                counts.append(model.graph_count())
+            for _ in range(3):     # back to the small batch: its graph is re-captured after its own warm-up, next to the other one
+                losses.append(model.train_step(XA, TA, loss_out=la, read_loss=True))
+                counts.append(model.graph_count())
+            if use_graph:
+                assert counts == [0, 0, 1, 1, 1, 0, 0, 1, 1, 1, 2], counts
+            # an unrelated op on the same ctx that needs far more scratch than the model ever used (split-K partials of a wgrad)
+            dy = torch.randn((16, 14, 14, 512), device="cuda")
+            x = torch.randn((16, 14, 14, 512), device="cuda")
+            ops.conv_bkwd_weight(ctx, dy, x, (512, 5, 5, 512), pad=2, stride=1, dil=1, layout=pkg.ZB_NHWC)   # >= 2 x 26 MB of partials
+            for _ in range(3):
+                losses.append(model.train_step(XA, TA, loss_out=la, read_loss=True))
+                counts.append(model.graph_count())
+            if use_graph:
+                assert counts[-3:] == [0, 0, 1], counts           # dropped with the arena, warmed up and captured again
+            model.train(False)
+            logits = model.forward(XA).clone()
+            model.train(True)
+            losses.append(model.train_step(XB, TB, loss_out=lb, read_loss=True))
+            ctx.check()
+            params = {k: v["data"].clone() for k, v in model.named_parameters().items()}
+            runs.append((losses, params, logits))
+            model.close()
+            ctx.close()
+        torch.cuda.synchronize()
+    (l0, p0, g0), (l1, p1, g1) = runs
+    assert all(np.isfinite(l0)) and l0 == l1
+    assert torch.equal(g0, g1)
+    for k in p0:
+        assert torch.equal(p0[k], p1[k]), k

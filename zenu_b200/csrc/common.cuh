@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <string>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,6 +38,8 @@ struct zb_ctx {
   bool owns_stream;
   void* ws;                  // library-owned scratch (split-K partials, BN partial sums, layout staging)
   size_t ws_bytes;
+  unsigned long long ws_generation;  // bumped whenever ws is reallocated: captured step graphs bake the address in
+  bool ws_grow_refused;      // a call needed more scratch while the stream was being captured (the capture must be abandoned)
   int* err_flag;             // device word: set by a kernel whose mbarrier wait timed out
   zb::EncodeTiledFn encode_tiled;
   zb::EncodeIm2colFn encode_im2col;
@@ -100,6 +103,21 @@ void plan_note(const char* fmt, ...);
       ZB_LAUNCH_CHECK(ctx);             \
     }                                   \
   } while (0)
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per kernel AND per device, so the "already done" state is kept per
+// device ordinal (a process may own contexts on several GPUs); each launcher holds one function-local static SmemOptIn.
+struct SmemOptIn {
+  static constexpr int kMaxDevices = 64;
+  std::atomic<size_t> bytes[kMaxDevices];
+};
+template <typename K>
+static inline int smem_opt_in(zb_ctx* ctx, SmemOptIn& st, K kernel, size_t bytes) {
+  const int dev = ctx->device;
+  if (dev >= 0 && dev < SmemOptIn::kMaxDevices && st.bytes[dev].load(std::memory_order_relaxed) >= bytes) return ZB_OK;
+  ZB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  if (dev >= 0 && dev < SmemOptIn::kMaxDevices) st.bytes[dev].store(bytes, std::memory_order_relaxed);
+  return ZB_OK;
+}
 
 // Per-op timing with CUDA events on the launching stream, grouped by kernel class (bench.py roofline):
 // class 0 = tcgen05 implicit-GEMM / GEMM launches (work = algorithmic FLOPs),

@@ -68,7 +68,16 @@ int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out) {
     return ZB_OK;
   }
   if (bytes > ctx->ws_bytes) {
+    // Never grow inside a stream capture: the free / malloc would become nodes of the graph (ctx->ws a graph-owned allocation that
+    // later eager kernels dereference).  The capturing caller abandons the capture and runs the step eagerly (model_api.cu).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+      ctx->ws_grow_refused = true;
+      set_last_error("scratch arena would have to grow (%zu -> %zu bytes) during stream capture", ctx->ws_bytes, bytes);
+      return ZB_ERR_UNSUPPORTED;
+    }
     // stream-ordered: kernels already enqueued keep using the old block until they retire
+    ++ctx->ws_generation;
     if (ctx->ws) ZB_CHECK_CUDA(cudaFreeAsync(ctx->ws, ctx->stream));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;

@@ -105,8 +105,17 @@ int zb_ckpt_write(const char* path, int dtype, int n, const char* const* names, 
   return write_file(path, w.buf);
 }
 
+static int ckpt_open_impl(const char* path, zb_ckpt** out);
 int zb_ckpt_open(const char* path, zb_ckpt** out) {
   ZB_REQUIRE(path && out, "zb_ckpt_open: NULL argument");
+  try {   // nothing thrown by the parser (bad_alloc, length_error on hostile sizes) may cross the C boundary
+    return ckpt_open_impl(path, out);
+  } catch (const std::exception& e) {
+    zb::set_last_error("Failed to load model: %s", e.what());
+    return ZB_ERR_INVALID;
+  }
+}
+static int ckpt_open_impl(const char* path, zb_ckpt** out) {
   FILE* f = fopen(path, "rb");
   if (!f) { zb::set_last_error("Failed to load model: cannot open %s", path); return ZB_ERR_INVALID; }
   std::vector<uint8_t> bin;
@@ -145,8 +154,16 @@ int zb_ckpt_open(const char* path, zb_ckpt** out) {
     e.ptr_offset = static_cast<int64_t>(r.u64());
     ZB_REQUIRE(r.ok, "Failed to load model: truncated entry '%s'", e.name.c_str());
     const size_t esz = dtype == ZB_F64 ? 8 : 4;
+    // the shape is file content: every extent must be non-negative and the element count (overflow-checked) can never exceed
+    // the elements the entry actually carries (a broadcast view, stride 0, may be smaller than len but never larger)
     int64_t numel = 1;
-    for (int64_t d : e.shape) numel *= d;
+    for (int64_t d : e.shape) {
+      ZB_REQUIRE(d >= 0, "Failed to load model: negative extent in the shape of '%s'", e.name.c_str());
+      ZB_REQUIRE(d == 0 || numel <= static_cast<int64_t>(bin.size()) / d, "Failed to load model: shape of '%s' is larger than the file",
+                 e.name.c_str());
+      numel *= d;
+    }
+    ZB_REQUIRE(static_cast<uint64_t>(numel) * esz <= bin.size(), "Failed to load model: shape of '%s' is larger than the file", e.name.c_str());
     // resolve (shape, stride, ptr_offset) into a dense row-major copy (Matrix::new(ptr, shape, stride), impl_serde.rs:160-168)
     e.data.resize(static_cast<size_t>(numel) * esz);
     std::vector<int64_t> idx(e.shape.size(), 0);
@@ -194,6 +211,8 @@ namespace zb { namespace host {
 ParamStore& model_params(zb_model* m);
 zb_ctx* model_ctx(zb_model* m);
 int model_dtype(zb_model* m);
+Optimizer& model_optimizer(zb_model* m);
+void model_drop_graphs(zb_model* m);
 } }
 
 static bool ends_with(const std::string& s, const char* suf) {
@@ -217,42 +236,106 @@ static void kcrs_to_krsc(const T* src, T* dst, int64_t K, int64_t C, int64_t R, 
         for (int64_t s = 0; s < S; ++s) dst[((k * R + r) * S + s) * C + c] = src[((k * C + c) * R + r) * S + s];
 }
 
-extern "C" {
+// one tensor of the model (a parameter, or the slice of an optimizer-state buffer that belongs to it) -> a file entry in the
+// reference's layout: filters KCRS, conv bias [1,K,1,1]
+static int append_device_tensor(Writer& w, const std::string& key, const std::string& param_name, const void* dev, const std::vector<int64_t>& dev_shape,
+                                int dtype, std::vector<uint8_t>& host, std::vector<uint8_t>& conv) {
+  const size_t esz = dtype == ZB_F64 ? 8 : 4;
+  int64_t numel = 1;
+  for (int64_t d : dev_shape) numel *= d;
+  host.resize(static_cast<size_t>(numel) * esz);
+  ZB_CHECK_CUDA(cudaMemcpy(host.data(), dev, host.size(), cudaMemcpyDeviceToHost));
+  std::vector<int64_t> shape = dev_shape;
+  const void* data = host.data();
+  if (ends_with(param_name, "conv2d.filter") && shape.size() == 4) {
+    conv.resize(host.size());
+    const int64_t K = shape[0], R = shape[1], S = shape[2], C = shape[3];
+    if (dtype == ZB_F64) krsc_to_kcrs(reinterpret_cast<const double*>(host.data()), reinterpret_cast<double*>(conv.data()), K, R, S, C);
+    else krsc_to_kcrs(reinterpret_cast<const float*>(host.data()), reinterpret_cast<float*>(conv.data()), K, R, S, C);
+    shape = {K, C, R, S};
+    data = conv.data();
+  } else if (ends_with(param_name, "conv2d.bias") && shape.size() == 1) {
+    shape = {1, shape[0], 1, 1};   // zenu-layer/src/layers/conv2d.rs:99
+  }
+  append_entry(w, key, shape, dtype, data);
+  return ZB_OK;
+}
 
-int zb_model_save(zb_model* m, const char* path) {
-  ZB_REQUIRE(m && path, "zb_model_save: NULL argument");
+// a file entry -> the device tensor of parameter `param_name` (or its optimizer-state slice); shapes validated by the caller
+static int load_device_tensor(const zb_ckpt_entry_t& e, const std::string& param_name, void* dev, const std::vector<int64_t>& dev_shape, int dtype,
+                              std::vector<uint8_t>& conv) {
+  const size_t esz = dtype == ZB_F64 ? 8 : 4;
+  const void* src = e.data.data();
+  if (ends_with(param_name, "conv2d.filter") && dev_shape.size() == 4) {
+    conv.resize(e.data.size());
+    const int64_t K = e.shape[0], C = e.shape[1], R = e.shape[2], S = e.shape[3];
+    if (dtype == ZB_F64) kcrs_to_krsc(reinterpret_cast<const double*>(e.data.data()), reinterpret_cast<double*>(conv.data()), K, C, R, S);
+    else kcrs_to_krsc(reinterpret_cast<const float*>(e.data.data()), reinterpret_cast<float*>(conv.data()), K, C, R, S);
+    src = conv.data();
+  }
+  int64_t numel = 1;
+  for (int64_t d : dev_shape) numel *= d;
+  ZB_CHECK_CUDA(cudaMemcpy(dev, src, static_cast<size_t>(numel) * esz, cudaMemcpyHostToDevice));
+  return ZB_OK;
+}
+
+static int check_entry_against(const zb_ckpt_entry_t& e, const std::string& param_name, const Tensor& t, int dtype) {
+  ZB_REQUIRE(e.dtype == dtype, "Failed to load model: Data type mismatch in '%s'", e.name.c_str());
+  int64_t numel = 1;
+  for (int64_t d : e.shape) numel *= d;
+  ZB_REQUIRE(numel == t.numel(), "Failed to load model: '%s' has %lld elements, the model expects %lld", e.name.c_str(),
+             static_cast<long long>(numel), static_cast<long long>(t.numel()));
+  if (ends_with(param_name, "conv2d.filter") && t.shape.size() == 4)
+    ZB_REQUIRE(e.shape.size() == 4 && e.shape[0] == t.shape[0] && e.shape[1] == t.shape[3] && e.shape[2] == t.shape[1] &&
+                   e.shape[3] == t.shape[2], "Failed to load model: filter '%s' shape mismatch (KCRS expected)", e.name.c_str());
+  return ZB_OK;
+}
+
+// Training-state files (zb_model_save_state / zb_model_load_state): the same container with, next to the parameters, the optimizer
+// state the reference keeps in memory only (zenu-optimizer/src/adam.rs:9-17: step, m and v as HashMap<String, Variable> keyed by the
+// parameter names): "optimizer.step" (scalar, completed updates), and for Adam / AdamW "optimizer.m.<param>" / "optimizer.v.<param>"
+// in the parameter's own reference layout.  A plain model file is a valid state file without optimizer entries.
+static const char kOptStep[] = "optimizer.step";
+static const char kOptM[] = "optimizer.m.";
+static const char kOptV[] = "optimizer.v.";
+
+static int save_impl(zb_model* m, const char* path, bool with_state) {
   ParamStore& ps = model_params(m);
   zb_ctx* ctx = model_ctx(m);
   const int dtype = model_dtype(m);
   const size_t esz = dtype == ZB_F64 ? 8 : 4;
+  Optimizer& opt = model_optimizer(m);
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  const bool adam = with_state && opt.kind != OPT_SGD && opt.m.defined() && opt.v.defined();
+  size_t count = ps.entries.size();
+  if (with_state) {
+    ++count;
+    if (adam)
+      for (const ParamEntry& e : ps.entries) count += e.kind != 2 ? 2 : 0;
+  }
   Writer w;
-  w.u64(ps.entries.size());
+  w.u64(count);
   std::vector<uint8_t> host, conv;
-  for (const ParamEntry& e : ps.entries) {
-    const Tensor& t = e.var->data;
-    const int64_t numel = t.numel();
-    host.resize(static_cast<size_t>(numel) * esz);
-    ZB_CHECK_CUDA(cudaMemcpy(host.data(), t.ptr, host.size(), cudaMemcpyDeviceToHost));
-    std::vector<int64_t> shape = t.shape;
-    const void* data = host.data();
-    if (ends_with(e.name, "conv2d.filter") && shape.size() == 4) {
-      conv.resize(host.size());
-      const int64_t K = shape[0], R = shape[1], S = shape[2], C = shape[3];
-      if (dtype == ZB_F64) krsc_to_kcrs(reinterpret_cast<const double*>(host.data()), reinterpret_cast<double*>(conv.data()), K, R, S, C);
-      else krsc_to_kcrs(reinterpret_cast<const float*>(host.data()), reinterpret_cast<float*>(conv.data()), K, R, S, C);
-      shape = {K, C, R, S};
-      data = conv.data();
-    } else if (ends_with(e.name, "conv2d.bias") && shape.size() == 1) {
-      shape = {1, shape[0], 1, 1};   // zenu-layer/src/layers/conv2d.rs:99
-    }
-    append_entry(w, e.name, shape, dtype, data);
+  int rc;
+  for (const ParamEntry& e : ps.entries)
+    if ((rc = append_device_tensor(w, e.name, e.name, e.var->data.ptr, e.var->data.shape, dtype, host, conv)) != ZB_OK) return rc;
+  if (with_state) {
+    const double step_d = static_cast<double>(opt.step);
+    const float step_f = static_cast<float>(opt.step);
+    append_entry(w, kOptStep, {}, dtype, dtype == ZB_F64 ? static_cast<const void*>(&step_d) : static_cast<const void*>(&step_f));
+    if (adam)
+      for (const ParamEntry& e : ps.entries) {
+        if (e.kind == 2) continue;   // buffers (BN running statistics) have no gradient and no optimizer state
+        const uint8_t* mp = static_cast<const uint8_t*>(opt.m.ptr) + e.offset * esz;
+        const uint8_t* vp = static_cast<const uint8_t*>(opt.v.ptr) + e.offset * esz;
+        if ((rc = append_device_tensor(w, kOptM + e.name, e.name, mp, e.var->data.shape, dtype, host, conv)) != ZB_OK) return rc;
+        if ((rc = append_device_tensor(w, kOptV + e.name, e.name, vp, e.var->data.shape, dtype, host, conv)) != ZB_OK) return rc;
+      }
   }
   return write_file(path, w.buf);
 }
 
-int zb_model_load(zb_model* m, const char* path) {
-  ZB_REQUIRE(m && path, "zb_model_load: NULL argument");
+static int load_impl(zb_model* m, const char* path, bool with_state) {
   zb_ckpt* ck = nullptr;
   int rc = zb_ckpt_open(path, &ck);
   if (rc != ZB_OK) return rc;
@@ -261,37 +344,74 @@ int zb_model_load(zb_model* m, const char* path) {
   zb_ctx* ctx = model_ctx(m);
   const int dtype = model_dtype(m);
   const size_t esz = dtype == ZB_F64 ? 8 : 4;
+  Optimizer& opt = model_optimizer(m);
   std::map<std::string, const ParamEntry*> by_name;
   for (const ParamEntry& e : ps.entries) by_name[e.name] = &e;
   // validate everything before touching the model
   for (const zb_ckpt_entry_t& e : ck->entries) {
-    auto it = by_name.find(e.name);
+    std::string pname = e.name;
+    if (with_state && e.name == kOptStep) {
+      ZB_REQUIRE(e.dtype == dtype && e.data.size() == esz, "Failed to load model: bad '%s' entry", kOptStep);
+      continue;
+    }
+    const bool is_m = with_state && e.name.compare(0, sizeof(kOptM) - 1, kOptM) == 0;
+    const bool is_v = with_state && e.name.compare(0, sizeof(kOptV) - 1, kOptV) == 0;
+    if (is_m || is_v) {
+      pname = e.name.substr(sizeof(kOptM) - 1);
+      ZB_REQUIRE(opt.kind != OPT_SGD && opt.m.defined() && opt.v.defined(),
+                 "Failed to load model: the file carries Adam state ('%s') but the model's optimizer is not Adam / AdamW "
+                 "(call zb_model_set_optimizer first)", e.name.c_str());
+    }
+    auto it = by_name.find(pname);
     ZB_REQUIRE(it != by_name.end(), "Failed to load model: the model has no parameter '%s'", e.name.c_str());
-    ZB_REQUIRE(e.dtype == dtype, "Failed to load model: Data type mismatch in '%s'", e.name.c_str());
-    int64_t numel = 1;
-    for (int64_t d : e.shape) numel *= d;
-    const Tensor& t = it->second->var->data;
-    ZB_REQUIRE(numel == t.numel(), "Failed to load model: '%s' has %lld elements, the model expects %lld", e.name.c_str(),
-               static_cast<long long>(numel), static_cast<long long>(t.numel()));
-    if (ends_with(e.name, "conv2d.filter") && t.shape.size() == 4)
-      ZB_REQUIRE(e.shape.size() == 4 && e.shape[0] == t.shape[0] && e.shape[1] == t.shape[3] && e.shape[2] == t.shape[1] &&
-                     e.shape[3] == t.shape[2], "Failed to load model: filter '%s' shape mismatch (KCRS expected)", e.name.c_str());
+    ZB_REQUIRE(!(is_m || is_v) || it->second->kind != 2, "Failed to load model: '%s' names a buffer, which has no optimizer state", e.name.c_str());
+    if ((rc = check_entry_against(e, pname, it->second->var->data, dtype)) != ZB_OK) return rc;
   }
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<uint8_t> conv;
   for (const zb_ckpt_entry_t& e : ck->entries) {
-    const Tensor& t = by_name[e.name]->var->data;
-    const void* src = e.data.data();
-    if (ends_with(e.name, "conv2d.filter") && t.shape.size() == 4) {
-      conv.resize(e.data.size());
-      const int64_t K = e.shape[0], C = e.shape[1], R = e.shape[2], S = e.shape[3];
-      if (dtype == ZB_F64) kcrs_to_krsc(reinterpret_cast<const double*>(e.data.data()), reinterpret_cast<double*>(conv.data()), K, C, R, S);
-      else kcrs_to_krsc(reinterpret_cast<const float*>(e.data.data()), reinterpret_cast<float*>(conv.data()), K, C, R, S);
-      src = conv.data();
+    if (with_state && e.name == kOptStep) {
+      const double v = dtype == ZB_F64 ? *reinterpret_cast<const double*>(e.data.data()) : static_cast<double>(*reinterpret_cast<const float*>(e.data.data()));
+      ZB_REQUIRE(v >= 0.0 && v < 9.0e15, "Failed to load model: bad optimizer step %g", v);
+      opt.step = static_cast<int64_t>(v);
+      opt.tbl_first = 0;   // the device table of Adam bias corrections is refilled from the restored step on the next update
+      continue;
     }
-    ZB_CHECK_CUDA(cudaMemcpy(t.ptr, src, static_cast<size_t>(t.numel()) * esz, cudaMemcpyHostToDevice));
+    const bool is_m = with_state && e.name.compare(0, sizeof(kOptM) - 1, kOptM) == 0;
+    const bool is_v = with_state && e.name.compare(0, sizeof(kOptV) - 1, kOptV) == 0;
+    if (is_m || is_v) {
+      const ParamEntry* pe = by_name[e.name.substr(sizeof(kOptM) - 1)];
+      uint8_t* base = static_cast<uint8_t*>(is_m ? opt.m.ptr : opt.v.ptr) + pe->offset * esz;
+      if ((rc = load_device_tensor(e, pe->name, base, pe->var->data.shape, dtype, conv)) != ZB_OK) return rc;
+    } else {
+      const ParamEntry* pe = by_name[e.name];
+      if ((rc = load_device_tensor(e, pe->name, pe->var->data.ptr, pe->var->data.shape, dtype, conv)) != ZB_OK) return rc;
+    }
   }
+  model_drop_graphs(m);   // captured steps stay valid address-wise, but a restored step count re-bases the Adam table window
   return ZB_OK;
+}
+
+extern "C" {
+
+int zb_model_save(zb_model* m, const char* path) {
+  ZB_REQUIRE(m && path, "zb_model_save: NULL argument");
+  return save_impl(m, path, false);
+}
+
+int zb_model_load(zb_model* m, const char* path) {
+  ZB_REQUIRE(m && path, "zb_model_load: NULL argument");
+  return load_impl(m, path, false);
+}
+
+int zb_model_save_state(zb_model* m, const char* path) {
+  ZB_REQUIRE(m && path, "zb_model_save_state: NULL argument");
+  return save_impl(m, path, true);
+}
+
+int zb_model_load_state(zb_model* m, const char* path) {
+  ZB_REQUIRE(m && path, "zb_model_load_state: NULL argument");
+  return load_impl(m, path, true);
 }
 
 }  // extern "C"

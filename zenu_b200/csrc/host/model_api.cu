@@ -18,21 +18,35 @@ struct zb_model {
   bool opt_ready = false;
   Variable last_loss;
   // CUDA-graph replay of the train step (zb_model_set_graph): one instantiated graph per distinct call signature
-  struct StepGraph {
+  // A captured step bakes in every address and every host-side decision: the call signature below, the activation allocator's
+  // blocks (Allocator::generation), the ctx scratch arena (zb_ctx::ws_generation), train / eval mode, the math mode and the
+  // data-parallel world (bucket allreduces are nodes of the graph).
+  struct StepSig {
     const void* x; const void* t; void* loss_dev;
     int64_t b, c, h, w;
-    uint64_t generation;        // Allocator::generation() at capture time
-    unsigned long long launches;  // kernels per replay (for zb_ctx_launch_count)
+    bool train;
+    int math, world;
+    bool operator==(const StepSig& o) const {
+      return x == o.x && t == o.t && loss_dev == o.loss_dev && b == o.b && c == o.c && h == o.h && w == o.w && train == o.train &&
+             math == o.math && world == o.world;
+    }
+  };
+  struct StepGraph {
+    StepSig sig;
+    uint64_t generation;              // Allocator::generation() at capture time
+    unsigned long long ws_generation; // zb_ctx::ws_generation at capture time
+    unsigned long long launches;      // kernels per replay (for zb_ctx_launch_count)
     cudaGraphExec_t exec;
   };
+  struct WarmUp { StepSig sig; int eager; };   // eager steps run per signature before it is captured (two: allocator + arena settle)
   bool graph_enabled = false;
-  int eager_steps = 0;          // steps run eagerly since the last (re)configuration: capture starts after two
+  std::vector<WarmUp> warm;
   std::vector<StepGraph> graphs;
   void* pinned_loss = nullptr;  // 8 bytes of pinned host memory: the loss read-back node of the graphs
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     graphs.clear();
-    eager_steps = 0;
+    warm.clear();
   }
 };
 
@@ -52,6 +66,8 @@ namespace zb { namespace host {   // accessors for checkpoint.cu
 ParamStore& model_params(zb_model* m) { return m->params; }
 zb_ctx* model_ctx(zb_model* m) { return m->ctx; }
 int model_dtype(zb_model* m) { return m->rt->dtype; }
+Optimizer& model_optimizer(zb_model* m) { return m->opt; }
+void model_drop_graphs(zb_model* m) { m->drop_graphs(); }
 } }
 
 static Variable run_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w) {
@@ -194,14 +210,33 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
   if (!m->graph_enabled || !m->opt_ready || m->rt->prof.enabled || zb::prof_active(ctx)) return 0;
   const size_t esz = m->rt->dtype == ZB_F64 ? 8 : 4;
   const uint64_t gen = m->rt->alloc.generation();
+  const zb_model::StepSig sig{x, t, loss_dev, b, c, h, w, m->rt->train, ctx->default_math, zb_dp_world(ctx)};
   zb_model::StepGraph* hit = nullptr;
   for (auto& g : m->graphs)
-    if (g.x == x && g.t == t && g.loss_dev == loss_dev && g.b == b && g.c == c && g.h == h && g.w == w) hit = &g;
-  if (hit && hit->generation != gen) { m->drop_graphs(); hit = nullptr; }
+    if (g.sig == sig) hit = &g;
+  // any captured step whose buffers went away is unusable, and so are its siblings (they share the allocator and the arena)
+  if (!m->graphs.empty() && (m->graphs.front().generation != gen || m->graphs.front().ws_generation != ctx->ws_generation)) {
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+    for (auto& wu : m->warm) wu.eager = 0;   // every signature warms up again before it is re-captured
+    hit = nullptr;
+  }
   if (!hit) {
-    if (m->eager_steps < 2) { ++m->eager_steps; return 0; }
-    if (m->graphs.size() >= 4) m->drop_graphs();   // callers rotating through many buffers: start over rather than grow
+    zb_model::WarmUp* wu = nullptr;
+    for (auto& e : m->warm)
+      if (e.sig == sig) wu = &e;
+    if (wu == nullptr) {
+      if (m->warm.size() >= 16) m->warm.clear();
+      m->warm.push_back({sig, 0});
+      wu = &m->warm.back();
+    }
+    if (wu->eager < 2) { ++wu->eager; return 0; }   // per signature: a new batch shape runs eagerly twice before its capture
+    if (m->graphs.size() >= 4) {   // callers rotating through many buffers: start over rather than grow
+      for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+      m->graphs.clear();
+    }
     const unsigned long long l0 = ctx->launches;
+    ctx->ws_grow_refused = false;
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
       cudaGetLastError();            // e.g. the ctx runs on the legacy default stream, which cannot be captured
@@ -220,6 +255,11 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
     if (rc != ZB_OK || ce != cudaSuccess || graph == nullptr) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
+      if (ctx->ws_grow_refused) {   // the arena had to grow: not capturable yet.  Nothing ran; this step goes eagerly and warms up again
+        ctx->ws_grow_refused = false;
+        wu->eager = 1;
+        return 0;
+      }
       if (rc != ZB_OK) return rc < 0 ? rc : -rc;   // the step's own error (message already recorded)
       m->graph_enabled = false;                    // this step cannot be captured: stay eager from now on
       return 0;
@@ -228,7 +268,7 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { cudaGetLastError(); m->graph_enabled = false; return 0; }
-    m->graphs.push_back({x, t, loss_dev, b, c, h, w, m->rt->alloc.generation(), captured, exec});
+    m->graphs.push_back({sig, m->rt->alloc.generation(), ctx->ws_generation, captured, exec});
     hit = &m->graphs.back();
   }
   try {

@@ -401,10 +401,22 @@ static int softmax_xent_t(zb_ctx* ctx, const T* z, const T* t, T* loss, T* dz, l
 
 using namespace zb;
 
+// argument validation shared by the pooling entry points (the conv entry points do the same through check_desc, api.cu)
+static int check_pool_args(int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw,
+                           int64_t ph, int64_t pw) {
+  ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "pool: unknown layout %d", layout);
+  ZB_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && kh > 0 && kw > 0, "pool: non-positive extent");
+  ZB_REQUIRE(sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "pool: bad stride / padding");
+  ZB_REQUIRE(h + 2 * ph >= kh && w + 2 * pw >= kw, "pool: window larger than the padded input");
+  ZB_REQUIRE(kh <= 255 && kw <= 255 && n * c * h * w < (1ll << 40), "pool: extent too large");
+  return ZB_OK;
+}
+
 extern "C" {
 
 int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t h, int64_t w,
                      int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  { const int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw); if (rc != ZB_OK) return rc; }
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_fwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<float*>(y));
   if (dtype == ZB_F64) return maxpool_fwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<double*>(y));
@@ -413,6 +425,7 @@ int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y,
 }
 int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const void* dy, void* dx, int64_t n, int64_t c,
                      int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  { const int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw); if (rc != ZB_OK) return rc; }
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_bwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx));
   if (dtype == ZB_F64) return maxpool_bwd_t<double>(ctx, g, static_cast<const double*>(x), static_cast<const double*>(dy), static_cast<double*>(dx));
@@ -427,7 +440,9 @@ static int check_idx_pool(int layout, int64_t c, int64_t kh, int64_t kw, const v
 }
 int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, void* idx, int64_t n, int64_t c, int64_t h,
                          int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
-  int rc = check_idx_pool(layout, c, kh, kw, x, y);
+  int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (rc != ZB_OK) return rc;
+  rc = check_idx_pool(layout, c, kh, kw, x, y);
   if (rc != ZB_OK) return rc;
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_idx_fwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<float*>(y), idx);
@@ -437,7 +452,9 @@ int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void
 }
 int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, const void* idx, void* dx, int64_t n, int64_t c,
                          int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
-  int rc = check_idx_pool(layout, c, kh, kw, dy, dx);
+  int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
+  if (rc != ZB_OK) return rc;
+  rc = check_idx_pool(layout, c, kh, kw, dy, dx);
   if (rc != ZB_OK) return rc;
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_idx_bwd_t<float>(ctx, g, static_cast<const float*>(dy), idx, static_cast<float*>(dx));
@@ -446,6 +463,7 @@ int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, con
   return ZB_ERR_INVALID;
 }
 int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t hw) {
+  ZB_REQUIRE((layout == ZB_NCHW || layout == ZB_NHWC) && n >= 0 && c >= 0 && hw > 0, "global average pool: bad layout / extent");
   const long long total = n * c;
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));
@@ -456,6 +474,7 @@ int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64
   return ZB_OK;
 }
 int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int64_t n, int64_t c, int64_t hw) {
+  ZB_REQUIRE((layout == ZB_NCHW || layout == ZB_NHWC) && n >= 0 && c >= 0 && hw > 0, "global average pool: bad layout / extent");
   const long long total = n * c * hw;
   if (total == 0) return ZB_OK;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 16ll));

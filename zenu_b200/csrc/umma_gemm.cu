@@ -1212,11 +1212,8 @@ template <int BN, int STAGES, bool OLD = false>
 static int launch_cfg(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   using L = UmmaSmem<BN, STAGES, OLD>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES, OLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  { const int rc = smem_opt_in(ctx, opt_in, umma_kernel<BN, STAGES, OLD>, L::TOTAL); if (rc != ZB_OK) return rc; }
   const int grid = launch_grid(ctx, p, 1);
   note_umma(p, BN, STAGES, OLD, 1, grid);
   if (plan_dry()) return ZB_OK;
@@ -1233,11 +1230,8 @@ template <int BN, int STAGES, bool OLD = false>
 static int launch_cfg_pair(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p) {
   using L = UmmaSmem<BN, STAGES, OLD, 2>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<BN, STAGES, OLD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  { const int rc = smem_opt_in(ctx, opt_in, umma_kernel<BN, STAGES, OLD, 2>, L::TOTAL); if (rc != ZB_OK) return rc; }
   CUtensorMap b2 = b;
   if (p.b_mode == B_TILED_K) {
     const int rc = make_map_2d(ctx, &b2, p.hb_base, p.hb_inner, p.hb_outer, p.hb_pitch, 32, BN / 2);
@@ -1482,11 +1476,8 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
 
 template <int BN, int CL, bool PAIR = false>
 static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, size_t smem, int grid) {
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(halo_conv_kernel<BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
+  static SmemOptIn opt_in;
+  { const int rc = smem_opt_in(ctx, opt_in, halo_conv_kernel<BN, CL, PAIR>, smem); if (rc != ZB_OK) return rc; }
   plan_note("halo_conv<bn=%d,cl=%d,pair=%d> resident=%d slots=%d b_stages=%d n_tiles=%d ntaps=%d c_chunks=%d beta=%d bias=%d stats=%d chain=%d tp=%d "
             "~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
             p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.m_tiles, grid);
@@ -2009,11 +2000,8 @@ static int smallc_pack_input(zb_ctx* ctx, const zb_conv2d_desc* d, const SmallcG
 
 template <int BN>
 static int stem_fprop_launch(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int grid, size_t smem) {
-  static size_t attr = 0;   // per instantiation: each kernel needs its own opt-in to > 48 KB of dynamic shared memory
-  if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
+  static SmemOptIn opt_in;   // per instantiation: each kernel needs its own opt-in to > 48 KB of dynamic shared memory
+  { const int rc = smem_opt_in(ctx, opt_in, stem_fprop_kernel<BN>, smem); if (rc != ZB_OK) return rc; }
   plan_note("stem_fprop<bn=%d> stages=%d taps=%d beta=%d bias=%d stats=%d ~m_tiles=%d ~grid=%d;", BN, p.halo_slots, p.ntaps, p.beta != 0.f ? 1 : 0,
             p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.m_tiles, grid);
   if (plan_dry()) return ZB_OK;

@@ -297,11 +297,8 @@ int umma_conv_stem_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (stem dgrad filter) failed (%d)", int(r)); return ZB_ERR_CUDA; }
   }
   const size_t smem = static_cast<size_t>(p.b_tiles) * 4096 + static_cast<size_t>(p.stages) * 16384 + 2 * 16384 + 512 + 1024;
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
+  static SmemOptIn opt_in;
+  { const int rc2 = smem_opt_in(ctx, opt_in, stem_dgrad_kernel, smem); if (rc2 != ZB_OK) return rc2; }
   const int grid = std::min(p.total_tiles, ctx->sm_count);
   plan_note("stem_dgrad stages=%d b_tiles=%d beta=%d ~tiles=%d ~grid=%d;", p.stages, p.b_tiles, beta != 0.f ? 1 : 0, p.total_tiles, grid);
   if (plan_dry()) return ZB_OK;

@@ -218,11 +218,8 @@ int umma_conv_stem_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
                                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (stem wgrad windows) failed (%d)", int(r)); return ZB_ERR_CUDA; }
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
+  static SmemOptIn opt_in;
+  { const int rc2 = smem_opt_in(ctx, opt_in, stem_wgrad_kernel, smem); if (rc2 != ZB_OK) return rc2; }
   plan_note("stem_wgrad ring=%d k_boxes=%d ~strips=%d ~grid=%d;", p.ring, p.k_boxes, p.strips, grid);
   *splits_out = grid;
   if (plan_dry()) return ZB_OK;

@@ -304,11 +304,8 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if ((rc = make_raster_map(ctx, &ma, dy, d->n, P, Q, d->k, p.Wr, p.tp)) != ZB_OK) return rc;
   if ((rc = make_raster_map(ctx, &mb, x, d->n, d->h, d->w, d->c, p.Wr, p.tp + R - 1)) != ZB_OK) return rc;
   const size_t smem = static_cast<size_t>(p.ring_bytes) + 256 + 1024;
-  static size_t attr = 0;
-  if (smem > attr) {
-    ZB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
+  static SmemOptIn opt_in;
+  { const int rc2 = smem_opt_in(ctx, opt_in, wgrad_halo_kernel, smem); if (rc2 != ZB_OK) return rc2; }
   plan_note("wgrad_halo R=%d S=%d a_boxes=%d stages=%d roles=%d tp=%d beta=%d ~splits=%d ~grid=%d;wgrad_reduce;", R, S, p.a_boxes, p.stages, roles,
             p.tp, beta != 0.f ? 1 : 0, p.splits, roles * p.splits);
   if (plan_dry()) return ZB_OK;

@@ -90,6 +90,13 @@ class Model:
     def load(self, path):
         check(self.lib.zb_model_load(self._h, str(path).encode()))
 
+    def save_state(self, path):
+        """Parameters + optimizer state (step count, Adam m / v): the file a data-parallel job resumes from."""
+        check(self.lib.zb_model_save_state(self._h, str(path).encode()))
+
+    def load_state(self, path):
+        check(self.lib.zb_model_load_state(self._h, str(path).encode()))
+
     def set_optimizer(self, kind="sgd", lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
         check(self.lib.zb_model_set_optimizer(self._h, OPT[kind], float(lr), float(beta1), float(beta2), float(eps),
                                               float(weight_decay)))
@@ -128,7 +135,9 @@ class Model:
         return host.value if read_loss else loss
 
     def set_graph(self, enable=True):
-        """Replay `train_step` from a CUDA graph (captured after two eager steps; single GPU + SGD, otherwise stays eager)."""
+        """Replay `train_step` from a CUDA graph: each distinct (buffers, batch shape, train mode, math mode, DP world) signature is
+        captured after two eager steps of its own -- SGD / Adam / AdamW, bucket allreduces included -- and dropped when the buffers
+        it bakes in go away.  Stays eager on the legacy default stream (not capturable) and while per-node profiling is on."""
         check(self.lib.zb_model_set_graph(self._h, int(bool(enable))))
         self._graph = bool(enable)
 
@@ -153,3 +162,66 @@ class Model:
 
     def bytes_reserved(self):
         return int(self.lib.zb_model_bytes_reserved(self._h))
+
+
+class InputStage:
+    """Library-owned input staging (zb_input_stage_*): pinned multi-buffered uint8 batches + int32 labels, asynchronous
+    host->device copy of the BYTES on a copy stream, on-device expansion into the model's NCHW float batch and one-hot targets.
+
+        stage = InputStage(ctx, n, c, h, w, classes, mean, std)
+        img, lab = stage.host_buffers(slot)        # numpy views of the pinned buffers: the decoder writes into them
+        stage.submit(slot)                         # H2D on the copy stream (overlaps the step of the previous batch)
+        x, t = stage.wait(slot)                    # compute stream waits, expands; torch views of the slot's device tensors
+
+    Replaces zenu/src/dataset.rs:74-100 + the synchronous f32 copy of Matrix::to::<Nvidia>() (zenu-matrix/src/matrix.rs:139-160,486)."""
+
+    def __init__(self, ctx, n, c, h, w, classes, mean=None, std=None, slots=2, src_layout=_lib.ZB_NHWC, dtype=torch.float32):
+        import numpy as np
+        self._np = np
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n, self.c, self.h, self.w, self.classes, self.slots = int(n), int(c), int(h), int(w), int(classes), int(slots)
+        self.src_layout, self.dtype = src_layout, dtype
+        zdt = ZB_F32 if dtype == torch.float32 else ZB_F64
+        cm = (ctypes.c_double * c)(*mean) if mean is not None else None
+        cs = (ctypes.c_double * c)(*std) if std is not None else None
+        self._h = ctypes.c_void_p()
+        check(self.lib.zb_input_stage_create(ctx.handle, zdt, src_layout, self.n, self.c, self.h, self.w, self.classes, cm, cs,
+                                             self.slots, ctypes.byref(self._h)))
+        ctx._children.add(self)
+        self.h2d_bytes = int(self.lib.zb_input_stage_h2d_bytes(self._h))
+
+    def close(self):
+        if self._h and self.ctx.handle:
+            self.lib.zb_input_stage_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def host_buffers(self, slot):
+        """(images uint8 [n,h,w,c] or [n,c,h,w] per src_layout, labels int32 [n]): numpy views of slot's PINNED host memory.
+        Blocks until an earlier copy out of this slot has finished (zb_input_stage_host_sync)."""
+        np = self._np
+        check(self.lib.zb_input_stage_host_sync(self._h, int(slot)))
+        img, lab = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.lib.zb_input_stage_host_buffers(self._h, int(slot), ctypes.byref(img), ctypes.byref(lab)))
+        shape = (self.n, self.h, self.w, self.c) if self.src_layout == _lib.ZB_NHWC else (self.n, self.c, self.h, self.w)
+        nbytes = self.n * self.c * self.h * self.w
+        a = np.frombuffer((ctypes.c_uint8 * nbytes).from_address(img.value), dtype=np.uint8).reshape(shape)
+        b = np.frombuffer((ctypes.c_int32 * self.n).from_address(lab.value), dtype=np.int32)
+        return a, b
+
+    def submit(self, slot):
+        check(self.lib.zb_input_stage_submit(self._h, int(slot)))
+
+    def wait(self, slot):
+        x, t = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.lib.zb_input_stage_wait(self._h, int(slot), ctypes.byref(x), ctypes.byref(t)))
+        typestr = "<f4" if self.dtype == torch.float32 else "<f8"
+        dev = f"cuda:{self.ctx.device}"
+        xs = torch.as_tensor(_DevView(x.value, (self.n, self.c, self.h, self.w), typestr), device=dev)
+        ts = torch.as_tensor(_DevView(t.value, (self.n, self.classes), typestr), device=dev)
+        return xs, ts
