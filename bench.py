@@ -6,8 +6,9 @@
 
 A step = one full train step (forward, cross-entropy, backward, SGD update; with N > 1 the bucketed NCCL gradient
 allreduce overlapped with backward) of ResNet-50 on a synthetic batch of 256 images (3x224x224, 1000 classes) per GPU.
-`value` is timed with the batch already resident in HBM; `e2e` is the same step fed from pinned HOST memory (H2D copy of
-the batch every step, prefetched on a side stream, and a D2H read of the loss) — both through the public API.
+`value` is timed with the batch already resident in HBM; `e2e` is the same step fed from pinned HOST memory through the
+library's input staging (zb_input_stage_*: the uint8 batch + int32 labels cross PCIe every step on a copy stream, are expanded on
+the device, and the loss is read back to the host) — both through the public API.  `--e2e-input f32` ships the f32 batch instead.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  L2: every step
 streams > 20 GB of activations, far larger than the 126 MB L2, so no explicit flush is needed.
 """
@@ -143,20 +144,33 @@ def cpu_reference_steps(arch, classes, hw, sample_batch, steps, warmup):
             "blas": "OpenBLAS (numpy bundled, all cores)" if blas else "plain C loops", "loss": float(loss)}
 
 
+def base_config(args, world):
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    return {"workload": workload_name(args), "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2 (each step streams > 20 GB of activations; L2 is 126 MB)" if args.arch != "small_cnn"
+                  else "L2 flushed by the step itself: 1.7 GB of activations + 134 MB of Linear weights per step vs 126 MB of L2",
+            "optimizer": "SGD lr 0.01 (zenu-optimizer/src/sgd.rs)",
+            "grad_allreduce": "bucketed NCCL sum, overlapped with backward" if world > 1 else "none (1 GPU)",
+            "input_grad_of_conv1": "computed (as the reference does)"}
+
+
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port: no Rust toolchain here) on the host cores, every
+    step a bounded sample of the workload: one full train step on `--ref-batch` of the batch's images (the whole batch for the
+    CPU-runnable config, small_cnn)."""
     if rank != 0:
         return
-    sample = args.ref_batch
-    r = cpu_reference_steps(args.arch, args.classes, args.hw, sample, args.steps, min(args.warmup, 1))
+    sample = min(args.ref_batch, args.batch) if args.arch != "small_cnn" else args.batch
+    r = cpu_reference_steps(args.arch, args.classes, args.hw, sample, args.steps, args.warmup)
     ms = r["sec_per_step"] * 1e3
     line = {
         "impl": "reference", "metric": metric_name(args), "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": f"each step = one full train step on {sample} of the 256 images",
-                   "note": "reference CPU path restated in C (oracle/): no Rust toolchain in this image, see DESIGN.md"},
+        "config": base_config(args, world),
         "cpu_baseline": {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": f"{args.steps} train steps at batch {sample} (of 256), {r['blas']}"},
+                         "sample": f"{args.steps} full train steps on {sample} of the {args.batch} images of a batch after {args.warmup} warm-up steps, "
+                                   f"{r['blas']}; reference CPU path restated in C (oracle/)"},
         "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -230,6 +244,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
+    value_graphs = model.graph_count()
     # same K steps again with a CUDA-event pair around every tensor-core launch / BatchNorm op (the live roofline numbers);
     # kept out of the headline region because ~280 extra event records per step cost ~2 % of it
     ops.check(lib.zb_ctx_profile_enable(ctx.handle, 1))
@@ -251,11 +266,13 @@ def run_ours(args, rank, world, local_rank):
     ctx.check()
     # ---------------------------------------------------------------- per-node table (outside the timed region): 2 more steps
     node_summary = None
+    node_rows = None
     try:
         model.profile(True)
         for _ in range(2):
             model.train_step(X, T, loss_out=loss_dev)
         rows = model.profile_table()
+        node_rows = rows
         model.profile(False)
         cls = {}
         for k, n, ms, fl, by in rows:
@@ -266,26 +283,53 @@ def run_ours(args, rank, world, local_rank):
     except Exception as e:  # noqa: BLE001
         node_summary = None
     # ---------------------------------------------------------------- e2e: batch comes from pinned host memory each step
-    copy_stream = torch.cuda.Stream()
-    bufs = [(torch.empty_like(X), torch.empty_like(T)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    if args.e2e_input == "u8":
+        # the library's input staging (zb_input_stage_*): uint8 NHWC images + int32 labels in pinned host memory -> copy stream ->
+        # device expansion (normalise, NCHW, one-hot) -> train step; the copy of batch i+1 overlaps the step of batch i
+        import numpy as np
+        stage = nn.InputStage(ctx, args.batch, 3, args.hw, args.hw, args.classes, mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], slots=2)
+        rng = np.random.default_rng(4321 + rank)
+        for sl in range(2):
+            img, lab = stage.host_buffers(sl)
+            img[...] = rng.integers(0, 256, img.shape, dtype=np.uint8)
+            lab[...] = rng.integers(0, args.classes, lab.shape, dtype=np.int32)
+        h2d_bytes = stage.h2d_bytes
+        prefetch = stage.submit
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])
-            bufs[i % 2][0].copy_(x_pin, non_blocking=True)
-            bufs[i % 2][1].copy_(t_pin, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+        def fetch(i):
+            return stage.wait(i % 2)
 
-    for e in consumed:
-        e.record()
-    # untimed: one pass over each staging buffer (with graph replay a new buffer address is a new capture)
-    for i in range(2):
-        prefetch(i)
-        torch.cuda.current_stream().wait_event(ready[i % 2])
-        model.train_step(bufs[i % 2][0], bufs[i % 2][1], loss_out=loss_dev, read_loss=True)
-        consumed[i % 2].record()
+        def done(i):
+            pass
+    else:
+        copy_stream = torch.cuda.Stream()
+        bufs = [(torch.empty_like(X), torch.empty_like(T)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        h2d_bytes = int(x_pin.numel() * 4 + t_pin.numel() * 4)
+        for e in consumed:
+            e.record()
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                bufs[i % 2][0].copy_(x_pin, non_blocking=True)
+                bufs[i % 2][1].copy_(t_pin, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def fetch(i):
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            return bufs[i % 2]
+
+        def done(i):
+            consumed[i % 2].record()
+
+    # untimed: two passes over each staging buffer (with graph replay a new buffer address is a new capture after its own warm-up)
+    for i in range(6):
+        prefetch(i % 2)
+        xb, tb = fetch(i)
+        model.train_step(xb, tb, loss_out=loss_dev, read_loss=True)
+        done(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -293,14 +337,14 @@ def run_ours(args, rank, world, local_rank):
     loss_host = 0.0
     for i in range(args.steps):
         if i + 1 < args.steps:
-            prefetch(i + 1)
-        torch.cuda.current_stream().wait_event(ready[i % 2])
-        xb, tb = bufs[i % 2]
+            prefetch((i + 1) % 2)
+        xb, tb = fetch(i)
         loss_host = model.train_step(xb, tb, loss_out=loss_dev, read_loss=True)   # D2H read of the loss, synchronises
-        consumed[i % 2].record()
+        done(i)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    e2e_graphs = model.graph_count()
     # ---------------------------------------------------------------- reduce over ranks (max time)
     times = torch.tensor([elapsed_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -351,22 +395,33 @@ def run_ours(args, rank, world, local_rank):
     train_tflop_per_step = 3.0 * FWD_GFLOP_PER_IMG.get(args.arch, 0.0) * args.batch / 1e3
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_steps(args.arch, args.classes, args.hw, args.cpu_batch, 2, 1)
+        full = args.arch == "small_cnn"        # BASELINE configs[0] is the CPU-runnable case: its train step is timed in full
+        cb = args.batch if full else min(args.cpu_batch, args.batch)
+        cs = 10 if full else 2
+        r = cpu_reference_steps(args.arch, args.classes, args.hw, cb, cs, 1)
         cpu_baseline = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                        "sample": f"2 train steps at batch {args.cpu_batch} (of 256) after 1 warm-up, {r['blas']}"}
+                        "sample": f"{cs} train steps at batch {cb} (of {args.batch}) after 1 warm-up, {r['blas']}"}
+    # whole-step roofline: images / sum over tape nodes of max(flops / tensor peak, algorithmic bytes / HBM bandwidth)
+    whole = None
+    if node_rows:
+        ideal_ms = sum(max(fl / 2 / (tf32_peak * 1e12), by / 2 / (peaks["hbm_gbs"] * 1e9)) for _, _, _, fl, by in node_rows) * 1e3
+        whole = {"ideal_ms_per_step": ideal_ms, "measured_ms_per_step": step_ms, "frac": ideal_ms / step_ms if step_ms > 0 else None,
+                 "ideal_images_per_s_per_gpu": args.batch / (ideal_ms / 1e3) if ideal_ms > 0 else None,
+                 "definition": "sum over the step's tape nodes (forward and backward) of max(algorithmic FLOPs / dense TF32 peak, algorithmic "
+                               "bytes / HBM copy bandwidth), peaks from MEASURED_PEAKS.json (sustained bf16 / 2, hbm_gbs)"}
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": global_batch, "parallelism": f"dp{world}",
-                   "l2": "inputs larger than L2 (each step streams > 20 GB of activations; L2 is 126 MB)",
-                   "optimizer": "SGD lr 0.01 (zenu-optimizer/src/sgd.rs)", "grad_allreduce": "bucketed NCCL sum, overlapped with backward" if world > 1 else "none (1 GPU)",
-                   "step_graphs": model.graph_count(),   # > 0: steps were replayed from CUDA graphs captured after the warm-up
-                   "input_grad_of_conv1": "computed (as the reference does)"},
+        "config": base_config(args, world),
+        "step_graphs": value_graphs,   # > 0: the timed steps were replayed from CUDA graphs captured during the warm-up
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + t_pin.numel() * 4),
-                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_host},
-        "roofline": roofline, "roofline_by_class": secondary, "tape_nodes_by_class": by_node,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_host,
+                "input": "uint8 NHWC images + int32 labels through zb_input_stage_* (pinned, double-buffered, expanded on the device)"
+                         if args.e2e_input == "u8" else "f32 NCHW batch + f32 one-hot targets from pinned memory (torch copy stream)",
+                "step_graphs": e2e_graphs},
+        "roofline": roofline, "roofline_by_class": secondary, "tape_nodes_by_class": by_node, "whole_step_roofline": whole,
         "step_model_flops": {"algorithmic_tflop_per_step_per_gpu": train_tflop_per_step,
                              "achieved_tflops_whole_step": train_tflop_per_step / (step_ms / 1e3) if step_ms > 0 else None},
         "cpu_baseline": cpu_baseline, "final_loss": final_loss, "hbm_bytes_reserved": model.bytes_reserved(),
@@ -383,9 +438,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="resnet50", choices=["resnet50", "resnet18", "small_cnn"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
-    ap.add_argument("--hw", type=int, default=224)
-    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: 256; small_cnn 64 = BASELINE configs[0])")
+    ap.add_argument("--hw", type=int, default=None, help="input height = width (default: 224; small_cnn 32)")
+    ap.add_argument("--classes", type=int, default=None, help="default: 1000; small_cnn 10")
+    ap.add_argument("--e2e-input", default="u8", choices=["u8", "f32"], help="what the e2e leg ships across PCIe every step")
     ap.add_argument("--bucket-mb", type=int, default=25)
     ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the cpu_baseline leg")
@@ -393,6 +449,10 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="run every step eagerly instead of replaying it from a CUDA graph (zb_model_set_graph; same kernels, bit-identical results)")
     args = ap.parse_args()
+    small = args.arch == "small_cnn"
+    args.batch = args.batch if args.batch is not None else (64 if small else 256)
+    args.hw = args.hw if args.hw is not None else (32 if small else 224)
+    args.classes = args.classes if args.classes is not None else (10 if small else 1000)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

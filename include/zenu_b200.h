@@ -265,6 +265,9 @@ int zb_dp_unique_id(zb_ctx* ctx, void* host_id128);
 int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world);
 int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n);
 int zb_dp_wait(zb_ctx* ctx);
+/* Polls ncclCommGetAsyncError (also done by zb_dp_wait once per step and by zb_ctx_check): a failure that surfaced asynchronously --
+ * a peer died, a link went down -- aborts the communicator, so blocked collectives are released, and returns ZB_ERR_NCCL from then on. */
+int zb_dp_check(zb_ctx* ctx);
 int zb_dp_rank(zb_ctx* ctx);
 int zb_dp_world(zb_ctx* ctx);
 

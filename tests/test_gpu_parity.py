@@ -794,3 +794,41 @@ def test_cudnn_frontend_shim(zb, ctx, golden_dir):
     assert maxabs(host(y), d["output"]) < 1e-4
     lib.destroy_conv_descriptor.argtypes = [ctypes.c_void_p]
     lib.destroy_conv_descriptor(desc)
+
+
+def test_input_stage(zb, ctx):
+    """zb_input_stage_* (SURVEY 8f-3): pinned multi-buffered uint8 staging + copy stream + device expansion.  Every batch that goes in
+    comes out as (u8 / 255 - mean) / std in NCHW and the labels as one-hot rows, slots reused several times with all the copies in
+    flight ahead of the waits."""
+    from zenu_b200 import ZB_NCHW, ZB_NHWC, nn
+    rng = np.random.default_rng(9)
+    n, c, h, w, classes = 5, 3, 12, 9, 7
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    for layout in (ZB_NHWC, ZB_NCHW):
+        st = nn.InputStage(ctx, n, c, h, w, classes, mean=mean, std=std, slots=3, src_layout=layout)
+        assert st.h2d_bytes == n * c * h * w + 4 * n
+        sent = {}
+        outs = []
+        for i in range(8):                      # keep two submits ahead of the consumer
+            if i < 8:
+                img, lab = st.host_buffers(i % 3)
+                img[...] = rng.integers(0, 256, img.shape, dtype=np.uint8)
+                lab[...] = rng.integers(0, classes, n, dtype=np.int32)
+                sent[i] = (img.copy(), lab.copy())
+                st.submit(i % 3)
+            if i >= 2:
+                x, t = st.wait((i - 2) % 3)
+                outs.append((i - 2, x.clone(), t.clone()))
+        for j in (6, 7):
+            x, t = st.wait(j % 3)
+            outs.append((j, x.clone(), t.clone()))
+        ctx.check()
+        for j, x, t in outs:
+            img, lab = sent[j]
+            chw = img.transpose(0, 3, 1, 2) if layout == ZB_NHWC else img
+            ref = (chw.astype(np.float64) / 255.0 - np.array(mean)[None, :, None, None]) / np.array(std)[None, :, None, None]
+            assert x.shape == (n, c, h, w) and maxabs(host(x), ref) < 1e-5, j
+            np.testing.assert_array_equal(host(t), np.eye(classes, dtype=np.float32)[lab])
+        with pytest.raises(Exception):
+            st.wait(0)                          # no submit pending on that slot
+        st.close()

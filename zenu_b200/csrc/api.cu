@@ -189,6 +189,7 @@ static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
 
 int zb_conv2d_fprop(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
                     const void* bias, void* y) {
+  ZB_API_RANGE();
   return fprop_impl(ctx, dtype, layout, math, d, x, w, bias, y, nullptr);
 }
 
@@ -196,6 +197,7 @@ int zb_conv2d_bnstats_rows(zb_ctx* ctx) { return ctx->sm_count * 4; }
 
 int zb_conv2d_fprop_bnstats(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* x, const void* w,
                             const void* bias, void* y, const void* shift, void* stat_partial, int64_t* stat_rows) {
+  ZB_API_RANGE();
   ZB_REQUIRE(shift != nullptr && stat_partial != nullptr && stat_rows != nullptr, "conv fprop + bn stats: NULL statistics argument");
   BnStats bs;
   bs.shift = static_cast<const float*>(shift);
@@ -249,11 +251,13 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
 
 int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
                     void* dx) {
+  ZB_API_RANGE();
   return dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 0.f);
 }
 
 int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
                         void* dx) {
+  ZB_API_RANGE();
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
@@ -315,6 +319,7 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
 
 int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* x,
                     void* dw) {
+  ZB_API_RANGE();
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
@@ -411,6 +416,7 @@ int64_t zb_ctx_plan_trace_read(zb_ctx* ctx, char* buf, int64_t cap) {
 
 int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const void* bias, void* y, int64_t n, int64_t k,
                        int64_t h, int64_t w) {
+  ZB_API_RANGE();
   if (layout == ZB_NHWC) return zb_binary_bcast_rows(ctx, dtype, ZB_OP_ADD, x, bias, y, n * h * w, k);
   ZB_REQUIRE(layout == ZB_NCHW, "bias_add: unknown layout %d", layout);
   if (dtype == ZB_F32) return bias_add_nchw<float>(ctx, static_cast<const float*>(x), static_cast<const float*>(bias), static_cast<float*>(y), n, k, h * w);
@@ -421,6 +427,7 @@ int zb_conv2d_bias_add(zb_ctx* ctx, int dtype, int layout, const void* x, const 
 
 int zb_gemm(zb_ctx* ctx, int dtype, int math, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
             const void* a, int64_t lda, const void* b, int64_t ldb, double beta, void* c, int64_t ldc) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative extent");
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "gemm: unknown dtype %d", dtype);
   if (m == 0 || n == 0) return ZB_OK;
@@ -442,6 +449,7 @@ int zb_gemm(zb_ctx* ctx, int dtype, int math, int trans_a, int trans_b, int64_t 
 
 int zb_linear_fwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* bias, void* y, int64_t batch,
                   int64_t in_f, int64_t out_f) {
+  ZB_API_RANGE();
   ZB_REQUIRE(batch > 0 && in_f > 0 && out_f > 0, "linear: non-positive extent");
   int mm;
   int rc = resolve_math(ctx, dtype, math, &mm);
@@ -460,6 +468,7 @@ int zb_linear_fwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w
 
 int zb_linear_bwd(zb_ctx* ctx, int dtype, int math, const void* x, const void* w, const void* dy, void* dx, void* dw,
                   void* dbias, int64_t batch, int64_t in_f, int64_t out_f) {
+  ZB_API_RANGE();
   ZB_REQUIRE(batch > 0 && in_f > 0 && out_f > 0, "linear: non-positive extent");
   int rc;
   if (dx) {  // dX[b,in] = dY[b,out] * W[out,in]

@@ -813,6 +813,7 @@ extern "C" {
 int zb_bn2d_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, double momentum,
                       const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
                       void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
   if (dtype == ZB_F32)
     return bn_fwd_train_t<float>(ctx, layout, n, c, h, w, momentum, static_cast<const float*>(x), static_cast<const float*>(scale),
@@ -832,6 +833,7 @@ int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, in
                                const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
                                void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu,
                                const void* stat_partial, int64_t stat_rows, const void* shift) {
+  ZB_API_RANGE();
   ZB_REQUIRE(stat_partial != nullptr && shift != nullptr && stat_rows > 0, "bn prestats: missing statistics");
   return zb_bn2d_fwd_train_fused(ctx, dtype, layout, n, c, h, w, momentum, x, scale, bias, running_mean, running_var, saved_mean,
                                  saved_inv_std, y, residual, relu, stat_partial, stat_rows, shift, nullptr);
@@ -843,6 +845,7 @@ int zb_bn2d_fwd_train_fused(zb_ctx* ctx, int dtype, int layout, int64_t n, int64
                             const void* x, const void* scale, const void* bias, void* running_mean, void* running_var,
                             void* saved_mean, void* saved_inv_std, void* y, const void* residual, int relu,
                             const void* stat_partial, int64_t stat_rows, const void* shift, void* relu_mask) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32, "bn fused forward: NHWC f32 only");
   ZB_REQUIRE(stat_partial == nullptr || (shift != nullptr && stat_rows > 0 && stat_rows < (1 << 30)), "bn fused forward: bad statistics");
   ZB_REQUIRE(relu_mask == nullptr || (relu && c % 32 == 0), "bn fused forward: the ReLU bit mask needs relu and C %% 32 == 0");
@@ -856,6 +859,7 @@ int zb_bn2d_fwd_train_fused(zb_ctx* ctx, int dtype, int layout, int64_t n, int64
 int zb_bn2d_bwd_mask(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x, const void* dy,
                      const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx, void* dscale, void* dbias,
                      const void* relu_mask, void* dres) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32 && c % 32 == 0, "bn bwd (bit mask): NHWC f32 with C %% 32 == 0 only");
   ZB_REQUIRE(relu_mask != nullptr && dres != nullptr && saved_mean != nullptr && saved_inv_std != nullptr,
              "bn bwd (bit mask): mask, residual-gradient buffer and saved statistics are required");
@@ -870,6 +874,7 @@ int zb_bn2d_bwd_mask(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, i
 
 int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                       const void* scale, const void* bias, const void* mean, const void* var, void* y) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
   if (dtype == ZB_F32)
     return bn_fwd_infer_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(scale),
@@ -886,6 +891,7 @@ int zb_bn2d_fwd_infer(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, 
 int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                 const void* dy, const void* scale, const void* saved_mean, const void* saved_inv_std, void* dx,
                 void* dscale, void* dbias, const void* y, void* dres) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
   if (dtype == ZB_F32)
     return bn_bwd_t<float>(ctx, layout, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(dy),
@@ -904,6 +910,7 @@ int zb_bn2d_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_
 int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, const void* x,
                      const void* dy, const void* scale, const void* bias, const void* saved_mean, const void* saved_inv_std,
                      void* dx, void* dscale, void* dbias) {
+  ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NCHW || layout == ZB_NHWC, "bn: unknown layout %d", layout);
   ZB_REQUIRE(bias != nullptr && saved_mean != nullptr && saved_inv_std != nullptr, "bn relu bwd: bias and saved statistics are required");
   if (dtype == ZB_F32)
@@ -922,6 +929,7 @@ int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, i
 
 int zb_conv2d_bias_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dbias, int64_t n, int64_t k, int64_t h,
                        int64_t w) {
+  ZB_API_RANGE();
   if (dtype == ZB_F32) return channel_sum<float>(ctx, layout, n, k, h * w, static_cast<const float*>(dy), static_cast<float*>(dbias));
   if (dtype == ZB_F64) return channel_sum<double>(ctx, layout, n, k, h * w, static_cast<const double*>(dy), static_cast<double*>(dbias));
   zb::set_last_error("unknown dtype %d", dtype);
@@ -929,6 +937,7 @@ int zb_conv2d_bias_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void*
 }
 
 int zb_sum_rows(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t rows, int64_t cols) {
+  ZB_API_RANGE();
   if (dtype == ZB_F32) return channel_sum<float>(ctx, ZB_NHWC, rows, cols, 1, static_cast<const float*>(a), static_cast<float*>(out));
   if (dtype == ZB_F64) return channel_sum<double>(ctx, ZB_NHWC, rows, cols, 1, static_cast<const double*>(a), static_cast<double*>(out));
   zb::set_last_error("unknown dtype %d", dtype);

@@ -8,6 +8,7 @@
 #include <string>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/zenu_b200.h"
 
@@ -49,6 +50,7 @@ struct zb_ctx {
   void* nccl_lib;
   void* nccl_comm;
   int rank, world;
+  bool nccl_failed;          // an asynchronous NCCL error was seen: the communicator has been aborted
   cudaEvent_t ev_ready, ev_done;  // compute->comm and comm->compute fences
   unsigned long long launches;  // number of kernels this ctx launched (bench.py's gpu_launches)
   zb::ProfState* prof;          // optional per-op CUDA-event timing (zb_ctx_profile_*)
@@ -82,6 +84,16 @@ namespace zb {
       return ZB_ERR_CUDA;                                                                     \
     }                                                                                         \
   } while (0)
+
+// NVTX range around every C-ABI entry point (tracing the reference does not have).  NVTX v3 is header-only: without
+// a profiler attached a push / pop is one predictable branch, under nsys / ncu the ABI calls show up as named ranges on the timeline.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define ZB_API_RANGE() zb::NvtxRange zb_nvtx_range_(__func__)
 
 // Plan trace (zb_conv2d_plan_describe / zb_ctx_plan_trace): while a PlanTrace is installed on the calling thread every launcher
 // appends one "kernel<variant> key=value ...;" segment per launch it plans (size-dependent values carry a '~' prefix so that a
@@ -126,6 +138,9 @@ enum ProfClass { PROF_TENSOR = 0, PROF_BN = 1, PROF_EWISE = 2, PROF_NUM = 3 };
 bool prof_active(zb_ctx* ctx);   // per-op timing is recording (events are being interleaved with the launches)
 void prof_begin(zb_ctx* ctx, int cls);
 void prof_end(zb_ctx* ctx, int cls, double work);
+
+int dp_poll_async_error(zb_ctx* ctx);   // dp.cu: ncclCommGetAsyncError; aborts the communicator on failure
+void dp_destroy(zb_ctx* ctx);
 
 // Grow-only scratch; stream-ordered so earlier kernels that still read the old block stay valid.
 int ctx_workspace(zb_ctx* ctx, size_t bytes, void** out);

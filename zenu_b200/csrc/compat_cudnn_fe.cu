@@ -118,6 +118,7 @@ CudnnFrontendError_t get_workspace_size(BatchNormDescriptor* desc, int64_t* ws) 
   return SUCCESS;
 }
 CudnnFrontendError_t execute_batch_norm_forward_training(BatchNormDescriptor* desc, BatchNormExecutionBuffers* b, void*, void*) {
+  ZB_API_RANGE();
   BnShim* s = reinterpret_cast<BnShim*>(desc);
   zb_ctx* ctx = compat_ctx();
   if (!s || !b || !ctx || s->backward) return INVALID_VALUE;
@@ -157,6 +158,7 @@ CudnnFrontendError_t get_backward_data_workspace_size(BatchNormBkwdDescriptor* d
   return SUCCESS;
 }
 CudnnFrontendError_t execute_batch_norm_backward_data(BatchNormBkwdDescriptor* desc, BatchNormBkwdExecutionBuffers* b, void*, void*) {
+  ZB_API_RANGE();
   BnShim* s = reinterpret_cast<BnShim*>(desc);
   zb_ctx* ctx = compat_ctx();
   if (!s || !b || !ctx || !s->backward) return INVALID_VALUE;
@@ -181,6 +183,7 @@ CudnnFrontendError_t get_conv_workspace_size(ConvDescriptor* desc, int64_t* ws) 
   return SUCCESS;
 }
 CudnnFrontendError_t execute_conv_forward(ConvDescriptor* desc, ConvBufers* b, void*, void*) {
+  ZB_API_RANGE();
   ConvShim* s = reinterpret_cast<ConvShim*>(desc);
   zb_ctx* ctx = compat_ctx();
   if (!s || !b || !ctx) return INVALID_VALUE;
@@ -202,6 +205,7 @@ CudnnFrontendError_t get_conv_backward_data_workspace_size(ConvBkwdDataDescripto
   return SUCCESS;
 }
 CudnnFrontendError_t execute_conv_backward_data(ConvBkwdDataDescriptor* desc, ConvBkwdDataBuffers* b, void*, void*) {
+  ZB_API_RANGE();
   ConvShim* s = reinterpret_cast<ConvShim*>(desc);
   zb_ctx* ctx = compat_ctx();
   if (!s || !b || !ctx) return INVALID_VALUE;
@@ -223,6 +227,7 @@ CudnnFrontendError_t get_conv_backward_filter_workspace_size(ConvBkwdFilterDescr
   return SUCCESS;
 }
 CudnnFrontendError_t execute_conv_backward_filter(ConvBkwdFilterDescriptor* desc, ConvBkwdFilterBuffers* b, void*, void*) {
+  ZB_API_RANGE();
   ConvShim* s = reinterpret_cast<ConvShim*>(desc);
   zb_ctx* ctx = compat_ctx();
   if (!s || !b || !ctx) return INVALID_VALUE;

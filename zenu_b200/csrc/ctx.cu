@@ -103,6 +103,7 @@ int64_t zb_conv_out_size(int64_t in, int64_t k, int64_t pad, int64_t stride, int
 }
 
 int zb_ctx_create(zb_ctx** out, int device, void* stream) {
+  ZB_API_RANGE();
   ZB_REQUIRE(out != nullptr, "zb_ctx_create: out is NULL");
   ZB_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -145,10 +146,12 @@ int zb_ctx_create(zb_ctx** out, int device, void* stream) {
 }
 
 int zb_ctx_destroy(zb_ctx* ctx) {
+  ZB_API_RANGE();
   if (!ctx) return ZB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->comm_stream);
+  zb::dp_destroy(ctx);
   if (ctx->prof) { zb::prof_clear(ctx->prof); delete ctx->prof; }
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->err_flag) cudaFree(ctx->err_flag);
@@ -159,6 +162,7 @@ int zb_ctx_destroy(zb_ctx* ctx) {
 }
 
 int zb_ctx_profile_enable(zb_ctx* ctx, int enable) {
+  ZB_API_RANGE();
   if (!ctx->prof) ctx->prof = new zb::ProfState();
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   zb::prof_clear(ctx->prof);
@@ -167,6 +171,7 @@ int zb_ctx_profile_enable(zb_ctx* ctx, int enable) {
 }
 
 int zb_ctx_profile_read(zb_ctx* ctx, int cls, int64_t* ops, double* total_ms, double* work) {
+  ZB_API_RANGE();
   ZB_REQUIRE(cls >= 0 && cls < zb::PROF_NUM, "profile class out of range");
   if (ops) *ops = 0;
   if (total_ms) *total_ms = 0.0;
@@ -187,11 +192,13 @@ int zb_ctx_profile_read(zb_ctx* ctx, int cls, int64_t* ops, double* total_ms, do
 }
 
 int zb_ctx_synchronize(zb_ctx* ctx) {
+  ZB_API_RANGE();
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return ZB_OK;
 }
 
 int zb_ctx_set_math(zb_ctx* ctx, int math_mode) {
+  ZB_API_RANGE();
   ZB_REQUIRE(math_mode == ZB_MATH_TF32 || math_mode == ZB_MATH_TF32X3 || math_mode == ZB_MATH_FP32, "unknown math mode %d", math_mode);
   ctx->default_math = math_mode;
   return ZB_OK;
@@ -207,6 +214,7 @@ double zb_ctx_bn_epsilon(zb_ctx* ctx) { return ctx ? ctx->bn_eps : 0.0; }
 void* zb_ctx_stream(zb_ctx* ctx) { return ctx->stream; }
 
 int zb_ctx_check(zb_ctx* ctx) {
+  ZB_API_RANGE();
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   int flag = 0;
   ZB_CHECK_CUDA(cudaMemcpy(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
@@ -215,7 +223,8 @@ int zb_ctx_check(zb_ctx* ctx) {
     zb::set_last_error("device-side barrier wait timed out (tcgen05 pipeline protocol error)");
     return ZB_ERR_TIMEOUT;
   }
-  return ZB_OK;
+  if (ctx->nccl_failed) { zb::set_last_error("the NCCL communicator was aborted after an asynchronous error"); return ZB_ERR_NCCL; }
+  return zb::dp_poll_async_error(ctx);
 }
 
 unsigned long long zb_ctx_launch_count(zb_ctx* ctx) { return ctx->launches; }

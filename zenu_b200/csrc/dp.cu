@@ -20,6 +20,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -42,6 +44,8 @@ static int load_nccl() {
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  g_nccl.CommAbort = reinterpret_cast<decltype(g_nccl.CommAbort)>(dlsym(h, "ncclCommAbort"));
+  g_nccl.CommGetAsyncError = reinterpret_cast<decltype(g_nccl.CommGetAsyncError)>(dlsym(h, "ncclCommGetAsyncError"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
     set_last_error("libnccl is missing required symbols");
     return ZB_ERR_NCCL;
@@ -58,6 +62,32 @@ static int load_nccl() {
       return ZB_ERR_NCCL;                                                                           \
     }                                                                                               \
   } while (0)
+
+// Asynchronous NCCL failures (a peer died, a link went down) do not come back through the enqueue calls' return codes: they are
+// polled from the communicator.  On error the communicator is aborted (so that kernels blocked in the collective are released
+// instead of hanging the stream) and every later data-parallel call fails with ZB_ERR_NCCL.
+int dp_poll_async_error(zb_ctx* ctx) {
+  if (ctx->world <= 1 || ctx->nccl_comm == nullptr || g_nccl.CommGetAsyncError == nullptr) return ZB_OK;
+  ncclResult_t async = ncclSuccess;
+  const ncclResult_t r = g_nccl.CommGetAsyncError(static_cast<ncclComm_t>(ctx->nccl_comm), &async);
+  if (r == ncclSuccess && (async == ncclSuccess || async == ncclInProgress)) return ZB_OK;
+  const ncclResult_t bad = r != ncclSuccess ? r : async;
+  set_last_error("NCCL asynchronous error on rank %d of %d: %s (communicator aborted)", ctx->rank, ctx->world,
+                 g_nccl.GetErrorString ? g_nccl.GetErrorString(bad) : "?");
+  if (g_nccl.CommAbort) g_nccl.CommAbort(static_cast<ncclComm_t>(ctx->nccl_comm));
+  ctx->nccl_comm = nullptr;
+  ctx->nccl_failed = true;
+  return ZB_ERR_NCCL;
+}
+
+void dp_destroy(zb_ctx* ctx) {
+  // The communicator itself is left to process teardown: ncclCommDestroy synchronises with the peers' destroy calls, and a rank
+  // whose peers have already exited (the normal end of a torchrun job) would block in it.
+  ctx->nccl_comm = nullptr;
+  if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+  ctx->ev_ready = ctx->ev_done = nullptr;
+}
 
 }  // namespace zb
 
@@ -97,6 +127,7 @@ int zb_dp_plan_buckets(const int64_t* numel, const int* kind, int n, int64_t buc
 }
 
 int zb_dp_unique_id(zb_ctx* ctx, void* host_id128) {
+  ZB_API_RANGE();
   (void)ctx;
   int rc = load_nccl();
   if (rc != ZB_OK) return rc;
@@ -108,6 +139,7 @@ int zb_dp_unique_id(zb_ctx* ctx, void* host_id128) {
 }
 
 int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world) {
+  ZB_API_RANGE();
   ZB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "zb_dp_init: bad rank/world %d/%d", rank, world);
   ctx->rank = rank;
   ctx->world = world;
@@ -128,7 +160,9 @@ int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world) {
 }
 
 int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n) {
+  ZB_API_RANGE();
   if (ctx->world <= 1 || n == 0) return ZB_OK;
+  if (ctx->nccl_failed) { set_last_error("zb_dp_allreduce_sum: the NCCL communicator was aborted after an asynchronous error"); return ZB_ERR_NCCL; }
   ZB_REQUIRE(ctx->nccl_comm != nullptr, "zb_dp_allreduce_sum: zb_dp_init was not called");
   ZB_CHECK_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
   ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
@@ -139,9 +173,21 @@ int zb_dp_allreduce_sum(zb_ctx* ctx, int dtype, void* buf, int64_t n) {
 }
 
 int zb_dp_wait(zb_ctx* ctx) {
+  ZB_API_RANGE();
   if (ctx->world <= 1 || !ctx->ev_done) return ZB_OK;
+  if (ctx->nccl_failed) { set_last_error("zb_dp_wait: the NCCL communicator was aborted after an asynchronous error"); return ZB_ERR_NCCL; }
   ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_done, 0));
+  // once per step (this is the optimizer's fence): has any collective enqueued so far failed asynchronously?
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) return dp_poll_async_error(ctx);
   return ZB_OK;
+}
+
+int zb_dp_check(zb_ctx* ctx) {
+  ZB_API_RANGE();
+  ZB_REQUIRE(ctx != nullptr, "zb_dp_check: ctx is NULL");
+  if (ctx->nccl_failed) { set_last_error("the NCCL communicator was aborted after an asynchronous error"); return ZB_ERR_NCCL; }
+  return dp_poll_async_error(ctx);
 }
 
 int zb_dp_rank(zb_ctx* ctx) { return ctx->rank; }

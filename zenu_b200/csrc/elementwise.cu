@@ -320,30 +320,37 @@ __global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ lab
 extern "C" {
 
 int zb_relu(zb_ctx* ctx, int dtype, const void* x, void* y, double alpha, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, relu_t<float>(ctx, x, y, alpha, n), relu_t<double>(ctx, x, y, alpha, n));
 }
 int zb_relu_backward_mask(zb_ctx* ctx, int dtype, const void* x, void* mask, double alpha, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, relu_mask_t<float>(ctx, x, mask, alpha, n), relu_mask_t<double>(ctx, x, mask, alpha, n));
 }
 int zb_relu_bwd(zb_ctx* ctx, int dtype, const void* x, const void* dy, void* dx, double alpha, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, relu_bwd_t<float>(ctx, x, dy, dx, alpha, n), relu_bwd_t<double>(ctx, x, dy, dx, alpha, n));
 }
 int zb_binary(zb_ctx* ctx, int dtype, int op, const void* a, const void* b, void* c, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype,
                   (dispatch_binop<float, BinF>(ctx, op, static_cast<float*>(c), static_cast<const float*>(a), static_cast<const float*>(b), n)),
                   (dispatch_binop<double, BinF>(ctx, op, static_cast<double*>(c), static_cast<const double*>(a), static_cast<const double*>(b), n)));
 }
 int zb_binary_scalar(zb_ctx* ctx, int dtype, int op, const void* a, double scalar, void* c, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype,
                   (dispatch_unop<float, BinScalarF>(ctx, op, static_cast<float*>(c), static_cast<const float*>(a), n, static_cast<float>(scalar))),
                   (dispatch_unop<double, BinScalarF>(ctx, op, static_cast<double*>(c), static_cast<const double*>(a), n, scalar)));
 }
 int zb_binary_bcast_rows(zb_ctx* ctx, int dtype, int op, const void* a, const void* b, void* c, int64_t rows, int64_t cols) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype,
                   (dispatch_unop<float, BcastRowsF>(ctx, op, static_cast<float*>(c), static_cast<const float*>(a), rows * cols, static_cast<const float*>(b), static_cast<long long>(cols))),
                   (dispatch_unop<double, BcastRowsF>(ctx, op, static_cast<double*>(c), static_cast<const double*>(a), rows * cols, static_cast<const double*>(b), static_cast<long long>(cols))));
 }
 int zb_fill(zb_ctx* ctx, int dtype, void* x, double value, int64_t n) {
+  ZB_API_RANGE();
   if (value == 0.0 && n > 0) {
     ZB_CHECK_CUDA(cudaMemsetAsync(x, 0, static_cast<size_t>(n) * (dtype == ZB_F64 ? 8 : 4), ctx->stream));
     return ZB_OK;
@@ -353,30 +360,36 @@ int zb_fill(zb_ctx* ctx, int dtype, void* x, double value, int64_t n) {
                   (launch_map<double, 0>(ctx, FillF<double>{value}, static_cast<double*>(x), static_cast<const double*>(nullptr), static_cast<const double*>(nullptr), n)));
 }
 int zb_copy(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype,
                   (launch_map<float, 1>(ctx, CopyF<float>{}, static_cast<float*>(dst), static_cast<const float*>(src), static_cast<const float*>(nullptr), n)),
                   (launch_map<double, 1>(ctx, CopyF<double>{}, static_cast<double*>(dst), static_cast<const double*>(src), static_cast<const double*>(nullptr), n)));
 }
 int zb_nchw_to_nhwc(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, transpose_batched<float>(ctx, static_cast<const float*>(src), static_cast<float*>(dst), n, c, h * w),
                   transpose_batched<double>(ctx, static_cast<const double*>(src), static_cast<double*>(dst), n, c, h * w));
 }
 int zb_nhwc_to_nchw(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, transpose_batched<float>(ctx, static_cast<const float*>(src), static_cast<float*>(dst), n, h * w, c),
                   transpose_batched<double>(ctx, static_cast<const double*>(src), static_cast<double*>(dst), n, h * w, c));
 }
 int zb_sgd_step(zb_ctx* ctx, int dtype, void* param, const void* grad, double lr, double grad_scale, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype,
                   (launch_map<float, 2>(ctx, SgdF<float>{static_cast<float>(lr), static_cast<float>(grad_scale)}, static_cast<float*>(param), static_cast<const float*>(param), static_cast<const float*>(grad), n)),
                   (launch_map<double, 2>(ctx, SgdF<double>{lr, grad_scale}, static_cast<double*>(param), static_cast<const double*>(param), static_cast<const double*>(grad), n)));
 }
 int zb_adam_step(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m, void* v, double lr, double beta1,
                  double beta2, double eps, double weight_decay, int decay, int64_t step_t, double grad_scale, int64_t n) {
+  ZB_API_RANGE();
   ZB_DTYPE_SWITCH(dtype, adam_t<float>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, step_t, grad_scale, n),
                   adam_t<double>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, step_t, grad_scale, n));
 }
 
 int zb_adam_table_fill(zb_ctx* ctx, int dtype, double beta1, double beta2, int64_t first_step, int64_t count, void* table) {
+  ZB_API_RANGE();
   ZB_REQUIRE(table != nullptr && first_step >= 1 && count >= 1, "zb_adam_table_fill: bad argument");
   ZB_DTYPE_SWITCH(dtype, adam_table_fill_t<float>(ctx, beta1, beta2, first_step, count, table),
                   adam_table_fill_t<double>(ctx, beta1, beta2, first_step, count, table));
@@ -384,11 +397,13 @@ int zb_adam_table_fill(zb_ctx* ctx, int dtype, double beta1, double beta2, int64
 int zb_adam_step_table(zb_ctx* ctx, int dtype, void* param, const void* grad, void* m, void* v, double lr, double beta1, double beta2,
                        double eps, double weight_decay, int decay, const void* table, const int32_t* step_index, double grad_scale,
                        int64_t n) {
+  ZB_API_RANGE();
   ZB_REQUIRE(table != nullptr && step_index != nullptr, "zb_adam_step_table: NULL table / step index");
   ZB_DTYPE_SWITCH(dtype, adam_table_t<float>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, table, step_index, grad_scale, n),
                   adam_table_t<double>(ctx, param, grad, m, v, lr, beta1, beta2, eps, weight_decay, decay, table, step_index, grad_scale, n));
 }
 int zb_adam_advance(zb_ctx* ctx, int32_t* step_index) {
+  ZB_API_RANGE();
   ZB_REQUIRE(step_index != nullptr, "zb_adam_advance: NULL step index");
   adam_advance_kernel<<<1, 1, 0, ctx->stream>>>(step_index);
   ZB_LAUNCH_CHECK(ctx);
@@ -397,6 +412,7 @@ int zb_adam_advance(zb_ctx* ctx, int32_t* step_index) {
 
 int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src_u8, void* dst_nchw, int64_t n, int64_t c, int64_t h,
                          int64_t w, const double* host_mean, const double* host_std) {
+  ZB_API_RANGE();
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "input: unknown dtype %d", dtype);
   ZB_REQUIRE(src_layout == ZB_NCHW || src_layout == ZB_NHWC, "input: unknown source layout %d", src_layout);
   ZB_REQUIRE(c >= 1 && c <= 8, "input: 1..8 channels supported (got %lld)", static_cast<long long>(c));
@@ -420,6 +436,7 @@ int zb_input_u8_to_float(zb_ctx* ctx, int dtype, int src_layout, const void* src
   return ZB_OK;
 }
 int zb_onehot(zb_ctx* ctx, int dtype, const void* labels_i32, void* out, int64_t n, int64_t classes) {
+  ZB_API_RANGE();
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "onehot: unknown dtype %d", dtype);
   if (n * classes == 0) return ZB_OK;
   const long long total = n * classes;

@@ -94,6 +94,7 @@ extern "C" {
 
 int zb_ckpt_write(const char* path, int dtype, int n, const char* const* names, const int* ndims, const int64_t* const* shapes,
                   const void* const* host_data) {
+  ZB_API_RANGE();
   ZB_REQUIRE(path && (n == 0 || (names && ndims && shapes && host_data)), "zb_ckpt_write: NULL argument");
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "zb_ckpt_write: unknown dtype %d", dtype);
   Writer w;
@@ -107,6 +108,7 @@ int zb_ckpt_write(const char* path, int dtype, int n, const char* const* names, 
 
 static int ckpt_open_impl(const char* path, zb_ckpt** out);
 int zb_ckpt_open(const char* path, zb_ckpt** out) {
+  ZB_API_RANGE();
   ZB_REQUIRE(path && out, "zb_ckpt_open: NULL argument");
   try {   // nothing thrown by the parser (bad_alloc, length_error on hostile sizes) may cross the C boundary
     return ckpt_open_impl(path, out);
@@ -187,6 +189,7 @@ int zb_ckpt_count(const zb_ckpt* ck) { return ck ? static_cast<int>(ck->entries.
 
 int zb_ckpt_entry(const zb_ckpt* ck, int index, char* name, int name_cap, int64_t* shape, int* ndim, int* dtype, const void** host_data,
                   int64_t* numel) {
+  ZB_API_RANGE();
   ZB_REQUIRE(ck && index >= 0 && index < static_cast<int>(ck->entries.size()), "zb_ckpt_entry: index out of range");
   const zb_ckpt_entry_t& e = ck->entries[index];
   if (name && name_cap > 0) { strncpy(name, e.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
@@ -199,6 +202,7 @@ int zb_ckpt_entry(const zb_ckpt* ck, int index, char* name, int name_cap, int64_
 }
 
 int zb_ckpt_close(zb_ckpt* ck) {
+  ZB_API_RANGE();
   delete ck;
   return ZB_OK;
 }
@@ -395,21 +399,25 @@ static int load_impl(zb_model* m, const char* path, bool with_state) {
 extern "C" {
 
 int zb_model_save(zb_model* m, const char* path) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m && path, "zb_model_save: NULL argument");
   return save_impl(m, path, false);
 }
 
 int zb_model_load(zb_model* m, const char* path) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m && path, "zb_model_load: NULL argument");
   return load_impl(m, path, false);
 }
 
 int zb_model_save_state(zb_model* m, const char* path) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m && path, "zb_model_save_state: NULL argument");
   return save_impl(m, path, true);
 }
 
 int zb_model_load_state(zb_model* m, const char* path) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m && path, "zb_model_load_state: NULL argument");
   return load_impl(m, path, true);
 }

@@ -84,6 +84,7 @@ extern "C" {
 
 int zb_model_create(zb_ctx* ctx, const char* arch, int dtype, int num_classes, int fused, uint64_t seed, int64_t bucket_bytes,
                     zb_model** out) {
+  ZB_API_RANGE();
   ZB_REQUIRE(ctx && arch && out, "zb_model_create: NULL argument");
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "zb_model_create: unknown dtype %d", dtype);
   ZB_HOST_TRY({
@@ -98,6 +99,7 @@ int zb_model_create(zb_ctx* ctx, const char* arch, int dtype, int num_classes, i
 }
 
 int zb_model_destroy(zb_model* m) {
+  ZB_API_RANGE();
   if (!m) return ZB_OK;
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->comm_stream);
@@ -112,6 +114,7 @@ int zb_model_param_count(zb_model* m) { return static_cast<int>(m->params.entrie
 
 int zb_model_param_info(zb_model* m, int index, char* name, int name_cap, int64_t* shape, int* ndim, int* kind, void** data,
                         void** grad) {
+  ZB_API_RANGE();
   ZB_REQUIRE(index >= 0 && index < static_cast<int>(m->params.entries.size()), "param index out of range");
   const ParamEntry& e = m->params.entries[index];
   if (name && name_cap > 0) {
@@ -128,11 +131,13 @@ int zb_model_param_info(zb_model* m, int index, char* name, int name_cap, int64_
 }
 
 int zb_model_set_train(zb_model* m, int train) {
+  ZB_API_RANGE();
   m->rt->train = train != 0;
   return ZB_OK;
 }
 
 int zb_model_set_optimizer(zb_model* m, int kind, double lr, double beta1, double beta2, double eps, double weight_decay) {
+  ZB_API_RANGE();
   ZB_REQUIRE(kind >= 0 && kind <= 2, "unknown optimizer kind %d", kind);
   cudaStreamSynchronize(m->ctx->stream);
   m->drop_graphs();   // learning rate, betas ... are kernel arguments baked into captured steps
@@ -149,6 +154,7 @@ int zb_model_set_optimizer(zb_model* m, int kind, double lr, double beta1, doubl
 }
 
 int zb_model_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, int64_t h, int64_t w, void* logits_out) {
+  ZB_API_RANGE();
   ZB_HOST_TRY({
     Variable logits = run_forward(m, x_nchw, batch, c, h, w);
     check_rc(zb_copy(m->ctx, m->rt->dtype, logits->data.ptr, logits_out, logits->data.numel()), "copy logits");
@@ -158,6 +164,7 @@ int zb_model_forward(zb_model* m, const void* x_nchw, int64_t batch, int64_t c, 
 
 int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h,
                               int64_t w, void* loss_dev) {
+  ZB_API_RANGE();
   ZB_HOST_TRY({
     Runtime& rt = *m->rt;
     if (m->last_loss.defined()) { m->last_loss.clear_grad(); m->last_loss = Variable(); }
@@ -183,11 +190,13 @@ int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targe
 }
 
 int zb_model_update(zb_model* m) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m->opt_ready, "zb_model_update: call zb_model_set_optimizer first");
   ZB_HOST_TRY({ m->opt.update(*m->rt, m->params); });
 }
 
 int zb_model_set_graph(zb_model* m, int enable) {
+  ZB_API_RANGE();
   ZB_REQUIRE(m, "zb_model_set_graph: NULL model");
   ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
   m->drop_graphs();
@@ -294,6 +303,7 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
 
 int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h, int64_t w,
                         void* loss_dev, double* host_loss) {
+  ZB_API_RANGE();
   const int g = train_step_graph(m, x_nchw, targets, batch, c, h, w, loss_dev, host_loss);
   if (g == 1) return ZB_OK;
   if (g < 0) return -g;
@@ -317,6 +327,7 @@ int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, in
 }
 
 int zb_model_profile_enable(zb_model* m, int enable) {
+  ZB_API_RANGE();
   ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
   m->rt->prof.clear();
   m->rt->prof.enabled = enable != 0;
@@ -324,6 +335,7 @@ int zb_model_profile_enable(zb_model* m, int enable) {
 }
 
 int64_t zb_model_profile_dump(zb_model* m, char* buf, int64_t cap) {
+  ZB_API_RANGE();
   cudaStreamSynchronize(m->ctx->stream);
   struct Agg { int64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
   std::map<std::string, Agg> agg;

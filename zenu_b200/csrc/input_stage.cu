@@ -39,6 +39,7 @@ struct zb_input_stage {
 extern "C" {
 
 int zb_input_stage_destroy(zb_input_stage* st) {
+  ZB_API_RANGE();
   if (!st) return ZB_OK;
   cudaStreamSynchronize(st->copy_stream);
   cudaStreamSynchronize(st->ctx->stream);
@@ -59,6 +60,7 @@ int zb_input_stage_destroy(zb_input_stage* st) {
 
 int zb_input_stage_create(zb_ctx* ctx, int dtype, int src_layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t classes,
                           const double* host_mean, const double* host_std, int slots, zb_input_stage** out) {
+  ZB_API_RANGE();
   ZB_REQUIRE(ctx != nullptr && out != nullptr, "input stage: NULL argument");
   ZB_REQUIRE(dtype == ZB_F32 || dtype == ZB_F64, "input stage: unknown dtype %d", dtype);
   ZB_REQUIRE(src_layout == ZB_NCHW || src_layout == ZB_NHWC, "input stage: unknown source layout %d", src_layout);
@@ -100,6 +102,7 @@ int zb_input_stage_create(zb_ctx* ctx, int dtype, int src_layout, int64_t n, int
 int64_t zb_input_stage_h2d_bytes(const zb_input_stage* st) { return st ? st->n * st->c * st->h * st->w + st->n * 4 : 0; }
 
 int zb_input_stage_host_buffers(zb_input_stage* st, int slot, void** images_u8, void** labels_i32) {
+  ZB_API_RANGE();
   ZB_REQUIRE(st != nullptr && slot >= 0 && slot < st->slots, "input stage: slot out of range");
   if (images_u8) *images_u8 = st->slot[slot].host_img;
   if (labels_i32) *labels_i32 = st->slot[slot].host_lab;
@@ -107,6 +110,7 @@ int zb_input_stage_host_buffers(zb_input_stage* st, int slot, void** images_u8, 
 }
 
 int zb_input_stage_host_sync(zb_input_stage* st, int slot) {
+  ZB_API_RANGE();
   ZB_REQUIRE(st != nullptr && slot >= 0 && slot < st->slots, "input stage: slot out of range");
   auto& s = st->slot[slot];
   if (s.submitted || s.ever_consumed) ZB_CHECK_CUDA(cudaEventSynchronize(s.ready));   // the H2D copy has left the pinned buffers
@@ -114,6 +118,7 @@ int zb_input_stage_host_sync(zb_input_stage* st, int slot) {
 }
 
 int zb_input_stage_submit(zb_input_stage* st, int slot) {
+  ZB_API_RANGE();
   ZB_REQUIRE(st != nullptr && slot >= 0 && slot < st->slots, "input stage: slot out of range");
   auto& s = st->slot[slot];
   // the previous batch staged in this slot must have been expanded before its device staging is overwritten
@@ -126,6 +131,7 @@ int zb_input_stage_submit(zb_input_stage* st, int slot) {
 }
 
 int zb_input_stage_wait(zb_input_stage* st, int slot, void** x_nchw, void** targets_onehot) {
+  ZB_API_RANGE();
   ZB_REQUIRE(st != nullptr && slot >= 0 && slot < st->slots, "input stage: slot out of range");
   auto& s = st->slot[slot];
   ZB_REQUIRE(s.submitted, "input stage: wait on slot %d without a submit", slot);

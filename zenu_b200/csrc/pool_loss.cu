@@ -416,6 +416,7 @@ extern "C" {
 
 int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t h, int64_t w,
                      int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  ZB_API_RANGE();
   { const int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw); if (rc != ZB_OK) return rc; }
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_fwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<float*>(y));
@@ -425,6 +426,7 @@ int zb_maxpool2d_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y,
 }
 int zb_maxpool2d_bwd(zb_ctx* ctx, int dtype, int layout, const void* x, const void* dy, void* dx, int64_t n, int64_t c,
                      int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  ZB_API_RANGE();
   { const int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw); if (rc != ZB_OK) return rc; }
   const PoolGeom g = pool_geom(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (dtype == ZB_F32) return maxpool_bwd_t<float>(ctx, g, static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx));
@@ -440,6 +442,7 @@ static int check_idx_pool(int layout, int64_t c, int64_t kh, int64_t kw, const v
 }
 int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, void* idx, int64_t n, int64_t c, int64_t h,
                          int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  ZB_API_RANGE();
   int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (rc != ZB_OK) return rc;
   rc = check_idx_pool(layout, c, kh, kw, x, y);
@@ -452,6 +455,7 @@ int zb_maxpool2d_fwd_idx(zb_ctx* ctx, int dtype, int layout, const void* x, void
 }
 int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, const void* idx, void* dx, int64_t n, int64_t c,
                          int64_t h, int64_t w, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+  ZB_API_RANGE();
   int rc = check_pool_args(layout, n, c, h, w, kh, kw, sh, sw, ph, pw);
   if (rc != ZB_OK) return rc;
   rc = check_idx_pool(layout, c, kh, kw, dy, dx);
@@ -463,6 +467,7 @@ int zb_maxpool2d_bwd_idx(zb_ctx* ctx, int dtype, int layout, const void* dy, con
   return ZB_ERR_INVALID;
 }
 int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64_t n, int64_t c, int64_t hw) {
+  ZB_API_RANGE();
   ZB_REQUIRE((layout == ZB_NCHW || layout == ZB_NHWC) && n >= 0 && c >= 0 && hw > 0, "global average pool: bad layout / extent");
   const long long total = n * c;
   if (total == 0) return ZB_OK;
@@ -474,6 +479,7 @@ int zb_gap_fwd(zb_ctx* ctx, int dtype, int layout, const void* x, void* y, int64
   return ZB_OK;
 }
 int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int64_t n, int64_t c, int64_t hw) {
+  ZB_API_RANGE();
   ZB_REQUIRE((layout == ZB_NCHW || layout == ZB_NHWC) && n >= 0 && c >= 0 && hw > 0, "global average pool: bad layout / extent");
   const long long total = n * c * hw;
   if (total == 0) return ZB_OK;
@@ -485,6 +491,7 @@ int zb_gap_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dx, int
   return ZB_OK;
 }
 int zb_softmax_xent(zb_ctx* ctx, int dtype, const void* z, const void* t, void* loss, void* dz, int64_t batch, int64_t classes) {
+  ZB_API_RANGE();
   if (dtype == ZB_F32) return softmax_xent_t<float>(ctx, static_cast<const float*>(z), static_cast<const float*>(t), static_cast<float*>(loss), static_cast<float*>(dz), batch, classes);
   if (dtype == ZB_F64) return softmax_xent_t<double>(ctx, static_cast<const double*>(z), static_cast<const double*>(t), static_cast<double*>(loss), static_cast<double*>(dz), batch, classes);
   zb::set_last_error("unknown dtype %d", dtype);

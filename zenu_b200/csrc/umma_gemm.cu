@@ -292,7 +292,6 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, r);
           tmem_ld_wait();
-          if (p.dbg_epi == 2) continue;
 #pragma unroll
           for (int v = 0; v < 8; ++v)
             sts128(stage_u32 + lane * 128 + ((v ^ (lane & 7)) << 4), __uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]),
@@ -310,7 +309,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             if (plain) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                if ((FULL || off32[it] >= 0) && p.dbg_epi != 1) *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = vals[it];
+                if (FULL || off32[it] >= 0) *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = vals[it];
             } else {
               float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
               if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
@@ -569,7 +568,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d_pair(sB, &tmB, fullp, k0, nB0);
           } else if (p.b_mode == B_TILED_MN) {
             if (CL == 1) {
-              for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK - p.dbg_b_shift);
+              for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK);
             } else {
               for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(sB + j * 4096, &tmB, fullp, nB0 + 32 * j, kb * kUmmaBK);
             }
@@ -605,11 +604,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // formed once per launch and advanced by adding to their 14-bit address field (smem addresses < 256 KB: no carry out; in a
       // cluster the shared-window address of rank 1 carries the CTA rank in bit 24, which must not leak into the LBO field).
       const uint64_t a_desc0 = (a_mn ? make_smem_desc(0, 4096, 512, kSmemLayoutSw128Base32)
-                                     : make_smem_desc(0, 16, 1024, kSmemLayoutSw128, p.dbg_base_mode == 2 ? (p.dbg_a_shift & 7) : 0)) +
-                               (((smem_u32(smem) & 0x3FFFFu) + (a_mn ? 0 : p.dbg_a_shift * 128)) >> 4);
-      const uint64_t b_desc0 = (b_mn ? make_smem_desc(0, p.dbg_b_lbo ? p.dbg_b_lbo : 4096, 512, kSmemLayoutSw128Base32)
                                      : make_smem_desc(0, 16, 1024, kSmemLayoutSw128)) +
-                               (((smem_u32(smem) & 0x3FFFFu) + L::A_BYTES + (b_mn ? p.dbg_b_shift * 128 : 0)) >> 4);
+                               ((smem_u32(smem) & 0x3FFFFu) >> 4);
+      const uint64_t b_desc0 = (b_mn ? make_smem_desc(0, 4096, 512, kSmemLayoutSw128Base32)
+                                     : make_smem_desc(0, 16, 1024, kSmemLayoutSw128)) +
+                               (((smem_u32(smem) & 0x3FFFFu) + L::A_BYTES) >> 4);
       const uint32_t a_kstep = a_mn ? (1024 >> 4) : (32 >> 4), b_kstep = b_mn ? (1024 >> 4) : (32 >> 4);
       int stage = 0;
       uint32_t phase = 0;
@@ -679,7 +678,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // zero fill) for a 32-channel chunk, each pixel one 128-byte row of the K-major SWIZZLE_128B layout; the M tile is the raster
 // positions of tp output rows, and tap (r, s) is the SAME smem data read through a descriptor that starts r*Wr + s rows later
 // (the hardware swizzle is a function of the absolute smem address, so a start that is 128- but not 1024-byte aligned is
-// legal: measured with tools/probe_desc_shift.py).  Filter tiles stream through their own ring, or stay resident for the
+// legal: measured in round 1 with a descriptor-shift probe build, git history: tools/probe_desc_shift.py).  Filter tiles stream through their own ring, or stay resident for the
 // whole persistent CTA when the filter fits (64 -> 64 channels).  Output positions in halo columns are computed and dropped.
 // CL > 1: thread-block cluster of CL CTAs working on CL consecutive row blocks of the same column block in lockstep.  The
 // streamed filter tiles are what bounds the >= 128-channel 3x3 layers (a 128-pixel tile re-reads the whole [BN][taps*C] filter
@@ -1176,7 +1175,6 @@ static int pair_cl(const UmmaParams& p, int bn) {
   if (p.b_mode != B_TILED_K && p.b_mode != B_TILED_MN && p.b_mode != B_IM2COL_MN) return 1;
   if (p.b_mode == B_TILED_K && p.hb_base == nullptr) return 1;
   if (p.out_mode != OUT_ROWS && p.out_mode != OUT_SCATTER) return 1;
-  if (p.dbg_b_shift != 0 || p.dbg_a_shift != 0) return 1;
   return 2;
 }
 // persistent grid of a launch: one CTA per SM (or per tile), a multiple of n_tiles (of cl * n_tiles) with fused statistics
@@ -1364,17 +1362,6 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
   p.stride_w = p.stride_h = 1;
   p.alpha = 1.f;
   p.err_flag = ctx->err_flag;
-  struct DbgEnv {   // hardware-probe knobs (tools/probe_*.py), parsed once
-    int a_shift = 0, base_mode = 0, epi = 0, b_shift = 0, b_lbo = 0;
-    DbgEnv() {
-      if (const char* e = getenv("ZENU_B200_DBG_ASHIFT")) sscanf(e, "%d,%d", &a_shift, &base_mode);
-      if (const char* e = getenv("ZENU_B200_DBG_EPI")) epi = atoi(e);
-      if (const char* e = getenv("ZENU_B200_DBG_BSHIFT")) sscanf(e, "%d,%d", &b_shift, &b_lbo);
-    }
-  };
-  static const DbgEnv dbg;
-  p.dbg_a_shift = dbg.a_shift; p.dbg_base_mode = dbg.base_mode; p.dbg_epi = dbg.epi;
-  p.dbg_b_shift = dbg.b_shift; p.dbg_b_lbo = dbg.b_lbo;
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM

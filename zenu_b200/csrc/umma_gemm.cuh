@@ -73,8 +73,6 @@ struct UmmaParams {
   // a CTA only ever sees one column block) and written once to stat_partial[(blockIdx.x / n_tiles) * 4 + warp][2][N]
   float* stat_partial;
   const float* stat_shift;
-  int dbg_b_shift, dbg_b_lbo;  // experiments only (ZENU_B200_DBG_BSHIFT): MN-major B descriptor start shifted by 128-byte rows / overlapped N boxes
-  int dbg_a_shift, dbg_base_mode, dbg_epi;  // experiments only (ZENU_B200_DBG_ASHIFT): A descriptor start shifted by whole 128-byte rows
   // host only: the K-major B matrix as given to make_map_2d, so that the launcher can re-encode its tensor map with a half-height box
   // when it runs the launch on CTA pairs (umma_kernel CL = 2)
   const float* hb_base;

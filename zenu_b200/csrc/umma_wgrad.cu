@@ -12,7 +12,7 @@
 //   * filter column s = the next 32-column group of N with a leading-dimension stride of ONE row (LBO = 128 B): the S
 //     N-groups of one MMA are the same smem rows shifted by 0..S-1 pixels.
 // (The swizzle is a function of the absolute smem address, so row-granular descriptor starts and overlapping N groups are
-// legal: measured with tools/probe_mn_shift.py.)  One MMA = [128 k] x [S*32 (s, c)] x [8 pixels]; R accumulators of S*32
+// legal: measured in round 1 with a descriptor-shift probe build, git history: tools/probe_mn_shift.py.)  One MMA = [128 k] x [S*32 (s, c)] x [8 pixels]; R accumulators of S*32
 // columns live in TMEM for the whole kernel: each CTA owns (32-channel chunk, 128-k tile, pixel range) and drains TMEM once.
 // dY and X are each fetched once per CTA role instead of once per tap.  Partials [split][K][R*S*C] -> deterministic reduce.
 #include <algorithm>
