@@ -71,6 +71,27 @@ def test_reference_ffi_surface_is_exported_with_the_reference_prototypes(lib, su
     assert not bad, bad
 
 
+def test_rust_sys_crate_in_sync():
+    """rust/zenu-b200-sys/src/lib.rs (the bindings the Rust glue under rust/patches binds) is what tools/gen_rust_sys.py derives
+    from include/zenu_b200.h today: every zb_* function, in header order, with the C types mapped 1:1."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = mod.generate()
+    with open(mod.OUT) as f:
+        assert f.read() == text, "run `python tools/gen_rust_sys.py` after changing include/zenu_b200.h"
+    declared = set(_declared("zenu_b200.h"))
+    bound = set(re.findall(r"pub fn (zb_\w+)\(", text))
+    assert bound == declared, sorted(bound ^ declared)
+    # every zb_* call made by the patched reference sources exists in the bindings
+    used = set()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rust", "patches")):
+        for fn in files:
+            used |= set(re.findall(r"sys::(zb_\w+)\(", open(os.path.join(dirpath, fn)).read()))
+    assert used and used <= bound, sorted(used - bound)
+
+
 def test_header_prototypes_parse():
     protos = _lib.parse_header(os.path.join(ROOT, "include", "zenu_b200.h"))
     assert protos["zb_conv2d_fprop"][1][4] is ctypes.c_void_p
