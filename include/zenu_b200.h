@@ -68,6 +68,15 @@ int zb_ctx_set_math(zb_ctx* ctx, int math_mode);
 int zb_ctx_set_bn_epsilon(zb_ctx* ctx, double eps);
 double zb_ctx_bn_epsilon(zb_ctx* ctx);
 void* zb_ctx_stream(zb_ctx* ctx);
+/* Side context: a child ctx on its own non-blocking stream with its own scratch arena, for work that may overlap the parent's stream
+ * (the host model runs conv wgrad there: its result is only needed by the optimizer, and a tensor-bound wgrad co-resides with the
+ * HBM-bound BatchNorm-backward kernels of the next layer).  Created on first use, destroyed with the parent, included in
+ * zb_ctx_synchronize / zb_ctx_check / zb_ctx_launch_count.  zb_ctx_fork makes the side stream wait for everything enqueued on the
+ * parent so far; zb_ctx_join makes the parent wait for everything enqueued on the side stream.  Both are event based (no host sync)
+ * and capturable.  Buffers a side kernel reads must stay alive (and unwritten by the parent stream) until the join. */
+zb_ctx* zb_ctx_side(zb_ctx* ctx);
+int zb_ctx_fork(zb_ctx* ctx);
+int zb_ctx_join(zb_ctx* ctx);
 /* Non-zero status if any kernel since the last call hit a device-side timeout. Synchronises. */
 int zb_ctx_check(zb_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py reports the delta as gpu_launches). */

@@ -53,6 +53,10 @@ struct zb_ctx {
   bool nccl_failed;          // an asynchronous NCCL error was seen: the communicator has been aborted
   cudaEvent_t ev_ready, ev_done;  // compute->comm and comm->compute fences
   unsigned long long launches;  // number of kernels this ctx launched (bench.py's gpu_launches)
+  // side context (zb_ctx_side): own stream + own scratch arena for work that may overlap this ctx's stream; forked / joined with events
+  zb_ctx* side;
+  zb_ctx* parent;            // non-NULL in a side context
+  cudaEvent_t ev_fork, ev_join;
   zb::ProfState* prof;          // optional per-op CUDA-event timing (zb_ctx_profile_*)
 };
 

@@ -145,10 +145,52 @@ int zb_ctx_create(zb_ctx** out, int device, void* stream) {
   return ZB_OK;
 }
 
+zb_ctx* zb_ctx_side(zb_ctx* ctx) {
+  if (ctx == nullptr) return nullptr;
+  if (ctx->parent != nullptr) return ctx;   // a side context has no side of its own
+  if (ctx->side == nullptr) {
+    zb_ctx* s = nullptr;
+    if (zb_ctx_create(&s, ctx->device, nullptr) != ZB_OK) return nullptr;
+    s->parent = ctx;
+    s->default_math = ctx->default_math;
+    s->bn_eps = ctx->bn_eps;
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      zb::set_last_error("zb_ctx_side: cannot create the fork / join events");
+      zb_ctx_destroy(s);
+      return nullptr;
+    }
+    ctx->side = s;
+  }
+  ctx->side->default_math = ctx->default_math;
+  return ctx->side;
+}
+
+int zb_ctx_fork(zb_ctx* ctx) {
+  ZB_REQUIRE(ctx != nullptr && ctx->side != nullptr, "zb_ctx_fork: no side context (call zb_ctx_side first)");
+  ZB_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->side->stream, ctx->ev_fork, 0));
+  return ZB_OK;
+}
+
+int zb_ctx_join(zb_ctx* ctx) {
+  ZB_REQUIRE(ctx != nullptr, "zb_ctx_join: ctx is NULL");
+  if (ctx->side == nullptr) return ZB_OK;
+  ZB_CHECK_CUDA(cudaEventRecord(ctx->ev_join, ctx->side->stream));
+  ZB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return ZB_OK;
+}
+
 int zb_ctx_destroy(zb_ctx* ctx) {
   ZB_API_RANGE();
   if (!ctx) return ZB_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->side) {
+    zb_ctx_destroy(ctx->side);
+    ctx->side = nullptr;
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->comm_stream);
   zb::dp_destroy(ctx);
@@ -193,6 +235,7 @@ int zb_ctx_profile_read(zb_ctx* ctx, int cls, int64_t* ops, double* total_ms, do
 
 int zb_ctx_synchronize(zb_ctx* ctx) {
   ZB_API_RANGE();
+  if (ctx->side) ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->side->stream));
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return ZB_OK;
 }
@@ -215,6 +258,10 @@ void* zb_ctx_stream(zb_ctx* ctx) { return ctx->stream; }
 
 int zb_ctx_check(zb_ctx* ctx) {
   ZB_API_RANGE();
+  if (ctx->side) {   // kernels on the side stream report through their own flag
+    const int rc = zb_ctx_check(ctx->side);
+    if (rc != ZB_OK) return rc;
+  }
   ZB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   int flag = 0;
   ZB_CHECK_CUDA(cudaMemcpy(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
@@ -227,6 +274,6 @@ int zb_ctx_check(zb_ctx* ctx) {
   return zb::dp_poll_async_error(ctx);
 }
 
-unsigned long long zb_ctx_launch_count(zb_ctx* ctx) { return ctx->launches; }
+unsigned long long zb_ctx_launch_count(zb_ctx* ctx) { return ctx->launches + (ctx->side ? ctx->side->launches : 0ull); }
 
 }  // extern "C"

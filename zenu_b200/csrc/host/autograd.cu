@@ -47,6 +47,19 @@ void Allocator::release_cached() {
   }
 }
 
+Runtime::Runtime(zb_ctx* c) : ctx(c), alloc(c) {
+  // ZENU_B200_WGRAD_OVERLAP=0 keeps every kernel on the one compute stream
+  static const bool on = []() { const char* e = getenv("ZENU_B200_WGRAD_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+  overlap_wgrad = on && zb_ctx_side(c) != nullptr;
+}
+
+void Runtime::join_side() {
+  if (!side_pending) return;
+  check_rc(zb_ctx_join(ctx), "join");
+  side_hold.clear();
+  side_pending = false;
+}
+
 Tensor Runtime::empty(std::vector<int64_t> shape) {
   Tensor t;
   t.shape = std::move(shape);
@@ -227,7 +240,15 @@ struct ConvFn : Function {
   void backward(Runtime& rt, const Tensor& gy) override {
     VariableInner& xv = *inputs[0];
     VariableInner& wv = *inputs[1];
-    if (wv.requires_grad) {
+    // wgrad feeds nothing but the optimizer: with overlap enabled it runs on the side stream, after the dgrad below has been
+    // enqueued on the main stream (which is the critical path: it is dispatched first), and overlaps the BatchNorm-backward kernels
+    // of the next layer.  The previous layer's side work is joined first, so at most one wgrad is in flight and the tensors it reads
+    // (held in rt.side_hold) are released before the main stream can be handed their memory again.
+    const bool side_wgrad = wv.requires_grad && rt.overlap_wgrad && !rt.prof.enabled && !prof_active(rt.ctx) && x_layout == ZB_NHWC &&
+                            !wv.grad.defined();
+    if (rt.side_pending) rt.join_side();
+    if (side_wgrad) check_rc(zb_ctx_fork(rt.ctx), "fork");   // gy (and everything before it) is complete for the side stream
+    if (wv.requires_grad && !side_wgrad) {
       Tensor dw = grad_target(rt, wv);
       ProfScope ps(rt, conv_key("wgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
       check_rc(zb_conv2d_wgrad(rt.ctx, gy.dtype, x_layout, ZB_MATH_DEFAULT, &d, gy.ptr, x.ptr, dw.ptr), "conv wgrad");
@@ -251,6 +272,14 @@ struct ConvFn : Function {
         check_rc(zb_conv2d_dgrad(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, dx.ptr), "conv dgrad");
         commit_grad(rt, xv, dx);
       }
+    }
+    if (side_wgrad) {
+      Tensor dw = grad_target(rt, wv);
+      check_rc(zb_conv2d_wgrad(zb_ctx_side(rt.ctx), gy.dtype, x_layout, ZB_MATH_DEFAULT, &d, gy.ptr, x.ptr, dw.ptr), "conv wgrad (side stream)");
+      rt.side_hold.push_back(x);
+      rt.side_hold.push_back(gy);
+      rt.side_pending = true;
+      commit_grad(rt, wv, dw);
     }
     x = Tensor();
   }

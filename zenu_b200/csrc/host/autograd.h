@@ -88,7 +88,13 @@ struct Runtime {  // one per model: ctx + allocator + train flag (reference: glo
   bool train = true;
   int dtype = ZB_F32;
   OpProfiler prof;
-  explicit Runtime(zb_ctx* c) : ctx(c), alloc(c) {}
+  // conv wgrad on the ctx's side stream (zb_ctx_side): overlaps the BatchNorm-backward / dgrad chain of the following layers.
+  // Tensors the side kernels read are held here until join_side() has made the main stream wait for them.
+  bool overlap_wgrad = false;
+  bool side_pending = false;
+  std::vector<Tensor> side_hold;
+  void join_side();
+  explicit Runtime(zb_ctx* c);
   Tensor empty(std::vector<int64_t> shape);
   Tensor zeros(std::vector<int64_t> shape);
   Tensor borrow(void* p, std::vector<int64_t> shape);  // non-owning

@@ -101,8 +101,11 @@ int zb_model_create(zb_ctx* ctx, const char* arch, int dtype, int num_classes, i
 int zb_model_destroy(zb_model* m) {
   ZB_API_RANGE();
   if (!m) return ZB_OK;
+  if (m->ctx->side) cudaStreamSynchronize(m->ctx->side->stream);
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->comm_stream);
+  m->rt->side_hold.clear();
+  m->rt->side_pending = false;
   if (m->last_loss.defined()) m->last_loss.clear_grad();
   m->drop_graphs();
   if (m->pinned_loss) cudaFreeHost(m->pinned_loss);
@@ -167,6 +170,7 @@ int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targe
   ZB_API_RANGE();
   ZB_HOST_TRY({
     Runtime& rt = *m->rt;
+    rt.join_side();   // (only pending when an earlier step threw half way through its backward)
     if (m->last_loss.defined()) { m->last_loss.clear_grad(); m->last_loss = Variable(); }
     for (auto& e : m->params.entries) e.var->grad = Tensor();  // loss.clear_grad() of the previous step
     m->params.reset_pending();
@@ -180,10 +184,12 @@ int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targe
     loss.backward(rt, [&](int code) {
       const int b = -1 - code;
       if (b < 0 || b >= static_cast<int>(ps.buckets.size())) return;
-      if (--ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1)
+      if (--ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1) rt.join_side();   // the bucket's last wgrad may be on the side stream
+      if (ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1)
         check_rc(zb_dp_allreduce_sum(ctx, rt.dtype, static_cast<uint8_t*>(ps.flat_grads.ptr) + ps.buckets[b].offset * esz,
                                      ps.buckets[b].numel), "bucket allreduce");
     });
+    rt.join_side();   // every gradient is complete on the compute stream from here on (optimizer, capture end)
     if (loss_dev) check_rc(zb_copy(ctx, rt.dtype, loss->data.ptr, loss_dev, 1), "copy loss");
     m->last_loss = loss;
   });
@@ -224,7 +230,8 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
   for (auto& g : m->graphs)
     if (g.sig == sig) hit = &g;
   // any captured step whose buffers went away is unusable, and so are its siblings (they share the allocator and the arena)
-  if (!m->graphs.empty() && (m->graphs.front().generation != gen || m->graphs.front().ws_generation != ctx->ws_generation)) {
+  const unsigned long long ws_gen = ctx->ws_generation + (ctx->side ? ctx->side->ws_generation : 0ull);   // both arenas only ever count up
+  if (!m->graphs.empty() && (m->graphs.front().generation != gen || m->graphs.front().ws_generation != ws_gen)) {
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
     m->graphs.clear();
     for (auto& wu : m->warm) wu.eager = 0;   // every signature warms up again before it is re-captured
@@ -244,8 +251,9 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
       for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
       m->graphs.clear();
     }
-    const unsigned long long l0 = ctx->launches;
+    const unsigned long long l0 = zb_ctx_launch_count(ctx);
     ctx->ws_grow_refused = false;
+    if (ctx->side) ctx->side->ws_grow_refused = false;
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
       cudaGetLastError();            // e.g. the ctx runs on the legacy default stream, which cannot be captured
@@ -259,13 +267,16 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
     if (rc == ZB_OK && cudaMemcpyAsync(m->pinned_loss, m->last_loss->data.ptr, esz, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
       rc = ZB_ERR_CUDA;
     const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-    const unsigned long long captured = ctx->launches - l0;
-    ctx->launches = l0;
+    const unsigned long long captured = zb_ctx_launch_count(ctx) - l0;
+    ctx->launches = l0 - (ctx->side ? ctx->side->launches : 0ull);   // nothing ran during capture: the replay below counts it
     if (rc != ZB_OK || ce != cudaSuccess || graph == nullptr) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
-      if (ctx->ws_grow_refused) {   // the arena had to grow: not capturable yet.  Nothing ran; this step goes eagerly and warms up again
+      if (ctx->ws_grow_refused || (ctx->side && ctx->side->ws_grow_refused)) {   // an arena had to grow: not capturable yet.  Nothing ran; this step goes eagerly and warms up again
         ctx->ws_grow_refused = false;
+        if (ctx->side) ctx->side->ws_grow_refused = false;
+        m->rt->side_hold.clear();
+        m->rt->side_pending = false;
         wu->eager = 1;
         return 0;
       }
@@ -277,7 +288,7 @@ static int train_step_graph(zb_model* m, const void* x, const void* t, int64_t b
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { cudaGetLastError(); m->graph_enabled = false; return 0; }
-    m->graphs.push_back({sig, m->rt->alloc.generation(), ctx->ws_generation, captured, exec});
+    m->graphs.push_back({sig, m->rt->alloc.generation(), ctx->ws_generation + (ctx->side ? ctx->side->ws_generation : 0ull), captured, exec});
     hit = &m->graphs.back();
   }
   try {
