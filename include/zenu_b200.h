@@ -345,6 +345,9 @@ int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_one
  * (buffers, shape) signature and replayed, NCCL bucket allreduces included.  Needs a ctx whose compute stream can be captured
  * (not the legacy default stream); otherwise, and while per-node profiling is on, steps keep running eagerly. */
 int zb_model_set_graph(zb_model* m, int enable);
+/* Run every conv wgrad of the backward sweep on the ctx's side stream (zb_ctx_side), overlapping the BatchNorm-backward / dgrad
+ * chain of the following layers; results are bit-identical.  Off by default: measured neutral-to-slower on B200. */
+int zb_model_set_wgrad_overlap(zb_model* m, int enable);
 int zb_model_graph_count(zb_model* m); /* step graphs captured so far (0: every step so far ran eagerly) */
 /* Per-node timing (CUDA events on the compute stream around every tape node, forward and backward).  dump writes one
  * line per distinct node key: "key\tcount\ttotal_ms\talgorithmic_flops\talgorithmic_bytes\n" (sums over count) and returns

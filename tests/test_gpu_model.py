@@ -324,3 +324,38 @@ def test_step_graphs_with_changing_shapes_and_scratch_growth(zb):
     assert torch.equal(g0, g1)
     for k in p0:
         assert torch.equal(p0[k], p1[k]), k
+
+
+@pytest.mark.parametrize("arch,n,hw,classes,graph", [("resnet18", 8, 64, 10, False), ("resnet18", 8, 64, 10, True), ("small_cnn", 32, 32, 10, True)])
+def test_wgrad_on_side_stream_is_bit_identical(zb, arch, n, hw, classes, graph):
+    """zb_model_set_wgrad_overlap: conv wgrad forked onto the ctx's side stream (zb_ctx_side / fork / join) while the main stream goes
+    on with dgrad and the next layer's BatchNorm backward.  Same kernels, same inputs: losses and parameters must match the
+    single-stream run bit for bit, eagerly and from a captured step graph (the fork / join edges are captured with it)."""
+    pkg, ops, nn = zb
+    x, t = batch(n, hw, classes, 77)
+    X, T = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    runs = []
+    for overlap in (False, True):
+        with torch.cuda.stream(side):
+            ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+            model = nn.Model(ctx, arch, classes, seed=6)
+            model.set_optimizer("sgd", lr=1e-3)
+            model.set_wgrad_overlap(overlap)
+            if graph:
+                model.set_graph(True)
+            lb = torch.empty((1,), dtype=torch.float32, device="cuda")
+            l0 = ctx.launch_count()
+            losses = [model.train_step(X, T, loss_out=lb, read_loss=True) for _ in range(5)]
+            launches = ctx.launch_count() - l0
+            ctx.check()
+            assert model.graph_count() == (1 if graph else 0)
+            runs.append((losses, {k: v["data"].clone() for k, v in model.named_parameters().items()}, launches))
+            model.close()
+            ctx.close()
+        torch.cuda.synchronize()
+    (l0, p0, n0), (l1, p1, n1) = runs
+    assert all(np.isfinite(l0)) and l0 == l1 and n0 == n1
+    for k in p0:
+        assert torch.equal(p0[k], p1[k]), k

@@ -48,8 +48,12 @@ void Allocator::release_cached() {
 }
 
 Runtime::Runtime(zb_ctx* c) : ctx(c), alloc(c) {
-  // ZENU_B200_WGRAD_OVERLAP=0 keeps every kernel on the one compute stream
-  static const bool on = []() { const char* e = getenv("ZENU_B200_WGRAD_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+  // Off by default (zb_model_set_wgrad_overlap / ZENU_B200_WGRAD_OVERLAP=1 turn it on).  Measured on ResNet-50, batch 256
+  // (profiles/r2b_wgrad_overlap.md): 36.99 ms / step with the overlap, 36.68 without.  The tensor-core kernels hold ~225 registers
+  // x 192 threads and up to 227 KB of shared memory per SM, so at most ONE 256-thread BatchNorm CTA fits beside a resident wgrad CTA
+  // (the reduce kernels, which need 8 KB of shared memory, none): the HBM-bound kernel on the critical path loses more bandwidth
+  // than the off-path wgrad gains.
+  static const bool on = []() { const char* e = getenv("ZENU_B200_WGRAD_OVERLAP"); return e != nullptr && e[0] == '1'; }();
   overlap_wgrad = on && zb_ctx_side(c) != nullptr;
 }
 

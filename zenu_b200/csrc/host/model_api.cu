@@ -201,6 +201,15 @@ int zb_model_update(zb_model* m) {
   ZB_HOST_TRY({ m->opt.update(*m->rt, m->params); });
 }
 
+int zb_model_set_wgrad_overlap(zb_model* m, int enable) {
+  ZB_API_RANGE();
+  ZB_REQUIRE(m, "zb_model_set_wgrad_overlap: NULL model");
+  ZB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  m->drop_graphs();   // the fork / join edges are part of a captured step
+  m->rt->overlap_wgrad = enable != 0 && zb_ctx_side(m->ctx) != nullptr;
+  return ZB_OK;
+}
+
 int zb_model_set_graph(zb_model* m, int enable) {
   ZB_API_RANGE();
   ZB_REQUIRE(m, "zb_model_set_graph: NULL model");

@@ -134,6 +134,10 @@ class Model:
                                            ctypes.c_void_p(loss.data_ptr()), ctypes.byref(host) if read_loss else None))
         return host.value if read_loss else loss
 
+    def set_wgrad_overlap(self, enable=True):
+        """conv wgrad on the ctx's side stream, overlapping the following layers' BatchNorm backward (bit-identical results)."""
+        check(self.lib.zb_model_set_wgrad_overlap(self._h, int(bool(enable))))
+
     def set_graph(self, enable=True):
         """Replay `train_step` from a CUDA graph: each distinct (buffers, batch shape, train mode, math mode, DP world) signature is
         captured after two eager steps of its own -- SGD / Adam / AdamW, bucket allreduces included -- and dropped when the buffers
