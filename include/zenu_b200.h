@@ -211,8 +211,24 @@ int zb_binary_bcast_rows(zb_ctx* ctx, int dtype, int op, const void* a, const vo
                          int64_t cols);
 /* out[j] = sum_r a[r, j]  (Matrix::sum(axis 0), operation/sum.rs:9-31: bias / gamma / beta gradients) */
 int zb_sum_rows(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t rows, int64_t cols);
+/* Axis reductions of a contiguous tensor viewed as [outer][len][inner] -> [outer][inner]: Matrix::sum(axis) (operation/sum.rs:9-31, a
+ * loop of `len` add_assign launches there), Matrix::mean(axis) (operation/mean.rs:8-20: sum / len) and Matrix::variance(axis)
+ * (operation/var.rs:18-26: biased, the mean of squared differences from the mean; mean_out, optional, also receives the mean).
+ * keep_dim is a view concern of the caller: the output has outer * inner elements either way. */
+int zb_sum_axis(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t outer, int64_t len, int64_t inner);
+int zb_mean_axis(zb_ctx* ctx, int dtype, const void* a, void* out, int64_t outer, int64_t len, int64_t inner);
+int zb_variance_axis(zb_ctx* ctx, int dtype, const void* a, void* out, void* mean_out, int64_t outer, int64_t len, int64_t inner);
+/* sum_to (operation/sum.rs:35-92; autograd node zenu-autograd/src/functions/sum_to.rs): reduce src to a shape it broadcasts from --
+ * shapes are right-aligned, missing leading axes and axes whose target extent is 1 are summed.  Host shape arrays, <= 8 axes. */
+int zb_sum_to(zb_ctx* ctx, int dtype, const void* src, const int64_t* src_shape, int src_ndim, void* dst, const int64_t* dst_shape,
+              int dst_ndim);
 int zb_fill(zb_ctx* ctx, int dtype, void* x, double value, int64_t n); /* zeros(): reference scales by 0 (NaN-unsafe) */
 int zb_copy(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n);
+/* Strided element copy, dst[sum_k i_k * dst_strides[k]] = src[sum_k i_k * src_strides[k]] over a <= 8-axis index space (element
+ * strides, host arrays): what copy_from / to_default_stride / transpose-materialise reach through CopyBlas::copy_raw
+ * (operation/copy_from.rs:9-55: one cublas{S,D}copy per contiguous run).  Dense-to-dense calls take the vectorised zb_copy. */
+int zb_copy_strided(zb_ctx* ctx, int dtype, const void* src, void* dst, int ndim, const int64_t* shape, const int64_t* src_strides,
+                    const int64_t* dst_strides);
 /* layout transforms (replace transpose_by_index_new_matrix + to_default_stride copies) */
 int zb_nchw_to_nhwc(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w);
 int zb_nhwc_to_nchw(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n, int64_t c, int64_t h, int64_t w);

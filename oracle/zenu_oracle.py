@@ -336,3 +336,47 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_t, weight_decay=0.0, decay
     assert p.flags.c_contiguous and m.flags.c_contiguous and v.flags.c_contiguous
     getattr(lib(), "zo_adam_step" + s)(_p(p), _p(_c(g, p.dtype)), _p(m), _p(v), ct(lr), ct(beta1), ct(beta2), ct(eps),
                                        ct(weight_decay), int(decay), I64(step_t), I64(p.size))
+
+
+# ---- axis reductions / strided copies (numpy restatements; the accumulation ORDER is the reference's) ----------------------------
+def sum_axis(a, axis, keep_dim=False):
+    """Matrix::sum(axis, keep_dim), zenu-matrix/src/operation/sum.rs:9-31: result = zeros; for i in 0..shape[axis]: result += a[.., i, ..]
+    (sequential accumulation in the element type, not numpy's pairwise sum)."""
+    a = np.asarray(a)
+    res = np.zeros(a.shape[:axis] + a.shape[axis + 1:], a.dtype)
+    for i in range(a.shape[axis]):
+        res += np.take(a, i, axis=axis)
+    return np.expand_dims(res, axis) if keep_dim else res
+
+
+def sum_to(a, shape):
+    """sum_to(source, target), operation/sum.rs:35-92: leading extra axes are summed away one by one (sum(0)), then every axis whose
+    target extent is 1 is summed with keep_dim."""
+    a = np.asarray(a)
+    shape = tuple(shape)
+    assert a.ndim >= len(shape)
+    while a.ndim > len(shape):
+        a = sum_axis(a, 0)
+    for k, (s, t) in enumerate(zip(a.shape, shape)):
+        if s != t:
+            assert t == 1, "sum_to: incompatible target shape"
+            a = sum_axis(a, k, keep_dim=True)
+    return a.copy()
+
+
+def mean_axis(a, axis, keep_dim=False):
+    """Matrix::mean(Some(axis), keep_dim), operation/mean.rs:8-20: sum / len in the element type."""
+    a = np.asarray(a)
+    return sum_axis(a, axis, keep_dim) / a.dtype.type(a.shape[axis])
+
+
+def variance_axis(a, axis, keep_dim=False):
+    """Matrix::variance(Some(axis), keep_dim), operation/var.rs:18-26: biased, mean((x - mean)^2)."""
+    a = np.asarray(a)
+    diff = a - mean_axis(a, axis, keep_dim=True)
+    return mean_axis(diff * diff, axis, keep_dim)
+
+
+def copy_strided(src_view):
+    """copy_from into a default-stride destination (operation/copy_from.rs:57-123): element order of the source VIEW."""
+    return np.ascontiguousarray(src_view)

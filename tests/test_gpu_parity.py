@@ -832,3 +832,63 @@ def test_input_stage(zb, ctx):
         with pytest.raises(Exception):
             st.wait(0)                          # no submit pending on that slot
         st.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_reductions_and_strided_copy_vs_oracle(zb, ctx, dtype):
+    """SURVEY 8a-12 / 8a-13 as first-class ops through the C ABI: Matrix::sum(axis) / sum_to / mean / variance
+    (zenu-matrix/src/operation/{sum.rs:9-92, mean.rs:8-20, var.rs:18-26}), zeros / copy / strided copy_from
+    (device/mod.rs:33-69, operation/copy_from.rs:9-123), against the oracle's restatements (reference accumulation order)."""
+    rng = np.random.default_rng(17)
+    tol = 2e-5 if dtype == np.float32 else 1e-12
+    lit = np.arange(120, dtype=dtype).reshape(2, 3, 4, 5)           # the reference's own test tensor (sum.rs:104-160)
+    for axis in range(4):
+        for keep in (False, True):
+            got = host(zb.sum_axis(ctx, dev(lit), axis, keep))
+            np.testing.assert_array_equal(got, zo.sum_axis(lit, axis, keep))
+    shapes = [((7, 5, 3), None), ((64, 1000), None), ((3, 700, 33), None), ((1, 5000, 1), None), ((6, 2, 4, 130), None), ((2048, 9), None),
+              ((4, 100000), None)]
+    for shape, _ in shapes:
+        a = (rng.standard_normal(shape) + 0.5).astype(dtype)
+        A = dev(a)
+        for axis in range(len(shape)):
+            ref = zo.sum_axis(a.astype(np.float64), axis)
+            scale = np.abs(a).astype(np.float64).sum(axis).max() + 1e-30
+            assert np.max(np.abs(host(zb.sum_axis(ctx, A, axis)) - ref)) / scale < tol, (shape, axis)
+            np.testing.assert_allclose(host(zb.mean_axis(ctx, A, axis, True)), zo.mean_axis(a.astype(np.float64), axis, True), rtol=50 * tol,
+                                       atol=50 * tol)
+            var, mean = zb.variance_axis(ctx, A, axis, want_mean=True)
+            np.testing.assert_allclose(host(var), zo.variance_axis(a.astype(np.float64), axis), rtol=100 * tol, atol=10 * tol)
+            np.testing.assert_allclose(host(mean), zo.mean_axis(a.astype(np.float64), axis), rtol=50 * tol, atol=50 * tol)
+            np.testing.assert_array_equal(host(zb.variance_axis(ctx, A, axis)), host(var))      # mean_out = NULL path
+    assert abs(float(host(zb.variance_axis(ctx, dev(np.array([1, 2, 3, 4], dtype)), 0))) - 1.25) < 1e-6   # var.rs:35-40
+    # sum_to: bias / gamma / beta gradients and broadcast backward (functions/sum_to.rs)
+    g = rng.standard_normal((5, 6, 7, 8)).astype(dtype)
+    G = dev(g)
+    for target in ((8,), (7, 8), (1, 8), (6, 1, 8), (5, 1, 7, 1), (1, 1, 1, 1), (5, 6, 7, 8), (1, 6, 1, 1), ()):
+        got = host(zb.sum_to(ctx, G, target))
+        ref = zo.sum_to(g.astype(np.float64), target)
+        assert got.shape == tuple(target)
+        np.testing.assert_allclose(got, ref, rtol=50 * tol, atol=200 * tol)
+    from zenu_b200 import ZenuB200Error
+    with pytest.raises(ZenuB200Error):
+        zb.sum_to(ctx, G, (5, 6, 7, 3))
+    e = torch.empty((4, 0, 3), dtype=G.dtype, device="cuda")
+    np.testing.assert_array_equal(host(zb.sum_axis(ctx, e, 1)), np.zeros((4, 3), dtype))      # empty axis -> zeros
+    # fill / copy / strided copies
+    x = torch.empty(100003, dtype=G.dtype, device="cuda")
+    assert float(zb.fill(ctx, x, 0.0).abs().max()) == 0.0 and float(zb.fill(ctx, x, 2.5).min()) == 2.5
+    np.testing.assert_array_equal(host(zb.copy(ctx, G)), g)
+    t4 = dev(rng.standard_normal((3, 4, 5, 6)).astype(dtype))
+    cases = [t4.permute(0, 2, 3, 1), t4.permute(3, 2, 1, 0), t4[:, ::2, 1:4, ::3], t4[1], t4.transpose(1, 2)[..., 2],
+             t4[:1, :1, :1, :].expand(3, 4, 5, 6)]                                      # transposes, stepped slices, a broadcast source
+    for v in cases:
+        out = torch.full(tuple(v.shape), -7.0, dtype=v.dtype, device="cuda")
+        zb.copy_strided(ctx, v, out)
+        np.testing.assert_array_equal(host(out), zo.copy_strided(host(v)))
+    big = torch.zeros((6, 10), dtype=G.dtype, device="cuda")
+    zb.copy_strided(ctx, t4[0, 0], big[1:, 2:8])                                        # strided DESTINATION (assign into a slice)
+    ref = np.zeros((6, 10), dtype)
+    ref[1:, 2:8] = host(t4[0, 0])
+    np.testing.assert_array_equal(host(big), ref)
+    ctx.check()

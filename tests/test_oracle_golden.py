@@ -185,3 +185,24 @@ def test_adamw_literal(lit):
                                                         a["eps"], step, a["weight_decay"], k.startswith("w"))
                                           for k in s], st)
     _check(st, a)
+
+
+def test_reductions_reference_literals():
+    """The reference's own literals for Matrix::sum / variance (zenu-matrix/src/operation/sum.rs:104-160 test_4d: arange(120) as
+    [2,3,4,5]; operation/var.rs:35-40: variance([1,2,3,4]) = 1.25) and sum_to's right-aligned semantics."""
+    src = np.arange(120, dtype=np.float32).reshape(2, 3, 4, 5)
+    s0 = zo.sum_axis(src, 0)
+    assert s0.shape == (3, 4, 5)
+    np.testing.assert_array_equal(s0.ravel(), np.arange(60, 179, 2, dtype=np.float32))           # sum.rs:124-133
+    s1 = zo.sum_axis(src, 1)
+    assert s1.shape == (2, 4, 5)
+    np.testing.assert_array_equal(s1.ravel()[:20], np.arange(60, 118, 3, dtype=np.float32))      # sum.rs:135-141
+    assert zo.sum_axis(src, 2).shape == (2, 3, 5) and zo.sum_axis(src, 3).shape == (2, 3, 4)
+    for axis in range(4):
+        np.testing.assert_array_equal(zo.sum_axis(src, axis), src.sum(axis))
+        np.testing.assert_array_equal(zo.sum_axis(src, axis, keep_dim=True), src.sum(axis, keepdims=True))
+    assert abs(float(zo.variance_axis(np.array([1.0, 2.0, 3.0, 4.0], np.float32), 0)) - 1.25) < 1e-6
+    np.testing.assert_array_equal(zo.sum_to(src, (4, 5)), src.sum((0, 1)))
+    np.testing.assert_array_equal(zo.sum_to(src, (2, 1, 4, 1)), src.sum((1, 3), keepdims=True))
+    np.testing.assert_array_equal(zo.sum_to(src, (2, 3, 4, 5)), src)
+    np.testing.assert_allclose(zo.mean_axis(src, 1), src.mean(1), rtol=1e-6)

@@ -393,6 +393,86 @@ def sum_rows(ctx, a):
     return out
 
 
+def _axis_view(shape, axis):
+    outer = 1
+    for v in shape[:axis]:
+        outer *= v
+    inner = 1
+    for v in shape[axis + 1:]:
+        inner *= v
+    return outer, shape[axis], inner
+
+
+def _reduced_shape(shape, axis, keep_dim):
+    return tuple(shape[:axis]) + ((1,) if keep_dim else ()) + tuple(shape[axis + 1:])
+
+
+def sum_axis(ctx, a, axis, keep_dim=False):
+    """Matrix::sum(axis, keep_dim) (zenu-matrix/src/operation/sum.rs:9-31)."""
+    _chk(a, "sum input")
+    outer, n, inner = _axis_view(tuple(a.shape), axis)
+    out = torch.empty(_reduced_shape(tuple(a.shape), axis, keep_dim), dtype=a.dtype, device=a.device)
+    check(ctx.lib.zb_sum_axis(ctx.handle, _DT[a.dtype], _p(a), _p(out), outer, n, inner))
+    return out
+
+
+def mean_axis(ctx, a, axis, keep_dim=False):
+    """Matrix::mean(Some(axis), keep_dim) (operation/mean.rs:8-20)."""
+    _chk(a, "mean input")
+    outer, n, inner = _axis_view(tuple(a.shape), axis)
+    out = torch.empty(_reduced_shape(tuple(a.shape), axis, keep_dim), dtype=a.dtype, device=a.device)
+    check(ctx.lib.zb_mean_axis(ctx.handle, _DT[a.dtype], _p(a), _p(out), outer, n, inner))
+    return out
+
+
+def variance_axis(ctx, a, axis, keep_dim=False, want_mean=False):
+    """Matrix::variance(Some(axis), keep_dim) (operation/var.rs:18-26): biased."""
+    _chk(a, "variance input")
+    outer, n, inner = _axis_view(tuple(a.shape), axis)
+    shp = _reduced_shape(tuple(a.shape), axis, keep_dim)
+    out = torch.empty(shp, dtype=a.dtype, device=a.device)
+    mean = torch.empty(shp, dtype=a.dtype, device=a.device) if want_mean else None
+    check(ctx.lib.zb_variance_axis(ctx.handle, _DT[a.dtype], _p(a), _p(out), _p(mean), outer, n, inner))
+    return (out, mean) if want_mean else out
+
+
+def sum_to(ctx, a, shape):
+    """sum_to(source, target) (operation/sum.rs:35-92): reduce `a` to a shape it broadcasts from (right-aligned)."""
+    _chk(a, "sum_to input")
+    shape = tuple(int(v) for v in shape)
+    out = torch.empty(shape, dtype=a.dtype, device=a.device)
+    ss = (ctypes.c_int64 * max(a.dim(), 1))(*a.shape)
+    ds = (ctypes.c_int64 * max(len(shape), 1))(*shape)
+    check(ctx.lib.zb_sum_to(ctx.handle, _DT[a.dtype], _p(a), ss, a.dim(), _p(out), ds, len(shape)))
+    return out
+
+
+def fill(ctx, x, value):
+    """DeviceBase::zeros and friends: x[:] = value (the reference zero-fills by scaling with 0, NaN-unsafe)."""
+    _chk(x, "fill target")
+    check(ctx.lib.zb_fill(ctx.handle, _DT[x.dtype], _p(x), float(value), x.numel()))
+    return x
+
+
+def copy(ctx, src, dst=None):
+    _chk(src, "copy source")
+    dst = torch.empty_like(src) if dst is None else dst
+    check(ctx.lib.zb_copy(ctx.handle, _DT[src.dtype], _p(src), _p(dst), src.numel()))
+    return dst
+
+
+def copy_strided(ctx, src, dst):
+    """copy_from for arbitrarily strided views (CopyBlas::copy_raw, operation/copy_from.rs:9-55): src and dst are torch views of the
+    same shape with any non-negative element strides (transposes, slices with steps, broadcast sources)."""
+    if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype or src.dtype not in _DT:
+        raise ZenuB200Error("copy_strided: shape / dtype mismatch")
+    nd = src.dim()
+    mk = lambda v: (ctypes.c_int64 * max(nd, 1))(*v)  # noqa: E731
+    check(ctx.lib.zb_copy_strided(ctx.handle, _DT[src.dtype], ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), nd,
+                                  mk(src.shape), mk(src.stride()), mk(dst.stride())))
+    return dst
+
+
 def to_nhwc(ctx, x):
     n, c, h, w = x.shape
     y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
