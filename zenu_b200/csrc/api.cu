@@ -233,6 +233,16 @@ static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   float* yf = static_cast<float*>(y);
   if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
     return tc_smallc_fprop(ctx, m, d, xf, 0, wf, bf, yf, bs);
+  if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv_smallc_supported(d)) {
+    // reference contract with C <= 4 (a network's first layer): the sliding-window kernels read the NCHW batch as it is; only the
+    // (tiny) filter and the output are staged
+    Temp tw(ctx), ty(ctx);
+    if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
+    if ((rc = ty.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
+    if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
+    if ((rc = tc_smallc_fprop(ctx, m, d, xf, 1, static_cast<float*>(tw.p), bf, static_cast<float*>(ty.p))) != ZB_OK) return rc;
+    return transpose_batched<float>(ctx, static_cast<float*>(ty.p), yf, d->n, P * Q, d->k);
+  }
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_fprop<float>(ctx, layout, d, xf, wf, bf, yf);
   if (layout == ZB_NHWC) return tc_fprop_nhwc(ctx, m, d, xf, wf, bf, yf, bs);
   // NCHW contract: stage through NHWC / KRSC
@@ -293,7 +303,7 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   const float* gf = static_cast<const float*>(dy);
   const float* wf = static_cast<const float*>(w);
   float* df = static_cast<float*>(dx);
-  const bool tc_ok = (d->k % 32 == 0) && d->kh * d->kw <= 64 && (layout == ZB_NHWC || d->c % 4 == 0);
+  const bool tc_ok = (d->k % 32 == 0) && d->kh * d->kw <= 64 && (layout == ZB_NHWC || d->c % 4 == 0 || umma_conv_smallc_dgrad_supported(d));
   if (beta != 0.f && !(layout == ZB_NHWC && m != ZB_MATH_FP32 && tc_ok)) {
     set_last_error("dgrad accumulate: not available on this path");
     return ZB_ERR_UNSUPPORTED;
@@ -311,7 +321,8 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   if ((rc = td.alloc(sizeof(float) * d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
   if ((rc = transpose_batched<float>(ctx, wf, static_cast<float*>(tw.p), d->k, d->c, d->kh * d->kw)) != ZB_OK) return rc;
-  rc = tc_dgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p), 0.f, false);
+  rc = tc_dgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), static_cast<float*>(tw.p), static_cast<float*>(td.p), 0.f,
+                     umma_conv_smallc_dgrad_supported(d));
   if (rc == ZB_ERR_UNSUPPORTED) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
   if (rc != ZB_OK) return rc;
   return transpose_batched<float>(ctx, static_cast<float*>(td.p), df, d->n, d->h * d->w, d->c);
@@ -340,6 +351,14 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* xf = static_cast<const float*>(x);
   float* wf = static_cast<float*>(dw);
   if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d)) return tc_wgrad_nhwc(ctx, m, d, P, Q, gf, xf, 0, wf, true);
+  if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv_smallc_supported(d)) {   // x stays NCHW; dy and the (tiny) dw are staged
+    Temp tg(ctx), tw(ctx);
+    if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
+    if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
+    if ((rc = transpose_batched<float>(ctx, gf, static_cast<float*>(tg.p), d->n, d->k, P * Q)) != ZB_OK) return rc;
+    if ((rc = tc_wgrad_nhwc(ctx, m, d, P, Q, static_cast<float*>(tg.p), xf, 1, static_cast<float*>(tw.p), true)) != ZB_OK) return rc;
+    return transpose_batched<float>(ctx, static_cast<float*>(tw.p), wf, d->k, d->kh * d->kw, d->c);  // KRSC -> KCRS
+  }
   if (m == ZB_MATH_FP32 || !umma_conv_supported(d)) return simt_conv_wgrad<float>(ctx, layout, d, gf, xf, wf);
   if (layout == ZB_NHWC) return tc_wgrad_nhwc(ctx, m, d, P, Q, gf, xf, 0, wf, false);
   Temp tg(ctx), tx(ctx), tw(ctx);
