@@ -892,3 +892,32 @@ def test_reductions_and_strided_copy_vs_oracle(zb, ctx, dtype):
     ref[1:, 2:8] = host(t4[0, 0])
     np.testing.assert_array_equal(host(big), ref)
     ctx.check()
+
+
+@pytest.mark.parametrize("case", [(2, 64, 8, 8, 128), (3, 96, 6, 10, 40), (2, 256, 14, 14, 64), (5, 32, 4, 8, 300), (2, 128, 28, 28, 512)])
+@pytest.mark.parametrize("math", ["tf32", "tf32x3"])
+def test_nchw_pointwise_conv_without_staging(zb, ctx, case, math):
+    """The reference contract (NCHW / KCRS, zenu-matrix/src/nn/conv/interface.rs:270-281) for 1x1 / stride-1 convs is served by
+    batched per-image GEMMs straight on the NCHW tensors (UmmaParams::batch_mode): no NHWC staging copies.  Ragged output-channel
+    tiles (rows of the NEXT image land in masked accumulator rows), ragged pixel tiles, bias, all three passes, vs the oracle; the
+    plan description must show the batched launch and no transpose."""
+    from zenu_b200 import ZB_NCHW
+    n, c, h, w, k = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, 1, 1)) * np.sqrt(2.0 / c)).astype(np.float32)
+    b = rng.standard_normal(k).astype(np.float32)
+    y_ref = zo.conv2d_bias_add(zo.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), 0, 1, 1), b.astype(np.float64))
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    m = math_of(zb, math)
+    for op in (zb.PLAN_FPROP, zb.PLAN_DGRAD, zb.PLAN_WGRAD):
+        plan = zb.conv_plan_describe(ctx, op, x.shape, wt.shape, layout=ZB_NCHW, math=m)
+        assert "batch_mode=" + ("2" if op == zb.PLAN_WGRAD else "1") in plan and "transpose" not in plan, plan
+    X, W, DY = dev(x), dev(wt), dev(dy)
+    tol = TOL[math]
+    assert rel_err(host(zb.conv_fwd(ctx, X, W, 0, 1, 1, bias=dev(b), layout=ZB_NCHW, math=m)), y_ref) < tol
+    dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, 0, 1, 1, layout=ZB_NCHW, math=m)
+    assert rel_err(host(dx), zo.conv2d_bkwd_data(dy.astype(np.float64), wt.astype(np.float64), x.shape, 0, 1, 1)) < tol
+    dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, 0, 1, 1, layout=ZB_NCHW, math=m)
+    assert rel_err(host(dw), zo.conv2d_bkwd_filter(dy.astype(np.float64), x.astype(np.float64), wt.shape, 0, 1, 1)) < tol
+    ctx.check()

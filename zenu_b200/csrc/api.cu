@@ -16,6 +16,10 @@ bool umma_conv_supported(const zb_conv2d_desc*);
 int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*, float, const float*, float*, int*);
 int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
+bool umma_conv1x1_nchw_supported(const zb_conv2d_desc*, int pass);
+int umma_conv1x1_nchw_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
+int umma_conv1x1_nchw_dgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
+int umma_conv1x1_nchw_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 bool umma_conv_smallc_supported(const zb_conv2d_desc*);
 int umma_conv_smallc_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, int, const float*, const float*, float*, float, const float*, float*, int*);
 int umma_conv_smallc_wgrad(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, int, float*, float);
@@ -233,6 +237,16 @@ static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   float* yf = static_cast<float*>(y);
   if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d))  // C <= 4 (network stems): sliding-window path
     return tc_smallc_fprop(ctx, m, d, xf, 0, wf, bf, yf, bs);
+  if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv1x1_nchw_supported(d, 0)) {
+    // reference contract, pointwise conv: batched per-image GEMMs straight on the NCHW tensors (no layout staging)
+    if (m == ZB_MATH_TF32X3)
+      rc = run_tf32x3(ctx, xf, d->n * d->c * d->h * d->w, wf, d->k * d->c, 0.f,
+                      [&](const float* xp, const float* wp, float bt, bool) { return umma_conv1x1_nchw_fprop(ctx, d, xp, wp, yf, bt); });
+    else
+      rc = umma_conv1x1_nchw_fprop(ctx, d, xf, wf, yf, 0.f);
+    if (rc != ZB_OK || bf == nullptr) return rc;
+    return bias_add_nchw<float>(ctx, yf, bf, yf, d->n, d->k, P * Q);
+  }
   if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv_smallc_supported(d)) {
     // reference contract with C <= 4 (a network's first layer): the sliding-window kernels read the NCHW batch as it is; only the
     // (tiny) filter and the output are staged
@@ -315,6 +329,12 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
     if (rc == ZB_ERR_UNSUPPORTED && beta == 0.f) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
     return rc;
   }
+  if (umma_conv1x1_nchw_supported(d, 1)) {   // pointwise conv on the reference's NCHW tensors: no layout staging
+    if (m == ZB_MATH_TF32X3)
+      return run_tf32x3(ctx, gf, d->n * d->k * P * Q, wf, d->k * d->c, 0.f,
+                        [&](const float* gp, const float* wp, float bt, bool) { return umma_conv1x1_nchw_dgrad(ctx, d, gp, wp, df, bt); });
+    return umma_conv1x1_nchw_dgrad(ctx, d, gf, wf, df, 0.f);
+  }
   Temp tg(ctx), tw(ctx), td(ctx);
   if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;
   if ((rc = tw.alloc(sizeof(float) * d->k * d->c * d->kh * d->kw)) != ZB_OK) return rc;
@@ -351,6 +371,12 @@ int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
   const float* xf = static_cast<const float*>(x);
   float* wf = static_cast<float*>(dw);
   if (m != ZB_MATH_FP32 && layout == ZB_NHWC && umma_conv_smallc_supported(d)) return tc_wgrad_nhwc(ctx, m, d, P, Q, gf, xf, 0, wf, true);
+  if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv1x1_nchw_supported(d, 2)) {   // pointwise conv, NCHW tensors as they are
+    if (m == ZB_MATH_TF32X3)
+      return run_tf32x3(ctx, gf, d->n * d->k * P * Q, xf, d->n * d->c * d->h * d->w, 0.f,
+                        [&](const float* gp, const float* xp, float bt, bool) { return umma_conv1x1_nchw_wgrad(ctx, d, gp, xp, wf, bt); });
+    return umma_conv1x1_nchw_wgrad(ctx, d, gf, xf, wf, 0.f);
+  }
   if (m != ZB_MATH_FP32 && layout == ZB_NCHW && umma_conv_smallc_supported(d)) {   // x stays NCHW; dy and the (tiny) dw are staged
     Temp tg(ctx), tw(ctx);
     if ((rc = tg.alloc(sizeof(float) * d->n * d->k * P * Q)) != ZB_OK) return rc;

@@ -82,6 +82,9 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
     const int h = tc.m_blk % p.dg_H;
     kb_begin = 0;
     kb_end = p.dg_cnt[(h + p.dg_ph) % p.dg_sh] * p.c_chunks;
+  } else if (p.batch_mode == 1) {   // the split index is an image: every tile reduces over the whole K range
+    kb_begin = 0;
+    kb_end = p.kb_total;
   } else {
     kb_begin = tc.split * p.kb_per_split;
     kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
@@ -115,7 +118,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.tap_col_stride & 3) == 0) && ((p.split_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-    const bool partial = p.splits > 1;
+    const bool partial = p.splits > 1 && p.batch_mode != 1;
     const int sub_row = lane >> 3, piece = lane & 7;
     float* stat_w = reinterpret_cast<float*>(smem + Lv.EPI_OFFSET + 4 * 4096) + ew * 3 * BN;   // this warp's [3][BN]: sum, sum sq, shift
     const bool stats = p.stat_partial != nullptr;
@@ -527,8 +530,11 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sB = sA + L::A_BYTES;
           const uint32_t fullp = full0 + stage * 8;
           // ---- A operand
+          // batched modes (see UmmaParams::batch_mode): image of this K block / tile and the K block inside the image
+          const int bimg = p.batch_mode == 2 ? kb / p.kb_per_batch : (p.batch_mode == 1 ? tc.split : 0);
+          const int bkb = p.batch_mode == 2 ? kb - bimg * p.kb_per_batch : kb;
           if (p.a_mode == A_TILED_K) {
-            if (CL == 1) tma_load_2d(sA, &tmA, &full_bar[stage], kb * kUmmaBK, m0);
+            if (CL == 1) tma_load_2d(sA, &tmA, &full_bar[stage], bkb * kUmmaBK, m0 + bimg * p.a_batch_rows);
             else tma_load_2d_pair(sA, &tmA, fullp, kb * kUmmaBK, m0);
           } else if (p.a_mode == A_IM2COL_K) {
             const int tap = kb / p.c_chunks, c0 = (kb - tap * p.c_chunks) * kUmmaBK;
@@ -563,12 +569,13 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               k0 = p.dg_r[(a_h + p.dg_ph) % p.dg_sh][i] * p.b_tap_stride + (kb - i * p.c_chunks) * kUmmaBK;
             }
             if (CL == 1)
-              tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+              tma_load_2d(sB, &tmB, &full_bar[stage], p.batch_mode == 2 ? bkb * kUmmaBK : k0, n0 + (p.batch_mode == 2 ? bimg * p.b_batch_rows : 0));
             else   // this CTA's half of the tile rows (the map's box is BN / 2 rows)
               tma_load_2d_pair(sB, &tmB, fullp, k0, nB0);
           } else if (p.b_mode == B_TILED_MN) {
             if (CL == 1) {
-              for (int j = 0; j < b_boxes; ++j) tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK);
+              for (int j = 0; j < b_boxes; ++j)
+                tma_load_2d(sB + j * 4096, &tmB, &full_bar[stage], n0 + 32 * j, kb * kUmmaBK + (p.batch_mode == 1 ? bimg * p.b_batch_rows : 0));
             } else {
               for (int j = 0; j < b_boxes; ++j) tma_load_2d_pair(sB + j * 4096, &tmB, fullp, nB0 + 32 * j, kb * kUmmaBK);
             }
@@ -1168,7 +1175,7 @@ static int pair_cl(const UmmaParams& p, int bn) {
     const char* e = getenv("ZENU_B200_PAIR");
     mode = e ? atoi(e) : 1;
   }
-  if (mode == 0 || bn < 128) return 1;
+  if (mode == 0 || bn < 128 || p.batch_mode != 0) return 1;
   if (mode == 1 && (bn < 256 || p.kb_per_split < 8)) return 1;
   if (p.m_tiles < 2 || (p.m_tiles & 1)) return 1;
   if (p.a_mode != A_TILED_K && p.a_mode != A_IM2COL_K && p.a_mode != A_TILED_MN) return 1;
@@ -1200,10 +1207,11 @@ static void stat_attach(zb_ctx* ctx, UmmaParams& p, const StatRequest* st, int t
 // plan-trace segment of one umma_kernel launch ('~' = value depends on the batch size, not on the kernel variant)
 static void note_umma(const UmmaParams& p, int bn, int stages, bool old, int cl, int grid) {
   if (tl_plan == nullptr) return;
-  plan_note("umma<bn=%d,stages=%d,old=%d,cl=%d> a_mode=%d b_mode=%d out_mode=%d n_tiles=%d tap_tiles=%d ntaps=%d splitk=%d beta=%d bias=%d stats=%d chain=%d "
+  plan_note("umma<bn=%d,stages=%d,old=%d,cl=%d> a_mode=%d b_mode=%d out_mode=%d n_tiles=%d tap_tiles=%d ntaps=%d splitk=%d beta=%d bias=%d stats=%d chain=%d batch_mode=%d "
             "~m_tiles=%d ~splits=%d ~kb_per_split=%d ~grid=%d;",
-            bn, stages, old ? 1 : 0, cl, p.a_mode, p.b_mode, p.out_mode, p.n_tiles, p.tap_tiles, p.ntaps, p.splits > 1 ? 1 : 0, p.beta != 0.f ? 1 : 0,
-            p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.chain_kb, p.m_tiles, p.splits, p.kb_per_split, grid);
+            bn, stages, old ? 1 : 0, cl, p.a_mode, p.b_mode, p.out_mode, p.n_tiles, p.tap_tiles, p.ntaps, (p.splits > 1 && p.batch_mode != 1) ? 1 : 0,
+            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.chain_kb, p.batch_mode, p.m_tiles, p.splits,
+            p.kb_per_split, grid);
 }
 
 template <int BN, int STAGES, bool OLD = false>
@@ -1407,6 +1415,85 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
   p.prof_flops = 2.0 * m * n * k;
   finish_split_fields(p, pick_splits(ctx, static_cast<long long>(p.m_tiles) * p.n_tiles, p.kb_total, 8));
   return run_with_splits(ctx, bn, ma, mb, p, m, n, c, ldc, alpha, beta, bias);
+}
+
+// ---------------------------------------------------------------------------------------------- NCHW pointwise convolutions
+// The reference contract (NCHW activations, KCRS filters; zenu-matrix/src/nn/conv/interface.rs:270-281) served WITHOUT layout staging
+// for 1x1 / stride-1 / unpadded convolutions: in NCHW the pixel dimension is the contiguous one, so per image
+//   fprop  Y_n[K][HW]  = W[K][C]    * X_n[C][HW]      A = W, K-major;        B = X_n, N-contiguous (MN-major)
+//   dgrad  dX_n[C][HW] = W^T[C][K]  * dY_n[K][HW]     A = W read M-contiguous; B = dY_n, MN-major
+//   wgrad  dW[K][C]    = sum_n dY_n[K][HW] * X_n[C][HW]^T   both operands K-major, the reduction runs over (image, pixel)
+// and [batch][rows][HW] tensors are plain 2-D matrices [batch * rows][HW] whose tensor-map row coordinate carries the image index
+// (UmmaParams::batch_mode).  One launch for the whole batch; outputs land in NCHW as they are.  Needs HW % 4 == 0 (16-byte TMA row
+// pitch) and a reduction length that is a whole number of 32-wide K blocks where K blocks would otherwise run into the next image.
+bool umma_conv1x1_nchw_supported(const zb_conv2d_desc* d, int pass) {
+  if (d->kh != 1 || d->kw != 1 || d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 0 || d->pad_w != 0) return false;
+  const long long HW = d->h * d->w;
+  if (HW % 4 != 0 || HW < 32 || d->n > 65535 || ZB_ENV_FLAG("ZENU_B200_NO_NCHW_DIRECT")) return false;
+  if (pass == 0) return d->c % 32 == 0;            // fprop: K blocks walk the input channels of ONE image
+  if (pass == 1) return d->k % 32 == 0;            // dgrad: K blocks walk the output channels
+  return true;                                     // wgrad: K blocks walk pixels; columns past HW are TMA zero fill
+}
+
+int umma_conv1x1_nchw_fprop(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, const float* w, float* y, float beta) {
+  const long long HW = d->h * d->w, C = d->c, K = d->k, N = d->n;
+  const int bn = pick_bn(HW);
+  CUtensorMap ma, mb;
+  UmmaParams p;
+  init_params(p, ctx);
+  int rc = make_map_2d(ctx, &ma, w, C, K, C, 32, kUmmaBM);
+  if (rc != ZB_OK) return rc;
+  if ((rc = make_map_2d(ctx, &mb, x, HW, N * C, HW, 32, kUmmaBK, true)) != ZB_OK) return rc;
+  p.a_mode = A_TILED_K; p.b_mode = B_TILED_MN; p.out_mode = OUT_ROWS;
+  p.M = static_cast<int>(K); p.N = static_cast<int>(HW);
+  p.m_tiles = ceil_div(K, kUmmaBM); p.n_tiles = ceil_div(HW, bn);
+  p.kb_total = static_cast<int>(C / kUmmaBK); p.kb_per_split = p.kb_total;
+  p.batch_mode = 1; p.splits = static_cast<int>(N); p.b_batch_rows = static_cast<int>(C);
+  p.split_stride = K * HW;
+  p.D = y; p.ldd = HW; p.alpha = 1.f; p.beta = beta;
+  p.prof_flops = 2.0 * N * HW * K * C;
+  return umma_launch(ctx, bn, ma, mb, p);
+}
+
+int umma_conv1x1_nchw_dgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
+  const long long HW = d->h * d->w, C = d->c, K = d->k, N = d->n;
+  const int bn = pick_bn(HW);
+  CUtensorMap ma, mb;
+  UmmaParams p;
+  init_params(p, ctx);
+  int rc = make_map_2d(ctx, &ma, w, C, K, C, 32, kUmmaBK, true);   // A[m = c][k] = W[k][c]: stored with M contiguous
+  if (rc != ZB_OK) return rc;
+  if ((rc = make_map_2d(ctx, &mb, dy, HW, N * K, HW, 32, kUmmaBK, true)) != ZB_OK) return rc;
+  p.a_mode = A_TILED_MN; p.b_mode = B_TILED_MN; p.out_mode = OUT_ROWS;
+  p.M = static_cast<int>(C); p.N = static_cast<int>(HW);
+  p.m_tiles = ceil_div(C, kUmmaBM); p.n_tiles = ceil_div(HW, bn);
+  p.kb_total = static_cast<int>(K / kUmmaBK); p.kb_per_split = p.kb_total;
+  p.batch_mode = 1; p.splits = static_cast<int>(N); p.b_batch_rows = static_cast<int>(K);
+  p.split_stride = C * HW;
+  p.D = dx; p.ldd = HW; p.alpha = 1.f; p.beta = beta;
+  p.prof_flops = 2.0 * N * HW * K * C;
+  return umma_launch(ctx, bn, ma, mb, p);
+}
+
+int umma_conv1x1_nchw_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* x, float* dw, float beta) {
+  const long long HW = d->h * d->w, C = d->c, K = d->k, N = d->n;
+  const int bn = pick_bn(C);
+  CUtensorMap ma, mb;
+  UmmaParams p;
+  init_params(p, ctx);
+  int rc = make_map_2d(ctx, &ma, dy, HW, N * K, HW, 32, kUmmaBM);
+  if (rc != ZB_OK) return rc;
+  if ((rc = make_map_2d(ctx, &mb, x, HW, N * C, HW, 32, bn)) != ZB_OK) return rc;
+  p.a_mode = A_TILED_K; p.b_mode = B_TILED_K; p.out_mode = OUT_ROWS;
+  p.M = static_cast<int>(K); p.N = static_cast<int>(C);
+  p.m_tiles = ceil_div(K, kUmmaBM); p.n_tiles = ceil_div(C, bn);
+  p.batch_mode = 2; p.kb_per_batch = ceil_div(HW, kUmmaBK); p.a_batch_rows = static_cast<int>(K); p.b_batch_rows = static_cast<int>(C);
+  if (N * p.kb_per_batch > 0x3fffffffll) { set_last_error("umma NCHW wgrad: reduction too long"); return ZB_ERR_UNSUPPORTED; }
+  p.kb_total = static_cast<int>(N * p.kb_per_batch);
+  p.D = dw; p.ldd = C;
+  p.prof_flops = 2.0 * N * HW * K * C;
+  finish_split_fields(p, pick_splits(ctx, static_cast<long long>(p.m_tiles) * p.n_tiles, p.kb_total, 16));
+  return run_with_splits(ctx, bn, ma, mb, p, K, C, dw, C, 1.f, beta, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------- halo conv planner

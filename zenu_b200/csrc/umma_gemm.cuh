@@ -73,6 +73,13 @@ struct UmmaParams {
   // a CTA only ever sees one column block) and written once to stat_partial[(blockIdx.x / n_tiles) * 4 + warp][2][N]
   float* stat_partial;
   const float* stat_shift;
+  // Batched GEMM over images (the NCHW pointwise convolutions served without layout staging): the operands are 2-D views
+  // [batch * rows][cols] of contiguous [batch][rows][cols] tensors, so a batch index is just an offset on a tensor map's row coordinate.
+  //   batch_mode 1: the split index of a tile IS the image (full K range per tile, B rows + split * b_batch_rows, output offset
+  //                 split * split_stride, epilogue applies alpha / beta / bias as for an unsplit launch)
+  //   batch_mode 2: the reduction runs over (image, K block): K block kb -> image kb / kb_per_batch, A / B row coordinates shifted by
+  //                 image * a_batch_rows / b_batch_rows (wgrad: both operands K-major); split-K slices that combined range
+  int batch_mode, a_batch_rows, b_batch_rows, kb_per_batch;
   // host only: the K-major B matrix as given to make_map_2d, so that the launcher can re-encode its tensor map with a half-height box
   // when it runs the launch on CTA pairs (umma_kernel CL = 2)
   const float* hb_base;
