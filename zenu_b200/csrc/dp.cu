@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -18,6 +19,7 @@ struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
@@ -41,6 +43,7 @@ static int load_nccl() {
   }
   g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
   g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.CommInitRankConfig = reinterpret_cast<decltype(g_nccl.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
@@ -112,6 +115,29 @@ int zb_dp_plan_buckets(const int64_t* numel, const int* kind, int n, int64_t buc
     bucket_out[i] = nb;
     acc += numel[i];
   }
+  // The bucket that completes LAST (the front of the network: its final gradient is the stem's wgrad, the last kernel of backward)
+  // has nothing left to overlap with except the optimizer: keep its exposed allreduce latency-sized by cutting a small tail bucket
+  // (<= 1/16 of bucket_bytes, at most 2 MB) off its front.  The bulk of the old last bucket then starts its exchange earlier.
+  {
+    const int64_t tail_cap = std::min<int64_t>(bucket_bytes / 16, 2ll << 20);
+    int64_t last_bytes = 0, tail_bytes = 0;
+    for (int i = 0; i < n; ++i)
+      if (bucket_out[i] == nb) last_bytes += numel[i] * elem_size;
+    if (last_bytes > 2 * tail_cap) {
+      int cut = -1;
+      for (int i = 0; i < n; ++i) {
+        if (bucket_out[i] != nb) continue;
+        if (tail_bytes + numel[i] * elem_size > tail_cap && tail_bytes > 0) break;
+        tail_bytes += numel[i] * elem_size;
+        cut = i;
+      }
+      if (cut >= 0 && tail_bytes < last_bytes) {
+        for (int i = 0; i <= cut; ++i)
+          if (bucket_out[i] == nb) bucket_out[i] = nb + 1;
+        ++nb;
+      }
+    }
+  }
   const int buckets = nb + 1;
   int64_t total = 0, buf_total = 0;
   for (int b = 0; b < buckets; ++b)
@@ -154,7 +180,18 @@ int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world) {
   memcpy(&id, host_id128, sizeof(id));
   ncclComm_t comm;
   ZB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  ZB_CHECK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+  // The compute kernels are persistent grids of one CTA per SM: every SM a collective occupies delays a whole CTA's worth of tiles of
+  // whatever tensor kernel runs beside it, while a 25 MB bucket over NVLink / NVSwitch (NVLS) needs only a few CTAs.  Cap NCCL's CTA
+  // count (ZENU_B200_NCCL_MAX_CTAS, default 4; 0 = NCCL's own default).
+  static const int max_ctas = []() { const char* e = getenv("ZENU_B200_NCCL_MAX_CTAS"); return e ? atoi(e) : 4; }();
+  if (g_nccl.CommInitRankConfig != nullptr && max_ctas > 0) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.maxCTAs = max_ctas;
+    cfg.minCTAs = 1;
+    ZB_CHECK_NCCL(g_nccl.CommInitRankConfig(&comm, world, id, rank, &cfg));
+  } else {
+    ZB_CHECK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+  }
   ctx->nccl_comm = comm;
   return ZB_OK;
 }
