@@ -929,3 +929,22 @@ def test_nchw_pointwise_conv_without_staging(zb, ctx, case, math):
     dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, 0, 1, 1, layout=ZB_NCHW, math=m)
     assert rel_err(host(dw), zo.conv2d_bkwd_filter(dy.astype(np.float64), x.astype(np.float64), wt.shape, 0, 1, 1)) < tol
     ctx.check()
+
+
+@pytest.mark.parametrize("dtype,math", [(np.float32, "fp32"), (np.float64, "fp32"), (np.float32, "tf32"), (np.float32, "tf32x3")])
+def test_wgrad_is_run_to_run_deterministic(zb, ctx, dtype, math):
+    """Every wgrad path reduces its split-K partials in a fixed order (the FFMA / DFMA kernels used atomicAdd in round 1): the same
+    call twice gives the same bits, for the SIMT kernels (ZB_MATH_FP32, all of f64) and the tensor-core kernels alike."""
+    from zenu_b200 import ZB_NHWC
+    rng = np.random.default_rng(41)
+    for (n, c, h, k, r, pad, stride) in ((16, 32, 20, 48, 3, 1, 1), (8, 3, 33, 16, 5, 2, 2), (4, 64, 14, 64, 1, 0, 1)):
+        x = rng.standard_normal((n, h, h, c)).astype(dtype)
+        p = (h + 2 * pad - r) // stride + 1
+        dy = rng.standard_normal((n, p, p, k)).astype(dtype)
+        X, DY = dev(x), dev(dy)
+        outs = [host(zb.conv_bkwd_weight(ctx, DY, X, (k, r, r, c), pad, stride, 1, layout=ZB_NHWC, math=math_of(zb, math))) for _ in range(3)]
+        np.testing.assert_array_equal(outs[0], outs[1])
+        np.testing.assert_array_equal(outs[0], outs[2])
+        ref = zo.conv2d_bkwd_filter(nchw(dy).astype(np.float64), nchw(x).astype(np.float64), (k, c, r, r), pad, stride, 1)
+        assert rel_err(nchw(outs[0]), ref) < (1e-10 if dtype == np.float64 else TOL[math])
+    ctx.check()

@@ -13,3 +13,8 @@ timeout 400 ncu --set full --clock-control none --import-source on --profile-fro
     -k regex:'bn_|col_reduce' -c 8 -f -o gpurun_out/prof_bn_${TAG} \
     python tools/ncu_step.py > gpurun_out/ncu_full_bn_${TAG}.log 2>&1
 ls -la gpurun_out | tail -12
+# the stem trio and the max-pool (the layers furthest below their HBM roofline: 3x224x224 -> 64x112x112 -> 64x56x56)
+timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'stem_fprop_kernel|stem_dgrad_kernel|stem_wgrad_kernel|maxpool_idx' -c 6 -f -o gpurun_out/prof_stem_${TAG} \
+    python tools/ncu_step.py > gpurun_out/ncu_full_stem_${TAG}.log 2>&1
+ls -la gpurun_out | grep ${TAG}

@@ -91,7 +91,7 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    for name in ("umma", "bn"):
+    for name in ("umma", "bn", "stem"):
         full(tag, name)
     sp = os.path.join(GP, "step_profile.tsv")
     if os.path.exists(sp):

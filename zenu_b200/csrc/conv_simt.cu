@@ -21,6 +21,7 @@ struct SimtConvParams {
   Strides4 xs, ws /* (k, c, r, s) */, ys;
   long long Mg, Ng, Kg;  // GEMM extents of this pass
   long long k_per_split;
+  long long split_stride;  // wgrad split-K: elements between the partial filter gradients of consecutive K slices
 };
 
 enum SimtMode { SIMT_FPROP = 0, SIMT_DGRAD = 1, SIMT_WGRAD = 2 };
@@ -156,14 +157,24 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(const SimtConvParams p, 
       const long long n = n0 + tx * 4 + j;
       if (n >= p.Ng) continue;
       const long long o = out_index<T, MODE>(p, m, n);
-      if (gridDim.z > 1) {
-        atomicAdd(out + o, acc[i][j]);
+      if (gridDim.z > 1) {   // split-K: this slice's partial; folded in a fixed order afterwards (no atomics: run-to-run deterministic)
+        out[static_cast<long long>(blockIdx.z) * p.split_stride + o] = acc[i][j];
       } else {
         T v = acc[i][j];
         if (MODE == SIMT_FPROP && bias != nullptr) v += bias[n];
         out[o] = v;
       }
     }
+  }
+}
+
+// dw[i] = sum over the K slices of partial[s][i], s ascending (fixed order)
+template <typename T>
+__global__ void simt_fold_kernel(const T* __restrict__ partial, T* __restrict__ out, long long n, int splits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    T acc = T(0);
+    for (int s = 0; s < splits; ++s) acc += partial[static_cast<long long>(s) * n + i];
+    out[i] = acc;
   }
 }
 
@@ -182,6 +193,7 @@ static Strides4 filt_strides(int layout, long long C, long long R, long long S) 
 
 static void fill_params(SimtConvParams& p, int layout, const zb_conv2d_desc* d) {
   p.N = d->n; p.C = d->c; p.H = d->h; p.W = d->w; p.K = d->k; p.R = d->kh; p.S = d->kw;
+  p.split_stride = 0;
   p.P = zb_conv_out_size(d->h, d->kh, d->pad_h, d->stride_h, d->dil_h);
   p.Q = zb_conv_out_size(d->w, d->kw, d->pad_w, d->stride_w, d->dil_w);
   p.pad_h = static_cast<int>(d->pad_h); p.pad_w = static_cast<int>(d->pad_w);
@@ -224,10 +236,22 @@ int simt_conv_wgrad(zb_ctx* ctx, int layout, const zb_conv2d_desc* d, const T* d
   splits = std::min<long long>(splits, 65535);
   p.k_per_split = ((p.Kg + splits - 1) / splits + SBK - 1) / SBK * SBK;
   splits = (p.Kg + p.k_per_split - 1) / p.k_per_split;
-  if (splits > 1 && !plan_dry()) ZB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(T) * p.K * p.C * p.R * p.S, ctx->stream));
   dim3 grid(ceil_div(p.Mg, SBM), ceil_div(p.Ng, SBN), static_cast<unsigned>(splits));
-  plan_note("simt_conv_wgrad<%s> layout=%d atomics=%d ~splits=%lld;", sizeof(T) == 8 ? "f64" : "f32", layout, splits > 1 ? 1 : 0, splits);
-  ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_WGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, x, static_cast<const T*>(nullptr), dw));
+  plan_note("simt_conv_wgrad<%s> layout=%d splitk=%d ~splits=%lld;", sizeof(T) == 8 ? "f64" : "f32", layout, splits > 1 ? 1 : 0, splits);
+  if (splits <= 1) {
+    ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_WGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, x, static_cast<const T*>(nullptr), dw));
+    return ZB_OK;
+  }
+  // split-K: one partial filter gradient per K slice in the scratch arena, then a fixed-order fold (round 1 used atomicAdd here, which
+  // made ZB_MATH_FP32 and every f64 wgrad run-to-run nondeterministic)
+  const long long total = static_cast<long long>(p.K) * p.C * p.R * p.S;
+  void* ws = nullptr;
+  const int rc = ctx_workspace(ctx, sizeof(T) * static_cast<size_t>(splits) * total, &ws);
+  if (rc != ZB_OK) return rc;
+  p.split_stride = total;
+  ZB_KLAUNCH(ctx, simt_conv_kernel<T, SIMT_WGRAD><<<grid, 256, 0, ctx->stream>>>(p, dy, x, static_cast<const T*>(nullptr), static_cast<T*>(ws)));
+  const int fgrid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
+  ZB_KLAUNCH(ctx, simt_fold_kernel<T><<<fgrid, 256, 0, ctx->stream>>>(static_cast<const T*>(ws), dw, total, static_cast<int>(splits)));
   return ZB_OK;
 }
 

@@ -56,16 +56,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef ZB_MBAR_TIMEOUT_CYCLES
 #define ZB_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
+// The timeout clock and the error word are looked at once every 256 failed polls only: the error word is a volatile GLOBAL load
+// (LDG.E.STRONG.SYS, several hundred cycles), and with one per poll -- as in round 1 -- a waiter noticed its barrier up to a load
+// latency late on every pipeline hand-off (ncu source view of stem_fprop_kernel, profiles/r2_ncu_full_stem.txt: 1.35 M such loads,
+// the compare behind them the second-hottest stall of the kernel).  mbarrier.try_wait itself suspends the thread in hardware until the
+// phase completes or a short system time limit passes, so re-polling immediately is the cheap part.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
   if (mbar_try_wait(bar, parity)) return true;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > ZB_MBAR_TIMEOUT_CYCLES || (err_flag && *err_flag)) {
+  const long long t0 = clock64();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spins & 255u) == 0u && (clock64() - t0 > ZB_MBAR_TIMEOUT_CYCLES || (err_flag && *err_flag))) {
       if (err_flag) *err_flag = 1;
       return false;
     }
   }
-  return true;
 }
 
 // ---------------------------------------------------------------- TMA
@@ -134,7 +139,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 // wait on a barrier of this CTA that is arrived on from another CTA of the cluster, bounded
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* err_flag) {
   long long t0 = 0;
-  for (;;) {
+  for (uint32_t spins = 0;; ++spins) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
@@ -145,7 +150,7 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "memory");
     if (ok) return true;
     if (t0 == 0) t0 = clock64();
-    if (clock64() - t0 > ZB_MBAR_TIMEOUT_CYCLES || (err_flag && *err_flag)) {
+    if ((spins & 255u) == 255u && (clock64() - t0 > ZB_MBAR_TIMEOUT_CYCLES || (err_flag && *err_flag))) {   // (see mbar_wait)
       if (err_flag) *err_flag = 1;
       return false;
     }
