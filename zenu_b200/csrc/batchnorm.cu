@@ -115,6 +115,8 @@ struct SumF {  // plain column sum
     for (int e = 0; e < VN; ++e) acc[0][e] += a[e];
   }
 };
+// MASK 5 = as 4 without writing the masked gradient: the residual branch takes (dy, bits) as it is (a "lazy" masked gradient that
+// its consumer -- a dgrad epilogue or the shortcut's BatchNorm backward -- masks on the fly): 5 + 2/32 tensor passes instead of 6 + 1/32
 // MASK: 0 = plain BN backward, 1 = ReLU mask from the saved output y (third stream), 2 = ReLU mask recomputed from x
 // (fused BN+ReLU without residual: y > 0 <=> bn_affine(x) > 0, so y is never read), 3 = as 1, and the masked gradient
 // dy' is also written to gm_out (it IS the residual-branch gradient; the apply pass then reads it instead of dy and y:
@@ -139,13 +141,13 @@ struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
   __device__ void operator()(const T* x, const T* dy, const T* y, T (*acc)[VN], long long off) const {
     T gv[VN];
     unsigned nib = 0u;
-    if (MASK == 4) nib = __ldg(bits + (off >> 5)) >> (off & 31);   // VN consecutive bits (VN divides 32, off % VN == 0)
+    if (MASK == 4 || MASK == 5) nib = __ldg(bits + (off >> 5)) >> (off & 31);   // VN consecutive bits (VN divides 32, off % VN == 0)
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       bool keep = true;
       if (MASK == 1 || MASK == 3) keep = y[e] > T(0);
       if (MASK == 2) keep = bn_affine(x[e], m[e], iv[e], gm[e], bt[e]) > T(0);
-      if (MASK == 4) keep = ((nib >> e) & 1u) != 0u;
+      if (MASK == 4 || MASK == 5) keep = ((nib >> e) & 1u) != 0u;
       const T g = keep ? dy[e] : T(0);
       gv[e] = g;
       acc[0][e] += g;
@@ -449,7 +451,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
                                                          const T* __restrict__ inv, const T* __restrict__ coef,
                                                          const T* __restrict__ gamma, const T* __restrict__ beta,
                                                          long long rows, long long C, long long rows_per_slab, int tx_n,
-                                                         int ty_n) {
+                                                         int ty_n, const uint32_t* __restrict__ bits = nullptr) {
+  // MASK 4: the gradient is dy masked by a 1-bit-per-element array (bit index = NHWC element index)
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
   if (c0 >= C) return;
@@ -476,11 +479,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       T o[VN], gm[VN];
+      unsigned nib = 0u;
+      if (MASK == 4) { const long long off = (r + u * ty_n) * C + c0; nib = __ldg(bits + (off >> 5)) >> (off & 31); }
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         bool keep = true;
         if (MASK == 1) keep = yy[u][e] > T(0);
         if (MASK == 2) keep = bn_affine(a[u][e], m[e], iv[e], ga[e], be[e]) > T(0);
+        if (MASK == 4) keep = ((nib >> e) & 1u) != 0u;
         gm[e] = keep ? g[u][e] : T(0);
         o[e] = k0[e] * (gm[e] - k1[e] - ((a[u][e] - m[e]) * iv[e]) * k2[e]);
       }
@@ -495,11 +501,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
     ldv<T, VN>(x + off, a);
     ldv<T, VN>(dy + off, g);
     if (MASK == 1) ldv<T, VN>(y + off, yy);
+    unsigned nib = 0u;
+    if (MASK == 4) nib = __ldg(bits + (off >> 5)) >> (off & 31);
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
       bool keep = true;
       if (MASK == 1) keep = yy[e] > T(0);
       if (MASK == 2) keep = bn_affine(a[e], m[e], iv[e], ga[e], be[e]) > T(0);
+      if (MASK == 4) keep = ((nib >> e) & 1u) != 0u;
       gm[e] = keep ? g[e] : T(0);
       o[e] = k0[e] * (gm[e] - k1[e] - ((a[e] - m[e]) * iv[e]) * k2[e]);
     }
@@ -602,6 +611,7 @@ template <typename T, int VN> using BnBwdNoMaskFT = BnBwdF<T, VN, 0>;
 template <typename T, int VN> using BnBwdRecomputeFT = BnBwdF<T, VN, 2>;
 template <typename T, int VN> using BnBwdMaskStoreFT = BnBwdF<T, VN, 3>;
 template <typename T, int VN> using BnBwdBitsStoreFT = BnBwdF<T, VN, 4>;
+template <typename T, int VN> using BnBwdBitsFT = BnBwdF<T, VN, 5>;
 
 // Upper bound on the slab count run_col_reduce may pick (sizes the partial buffer).
 static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
@@ -698,15 +708,16 @@ static int bn_fwd_infer_t(zb_ctx* ctx, int layout, long long N, long long C, lon
 template <typename T, int MASK, bool DRES>
 static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* dy,
                             const T* y, T* dx, T* dres, const T* mean, const T* inv, const T* coef, const T* gamma,
-                            const T* beta) {
+                            const T* beta, const uint32_t* bits = nullptr) {
   const long long rows = N * HW;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
     const bool vec = (C % VN == 0) && al16(x) && al16(dy) && al16(y) && al16(dx) && al16(dres);
+    ZB_REQUIRE(MASK != 4 || (vec && sizeof(T) == 4 && bits != nullptr), "bn bwd: the bit-mask apply needs aligned f32 NHWC tensors");
     if (vec) {
       ColGeom g = col_geom(ctx, rows, C, VN);
       dim3 grid(g.col_groups, g.slabs);
-      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty, bits);
     } else {
       ColGeom g = col_geom(ctx, rows, C, 1);
       dim3 grid(g.col_groups, g.slabs);
@@ -755,6 +766,9 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   if (relu_bias != nullptr)
     rc = run_col_reduce<T, BnBwdRecomputeFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
                                              [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs);
+  else if (relu_mask != nullptr && dres == nullptr)   // the masked gradient is not materialised (see BnBwdF, MASK 5)
+    rc = run_col_reduce<T, BnBwdBitsFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
+                                        [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = nullptr; f.bits = relu_mask; }, &slabs);
   else if (relu_mask != nullptr)
     rc = run_col_reduce<T, BnBwdBitsStoreFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
                                              [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; f.bits = relu_mask; }, &slabs);
@@ -772,6 +786,8 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
                                                                dscale, dbias, coef);
   ZB_LAUNCH_CHECK(ctx);
   if (relu_bias != nullptr) rc = launch_bwd_apply<T, 2, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
+  else if (relu_mask != nullptr && dres == nullptr)
+    rc = launch_bwd_apply<T, 4, false>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), dx, static_cast<T*>(nullptr), mean, inv, coef, scale, relu_bias, relu_mask);
   else if ((y != nullptr || relu_mask != nullptr) && dres != nullptr)   // dres already holds the masked gradient (written by the reduce pass)
     rc = launch_bwd_apply<T, 0, false>(ctx, layout, N, C, HW, x, dres, static_cast<const T*>(nullptr), dx, static_cast<T*>(nullptr), mean, inv, coef, scale, relu_bias);
   else if (y != nullptr) rc = launch_bwd_apply<T, 1, false>(ctx, layout, N, C, HW, x, dy, y, dx, dres, mean, inv, coef, scale, relu_bias);
@@ -780,7 +796,7 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   // algorithmic bytes: x, dy read twice + dx written (+ y read twice for the ReLU mask, + dres written); the fused
   // BN+add+ReLU backward reads x twice, dy and y once, writes and re-reads the masked gradient, writes dx: 7 passes
   prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) *
-                             (relu_mask ? 6.0 + 1.0 / 32.0 : (y && dres) ? 7.0 : 5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
+                             (relu_mask ? (dres ? 6.0 + 1.0 / 32.0 : 5.0 + 2.0 / 32.0) : (y && dres) ? 7.0 : 5.0 + (y ? 2.0 : 0.0) + (dres ? 1.0 : 0.0)));
   return rc;
 }
 
@@ -861,8 +877,8 @@ int zb_bn2d_bwd_mask(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, i
                      const void* relu_mask, void* dres) {
   ZB_API_RANGE();
   ZB_REQUIRE(layout == ZB_NHWC && dtype == ZB_F32 && c % 32 == 0, "bn bwd (bit mask): NHWC f32 with C %% 32 == 0 only");
-  ZB_REQUIRE(relu_mask != nullptr && dres != nullptr && saved_mean != nullptr && saved_inv_std != nullptr,
-             "bn bwd (bit mask): mask, residual-gradient buffer and saved statistics are required");
+  ZB_REQUIRE(relu_mask != nullptr && saved_mean != nullptr && saved_inv_std != nullptr,
+             "bn bwd (bit mask): the mask and the saved statistics are required");
   ZB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dres) & 15) == 0,
              "bn bwd (bit mask): tensors must be 16-byte aligned");
