@@ -118,6 +118,14 @@ int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2
 /* dx += dgrad(dy, w): gradient fan-in (zenu-autograd/src/lib.rs:480-481 `grad + old`) folded into the dgrad epilogue */
 int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                         const void* w, void* dx);
+/* dx = dgrad(dy, w) + mask(dx): as zb_conv2d_dgrad_acc, with the OLD dx taken through a 1-bit-per-element mask (bit i = element i of
+ * dx in its layout counts, else it is 0).  The fused BN+add+ReLU backward (zb_bn2d_bwd_mask with dres == NULL) leaves the residual
+ * branch's gradient as the pair (dy, ReLU bits) instead of writing the masked tensor; the convolution whose dgrad accumulates into
+ * that branch applies the mask in its epilogue.  old_bits == NULL is zb_conv2d_dgrad_acc. */
+int zb_conv2d_dgrad_acc_masked(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
+                               const void* w, void* dx, const void* old_bits);
+/* out[i] = bit i of `bits` ? x[i] : 0 (materialises such a masked gradient for a consumer that cannot mask on the fly; out may be x) */
+int zb_mask_apply(zb_ctx* ctx, int dtype, const void* x, const void* bits, void* out, int64_t n);
 int zb_conv2d_wgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy,
                     const void* x, void* dw);
 /* ---- plan description (parity-test support: which kernel variant serves a shape) ------------------------------------------
@@ -162,7 +170,9 @@ int zb_bn2d_fwd_train_prestats(zb_ctx* ctx, int dtype, int layout, int64_t n, in
 /* Superset of the two forwards above (NHWC f32): stat_partial may be NULL (statistics computed here), relu_mask may be NULL.
  * relu_mask (relu != 0, c % 32 == 0): zb_bn2d_relu_mask_words(n,c,h,w) 32-bit words, bit i = (output element i > 0) in NHWC
  * order.  zb_bn2d_bwd_mask then takes the ReLU mask from it instead of re-reading the forward output: the fused
- * BN+add+ReLU backward moves 6 tensor passes instead of 7 (dres is required: it receives the masked gradient). */
+ * BN+add+ReLU backward moves 6 tensor passes instead of 7 when dres receives the masked gradient, and 5 when dres is NULL: the
+ * residual branch then consumes (dy, relu_mask) directly (zb_conv2d_dgrad_acc_masked, or this same call as the shortcut BatchNorm's
+ * backward -- "the gradient is dy masked by these bits" is all zb_bn2d_bwd_mask means). */
 int64_t zb_bn2d_relu_mask_words(int64_t n, int64_t c, int64_t h, int64_t w);
 int zb_bn2d_fwd_train_fused(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w,
                             double momentum, const void* x, const void* scale, const void* bias, void* running_mean,

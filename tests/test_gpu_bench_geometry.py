@@ -142,6 +142,17 @@ def test_resnet50_conv_shape_at_bench_geometry(env, shape):
         ops.conv_bkwd_data_accumulate(ctx, DY, W, acc, math=tf32, **kw)
         assert rel_err(host(acc) - 1.0, host(dx)) < 1e-4, "dgrad accumulate"
         del acc
+        # ... and with a lazily masked first arrival (the residual gradient of a fused BN + add + ReLU): bit-identical to
+        # accumulating onto the materialised product old (.) mask, whichever path serves the shape
+        old = torch.randn_like(dx)
+        words = torch.randint(-2 ** 31, 2 ** 31 - 1, ((old.numel() + 31) // 32,), dtype=torch.int64, device="cuda").to(torch.int32)
+        want_acc = ops.mask_apply(ctx, old, words)
+        bits = np.unpackbits(host(words).view(np.uint8), bitorder="little")[: old.numel()].astype(bool)
+        np.testing.assert_array_equal(host(want_acc).ravel(), np.where(bits, host(old).ravel(), np.float32(0)))
+        ops.conv_bkwd_data_accumulate(ctx, DY, W, want_acc, math=tf32, **kw)
+        ops.conv_bkwd_data_accumulate_masked(ctx, DY, W, old, words, math=tf32, **kw)
+        np.testing.assert_array_equal(host(old), host(want_acc))
+        del old, words, want_acc
     del y, dx, dw, xr, wr, dyr, y_ref
 
     # ---- 3xTF32 against exact arithmetic

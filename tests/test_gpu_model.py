@@ -359,3 +359,35 @@ def test_wgrad_on_side_stream_is_bit_identical(zb, arch, n, hw, classes, graph):
     assert all(np.isfinite(l0)) and l0 == l1 and n0 == n1
     for k in p0:
         assert torch.equal(p0[k], p1[k]), k
+
+
+@pytest.mark.parametrize("arch,n,hw,classes", [("resnet18", 8, 64, 10), ("resnet50", 4, 64, 10)])
+def test_lazy_masked_residual_gradient_is_bit_identical(zb, arch, n, hw, classes, monkeypatch):
+    """The fused BN + add + ReLU backward hands its residual gradient on as (dy, ReLU bits) and the consumer masks while reading (the
+    next dgrad's accumulate epilogue in identity blocks, the downsample BatchNorm's backward otherwise) instead of writing dy (.) bits
+    out.  Same arithmetic on the same values: losses, gradients and parameters match the materialising run bit for bit."""
+    pkg, ops, nn = zb
+    x, t = batch(n, hw, classes, 78)
+    X, T = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    runs = []
+    for lazy in (False, True):
+        if lazy:
+            monkeypatch.delenv("ZENU_B200_NO_LAZY_MASK", raising=False)
+        else:
+            monkeypatch.setenv("ZENU_B200_NO_LAZY_MASK", "1")
+        ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+        model = nn.Model(ctx, arch, classes, seed=6)
+        model.set_optimizer("sgd", lr=1e-3)
+        lb = torch.empty((1,), dtype=torch.float32, device="cuda")
+        l0 = ctx.launch_count()
+        losses = [model.train_step(X, T, loss_out=lb, read_loss=True) for _ in range(3)]
+        launches = ctx.launch_count() - l0
+        ctx.check()
+        runs.append((losses, {k: v["data"].clone() for k, v in model.named_parameters().items()}, launches))
+        model.close()
+        ctx.close()
+    (l0, p0, n0), (l1, p1, n1) = runs
+    assert all(np.isfinite(l0)) and l0 == l1
+    assert n1 <= n0, "the lazy form must not add launches"
+    for k in p0:
+        assert torch.equal(p0[k], p1[k]), k

@@ -296,6 +296,13 @@ def test_conv_layers_tf32x3(zb, ctx, arch, n, hw):
             base = torch.ones_like(dx)
             zb.conv_bkwd_data_accumulate(ctx, DY, W, base, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
             assert rel_err(host(base) - 1.0, host(dx)) < 1e-4, (name, "dgrad accumulate")
+            # masked fan-in: dx = dgrad + old (.) mask must equal accumulating onto the materialised product, bit for bit
+            old = torch.randn_like(dx)
+            words = torch.randint(-2 ** 31, 2 ** 31 - 1, ((old.numel() + 31) // 32,), dtype=torch.int64, device="cuda").to(torch.int32)
+            want = zb.mask_apply(ctx, old, words)
+            zb.conv_bkwd_data_accumulate(ctx, DY, W, want, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+            zb.conv_bkwd_data_accumulate_masked(ctx, DY, W, old, words, pad, stride, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+            np.testing.assert_array_equal(host(old), host(want), err_msg=f"{name} masked accumulate")
     ctx.check()
 
 
@@ -551,6 +558,15 @@ def test_bn_add_relu_bit_mask(zb, ctx, shape):
     dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x, g, scale, sm_ref, si_ref)
     assert rel_err(nchw(host(dx)), dx_ref) < 1e-4 and rel_err(host(ds), ds_ref) < 1e-4 and rel_err(host(db), db_ref) < 1e-4
     assert rel_err(nchw(host(dres)), g) < 1e-6
+    # lazy form: the masked gradient is not written out, everything else is bit-identical; a plain BN (downsample branch) reading
+    # (dy, mask) lazily equals the same BN fed the materialised product
+    dx3, ds3, db3, none = zb.batch_norm_2d_backward_masked(ctx, X, DY, dev(scale), sm, si, mask, want_residual_grad=False)
+    assert none is None
+    for a, b in ((dx3, dx), (ds3, ds), (db3, db)):
+        np.testing.assert_array_equal(host(a), host(b))
+    np.testing.assert_array_equal(host(zb.mask_apply(ctx, DY, mask)), host(dres))
+    dx4, ds4, db4 = zb.batch_norm_2d_backward(ctx, X, dres, dev(scale), sm, si, layout=ZB_NHWC)
+    assert rel_err(host(dx3), host(dx4)) < 1e-5 and rel_err(host(ds3), host(ds4)) < 1e-5 and rel_err(host(db3), host(db4)) < 1e-5
     ctx.check()
 
 

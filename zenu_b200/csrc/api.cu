@@ -10,11 +10,11 @@
 namespace zb {
 // umma_gemm.cu
 int umma_gemm(zb_ctx*, bool, bool, long long, long long, long long, float, const float*, long long, const float*, long long,
-              float, float*, long long, const float*);
+              float, float*, long long, const float*, const uint32_t* old_bits = nullptr);
 void umma_set_chain_limit(int);
 bool umma_conv_supported(const zb_conv2d_desc*);
 int umma_conv_fprop_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, const float*, float*, float, const float*, float*, int*);
-int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
+int umma_conv_dgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float, const uint32_t* old_bits = nullptr);
 int umma_conv_wgrad_nhwc(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
 bool umma_conv1x1_nchw_supported(const zb_conv2d_desc*, int pass);
 int umma_conv1x1_nchw_fprop(zb_ctx*, const zb_conv2d_desc*, const float*, const float*, float*, float);
@@ -163,12 +163,15 @@ static int tc_smallc_fprop(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, const f
 }
 
 static int tc_dgrad_nhwc(zb_ctx* ctx, int mm, const zb_conv2d_desc* d, long long P, long long Q, const float* dy, const float* w,
-                         float* dx, float beta, bool smallc) {
+                         float* dx, float beta, bool smallc, const uint32_t* old_bits = nullptr) {
+  if (smallc && old_bits != nullptr) { set_last_error("dgrad: masked accumulate is not served by the small-C kernels"); return ZB_ERR_UNSUPPORTED; }
   if (mm != ZB_MATH_TF32X3)
-    return smallc ? umma_conv_smallc_dgrad(ctx, d, dy, w, dx, beta) : umma_conv_dgrad_nhwc(ctx, d, dy, w, dx, beta);
+    return smallc ? umma_conv_smallc_dgrad(ctx, d, dy, w, dx, beta) : umma_conv_dgrad_nhwc(ctx, d, dy, w, dx, beta, old_bits);
+  int pass = 0;   // the mask belongs to the caller's old dx: first pass only, the other two accumulate onto complete values
   return run_tf32x3(ctx, dy, d->n * P * Q * d->k, w, d->k * d->kh * d->kw * d->c, beta,
                     [&](const float* gp, const float* wp, float bt, bool) {
-                      return smallc ? umma_conv_smallc_dgrad(ctx, d, gp, wp, dx, bt) : umma_conv_dgrad_nhwc(ctx, d, gp, wp, dx, bt);
+                      const uint32_t* ob = pass++ == 0 ? old_bits : nullptr;
+                      return smallc ? umma_conv_smallc_dgrad(ctx, d, gp, wp, dx, bt) : umma_conv_dgrad_nhwc(ctx, d, gp, wp, dx, bt, ob);
                     });
 }
 
@@ -271,12 +274,35 @@ static int fprop_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
 }
 
 static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
-                      void* dx, float beta);
+                      void* dx, float beta, const uint32_t* old_bits = nullptr);
 
 int zb_conv2d_dgrad(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
                     void* dx) {
   ZB_API_RANGE();
   return dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 0.f);
+}
+
+int zb_mask_apply(zb_ctx* ctx, int dtype, const void* x, const void* bits, void* out, int64_t n);
+
+int zb_conv2d_dgrad_acc_masked(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
+                               void* dx, const void* old_bits) {
+  ZB_API_RANGE();
+  if (old_bits == nullptr) return zb_conv2d_dgrad_acc(ctx, dtype, layout, math, d, dy, w, dx);
+  long long P, Q;
+  int rc = check_desc(d, &P, &Q);
+  if (rc != ZB_OK) return rc;
+  int m;
+  rc = resolve_math(ctx, dtype, math, &m);
+  if (rc != ZB_OK) return rc;
+  const bool fused = dtype == ZB_F32 && layout == ZB_NHWC && m != ZB_MATH_FP32 && (d->k % 32 == 0) && (d->c % 32 == 0) && d->kh * d->kw <= 64 &&
+                     !ZB_ENV_FLAG("ZENU_B200_NO_MASKED_ACC");
+  if (fused) {
+    rc = dgrad_impl(ctx, dtype, layout, math, d, dy, w, dx, 1.f, static_cast<const uint32_t*>(old_bits));
+    if (rc != ZB_ERR_UNSUPPORTED) return rc;
+  }
+  // paths without the masking epilogue: materialise the masked old value in place, then the plain accumulate
+  if ((rc = zb_mask_apply(ctx, dtype, dx, old_bits, dx, d->n * d->c * d->h * d->w)) != ZB_OK) return rc;
+  return zb_conv2d_dgrad_acc(ctx, dtype, layout, math, d, dy, w, dx);
 }
 
 int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
@@ -303,7 +329,7 @@ int zb_conv2d_dgrad_acc(zb_ctx* ctx, int dtype, int layout, int math, const zb_c
 }
 
 static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_conv2d_desc* d, const void* dy, const void* w,
-                      void* dx, float beta) {
+                      void* dx, float beta, const uint32_t* old_bits) {
   long long P, Q;
   int rc = check_desc(d, &P, &Q);
   if (rc != ZB_OK) return rc;
@@ -325,7 +351,7 @@ static int dgrad_impl(zb_ctx* ctx, int dtype, int layout, int math, const zb_con
   if (m == ZB_MATH_FP32 || !tc_ok) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
   if (layout == ZB_NHWC && beta == 0.f && umma_conv_smallc_dgrad_supported(d)) return tc_dgrad_nhwc(ctx, m, d, P, Q, gf, wf, df, 0.f, true);
   if (layout == ZB_NHWC) {
-    rc = tc_dgrad_nhwc(ctx, m, d, P, Q, gf, wf, df, beta, false);
+    rc = tc_dgrad_nhwc(ctx, m, d, P, Q, gf, wf, df, beta, false, old_bits);
     if (rc == ZB_ERR_UNSUPPORTED && beta == 0.f) return simt_conv_dgrad<float>(ctx, layout, d, gf, wf, df);
     return rc;
   }

@@ -108,6 +108,10 @@ template <typename T> struct BiasNchwF {  // y[n,k,hw] = x + b[k]
 };
 template <typename T> struct FillF { T v; __device__ T operator()(T, T, long long) const { return v; } };
 template <typename T> struct CopyF { __device__ T operator()(T a, T, long long) const { return a; } };
+template <typename T> struct MaskBitsF {  // a[i] where bit i of a 1-bit-per-element array is set, else 0
+  const uint32_t* bits;
+  __device__ T operator()(T a, T, long long i) const { return ((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u) ? a : T(0); }
+};
 template <typename T> struct SgdF {  // p -= (g * scale) * lr   (sgd.rs:24-27: grad * lr then sub)
   T lr, scale;
   __device__ T operator()(T p, T g, long long) const { return p - (g * scale) * lr; }
@@ -358,6 +362,13 @@ int zb_fill(zb_ctx* ctx, int dtype, void* x, double value, int64_t n) {
   ZB_DTYPE_SWITCH(dtype,
                   (launch_map<float, 0>(ctx, FillF<float>{static_cast<float>(value)}, static_cast<float*>(x), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), n)),
                   (launch_map<double, 0>(ctx, FillF<double>{value}, static_cast<double*>(x), static_cast<const double*>(nullptr), static_cast<const double*>(nullptr), n)));
+}
+int zb_mask_apply(zb_ctx* ctx, int dtype, const void* x, const void* bits, void* out, int64_t n) {
+  ZB_API_RANGE();
+  ZB_REQUIRE(bits != nullptr, "zb_mask_apply: bits is NULL");
+  ZB_DTYPE_SWITCH(dtype,
+                  (launch_map<float, 1>(ctx, MaskBitsF<float>{static_cast<const uint32_t*>(bits)}, static_cast<float*>(out), static_cast<const float*>(x), static_cast<const float*>(nullptr), n)),
+                  (launch_map<double, 1>(ctx, MaskBitsF<double>{static_cast<const uint32_t*>(bits)}, static_cast<double*>(out), static_cast<const double*>(x), static_cast<const double*>(nullptr), n)));
 }
 int zb_copy(zb_ctx* ctx, int dtype, const void* src, void* dst, int64_t n) {
   ZB_API_RANGE();

@@ -55,6 +55,7 @@ Runtime::Runtime(zb_ctx* c) : ctx(c), alloc(c) {
   // than the off-path wgrad gains.
   static const bool on = []() { const char* e = getenv("ZENU_B200_WGRAD_OVERLAP"); return e != nullptr && e[0] == '1'; }();
   overlap_wgrad = on && zb_ctx_side(c) != nullptr;
+  lazy_mask = getenv("ZENU_B200_NO_LAZY_MASK") == nullptr;   // read per Runtime (not cached): tests build models both ways
 }
 
 void Runtime::join_side() {
@@ -157,7 +158,29 @@ Tensor grad_target(Runtime& rt, VariableInner& v) {
   return rt.empty(v.data.shape);
 }
 
+void materialise_grad(Runtime& rt, VariableInner& v) {
+  if (!v.grad_mask.defined()) return;
+  ProfScope ps(rt, "grad.mask " + shape_str(v.data.shape), 0.0, (2.0 + 1.0 / 32.0) * v.grad.bytes());
+  Tensor dst = (v.grad.storage && v.grad.storage.use_count() == 1) ? v.grad : rt.empty(v.data.shape);
+  check_rc(zb_mask_apply(rt.ctx, v.grad.dtype, v.grad.ptr, v.grad_mask.ptr, dst.ptr, v.grad.numel()), "grad mask");
+  v.grad = dst;
+  v.grad_mask = Tensor();
+}
+
+void commit_grad_masked(Runtime& rt, VariableInner& v, const Tensor& g, const Tensor& bits) {
+  if (!v.grad.defined() && !v.is_param) {
+    v.grad = g;
+    v.grad.shape = v.data.shape;
+    v.grad_mask = bits;
+    return;
+  }
+  Tensor m = rt.empty(v.data.shape);
+  check_rc(zb_mask_apply(rt.ctx, g.dtype, g.ptr, bits.ptr, m.ptr, g.numel()), "grad mask");
+  commit_grad(rt, v, m);
+}
+
 void commit_grad(Runtime& rt, VariableInner& v, const Tensor& g) {
+  materialise_grad(rt, v);
   if (!v.grad.defined()) {
     if (v.is_param && v.grad_slot.defined() && g.ptr != v.grad_slot.ptr) {
       ProfScope ps(rt, "grad.copy", 0.0, 2.0 * g.bytes());
@@ -200,9 +223,13 @@ void Variable::backward(Runtime& rt, const std::function<void(int)>& on_bucket_r
     heap.pop();
     VarPtr out = fn->output.lock();
     if (!out || !out->grad.defined()) continue;
+    if (out->grad_mask.defined() && !fn->takes_masked_grad()) materialise_grad(rt, *out);
+    fn->gy_mask = out->grad_mask;
     Tensor gy = out->grad;
     fn->backward(rt, gy);
+    fn->gy_mask = Tensor();
     out->grad = Tensor();  // intermediate gradients are not retained
+    out->grad_mask = Tensor();
     for (auto& in : fn->inputs) {
       if (in->is_param && in->grad.defined() && in->bucket >= 0 && on_bucket_ready) on_bucket_ready(-1 - in->bucket);
       if (in->creator && !seen.count(in->creator.get())) {
@@ -223,6 +250,7 @@ void Variable::clear_grad() const {
     if (!v || seen.count(v.get())) continue;
     seen.insert(v.get());
     v->grad = Tensor();
+    v->grad_mask = Tensor();
     if (v->creator) {
       for (auto& in : v->creator->inputs) stack.push_back(in);
       v->creator.reset();
@@ -268,8 +296,15 @@ struct ConvFn : Function {
     if (need_dx && (xv.requires_grad || xv.creator)) {
       ProfScope ps(rt, conv_key("dgrad", d), conv_flops(d), conv_bytes(d, gy.elem_size()));
       if (xv.grad.defined() && !xv.is_param && xv.grad.storage && xv.grad.storage.use_count() == 1 && x_layout == ZB_NHWC) {
-        // second arrival (residual fan-in): accumulate inside the dgrad epilogue instead of a separate add pass
-        check_rc(zb_conv2d_dgrad_acc(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, xv.grad.ptr), "conv dgrad (accumulate)");
+        // second arrival (residual fan-in): accumulate inside the dgrad epilogue instead of a separate add pass; a lazy masked
+        // first arrival (the residual gradient of a fused BN + add + ReLU) is masked as the epilogue reads it
+        if (xv.grad_mask.defined()) {
+          check_rc(zb_conv2d_dgrad_acc_masked(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, xv.grad.ptr, xv.grad_mask.ptr),
+                   "conv dgrad (masked accumulate)");
+          xv.grad_mask = Tensor();
+        } else {
+          check_rc(zb_conv2d_dgrad_acc(rt.ctx, gy.dtype, ZB_NHWC, ZB_MATH_DEFAULT, &d, gy.ptr, w.ptr, xv.grad.ptr), "conv dgrad (accumulate)");
+        }
       } else {
         // (for an NCHW network input the gradient is produced in NHWC order; nothing consumes it)
         Tensor dx = grad_target(rt, xv);
@@ -361,6 +396,8 @@ struct BnFn : Function {
   int64_t n, c, h, w;
   bool relu, has_res;
   const char* name() const override { return "batch_norm_2d"; }
+  // the plain BN of a downsample branch reads its (lazy) output gradient through the bit mask of the block's closing ReLU
+  bool takes_masked_grad() const override { return !relu && !has_res && x.dtype == ZB_F32 && c % 32 == 0; }
   void backward(Runtime& rt, const Tensor& gy) override {
     VariableInner& xv = *inputs[0];
     Tensor dx = grad_target(rt, xv);
@@ -368,15 +405,21 @@ struct BnFn : Function {
     Tensor db = grad_target(rt, *inputs[2]);
     Tensor dres;
     void* dres_ptr = nullptr;
-    if (has_res && relu) {
+    // fused BN + add + ReLU with a bit mask: the residual branch receives (gy, bits) lazily, the masked product is never stored
+    const bool lazy_res = has_res && relu && relu_mask.defined() && !inputs[3]->grad.defined() && !inputs[3]->is_param && rt.lazy_mask;
+    if (has_res && relu && !lazy_res) {
       dres = grad_target(rt, *inputs[3]);
       // a second consumer may already have written the slot: then produce into fresh memory and add
       if (inputs[3]->grad.defined()) dres = rt.empty(inputs[3]->data.shape);
       dres_ptr = dres.ptr;
     }
     ProfScope ps(rt, std::string("bn.bwd") + (relu ? "+relu" : "") + (has_res ? "+res" : "") + " " + shape_str(x.shape), 0.0,
-                 static_cast<double>(x.bytes()) * (5.0 + (relu && has_res ? (relu_mask.defined() ? 1.0 + 1.0 / 32.0 : 2.0) : 0.0)));
-    if (relu_mask.defined())
+                 static_cast<double>(x.bytes()) * (5.0 + (gy_mask.defined() ? 2.0 / 32.0 : 0.0) +
+                     (relu && has_res ? (lazy_res ? 2.0 / 32.0 : relu_mask.defined() ? 1.0 + 1.0 / 32.0 : 2.0) : 0.0)));
+    if (gy_mask.defined())
+      check_rc(zb_bn2d_bwd_mask(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
+                                ds.ptr, db.ptr, gy_mask.ptr, nullptr), "bn bwd (lazy masked gradient)");
+    else if (relu_mask.defined())
       check_rc(zb_bn2d_bwd_mask(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, x.ptr, gy.ptr, scale.ptr, saved_mean.ptr, saved_inv.ptr, dx.ptr,
                                 ds.ptr, db.ptr, relu_mask.ptr, dres_ptr), "bn bwd (bit mask)");
     else if (relu && !has_res)  // mask recomputed from x: the forward output is neither kept nor read
@@ -388,7 +431,10 @@ struct BnFn : Function {
     commit_grad(rt, xv, dx);
     commit_grad(rt, *inputs[1], ds);
     commit_grad(rt, *inputs[2], db);
-    if (has_res) commit_grad(rt, *inputs[3], relu ? dres : gy);
+    if (has_res) {
+      if (lazy_res) commit_grad_masked(rt, *inputs[3], gy, relu_mask);
+      else commit_grad(rt, *inputs[3], relu ? dres : gy);
+    }
     x = Tensor();
     y = Tensor();
     relu_mask = Tensor();

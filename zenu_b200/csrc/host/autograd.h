@@ -91,6 +91,9 @@ struct Runtime {  // one per model: ctx + allocator + train flag (reference: glo
   // conv wgrad on the ctx's side stream (zb_ctx_side): overlaps the BatchNorm-backward / dgrad chain of the following layers.
   // Tensors the side kernels read are held here until join_side() has made the main stream wait for them.
   bool overlap_wgrad = false;
+  // fused BN + add + ReLU backward hands its residual gradient on as (gy, ReLU bits) instead of writing gy (.) bits out; the consumer
+  // (the next dgrad's accumulate epilogue, or a downsample BN's backward) masks as it reads.  ZENU_B200_NO_LAZY_MASK=1 turns it off.
+  bool lazy_mask = true;
   bool side_pending = false;
   std::vector<Tensor> side_hold;
   void join_side();
@@ -119,11 +122,17 @@ struct Function {
   // consume the gradient of the output, produce/accumulate gradients of the inputs
   virtual void backward(Runtime& rt, const Tensor& gy) = 0;
   virtual const char* name() const = 0;
+  // A "lazy masked" output gradient is the pair (gy, 1 bit per element) whose value is gy where the bit is set, else 0 (what the
+  // fused BN + add + ReLU backward hands to its residual branch without writing the product out).  A function that can apply the
+  // mask while it reads gy says so here and finds the bits in gy_mask; for all others the sweep materialises the product first.
+  virtual bool takes_masked_grad() const { return false; }
+  Tensor gy_mask;
 };
 
 struct VariableInner {
   Tensor data;
   Tensor grad;                       // undefined until a gradient arrives
+  Tensor grad_mask;                  // defined: grad is lazy, its value is grad where the bit is set else 0 (see Function::gy_mask)
   Tensor grad_slot;                  // parameters: pre-assigned view into the flat gradient buffer
   std::shared_ptr<Function> creator;
   int gen = 0;
@@ -160,6 +169,9 @@ void accumulate_grad(Runtime& rt, VariableInner& v, const Tensor& g);
 // Returns where a first-arriving gradient of v should be written (the flat slot for parameters, else fresh memory)
 Tensor grad_target(Runtime& rt, VariableInner& v);
 void commit_grad(Runtime& rt, VariableInner& v, const Tensor& g);  // g was produced in grad_target() or elsewhere
+// first arrival: keeps (g, bits) lazily; otherwise the product is materialised and added
+void commit_grad_masked(Runtime& rt, VariableInner& v, const Tensor& g, const Tensor& bits);
+void materialise_grad(Runtime& rt, VariableInner& v);  // v.grad <- v.grad (.) bits, mask dropped (no-op when not lazy)
 
 // ---- differentiable functions (NHWC activations, KRSC filters) ------------------------------------------
 struct ConvArgs { int64_t pad_h, pad_w, stride_h, stride_w, dil_h, dil_w; };

@@ -93,7 +93,7 @@ __device__ __forceinline__ void tile_kb_range(const UmmaParams& p, const TileCoo
 
 // ---------------------------------------------------------------------------------------------- epilogue (warps 2-5)
 // Shared by the implicit-GEMM kernel and the halo-reuse conv kernel: drains finished TMEM accumulators tile by tile.
-template <int BN>
+template <int BN, bool MASKABLE = false, bool DEEP = false>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem, int epi_offset, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane, volatile int* err,
                                               bool halo = false, uint8_t* old_smem = nullptr, int n_acc = 2, int group = 1,
@@ -263,7 +263,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       // parallelism for the K = 64..256 gradient fan-in GEMMs, whose time is the read-modify-write of the output
       float4 olds[8];
       const bool prefetch = use_beta && tile_vec;
-      const bool deep = prefetch && old_smem != nullptr;
+      // DEEP (the OLD = true kernel variants): old tiles always come through the cp.async ring; the one-chunk-ahead register prefetch
+      // below is compiled out there (its 32 registers made those variants spill once the mask nibbles were added)
+      const bool deep = DEEP && prefetch && old_smem != nullptr;
+      // old values through a bit mask (UmmaParams::old_bits): first flush of the tile only, like the caller's beta itself
+      // (MASKABLE: only the kernel variants that serve beta launches carry the masking code and its registers)
+      const bool use_mask = MASKABLE && use_beta && sub == 0 && !partial && p.old_bits != nullptr;
       const uint32_t old_u32 = deep ? smem_u32(old_smem) + ew * (kOldDepth * 4096) + lane * 16 : 0u;
       auto issue_old = [&](int c) {
         if (n0 + c * 32 + 32 <= p.N && c < BN / 32) {
@@ -275,16 +280,38 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
+      // mask words of the whole tile (32 rows x BN / 32 words per warp) land in this warp's statistics slot (never used by a beta
+      // launch) through 4-byte cp.async: lane (sub_row, piece) fetches word (row it * 4 + sub_row, chunk piece).  They join the first
+      // group of the old-tile ring, so the first chunk's wait covers them and no chunk waits on a global load of its own.
+      constexpr int kMaskCh = BN / 32;
+      const bool mask_tile = use_mask && tile_vec;
+      const uint32_t mask_u32 = smem_u32(stat_w);
+      if (mask_tile) {
+        if (piece < kMaskCh && n0 + piece * 32 + 32 <= p.N) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (off32[it] >= 0) {
+              const long long idx = base_off + n0 + off32[it] + piece * 32;   // a multiple of 32 (ldd % 32 == 0: checked at launch)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(mask_u32 + ((it * 4 + sub_row) * kMaskCh + piece) * 4),
+                           "l"(p.old_bits + (idx >> 5)) : "memory");
+            }
+        }
+        if (!deep) asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       if (deep) {
 #pragma unroll
         for (int c = 0; c < kOldDepth; ++c) issue_old(c);
-      } else if (prefetch && n0 + 32 <= p.N) {
+      } else if (!DEEP && prefetch && n0 + 32 <= p.N) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
           olds[it] = off32[it] >= 0 ? *reinterpret_cast<const float4*>(wb + off32[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (!mbar_wait(&tfull_bar[acc], acc_phase, err)) { dead = true; break; }
       tc_fence_after();
+      if (mask_tile && !deep) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
       // FULL: every row of this warp exists (no per-row predicates)
       auto chunk_loop = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -319,11 +346,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
               float4 cur[8];
               if (deep) {
                 asm volatile("cp.async.wait_group %0;" ::"n"(kOldDepth - 1) : "memory");
+                if (mask_tile && c == 0) __syncwarp();   // the tile's mask words (other lanes' copies, first group) are visible
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
                   cur[it] = (FULL || off32[it] >= 0) ? lds128(old_u32 + ((c % kOldDepth) * 8 + it) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
                 issue_old(c + kOldDepth);   // refills the slot just read
-              } else {
+              } else if (!DEEP) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) cur[it] = olds[it];
                 if (use_beta && c + 1 < BN / 32 && col0 + 64 <= p.N) {   // next chunk's old values: in flight during this chunk's stores
@@ -331,6 +359,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
                   for (int it = 0; it < 8; ++it)
                     olds[it] = (FULL || off32[it] >= 0) ? *reinterpret_cast<const float4*>(wb + (off32[it] + coff + 32))
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+              if (use_mask) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const uint32_t nb = lds32(mask_u32 + ((it * 4 + sub_row) * kMaskCh + c) * 4) >> (piece * 4);
+                  cur[it].x = (nb & 1u) ? cur[it].x : 0.f; cur[it].y = (nb & 2u) ? cur[it].y : 0.f;
+                  cur[it].z = (nb & 4u) ? cur[it].z : 0.f; cur[it].w = (nb & 8u) ? cur[it].w : 0.f;
                 }
               }
 #pragma unroll
@@ -381,7 +417,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
                 if (col + e < p.N) {
                   float val = e == 0 ? v4.x : (e == 1 ? v4.y : (e == 2 ? v4.z : v4.w));
                   val = e_alpha * val + (e_bias != nullptr ? __ldg(e_bias + col + e) : 0.f);
-                  if (use_beta) val += e_beta * dst[e];
+                  if (use_beta) {
+                    const long long idx = off + col + e;
+                    const bool keep = !use_mask || ((__ldg(p.old_bits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u;
+                    if (keep) val += e_beta * dst[e];
+                  }
                   dst[e] = val;
                 }
             }
@@ -665,8 +705,8 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, OLD ? smem + L::OLD_OFFSET : nullptr,
-                      2, 1, CL, CL > 1);
+    epilogue_role<BN, OLD, OLD>(p, smem, L::EPI_OFFSET, tfull_bar, tempty_bar, tmem_base, warp, lane, err, false, OLD ? smem + L::OLD_OFFSET : nullptr,
+                           2, 1, CL, CL > 1);
   }
 
   tc_fence_before();
@@ -890,7 +930,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_role<BN>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true, nullptr, 2, 1, CL, PAIR);
+    epilogue_role<BN, true>(p, smem, epi_off, tfull_bar, tempty_bar, tmem_base, warp, lane, err, true, nullptr, 2, 1, CL, PAIR);
   }
   tc_fence_before();
   __syncthreads();
@@ -1277,6 +1317,11 @@ static int umma_launch(zb_ctx* ctx, int bn, const CUtensorMap& a, const CUtensor
   // launches whose epilogue reads the old output tile (beta != 0, chained 3xTF32 flushes): a shallower operand ring makes
   // room for the deep old-tile prefetch buffers (these are short-K, output-bound problems)
   const bool deep_old = (p.beta != 0.f || p.chain_kb > 0) && p.out_mode != OUT_WDGRAD && !ZB_ENV_FLAG("ZENU_B200_NO_DEEP_BETA");
+  if (p.old_bits != nullptr && (p.stat_partial != nullptr || (p.ldd & 31) != 0)) {
+    set_last_error("umma: masked accumulate needs ldd % 32 == 0 and no fused statistics");
+    return ZB_ERR_UNSUPPORTED;
+  }
+  if (p.old_bits != nullptr && !deep_old) { set_last_error("umma: masked accumulate needs the deep-beta kernel variants"); return ZB_ERR_UNSUPPORTED; }
   if (pair_cl(p, bn) == 2) {
     if (deep_old) return bn == 128 ? launch_cfg_pair<128, 6, true>(ctx, a, b, p) : launch_cfg_pair<256, 4, true>(ctx, a, b, p);
     return bn == 128 ? launch_cfg_pair<128, 8>(ctx, a, b, p) : launch_cfg_pair<256, 6>(ctx, a, b, p);
@@ -1377,7 +1422,7 @@ static void init_params(UmmaParams& p, zb_ctx* ctx) {
 // do not meet TMA alignment rules (caller then uses the SIMT kernel).
 int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n, long long k, float alpha,
               const float* a, long long lda, const float* b, long long ldb, float beta, float* c, long long ldc,
-              const float* bias) {
+              const float* bias, const uint32_t* old_bits) {
   if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15) ||
       m <= 0 || n <= 0 || k <= 0 || m > 0x7fffffffll || n > 0x7fffffffll || k > 0x7fffffffll) {
     set_last_error("umma_gemm: operands not TMA-compatible");
@@ -1414,6 +1459,10 @@ int umma_gemm(zb_ctx* ctx, bool trans_a, bool trans_b, long long m, long long n,
   p.ldd = ldc;
   p.prof_flops = 2.0 * m * n * k;
   finish_split_fields(p, pick_splits(ctx, static_cast<long long>(p.m_tiles) * p.n_tiles, p.kb_total, 8));
+  if (old_bits != nullptr) {
+    if (p.splits > 1 || beta == 0.f) { set_last_error("umma_gemm: masked accumulate needs an unsplit beta launch"); return ZB_ERR_UNSUPPORTED; }
+    p.old_bits = old_bits;
+  }
   return run_with_splits(ctx, bn, ma, mb, p, m, n, c, ldc, alpha, beta, bias);
 }
 
@@ -1582,7 +1631,7 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
 // tap_r/tap_s: raster offset of tap t (filter row / column in the orientation of `filt`)
 static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long long H, long long W, long long Cin, long long Kout, int R,
                           int S, int ph, int pw, const float* in, const float* filt, const float* bias, float* out, float beta,
-                          double flops, const StatRequest* st = nullptr) {
+                          double flops, const StatRequest* st = nullptr, const uint32_t* old_bits = nullptr) {
   const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
   CUtensorMap ma, mb;
   {
@@ -1625,6 +1674,11 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   p.D = out;
   p.ldd = Kout;
   p.alpha = 1.f; p.beta = beta; p.bias = bias;
+  p.old_bits = beta != 0.f ? old_bits : nullptr;
+  if (p.old_bits != nullptr && (st != nullptr || Kout % 32 != 0)) {   // the mask words use the epilogue's statistics slot
+    set_last_error("umma halo: masked accumulate needs Kout % 32 == 0 and no fused statistics");
+    return ZB_ERR_UNSUPPORTED;
+  }
   finish_split_fields(p, 1);
   p.split_stride = 0;
   stat_attach(ctx, p, st, p.m_tiles * p.n_tiles, Kout, out, bias);
@@ -1735,7 +1789,10 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
 
 // dx[N,H,W,C] = dgrad(dy[N,P,Q,K], w[K,R,S,C]).  Stride 1: one implicit GEMM over dy with the flipped filter.
 // Stride s > 1: one implicit GEMM per output parity class (h % s, w % s), scattered into dx.
-int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta) {
+int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, const float* w, float* dx, float beta,
+                         const uint32_t* old_bits) {
+  // old_bits (beta launches): the old dx counts through a 1-bit-per-element mask (UmmaParams::old_bits)
+  if (old_bits != nullptr && (beta == 0.f || d->c % 32 != 0)) { set_last_error("umma dgrad: masked accumulate unsupported here"); return ZB_ERR_UNSUPPORTED; }
   if (d->k % 32 != 0 || d->kh * d->kw > kUmmaMaxTaps) {
     set_last_error("umma dgrad: shape unsupported");
     return ZB_ERR_UNSUPPORTED;
@@ -1746,7 +1803,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const int R = static_cast<int>(d->kh), S = static_cast<int>(d->kw);
   if (R == 1 && S == 1 && sh == 1 && sw == 1 && d->pad_h == 0 && d->pad_w == 0 && d->c % 4 == 0 && d->k % 4 == 0) {
     // pointwise: dx[pixels][C] = dy[pixels][K] * w[K][C]: a plain GEMM on the filter as stored (no transform, tiled loads)
-    return umma_gemm(ctx, false, false, d->n * P * Q, d->c, d->k, 1.f, dy, d->k, w, d->c, beta, dx, d->c, nullptr);
+    return umma_gemm(ctx, false, false, d->n * P * Q, d->c, d->k, 1.f, dy, d->k, w, d->c, beta, dx, d->c, nullptr, old_bits);
   }
   if (sh == 1 && sw == 1 && d->dil_h == 1 && d->dil_w == 1 && R * S > 1 && d->pad_h <= R - 1 && d->pad_w <= S - 1) {
     // stride 1: dx = conv(dy, flipped filter) with padding R-1-pad; halo-reuse kernel over the dY raster
@@ -1765,7 +1822,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       plan_note("dgrad_filter;");
       ZB_KLAUNCH(ctx, dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), R * S, tl));
       return umma_conv_halo(ctx, hp, d->n, P, Q, d->k, d->c, R, S, ph2, pw2, dy, wt, nullptr, dx, beta,
-                            2.0 * d->n * P * Q * d->k * d->c * R * S);
+                            2.0 * d->n * P * Q * d->k * d->c * R * S, nullptr, old_bits);
     }
   }
   const int bn = pick_bn(d->c);
@@ -1818,6 +1875,10 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       }
       plans.push_back(cp);
     }
+  if (need_zero && old_bits != nullptr) {   // pixels no launch reaches would keep their old value unmasked
+    set_last_error("umma dgrad: masked accumulate needs every dx pixel covered by a parity class");
+    return ZB_ERR_UNSUPPORTED;
+  }
   if (need_zero && beta == 0.f) {
     plan_note("memset_dx;");
     if (!plan_dry()) ZB_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * d->n * d->h * d->w * d->c, ctx->stream));
@@ -1885,6 +1946,7 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
     finish_split_fields(p, 1);
     p.split_stride = 0;
     p.beta = beta;  // dx = dgrad + beta * dx: gradient fan-in (residual shortcuts) without a separate add pass
+    p.old_bits = beta != 0.f ? old_bits : nullptr;   // every pixel of dx belongs to exactly one parity class: each old value is read once
     rc = umma_launch(ctx, bn, ma, mb, p);
     if (rc != ZB_OK) return rc;
   }

@@ -60,6 +60,10 @@ struct UmmaParams {
   long long split_stride;     // elements between split-K partial buffers (0 when splits == 1)
   const float* bias;          // optional [N], added when splits == 1
   float alpha, beta;          // D = alpha*acc + bias + beta*D_old (splits == 1); partials store raw acc
+  // beta launches only: D_old is taken through a 1-bit-per-element mask (bit index = element index in D; 0 -> the old value counts
+  // as 0).  The fused BN+add+ReLU backward hands the residual branch (dy, ReLU bits) instead of a materialised masked gradient; the
+  // dgrad that accumulates into it masks on the fly (zb_conv2d_dgrad_acc_masked).  NULL = plain accumulate.
+  const uint32_t* old_bits;
   int scat_OH, scat_OW, scat_sy, scat_oy, scat_sx, scat_ox;  // OUT_SCATTER geometry
   // halo-reuse conv kernel (stride-1 RxS convs): one smem raster of (tp + R - 1) x Wr input pixels per 32-channel chunk
   // serves every filter tap through UMMA descriptors that start tap_w[t] rows (128 bytes each) into the raster

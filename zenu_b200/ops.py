@@ -82,6 +82,11 @@ def _chk(t, name):
                             "zenu-matrix/src/nn/conv/interface.rs:270-281)")
 
 
+def _chk_mask(t, name):
+    if not t.is_cuda or not t.is_contiguous() or t.dtype != torch.int32:
+        raise ZenuB200Error(f"{name}: expected a contiguous int32 CUDA tensor (1 bit per element)")
+
+
 def _desc(x_shape, w_shape, layout, pad, stride, dil):
     if layout == ZB_NCHW:
         n, c, h, w = x_shape
@@ -160,6 +165,29 @@ def conv_bkwd_data_accumulate(ctx, dy, w, dx, pad=0, stride=1, dil=1, layout=ZB_
         raise ZenuB200Error("conv_bkwd_data: dy shape does not match the conv geometry")
     check(ctx.lib.zb_conv2d_dgrad_acc(ctx.handle, _DT[dy.dtype], layout, math, ctypes.byref(d), _p(dy), _p(w), _p(dx)))
     return dx
+
+
+def conv_bkwd_data_accumulate_masked(ctx, dy, w, dx, mask, pad=0, stride=1, dil=1, layout=ZB_NCHW, math=ZB_MATH_DEFAULT):
+    """dx = conv_bkwd_data(dy, w) + dx (.) mask, in place: the fan-in above with a lazily masked first arrival (bit e of `mask`,
+    int32 words, keeps element e of dx in its memory order; the ReLU bits of batch_norm_2d_forward_train_masked)."""
+    _chk(dy, "conv_bkwd_data dy"); _chk(w, "conv_bkwd_data filter"); _chk(dx, "conv_bkwd_data dx"); _chk_mask(mask, "conv_bkwd_data mask")
+    d = _desc(tuple(dx.shape), tuple(w.shape), layout, pad, stride, dil)
+    if tuple(dy.shape) != conv_out_shape(tuple(dx.shape), tuple(w.shape), layout, pad, stride, dil):
+        raise ZenuB200Error("conv_bkwd_data: dy shape does not match the conv geometry")
+    if mask.numel() * 32 < dx.numel():
+        raise ZenuB200Error("conv_bkwd_data: mask shorter than dx")
+    check(ctx.lib.zb_conv2d_dgrad_acc_masked(ctx.handle, _DT[dy.dtype], layout, math, ctypes.byref(d), _p(dy), _p(w), _p(dx), _p(mask)))
+    return dx
+
+
+def mask_apply(ctx, x, mask, out=None):
+    """out[e] = x[e] if bit e of `mask` (int32 words) is set else 0."""
+    _chk(x, "mask_apply x"); _chk_mask(mask, "mask_apply mask")
+    if mask.numel() * 32 < x.numel():
+        raise ZenuB200Error("mask_apply: mask shorter than x")
+    out = torch.empty_like(x) if out is None else out
+    check(ctx.lib.zb_mask_apply(ctx.handle, _DT[x.dtype], _p(x), _p(mask), _p(out), x.numel()))
+    return out
 
 
 def conv_bkwd_weight(ctx, dy, x, w_shape, pad=0, stride=1, dil=1, layout=ZB_NCHW, math=ZB_MATH_DEFAULT):
@@ -256,10 +284,12 @@ def batch_norm_2d_forward_train_masked(ctx, momentum, x, scale, bias, mean, vari
     return y, sm, si, mask
 
 
-def batch_norm_2d_backward_masked(ctx, x, y_grad, scale, saving_mean, saving_inv_variance, mask):
-    """Backward of the fused BN+add+ReLU with the ReLU mask taken from `mask`: (x_grad, scale_grad, bias_grad, residual_grad)."""
+def batch_norm_2d_backward_masked(ctx, x, y_grad, scale, saving_mean, saving_inv_variance, mask, want_residual_grad=True):
+    """Backward of the fused BN+add+ReLU with the ReLU mask taken from `mask`: (x_grad, scale_grad, bias_grad, residual_grad).
+    want_residual_grad=False: the masked gradient y_grad (.) mask is not written out (residual_grad is None; the caller keeps
+    (y_grad, mask) and masks where it is consumed)."""
     n, c, h, w = _nkhw(x.shape, ZB_NHWC)
-    dx, dres = torch.empty_like(x), torch.empty_like(x)
+    dx, dres = torch.empty_like(x), (torch.empty_like(x) if want_residual_grad else None)
     ds = torch.empty((c,), dtype=x.dtype, device=x.device)
     db = torch.empty((c,), dtype=x.dtype, device=x.device)
     check(ctx.lib.zb_bn2d_bwd_mask(ctx.handle, _DT[x.dtype], ZB_NHWC, n, c, h, w, _p(x), _p(y_grad), _p(scale), _p(saving_mean),
