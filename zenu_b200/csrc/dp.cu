@@ -180,10 +180,11 @@ int zb_dp_init(zb_ctx* ctx, const void* host_id128, int rank, int world) {
   memcpy(&id, host_id128, sizeof(id));
   ncclComm_t comm;
   ZB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  // The compute kernels are persistent grids of one CTA per SM: every SM a collective occupies delays a whole CTA's worth of tiles of
-  // whatever tensor kernel runs beside it, while a 25 MB bucket over NVLink / NVSwitch (NVLS) needs only a few CTAs.  Cap NCCL's CTA
-  // count (ZENU_B200_NCCL_MAX_CTAS, default 4; 0 = NCCL's own default).
-  static const int max_ctas = []() { const char* e = getenv("ZENU_B200_NCCL_MAX_CTAS"); return e ? atoi(e) : 4; }();
+  // The compute kernels are persistent grids of one CTA per SM, so every SM a collective occupies delays a whole CTA's worth of tiles
+  // of the tensor kernel beside it; ZENU_B200_NCCL_MAX_CTAS caps NCCL's CTA count per collective.  Measured at N = 2 on one box
+  // (profiles/r2_scaling.md): NCCL's own choice 37.09 ms / step, cap 4 37.24, cap 16 37.12 (1 GPU: 36.56) - the cap buys nothing, so
+  // the default is 0 = leave it to NCCL.
+  static const int max_ctas = []() { const char* e = getenv("ZENU_B200_NCCL_MAX_CTAS"); return e ? atoi(e) : 0; }();
   if (g_nccl.CommInitRankConfig != nullptr && max_ctas > 0) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
     cfg.maxCTAs = max_ctas;

@@ -188,6 +188,41 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// Division by a kernel-invariant divisor d (tile counts, row / column extents) as multiply-high + shift (Granlund-Montgomery:
+// m = ceil(2^(31 + l) / d), l = ceil(log2 d); exact for 0 <= n < 2^31).  The role loops decode a tile id and a row index per tile;
+// a hardware-free 32-bit division is ~25 instructions, and the epilogue warps are bound by their own instruction stream.
+struct FastDiv { uint32_t mul, shr; };
+__device__ __forceinline__ FastDiv fastdiv_make(int d) {
+  FastDiv f;
+  if (d <= 1) { f.mul = 0u; f.shr = 0u; return f; }
+  const int l = 32 - __clz(d - 1);
+  f.mul = static_cast<uint32_t>(((1ull << (31 + l)) + static_cast<unsigned long long>(d) - 1ull) / static_cast<unsigned long long>(d));
+  f.shr = static_cast<uint32_t>(l - 1);
+  return f;
+}
+__device__ __forceinline__ int fastdiv(int n, FastDiv f) {
+  return f.mul != 0u ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.mul) >> f.shr) : n;
+}
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100): the same IEEE results as the scalar forms, half the instructions
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 sub_f32x2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ void stg128(float* p, float4 v) {   // explicit .global: the pointer may have passed through an opaque asm
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

@@ -51,28 +51,45 @@ struct TileCoord {
   int m_blk, n_blk, tap, split;
 };
 template <bool V> struct FullTag { static constexpr bool value = V; };
-__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
+struct TileDiv {   // the divisors of a tile id, as multiply-high constants (built once per role)
+  FastDiv n, t, m;
+  int m_groups;
+};
+__device__ __forceinline__ TileDiv make_tile_div(const UmmaParams& p, int cl) {
+  TileDiv d;
+  d.m_groups = (p.m_tiles + cl - 1) / cl;
+  d.n = fastdiv_make(p.n_tiles);
+  d.t = fastdiv_make(p.tap_tiles);
+  d.m = fastdiv_make(d.m_groups);
+  return d;
+}
+__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile, const TileDiv& d) {
   TileCoord t;
-  t.n_blk = tile % p.n_tiles;
-  tile /= p.n_tiles;
-  t.tap = tile % p.tap_tiles;
-  tile /= p.tap_tiles;
-  t.m_blk = tile % p.m_tiles;
-  t.split = tile / p.m_tiles;
+  int q = fastdiv(tile, d.n);
+  t.n_blk = tile - q * p.n_tiles;
+  tile = q;
+  q = fastdiv(tile, d.t);
+  t.tap = tile - q * p.tap_tiles;
+  tile = q;
+  q = fastdiv(tile, d.m);
+  t.m_blk = tile - q * p.m_tiles;
+  t.split = q;
   return t;
 }
 
 // Cluster walk (CL CTAs on CL consecutive row blocks of the same column block / tap / split): work item q of the cluster ->
 // this CTA's tile.  m_tiles need not be a multiple of CL for the halo kernel (a row block past the end is a dummy).
-__device__ __forceinline__ TileCoord decode_tile_cluster(const UmmaParams& p, int q, int cl, int rank) {
+__device__ __forceinline__ TileCoord decode_tile_cluster(const UmmaParams& p, int q, int cl, int rank, const TileDiv& d) {
   TileCoord t;
-  const int m_groups = (p.m_tiles + cl - 1) / cl;
-  t.n_blk = q % p.n_tiles;
-  q /= p.n_tiles;
-  t.tap = q % p.tap_tiles;
-  q /= p.tap_tiles;
-  t.m_blk = (q % m_groups) * cl + rank;
-  t.split = q / m_groups;
+  int u = fastdiv(q, d.n);
+  t.n_blk = q - u * p.n_tiles;
+  q = u;
+  u = fastdiv(q, d.t);
+  t.tap = q - u * p.tap_tiles;
+  q = u;
+  u = fastdiv(q, d.m);
+  t.m_blk = (q - u * d.m_groups) * cl + rank;
+  t.split = u;
   return t;
 }
 
@@ -132,19 +149,25 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
       __syncwarp();
     }
     const int groups = total_tiles / group;
+    const TileDiv tdiv = make_tile_div(p, cluster);
+    const FastDiv fd_group = fastdiv_make(group);
+    const FastDiv fd_win_img = fastdiv_make(p.win_p_tiles * p.win_q_tiles), fd_win_qt = fastdiv_make(p.win_q_tiles),
+                  fd_win_bq = fastdiv_make(p.win_box_q);
+    const FastDiv fd_pq = fastdiv_make(p.conv_P * p.conv_Q), fd_q = fastdiv_make(p.conv_Q);
     const int cl_id = blockIdx.x / cluster, n_cl = gridDim.x / cluster, cl_rank = blockIdx.x % cluster;
     const int cl_groups = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles * p.tap_tiles * p.splits;
     for (int step = 0;; ++step) {
       TileCoord tc;
       bool tile_exists = true;
       if (cluster == 1) {
-        const int grp = blockIdx.x + (step / group) * gridDim.x;
+        const int sg = fastdiv(step, fd_group);
+        const int grp = blockIdx.x + sg * gridDim.x;
         if (grp >= groups) break;
-        tc = decode_tile(p, grp * group + step % group);
+        tc = decode_tile(p, grp * group + (step - sg * group), tdiv);
       } else {
         const int q = cl_id + step * n_cl;
         if (q >= cl_groups) break;
-        tc = decode_tile_cluster(p, q, cluster, cl_rank);
+        tc = decode_tile_cluster(p, q, cluster, cl_rank, tdiv);
         tile_exists = tc.m_blk < p.m_tiles;
       }
       const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
@@ -154,9 +177,9 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         const int l = ew * 32 + lane;
         if (p.out_mode == OUT_WINDOW) {
           const int per_img = p.win_p_tiles * p.win_q_tiles;
-          const int img = tc.m_blk / per_img, rem = tc.m_blk - img * per_img;
-          const int pt = rem / p.win_q_tiles, qt = rem - pt * p.win_q_tiles;
-          const int pl = l / p.win_box_q, ql = l - pl * p.win_box_q;
+          const int img = fastdiv(tc.m_blk, fd_win_img), rem = tc.m_blk - img * per_img;
+          const int pt = fastdiv(rem, fd_win_qt), qt = rem - pt * p.win_q_tiles;
+          const int pl = fastdiv(l, fd_win_bq), ql = l - pl * p.win_box_q;
           const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
           if (tile_exists && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
             my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
@@ -166,8 +189,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
             long long orow = row;
             if (p.out_mode == OUT_SCATTER) {
               const int pq = p.conv_P * p.conv_Q;
-              const int img = row / pq, rem = row - img * pq;
-              const int pp = rem / p.conv_Q, qq = rem - pp * p.conv_Q;
+              const int img = fastdiv(row, fd_pq), rem = row - img * pq;
+              const int pp = fastdiv(rem, fd_q), qq = rem - pp * p.conv_Q;
               orow = (static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox;
             }
             my_off = orow * p.ldd;
@@ -336,10 +359,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
               vals[it] = lds128(stage_u32 + rr * 128 + ((piece ^ (rr & 7)) << 4));
             }
             const int coff = c * 32;
+            // chunk base kept as ONE opaque 64-bit register: each store address is a single IMAD.WIDE (off32 * 4 + cb) instead of a
+            // 64-bit offset sum rebuilt per store (5 instructions each in the SASS of the previous form)
+            float* cb = wb + coff;
+            asm volatile("" : "+l"(cb));
             if (plain) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                if (FULL || off32[it] >= 0) *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = vals[it];
+                if (FULL || off32[it] >= 0) stg128(cb + off32[it], vals[it]);
             } else {
               float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
               if (e_bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(e_bias + col));
@@ -369,39 +396,48 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
                   cur[it].z = (nb & 4u) ? cur[it].z : 0.f; cur[it].w = (nb & 8u) ? cur[it].w : 0.f;
                 }
               }
+              const float2 al2 = make_float2(e_alpha, e_alpha), be2 = make_float2(e_beta, e_beta);
+              const float2 bva = make_float2(bv.x, bv.y), bvb = make_float2(bv.z, bv.w);
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 if (!FULL && off32[it] < 0) continue;
-                float4 o = vals[it];
-                o.x = e_alpha * o.x + bv.x; o.y = e_alpha * o.y + bv.y; o.z = e_alpha * o.z + bv.z; o.w = e_alpha * o.w + bv.w;
+                // alpha * acc + bias (+ beta * old) as packed fused multiply-adds: the roundings of the scalar fmaf forms
+                float2 oa = fma_f32x2(al2, make_float2(vals[it].x, vals[it].y), bva);
+                float2 ob = fma_f32x2(al2, make_float2(vals[it].z, vals[it].w), bvb);
                 if (use_beta) {
-                  o.x += e_beta * cur[it].x; o.y += e_beta * cur[it].y; o.z += e_beta * cur[it].z; o.w += e_beta * cur[it].w;
+                  oa = fma_f32x2(be2, make_float2(cur[it].x, cur[it].y), oa);
+                  ob = fma_f32x2(be2, make_float2(cur[it].z, cur[it].w), ob);
                 }
+                const float4 o = make_float4(oa.x, oa.y, ob.x, ob.y);
                 vals[it] = o;
-                *reinterpret_cast<float4*>(wb + (off32[it] + coff)) = o;
+                stg128(cb + off32[it], o);
               }
             }
             if (stats) {   // BatchNorm statistics of the values just stored (rows that exist only)
               const float4 sh = lds128(stat_u32 + (2 * BN + coff) * 4);
-              float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+              // packed fp32 pairs (FADD2 / FFMA2): d = v - shift, s1 += d, s2 = fma(d, d, s2) with the roundings of the scalar forms
+              const float2 sha = make_float2(sh.x, sh.y), shb = make_float2(sh.z, sh.w);
+              float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 if (!FULL && off32[it] < 0) continue;
-                const float dx = vals[it].x - sh.x, dy = vals[it].y - sh.y, dz = vals[it].z - sh.z, dw = vals[it].w - sh.w;
-                s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
-                s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+                const float2 da = sub_f32x2(make_float2(vals[it].x, vals[it].y), sha), db = sub_f32x2(make_float2(vals[it].z, vals[it].w), shb);
+                s1a = add_f32x2(s1a, da); s1b = add_f32x2(s1b, db);
+                s2a = fma_f32x2(da, da, s2a); s2b = fma_f32x2(db, db, s2b);
               }
 #pragma unroll
               for (int o = 8; o <= 16; o <<= 1) {
-                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+                s1a = add_f32x2(s1a, make_float2(__shfl_xor_sync(0xffffffffu, s1a.x, o), __shfl_xor_sync(0xffffffffu, s1a.y, o)));
+                s1b = add_f32x2(s1b, make_float2(__shfl_xor_sync(0xffffffffu, s1b.x, o), __shfl_xor_sync(0xffffffffu, s1b.y, o)));
+                s2a = add_f32x2(s2a, make_float2(__shfl_xor_sync(0xffffffffu, s2a.x, o), __shfl_xor_sync(0xffffffffu, s2a.y, o)));
+                s2b = add_f32x2(s2b, make_float2(__shfl_xor_sync(0xffffffffu, s2b.x, o), __shfl_xor_sync(0xffffffffu, s2b.y, o)));
               }
               if (sub_row == 0) {
                 const float4 t1 = lds128(stat_u32 + coff * 4), t2 = lds128(stat_u32 + (BN + coff) * 4);
-                sts128(stat_u32 + coff * 4, t1.x + s1.x, t1.y + s1.y, t1.z + s1.z, t1.w + s1.w);
-                sts128(stat_u32 + (BN + coff) * 4, t2.x + s2.x, t2.y + s2.y, t2.z + s2.z, t2.w + s2.w);
+                const float2 u1a = add_f32x2(make_float2(t1.x, t1.y), s1a), u1b = add_f32x2(make_float2(t1.z, t1.w), s1b);
+                const float2 u2a = add_f32x2(make_float2(t2.x, t2.y), s2a), u2b = add_f32x2(make_float2(t2.z, t2.w), s2b);
+                sts128(stat_u32 + coff * 4, u1a.x, u1a.y, u1b.x, u1b.y);
+                sts128(stat_u32 + (BN + coff) * 4, u2a.x, u2a.y, u2b.x, u2b.y);
               }
             }
           } else {   // ragged chunk or unaligned output: element-wise (kept out of registers: rare path)
@@ -515,6 +551,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int total_tiles = (p.m_tiles / CL) * p.n_tiles * p.tap_tiles * p.splits;
   const int cl_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
+  const TileDiv tdiv = make_tile_div(p, CL);
   const bool a_mn = (p.a_mode == A_TILED_MN);
   const bool b_mn = (p.b_mode != B_TILED_K);
 
@@ -525,7 +562,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       const int pq = p.conv_P * p.conv_Q;
       for (int tile = w_first; tile < total_tiles; tile += w_step) {
-        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank) : decode_tile(p, tile);
+        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank, tdiv) : decode_tile(p, tile, tdiv);
         const int m0 = tc.m_blk * kUmmaBM, n0 = tc.n_blk * BN;
         int kb_begin, kb_end;
         tile_kb_range(p, tc, kb_begin, kb_end);
@@ -662,7 +699,7 @@ umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = w_first; tile < total_tiles; tile += w_step) {
-        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank) : decode_tile(p, tile);
+        const TileCoord tc = CL > 1 ? decode_tile_cluster(p, tile, CL, cl_rank, tdiv) : decode_tile(p, tile, tdiv);
         int kb_begin, kb_end;
         tile_kb_range(p, tc, kb_begin, kb_end);
         bool ok = true;
