@@ -194,6 +194,22 @@ int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, i
                      const void* dy, const void* scale, const void* bias, const void* saved_mean,
                      const void* saved_inv_std, void* dx, void* dscale, void* dbias);
 
+/* Network stem: BatchNorm2d(train) + ReLU + max_pool2d(3x3, stride 2, pad 1) as one pass each way, NHWC f32.  Results of the
+ * forward (pooled values, winner codes in the zb_maxpool2d_fwd_idx format, running / saved statistics) are those of
+ * zb_bn2d_fwd_train_fused(relu = 1) followed by zb_maxpool2d_fwd_idx, without writing the BatchNorm output; the backward equals
+ * zb_maxpool2d_bwd_idx followed by zb_bn2d_relu_bwd without materialising the un-pooled gradient.  Replaces the node sequence
+ * batch_norm_2d -> relu -> max_pool_2d of zenu-autograd (src/nn/batch_norm.rs:107-119, src/activation/relu.rs,
+ * src/nn/pool2d.rs:149-201).  ZB_ERR_UNSUPPORTED for other windows / dtypes / layouts or when C / 4 is not a power of two <= 256:
+ * the caller composes the separate entry points then.  stat_partial / stat_rows / shift: as zb_bn2d_fwd_train_fused (NULL / 0 /
+ * NULL: statistics are reduced here). */
+int zb_bn2d_relu_maxpool_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k,
+                                   int64_t stride, int64_t pad, double momentum, const void* x, const void* scale, const void* bias,
+                                   void* running_mean, void* running_var, void* saved_mean, void* saved_inv_std, void* y_pool,
+                                   void* pool_idx, const void* stat_partial, int64_t stat_rows, const void* shift);
+int zb_bn2d_relu_maxpool_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k, int64_t stride,
+                             int64_t pad, const void* x, const void* dy_pool, const void* pool_idx, const void* scale, const void* bias,
+                             const void* saved_mean, const void* saved_inv_std, void* dx, void* dscale, void* dbias);
+
 /* ---- GEMM / Linear ------------------------------------------------------------------------------
  * Replaces Gemm::gemm_unchecked (zenu-matrix/src/operation/mul.rs:12-29,113-147 -> cublas{S,D}gemm_v2_64,
  * zenu-cuda/src/cublas/mod.rs:84-160).  Row-major: C[m,n] = alpha*op(A)*op(B) + beta*C. */

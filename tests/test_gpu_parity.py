@@ -634,6 +634,71 @@ def test_maxpool_indexed(zb, ctx):
         np.testing.assert_allclose(nchw(host(dx)), dx_ref, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape,prestats", [((3, 64, 12, 10), False), ((2, 16, 9, 11), False), ((4, 64, 16, 16), True), ((2, 256, 6, 8), False)])
+def test_bn_relu_maxpool_fused_stem(zb, ctx, shape, prestats):
+    """zb_bn2d_relu_maxpool_fwd_train / _bwd (the ResNet stem as one pass each way) against (a) the separate entry points they replace
+    - forward bit for bit (pooled values, winner codes, saved and running statistics), backward to rounding (other summation order) -
+    and (b) the oracle's batch_norm -> relu -> max_pool nodes (zenu-matrix/src/nn/batch_norm.rs:283-420, nn/pool2d semantics:
+    zero padding takes part, first max wins).  Odd and even extents; statistics reduced here or handed over by the conv epilogue."""
+    from zenu_b200 import ZB_MATH_TF32, ZB_NHWC
+    rng = np.random.default_rng(sum(shape))
+    n, c, h, w = shape
+    x = (rng.standard_normal(shape) * 1.3 + 0.2).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, c).astype(np.float32) * np.where(rng.random(c) < 0.2, -1.0, 1.0).astype(np.float32)
+    bias = (0.3 * rng.standard_normal(c)).astype(np.float32)
+    X, S, B = dev(nhwc(x)), dev(scale), dev(bias)
+    kw = {}
+    if prestats:   # statistics from a conv epilogue: a 1x1 identity conv reproduces x and hands its partial sums over
+        eye = dev(np.eye(c, dtype=np.float32).reshape(c, 1, 1, c))
+        shift = dev((0.05 * rng.standard_normal(c)).astype(np.float32))
+        xs, partial, rows = zb.conv_fwd_bnstats(ctx, X, eye, shift, pad=0, stride=1, dil=1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+        assert rows > 0
+        X = xs
+        x = nchw(host(X))
+        kw = dict(stat_partial=partial, stat_rows=rows, shift=shift)
+    rm1, rv1 = dev(np.zeros(c, np.float32)), dev(np.ones(c, np.float32))
+    yp, idx, sm, si = zb.batch_norm_relu_max_pool_forward_train(ctx, 0.9, X, S, B, rm1, rv1, **kw)
+    # (a) the separate entry points
+    rm2, rv2 = dev(np.zeros(c, np.float32)), dev(np.ones(c, np.float32))
+    if prestats:
+        y2, sm2, si2 = zb.batch_norm_2d_forward_train_prestats(ctx, 0.9, X, S, B, rm2, rv2, partial, rows, shift, relu=True)
+    else:
+        y2, sm2, si2 = zb.batch_norm_2d_forward_train(ctx, 0.9, X, S, B, rm2, rv2, layout=ZB_NHWC, relu=True)
+    yp2, idx2 = zb.max_pool_2d_indexed(ctx, y2, 3, 2, 1)
+    for a, b in ((yp, yp2), (idx, idx2), (sm, sm2), (si, si2), (rm1, rm2), (rv1, rv2)):
+        np.testing.assert_array_equal(host(a), host(b))
+    dyp = rng.standard_normal(tuple(yp.shape)).astype(np.float32)
+    DYP = dev(dyp)
+    dx, ds, db = zb.batch_norm_relu_max_pool_backward(ctx, X, DYP, idx, S, B, sm, si)
+    dy2 = zb.max_pool_2d_indexed_backward(ctx, DYP, idx2, tuple(y2.shape), 3, 2, 1)
+    dx2, ds2, db2 = zb.batch_norm_2d_relu_backward(ctx, X, dy2, S, B, sm2, si2, layout=ZB_NHWC)
+    assert rel_err(host(dx), host(dx2)) < 2e-5 and rel_err(host(ds), host(ds2)) < 2e-5 and rel_err(host(db), host(db2)) < 2e-5
+    # (b) the oracle's separate nodes
+    bn_ref, _, _, sm_ref, si_ref = zo.bn2d_fwd_train(x, scale, bias, np.zeros(c, np.float32), np.ones(c, np.float32), 0.9)
+    act = zo.relu(bn_ref)
+    yp_ref = zo.maxpool2d_fwd(act, 3, 2, 1)
+    assert rel_err(nchw(host(yp)), yp_ref) < 2e-5
+    g_act = zo.maxpool2d_bwd(act, nchw(dyp), 3, 2, 1)
+    g_bn = zo.ewise("mul", g_act, (bn_ref > 0).astype(np.float32))
+    dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x, g_bn, scale, sm_ref, si_ref)
+    assert rel_err(nchw(host(dx)), dx_ref) < 2e-4 and rel_err(host(ds), ds_ref) < 2e-4 and rel_err(host(db), db_ref) < 2e-4
+    ctx.check()
+
+
+def test_bn_relu_maxpool_unsupported_geometries(zb, ctx):
+    """Anything but f32 NHWC 3x3 / 2 / 1 with C / 4 a power of two reports ZB_ERR_UNSUPPORTED (the caller composes the separate calls)."""
+    from zenu_b200 import ZenuB200Error
+    x = torch.randn((2, 6, 6, 24), device="cuda")   # C / 4 = 6: not a power of two
+    c = 24
+    args = (dev(np.ones(c, np.float32)), dev(np.zeros(c, np.float32)), dev(np.zeros(c, np.float32)), dev(np.ones(c, np.float32)))
+    with pytest.raises(ZenuB200Error):
+        zb.batch_norm_relu_max_pool_forward_train(ctx, 0.9, x, *args)
+    x = torch.randn((2, 6, 6, 16), device="cuda")
+    args = tuple(dev(a) for a in (np.ones(16, np.float32), np.zeros(16, np.float32), np.zeros(16, np.float32), np.ones(16, np.float32)))
+    with pytest.raises(ZenuB200Error):
+        zb.batch_norm_relu_max_pool_forward_train(ctx, 0.9, x, *args, kernel=2, stride=2, pad=0)
+
+
 # ------------------------------------------------------------------------------------------------ elementwise / pool / loss / optim
 def test_elementwise_vs_oracle(zb, ctx):
     rng = np.random.default_rng(5)

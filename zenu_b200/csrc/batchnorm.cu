@@ -800,6 +800,250 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
   return rc;
 }
 
+
+// ---- network stem: BatchNorm + ReLU + 3x3 / stride 2 / pad 1 max-pool as ONE pass each way (NHWC f32) ----------------------------
+// The stem's BatchNorm output is the largest activation of a ResNet (256 x 112 x 112 x 64 f32 = 822 MB at batch 256) and the only
+// thing that reads it is the max-pool.  Forward: every pooled output normalises its 9 taps from x on the fly (the values, the
+// first-max tie rule and the "a padding zero won" code 255 are exactly those of zb_bn2d_fwd_train(relu) followed by
+// zb_maxpool2d_fwd_idx), so the BN output is never written or re-read.  Backward: the gradient of the BN output is the max-pool's
+// gather over the <= 4 windows that cover a pixel; both BN-backward passes (statistics, then dx) rebuild it per 2 x 2 input patch
+// from the pooled gradient and the winner codes (4 window reads per 4 pixels, L2-resident: they are 1/4 + 1/16 of the tensor)
+// instead of reading an 822 MB dy that a separate max-pool backward would first have to write.  ReLU mask: recomputed from x
+// (bn_affine(x) > 0), as in zb_bn2d_relu_bwd.
+// Forward thread = (pooled output, 4 channels), nine independent 128-bit loads in flight.  (A sliding-window form that carries the
+// column two neighbouring windows share - 6 taps normalised per output instead of 9 - measured SLOWER: 0.63 vs 0.37 ms on the
+// 256 x 112 x 112 x 64 stem, 99 registers and a serial walk per thread against 48 registers and 5 resident blocks per SM here.)
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ coef,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ y, uchar4* __restrict__ idx, int N, int H, int W,
+                                                               int C, int P, int Q) {
+  const int c4n = C >> 2;
+  const int total = N * P * Q * c4n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = i % c4n;
+    int t = i / c4n;
+    const int q = t % Q; t /= Q;
+    const int p = t % P;
+    const int n = t / P;
+    const float4 m = __ldg(reinterpret_cast<const float4*>(coef) + c4), iv = __ldg(reinterpret_cast<const float4*>(coef + C) + c4);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const float* xb = x + static_cast<long long>(n) * H * W * C + c4 * 4;
+    float best[4];
+    unsigned char bi[4];
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = p * 2 + r - 1;
+#pragma unroll
+      for (int s_ = 0; s_ < 3; ++s_) {
+        const int iw = q * 2 + s_ - 1;
+        const bool oob = ih < 0 || ih >= H || iw < 0 || iw >= W;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!oob) {
+          const float4 vv = *reinterpret_cast<const float4*>(xb + (static_cast<long long>(ih) * W + iw) * C);
+          v[0] = bn_affine(vv.x, m.x, iv.x, g.x, b.x); v[1] = bn_affine(vv.y, m.y, iv.y, g.y, b.y);
+          v[2] = bn_affine(vv.z, m.z, iv.z, g.z, b.z); v[3] = bn_affine(vv.w, m.w, iv.w, g.w, b.w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.f;
+        }
+        const unsigned char tap = oob ? 255 : static_cast<unsigned char>(r * 3 + s_);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (first || v[e] > best[e]) { best[e] = v[e]; bi[e] = tap; }
+        first = false;
+      }
+    }
+    *reinterpret_cast<float4*>(y + static_cast<long long>(i) * 4) = make_float4(best[0], best[1], best[2], best[3]);
+    idx[i] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
+// APPLY = false: per-block partial sums [block][2][C] of g and g * xhat (g = ReLU-masked gathered gradient); APPLY = true: dx.
+// Thread = (2 x 2 input patch (2a.., 2b..), 4 channels); the channel group of a thread is fixed (256 % (C / 4) == 0), so its sums stay
+// in registers.  3x3 / 2 / 1 windows: the patch is covered by windows (a, b), (a, b+1), (a+1, b), (a+1, b+1) and its pixels sit at
+// fixed taps of each: (0,0) <- code 4 of w00; (0,1) <- 5 of w00, 3 of w01; (1,0) <- 7 of w00, 1 of w10; (1,1) <- 8 of w00, 6 of w01,
+// 2 of w10, 0 of w11 (added in zb_maxpool2d_bwd_idx's order).  All twelve loads of a patch are issued before any is used.
+template <bool APPLY>
+__global__ void __launch_bounds__(256, 3) bn_relu_pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dyp,
+                                                                  const uchar4* __restrict__ idx, const float* __restrict__ mean,
+                                                                  const float* __restrict__ inv, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, const float* __restrict__ coef,
+                                                                  float* __restrict__ dx, float* __restrict__ partial, int N, int H,
+                                                                  int W, int C, int P, int Q) {
+  __shared__ float red[APPLY ? 1 : 2][APPLY ? 1 : 256][4];
+  const int c4n = C >> 2, G = 256 / c4n;
+  const int c4 = threadIdx.x % c4n, grp = threadIdx.x / c4n;
+  const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+  const int patches = N * H2 * W2;
+  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean) + c4), iv4 = __ldg(reinterpret_cast<const float4*>(inv) + c4);
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  const float m[4] = {m4.x, m4.y, m4.z, m4.w}, iv[4] = {iv4.x, iv4.y, iv4.z, iv4.w};
+  const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+  float k0[4] = {0.f, 0.f, 0.f, 0.f}, k1[4] = {0.f, 0.f, 0.f, 0.f}, k2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (APPLY) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(coef) + c4), b = __ldg(reinterpret_cast<const float4*>(coef + C) + c4);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(coef + 2 * C) + c4);
+    k0[0] = a.x; k0[1] = a.y; k0[2] = a.z; k0[3] = a.w;
+    k1[0] = b.x; k1[1] = b.y; k1[2] = b.z; k1[3] = b.w;
+    k2[0] = c.x; k2[1] = c.y; k2[2] = c.z; k2[3] = c.w;
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int pi = blockIdx.x * G + grp; pi < patches; pi += gridDim.x * G) {
+    const int bq = pi % W2;
+    int t = pi / W2;
+    const int a = t % H2;
+    const int n = t / H2;
+    const int h0 = 2 * a, w0 = 2 * bq;
+    const bool row1 = h0 + 1 < H, col1 = w0 + 1 < W;          // the patch's second row / column exists
+    const bool win_p0 = a < P, win_q0 = bq < Q;               // (odd H: the last patch row can lie below the last window)
+    const bool win_p1 = a + 1 < P, win_q1 = bq + 1 < Q;
+    const float* xp = x + ((static_cast<long long>(n) * H + h0) * W + w0) * C + c4 * 4;
+    const long long rs = static_cast<long long>(W) * C;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 x00 = *reinterpret_cast<const float4*>(xp);
+    const float4 x01 = col1 ? *reinterpret_cast<const float4*>(xp + C) : zero4;
+    const float4 x10 = row1 ? *reinterpret_cast<const float4*>(xp + rs) : zero4;
+    const float4 x11 = (row1 && col1) ? *reinterpret_cast<const float4*>(xp + rs + C) : zero4;
+    const int pa = win_p0 ? a : P - 1, pb = win_p1 ? a + 1 : P - 1, qa = win_q0 ? bq : Q - 1, qb = win_q1 ? bq + 1 : Q - 1;
+    const int o00 = ((n * P + pa) * Q + qa) * c4n + c4, o01 = ((n * P + pa) * Q + qb) * c4n + c4;
+    const int o10 = ((n * P + pb) * Q + qa) * c4n + c4, o11 = ((n * P + pb) * Q + qb) * c4n + c4;
+    const uchar4 i00 = __ldg(idx + o00), i01 = __ldg(idx + o01), i10 = __ldg(idx + o10), i11 = __ldg(idx + o11);
+    const float4 d00 = __ldg(reinterpret_cast<const float4*>(dyp) + o00), d01 = __ldg(reinterpret_cast<const float4*>(dyp) + o01);
+    const float4 d10 = __ldg(reinterpret_cast<const float4*>(dyp) + o10), d11 = __ldg(reinterpret_cast<const float4*>(dyp) + o11);
+    const bool v00 = win_p0 && win_q0, v01 = win_p0 && win_q1, v10 = win_p1 && win_q0, v11 = win_p1 && win_q1;
+    const unsigned char w00[4] = {i00.x, i00.y, i00.z, i00.w}, w01[4] = {i01.x, i01.y, i01.z, i01.w};
+    const unsigned char w10[4] = {i10.x, i10.y, i10.z, i10.w}, w11[4] = {i11.x, i11.y, i11.z, i11.w};
+    const float g00[4] = {d00.x, d00.y, d00.z, d00.w}, g01[4] = {d01.x, d01.y, d01.z, d01.w};
+    const float g10[4] = {d10.x, d10.y, d10.z, d10.w}, g11[4] = {d11.x, d11.y, d11.z, d11.w};
+    float acc[2][2][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[0][0][e] = (v00 && w00[e] == 4) ? g00[e] : 0.f;
+      float t01 = (v00 && w00[e] == 5) ? g00[e] : 0.f;
+      if (v01 && w01[e] == 3) t01 += g01[e];
+      acc[0][1][e] = t01;
+      float t10 = (v00 && w00[e] == 7) ? g00[e] : 0.f;
+      if (v10 && w10[e] == 1) t10 += g10[e];
+      acc[1][0][e] = t10;
+      float t11 = (v00 && w00[e] == 8) ? g00[e] : 0.f;
+      if (v01 && w01[e] == 6) t11 += g01[e];
+      if (v10 && w10[e] == 2) t11 += g10[e];
+      if (v11 && w11[e] == 0) t11 += g11[e];
+      acc[1][1][e] = t11;
+    }
+    const float4 xv[2][2] = {{x00, x01}, {x10, x11}};
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy) {
+#pragma unroll
+      for (int xx = 0; xx < 2; ++xx) {
+        const bool exists = (yy == 0 || row1) && (xx == 0 || col1);
+        const float xs[4] = {xv[yy][xx].x, xv[yy][xx].y, xv[yy][xx].z, xv[yy][xx].w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool keep = exists && bn_affine(xs[e], m[e], iv[e], ga[e], be[e]) > 0.f;
+          const float gg = keep ? acc[yy][xx][e] : 0.f;
+          const float xh = (xs[e] - m[e]) * iv[e];
+          if (APPLY) o[e] = k0[e] * (gg - k1[e] - xh * k2[e]);
+          else { s1[e] += gg; s2[e] += gg * xh; }
+        }
+        if (APPLY && exists) *reinterpret_cast<float4*>(dx + (xp - x) + yy * rs + xx * C) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[0][threadIdx.x][e] = s1[e]; red[1][threadIdx.x][e] = s2[e]; }
+    __syncthreads();
+    for (int half = G >> 1; half > 0; half >>= 1) {
+      if (grp < half) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          red[0][threadIdx.x][e] += red[0][threadIdx.x + half * c4n][e];
+          red[1][threadIdx.x][e] += red[1][threadIdx.x + half * c4n][e];
+        }
+      }
+      __syncthreads();
+    }
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        partial[(static_cast<long long>(blockIdx.x) * 2 + 0) * C + c4 * 4 + e] = red[0][threadIdx.x][e];
+        partial[(static_cast<long long>(blockIdx.x) * 2 + 1) * C + c4 * 4 + e] = red[1][threadIdx.x][e];
+      }
+    }
+  }
+}
+
+static bool bn_pool_supported(long long N, long long C, long long H, long long W) {
+  const long long c4n = C / 4;
+  return C % 4 == 0 && c4n >= 1 && c4n <= 256 && 256 % c4n == 0 && H >= 2 && W >= 2 && N * (H + 1) * (W + 1) * C < (1ll << 31) - (1ll << 24);
+}
+
+static int bn_relu_pool_fwd_f32(zb_ctx* ctx, long long N, long long C, long long H, long long W, double momentum, const float* x,
+                                const float* scale, const float* bias, float* run_mean, float* run_var, float* saved_mean,
+                                float* saved_inv, float* y_pool, void* idx, const float* pre_partial, int pre_rows, const float* pre_shift) {
+  const long long P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1, HW = H * W;
+  const long long ms = max_slabs(ctx, ZB_NHWC, N, C);
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(float) * (ms * 2 * C + 2 * C), &ws);
+  if (rc != ZB_OK) return rc;
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + ms * 2 * C;
+  prof_begin(ctx, PROF_BN);
+  if (pre_partial != nullptr) {
+    bn_fwd_finalize<float><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(pre_partial, pre_rows, C, static_cast<double>(N * HW), momentum, ctx->bn_eps,
+                                                                   pre_shift, 1, run_mean, run_var, saved_mean, saved_inv, coef);
+    ZB_LAUNCH_CHECK(ctx);
+  } else {
+    int slabs = 0;
+    rc = run_col_reduce<float, StatsFT>(ctx, ZB_NHWC, N, C, HW, x, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+                                        partial, ms * 2 * C, [&](auto& f) { f.x0 = x; f.sstride = 1; }, &slabs);
+    if (rc != ZB_OK) return rc;
+    bn_fwd_finalize<float><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), momentum, ctx->bn_eps, x, 1,
+                                                                   run_mean, run_var, saved_mean, saved_inv, coef);
+    ZB_LAUNCH_CHECK(ctx);
+  }
+  const long long total = N * P * Q * (C / 4);
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll)));
+  bn_relu_pool_fwd_kernel<<<grid, 256, 0, ctx->stream>>>(x, coef, scale, bias, y_pool, static_cast<uchar4*>(idx), static_cast<int>(N),
+                                                         static_cast<int>(H), static_cast<int>(W), static_cast<int>(C), static_cast<int>(P),
+                                                         static_cast<int>(Q));
+  ZB_LAUNCH_CHECK(ctx);
+  // algorithmic bytes: x read (twice when the statistics did not come with the conv), pooled output + winner codes written
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * 4.0 * (pre_partial ? 1.0 : 2.0) + static_cast<double>(N * C * P * Q) * 5.0);
+  return ZB_OK;
+}
+
+static int bn_relu_pool_bwd_f32(zb_ctx* ctx, long long N, long long C, long long H, long long W, const float* x, const float* dyp,
+                                const void* idx, const float* scale, const float* bias, const float* mean, const float* inv, float* dx,
+                                float* dscale, float* dbias) {
+  const long long P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const long long ms = ctx->sm_count * 8ll;
+  void* ws = nullptr;
+  int rc = ctx_workspace(ctx, sizeof(float) * (ms * 2 * C + 3 * C), &ws);
+  if (rc != ZB_OK) return rc;
+  float* partial = static_cast<float*>(ws);
+  float* coef = partial + ms * 2 * C;
+  const int G = static_cast<int>(256 / (C / 4));
+  const long long patches = N * ((H + 1) / 2) * ((W + 1) / 2);
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((patches + G - 1) / G, ms)));
+  prof_begin(ctx, PROF_BN);
+  bn_relu_pool_bwd_kernel<false><<<grid, 256, 0, ctx->stream>>>(x, dyp, static_cast<const uchar4*>(idx), mean, inv, scale, bias, nullptr, nullptr,
+                                                                partial, static_cast<int>(N), static_cast<int>(H), static_cast<int>(W),
+                                                                static_cast<int>(C), static_cast<int>(P), static_cast<int>(Q));
+  ZB_LAUNCH_CHECK(ctx);
+  bn_bwd_finalize<float><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, grid, C, static_cast<double>(N * H * W), scale, inv, dscale, dbias, coef);
+  ZB_LAUNCH_CHECK(ctx);
+  bn_relu_pool_bwd_kernel<true><<<grid, 256, 0, ctx->stream>>>(x, dyp, static_cast<const uchar4*>(idx), mean, inv, scale, bias, coef, dx, nullptr,
+                                                               static_cast<int>(N), static_cast<int>(H), static_cast<int>(W),
+                                                               static_cast<int>(C), static_cast<int>(P), static_cast<int>(Q));
+  ZB_LAUNCH_CHECK(ctx);
+  // algorithmic bytes: x read twice, dx written, pooled gradient + winner codes read twice
+  prof_end(ctx, PROF_BN, static_cast<double>(N * C * H * W) * 4.0 * 3.0 + static_cast<double>(N * C * P * Q) * 2.0 * 5.0);
+  return ZB_OK;
+}
+
 // out[c] = sum over (n, hw) of a — conv bias gradient / Matrix::sum(axis 0) on a [rows][cols] matrix (NHWC, HW = 1)
 template <typename T>
 int channel_sum(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* a, T* out) {
@@ -941,6 +1185,47 @@ int zb_bn2d_relu_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, i
                             static_cast<double*>(dbias), nullptr, nullptr, static_cast<const double*>(bias));
   zb::set_last_error("unknown dtype %d", dtype);
   return ZB_ERR_INVALID;
+}
+
+static int check_bn_pool(int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k, int64_t stride, int64_t pad) {
+  ZB_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "bn + max-pool: empty tensor");
+  if (dtype != ZB_F32 || layout != ZB_NHWC || k != 3 || stride != 2 || pad != 1 || !bn_pool_supported(n, c, h, w)) {
+    zb::set_last_error("bn + relu + max-pool: served for f32 NHWC, 3x3 / stride 2 / pad 1 windows and C / 4 a power of two <= 256");
+    return ZB_ERR_UNSUPPORTED;
+  }
+  return ZB_OK;
+}
+
+int zb_bn2d_relu_maxpool_fwd_train(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k,
+                                   int64_t stride, int64_t pad, double momentum, const void* x, const void* scale, const void* bias,
+                                   void* running_mean, void* running_var, void* saved_mean, void* saved_inv_std, void* y_pool,
+                                   void* pool_idx, const void* stat_partial, int64_t stat_rows, const void* shift) {
+  ZB_API_RANGE();
+  const int rc = check_bn_pool(dtype, layout, n, c, h, w, k, stride, pad);
+  if (rc != ZB_OK) return rc;
+  ZB_REQUIRE(x && scale && bias && y_pool && pool_idx, "bn + relu + max-pool: null argument");
+  ZB_REQUIRE(al16(x) && al16(y_pool) && al16(scale) && al16(bias), "bn + relu + max-pool: tensors must be 16-byte aligned");
+  ZB_REQUIRE(stat_partial == nullptr || (shift != nullptr && stat_rows > 0 && stat_rows < (1 << 30)), "bn + relu + max-pool: bad statistics");
+  return bn_relu_pool_fwd_f32(ctx, n, c, h, w, momentum, static_cast<const float*>(x), static_cast<const float*>(scale),
+                              static_cast<const float*>(bias), static_cast<float*>(running_mean), static_cast<float*>(running_var),
+                              static_cast<float*>(saved_mean), static_cast<float*>(saved_inv_std), static_cast<float*>(y_pool), pool_idx,
+                              static_cast<const float*>(stat_partial), static_cast<int>(stat_rows), static_cast<const float*>(shift));
+}
+
+int zb_bn2d_relu_maxpool_bwd(zb_ctx* ctx, int dtype, int layout, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k, int64_t stride,
+                             int64_t pad, const void* x, const void* dy_pool, const void* pool_idx, const void* scale, const void* bias,
+                             const void* saved_mean, const void* saved_inv_std, void* dx, void* dscale, void* dbias) {
+  ZB_API_RANGE();
+  const int rc = check_bn_pool(dtype, layout, n, c, h, w, k, stride, pad);
+  if (rc != ZB_OK) return rc;
+  ZB_REQUIRE(x && dy_pool && pool_idx && scale && bias && saved_mean && saved_inv_std && dx && dscale && dbias,
+             "bn + relu + max-pool backward: null argument");
+  ZB_REQUIRE(al16(x) && al16(dy_pool) && al16(dx) && al16(scale) && al16(bias) && al16(saved_mean) && al16(saved_inv_std),
+             "bn + relu + max-pool backward: tensors must be 16-byte aligned");
+  return bn_relu_pool_bwd_f32(ctx, n, c, h, w, static_cast<const float*>(x), static_cast<const float*>(dy_pool), pool_idx,
+                              static_cast<const float*>(scale), static_cast<const float*>(bias), static_cast<const float*>(saved_mean),
+                              static_cast<const float*>(saved_inv_std), static_cast<float*>(dx), static_cast<float*>(dscale),
+                              static_cast<float*>(dbias));
 }
 
 int zb_conv2d_bias_bwd(zb_ctx* ctx, int dtype, int layout, const void* dy, void* dbias, int64_t n, int64_t k, int64_t h,

@@ -55,7 +55,8 @@ Runtime::Runtime(zb_ctx* c) : ctx(c), alloc(c) {
   // than the off-path wgrad gains.
   static const bool on = []() { const char* e = getenv("ZENU_B200_WGRAD_OVERLAP"); return e != nullptr && e[0] == '1'; }();
   overlap_wgrad = on && zb_ctx_side(c) != nullptr;
-  lazy_mask = getenv("ZENU_B200_NO_LAZY_MASK") == nullptr;   // read per Runtime (not cached): tests build models both ways
+  lazy_mask = getenv("ZENU_B200_NO_LAZY_MASK") == nullptr;
+  fuse_stem_pool = getenv("ZENU_B200_NO_STEM_POOL_FUSION") == nullptr;   // read per Runtime (not cached): tests build models both ways
 }
 
 void Runtime::join_side() {
@@ -604,6 +605,66 @@ Variable max_pool_2d(Runtime& rt, const Variable& x, int64_t k, int64_t stride, 
   return make_output(y, fn);
 }
 
+// BatchNorm2d(train) + ReLU + max_pool_2d(3, 2, 1) as one node (the ResNet stem): the BN output, the largest activation of the
+// network, is neither written nor read back; backward gathers the pooled gradient inside both BN-backward passes
+// (zb_bn2d_relu_maxpool_fwd_train / _bwd).  Same results as the three separate nodes.
+struct BnReluPoolFn : Function {
+  Tensor x, idx, scale, bias, saved_mean, saved_inv;
+  int64_t n, c, h, w;
+  const char* name() const override { return "batch_norm_2d+relu+max_pool_2d"; }
+  void backward(Runtime& rt, const Tensor& gy) override {
+    VariableInner& xv = *inputs[0];
+    Tensor dx = grad_target(rt, xv);
+    Tensor ds = grad_target(rt, *inputs[1]);
+    Tensor db = grad_target(rt, *inputs[2]);
+    ProfScope ps(rt, "bn.bwd+relu+maxpool " + shape_str(x.shape), 0.0, 3.0 * x.bytes() + 2.0 * (gy.bytes() + gy.numel()));
+    check_rc(zb_bn2d_relu_maxpool_bwd(rt.ctx, gy.dtype, ZB_NHWC, n, c, h, w, 3, 2, 1, x.ptr, gy.ptr, idx.ptr, scale.ptr, bias.ptr,
+                                      saved_mean.ptr, saved_inv.ptr, dx.ptr, ds.ptr, db.ptr), "bn + relu + maxpool bwd");
+    commit_grad(rt, xv, dx);
+    commit_grad(rt, *inputs[1], ds);
+    commit_grad(rt, *inputs[2], db);
+    x = Tensor();
+    idx = Tensor();
+  }
+};
+
+bool batch_norm_relu_max_pool_fusable(Runtime& rt, const Variable& x, int64_t k, int64_t stride, int64_t pad) {
+  const auto& s = x.shape();
+  if (!rt.train || !rt.fuse_stem_pool || rt.dtype != ZB_F32 || s.size() != 4 || k != 3 || stride != 2 || pad != 1) return false;
+  const int64_t c4 = s[3] / 4;
+  return s[3] % 4 == 0 && c4 >= 1 && c4 <= 256 && (256 % c4) == 0 && s[1] >= 2 && s[2] >= 2 &&
+         s[0] * (s[1] + 1) * (s[2] + 1) * s[3] < (1ll << 31) - (1ll << 24);
+}
+
+Variable batch_norm_relu_max_pool(Runtime& rt, const Variable& x, const Variable& scale, const Variable& bias, const Variable& mean,
+                                  const Variable& variance, double momentum) {
+  const auto& s = x.shape();
+  const int64_t n = s[0], h = s[1], w = s[2], c = s[3];
+  const int64_t P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
+  Tensor y = rt.empty({n, P, Q, c});
+  auto fn = std::make_shared<BnReluPoolFn>();
+  fn->saved_mean = rt.empty({c});
+  fn->saved_inv = rt.empty({c});
+  fn->idx = rt.empty({(y.numel() + 3) / 4});   // one byte per pooled element
+  const bool have_stats = x->bn_stat_rows > 0 && x->bn_shift == mean->data.ptr;
+  {
+    ProfScope ps(rt, "bn.fwd+relu+maxpool " + shape_str(s), 0.0,
+                 static_cast<double>(x->data.bytes()) * (have_stats ? 1.0 : 2.0) + static_cast<double>(y.bytes()) + y.numel());
+    check_rc(zb_bn2d_relu_maxpool_fwd_train(rt.ctx, y.dtype, ZB_NHWC, n, c, h, w, 3, 2, 1, momentum, x->data.ptr, scale->data.ptr,
+                                            bias->data.ptr, mean->data.ptr, variance->data.ptr, fn->saved_mean.ptr, fn->saved_inv.ptr,
+                                            y.ptr, fn->idx.ptr, have_stats ? x->bn_stats.ptr : nullptr, have_stats ? x->bn_stat_rows : 0,
+                                            have_stats ? x->bn_shift : nullptr), "bn + relu + maxpool fwd");
+  }
+  x->bn_stats = Tensor();
+  x->bn_stat_rows = 0;
+  fn->inputs = {x.ptr(), scale.ptr(), bias.ptr()};
+  fn->x = x->data;
+  fn->scale = scale->data;
+  fn->bias = bias->data;
+  fn->n = n; fn->c = c; fn->h = h; fn->w = w;
+  return make_output(y, fn);
+}
+
 struct GapFn : Function {
   int64_t n, c, hw;
   const char* name() const override { return "global_avg_pool"; }
@@ -881,8 +942,12 @@ struct ResNet : Model {
   }
   Variable call(Runtime& rt, const Variable& x) override {
     Variable h = conv1->call(rt, x);
-    h = fused ? bn1->call_fused(rt, h, nullptr, true) : relu(rt, bn1->call(rt, h));
-    h = max_pool_2d(rt, h, 3, 2, 1);
+    if (fused && batch_norm_relu_max_pool_fusable(rt, h, 3, 2, 1)) {
+      h = batch_norm_relu_max_pool(rt, h, bn1->scale, bn1->bias, bn1->mean, bn1->variance, bn1->momentum);
+    } else {
+      h = fused ? bn1->call_fused(rt, h, nullptr, true) : relu(rt, bn1->call(rt, h));
+      h = max_pool_2d(rt, h, 3, 2, 1);
+    }
     for (auto& b : blocks) h = b.second->call(rt, h);
     h = global_avg_pool(rt, h);
     return fc->call(rt, h);

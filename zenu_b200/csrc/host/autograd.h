@@ -94,6 +94,8 @@ struct Runtime {  // one per model: ctx + allocator + train flag (reference: glo
   // fused BN + add + ReLU backward hands its residual gradient on as (gy, ReLU bits) instead of writing gy (.) bits out; the consumer
   // (the next dgrad's accumulate epilogue, or a downsample BN's backward) masks as it reads.  ZENU_B200_NO_LAZY_MASK=1 turns it off.
   bool lazy_mask = true;
+  // the ResNet stem's BatchNorm + ReLU + max-pool run as one node (ZENU_B200_NO_STEM_POOL_FUSION=1: three nodes)
+  bool fuse_stem_pool = true;
   bool side_pending = false;
   std::vector<Tensor> side_hold;
   void join_side();
@@ -181,6 +183,10 @@ Variable conv2d(Runtime& rt, const Variable& x, const Variable& w, const Variabl
 // BatchNorm2d with optional fused residual add and ReLU; running stats updated in place when training
 Variable batch_norm_2d(Runtime& rt, const Variable& x, const Variable& scale, const Variable& bias, const Variable& mean,
                        const Variable& variance, double momentum, const Variable* residual, bool relu);
+// BatchNorm2d(train) + ReLU + max_pool_2d(k, stride, pad) as one node where zb_bn2d_relu_maxpool_* serves the geometry
+bool batch_norm_relu_max_pool_fusable(Runtime& rt, const Variable& x, int64_t k, int64_t stride, int64_t pad);
+Variable batch_norm_relu_max_pool(Runtime& rt, const Variable& x, const Variable& scale, const Variable& bias, const Variable& mean,
+                                  const Variable& variance, double momentum);
 Variable relu(Runtime& rt, const Variable& x);
 Variable add(Runtime& rt, const Variable& a, const Variable& b);
 Variable linear(Runtime& rt, const Variable& x, const Variable& w, const Variable* bias);

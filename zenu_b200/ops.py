@@ -556,6 +556,36 @@ def max_pool_2d_indexed_backward(ctx, dy, idx, x_shape, kernel, stride, pad):
     return dx
 
 
+def batch_norm_relu_max_pool_forward_train(ctx, momentum, x, scale, bias, mean, variance, stat_partial=None, stat_rows=0, shift=None,
+                                           kernel=3, stride=2, pad=1):
+    """NHWC f32: BatchNorm2d(train) + ReLU + max_pool_2d(3, 2, 1) in one pass (the ResNet stem).  Returns (y_pool, idx, saving_mean,
+    saving_inv_variance); running mean / variance are updated in place.  Raises ZenuB200Error (unsupported) for other geometries."""
+    for t, nm in ((x, "x"), (scale, "scale"), (bias, "bias"), (mean, "mean"), (variance, "variance")):
+        _chk(t, "batch_norm_relu_max_pool " + nm)
+    n, c, h, w = _nkhw(x.shape, ZB_NHWC)
+    p, q = (h + 2 * pad - kernel) // stride + 1, (w + 2 * pad - kernel) // stride + 1
+    y = torch.empty((n, p, q, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((n, p, q, c), dtype=torch.uint8, device=x.device)
+    sm = torch.empty((c,), dtype=x.dtype, device=x.device)
+    si = torch.empty((c,), dtype=x.dtype, device=x.device)
+    check(ctx.lib.zb_bn2d_relu_maxpool_fwd_train(ctx.handle, _DT[x.dtype], ZB_NHWC, n, c, h, w, kernel, stride, pad, float(momentum), _p(x),
+                                                 _p(scale), _p(bias), _p(mean), _p(variance), _p(sm), _p(si), _p(y),
+                                                 ctypes.c_void_p(idx.data_ptr()), _p(stat_partial), int(stat_rows), _p(shift)))
+    return y, idx, sm, si
+
+
+def batch_norm_relu_max_pool_backward(ctx, x, dy_pool, idx, scale, bias, saving_mean, saving_inv_variance, kernel=3, stride=2, pad=1):
+    """Backward of batch_norm_relu_max_pool_forward_train: (x_grad, scale_grad, bias_grad)."""
+    n, c, h, w = _nkhw(x.shape, ZB_NHWC)
+    dx = torch.empty_like(x)
+    ds = torch.empty((c,), dtype=x.dtype, device=x.device)
+    db = torch.empty((c,), dtype=x.dtype, device=x.device)
+    check(ctx.lib.zb_bn2d_relu_maxpool_bwd(ctx.handle, _DT[x.dtype], ZB_NHWC, n, c, h, w, kernel, stride, pad, _p(x), _p(dy_pool),
+                                           ctypes.c_void_p(idx.data_ptr()), _p(scale), _p(bias), _p(saving_mean), _p(saving_inv_variance),
+                                           _p(dx), _p(ds), _p(db)))
+    return dx, ds, db
+
+
 def global_avg_pool(ctx, x, layout=ZB_NCHW):
     n, c, h, w = _nkhw(x.shape, layout)
     y = torch.empty((n, c), dtype=x.dtype, device=x.device)
