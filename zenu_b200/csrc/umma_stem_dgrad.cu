@@ -168,6 +168,7 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       w_sx0[i] = (w + p.pw) % p.sw;
       w_q0[i] = (w + p.pw - w_sx0[i]) / p.sw;
     }
+    const bool fast_taps = p.sw == 2 && p.S <= 8;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.h_blocks, hb = tile - img * p.h_blocks;
       const int h0 = hb * kSdTH, h1 = min(h0 + kSdTH, p.H) - 1;
@@ -195,10 +196,25 @@ stem_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (w >= p.W) break;
           float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
           int q = w_q0[i];
-          for (int sx = w_sx0[i]; sx < p.S; sx += p.sw, --q) {
-            if (q >= 0 && q < p.Q) {
-              const float4 t = stage4[q * 8 + (sx ^ (q & 7))];
-              sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+          if (fast_taps) {
+            // S <= 8, stride 2 (the ResNet stem: 7 / 2): at most four filter columns reach a pixel.  Their four 128-bit smem reads are
+            // issued together (the runtime-bound loop below serialises one read + add per trip: ncu had the epilogue warps waiting on
+            // exactly that chain) and summed in the loop's order; a column that does not exist contributes +0.
+            float4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int sx = w_sx0[i] + 2 * j, qj = q - j;
+              const bool ok = sx < p.S && qj >= 0 && qj < p.Q;
+              t[j] = ok ? stage4[qj * 8 + (sx ^ (qj & 7))] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sum.x += t[j].x; sum.y += t[j].y; sum.z += t[j].z; sum.w += t[j].w; }
+          } else {
+            for (int sx = w_sx0[i]; sx < p.S; sx += p.sw, --q) {
+              if (q >= 0 && q < p.Q) {
+                const float4 t = stage4[q * 8 + (sx ^ (q & 7))];
+                sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+              }
             }
           }
           float* o = out_row + w * p.C;
