@@ -213,7 +213,9 @@ void Variable::backward(Runtime& rt, const std::function<void(int)>& on_bucket_r
     p_->grad = one;
   }
   struct Cmp {
-    bool operator()(const std::shared_ptr<Function>& a, const std::shared_ptr<Function>& b) const { return a->gen < b->gen; }
+    bool operator()(const std::shared_ptr<Function>& a, const std::shared_ptr<Function>& b) const {
+      return a->gen < b->gen || (a->gen == b->gen && a->order_hint() > b->order_hint());
+    }
   };
   std::priority_queue<std::shared_ptr<Function>, std::vector<std::shared_ptr<Function>>, Cmp> heap;
   std::set<Function*> seen;
@@ -270,6 +272,9 @@ struct ConvFn : Function {
   bool has_bias, need_dx;
   int x_layout = ZB_NHWC;  // ZB_NCHW_X when the stem consumed the NCHW network input directly
   const char* name() const override { return "conv2d"; }
+  int order_hint() const override {
+    return (d.kh == 1 && d.kw == 1 && (d.stride_h > 1 || d.stride_w > 1) && !ZB_ENV_FLAG("ZENU_B200_NO_ORDER_HINT")) ? 1 : 0;
+  }
   void backward(Runtime& rt, const Tensor& gy) override {
     VariableInner& xv = *inputs[0];
     VariableInner& wv = *inputs[1];

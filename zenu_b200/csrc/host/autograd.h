@@ -128,6 +128,11 @@ struct Function {
   // fused BN + add + ReLU backward hands to its residual branch without writing the product out).  A function that can apply the
   // mask while it reads gy says so here and finds the bits in gy_mask; for all others the sweep materialises the product first.
   virtual bool takes_masked_grad() const { return false; }
+  // Functions of one generation may run in any order (their input gradients are summed, and a + b == b + a bit for bit); the sweep
+  // runs lower hints first.  A strided pointwise conv asks to go last: as the FIRST arrival its dgrad must zero-fill the whole input
+  // gradient and scatter into it, and the sibling then re-reads all of it to accumulate; as the second arrival it only touches the
+  // pixels it reaches, on top of the sibling's plain write.
+  virtual int order_hint() const { return 0; }
   Tensor gy_mask;
 };
 
