@@ -185,11 +185,20 @@ int zb_model_forward_backward(zb_model* m, const void* x_nchw, const void* targe
       const int b = -1 - code;
       if (b < 0 || b >= static_cast<int>(ps.buckets.size())) return;
       if (--ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1) rt.join_side();   // the bucket's last wgrad may be on the side stream
-      if (ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1)
+      // ZENU_B200_DP_MODE (measurement only, profiles/r2_scaling.md): "skip" = no exchange at all (wrong gradients; what the step
+      // costs without NCCL beside it), "tail" = every bucket exchanged after the backward pass (no overlap)
+      static const int dp_mode = []() { const char* e = getenv("ZENU_B200_DP_MODE"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0)); }();
+      if (ps.buckets[b].pending == 0 && zb_dp_world(ctx) > 1 && dp_mode == 0)
         check_rc(zb_dp_allreduce_sum(ctx, rt.dtype, static_cast<uint8_t*>(ps.flat_grads.ptr) + ps.buckets[b].offset * esz,
                                      ps.buckets[b].numel), "bucket allreduce");
     });
     rt.join_side();   // every gradient is complete on the compute stream from here on (optimizer, capture end)
+    {
+      const char* e = getenv("ZENU_B200_DP_MODE");
+      if (e != nullptr && e[0] == 't' && zb_dp_world(ctx) > 1)
+        for (auto& bk : ps.buckets)
+          check_rc(zb_dp_allreduce_sum(ctx, rt.dtype, static_cast<uint8_t*>(ps.flat_grads.ptr) + bk.offset * esz, bk.numel), "bucket allreduce (tail)");
+    }
     if (loss_dev) check_rc(zb_copy(ctx, rt.dtype, loss->data.ptr, loss_dev, 1), "copy loss");
     m->last_loss = loss;
   });
