@@ -58,6 +58,11 @@ def main():
             acc = torch.ones_like(dx)
             if c % 32 == 0:
                 ops.conv_bkwd_data_accumulate(ctx, DY, W, acc, **kw)
+                words = torch.randint(-2 ** 31, 2 ** 31 - 1, ((acc.numel() + 31) // 32,), dtype=torch.int64, device="cuda").to(torch.int32)
+                want = ops.mask_apply(ctx, acc, words)
+                ops.conv_bkwd_data_accumulate(ctx, DY, W, want, **kw)
+                ops.conv_bkwd_data_accumulate_masked(ctx, DY, W, acc, words, **kw)   # lazy masked fan-in (epilogue mask prefetch)
+                assert torch.equal(acc, want), (name, "masked accumulate")
             ctx.check()
             assert rel(nchw(y), y_ref) < tol, (name, "fprop")
             assert rel(nchw(dx), zo.conv2d_bkwd_data(dy.astype(np.float64), w.astype(np.float64), x.shape, pad, stride, 1)) < tol, (name, "dgrad")
@@ -86,6 +91,11 @@ def main():
                 y3, sm3, si3, mask = ops.batch_norm_2d_forward_train_masked(ctx, 0.9, X, dev(sc), dev(bi), dev(np.zeros(c, np.float32)),
                                                                             dev(np.ones(c, np.float32)), residual=R)
                 ops.batch_norm_2d_backward_masked(ctx, X, DY, dev(sc), sm3, si3, mask)
+                ops.batch_norm_2d_backward_masked(ctx, X, DY, dev(sc), sm3, si3, mask, want_residual_grad=False)
+            if c % 4 == 0 and (256 % (c // 4)) == 0:   # fused stem: BN + ReLU + 3x3 / 2 max-pool, both ways
+                yp, pidx, sm4, si4 = ops.batch_norm_relu_max_pool_forward_train(ctx, 0.9, X, dev(sc), dev(bi), dev(np.zeros(c, np.float32)),
+                                                                                dev(np.ones(c, np.float32)))
+                ops.batch_norm_relu_max_pool_backward(ctx, X, torch.randn_like(yp), pidx, dev(sc), dev(bi), sm4, si4)
             ctx.check()
             bn, _, _, sm_r, si_r = zo.bn2d_fwd_train(x, sc, bi, np.zeros(c, np.float32), np.ones(c, np.float32), 0.9)
             out_ref = zo.relu(zo.ewise("add", bn, res))
