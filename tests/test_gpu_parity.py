@@ -494,6 +494,46 @@ def test_conv_fused_bn_statistics(zb, ctx, case):
     ctx.check()
 
 
+@pytest.mark.parametrize("case", [
+    (2, 64, 32, 32, 64, 3, 1),       # 3x3 / 2 / pad 1: Q = 16, three row blocks per image
+    (3, 32, 33, 31, 128, 3, 1),      # odd extents (last window row / column partly in the padding), 128 output channels
+    (2, 64, 36, 36, 96, 5, 2),       # 5x5 / 2 / pad 2: plane offsets 0..2, N = 96 (partly empty BN = 128 tile)
+    (2, 128, 30, 34, 256, 3, 0),     # no padding: both parity planes start at 0 / 1, streamed filter, CTA pairs
+])
+def test_conv_stride2_halo_planes(zb, ctx, case):
+    """Stride-2 RxS forward convs on the halo-reuse kernel: the input's four (row, column) parity planes land as dense rasters through ONE
+    tensor map with element strides (1, 2, 2, 1), tap (r, s) = a raster offset inside plane ((r - pad) mod 2, (s - pad) mod 2).  The plan
+    must say so (planes=4), the result must match the tf32-rounded oracle (5e-5), 3xTF32 exact arithmetic (1e-5), the fused BatchNorm
+    statistics the values stored, and the im2col form (ZENU_B200_NO_HALO_S2 is the A/B switch; here: the FFMA kernel as second opinion)."""
+    from zenu_b200 import ZB_MATH_FP32, ZB_MATH_TF32, ZB_MATH_TF32X3, ZB_NHWC
+    n, c, h, w_, k, r, pad = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((n, c, h, w_)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+    X, W = dev(nhwc(x)), dev(nhwc(wt))
+    plan = zb.conv_plan_describe(ctx, zb.PLAN_FPROP, tuple(X.shape), tuple(W.shape), pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert "halo_conv" in plan and "planes=4" in plan, plan
+    shift = dev((0.1 * rng.standard_normal(k)).astype(np.float32))
+    y, partial, rows = zb.conv_fwd_bnstats(ctx, X, W, shift, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rows > 0
+    xr, wr = zo.tf32_round(x, "rne"), zo.tf32_round(wt, "rne")
+    y_ref = zo.conv2d_fwd(xr, wr, pad, 2, 1)
+    y_h = nchw(host(y))
+    assert rel_err(y_h, y_ref) < 5e-5
+    part = host(partial)[:rows].astype(np.float64).sum(axis=0)
+    dlt = y_h.astype(np.float64) - host(shift).astype(np.float64)[None, :, None, None]
+    np.testing.assert_allclose(part[0], dlt.sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-3 * np.sqrt(dlt[:, 0].size))
+    np.testing.assert_allclose(part[1], (dlt * dlt).sum(axis=(0, 2, 3)), rtol=1e-4)
+    y3 = zb.conv_fwd(ctx, X, W, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+    assert rel_err(nchw(host(y3)), zo.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), pad, 2, 1)) < 1e-5
+    yf = zb.conv_fwd(ctx, X, W, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_FP32)
+    assert rel_err(host(y3), host(yf)) < 1e-5
+    bias = dev(rng.standard_normal(k).astype(np.float32))
+    yb = zb.conv_fwd(ctx, X, W, pad, 2, 1, bias=bias, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rel_err(host(yb), host(y) + host(bias)[None, None, None, :]) < 1e-6
+    ctx.check()
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 def test_bn_fused_relu_residual(zb, ctx, layout):
     """Fused BN+add+ReLU fwd/bwd == the reference's separate nodes (BN -> add -> relu) composed from oracle ops."""

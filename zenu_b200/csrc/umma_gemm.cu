@@ -848,12 +848,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int q = cl_id; q < total_q && ok; q += n_cl) {
         const int n_blk = q % p.n_tiles, m_blk = (q / p.n_tiles) * CL + cl_rank;
         const int img = m_blk / p.win_p_tiles, pt = m_blk - img * p.win_p_tiles;
-        const int h0 = pt * p.win_box_p + p.lower_h;
+        const int h0 = pt * p.win_box_p * p.halo_stride;
         for (int c = 0; c < chunks && ok; ++c) {
           if (!mbar_wait(&a_empty[ai], aph ^ 1, err)) { ok = false; break; }
           if (lead) mbar_arrive_expect_tx(&a_full[ai], kShare * static_cast<uint32_t>(p.halo_raster_bytes));
-          if (PAIR) tma_load_4d_pair(sA + ai * p.halo_slot_bytes, &tmA, afull0 + ai * 8, c * kUmmaBK, p.lower_w, h0, img);
-          else tma_load_4d(sA + ai * p.halo_slot_bytes, &tmA, &a_full[ai], c * kUmmaBK, p.lower_w, h0, img);
+          for (int pl = 0; pl < p.halo_planes; ++pl) {   // one raster (stride 1) or one per input parity class (stride 2)
+            uint8_t* dst = sA + ai * p.halo_slot_bytes + pl * p.halo_plane_bytes;
+            if (PAIR) tma_load_4d_pair(dst, &tmA, afull0 + ai * 8, c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], img);
+            else tma_load_4d(dst, &tmA, &a_full[ai], c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], img);
+          }
           if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
           if (!resident) {
             for (int t = 0; t < taps; ++t) {
@@ -1585,35 +1588,58 @@ int umma_conv1x1_nchw_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* d
 // ---------------------------------------------------------------------------------------------- halo conv planner
 struct HaloPlan {
   int Wr, tp, p_tiles, slots, slot_bytes, raster_bytes, b_stages, resident, bn;
+  int stride, planes, plane_bytes, rows_pl;                 // stride-2 form: four parity planes per slot (see UmmaParams::halo_planes)
+  int dh[4], dw[4], row_par[8], row_off[8], col_par[8], col_off[8];
   int pair;   // run on CTA pairs (halo_conv_kernel<BN, 2, true>): each CTA holds half of every filter tile
   size_t smem;
 };
 // in: [N][H][W][Cin] NHWC; filt: [Kout][R*S*Cin] (tap-major, channel-minor); out: [N][P][Q][Kout] with P = H + 2*ph - R + 1.
 static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long long Cin, long long Kout, int R, int S, int ph, int pw,
-                      HaloPlan* hp) {
+                      HaloPlan* hp, int stride = 1) {
   (void)ctx;
   if (ZB_ENV_FLAG("ZENU_B200_NO_HALO")) return false;
-  const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
+  if (stride != 1 && (stride != 2 || ZB_ENV_FLAG("ZENU_B200_NO_HALO_S2"))) return false;
+  const long long P = (H + 2 * ph - R) / stride + 1, Q = (W + 2 * pw - S) / stride + 1;
   if (R * S < 2 || R * S > kUmmaMaxTaps || Cin % 32 != 0 || Kout % 4 != 0 || P <= 0 || Q <= 0 || ph < 0 || pw < 0) return false;
-  const long long Wr = W + 2 * pw;  // raster width = Q + S - 1
-  if (Wr > kUmmaBM || Wr > 256) return false;
+  hp->stride = stride;
+  hp->planes = 1;
+  hp->dh[0] = -ph; hp->dw[0] = -pw;
+  int max_row_off = R - 1, max_col_off = S - 1;
+  if (stride == 2) {
+    // tap (r, s) reads input (2p + r - ph, 2q + s - pw): parity class ((r - ph) mod 2, (s - pw) mod 2), and inside the class' dense
+    // plane (start = the smallest r - ph of that parity) the position (p + row_off, q + col_off)
+    if (R < 2 || S < 2 || R > 8 || S > 8) return false;   // both parities must occur in each dimension (4 planes)
+    int base_h[2] = {1 << 20, 1 << 20}, base_w[2] = {1 << 20, 1 << 20};
+    for (int r = 0; r < R; ++r) { const int e = r - ph, par = ((e % 2) + 2) % 2; base_h[par] = std::min(base_h[par], e); }
+    for (int s_ = 0; s_ < S; ++s_) { const int e = s_ - pw, par = ((e % 2) + 2) % 2; base_w[par] = std::min(base_w[par], e); }
+    max_row_off = 0; max_col_off = 0;
+    for (int r = 0; r < R; ++r) { const int e = r - ph, par = ((e % 2) + 2) % 2; hp->row_par[r] = par; hp->row_off[r] = (e - base_h[par]) / 2; max_row_off = std::max(max_row_off, hp->row_off[r]); }
+    for (int s_ = 0; s_ < S; ++s_) { const int e = s_ - pw, par = ((e % 2) + 2) % 2; hp->col_par[s_] = par; hp->col_off[s_] = (e - base_w[par]) / 2; max_col_off = std::max(max_col_off, hp->col_off[s_]); }
+    hp->planes = 4;
+    for (int pl = 0; pl < 4; ++pl) { hp->dh[pl] = base_h[pl >> 1]; hp->dw[pl] = base_w[pl & 1]; }
+  }
+  const long long Wr = stride == 1 ? W + 2 * pw : Q + max_col_off;  // raster width (stride 1: = Q + S - 1)
+  if (Wr > kUmmaBM || stride * (Wr - 1) + 1 > 256) return false;
   int tp = static_cast<int>(std::min<long long>(P, kUmmaBM / Wr));
   // balance the row blocks of an image (14 rows, tp 8 -> 7 + 7 instead of 8 + 6)
   const int p_tiles = ceil_div(P, tp);
   tp = ceil_div(P, p_tiles);
-  if (tp + R - 1 > 256) return false;
+  const int rows_pl = tp + max_row_off;   // raster rows per plane (stride 1: tp + R - 1)
+  if (stride * (rows_pl - 1) + 1 > 256) return false;
   if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) return false;  // too many dead MMA rows
-  hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles;
+  hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles; hp->rows_pl = rows_pl;
   hp->bn = pick_bn(Kout);
   // CTA pairs: ZENU_B200_HALO_PAIR = 0 never, 1 only the N <= 128 layers, 2 (default) every layer.  Measured (tools/bench_conv.py --only
   // 3x3, fprop / dgrad): 256 -> 256 @14x14 0.113 -> 0.101 / 0.116 -> 0.105 ms, 128 -> 128 @28x28 0.145 -> 0.137 / 0.149 -> 0.138,
   // 64 -> 64 @56x56 0.211 -> 0.205 / 0.212 -> 0.205 (that layer is not bound by the MMA issue rate after all).
   static const int pair_mode = []() { const char* e = getenv("ZENU_B200_HALO_PAIR"); return e ? atoi(e) : 2; }();
   hp->pair = (pair_mode > 0 && hp->bn >= 64 && (pair_mode > 1 || hp->bn <= 128) && N * p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 1 : 0;
-  hp->raster_bytes = (tp + R - 1) * static_cast<int>(Wr) * 128;
-  // rows a tap descriptor may touch beyond the raster ((R-1)*Wr + S-1 + 127 is the last row read) stay inside the slot
-  const int last_row = (R - 1) * static_cast<int>(Wr) + (S - 1) + kUmmaBM;
-  hp->slot_bytes = (std::max(hp->raster_bytes, last_row * 128) + 1023) & ~1023;
+  const int plane_data = rows_pl * static_cast<int>(Wr) * 128;
+  hp->plane_bytes = hp->planes == 1 ? 0 : ((plane_data + 1023) & ~1023);   // every plane starts on a swizzle-pattern boundary
+  hp->raster_bytes = hp->planes * plane_data;   // bytes the TMA loads of one slot deliver
+  // rows a tap descriptor may touch beyond its raster (tap offset + 127 is the last row an MMA reads) stay inside the slot
+  const int last_row = max_row_off * static_cast<int>(Wr) + max_col_off + kUmmaBM;
+  hp->slot_bytes = ((hp->planes - 1) * hp->plane_bytes + std::max(plane_data, last_row * 128) + 1023) & ~1023;
   const int b_bytes = hp->bn * 128 / (hp->pair ? 2 : 1);
   const int chunks = static_cast<int>(Cin / 32);
   const int budget = 227 * 1024 - 1024 - 16384 - 48 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
@@ -1639,8 +1665,8 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
   static SmemOptIn opt_in;
   { const int rc = smem_opt_in(ctx, opt_in, halo_conv_kernel<BN, CL, PAIR>, smem); if (rc != ZB_OK) return rc; }
   plan_note("halo_conv<bn=%d,cl=%d,pair=%d> resident=%d slots=%d b_stages=%d n_tiles=%d ntaps=%d c_chunks=%d beta=%d bias=%d stats=%d chain=%d tp=%d "
-            "~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
-            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.m_tiles, grid);
+            "planes=%d ~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
+            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.halo_planes, p.m_tiles, grid);
   if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   if (CL == 1) {
@@ -1669,14 +1695,17 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
 static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long long H, long long W, long long Cin, long long Kout, int R,
                           int S, int ph, int pw, const float* in, const float* filt, const float* bias, float* out, float beta,
                           double flops, const StatRequest* st = nullptr, const uint32_t* old_bits = nullptr) {
-  const long long P = H + 2 * ph - R + 1, Q = W + 2 * pw - S + 1;
+  const int st_ = hp.stride;
+  const long long P = (H + 2 * ph - R) / st_ + 1, Q = (W + 2 * pw - S) / st_ + 1;
   CUtensorMap ma, mb;
   {
     ZB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "TMA operand must be 16-byte aligned");
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 4, static_cast<cuuint64_t>(W) * Cin * 4, static_cast<cuuint64_t>(H) * W * Cin * 4};
-    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(hp.Wr), static_cast<cuuint32_t>(hp.tp + R - 1), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // stride 2: the box spans stride * (n - 1) + 1 positions and the element strides pick every second one, i.e. Wr x rows_pl pixels of
+    // ONE parity plane land as a dense raster; which plane is decided by the parity of the start coordinate the producer passes
+    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(st_ * (hp.Wr - 1) + 1), static_cast<cuuint32_t>(st_ * (hp.rows_pl - 1) + 1), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(st_), static_cast<cuuint32_t>(st_), 1};
     CUresult r = ctx->encode_tiled(&ma, operand_dtype(), 4, const_cast<float*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (halo raster) failed (%d)", int(r)); return ZB_ERR_CUDA; }
@@ -1702,7 +1731,12 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   p.c_chunks = static_cast<int>(Cin / 32);
   p.b_tap_stride = static_cast<int>(Cin);
   for (int r = 0; r < R; ++r)
-    for (int sx = 0; sx < S; ++sx) p.tap_w[r * S + sx] = static_cast<uint16_t>(r * hp.Wr + sx);
+    for (int sx = 0; sx < S; ++sx)
+      p.tap_w[r * S + sx] = st_ == 1 ? static_cast<uint16_t>(r * hp.Wr + sx)
+                                     : static_cast<uint16_t>((hp.row_par[r] * 2 + hp.col_par[sx]) * (hp.plane_bytes / 128) + hp.row_off[r] * hp.Wr +
+                                                             hp.col_off[sx]);
+  p.halo_planes = hp.planes; p.halo_plane_bytes = hp.plane_bytes; p.halo_stride = st_;
+  for (int pl = 0; pl < 4; ++pl) { p.halo_dh[pl] = hp.dh[pl % hp.planes]; p.halo_dw[pl] = hp.dw[pl % hp.planes]; }
   p.halo_slots = hp.slots; p.halo_slot_bytes = hp.slot_bytes; p.halo_raster_bytes = hp.raster_bytes;
   p.halo_b_stages = hp.b_stages; p.halo_b_resident = hp.resident;
   p.halo_chain = p.chain_kb > 0 ? std::max(1, p.chain_kb / taps) : 0;
@@ -1771,10 +1805,10 @@ int umma_conv_fprop_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* x, c
   const long long M = d->n * P * Q;
   const int bn = pick_bn(d->k);
   const int taps = static_cast<int>(d->kh * d->kw);
-  if (d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1 && taps > 1) {
+  if (d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2) && d->dil_h == 1 && d->dil_w == 1 && taps > 1) {
     HaloPlan hp;
     if (halo_plan(ctx, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw), static_cast<int>(d->pad_h),
-                  static_cast<int>(d->pad_w), &hp))
+                  static_cast<int>(d->pad_w), &hp, static_cast<int>(d->stride_h)))
       return umma_conv_halo(ctx, hp, d->n, d->h, d->w, d->c, d->k, static_cast<int>(d->kh), static_cast<int>(d->kw),
                             static_cast<int>(d->pad_h), static_cast<int>(d->pad_w), x, w, bias, y, beta, 2.0 * M * d->k * d->c * taps, &st);
   }

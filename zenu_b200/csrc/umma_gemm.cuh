@@ -68,6 +68,11 @@ struct UmmaParams {
   // halo-reuse conv kernel (stride-1 RxS convs): one smem raster of (tp + R - 1) x Wr input pixels per 32-channel chunk
   // serves every filter tap through UMMA descriptors that start tap_w[t] rows (128 bytes each) into the raster
   int halo_slots, halo_slot_bytes, halo_raster_bytes, halo_b_stages, halo_b_resident;
+  // stride-2 halo form: the slot holds halo_planes (4) dense rasters, one per (row, column) parity of the input, loaded through ONE
+  // tensor map with element strides (1, 2, 2, 1) from shifted start coordinates (halo_dh / halo_dw, relative to stride * first output row /
+  // column of the tile); stride 1: one plane, halo_dh[0] / halo_dw[0] = -pad
+  int halo_planes, halo_plane_bytes, halo_stride;
+  int halo_dh[4], halo_dw[4];
   // accumulation-chain limit (3xTF32 mode): the tensor core adds into TMEM with truncation, a bias that grows with the number
   // of MMA steps; with chain_kb > 0 the accumulator is flushed through the epilogue (fp32 round-to-nearest adds into D) every
   // chain_kb K blocks (halo kernel: every halo_chain channel chunks) instead of once per tile.  0 = one chain per tile.
