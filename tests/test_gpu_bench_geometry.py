@@ -187,7 +187,9 @@ def test_plan_describe_reports_every_kernel_family(env):
     assert "wgrad_halo " in p(ops.PLAN_WGRAD, 128, 28, 128, 3, 1, 1)
     assert ",cl=2>" in p(ops.PLAN_FPROP, 1024, 14, 512, 1, 1, 0)                       # CTA pairs on the wide, long-K pointwise layers
     assert "splitk=1" in p(ops.PLAN_WGRAD, 512, 7, 2048, 1, 1, 0)                      # split-K wgrad + deterministic reduce
-    assert p(ops.PLAN_DGRAD, 128, 56, 128, 3, 2, 1).count("umma<") == 4                # one launch per (h, w) parity class
+    d_s2 = p(ops.PLAN_DGRAD, 128, 56, 128, 3, 2, 1)                                    # one launch per (h, w) parity class:
+    assert d_s2.count("umma<") == 1 and d_s2.count("halo_conv<") == 3                  # the single-tap class as a GEMM, the 2- / 2- / 4-tap classes on the halo kernel
+    assert "planes=4" in p(ops.PLAN_FPROP, 128, 56, 128, 3, 2, 1)                      # stride-2 forward: four input parity planes per raster slot
     assert "simt_conv_fprop<f64>" in ops.conv_plan_describe(ctx, ops.PLAN_FPROP, (2, 8, 8, 32), (32, 3, 3, 32), pad=1,
                                                              layout=pkg.ZB_NHWC, dtype=torch.float64)
     with pytest.raises(pkg.ZenuB200Error):

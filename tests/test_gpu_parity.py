@@ -531,6 +531,25 @@ def test_conv_stride2_halo_planes(zb, ctx, case):
     bias = dev(rng.standard_normal(k).astype(np.float32))
     yb = zb.conv_fwd(ctx, X, W, pad, 2, 1, bias=bias, layout=ZB_NHWC, math=ZB_MATH_TF32)
     assert rel_err(host(yb), host(y) + host(bias)[None, None, None, :]) < 1e-6
+    # backward data: every parity class with two or more taps is a stride-1 conv over dY on the same kernel (custom tap set, outputs
+    # scattered to the class' pixels); plain, accumulating and masked-accumulating forms
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    DY = dev(nhwc(dy))
+    dplan = zb.conv_plan_describe(ctx, zb.PLAN_DGRAD, tuple(X.shape), tuple(W.shape), pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert "halo_conv" in dplan, dplan
+    dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(zo.tf32_round(dy, "rne"), wr, x.shape, pad, 2, 1)) < 5e-5
+    dx3 = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+    assert rel_err(nchw(host(dx3)), zo.conv2d_bkwd_data(dy.astype(np.float64), wt.astype(np.float64), x.shape, pad, 2, 1)) < 1e-5
+    old = torch.randn_like(dx)
+    acc = old.clone()
+    zb.conv_bkwd_data_accumulate(ctx, DY, W, acc, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rel_err(host(acc) - host(old), host(dx)) < 1e-4
+    words = torch.randint(-2 ** 31, 2 ** 31 - 1, ((old.numel() + 31) // 32,), dtype=torch.int64, device="cuda").to(torch.int32)
+    want = zb.mask_apply(ctx, old, words)
+    zb.conv_bkwd_data_accumulate(ctx, DY, W, want, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    zb.conv_bkwd_data_accumulate_masked(ctx, DY, W, old, words, pad, 2, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    np.testing.assert_array_equal(host(old), host(want))
     ctx.check()
 
 

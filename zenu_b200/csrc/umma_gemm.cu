@@ -51,6 +51,7 @@ struct TileCoord {
   int m_blk, n_blk, tap, split;
 };
 template <bool V> struct FullTag { static constexpr bool value = V; };
+template <int V> struct IntTag { static constexpr int value = V; };
 struct TileDiv {   // the divisors of a tile id, as multiply-high constants (built once per role)
   FastDiv n, t, m;
   int m_groups;
@@ -181,8 +182,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
           const int pt = fastdiv(rem, fd_win_qt), qt = rem - pt * p.win_q_tiles;
           const int pl = fastdiv(l, fd_win_bq), ql = l - pl * p.win_box_q;
           const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
-          if (tile_exists && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q)
-            my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
+          if (tile_exists && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q) {
+            if (p.scat_sy != 0)   // a parity class of a strided dgrad: window (pp, qq) is input pixel (pp * sy + oy, qq * sx + ox)
+              my_off = ((static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox) * p.ldd;
+            else
+              my_off = ((static_cast<long long>(img) * p.conv_P + pp) * p.conv_Q + qq) * p.ldd;
+          }
         } else {
           const int row = m0 + l;
           if (row < p.M) {
@@ -927,22 +932,34 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else umma_commit_multicast(&b_empty[bi], kClMask);
             if (++bi == p.halo_b_stages) { bi = 0; bph ^= 1; }
           };
-          if (taps == 9 && resident) {
-            uint64_t db = b_desc0 + static_cast<uint32_t>(c * 9 * (B_BYTES >> 4));
-            mma4(a_slot + tapoff[0], db, c > c_begin ? 1u : 0u);
+          // NT taps fully unrolled (offsets in registers): 9 = 3x3 filters, 4 / 2 = the multi-tap parity classes of a stride-2 dgrad
+          auto taps_unrolled = [&](auto tag) -> bool {
+            constexpr int NT = decltype(tag)::value;
+            if (resident) {
+              uint64_t db = b_desc0 + static_cast<uint32_t>(c * NT * (B_BYTES >> 4));
+              mma4(a_slot + tapoff[0], db, c > c_begin ? 1u : 0u);
 #pragma unroll
-            for (int t = 1; t < 9; ++t) {
-              db += B_BYTES >> 4;
-              mma4(a_slot + tapoff[t], db, 1u);
-            }
-          } else if (taps == 9) {
+              for (int t = 1; t < NT; ++t) {
+                db += B_BYTES >> 4;
+                mma4(a_slot + tapoff[t], db, 1u);
+              }
+            } else {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (!mbar_wait(&b_full[bi], bph, err)) { ok = false; break; }
-              tc_fence_after();
-              mma4(a_slot + tapoff[t], b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4)), (c > c_begin || t > 0) ? 1u : 0u);
-              b_release();
+              for (int t = 0; t < NT; ++t) {
+                if (!mbar_wait(&b_full[bi], bph, err)) return false;
+                tc_fence_after();
+                mma4(a_slot + tapoff[t], b_desc0 + static_cast<uint32_t>(bi * (B_BYTES >> 4)), (c > c_begin || t > 0) ? 1u : 0u);
+                b_release();
+              }
             }
+            return true;
+          };
+          if (taps == 9) {
+            if (!taps_unrolled(IntTag<9>{})) { ok = false; break; }
+          } else if (taps == 4) {
+            if (!taps_unrolled(IntTag<4>{})) { ok = false; break; }
+          } else if (taps == 2) {
+            if (!taps_unrolled(IntTag<2>{})) { ok = false; break; }
           } else {
 #pragma unroll 1
             for (int t = 0; t < taps; ++t) {
@@ -1586,6 +1603,14 @@ int umma_conv1x1_nchw_wgrad(zb_ctx* ctx, const zb_conv2d_desc* d, const float* d
 }
 
 // ---------------------------------------------------------------------------------------------- halo conv planner
+// A custom tap set for the halo kernel (one parity class of a strided dgrad): `ntaps` taps at raster offsets (off_h, off_w) >= 0 from
+// the tile's first input position (lower_h + first output row, lower_w), out_h x out_w outputs per image written to pixel
+// (p * sy + oy, q * sx + ox) of an OH x OW image.
+struct HaloTapSet {
+  int ntaps, lower_h, lower_w, sy, oy, sx, ox;
+  long long out_h, out_w, OH, OW;
+  int off_h[kUmmaMaxTaps], off_w[kUmmaMaxTaps];
+};
 struct HaloPlan {
   int Wr, tp, p_tiles, slots, slot_bytes, raster_bytes, b_stages, resident, bn;
   int stride, planes, plane_bytes, rows_pl;                 // stride-2 form: four parity planes per slot (see UmmaParams::halo_planes)
@@ -1595,16 +1620,22 @@ struct HaloPlan {
 };
 // in: [N][H][W][Cin] NHWC; filt: [Kout][R*S*Cin] (tap-major, channel-minor); out: [N][P][Q][Kout] with P = H + 2*ph - R + 1.
 static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long long Cin, long long Kout, int R, int S, int ph, int pw,
-                      HaloPlan* hp, int stride = 1) {
+                      HaloPlan* hp, int stride = 1, const HaloTapSet* ts = nullptr) {
   (void)ctx;
   if (ZB_ENV_FLAG("ZENU_B200_NO_HALO")) return false;
   if (stride != 1 && (stride != 2 || ZB_ENV_FLAG("ZENU_B200_NO_HALO_S2"))) return false;
-  const long long P = (H + 2 * ph - R) / stride + 1, Q = (W + 2 * pw - S) / stride + 1;
-  if (R * S < 2 || R * S > kUmmaMaxTaps || Cin % 32 != 0 || Kout % 4 != 0 || P <= 0 || Q <= 0 || ph < 0 || pw < 0) return false;
+  if (ts != nullptr && stride != 1) return false;
+  const long long P = ts ? ts->out_h : (H + 2 * ph - R) / stride + 1, Q = ts ? ts->out_w : (W + 2 * pw - S) / stride + 1;
+  const int ntaps = ts ? ts->ntaps : R * S;
+  if (ntaps < 2 || ntaps > kUmmaMaxTaps || Cin % 32 != 0 || Kout % 4 != 0 || P <= 0 || Q <= 0 || (!ts && (ph < 0 || pw < 0))) return false;
   hp->stride = stride;
   hp->planes = 1;
-  hp->dh[0] = -ph; hp->dw[0] = -pw;
+  hp->dh[0] = ts ? ts->lower_h : -ph; hp->dw[0] = ts ? ts->lower_w : -pw;
   int max_row_off = R - 1, max_col_off = S - 1;
+  if (ts) {
+    max_row_off = 0; max_col_off = 0;
+    for (int t = 0; t < ts->ntaps; ++t) { max_row_off = std::max(max_row_off, ts->off_h[t]); max_col_off = std::max(max_col_off, ts->off_w[t]); }
+  }
   if (stride == 2) {
     // tap (r, s) reads input (2p + r - ph, 2q + s - pw): parity class ((r - ph) mod 2, (s - pw) mod 2), and inside the class' dense
     // plane (start = the smallest r - ph of that parity) the position (p + row_off, q + col_off)
@@ -1618,7 +1649,7 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
     hp->planes = 4;
     for (int pl = 0; pl < 4; ++pl) { hp->dh[pl] = base_h[pl >> 1]; hp->dw[pl] = base_w[pl & 1]; }
   }
-  const long long Wr = stride == 1 ? W + 2 * pw : Q + max_col_off;  // raster width (stride 1: = Q + S - 1)
+  const long long Wr = (stride == 1 && !ts) ? W + 2 * pw : Q + max_col_off;  // raster width (stride 1: = Q + S - 1)
   if (Wr > kUmmaBM || stride * (Wr - 1) + 1 > 256) return false;
   int tp = static_cast<int>(std::min<long long>(P, kUmmaBM / Wr));
   // balance the row blocks of an image (14 rows, tp 8 -> 7 + 7 instead of 8 + 6)
@@ -1645,9 +1676,9 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   const int budget = 227 * 1024 - 1024 - 16384 - 48 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
   const int n_tiles = ceil_div(Kout, hp->bn);
   hp->resident = 0;
-  if (n_tiles == 1 && R * S * chunks <= kHaloMaxB && R * S * chunks * b_bytes + 2 * hp->slot_bytes <= budget) {
+  if (n_tiles == 1 && ntaps * chunks <= kHaloMaxB && ntaps * chunks * b_bytes + 2 * hp->slot_bytes <= budget) {
     hp->resident = 1;
-    hp->b_stages = R * S * chunks;
+    hp->b_stages = ntaps * chunks;
     hp->slots = std::min(4, (budget - hp->b_stages * b_bytes) / hp->slot_bytes);
   } else {
     hp->slots = std::min(3, std::max(2, chunks >= 2 ? 3 : 2));
@@ -1694,9 +1725,9 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
 // tap_r/tap_s: raster offset of tap t (filter row / column in the orientation of `filt`)
 static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long long H, long long W, long long Cin, long long Kout, int R,
                           int S, int ph, int pw, const float* in, const float* filt, const float* bias, float* out, float beta,
-                          double flops, const StatRequest* st = nullptr, const uint32_t* old_bits = nullptr) {
+                          double flops, const StatRequest* st = nullptr, const uint32_t* old_bits = nullptr, const HaloTapSet* ts = nullptr) {
   const int st_ = hp.stride;
-  const long long P = (H + 2 * ph - R) / st_ + 1, Q = (W + 2 * pw - S) / st_ + 1;
+  const long long P = ts ? ts->out_h : (H + 2 * ph - R) / st_ + 1, Q = ts ? ts->out_w : (W + 2 * pw - S) / st_ + 1;
   CUtensorMap ma, mb;
   {
     ZB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "TMA operand must be 16-byte aligned");
@@ -1710,7 +1741,7 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled (halo raster) failed (%d)", int(r)); return ZB_ERR_CUDA; }
   }
-  const int taps = R * S;
+  const int taps = ts ? ts->ntaps : R * S;
   // streamed filter + at least two row blocks: pairs of CTAs share every filter tile through TMA multicast (halo_conv_kernel CL = 2)
   const int cl = (hp.pair || (!hp.resident && hp.bn >= 64 && static_cast<long long>(N) * hp.p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER"))) ? 2 : 1;
   int rc = make_map_2d(ctx, &mb, filt, static_cast<long long>(taps) * Cin, Kout, static_cast<long long>(taps) * Cin, 32, hp.bn / cl);
@@ -1730,7 +1761,12 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   p.ntaps = taps;
   p.c_chunks = static_cast<int>(Cin / 32);
   p.b_tap_stride = static_cast<int>(Cin);
-  for (int r = 0; r < R; ++r)
+  if (ts) {
+    for (int t = 0; t < taps; ++t) p.tap_w[t] = static_cast<uint16_t>(ts->off_h[t] * hp.Wr + ts->off_w[t]);
+    p.scat_OH = static_cast<int>(ts->OH); p.scat_OW = static_cast<int>(ts->OW);
+    p.scat_sy = ts->sy; p.scat_oy = ts->oy; p.scat_sx = ts->sx; p.scat_ox = ts->ox;
+  }
+  for (int r = 0; r < R && !ts; ++r)
     for (int sx = 0; sx < S; ++sx)
       p.tap_w[r * S + sx] = st_ == 1 ? static_cast<uint16_t>(r * hp.Wr + sx)
                                      : static_cast<uint16_t>((hp.row_par[r] * 2 + hp.col_par[sx]) * (hp.plane_bytes / 128) + hp.row_off[r] * hp.Wr +
@@ -1975,6 +2011,22 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
       const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
       plan_note("dgrad_filter(class %d,%d);", cp.a, cp.b);
       ZB_KLAUNCH(ctx, dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), cp.ntaps, tl));
+    }
+    if (cp.ntaps >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_HALO_DGRAD_CLASS")) {
+      // a class with several taps is a stride-1 conv over dY with that tap subset: on the halo kernel its dY raster is fetched once per
+      // channel chunk instead of once per tap (outputs scattered to the class' pixels by the epilogue)
+      HaloTapSet ts;
+      ts.ntaps = cp.ntaps; ts.lower_h = cp.lower_h; ts.lower_w = cp.lower_w;
+      ts.sy = sh; ts.oy = cp.a; ts.sx = sw; ts.ox = cp.b;
+      ts.out_h = cp.Ha; ts.out_w = cp.Wb; ts.OH = d->h; ts.OW = d->w;
+      for (int t = 0; t < cp.ntaps; ++t) { ts.off_h[t] = cp.off_h[t]; ts.off_w[t] = cp.off_w[t]; }
+      HaloPlan hp;
+      if (halo_plan(ctx, d->n, P, Q, d->k, d->c, 1, 1, 0, 0, &hp, 1, &ts)) {
+        rc = umma_conv_halo(ctx, hp, d->n, P, Q, d->k, d->c, 1, 1, 0, 0, dy, wt, nullptr, dx, beta,
+                            2.0 * d->n * cp.Ha * cp.Wb * static_cast<double>(d->c) * d->k * cp.ntaps, nullptr, beta != 0.f ? old_bits : nullptr, &ts);
+        if (rc != ZB_OK) return rc;
+        continue;
+      }
     }
     CUtensorMap ma, mb;
     rc = make_map_im2col(ctx, &ma, dy, d->n, P, Q, d->k, cp.lower_w, cp.lower_h, cp.upper_w, cp.upper_h, 1, 1, kUmmaBM);
