@@ -1184,6 +1184,28 @@ __global__ void dgrad_filter_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// All parity classes of a strided dgrad in one launch: their tap sets partition the R*S taps, so the class filters ([C][ntaps][K]
+// each, back to back in the workspace) are one permutation of the filter.
+struct ClassTable {
+  int n;
+  long long start[17];   // element offset of class i's filter in wt (start[n] = total)
+  int ntaps[16], tap_base[16];
+  int rs[kUmmaMaxTaps];  // r*S+s of tap (tap_base[i] + t) of class i
+};
+__global__ void dgrad_filter_classes_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int RS, int C, const ClassTable tb) {
+  const long long total = tb.start[tb.n];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int ci = 0;
+    while (ci + 1 < tb.n && i >= tb.start[ci + 1]) ++ci;
+    const long long j = i - tb.start[ci];
+    const int k = static_cast<int>(j % K);
+    const long long r = j / K;
+    const int t = static_cast<int>(r % tb.ntaps[ci]), c = static_cast<int>(r / tb.ntaps[ci]);
+    wt[i] = w[(static_cast<long long>(k) * RS + tb.rs[tb.tap_base[ci] + t]) * C + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
@@ -1999,19 +2021,29 @@ int umma_conv_dgrad_nhwc(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if (rc != ZB_OK) return rc;
   float* wt_base = static_cast<float*>(ws);
 
+  if (!plans.empty()) {   // the transformed filters of every class, one launch
+    if (plans.size() > 16) { set_last_error("umma dgrad: too many parity classes"); return ZB_ERR_UNSUPPORTED; }
+    ClassTable tb;
+    memset(&tb, 0, sizeof(tb));
+    tb.n = static_cast<int>(plans.size());
+    int tap_base = 0;
+    for (size_t ci = 0; ci < plans.size(); ++ci) {
+      tb.ntaps[ci] = plans[ci].ntaps;
+      tb.tap_base[ci] = tap_base;
+      for (int t = 0; t < plans[ci].ntaps; ++t) tb.rs[tap_base + t] = plans[ci].tap_rs[t];
+      tap_base += plans[ci].ntaps;
+      tb.start[ci + 1] = tb.start[ci] + static_cast<long long>(d->c) * plans[ci].ntaps * d->k;
+    }
+    const long long total = tb.start[tb.n];
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll)));
+    plan_note("dgrad_filter(classes=%d);", tb.n);
+    ZB_KLAUNCH(ctx, dgrad_filter_classes_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt_base, static_cast<int>(d->k), R * S, static_cast<int>(d->c), tb));
+  }
   size_t wt_off = 0;
   for (size_t ci = 0; ci < plans.size(); ++ci) {
     const ClassPlan& cp = plans[ci];
     float* wt = wt_base + wt_off;
     wt_off += static_cast<size_t>(d->c) * cp.ntaps * d->k;
-    TapList tl;
-    memcpy(tl.rs, cp.tap_rs, sizeof(tl.rs));
-    {
-      const long long total = static_cast<long long>(d->c) * cp.ntaps * d->k;
-      const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, ctx->sm_count * 8ll));
-      plan_note("dgrad_filter(class %d,%d);", cp.a, cp.b);
-      ZB_KLAUNCH(ctx, dgrad_filter_kernel<<<grid, 256, 0, ctx->stream>>>(w, wt, static_cast<int>(d->k), R * S, static_cast<int>(d->c), cp.ntaps, tl));
-    }
     if (cp.ntaps >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_HALO_DGRAD_CLASS")) {
       // a class with several taps is a stride-1 conv over dY with that tap subset: on the halo kernel its dY raster is fetched once per
       // channel chunk instead of once per tap (outputs scattered to the class' pixels by the epilogue)
