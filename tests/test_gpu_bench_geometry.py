@@ -230,3 +230,34 @@ def test_batchnorm_at_bench_tensor_size(env):
     dx_ref, ds_ref, db_ref = zo.bn2d_bwd(x64, dy64, f8(scale), sm_ref, si_ref)
     assert rel_err(dx_h, dx_ref) < 20 * tol
     assert rel_err(host(ds), ds_ref) < 20 * tol and rel_err(host(db), db_ref) < 20 * tol
+
+
+def test_fused_stem_bn_relu_pool_at_bench_size(env):
+    """zb_bn2d_relu_maxpool_fwd_train / _bwd on the stem activation of the benchmarked step (256 x 112 x 112 x 64 f32 = 822 MB, pooled to
+    56 x 56): forward bit-identical to zb_bn2d_fwd_train(relu) + zb_maxpool2d_fwd_idx, backward equal to zb_maxpool2d_bwd_idx +
+    zb_bn2d_relu_bwd up to the summation order (both were checked against the oracle at small sizes, tests/test_gpu_parity.py)."""
+    pkg, ops, ctx = env
+    n, c, h, w = 256, 64, 112, 112
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn((n, h, w, c), device="cuda", generator=g) * 1.2 + 0.1
+    scale = torch.rand((c,), device="cuda", generator=g) + 0.5
+    scale[::7] *= -1.0     # negative scales: the max of the normalised values is not the max of x
+    bias = 0.3 * torch.randn((c,), device="cuda", generator=g)
+    rm1, rv1 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    yp, idx, sm, si = ops.batch_norm_relu_max_pool_forward_train(ctx, 0.9, X, scale, bias, rm1, rv1)
+    y2, sm2, si2 = ops.batch_norm_2d_forward_train(ctx, 0.9, X, scale, bias, rm2, rv2, layout=pkg.ZB_NHWC, relu=True)
+    yp2, idx2 = ops.max_pool_2d_indexed(ctx, y2, 3, 2, 1)
+    for a, b in ((yp, yp2), (idx, idx2), (sm, sm2), (si, si2), (rm1, rm2), (rv1, rv2)):
+        assert torch.equal(a, b)
+    del yp2, idx2
+    DYP = torch.randn(tuple(yp.shape), device="cuda", generator=g)
+    dx, ds, db = ops.batch_norm_relu_max_pool_backward(ctx, X, DYP, idx, scale, bias, sm, si)
+    dy2 = ops.max_pool_2d_indexed_backward(ctx, DYP, idx, tuple(y2.shape), 3, 2, 1)
+    del y2
+    dx2, ds2, db2 = ops.batch_norm_2d_relu_backward(ctx, X, dy2, scale, bias, sm, si, layout=pkg.ZB_NHWC)
+    ctx.check()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(dx, dx2) < 5e-5 and rel(ds, ds2) < 5e-5 and rel(db, db2) < 5e-5
