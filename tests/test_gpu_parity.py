@@ -553,6 +553,54 @@ def test_conv_stride2_halo_planes(zb, ctx, case):
     ctx.check()
 
 
+@pytest.mark.parametrize("case", [
+    (5, 64, 7, 7, 64, 3, 1),        # 7x7, resident filter, odd batch: the last tile holds ONE image (the other is TMA zero fill)
+    (6, 128, 7, 7, 512, 3, 1),      # streamed filter, two column blocks, CTA pairs
+    (9, 64, 3, 7, 64, 3, 1),        # 3x7: four images per tile, the last tile holds one
+    (7, 32, 7, 3, 96, 3, 1),        # 7x3: four images per tile, N = 96 (partly empty BN = 128 column block)
+])
+def test_conv_small_maps_stacked_tiles(zb, ctx, case):
+    """Small feature maps (the 7x7 stage) on the halo kernel with several images per 128-row tile: the rasters are stacked with the
+    padding rows / columns shared between neighbouring rows and images.  fprop (+ bias, + fused statistics) and dgrad (plain, accumulate,
+    masked accumulate) against the tf32-rounded oracle (5e-5) and 3xTF32 against exact arithmetic (1e-5); the plan must name the mode."""
+    from zenu_b200 import ZB_MATH_TF32, ZB_MATH_TF32X3, ZB_NHWC
+    n, c, h, w_, k, r, pad = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((n, c, h, w_)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+    X, W = dev(nhwc(x)), dev(nhwc(wt))
+    plan = zb.conv_plan_describe(ctx, zb.PLAN_FPROP, tuple(X.shape), tuple(W.shape), pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert "halo_conv" in plan and "stack=1" not in plan, plan
+    shift = dev((0.1 * rng.standard_normal(k)).astype(np.float32))
+    y, partial, rows = zb.conv_fwd_bnstats(ctx, X, W, shift, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rows > 0
+    xr, wr = zo.tf32_round(x, "rne"), zo.tf32_round(wt, "rne")
+    y_ref = zo.conv2d_fwd(xr, wr, pad, 1, 1)
+    y_h = nchw(host(y))
+    assert rel_err(y_h, y_ref) < 5e-5
+    part = host(partial)[:rows].astype(np.float64).sum(axis=0)
+    dlt = y_h.astype(np.float64) - host(shift).astype(np.float64)[None, :, None, None]
+    np.testing.assert_allclose(part[0], dlt.sum(axis=(0, 2, 3)), rtol=1e-4, atol=1e-3 * np.sqrt(dlt[:, 0].size))
+    np.testing.assert_allclose(part[1], (dlt * dlt).sum(axis=(0, 2, 3)), rtol=1e-4)
+    y3 = zb.conv_fwd(ctx, X, W, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+    assert rel_err(nchw(host(y3)), zo.conv2d_fwd(x.astype(np.float64), wt.astype(np.float64), pad, 1, 1)) < 1e-5
+    dy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    DY = dev(nhwc(dy))
+    dplan = zb.conv_plan_describe(ctx, zb.PLAN_DGRAD, tuple(X.shape), tuple(W.shape), pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert "halo_conv" in dplan and "stack=1" not in dplan, dplan
+    dx = zb.conv_bkwd_data(ctx, DY, W, X.shape, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rel_err(nchw(host(dx)), zo.conv2d_bkwd_data(zo.tf32_round(dy, "rne"), wr, x.shape, pad, 1, 1)) < 5e-5
+    if c % 32 == 0:
+        old = torch.randn_like(dx)
+        words = torch.randint(-2 ** 31, 2 ** 31 - 1, ((old.numel() + 31) // 32,), dtype=torch.int64, device="cuda").to(torch.int32)
+        want = zb.mask_apply(ctx, old, words)
+        zb.conv_bkwd_data_accumulate(ctx, DY, W, want, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+        assert rel_err(host(want) - host(zb.mask_apply(ctx, old, words)), host(dx)) < 1e-4
+        zb.conv_bkwd_data_accumulate_masked(ctx, DY, W, old, words, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+        np.testing.assert_array_equal(host(old), host(want))
+    ctx.check()
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 def test_bn_fused_relu_residual(zb, ctx, layout):
     """Fused BN+add+ReLU fwd/bwd == the reference's separate nodes (BN -> add -> relu) composed from oracle ops."""

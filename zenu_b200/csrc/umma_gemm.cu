@@ -155,6 +155,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
     const FastDiv fd_win_img = fastdiv_make(p.win_p_tiles * p.win_q_tiles), fd_win_qt = fastdiv_make(p.win_q_tiles),
                   fd_win_bq = fastdiv_make(p.win_box_q);
     const FastDiv fd_pq = fastdiv_make(p.conv_P * p.conv_Q), fd_q = fastdiv_make(p.conv_Q);
+    const FastDiv fd_stack = fastdiv_make(p.halo_stack_rows > 0 ? p.halo_stack_rows : 1);
     const int cl_id = blockIdx.x / cluster, n_cl = gridDim.x / cluster, cl_rank = blockIdx.x % cluster;
     const int cl_groups = ((p.m_tiles + cluster - 1) / cluster) * p.n_tiles * p.tap_tiles * p.splits;
     for (int step = 0;; ++step) {
@@ -178,11 +179,20 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint8_t* smem
         const int l = ew * 32 + lane;
         if (p.out_mode == OUT_WINDOW) {
           const int per_img = p.win_p_tiles * p.win_q_tiles;
-          const int img = fastdiv(tc.m_blk, fd_win_img), rem = tc.m_blk - img * per_img;
+          int img = fastdiv(tc.m_blk, fd_win_img);
+          const int rem = tc.m_blk - img * per_img;
           const int pt = fastdiv(rem, fd_win_qt), qt = rem - pt * p.win_q_tiles;
-          const int pl = fastdiv(l, fd_win_bq), ql = l - pl * p.win_box_q;
+          int pl = fastdiv(l, fd_win_bq);
+          const int ql = l - pl * p.win_box_q;
+          bool img_ok = true;
+          if (p.halo_stack > 1) {   // stacked tile: window row pl = image pl / stack_rows of the group, output row pl % stack_rows
+            const int g = fastdiv(pl, fd_stack);
+            pl -= g * p.halo_stack_rows;
+            img = tc.m_blk * p.halo_stack + g;
+            img_ok = g < p.halo_stack && img < p.batch_n;
+          }
           const int pp = pt * p.win_box_p + pl, qq = qt * p.win_box_q + ql;
-          if (tile_exists && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q) {
+          if (tile_exists && img_ok && pl < p.win_box_p && pp < p.conv_P && qq < p.conv_Q) {
             if (p.scat_sy != 0)   // a parity class of a strided dgrad: window (pp, qq) is input pixel (pp * sy + oy, qq * sx + ox)
               my_off = ((static_cast<long long>(img) * p.scat_OH + pp * p.scat_sy + p.scat_oy) * p.scat_OW + qq * p.scat_sx + p.scat_ox) * p.ldd;
             else
@@ -821,6 +831,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tmem_relinquish();
     }
   }
+  if (p.halo_stack > 1) {   // the rows below the last image of every slot are its bottom padding: zero, and no TMA load ever writes them
+    for (int sl = 0; sl < p.halo_slots; ++sl) {
+      uint4* z = reinterpret_cast<uint4*>(sA + sl * p.halo_slot_bytes + p.halo_raster_bytes);
+      const int n16 = (p.halo_slot_bytes - p.halo_raster_bytes) / 16;
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's (async-proxy) operand reads
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
@@ -852,15 +870,19 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool ok = true;
       for (int q = cl_id; q < total_q && ok; q += n_cl) {
         const int n_blk = q % p.n_tiles, m_blk = (q / p.n_tiles) * CL + cl_rank;
-        const int img = m_blk / p.win_p_tiles, pt = m_blk - img * p.win_p_tiles;
+        const bool stacked = p.halo_stack > 1;
+        const int img = stacked ? m_blk * p.halo_stack : m_blk / p.win_p_tiles, pt = stacked ? 0 : m_blk - img * p.win_p_tiles;
         const int h0 = pt * p.win_box_p * p.halo_stride;
         for (int c = 0; c < chunks && ok; ++c) {
           if (!mbar_wait(&a_empty[ai], aph ^ 1, err)) { ok = false; break; }
           if (lead) mbar_arrive_expect_tx(&a_full[ai], kShare * static_cast<uint32_t>(p.halo_raster_bytes));
-          for (int pl = 0; pl < p.halo_planes; ++pl) {   // one raster (stride 1) or one per input parity class (stride 2)
+          // one raster (stride 1), one per input parity class (stride 2), or one per image of a stacked tile (an image past the end
+          // of the batch arrives as zero fill)
+          for (int pl = 0; pl < p.halo_planes; ++pl) {
             uint8_t* dst = sA + ai * p.halo_slot_bytes + pl * p.halo_plane_bytes;
-            if (PAIR) tma_load_4d_pair(dst, &tmA, afull0 + ai * 8, c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], img);
-            else tma_load_4d(dst, &tmA, &a_full[ai], c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], img);
+            const int im = stacked ? img + pl : img;
+            if (PAIR) tma_load_4d_pair(dst, &tmA, afull0 + ai * 8, c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], im);
+            else tma_load_4d(dst, &tmA, &a_full[ai], c * kUmmaBK, p.halo_dw[pl], h0 + p.halo_dh[pl], im);
           }
           if (++ai == p.halo_slots) { ai = 0; aph ^= 1; }
           if (!resident) {
@@ -1636,6 +1658,7 @@ struct HaloTapSet {
 struct HaloPlan {
   int Wr, tp, p_tiles, slots, slot_bytes, raster_bytes, b_stages, resident, bn;
   int stride, planes, plane_bytes, rows_pl;                 // stride-2 form: four parity planes per slot (see UmmaParams::halo_planes)
+  int stack, stack_rows;                                    // small maps: `stack` images per tile (see UmmaParams::halo_stack)
   int dh[4], dw[4], row_par[8], row_off[8], col_par[8], col_off[8];
   int pair;   // run on CTA pairs (halo_conv_kernel<BN, 2, true>): each CTA holds half of every filter tile
   size_t smem;
@@ -1677,22 +1700,45 @@ static bool halo_plan(zb_ctx* ctx, long long N, long long H, long long W, long l
   // balance the row blocks of an image (14 rows, tp 8 -> 7 + 7 instead of 8 + 6)
   const int p_tiles = ceil_div(P, tp);
   tp = ceil_div(P, p_tiles);
-  const int rows_pl = tp + max_row_off;   // raster rows per plane (stride 1: tp + R - 1)
+  int rows_pl = tp + max_row_off;   // raster rows per plane (stride 1: tp + R - 1)
   if (stride * (rows_pl - 1) + 1 > 256) return false;
-  if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) return false;  // too many dead MMA rows
-  hp->Wr = static_cast<int>(Wr); hp->tp = tp; hp->p_tiles = p_tiles; hp->rows_pl = rows_pl;
+  hp->stack = 1; hp->stack_rows = 0;
+  int Wr_i = static_cast<int>(Wr);
+  if (static_cast<double>(P * Q) / (static_cast<double>(p_tiles) * kUmmaBM) < 0.6) {   // too many dead MMA rows for one image per tile
+    // small maps (7x7): several images per tile, padding rows / columns shared between neighbours (UmmaParams::halo_stack)
+    if (stride != 1 || ts != nullptr || ZB_ENV_FLAG("ZENU_B200_NO_HALO_STACK")) return false;
+    if (S - 1 - pw > pw || R - 1 - ph > ph || pw < 0 || ph < 0) return false;   // the shared zeros must cover both sides
+    const int Ws = static_cast<int>(W) + pw, Hs = static_cast<int>(H) + ph;
+    if ((Hs * Ws) % 8 != 0) return false;                                       // every image's raster starts on a swizzle-pattern boundary
+    int G = 1;
+    while (G < 4 && (static_cast<long long>(G) * Hs + P) * Ws <= kUmmaBM) ++G;   // rows ((G - 1) * Hs + P) * Ws of the tile are live
+    if (G < 2 || N < G || static_cast<double>(G * P * Q) / kUmmaBM < 0.6) return false;
+    hp->stack = G; hp->stack_rows = Hs;
+    Wr_i = Ws; tp = static_cast<int>(P); rows_pl = Hs;
+    hp->Wr = Wr_i; hp->tp = tp; hp->p_tiles = 1; hp->rows_pl = rows_pl;
+  } else {
+    hp->Wr = Wr_i; hp->tp = tp; hp->p_tiles = p_tiles; hp->rows_pl = rows_pl;
+  }
   hp->bn = pick_bn(Kout);
   // CTA pairs: ZENU_B200_HALO_PAIR = 0 never, 1 only the N <= 128 layers, 2 (default) every layer.  Measured (tools/bench_conv.py --only
   // 3x3, fprop / dgrad): 256 -> 256 @14x14 0.113 -> 0.101 / 0.116 -> 0.105 ms, 128 -> 128 @28x28 0.145 -> 0.137 / 0.149 -> 0.138,
   // 64 -> 64 @56x56 0.211 -> 0.205 / 0.212 -> 0.205 (that layer is not bound by the MMA issue rate after all).
   static const int pair_mode = []() { const char* e = getenv("ZENU_B200_HALO_PAIR"); return e ? atoi(e) : 2; }();
-  hp->pair = (pair_mode > 0 && hp->bn >= 64 && (pair_mode > 1 || hp->bn <= 128) && N * p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 1 : 0;
-  const int plane_data = rows_pl * static_cast<int>(Wr) * 128;
-  hp->plane_bytes = hp->planes == 1 ? 0 : ((plane_data + 1023) & ~1023);   // every plane starts on a swizzle-pattern boundary
+  hp->pair = (pair_mode > 0 && hp->bn >= 64 && (pair_mode > 1 || hp->bn <= 128) && (N / hp->stack) * hp->p_tiles >= 2 && !ZB_ENV_FLAG("ZENU_B200_NO_CLUSTER")) ? 1 : 0;
+  const int plane_data = rows_pl * hp->Wr * 128;
+  if (hp->stack > 1) {
+    hp->planes = hp->stack;            // one TMA box per image, back to back
+    hp->plane_bytes = plane_data;      // (a multiple of 1024: checked above)
+    for (int g = 1; g < hp->stack; ++g) { hp->dh[g] = hp->dh[0]; hp->dw[g] = hp->dw[0]; }
+  } else {
+    hp->plane_bytes = hp->planes == 1 ? 0 : ((plane_data + 1023) & ~1023);   // every plane starts on a swizzle-pattern boundary
+  }
   hp->raster_bytes = hp->planes * plane_data;   // bytes the TMA loads of one slot deliver
   // rows a tap descriptor may touch beyond its raster (tap offset + 127 is the last row an MMA reads) stay inside the slot
-  const int last_row = max_row_off * static_cast<int>(Wr) + max_col_off + kUmmaBM;
+  const int last_row = max_row_off * hp->Wr + max_col_off + kUmmaBM;
   hp->slot_bytes = ((hp->planes - 1) * hp->plane_bytes + std::max(plane_data, last_row * 128) + 1023) & ~1023;
+  if (hp->stack > 1)   // + the zero rows below the last image (its bottom padding and the wrap of its last row), never written by TMA
+    hp->slot_bytes = (std::max(hp->stack * plane_data + ((R - 1 - ph) * hp->Wr + S) * 128, last_row * 128) + 1023) & ~1023;
   const int b_bytes = hp->bn * 128 / (hp->pair ? 2 : 1);
   const int chunks = static_cast<int>(Cin / 32);
   const int budget = 227 * 1024 - 1024 - 16384 - 48 * hp->bn - 1024;  // alignment slack, epilogue staging, BN statistics, barriers
@@ -1718,8 +1764,9 @@ static int halo_launch_bn(zb_ctx* ctx, const CUtensorMap& a, const CUtensorMap& 
   static SmemOptIn opt_in;
   { const int rc = smem_opt_in(ctx, opt_in, halo_conv_kernel<BN, CL, PAIR>, smem); if (rc != ZB_OK) return rc; }
   plan_note("halo_conv<bn=%d,cl=%d,pair=%d> resident=%d slots=%d b_stages=%d n_tiles=%d ntaps=%d c_chunks=%d beta=%d bias=%d stats=%d chain=%d tp=%d "
-            "planes=%d ~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
-            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.halo_planes, p.m_tiles, grid);
+            "planes=%d stack=%d ~m_tiles=%d ~grid=%d;", BN, CL, PAIR ? 1 : 0, p.halo_b_resident, p.halo_slots, p.halo_b_stages, p.n_tiles, p.ntaps, p.c_chunks,
+            p.beta != 0.f ? 1 : 0, p.bias != nullptr ? 1 : 0, p.stat_partial != nullptr ? 1 : 0, p.halo_chain, p.win_box_p, p.halo_planes, p.halo_stack,
+            p.m_tiles, grid);
   if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   if (CL == 1) {
@@ -1775,9 +1822,11 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
   p.out_mode = OUT_WINDOW;
   p.M = static_cast<int>(N * P * Q);
   p.N = static_cast<int>(Kout);
-  p.m_tiles = static_cast<int>(N) * hp.p_tiles;
+  p.m_tiles = hp.stack > 1 ? ceil_div(N, hp.stack) : static_cast<int>(N) * hp.p_tiles;
   p.n_tiles = ceil_div(Kout, hp.bn);
   p.win_box_q = hp.Wr; p.win_box_p = hp.tp; p.win_q_tiles = 1; p.win_p_tiles = hp.p_tiles;
+  p.halo_stack = hp.stack; p.halo_stack_rows = hp.stack_rows;
+  p.batch_n = static_cast<int>(N);
   p.conv_P = static_cast<int>(P); p.conv_Q = static_cast<int>(Q);
   p.lower_w = -pw; p.lower_h = -ph;
   p.ntaps = taps;
@@ -1795,6 +1844,7 @@ static int umma_conv_halo(zb_ctx* ctx, const HaloPlan& hp, long long N, long lon
                                                              hp.col_off[sx]);
   p.halo_planes = hp.planes; p.halo_plane_bytes = hp.plane_bytes; p.halo_stride = st_;
   for (int pl = 0; pl < 4; ++pl) { p.halo_dh[pl] = hp.dh[pl % hp.planes]; p.halo_dw[pl] = hp.dw[pl % hp.planes]; }
+  if (hp.stack > 1) p.halo_stride = 1;
   p.halo_slots = hp.slots; p.halo_slot_bytes = hp.slot_bytes; p.halo_raster_bytes = hp.raster_bytes;
   p.halo_b_stages = hp.b_stages; p.halo_b_resident = hp.resident;
   p.halo_chain = p.chain_kb > 0 ? std::max(1, p.chain_kb / taps) : 0;

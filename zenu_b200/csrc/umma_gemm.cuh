@@ -73,6 +73,10 @@ struct UmmaParams {
   // column of the tile); stride 1: one plane, halo_dh[0] / halo_dw[0] = -pad
   int halo_planes, halo_plane_bytes, halo_stride;
   int halo_dh[4], halo_dw[4];
+  // small feature maps (7x7): halo_stack images share ONE 128-row tile.  Their rasters ([pad rows, H rows] x [pad columns, W columns]
+  // each: the bottom / right padding of one row or image IS the top / left padding of the next, both are zeros) are stacked in the
+  // slot, one TMA box per image; window row ps of the tile = image ps / halo_stack_rows, output row ps % halo_stack_rows
+  int halo_stack, halo_stack_rows, batch_n;
   // accumulation-chain limit (3xTF32 mode): the tensor core adds into TMEM with truncation, a bias that grows with the number
   // of MMA steps; with chain_kb > 0 the accumulator is flushed through the epilogue (fp32 round-to-nearest adds into D) every
   // chain_kb K blocks (halo kernel: every halo_chain channel chunks) instead of once per tile.  0 = one chain per tile.
