@@ -598,6 +598,14 @@ def test_conv_small_maps_stacked_tiles(zb, ctx, case):
         assert rel_err(host(want) - host(zb.mask_apply(ctx, old, words)), host(dx)) < 1e-4
         zb.conv_bkwd_data_accumulate_masked(ctx, DY, W, old, words, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
         np.testing.assert_array_equal(host(old), host(want))
+    # backward filter: the pixel reduction of the halo wgrad kernel walks the same stacked rasters (dY's rows >= P and columns >= Q, and
+    # the images past the end of the batch, are TMA zero fill)
+    wplan = zb.conv_plan_describe(ctx, zb.PLAN_WGRAD, tuple(X.shape), tuple(W.shape), pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert "wgrad_halo" in wplan and "stack=1 " not in wplan, wplan
+    dw = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32)
+    assert rel_err(nchw(host(dw)), zo.conv2d_bkwd_filter(zo.tf32_round(dy, "rne"), xr, wt.shape, pad, 1, 1)) < 5e-5
+    dw3 = zb.conv_bkwd_weight(ctx, DY, X, W.shape, pad, 1, 1, layout=ZB_NHWC, math=ZB_MATH_TF32X3)
+    assert rel_err(nchw(host(dw3)), zo.conv2d_bkwd_filter(dy.astype(np.float64), x.astype(np.float64), wt.shape, pad, 1, 1)) < 1e-5
     ctx.check()
 
 

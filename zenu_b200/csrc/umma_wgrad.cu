@@ -40,6 +40,9 @@ struct WgHaloParams {
   int stage_bytes, stages, ring_bytes;
   int c_chunks, k_tiles, splits;
   int total_tiles, tiles_per_split;   // pixel tiles = N * p_tiles
+  // small feature maps (7x7): `stack` images per tile, their rasters ([pad rows, H rows] x [pad columns, W columns], bottom / right padding
+  // = the next row's / image's top / left padding) back to back, img_bytes each, one TMA box per image and operand (see UmmaParams::halo_stack)
+  int stack, img_bytes;
   int K, C;
   int lower_w, lower_h;
   float* partial;       // [splits][K][R*S*C]
@@ -105,14 +108,23 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       const uint32_t bytes = static_cast<uint32_t>(k_boxes) * p.a_tx_bytes + p.x_tx_bytes;
       for (int tile = t_begin; tile < t_end; ++tile) {
-        const int img = tile / p.p_tiles, pt = tile - img * p.p_tiles;
-        const int p0 = pt * p.tp;
         if (!mbar_wait(&empty_bar[stage], phase ^ 1, err)) break;
         mbar_arrive_expect_tx(&full_bar[stage], bytes);
         uint8_t* sA = smem + stage * p.stage_bytes;
         uint8_t* sX = sA + p.a_boxes * p.a_box_bytes;
-        for (int j = 0; j < k_boxes; ++j) tma_load_4d(sA + j * p.a_box_bytes, &tmA, &full_bar[stage], m0 + 32 * j, 0, p0, img);
-        tma_load_4d(sX, &tmB, &full_bar[stage], c0, p.lower_w, p0 + p.lower_h, img);
+        if (p.stack > 1) {   // an image past the end of the batch arrives as zero fill on both sides
+          for (int g = 0; g < p.stack; ++g) {
+            const int img = tile * p.stack + g;
+            for (int j = 0; j < k_boxes; ++j)
+              tma_load_4d(sA + j * p.a_box_bytes + g * p.img_bytes, &tmA, &full_bar[stage], m0 + 32 * j, 0, 0, img);
+            tma_load_4d(sX + g * p.img_bytes, &tmB, &full_bar[stage], c0, p.lower_w, p.lower_h, img);
+          }
+        } else {
+          const int img = tile / p.p_tiles, pt = tile - img * p.p_tiles;
+          const int p0 = pt * p.tp;
+          for (int j = 0; j < k_boxes; ++j) tma_load_4d(sA + j * p.a_box_bytes, &tmA, &full_bar[stage], m0 + 32 * j, 0, p0, img);
+          tma_load_4d(sX, &tmB, &full_bar[stage], c0, p.lower_w, p0 + p.lower_h, img);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -257,15 +269,39 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   const long long P = d->h + 2 * ph - R + 1, Q = d->w + 2 * pw - S + 1;
   const long long Wr = d->w + 2 * pw;
   if (P <= 0 || Q <= 0 || Wr > 256 || d->n * P > 0x3fffffffll) return ZB_ERR_UNSUPPORTED;
-  // tiny images (7x7): a tile is one image of <= 64 raster pixels, 42 KB of loads per 24 MMAs: L2 bound, the per-tap kernel wins
-  if (P * Wr <= 64 && !ZB_ENV_FLAG("ZENU_B200_WGRAD_HALO_ALL")) return ZB_ERR_UNSUPPORTED;
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
   p.R = R; p.S = S; p.Wr = static_cast<int>(Wr);
   p.K = static_cast<int>(d->k); p.C = static_cast<int>(d->c);
   p.a_boxes = static_cast<int>(std::min<long long>(4, (d->k + 31) / 32));
+  p.stack = 1;
   const int budget = 227 * 1024 - 1024 - 256;   // alignment slack, barriers
   bool found = false;
+  // tiny images (7x7): one image is <= 64 raster pixels, 42 KB of loads per 24 MMAs (L2 bound: the per-tap kernel wins), so several
+  // images share a tile: their rasters are stacked with the padding rows / columns shared between neighbours
+  const bool tiny = P * Wr <= 64 && !ZB_ENV_FLAG("ZENU_B200_WGRAD_HALO_ALL");
+  if (tiny) {
+    const int Ws = static_cast<int>(d->w) + pw, Hs = static_cast<int>(d->h) + ph;
+    if (ZB_ENV_FLAG("ZENU_B200_NO_HALO_STACK") || S - 1 - pw > pw || R - 1 - ph > ph || (Hs * Ws) % 8 != 0) return ZB_ERR_UNSUPPORTED;
+    for (int pass = 0; pass < 2 && !found; ++pass)   // first choice: three stages in flight, else two
+    for (int G = static_cast<int>(std::min<long long>(8, d->n)); G >= 2 && !found; --G) {
+      const int kt = G * Hs * Ws;   // raster pixels (GEMM-K rows) per tile, a multiple of 8
+      const int a_box = (kt * 128 + 1023) & ~1023;
+      const int x_rows = (R - 1) * Ws + (S - 1) + kt;
+      const int x_slot = (x_rows * 128 + 1023) & ~1023;
+      const int stage = p.a_boxes * a_box + x_slot;
+      const int tail = std::max(0, 4 * a_box - stage);
+      if ((pass == 0 ? 3 : 2) * stage + tail > budget) continue;
+      p.stack = G; p.img_bytes = Hs * Ws * 128;
+      p.Wr = Ws; p.tp = Hs; p.p_tiles = 1; p.kt_pad = kt; p.a_box_bytes = a_box; p.a_tx_bytes = kt * 128;
+      p.x_slot_bytes = x_slot; p.x_tx_bytes = kt * 128;
+      p.stage_bytes = stage;
+      p.stages = std::min(4, (budget - tail) / stage);
+      p.ring_bytes = p.stages * stage + tail;
+      found = true;
+    }
+    if (!found) return ZB_ERR_UNSUPPORTED;
+  }
   for (int tp0 = static_cast<int>(std::min<long long>(P, 256 - R + 1)); tp0 >= 1 && !found; --tp0) {
     const int p_tiles = ceil_div(P, tp0);
     const int tp = ceil_div(P, p_tiles);
@@ -286,7 +322,7 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if (!found) return ZB_ERR_UNSUPPORTED;
   p.c_chunks = static_cast<int>(d->c / 32);
   p.k_tiles = ceil_div(d->k, kUmmaBM);
-  p.total_tiles = static_cast<int>(d->n) * p.p_tiles;
+  p.total_tiles = p.stack > 1 ? ceil_div(d->n, p.stack) : static_cast<int>(d->n) * p.p_tiles;
   const int roles = p.c_chunks * p.k_tiles;
   int splits = std::max(1, std::min(p.total_tiles, (ctx->sm_count + roles - 1) / roles));
   if (roles * splits > ctx->sm_count && splits > 1 && roles * (splits - 1) >= (ctx->sm_count * 3) / 4) --splits;   // one wave, >= 75 % full
@@ -301,13 +337,14 @@ int umma_conv_wgrad_halo(zb_ctx* ctx, const zb_conv2d_desc* d, const float* dy, 
   if (rc != ZB_OK) return rc;
   p.partial = static_cast<float*>(ws);
   CUtensorMap ma, mb;
+  // (stacked: both boxes are one image's Wr x tp raster; dY rows >= P / columns >= Q and X's padding arrive as zero fill)
   if ((rc = make_raster_map(ctx, &ma, dy, d->n, P, Q, d->k, p.Wr, p.tp)) != ZB_OK) return rc;
-  if ((rc = make_raster_map(ctx, &mb, x, d->n, d->h, d->w, d->c, p.Wr, p.tp + R - 1)) != ZB_OK) return rc;
+  if ((rc = make_raster_map(ctx, &mb, x, d->n, d->h, d->w, d->c, p.Wr, p.stack > 1 ? p.tp : p.tp + R - 1)) != ZB_OK) return rc;
   const size_t smem = static_cast<size_t>(p.ring_bytes) + 256 + 1024;
   static SmemOptIn opt_in;
   { const int rc2 = smem_opt_in(ctx, opt_in, wgrad_halo_kernel, smem); if (rc2 != ZB_OK) return rc2; }
-  plan_note("wgrad_halo R=%d S=%d a_boxes=%d stages=%d roles=%d tp=%d beta=%d ~splits=%d ~grid=%d;wgrad_reduce;", R, S, p.a_boxes, p.stages, roles,
-            p.tp, beta != 0.f ? 1 : 0, p.splits, roles * p.splits);
+  plan_note("wgrad_halo R=%d S=%d a_boxes=%d stages=%d roles=%d tp=%d stack=%d beta=%d ~splits=%d ~grid=%d;wgrad_reduce;", R, S, p.a_boxes, p.stages, roles,
+            p.tp, p.stack, beta != 0.f ? 1 : 0, p.splits, roles * p.splits);
   if (plan_dry()) return ZB_OK;
   prof_begin(ctx, PROF_TENSOR);
   wgrad_halo_kernel<<<roles * p.splits, 192, smem, ctx->stream>>>(ma, mb, p);
