@@ -86,6 +86,58 @@ static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
   return g;
 }
 
+// Order in which an NHWC kernel of this file walks its rows.  For the apply kernels the result does not depend on it (for the
+// reduce kernels only the summation order does); what it decides is which part of the tensor a kernel touches FIRST, i.e.
+// whether it finds the lines its producer touched LAST still in the 126 MB L2.
+//   ROWS_SLAB_UP     the grid's y index owns one contiguous slab and walks it upwards
+//   ROWS_SLAB_DOWN   same slabs, walked downwards: a second pass that starts where a ROWS_SLAB_UP pass over the same slabs ended
+//   ROWS_SWEEP_DOWN  small slabs handed out round-robin from the END of the tensor, so the whole grid moves through memory as
+//                    one front, last row first: follows a convolution, whose persistent CTAs write their row tiles in
+//                    ascending order, and leaves the FIRST rows of its own output in L2 for the next convolution
+//   ROWS_SWEEP_UP    the same front, first row first: the second pass after a ROWS_SWEEP_DOWN statistics pass
+enum { ROWS_SLAB_UP = 0, ROWS_SLAB_DOWN = 1, ROWS_SWEEP_DOWN = 2, ROWS_SWEEP_UP = 3 };
+struct RowWalk {
+  long long rows_per_slab, nslabs;
+  int sweep, down;
+};
+#define ZB_ROW_WALK_BEGIN(walk, rows, ty, ty_n)                                                                        \
+  {                                                                                                                    \
+    long long zb_s = ((walk).sweep && (walk).down) ? (walk).nslabs - 1 - blockIdx.y : blockIdx.y;                      \
+    const long long zb_sstep = !(walk).sweep ? (walk).nslabs                                                           \
+                                             : (walk).down ? -static_cast<long long>(gridDim.y) : static_cast<long long>(gridDim.y); \
+    const long long step = (walk).down ? -(ty_n) : (ty_n);                                                             \
+    for (; zb_s >= 0 && zb_s < (walk).nslabs; zb_s += zb_sstep) {                                                      \
+      const long long r0 = zb_s * (walk).rows_per_slab;                                                                \
+      const long long r1 = (r0 + (walk).rows_per_slab < (rows)) ? r0 + (walk).rows_per_slab : (rows);                  \
+      long long r = (walk).down ? r1 - 1 - (ty) : r0 + (ty);                                                           \
+      auto zb_in = [r0, r1](long long q) { return q >= r0 && q < r1; };
+#define ZB_ROW_WALK_END \
+    }                   \
+  }
+
+// Row-order policy (A/B knob ZENU_B200_BN_ORDER): 0 = every kernel walks its slab upwards (round 1); 1 = the forward apply follows
+// the conv that produced x, the backward apply walks the statistics pass's slabs downwards; 2 (default) = additionally the backward
+// statistics pass sweeps downwards behind the dgrad that produced dy and the backward apply sweeps back up.
+static int bn_row_order_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("ZENU_B200_BN_ORDER"); mode = e ? atoi(e) : 2; }
+  return mode;
+}
+
+static RowWalk make_walk(const ColGeom& g, long long rows, int order) {
+  RowWalk w;
+  w.sweep = order >= ROWS_SWEEP_DOWN;
+  w.down = order == ROWS_SLAB_DOWN || order == ROWS_SWEEP_DOWN;
+  if (w.sweep) {
+    w.rows_per_slab = g.ty * 8ll;   // every thread row takes 8 rows of a small slab (two unrolled groups of 4)
+    w.nslabs = (rows + w.rows_per_slab - 1) / w.rows_per_slab;
+  } else {
+    w.rows_per_slab = g.rows_per_slab;
+    w.nslabs = g.slabs;
+  }
+  return w;
+}
+
 // ---- functors for the NHWC column reduce: NS statistics from up to three input streams -------------------
 template <typename T, int VN>
 struct StatsF {  // sum(x - shift), sum((x - shift)^2); shift = first row
@@ -161,7 +213,7 @@ struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
 template <typename T, int VN, typename F>
 __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict__ in0, const T* __restrict__ in1,
                                                        const T* __restrict__ in2, T* __restrict__ partial, long long rows,
-                                                       long long C, long long rows_per_slab, int tx_n, int ty_n) {
+                                                       long long C, RowWalk walk, int tx_n, int ty_n) {
   constexpr int NS = F::NS;
   extern __shared__ unsigned char red_raw[];
   T* red = reinterpret_cast<T*>(red_raw);  // [ty][NS][tx*VN]
@@ -169,8 +221,6 @@ __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict_
   const long long cv = static_cast<long long>(blockIdx.x) * tx_n + tx;
   const bool active = cv * VN < C;
   const long long c0 = cv * VN;
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
-  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
   T acc[NS][VN];
 #pragma unroll
   for (int s = 0; s < NS; ++s)
@@ -179,20 +229,20 @@ __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict_
   if (active) {
     f.init(c0);
     constexpr int U = 4;
-    long long r = r0 + ty;
-    for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+    ZB_ROW_WALK_BEGIN(walk, rows, ty, ty_n)
+    for (; zb_in(r + (U - 1) * step); r += U * step) {
       T a[U][VN], b[U][VN], c[U][VN];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long off = (r + u * ty_n) * C + c0;
+        const long long off = (r + u * step) * C + c0;
         ldv<T, VN>(in0 + off, a[u]);
         if (F::NIN >= 2) ldv<T, VN>(in1 + off, b[u]);
         if (F::NIN >= 3) ldv<T, VN>(in2 + off, c[u]);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) f(a[u], b[u], c[u], acc, (r + u * ty_n) * C + c0);
+      for (int u = 0; u < U; ++u) f(a[u], b[u], c[u], acc, (r + u * step) * C + c0);
     }
-    for (; r < r1; r += ty_n) {
+    for (; zb_in(r); r += step) {
       T a[VN], b[VN], c[VN];
       const long long off = r * C + c0;
       ldv<T, VN>(in0 + off, a);
@@ -200,6 +250,7 @@ __global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict_
       if (F::NIN >= 3) ldv<T, VN>(in2 + off, c);
       f(a, b, c, acc, off);
     }
+    ZB_ROW_WALK_END
   }
   const int row_elems = NS * tx_n * VN;
 #pragma unroll
@@ -390,7 +441,7 @@ template <typename T, int VN, bool RELU, bool RES>
 __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ res,
                                                      T* __restrict__ y, const T* __restrict__ coef,
                                                      const T* __restrict__ gamma, const T* __restrict__ beta,
-                                                     long long rows, long long C, long long rows_per_slab, int tx_n,
+                                                     long long rows, long long C, RowWalk walk, int tx_n,
                                                      int ty_n, uint32_t* __restrict__ mask = nullptr) {
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const long long c0 = (static_cast<long long>(blockIdx.x) * tx_n + tx) * VN;
@@ -398,15 +449,13 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
   T m[VN], iv[VN], g[VN], b[VN];
 #pragma unroll
   for (int e = 0; e < VN; ++e) { m[e] = coef[c0 + e]; iv[e] = coef[C + c0 + e]; g[e] = gamma[c0 + e]; b[e] = beta[c0 + e]; }
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
-  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
+  ZB_ROW_WALK_BEGIN(walk, rows, ty, ty_n)
   constexpr int U = 4;
-  long long r = r0 + ty;
-  for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+  for (; zb_in(r + (U - 1) * step); r += U * step) {
     T a[U][VN], rr[U][VN];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long off = (r + u * ty_n) * C + c0;
+      const long long off = (r + u * step) * C + c0;
       ldv<T, VN>(x + off, a[u]);
       if (RES) ldv<T, VN>(res + off, rr[u]);
     }
@@ -421,11 +470,11 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
         if (RELU) { nib |= (v > T(0) ? 1u : 0u) << e; v = v > T(0) ? v : T(0); }
         o[e] = v;
       }
-      stv<T, VN>(y + (r + u * ty_n) * C + c0, o);
-      if (RELU && VN == 4 && mask != nullptr) store_mask_nibble(mask, (r + u * ty_n) * C + c0, nib);
+      stv<T, VN>(y + (r + u * step) * C + c0, o);
+      if (RELU && VN == 4 && mask != nullptr) store_mask_nibble(mask, (r + u * step) * C + c0, nib);
     }
   }
-  for (; r < r1; r += ty_n) {
+  for (; zb_in(r); r += step) {
     T a[VN], rr[VN], o[VN];
     const long long off = r * C + c0;
     ldv<T, VN>(x + off, a);
@@ -441,6 +490,7 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
     stv<T, VN>(y + off, o);
     if (RELU && VN == 4 && mask != nullptr) store_mask_nibble(mask, off, nib);
   }
+  ZB_ROW_WALK_END
 }
 
 // backward: dx = coef * (dy' - c1 - xhat * c2);  dres = dy'
@@ -450,7 +500,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
                                                          T* __restrict__ dres, const T* __restrict__ mean,
                                                          const T* __restrict__ inv, const T* __restrict__ coef,
                                                          const T* __restrict__ gamma, const T* __restrict__ beta,
-                                                         long long rows, long long C, long long rows_per_slab, int tx_n,
+                                                         long long rows, long long C, RowWalk walk, int tx_n,
                                                          int ty_n, const uint32_t* __restrict__ bits = nullptr) {
   // MASK 4: the gradient is dy masked by a 1-bit-per-element array (bit index = NHWC element index)
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
@@ -463,15 +513,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
     k0[e] = coef[c0 + e]; k1[e] = coef[C + c0 + e]; k2[e] = coef[2 * C + c0 + e];
     if (MASK == 2) { ga[e] = gamma[c0 + e]; be[e] = beta[c0 + e]; }
   }
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
-  const long long r1 = (r0 + rows_per_slab < rows) ? r0 + rows_per_slab : rows;
+  ZB_ROW_WALK_BEGIN(walk, rows, ty, ty_n)
   constexpr int U = MASK == 1 ? 2 : 4;
-  long long r = r0 + ty;
-  for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+  for (; zb_in(r + (U - 1) * step); r += U * step) {
     T a[U][VN], g[U][VN], yy[U][VN];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long off = (r + u * ty_n) * C + c0;
+      const long long off = (r + u * step) * C + c0;
       ldv<T, VN>(x + off, a[u]);
       ldv<T, VN>(dy + off, g[u]);
       if (MASK == 1) ldv<T, VN>(y + off, yy[u]);
@@ -480,7 +528,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
     for (int u = 0; u < U; ++u) {
       T o[VN], gm[VN];
       unsigned nib = 0u;
-      if (MASK == 4) { const long long off = (r + u * ty_n) * C + c0; nib = __ldg(bits + (off >> 5)) >> (off & 31); }
+      if (MASK == 4) { const long long off = (r + u * step) * C + c0; nib = __ldg(bits + (off >> 5)) >> (off & 31); }
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         bool keep = true;
@@ -490,12 +538,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
         gm[e] = keep ? g[u][e] : T(0);
         o[e] = k0[e] * (gm[e] - k1[e] - ((a[u][e] - m[e]) * iv[e]) * k2[e]);
       }
-      const long long off = (r + u * ty_n) * C + c0;
+      const long long off = (r + u * step) * C + c0;
       stv<T, VN>(dx + off, o);
       if (DRES) stv<T, VN>(dres + off, gm);
     }
   }
-  for (; r < r1; r += ty_n) {
+  for (; zb_in(r); r += step) {
     T a[VN], g[VN], yy[VN], o[VN], gm[VN];
     const long long off = r * C + c0;
     ldv<T, VN>(x + off, a);
@@ -515,6 +563,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
     stv<T, VN>(dx + off, o);
     if (DRES) stv<T, VN>(dres + off, gm);
   }
+  ZB_ROW_WALK_END
 }
 
 // NCHW apply kernels: one block per (n, c) plane.
@@ -562,7 +611,8 @@ template <typename T> constexpr int vec_n() { return 16 / sizeof(T); }
 // Runs a column reduce (NHWC or NCHW) into `partial` ([slabs][NS][C]); returns the slab count.
 template <typename T, template <typename, int> class FT, typename Init>
 static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* in0, const T* in1,
-                          const T* in2, T* partial, long long partial_cap_elems, Init init, int* slabs_out) {
+                          const T* in2, T* partial, long long partial_cap_elems, Init init, int* slabs_out,
+                          int order = ROWS_SLAB_UP) {
   const long long rows = N * HW;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
@@ -574,7 +624,7 @@ static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, lon
       ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
       dim3 grid(g.col_groups, g.slabs);
       const size_t smem = sizeof(T) * g.ty * F::NS * g.tx * VN;
-      col_reduce_nhwc<T, VN, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, g.rows_per_slab, g.tx, g.ty);
+      col_reduce_nhwc<T, VN, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, make_walk(g, rows, order), g.tx, g.ty);
       ZB_LAUNCH_CHECK(ctx);
       *slabs_out = g.slabs;
     } else {
@@ -584,7 +634,7 @@ static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, lon
       ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
       dim3 grid(g.col_groups, g.slabs);
       const size_t smem = sizeof(T) * g.ty * F::NS * g.tx;
-      col_reduce_nhwc<T, 1, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, g.rows_per_slab, g.tx, g.ty);
+      col_reduce_nhwc<T, 1, F><<<grid, 256, smem, ctx->stream>>>(f, in0, in1, in2, partial, rows, C, make_walk(g, rows, order), g.tx, g.ty);
       ZB_LAUNCH_CHECK(ctx);
       *slabs_out = g.slabs;
     }
@@ -621,7 +671,7 @@ static long long max_slabs(zb_ctx* ctx, int layout, long long N, long long C) {
 
 template <typename T, bool RELU, bool RES>
 static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
-                        const T* coef, const T* gamma, const T* beta, uint32_t* mask = nullptr) {
+                        const T* coef, const T* gamma, const T* beta, uint32_t* mask = nullptr, int order = ROWS_SLAB_UP) {
   const long long rows = N * HW;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
@@ -630,12 +680,12 @@ static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long 
       ColGeom g = col_geom(ctx, rows, C, VN);
       dim3 grid(g.col_groups, g.slabs);
       ZB_REQUIRE(mask == nullptr || (sizeof(T) == 4 && RELU && C % 32 == 0), "bn: ReLU bit mask needs f32, relu and C %% 32 == 0");
-      bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty, mask);
+      bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty, mask);
     } else {
       ZB_REQUIRE(mask == nullptr, "bn: ReLU bit mask needs 16-byte aligned NHWC tensors");
       ColGeom g = col_geom(ctx, rows, C, 1);
       dim3 grid(g.col_groups, g.slabs);
-      bn_apply_nhwc<T, 1, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+      bn_apply_nhwc<T, 1, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty);
     }
   } else {
     ZB_REQUIRE(mask == nullptr, "bn: ReLU bit mask is NHWC only");
@@ -647,12 +697,13 @@ static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long 
 
 template <typename T>
 static int dispatch_apply(zb_ctx* ctx, int layout, long long N, long long C, long long HW, const T* x, const T* res, T* y,
-                          const T* coef, const T* gamma, const T* beta, int relu, uint32_t* mask = nullptr) {
+                          const T* coef, const T* gamma, const T* beta, int relu, uint32_t* mask = nullptr,
+                          int order = ROWS_SLAB_UP) {
   ZB_REQUIRE(mask == nullptr || relu, "bn: a ReLU bit mask without relu");
-  if (relu && res) return launch_apply<T, true, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask);
-  if (relu) return launch_apply<T, true, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask);
-  if (res) return launch_apply<T, false, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
-  return launch_apply<T, false, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta);
+  if (relu && res) return launch_apply<T, true, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask, order);
+  if (relu) return launch_apply<T, true, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, mask, order);
+  if (res) return launch_apply<T, false, true>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, nullptr, order);
+  return launch_apply<T, false, false>(ctx, layout, N, C, HW, x, res, y, coef, gamma, beta, nullptr, order);
 }
 
 template <typename T>
@@ -687,7 +738,9 @@ static int bn_fwd_train_t(zb_ctx* ctx, int layout, long long N, long long C, lon
                                                                  saved_inv, coef);
     ZB_LAUNCH_CHECK(ctx);
   }
-  rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu, relu_mask);
+  // statistics from the conv epilogue: x was written by a convolution, last row tiles last; own statistics pass: same slabs
+  rc = dispatch_apply<T>(ctx, layout, N, C, HW, x, res, y, coef, scale, bias, relu, relu_mask,
+                         bn_row_order_mode() == 0 ? ROWS_SLAB_UP : pre_partial != nullptr ? ROWS_SWEEP_DOWN : ROWS_SLAB_DOWN);
   // algorithmic bytes: x read twice (once when the statistics came with the conv) + y written (+ residual read)
   prof_end(ctx, PROF_BN, static_cast<double>(N * C * HW) * sizeof(T) * ((res ? 4.0 : 3.0) - (pre_partial ? 1.0 : 0.0)));
   return rc;
@@ -710,6 +763,7 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
                             const T* y, T* dx, T* dres, const T* mean, const T* inv, const T* coef, const T* gamma,
                             const T* beta, const uint32_t* bits = nullptr) {
   const long long rows = N * HW;
+  const int order = bn_row_order_mode() == 0 ? ROWS_SLAB_UP : bn_row_order_mode() == 1 ? ROWS_SLAB_DOWN : ROWS_SWEEP_UP;
   if (layout == ZB_NHWC) {
     constexpr int VN = vec_n<T>();
     const bool vec = (C % VN == 0) && al16(x) && al16(dy) && al16(y) && al16(dx) && al16(dres);
@@ -717,11 +771,11 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
     if (vec) {
       ColGeom g = col_geom(ctx, rows, C, VN);
       dim3 grid(g.col_groups, g.slabs);
-      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty, bits);
+      bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty, bits);
     } else {
       ColGeom g = col_geom(ctx, rows, C, 1);
       dim3 grid(g.col_groups, g.slabs);
-      bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, g.rows_per_slab, g.tx, g.ty);
+      bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty);
     }
   } else {
     bn_bwd_apply_nchw<T, MASK, DRES><<<static_cast<unsigned>(N * C), 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, C, HW);
@@ -763,24 +817,25 @@ static int bn_bwd_t(zb_ctx* ctx, int layout, long long N, long long C, long long
     if (inv == nullptr) inv = stats + C;
   }
   prof_begin(ctx, PROF_BN);
+  const int rorder = bn_row_order_mode() >= 2 ? ROWS_SWEEP_DOWN : ROWS_SLAB_UP;   // dy was written by a dgrad, last row tiles last
   if (relu_bias != nullptr)
     rc = run_col_reduce<T, BnBwdRecomputeFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
-                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs);
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gamma = scale; f.beta = relu_bias; }, &slabs, rorder);
   else if (relu_mask != nullptr && dres == nullptr)   // the masked gradient is not materialised (see BnBwdF, MASK 5)
     rc = run_col_reduce<T, BnBwdBitsFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
-                                        [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = nullptr; f.bits = relu_mask; }, &slabs);
+                                        [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = nullptr; f.bits = relu_mask; }, &slabs, rorder);
   else if (relu_mask != nullptr)
     rc = run_col_reduce<T, BnBwdBitsStoreFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
-                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; f.bits = relu_mask; }, &slabs);
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; f.bits = relu_mask; }, &slabs, rorder);
   else if (y != nullptr && dres != nullptr)
     rc = run_col_reduce<T, BnBwdMaskStoreFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
-                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; }, &slabs);
+                                             [&](auto& f) { f.mean = mean; f.inv = inv; f.gm_out = dres; }, &slabs, rorder);
   else if (y != nullptr)
     rc = run_col_reduce<T, BnBwdMaskFT>(ctx, layout, N, C, HW, x, dy, y, partial, ms * 2 * C,
-                                        [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
+                                        [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs, rorder);
   else
     rc = run_col_reduce<T, BnBwdNoMaskFT>(ctx, layout, N, C, HW, x, dy, static_cast<const T*>(nullptr), partial, ms * 2 * C,
-                                          [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs);
+                                          [&](auto& f) { f.mean = mean; f.inv = inv; }, &slabs, rorder);
   if (rc != ZB_OK) return rc;
   bn_bwd_finalize<T><<<ZB_FIN_GRID(C), 0, ctx->stream>>>(partial, slabs, C, static_cast<double>(N * HW), scale, inv,
                                                                dscale, dbias, coef);
