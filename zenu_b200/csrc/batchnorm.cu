@@ -36,6 +36,16 @@ __device__ __forceinline__ void ldv(const T* p, T* o) {
 #pragma unroll
   for (int e = 0; e < VN; ++e) o[e] = s[e];
 }
+// Load of a line that nobody reads again soon (second pass of a BatchNorm): ld.global.cs marks it evict-first in L2, so the pass's
+// own dead lines are displaced before the lines it has yet to reach (left there by the previous kernel) and before its output.
+template <typename T, int VN>
+__device__ __forceinline__ void ldv_once(const T* p, T* o, bool once) {
+  using V = typename VecT<T, VN>::type;
+  const V v = once ? __ldcs(reinterpret_cast<const V*>(p)) : *reinterpret_cast<const V*>(p);
+  const T* s = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int e = 0; e < VN; ++e) o[e] = s[e];
+}
 template <typename T, int VN>
 __device__ __forceinline__ void stv(T* p, const T* o) {
   using V = typename VecT<T, VN>::type;
@@ -99,6 +109,7 @@ enum { ROWS_SLAB_UP = 0, ROWS_SLAB_DOWN = 1, ROWS_SWEEP_DOWN = 2, ROWS_SWEEP_UP 
 struct RowWalk {
   long long rows_per_slab, nslabs;
   int sweep, down;
+  int once;   // apply kernels: the inputs are read with ldv_once
 };
 #define ZB_ROW_WALK_BEGIN(walk, rows, ty, ty_n)                                                                        \
   {                                                                                                                    \
@@ -126,6 +137,9 @@ static int bn_row_order_mode() {
 
 static RowWalk make_walk(const ColGeom& g, long long rows, int order) {
   RowWalk w;
+  static int once = -1;   // A/B knob: ZENU_B200_BN_LDCS=0 loads everything with the default policy
+  if (once < 0) { const char* e = getenv("ZENU_B200_BN_LDCS"); once = e ? atoi(e) : 1; }
+  w.once = once;
   w.sweep = order >= ROWS_SWEEP_DOWN;
   w.down = order == ROWS_SLAB_DOWN || order == ROWS_SWEEP_DOWN;
   if (w.sweep) {
@@ -456,8 +470,8 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long off = (r + u * step) * C + c0;
-      ldv<T, VN>(x + off, a[u]);
-      if (RES) ldv<T, VN>(res + off, rr[u]);
+      ldv_once<T, VN>(x + off, a[u], walk.once);
+      if (RES) ldv_once<T, VN>(res + off, rr[u], walk.once);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -477,8 +491,8 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
   for (; zb_in(r); r += step) {
     T a[VN], rr[VN], o[VN];
     const long long off = r * C + c0;
-    ldv<T, VN>(x + off, a);
-    if (RES) ldv<T, VN>(res + off, rr);
+    ldv_once<T, VN>(x + off, a, walk.once);
+    if (RES) ldv_once<T, VN>(res + off, rr, walk.once);
     unsigned nib = 0u;
 #pragma unroll
     for (int e = 0; e < VN; ++e) {
@@ -520,9 +534,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long off = (r + u * step) * C + c0;
-      ldv<T, VN>(x + off, a[u]);
-      ldv<T, VN>(dy + off, g[u]);
-      if (MASK == 1) ldv<T, VN>(y + off, yy[u]);
+      ldv_once<T, VN>(x + off, a[u], walk.once);
+      ldv_once<T, VN>(dy + off, g[u], walk.once);
+      if (MASK == 1) ldv_once<T, VN>(y + off, yy[u], walk.once);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -546,9 +560,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x
   for (; zb_in(r); r += step) {
     T a[VN], g[VN], yy[VN], o[VN], gm[VN];
     const long long off = r * C + c0;
-    ldv<T, VN>(x + off, a);
-    ldv<T, VN>(dy + off, g);
-    if (MASK == 1) ldv<T, VN>(y + off, yy);
+    ldv_once<T, VN>(x + off, a, walk.once);
+    ldv_once<T, VN>(dy + off, g, walk.once);
+    if (MASK == 1) ldv_once<T, VN>(y + off, yy, walk.once);
     unsigned nib = 0u;
     if (MASK == 4) nib = __ldg(bits + (off >> 5)) >> (off & 31);
 #pragma unroll
