@@ -1,23 +1,16 @@
 mkdir -p gpurun_out
 b() { # name env...
   n=$1; shift
-  env "$@" timeout 200 python bench.py --no-cpu-baseline --steps 20 --warmup 5 $EXTRA 2>gpurun_out/r2p_err_$n.log | tee -a gpurun_out/r2p_bench_$n.json | python -c "
+  env "$@" timeout 200 python bench.py --no-cpu-baseline --steps 20 --warmup 5 $EXTRA 2>gpurun_out/r2o_err_$n.log | tee -a gpurun_out/r2o_bench_$n.json | python -c "
 import json,sys
 for l in sys.stdin:
     d=json.loads(l); print('$n', d['metric'], round(d['ms_per_step'],4), round(d['e2e']['ms_per_step'],4), d['clocks']['sm_mhz'], d.get('step_graphs'), d['tape_nodes_by_class']['bn']['ms_per_step'], d['tape_nodes_by_class']['conv']['ms_per_step'], d['final_loss'])
 "
 }
-b pdl0_cs0 ZENU_B200_PDL=0 ZENU_B200_BN_LDCS=0
-b pdl0_cs1 ZENU_B200_PDL=0 ZENU_B200_BN_LDCS=1
-b pdl1_cs1 ZENU_B200_PDL=1 ZENU_B200_BN_LDCS=1
-b pdl1_cs0 ZENU_B200_PDL=1 ZENU_B200_BN_LDCS=0
-b pdl0_cs0 ZENU_B200_PDL=0 ZENU_B200_BN_LDCS=0
-b pdl1_cs1 ZENU_B200_PDL=1 ZENU_B200_BN_LDCS=1
-EXTRA="--arch small_cnn"
-b s_pdl0 ZENU_B200_PDL=0
-b s_pdl1 ZENU_B200_PDL=1
-EXTRA="--arch resnet18"
-b r18_pdl0 ZENU_B200_PDL=0
-b r18_pdl1 ZENU_B200_PDL=1
-timeout 400 python -m pytest tests/test_gpu_model.py -m gpu -x -q > gpurun_out/r2p_model_tests.log 2>&1; tail -n 3 gpurun_out/r2p_model_tests.log
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bn or golden or gemm or elementwise or pool" > gpurun_out/r2p_parity_tests.log 2>&1; tail -n 3 gpurun_out/r2p_parity_tests.log
+b once0 ZENU_B200_TMA_ONCE=0
+b once1 ZENU_B200_TMA_ONCE=1
+b once0 ZENU_B200_TMA_ONCE=0
+b once1 ZENU_B200_TMA_ONCE=1
+ZENU_B200_TMA_ONCE=0 timeout 200 python tools/profile_step.py --out gpurun_out/r2o_step_profile_once0.tsv > /dev/null 2>&1
+ZENU_B200_TMA_ONCE=1 timeout 200 python tools/profile_step.py --out gpurun_out/r2o_step_profile_once1.tsv > /dev/null 2>&1
+timeout 240 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "conv_vs_oracle or conv_golden or dgrad_accumulate or gemm" > gpurun_out/r2o_parity_tests.log 2>&1; tail -n 3 gpurun_out/r2o_parity_tests.log
