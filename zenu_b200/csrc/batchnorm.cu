@@ -143,7 +143,9 @@ static RowWalk make_walk(const ColGeom& g, long long rows, int order) {
   w.sweep = order >= ROWS_SWEEP_DOWN;
   w.down = order == ROWS_SLAB_DOWN || order == ROWS_SWEEP_DOWN;
   if (w.sweep) {
-    w.rows_per_slab = g.ty * 8ll;   // every thread row takes 8 rows of a small slab (two unrolled groups of 4)
+    static int per = -1;   // rows every thread row takes of a small slab (tuning knob: ZENU_B200_BN_SWEEP_ROWS)
+    if (per < 0) { const char* e = getenv("ZENU_B200_BN_SWEEP_ROWS"); per = e ? std::max(4, atoi(e)) : 8; }
+    w.rows_per_slab = g.ty * static_cast<long long>(per);
     w.nslabs = (rows + w.rows_per_slab - 1) / w.rows_per_slab;
   } else {
     w.rows_per_slab = g.rows_per_slab;
