@@ -335,12 +335,22 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     prefetch(0)
     loss_host = 0.0
+    # Every step's loss is read on the host inside the timed region, one step behind (zb_model_train_step_async / zb_model_loss_wait:
+    # the loss lands in a pinned ring slot behind its step; the host blocks on step i-1 after it has enqueued step i, the last loss
+    # is waited for before the region ends), so the device has the next step queued while the host stages the one after.
+    losses_read = 0
     for i in range(args.steps):
         if i + 1 < args.steps:
             prefetch((i + 1) % 2)
         xb, tb = fetch(i)
-        loss_host = model.train_step(xb, tb, loss_out=loss_dev, read_loss=True)   # D2H read of the loss, synchronises
+        model.train_step_async(xb, tb, loss_dev)
         done(i)
+        if i > 0:
+            loss_host = model.loss_wait(1)   # D2H read of step i-1's loss
+            losses_read += 1
+    loss_host = model.loss_wait(0)           # ... and of the last step's
+    losses_read += 1
+    assert losses_read == args.steps
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -420,6 +430,8 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "loss": loss_host,
                 "input": "uint8 NHWC images + int32 labels through zb_input_stage_* (pinned, double-buffered, expanded on the device)"
                          if args.e2e_input == "u8" else "f32 NCHW batch + f32 one-hot targets from pinned memory (torch copy stream)",
+                "loss_read": "every step's loss is copied to the host inside the timed region, read one step behind "
+                             "(zb_model_train_step_async / zb_model_loss_wait); the last one is waited for before the region ends",
                 "step_graphs": e2e_graphs},
         "roofline": roofline, "roofline_by_class": secondary, "tape_nodes_by_class": by_node, "whole_step_roofline": whole,
         "step_model_flops": {"algorithmic_tflop_per_step_per_gpu": train_tflop_per_step,

@@ -382,6 +382,14 @@ int zb_model_update(zb_model* m); /* Optimizer::update */
 /* forward_backward + update; if host_loss != NULL the loss is copied back (synchronises the stream) */
 int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
                         int64_t h, int64_t w, void* loss_dev, double* host_loss);
+/* zb_model_train_step without waiting for it: the step is enqueued and its loss is copied, behind it on the compute stream, into a
+ * pinned two-slot ring.  zb_model_loss_wait(m, age, &v) blocks until the step enqueued `age` calls ago (0 = the latest, 1 = the one
+ * before it) has completed and returns its loss.  A loop that logs every step's loss waits with age 1 right after enqueueing, so the
+ * device never idles while the host stages the next batch (the reference's loop reads the loss synchronously each step:
+ * zenu/examples/mnist.rs:138 `loss.get_data().asum()`). */
+int zb_model_train_step_async(zb_model* m, const void* x_nchw, const void* targets_onehot, int64_t batch, int64_t c,
+                              int64_t h, int64_t w, void* loss_dev);
+int zb_model_loss_wait(zb_model* m, int age, double* host_loss);
 /* CUDA-graph replay of zb_model_train_step (the reference rebuilds and walks its Rc<RefCell> tape every step,
  * zenu-autograd/src/lib.rs:220-237): after two eager steps the step is captured from the compute stream once per distinct
  * (buffers, shape) signature and replayed, NCCL bucket allreduces included.  Needs a ctx whose compute stream can be captured

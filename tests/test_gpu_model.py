@@ -213,6 +213,55 @@ def test_train_step_graph_replay_matches_eager(zb, arch, n, hw, classes, opt):
         assert torch.equal(pa[k], pb[k]), k
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_step_async_loss_ring(zb, graph):
+    """zb_model_train_step_async / zb_model_loss_wait: the step is enqueued without a host wait, every step's loss is read one step
+    behind (age 1) and the last one with age 0; losses and parameters equal the synchronous loop's bit for bit.  Asking for a step
+    that was never enqueued, or for an age beyond the two-slot ring, is an error."""
+    pkg, ops, nn = zb
+    xs = [torch.from_numpy(batch(16, 32, 10, 21 + i)[0]).cuda() for i in range(2)]
+    T = torch.from_numpy(batch(16, 32, 10, 21)[1]).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    runs = []
+    for use_async in (False, True):
+        with torch.cuda.stream(side):
+            ctx = ops.Context(math=pkg.ZB_MATH_TF32)
+            model = nn.Model(ctx, "small_cnn", 10, seed=17)
+            model.set_optimizer("sgd", lr=1e-2)
+            if graph:
+                model.set_graph(True)
+            loss_buf = torch.empty((1,), dtype=torch.float32, device="cuda")
+            steps = 8
+            if not use_async:
+                losses = [model.train_step(xs[i % 2], T, loss_out=loss_buf, read_loss=True) for i in range(steps)]
+            else:
+                with pytest.raises(RuntimeError):
+                    model.loss_wait(0)          # nothing enqueued yet
+                losses = []
+                for i in range(steps):
+                    model.train_step_async(xs[i % 2], T, loss_buf)
+                    if i > 0:
+                        losses.append(model.loss_wait(1))
+                    else:
+                        with pytest.raises(RuntimeError):
+                            model.loss_wait(1)  # only one step so far
+                losses.append(model.loss_wait(0))
+                assert model.loss_wait(0) == losses[-1] and model.loss_wait(1) == losses[-2]   # reading does not consume
+                with pytest.raises(RuntimeError):
+                    model.loss_wait(2)
+            ctx.check()
+            params = {k: v["data"].clone() for k, v in model.named_parameters().items()}
+            runs.append((losses, params))
+            model.close()
+            ctx.close()
+        torch.cuda.synchronize()
+    (la, pa), (lb, pb) = runs
+    assert all(np.isfinite(la)) and la == lb
+    for k in pa:
+        assert torch.equal(pa[k], pb[k]), k
+
+
 def test_graph_mode_stays_eager_where_it_cannot_capture(zb):
     """A ctx on the legacy default stream cannot be captured: zb_model_set_graph must leave it on the eager path (no graph
     captured) with unchanged results; the same model on a real stream is captured (Adam included: its bias corrections come from

@@ -43,6 +43,10 @@ struct zb_model {
   std::vector<WarmUp> warm;
   std::vector<StepGraph> graphs;
   void* pinned_loss = nullptr;  // 8 bytes of pinned host memory: the loss read-back node of the graphs
+  // deferred loss read (zb_model_train_step_async / zb_model_loss_wait): two pinned slots + the events that mark them written
+  void* loss_ring = nullptr;
+  cudaEvent_t loss_ev[2] = {nullptr, nullptr};
+  unsigned long long loss_seq = 0;   // steps enqueued through zb_model_train_step_async
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     graphs.clear();
@@ -109,6 +113,9 @@ int zb_model_destroy(zb_model* m) {
   if (m->last_loss.defined()) m->last_loss.clear_grad();
   m->drop_graphs();
   if (m->pinned_loss) cudaFreeHost(m->pinned_loss);
+  if (m->loss_ring) cudaFreeHost(m->loss_ring);
+  for (auto& e : m->loss_ev)
+    if (e) cudaEventDestroy(e);
   delete m;
   return ZB_OK;
 }
@@ -352,6 +359,39 @@ int zb_model_train_step(zb_model* m, const void* x_nchw, const void* targets, in
       *host_loss = f;
     }
   }
+  return ZB_OK;
+}
+
+// The step without the host waiting for it: the loss goes to a pinned ring slot behind the step, on the compute stream, and an event
+// marks the slot written.  A training loop that logs every loss then blocks on the step BEFORE the one it has just enqueued
+// (zb_model_loss_wait(m, 1, ..)): the device always has the next step queued while the host prepares the one after.
+int zb_model_train_step_async(zb_model* m, const void* x_nchw, const void* targets, int64_t batch, int64_t c, int64_t h, int64_t w,
+                              void* loss_dev) {
+  ZB_API_RANGE();
+  ZB_REQUIRE(m != nullptr && loss_dev != nullptr, "train_step_async: a device loss scalar is required");
+  if (!m->loss_ring) {
+    ZB_CHECK_CUDA(cudaMallocHost(&m->loss_ring, 16));
+    for (auto& e : m->loss_ev) ZB_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int rc = zb_model_train_step(m, x_nchw, targets, batch, c, h, w, loss_dev, nullptr);
+  if (rc != ZB_OK) return rc;
+  const int slot = static_cast<int>(m->loss_seq & 1ull);
+  const size_t esz = m->rt->dtype == ZB_F64 ? 8 : 4;
+  ZB_CHECK_CUDA(cudaMemcpyAsync(static_cast<char*>(m->loss_ring) + 8 * slot, loss_dev, esz, cudaMemcpyDeviceToHost, m->ctx->stream));
+  ZB_CHECK_CUDA(cudaEventRecord(m->loss_ev[slot], m->ctx->stream));
+  ++m->loss_seq;
+  return ZB_OK;
+}
+
+int zb_model_loss_wait(zb_model* m, int age, double* host_loss) {
+  ZB_API_RANGE();
+  ZB_REQUIRE(m != nullptr && host_loss != nullptr, "loss_wait: null argument");
+  ZB_REQUIRE(age == 0 || age == 1, "loss_wait: age must be 0 (the step enqueued last) or 1 (the one before it)");
+  ZB_REQUIRE(m->loss_seq > static_cast<unsigned long long>(age), "loss_wait: no such step has been enqueued");
+  const int slot = static_cast<int>((m->loss_seq - 1ull - static_cast<unsigned long long>(age)) & 1ull);
+  ZB_CHECK_CUDA(cudaEventSynchronize(m->loss_ev[slot]));
+  const char* src = static_cast<const char*>(m->loss_ring) + 8 * slot;
+  *host_loss = m->rt->dtype == ZB_F64 ? *reinterpret_cast<const double*>(src) : static_cast<double>(*reinterpret_cast<const float*>(src));
   return ZB_OK;
 }
 

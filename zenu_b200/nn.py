@@ -134,6 +134,19 @@ class Model:
                                            ctypes.c_void_p(loss.data_ptr()), ctypes.byref(host) if read_loss else None))
         return host.value if read_loss else loss
 
+    def train_step_async(self, x, targets, loss_out):
+        """`train_step` without the host waiting for it: the step is enqueued and its loss lands in a pinned two-slot ring behind it
+        (`loss_wait`).  `loss_out`: the persistent device scalar the step writes its loss to."""
+        n, c, h, w = x.shape
+        check(self.lib.zb_model_train_step_async(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(targets.data_ptr()), n, c, h, w,
+                                                 ctypes.c_void_p(loss_out.data_ptr())))
+
+    def loss_wait(self, age=0):
+        """Loss of the step enqueued `age` `train_step_async` calls ago (0 = the latest, 1 = the one before); blocks until that step is done."""
+        host = ctypes.c_double(0.0)
+        check(self.lib.zb_model_loss_wait(self._h, int(age), ctypes.byref(host)))
+        return host.value
+
     def set_wgrad_overlap(self, enable=True):
         """conv wgrad on the ctx's side stream, overlapping the following layers' BatchNorm backward (bit-identical results)."""
         check(self.lib.zb_model_set_wgrad_overlap(self._h, int(bool(enable))))
