@@ -70,7 +70,18 @@ struct ColGeom {
   long long rows_per_slab, cvecs;
 };
 
-static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
+// CTAs of `kernel` (256 threads, `smem` dynamic bytes) that are resident on one SM.  The NHWC kernels hold 52 - 92 registers per thread
+// (four 128-bit loads per stream in flight), i.e. 2 - 4 CTAs per SM; their grids are sized to exactly ONE wave of that, so that no
+// trailing partial wave is left and a ROWS_SWEEP walk really is one front through the tensor (a grid of 8 CTAs per SM, which the
+// register file does not hold, ran as 2.67 waves with the last one two thirds empty).
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, smem) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return std::min(8, std::max(1, n));
+}
+
+static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn, int resident = 8) {
   ColGeom g;
   g.cvecs = C / vn;
   int tx = 1;
@@ -78,11 +89,12 @@ static ColGeom col_geom(zb_ctx* ctx, long long rows, long long C, int vn) {
   g.tx = tx;
   g.ty = 256 / tx;
   g.col_groups = static_cast<int>((g.cvecs + tx - 1) / tx);
-  static int ctas_per_sm = -1;   // CTAs per SM the grid is sized for (tuning knob: ZENU_B200_BN_CTAS)
-  if (ctas_per_sm < 0) {
+  static int ctas_knob = -1;   // CTAs per SM the grid is sized for, overriding the kernel's own residency (tuning knob: ZENU_B200_BN_CTAS)
+  if (ctas_knob < 0) {
     const char* e = getenv("ZENU_B200_BN_CTAS");
-    ctas_per_sm = e ? std::min(8, std::max(1, atoi(e))) : 8;
+    ctas_knob = e ? std::min(8, std::max(1, atoi(e))) : 0;
   }
+  const int ctas_per_sm = ctas_knob > 0 ? ctas_knob : resident;
   long long max_slabs = std::max<long long>(1, (ctx->sm_count * static_cast<long long>(ctas_per_sm)) / g.col_groups);
   static int rows_per_thread = -1;   // rows each thread walks per slab (tuning knob: ZENU_B200_BN_ROWS)
   if (rows_per_thread < 0) {
@@ -636,7 +648,8 @@ static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, lon
     if (vec) {
       using F = FT<T, VN>;
       F f; init(f);
-      ColGeom g = col_geom(ctx, rows, C, VN);
+      static const int occ = resident_ctas(col_reduce_nhwc<T, VN, F>, sizeof(T) * 256 * F::NS * VN);
+      ColGeom g = col_geom(ctx, rows, C, VN, occ);
       ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
       dim3 grid(g.col_groups, g.slabs);
       const size_t smem = sizeof(T) * g.ty * F::NS * g.tx * VN;
@@ -646,7 +659,8 @@ static int run_col_reduce(zb_ctx* ctx, int layout, long long N, long long C, lon
     } else {
       using F = FT<T, 1>;
       F f; init(f);
-      ColGeom g = col_geom(ctx, rows, C, 1);
+      static const int occ = resident_ctas(col_reduce_nhwc<T, 1, F>, sizeof(T) * 256 * F::NS);
+      ColGeom g = col_geom(ctx, rows, C, 1, occ);
       ZB_REQUIRE(static_cast<long long>(g.slabs) * F::NS * C <= partial_cap_elems, "bn: partial buffer too small");
       dim3 grid(g.col_groups, g.slabs);
       const size_t smem = sizeof(T) * g.ty * F::NS * g.tx;
@@ -693,13 +707,15 @@ static int launch_apply(zb_ctx* ctx, int layout, long long N, long long C, long 
     constexpr int VN = vec_n<T>();
     const bool vec = (C % VN == 0) && al16(x) && al16(res) && al16(y);
     if (vec) {
-      ColGeom g = col_geom(ctx, rows, C, VN);
+      static const int occ = resident_ctas(bn_apply_nhwc<T, VN, RELU, RES>, 0);
+      ColGeom g = col_geom(ctx, rows, C, VN, occ);
       dim3 grid(g.col_groups, g.slabs);
       ZB_REQUIRE(mask == nullptr || (sizeof(T) == 4 && RELU && C % 32 == 0), "bn: ReLU bit mask needs f32, relu and C %% 32 == 0");
       bn_apply_nhwc<T, VN, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty, mask);
     } else {
       ZB_REQUIRE(mask == nullptr, "bn: ReLU bit mask needs 16-byte aligned NHWC tensors");
-      ColGeom g = col_geom(ctx, rows, C, 1);
+      static const int occ = resident_ctas(bn_apply_nhwc<T, 1, RELU, RES>, 0);
+      ColGeom g = col_geom(ctx, rows, C, 1, occ);
       dim3 grid(g.col_groups, g.slabs);
       bn_apply_nhwc<T, 1, RELU, RES><<<grid, 256, 0, ctx->stream>>>(x, res, y, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty);
     }
@@ -785,11 +801,13 @@ static int launch_bwd_apply(zb_ctx* ctx, int layout, long long N, long long C, l
     const bool vec = (C % VN == 0) && al16(x) && al16(dy) && al16(y) && al16(dx) && al16(dres);
     ZB_REQUIRE(MASK != 4 || (vec && sizeof(T) == 4 && bits != nullptr), "bn bwd: the bit-mask apply needs aligned f32 NHWC tensors");
     if (vec) {
-      ColGeom g = col_geom(ctx, rows, C, VN);
+      static const int occ = resident_ctas(bn_bwd_apply_nhwc<T, VN, MASK, DRES>, 0);
+      ColGeom g = col_geom(ctx, rows, C, VN, occ);
       dim3 grid(g.col_groups, g.slabs);
       bn_bwd_apply_nhwc<T, VN, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty, bits);
     } else {
-      ColGeom g = col_geom(ctx, rows, C, 1);
+      static const int occ = resident_ctas(bn_bwd_apply_nhwc<T, 1, MASK, DRES>, 0);
+      ColGeom g = col_geom(ctx, rows, C, 1, occ);
       dim3 grid(g.col_groups, g.slabs);
       bn_bwd_apply_nhwc<T, 1, MASK, DRES><<<grid, 256, 0, ctx->stream>>>(x, dy, y, dx, dres, mean, inv, coef, gamma, beta, rows, C, make_walk(g, rows, order), g.tx, g.ty);
     }
@@ -1077,7 +1095,9 @@ static int bn_relu_pool_fwd_f32(zb_ctx* ctx, long long N, long long C, long long
     ZB_LAUNCH_CHECK(ctx);
   }
   const long long total = N * P * Q * (C / 4);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 32ll)));
+  // whole waves of the 5 CTAs per SM that are resident (48 registers x 256 threads)
+  static const bool whole_waves = []() { const char* e = getenv("ZENU_B200_POOL_GRID"); return e == nullptr || atoi(e) != 0; }();
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * (whole_waves ? 30ll : 32ll))));
   bn_relu_pool_fwd_kernel<<<grid, 256, 0, ctx->stream>>>(x, coef, scale, bias, y_pool, static_cast<uchar4*>(idx), static_cast<int>(N),
                                                          static_cast<int>(H), static_cast<int>(W), static_cast<int>(C), static_cast<int>(P),
                                                          static_cast<int>(Q));
@@ -1099,7 +1119,10 @@ static int bn_relu_pool_bwd_f32(zb_ctx* ctx, long long N, long long C, long long
   float* coef = partial + ms * 2 * C;
   const int G = static_cast<int>(256 / (C / 4));
   const long long patches = N * ((H + 1) / 2) * ((W + 1) / 2);
-  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((patches + G - 1) / G, ms)));
+  // one full wave: the kernels hold 80 registers x 256 threads, i.e. 3 CTAs per SM are resident, and every CTA strides over the patches
+  // (a grid of sm_count * 8 was 2.67 waves, the last one two thirds empty).  ZENU_B200_POOL_GRID=0: the old grid (A/B knob)
+  static const bool one_wave = []() { const char* e = getenv("ZENU_B200_POOL_GRID"); return e == nullptr || atoi(e) != 0; }();
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((patches + G - 1) / G, one_wave ? ctx->sm_count * 3ll : ms)));
   prof_begin(ctx, PROF_BN);
   bn_relu_pool_bwd_kernel<false><<<grid, 256, 0, ctx->stream>>>(x, dyp, static_cast<const uchar4*>(idx), mean, inv, scale, bias, nullptr, nullptr,
                                                                 partial, static_cast<int>(N), static_cast<int>(H), static_cast<int>(W),
