@@ -377,7 +377,9 @@ def run_ours(args, rank, world, local_rank):
     tensor_tflops = (t_flops / (t_ms * 1e-3)) / 1e12 if t_ms > 0 else 0.0
     bn_gbs = (b_bytes / (b_ms * 1e-3)) / 1e9 if b_ms > 0 else 0.0
     if tensor_share >= bn_share:
-        traffic, traffic_src = ncu_traffic(TENSOR_KERNELS)
+        # the committed ncu capture is of the headline workload only (tools/ncu_step.py: ResNet-50, batch 256, 3x224x224)
+        headline = args.arch == "resnet50" and args.batch == 256 and args.hw == 224
+        traffic, traffic_src = ncu_traffic(TENSOR_KERNELS) if headline else (None, None)
         roofline = {"kernel": "tcgen05 kind::tf32 conv/GEMM kernels (zb::umma_kernel, halo_conv_kernel, wgrad_halo_kernel, stem_dgrad_kernel)",
                     "bound": "tensor", "achieved": tensor_tflops,
                     "peak": tf32_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tf32_peak if tf32_peak else None, "traffic": traffic,
