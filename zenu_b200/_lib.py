@@ -9,7 +9,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libzenu_b200.so")
+# ZENU_B200_LIB: another build of the same library (A/B of build-time knobs); it must still be the in-tree CUDA library
+LIB_PATH = os.environ.get("ZENU_B200_LIB") or os.path.join(_HERE, "lib", "libzenu_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 ZB_OK = 0

@@ -65,6 +65,15 @@ __device__ __forceinline__ double bn_affine(double a, double m, double iv, doubl
   return __fma_rn(__dmul_rn(__dsub_rn(a, m), iv), g, b);
 }
 
+// Minimum CTAs per SM the three streaming NHWC kernels (statistics pass, forward apply, backward apply) are compiled for; the grids
+// follow the resulting residency through resident_ctas().  3 caps them at 85 registers: the two-stream BN+add+ReLU forward apply
+// (92 registers left alone, i.e. 2 CTAs = 64 KB of loads in flight per SM) gets a third CTA, the others may use more registers than
+// the default heuristic gives them and stay at 3.  Measured per ResNet-50 step (separate builds, one box): unconstrained 34.48 ms,
+// 3: 34.09 ms, 4 (64 registers, spills): 35.63 ms; 8 instead of 4 rows in flight in the single-stream apply: no change.
+#ifndef ZB_BN_MIN_CTAS
+#define ZB_BN_MIN_CTAS 3
+#endif
+
 struct ColGeom {
   int tx, ty, col_groups, slabs;
   long long rows_per_slab, cvecs;
@@ -239,7 +248,7 @@ struct BnBwdF {  // sum(dy'), sum(dy' * xhat); inputs: x, dy, y(mask)
 
 // partial layout: [slab][stat][C]
 template <typename T, int VN, typename F>
-__global__ void __launch_bounds__(256) col_reduce_nhwc(F f, const T* __restrict__ in0, const T* __restrict__ in1,
+__global__ void __launch_bounds__(256, ZB_BN_MIN_CTAS) col_reduce_nhwc(F f, const T* __restrict__ in0, const T* __restrict__ in1,
                                                        const T* __restrict__ in2, T* __restrict__ partial, long long rows,
                                                        long long C, RowWalk walk, int tx_n, int ty_n) {
   constexpr int NS = F::NS;
@@ -466,7 +475,7 @@ __device__ __forceinline__ void store_mask_nibble(uint32_t* __restrict__ mask, l
 }
 
 template <typename T, int VN, bool RELU, bool RES>
-__global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ res,
+__global__ void __launch_bounds__(256, ZB_BN_MIN_CTAS) bn_apply_nhwc(const T* __restrict__ x, const T* __restrict__ res,
                                                      T* __restrict__ y, const T* __restrict__ coef,
                                                      const T* __restrict__ gamma, const T* __restrict__ beta,
                                                      long long rows, long long C, RowWalk walk, int tx_n,
@@ -523,7 +532,7 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc(const T* __restrict__ x, co
 
 // backward: dx = coef * (dy' - c1 - xhat * c2);  dres = dy'
 template <typename T, int VN, int MASK, bool DRES>
-__global__ void __launch_bounds__(256) bn_bwd_apply_nhwc(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, ZB_BN_MIN_CTAS) bn_bwd_apply_nhwc(const T* __restrict__ x, const T* __restrict__ dy,
                                                          const T* __restrict__ y, T* __restrict__ dx,
                                                          T* __restrict__ dres, const T* __restrict__ mean,
                                                          const T* __restrict__ inv, const T* __restrict__ coef,
