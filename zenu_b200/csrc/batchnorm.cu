@@ -13,6 +13,8 @@
 //   finalize: one thread per channel folds the slab partials in double precision
 //   apply   : same geometry as reduce; per-channel coefficients live in registers
 // Statistics use a per-channel shift (the first row) so the single-pass sum / sum-of-squares does not cancel.
+// Grids are one wave of the CTAs that are resident for the kernel instantiation at hand (resident_ctas); the order in which a
+// kernel walks its rows follows what the previous kernel of the step left in L2 (RowWalk).
 #include <algorithm>
 #include <cstdlib>
 
